@@ -1,0 +1,196 @@
+/*
+ * b200sparse.h -- C ABI of libb200sparse.so, the B200 (sm_100a) sparse direct-solve engine that
+ * kvxopt's `cholmod` and `klu` extension modules call in place of SuiteSparse.
+ *
+ * Every entry point names the reference interface it replaces (paths under the kvxopt source tree,
+ * file:line).  All pointers are HOST pointers unless the name ends in `_dev`; all index arrays are
+ * 64-bit (kvxopt's int_t = Py_ssize_t, src/C/kvxopt.h:46) compressed-column storage exactly as held
+ * by a kvxopt `spmatrix` (src/C/kvxopt.h:58-69): colptr[ncols+1], rowind[nnz] sorted per column,
+ * values[nnz].  Dense blocks are column-major FP64 as held by a kvxopt `matrix` (kvxopt.h:48-56).
+ *
+ * The numeric work (factorization, triangular solves, batched refactorization) runs in hand-written
+ * CUDA kernels; there is no CPU fallback: numeric calls return B200S_NO_DEVICE when no GPU is present.
+ * The symbolic analysis runs on the host and its result is uploaded once per sparsity pattern.
+ */
+#ifndef B200SPARSE_H
+#define B200SPARSE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t b200s_int;
+
+/* Status codes mirror the ones the reference wrappers branch on
+ * (src/C/cholmod.c:366-395, 679-723; src/C/klu.c:144-183, 370-375). */
+typedef enum {
+    B200S_OK            = 0,
+    B200S_NOT_POSDEF    = 1,   /* CHOLMOD_NOT_POSDEF: `minor` holds the failing column        */
+    B200S_SINGULAR      = 2,   /* KLU_SINGULAR / zero pivot                                   */
+    B200S_OUT_OF_MEMORY = -2,  /* CHOLMOD_OUT_OF_MEMORY / KLU_OUT_OF_MEMORY -> MemoryError     */
+    B200S_TOO_LARGE     = -3,  /* CHOLMOD_TOO_LARGE / KLU_TOO_LARGE                            */
+    B200S_INVALID       = -4,  /* CHOLMOD_INVALID / KLU_INVALID -> ValueError                  */
+    B200S_NO_DEVICE     = -5,  /* no CUDA device: numeric paths refuse to run (no CPU fallback)*/
+    B200S_CUDA_ERROR    = -6   /* a CUDA runtime call failed; see b200s_last_error()           */
+} b200s_status;
+
+const char* b200s_strerror(b200s_status s);
+const char* b200s_last_error(void);      /* text of the last CUDA/runtime failure on this thread */
+const char* b200s_version(void);
+int         b200s_device_count(void);    /* 0 when no GPU / driver                                */
+b200s_status b200s_set_device(int dev);  /* device used by handles created afterwards             */
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse Cholesky  (replaces the cholmod_l_* calls of src/C/cholmod.c)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct b200s_chol b200s_chol;    /* opaque: symbolic plan + device-resident numeric factor */
+
+/* Mirrors the `cholmod.options` keys read by set_options (src/C/cholmod.c:87-129) plus the relaxed
+ * supernode parameters CHOLMOD keeps in its Common object. */
+typedef struct {
+    int    supernodal;   /* only 2 (supernodal LL^T) is implemented; 0/1 are rejected with INVALID  */
+    int    nmethods;     /* 0: user perm if given else AMD; 1: user perm (must be given); 2: as 0   */
+    int    postorder;    /* 1: etree postorder after the fill-reducing ordering (always applied to  */
+                         /*    make supernodes contiguous; 0 is accepted and ignored)               */
+    double dbound;       /* lower bound for diagonal entries of L (0 = off)                         */
+    int    ordering;     /* 0: AMD (own implementation); 1: natural (identity) when no user perm    */
+    int    nrelax[3];    /* relaxed amalgamation thresholds, default {4,16,48}                      */
+    double zrelax[3];    /* default {0.8,0.1,0.05}                                                  */
+    int    block;        /* dense block-column width used inside large fronts (0 = default 128)     */
+} b200s_chol_opts;
+
+void b200s_chol_default_opts(b200s_chol_opts* o);
+
+/* cholmod.symbolic (src/C/cholmod.c:244-291): pack(A,uplo) :132-181 + cholmod_l_analyze_p :269.
+ * Only the `uplo` triangle of (colptr,rowind) is referenced.  perm may be NULL. Host only. */
+b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200s_int* rowind,
+                                char uplo, const b200s_int* perm, const b200s_chol_opts* opts,
+                                b200s_chol** out);
+
+/* cholmod.numeric (src/C/cholmod.c:322-398): cholmod_l_factorize :362 on a matrix with the pattern
+ * given to analyze.  val[k] belongs to (rowind[k], column of k) of the SAME colptr/rowind.
+ * On B200S_NOT_POSDEF *minor_out is the first non-positive pivot column (in permuted order, like
+ * L->minor, cholmod.c:376-380). */
+b200s_status b200s_chol_factorize(b200s_chol* F, const double* val, b200s_int* minor_out);
+/* Same with val already resident in device memory (HBM); used by bench `value`. */
+b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200s_int* minor_out);
+
+/* cholmod.solve (src/C/cholmod.c:429-499) -- all nrhs columns in one call instead of the
+ * reference's per-column loop :481-493.  sys: 0 A x=b, 4 L x=b, 5 L^T x=b, 7 x=P b, 8 x=P^T b;
+ * with LL^T D=I so 1 (LDL^T x=b) = 0-without-permutation, 2 (LD x=b) = 4, 3 (DL^T x=b) = 5, 6 = copy
+ * (cholmod.c:437-439).  B is n x nrhs column-major with leading dimension ldB, overwritten. */
+b200s_status b200s_chol_solve(b200s_chol* F, int sys, double* B, b200s_int nrhs, b200s_int ldB);
+b200s_status b200s_chol_solve_dev(b200s_chol* F, int sys, double* B_dev, b200s_int nrhs, b200s_int ldB);
+
+/* cholmod.spsolve (src/C/cholmod.c:524-587): sparse right-hand side, sparse result holding the
+ * numerically nonzero entries.  Output arrays are allocated by the library; release with b200s_free. */
+b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_int ncols,
+                                const b200s_int* Bp, const b200s_int* Bi, const double* Bx,
+                                b200s_int** Xp, b200s_int** Xi, double** Xx);
+
+/* cholmod.diag (src/C/cholmod.c:900-945): the n diagonal entries of L, in factor (permuted) order. */
+b200s_status b200s_chol_diag(b200s_chol* F, double* d_out);
+
+/* cholmod.getfactor (src/C/cholmod.c:948-985): L as CCS (cholmod_l_factor_to_sparse), zeros inside
+ * relaxed supernodes are dropped.  Arrays are library-allocated; release with b200s_free. */
+b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, double** Lx);
+
+typedef struct {
+    b200s_int n, nsuper, nnz_L, nnz_A, nlevels, max_front_rows, max_front_cols;
+    b200s_int factor_bytes, workspace_bytes;
+    double    flops;          /* sum over supernodes of c^3/3 + c^2 r + c r^2 (r = rows below)      */
+    double    flops_potrf, flops_trsm, flops_syrk;
+    int       is_numeric;     /* 0 after analyze, 1 after a successful factorize                    */
+    b200s_int minor;          /* n when the last factorization succeeded                            */
+    /* device-event timings (ms) of the last factorize / solve call, 0 when not measured            */
+    double    ms_h2d, ms_assemble, ms_factor, ms_total, ms_solve;
+    double    ms_analyze;     /* host wall time of analyze                                          */
+    double    ms_dense_update; /* device time inside the SYRK/GEMM update kernels of the last factorize */
+    double    ms_potrf, ms_trsm, ms_extend;
+} b200s_chol_info_t;
+b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info);
+/* when on, factorize records per-kernel-class CUDA events (adds launch gaps; for profiling only) */
+b200s_status b200s_chol_set_profiling(b200s_chol* F, int on);
+
+/* L->Perm (fill-reducing + postorder): perm_out[k] = original index of row/column k of P A P^T. */
+b200s_status b200s_chol_get_perm(const b200s_chol* F, b200s_int* perm_out);
+/* supernode partition for tests / tools: super[nsuper+1] first columns, rowptr[nsuper+1], rows[] */
+b200s_status b200s_chol_get_super(const b200s_chol* F, b200s_int* super_out, b200s_int* rowptr_out,
+                                  b200s_int* rows_out /* may be NULL to query sizes only */);
+
+void b200s_chol_free(b200s_chol* F);     /* capsule destructor (src/C/cholmod.c:210-214) */
+void b200s_free(void* p);
+
+/* Geometric nested-dissection permutation of an nx*ny*nz grid numbered x-fastest (BASELINE config 4).
+ * perm_out[k] = grid index eliminated k-th; pass it as `perm` to b200s_chol_analyze. */
+b200s_status b200s_grid_nd_perm(b200s_int nx, b200s_int ny, b200s_int nz, b200s_int leaf,
+                                b200s_int* perm_out);
+/* AMD ordering of the symmetric pattern of the `uplo` triangle (src/C/amd.c `order`, host only). */
+b200s_status b200s_amd_order(b200s_int n, const b200s_int* colptr, const b200s_int* rowind,
+                             char uplo, b200s_int* perm_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * KLU  (replaces the klu_l_* calls of src/C/klu.c)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct b200s_klu_sym b200s_klu_sym;   /* BTF + per-block ordering (klu_l_symbolic)          */
+typedef struct b200s_klu_num b200s_klu_num;   /* L, U, F, pivots, row scaling (klu_l_numeric) plus   */
+                                              /* the device-resident refactor plan                   */
+
+/* klu.symbolic (src/C/klu.c:242-291): klu_l_analyze with klu_defaults (btf=1, AMD, scale=2). Host. */
+b200s_status b200s_klu_analyze(b200s_int n, const b200s_int* colptr, const b200s_int* rowind,
+                               b200s_klu_sym** out);
+/* klu.numeric (src/C/klu.c:310-379): klu_l_factor -- threshold partial pivoting (tol 1e-3, diagonal
+ * preferred), row scaling by max |row|.  The pivot search runs on the host once per pattern; the
+ * resulting pattern + pivot sequence is what the batched device refactorization reuses. */
+b200s_status b200s_klu_factor(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind,
+                              const double* val, b200s_klu_num** out);
+
+/* Batched numeric refactorization (klu_refactor semantics: same pattern, same pivot sequence, fresh
+ * row scaling) of `batch` matrices whose values are vals[b*ldv + k], k indexing the CCS given to
+ * b200s_klu_factor.  Factors stay resident on the device for b200s_klu_solve_batch.
+ * status_per_matrix[b] = B200S_OK or B200S_SINGULAR (zero/NaN pivot).  May be NULL. */
+b200s_status b200s_klu_refactor_batch(b200s_klu_num* N, const double* vals, b200s_int batch,
+                                      b200s_int ldv, int* status_per_matrix);
+b200s_status b200s_klu_refactor_batch_dev(b200s_klu_num* N, const double* vals_dev, b200s_int batch,
+                                          b200s_int ldv, int* status_per_matrix);
+/* klu.solve (src/C/klu.c:593-690) for every matrix of the last refactored batch:
+ * B is batch blocks of n x nrhs column-major (block stride ldB*nrhs), overwritten.  trans 0 = 'N', 1 = 'T'. */
+b200s_status b200s_klu_solve_batch(b200s_klu_num* N, int trans, double* B, b200s_int nrhs,
+                                   b200s_int ldB, b200s_int batch);
+b200s_status b200s_klu_solve_batch_dev(b200s_klu_num* N, int trans, double* B_dev, b200s_int nrhs,
+                                       b200s_int ldB, b200s_int batch);
+/* klu.solve for the single matrix given to b200s_klu_factor (a batch of one on the device). */
+b200s_status b200s_klu_solve(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB);
+
+typedef struct {
+    b200s_int n, nblocks, nnz_A, nnz_L, nnz_U, nnz_F, nlevels, max_block;
+    double    flops;             /* multiply-adds x2 of one refactorization                        */
+    b200s_int bytes_per_refactor;/* 8*(nnz_A + nnz_L + nnz_U + nnz_F + 2n): compulsory traffic      */
+    double    ms_h2d, ms_refactor, ms_solve;  /* device-event times of the last batch call          */
+} b200s_klu_info_t;
+b200s_status b200s_klu_info(const b200s_klu_num* N, b200s_klu_info_t* info);
+
+/* klu.get_numeric (src/C/klu.c:392-566): klu_l_extract of the host factor.  Sizes come from
+ * b200s_klu_info; arrays are caller-allocated: Lp[n+1],Li[nnz_L],Lx; Up[n+1],Ui[nnz_U],Ux;
+ * Fp[n+1],Fi[nnz_F],Fx; P[n],Q[n],Rs[n] (the scale factors themselves, NOT inverted), R[nblocks+1].
+ * Any pointer may be NULL. */
+b200s_status b200s_klu_extract(const b200s_klu_num* N,
+                               b200s_int* Lp, b200s_int* Li, double* Lx,
+                               b200s_int* Up, b200s_int* Ui, double* Ux,
+                               b200s_int* Fp, b200s_int* Fi, double* Fx,
+                               b200s_int* P, b200s_int* Q, double* Rs, b200s_int* R);
+/* download the factor of matrix b of the last batch in the same layout (values only; pattern/P/Q shared) */
+b200s_status b200s_klu_extract_batch(b200s_klu_num* N, b200s_int b, double* Lx, double* Ux,
+                                     double* Fx, double* Rs);
+
+void b200s_klu_free_symbolic(b200s_klu_sym* S);   /* src/C/klu.c:51-61 */
+void b200s_klu_free_numeric(b200s_klu_num* N);    /* src/C/klu.c:63-72 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H */

@@ -1,0 +1,31 @@
+"""ctypes mirrors of the structs in include/b200sparse.h"""
+import ctypes as C
+
+i64 = C.c_int64
+
+class CholOpts(C.Structure):
+    _fields_ = [("supernodal", C.c_int), ("nmethods", C.c_int), ("postorder", C.c_int), ("dbound", C.c_double),
+                ("ordering", C.c_int), ("nrelax", C.c_int * 3), ("zrelax", C.c_double * 3), ("block", C.c_int)]
+
+
+class CholInfo(C.Structure):
+    _fields_ = [(k, i64) for k in ("n", "nsuper", "nnz_L", "nnz_A", "nlevels", "max_front_rows", "max_front_cols",
+                                   "factor_bytes", "workspace_bytes")] + \
+               [(k, C.c_double) for k in ("flops", "flops_potrf", "flops_trsm", "flops_syrk")] + \
+               [("is_numeric", C.c_int), ("minor", i64)] + \
+               [(k, C.c_double) for k in ("ms_h2d", "ms_assemble", "ms_factor", "ms_total", "ms_solve", "ms_analyze",
+                                          "ms_dense_update", "ms_potrf", "ms_trsm", "ms_extend")]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class KluInfo(C.Structure):
+    _fields_ = [(k, i64) for k in ("n", "nblocks", "nnz_A", "nnz_L", "nnz_U", "nnz_F", "nlevels", "max_block")] + \
+               [("flops", C.c_double), ("bytes_per_refactor", i64)] + \
+               [(k, C.c_double) for k in ("ms_h2d", "ms_refactor", "ms_solve")]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+

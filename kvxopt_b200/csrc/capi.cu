@@ -1,0 +1,280 @@
+// extern "C" boundary of libb200sparse.so (include/b200sparse.h): plain pointers and sizes, no C++ or
+// torch types.  Cholesky half; the KLU half lives in klu_capi.cu.
+#include "../../include/b200sparse.h"
+#include "gpu.hpp"
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <vector>
+
+using namespace b200s;
+
+struct b200s_chol {
+    CholPlan plan;
+    CholOpts opts;
+    CholDevice* dev = nullptr;
+    int device = 0;
+    CholTimes times;
+    i64 minor = 0;
+    bool numeric = false, profiling = false;
+};
+
+static_assert(B200S_OK == ST_OK && B200S_NOT_POSDEF == ST_NOT_POSDEF && B200S_SINGULAR == ST_SINGULAR &&
+              B200S_OUT_OF_MEMORY == ST_OOM && B200S_TOO_LARGE == ST_TOO_LARGE && B200S_INVALID == ST_INVALID &&
+              B200S_NO_DEVICE == ST_NO_DEVICE && B200S_CUDA_ERROR == ST_CUDA, "status codes out of sync");
+
+extern "C" {
+
+const char* b200s_strerror(b200s_status s) {
+    switch (s) {
+        case B200S_OK: return "ok";
+        case B200S_NOT_POSDEF: return "matrix is not positive definite";
+        case B200S_SINGULAR: return "singular matrix";
+        case B200S_OUT_OF_MEMORY: return "out of memory";
+        case B200S_TOO_LARGE: return "problem too large";
+        case B200S_INVALID: return "invalid input";
+        case B200S_NO_DEVICE: return "no CUDA device (the numeric phase has no CPU fallback)";
+        case B200S_CUDA_ERROR: return "CUDA error";
+    }
+    return "unknown status";
+}
+const char* b200s_last_error(void) { return get_last_error(); }
+const char* b200s_version(void) { return "b200sparse 0.1 (sm_100a)"; }
+int b200s_device_count(void) { return device_count(); }
+b200s_status b200s_set_device(int dev) {
+    if (dev < 0 || dev >= device_count()) return B200S_INVALID;
+    set_current_device(dev);
+    return B200S_OK;
+}
+
+void b200s_chol_default_opts(b200s_chol_opts* o) {
+    if (!o) return;
+    CholOpts d;
+    o->supernodal = d.supernodal; o->nmethods = d.nmethods; o->postorder = d.postorder; o->dbound = d.dbound;
+    o->ordering = d.ordering; o->block = d.block;
+    for (int i = 0; i < 3; i++) { o->nrelax[i] = d.nrelax[i]; o->zrelax[i] = d.zrelax[i]; }
+}
+
+b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, char uplo,
+                                const b200s_int* perm, const b200s_chol_opts* opts, b200s_chol** out) {
+    if (!out) return B200S_INVALID;
+    *out = nullptr;
+    if (n < 0 || (n > 0 && (!colptr || (colptr[n] > 0 && !rowind)))) return B200S_INVALID;
+    b200s_chol* F = new (std::nothrow) b200s_chol();
+    if (!F) return B200S_OUT_OF_MEMORY;
+    if (opts) {
+        F->opts.supernodal = opts->supernodal; F->opts.nmethods = opts->nmethods; F->opts.postorder = opts->postorder;
+        F->opts.dbound = opts->dbound; F->opts.ordering = opts->ordering;
+        if (opts->block > 0) F->opts.block = opts->block;
+        for (int i = 0; i < 3; i++) { F->opts.nrelax[i] = opts->nrelax[i]; F->opts.zrelax[i] = opts->zrelax[i]; }
+    }
+    if (F->opts.supernodal != 2 && F->opts.supernodal != 1) {
+        set_last_error("only the supernodal LL^T factorization (cholmod.options['supernodal'] = 2) is implemented");
+        delete F;
+        return B200S_INVALID;
+    }
+    F->device = current_device();
+    try {
+        static const b200s_int zero = 0;
+        chol_analyze(n, n > 0 ? colptr : &zero, rowind, uplo, perm, F->opts, F->plan);
+    } catch (const std::bad_alloc&) {
+        delete F;
+        return B200S_OUT_OF_MEMORY;
+    } catch (const std::invalid_argument& e) {
+        set_last_error(e.what());
+        delete F;
+        return B200S_INVALID;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        delete F;
+        return B200S_INVALID;
+    }
+    F->minor = n;
+    *out = F;
+    return B200S_OK;
+}
+
+static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_device, b200s_int* minor_out) {
+    if (!F) return B200S_INVALID;
+    F->numeric = false;
+    if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
+    if (!val && F->plan.nnzA > 0) return B200S_INVALID;
+    if (!F->dev) {
+        int st = ST_OK;
+        F->dev = chol_device_create(F->plan, F->opts, F->device, &st);
+        if (!F->dev) return (b200s_status)st;
+        chol_device_set_profiling(F->dev, F->profiling);
+    }
+    i64 minor = F->plan.n;
+    int st = chol_device_factorize(F->dev, val, on_device, &minor, &F->times);
+    F->minor = minor;
+    if (minor_out) *minor_out = minor;
+    F->numeric = (st == ST_OK);
+    return (b200s_status)st;
+}
+b200s_status b200s_chol_factorize(b200s_chol* F, const double* val, b200s_int* minor_out) {
+    return factorize_impl(F, val, false, minor_out);
+}
+b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200s_int* minor_out) {
+    return factorize_impl(F, val_dev, true, minor_out);
+}
+
+static b200s_status solve_impl(b200s_chol* F, int sys, double* B, b200s_int nrhs, b200s_int ldB, bool on_device) {
+    if (!F || sys < 0 || sys > 8 || nrhs < 0) return B200S_INVALID;
+    if (F->plan.n == 0 || nrhs == 0) return B200S_OK;
+    if (!B || ldB < F->plan.n) return B200S_INVALID;
+    if (!F->numeric || !F->dev) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
+    return (b200s_status)chol_device_solve(F->dev, sys, B, nrhs, ldB, on_device, &F->times);
+}
+b200s_status b200s_chol_solve(b200s_chol* F, int sys, double* B, b200s_int nrhs, b200s_int ldB) {
+    return solve_impl(F, sys, B, nrhs, ldB, false);
+}
+b200s_status b200s_chol_solve_dev(b200s_chol* F, int sys, double* B_dev, b200s_int nrhs, b200s_int ldB) {
+    return solve_impl(F, sys, B_dev, nrhs, ldB, true);
+}
+
+b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_int ncols, const b200s_int* Bp,
+                                const b200s_int* Bi, const double* Bx, b200s_int** Xp, b200s_int** Xi, double** Xx) {
+    if (!F || !Xp || !Xi || !Xx || nrows != F->plan.n || ncols < 0) return B200S_INVALID;
+    *Xp = nullptr; *Xi = nullptr; *Xx = nullptr;
+    const i64 n = nrows;
+    // sparse right-hand sides are expanded column by column; the device solve runs on dense blocks
+    std::vector<double> dense;
+    try { dense.assign((size_t)n * (size_t)ncols, 0.0); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    for (i64 j = 0; j < ncols; j++)
+        for (i64 k = Bp[j]; k < Bp[j + 1]; k++) {
+            if (Bi[k] < 0 || Bi[k] >= n) return B200S_INVALID;
+            dense[(size_t)j * n + Bi[k]] = Bx[k];
+        }
+    if (n > 0 && ncols > 0) {
+        b200s_status st = solve_impl(F, sys, dense.data(), ncols, n, false);
+        if (st != B200S_OK) return st;
+    }
+    i64 nnz = 0;
+    for (double v : dense) if (v != 0.0) nnz++;
+    b200s_int* xp = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)(ncols + 1));
+    b200s_int* xi = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)std::max<i64>(nnz, 1));
+    double* xx = (double*)malloc(sizeof(double) * (size_t)std::max<i64>(nnz, 1));
+    if (!xp || !xi || !xx) { free(xp); free(xi); free(xx); return B200S_OUT_OF_MEMORY; }
+    i64 p = 0;
+    xp[0] = 0;
+    for (i64 j = 0; j < ncols; j++) {
+        for (i64 i = 0; i < n; i++) {
+            double v = dense[(size_t)j * n + i];
+            if (v != 0.0) { xi[p] = i; xx[p] = v; p++; }
+        }
+        xp[j + 1] = p;
+    }
+    *Xp = xp; *Xi = xi; *Xx = xx;
+    return B200S_OK;
+}
+
+b200s_status b200s_chol_diag(b200s_chol* F, double* d_out) {
+    if (!F) return B200S_INVALID;
+    if (F->plan.n == 0) return B200S_OK;
+    if (!d_out) return B200S_INVALID;
+    if (!F->numeric || !F->dev) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
+    return (b200s_status)chol_device_diag(F->dev, d_out);
+}
+
+b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, double** Lx) {
+    if (!F || !Lp || !Li || !Lx) return B200S_INVALID;
+    *Lp = nullptr; *Li = nullptr; *Lx = nullptr;
+    const CholPlan& P = F->plan;
+    const i64 n = P.n;
+    if (n > 0 && (!F->numeric || !F->dev)) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
+    std::vector<double> raw;
+    try { raw.resize((size_t)std::max<i64>(P.lsize, 1)); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    if (n > 0) {
+        int st = chol_device_download_L(F->dev, raw.data());
+        if (st != ST_OK) return (b200s_status)st;
+    }
+    i64 nnz = 0;
+    for (const Front& f : P.fronts)
+        for (i32 c = 0; c < f.nc; c++)
+            for (i32 r = c; r < f.nr; r++)
+                if (r == c || raw[f.loff + (i64)c * f.ld + r] != 0.0) nnz++;
+    b200s_int* lp = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)(n + 1));
+    b200s_int* li = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)std::max<i64>(nnz, 1));
+    double* lx = (double*)malloc(sizeof(double) * (size_t)std::max<i64>(nnz, 1));
+    if (!lp || !li || !lx) { free(lp); free(li); free(lx); return B200S_OUT_OF_MEMORY; }
+    i64 p = 0;
+    lp[0] = 0;
+    for (const Front& f : P.fronts)
+        for (i32 c = 0; c < f.nc; c++) {
+            for (i32 r = c; r < f.nr; r++) {
+                double v = raw[f.loff + (i64)c * f.ld + r];
+                if (r == c || v != 0.0) { li[p] = P.rows[f.rowptr + r]; lx[p] = v; p++; }
+            }
+            lp[f.col0 + c + 1] = p;
+        }
+    *Lp = lp; *Li = li; *Lx = lx;
+    return B200S_OK;
+}
+
+b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info) {
+    if (!F || !info) return B200S_INVALID;
+    const CholPlan& P = F->plan;
+    memset(info, 0, sizeof *info);
+    info->n = P.n; info->nsuper = (b200s_int)P.fronts.size(); info->nnz_L = P.nnzL; info->nnz_A = P.nnzA;
+    info->nlevels = P.nlevels; info->max_front_rows = P.max_nr; info->max_front_cols = P.max_nc;
+    info->factor_bytes = P.lsize * 8; info->workspace_bytes = P.wsize * 8;
+    info->flops = P.flops; info->flops_potrf = P.flops_potrf; info->flops_trsm = P.flops_trsm; info->flops_syrk = P.flops_syrk;
+    info->is_numeric = F->numeric ? 1 : 0; info->minor = F->minor;
+    info->ms_h2d = F->times.ms_h2d; info->ms_assemble = F->times.ms_assemble; info->ms_factor = F->times.ms_factor;
+    info->ms_total = F->times.ms_total; info->ms_solve = F->times.ms_solve; info->ms_analyze = P.ms_analyze;
+    info->ms_dense_update = F->times.ms_dense_update; info->ms_potrf = F->times.ms_potrf;
+    info->ms_trsm = F->times.ms_trsm; info->ms_extend = F->times.ms_extend;
+    return B200S_OK;
+}
+b200s_status b200s_chol_set_profiling(b200s_chol* F, int on) {
+    if (!F) return B200S_INVALID;
+    F->profiling = on != 0;
+    if (F->dev) chol_device_set_profiling(F->dev, F->profiling);
+    return B200S_OK;
+}
+b200s_status b200s_chol_get_perm(const b200s_chol* F, b200s_int* perm_out) {
+    if (!F || (!perm_out && F->plan.n > 0)) return B200S_INVALID;
+    for (i32 k = 0; k < F->plan.n; k++) perm_out[k] = F->plan.perm[k];
+    return B200S_OK;
+}
+b200s_status b200s_chol_get_super(const b200s_chol* F, b200s_int* super_out, b200s_int* rowptr_out, b200s_int* rows_out) {
+    if (!F) return B200S_INVALID;
+    const CholPlan& P = F->plan;
+    const size_t ns = P.fronts.size();
+    for (size_t s = 0; s < ns; s++) {
+        if (super_out) super_out[s] = P.fronts[s].col0;
+        if (rowptr_out) rowptr_out[s] = P.fronts[s].rowptr;
+    }
+    if (super_out) super_out[ns] = P.n;
+    if (rowptr_out) rowptr_out[ns] = (b200s_int)P.rows.size();
+    if (rows_out) for (size_t k = 0; k < P.rows.size(); k++) rows_out[k] = P.rows[k];
+    return B200S_OK;
+}
+void b200s_chol_free(b200s_chol* F) {
+    if (!F) return;
+    if (F->dev) chol_device_destroy(F->dev);
+    delete F;
+}
+void b200s_free(void* p) { free(p); }
+
+b200s_status b200s_grid_nd_perm(b200s_int nx, b200s_int ny, b200s_int nz, b200s_int leaf, b200s_int* perm_out) {
+    if (nx < 1 || ny < 1 || nz < 1 || !perm_out || nx * ny * nz > 0x7fffffff) return B200S_INVALID;
+    std::vector<i32> p = grid_nd(nx, ny, nz, leaf);
+    for (size_t k = 0; k < p.size(); k++) perm_out[k] = p[k];
+    return B200S_OK;
+}
+b200s_status b200s_amd_order(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, char uplo, b200s_int* perm_out) {
+    if (n < 0 || n > 0x7fffffff - 16 || (n > 0 && (!colptr || !perm_out))) return B200S_INVALID;
+    try {
+        std::vector<i32> p = amd_order(sym_pattern_from_triangle(n, colptr, rowind, uplo));
+        for (size_t k = 0; k < p.size(); k++) perm_out[k] = p[k];
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return B200S_INVALID;
+    }
+    return B200S_OK;
+}
+
+}  // extern "C"

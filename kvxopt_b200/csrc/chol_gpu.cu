@@ -1,0 +1,957 @@
+// Numeric phase of the multifrontal supernodal Cholesky on B200 (sm_100a) and the supernodal
+// triangular solves.  This is what runs in place of cholmod_l_factorize (src/C/cholmod.c:362,677,824)
+// and cholmod_l_solve (src/C/cholmod.c:483,735).
+//
+// Data layout in HBM (all FP64, column-major):
+//   L   : one nr x nc panel per front, leading dimension ld (even), 128-byte aligned; rows follow the
+//         front's sorted row list, the first nc rows are the pivots (dense nc x nc lower triangle on top).
+//   W   : update (Schur complement) matrices, one per front with rows below the pivots, placed by
+//         lifetime (host.hpp Front::uoff); only the lower triangle is ever touched.
+// Schedule: fronts are grouped by level of the supernodal elimination tree (leaves first).  Per level:
+//   k_extend_add  zeroes the update matrix and adds the children's update matrices into the front
+//                 (parent-driven, children in fixed order => deterministic sums, no atomics);
+//   k_small_front fronts with <= 128 rows: whole front factored in shared memory by one CTA;
+//   k_panel       large fronts, per 128-column block: diagonal-block Cholesky in shared memory +
+//                 triangular solve of 64-row tiles (FP64 DMMA for the GEMM part, register substitution);
+//   k_update      C -= A_i A_j^T on 128x128 tiles with FP64 tensor-core DMMA (mma.sync m8n8k4.f64),
+//                 operands staged by a 4-stage cp.async pipeline; used for the in-panel trailing update
+//                 (K = 128) and for the Schur complement (K = nc).
+#include "gpu.hpp"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace b200s {
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int g_device = 0;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* get_last_error() { return g_last_error.c_str(); }
+int current_device() { return g_device; }
+void set_current_device(int d) { g_device = d; }
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,       \
+                     cudaGetErrorString(e__));                                                       \
+            set_last_error(buf__);                                                                   \
+            return e__ == cudaErrorMemoryAllocation ? ST_OOM : ST_CUDA;                              \
+        }                                                                                            \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// device structures
+// ---------------------------------------------------------------------------------------------------
+struct FrontD {
+    long long loff, uoff, reloff, rowptr;
+    int col0, nc, nr, ld;
+    int nchild, childptr, parent, level;
+};
+struct EAItem { int front, c0, c1; };
+
+constexpr int NB = 128;        // block-column width inside large fronts
+constexpr int TR = 64;         // rows per CTA in the panel triangular solve
+constexpr int LDL = NB + 4;    // smem stride of the diagonal block   (stride % 16 == 4 -> conflict-free DMMA fragment loads)
+constexpr int LDX = TR + 4;    // smem stride of the row tile
+constexpr int SMALL_NR = 128;  // fronts with nr <= SMALL_NR are factored by one CTA in shared memory
+constexpr int BT = 128;        // update tile is BT x BT
+constexpr int BK = 16;         // k-depth per pipeline stage
+constexpr int STAGES = 4;
+constexpr int LDT = BT + 4;    // smem stride of operand tiles
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ int lower_bound_dev(const int* a, int n, int v) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// group lookup: prefix[0..ng] increasing, returns g with prefix[g] <= b < prefix[g+1]
+__device__ __forceinline__ int find_group(const int* prefix, int ng, int b) {
+    int lo = 0, hi = ng;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= b) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: scatter the caller's CCS values into the (zeroed) panels
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_scatter_A(const double* __restrict__ val, const long long* __restrict__ amap, long long nnz,
+                            double* __restrict__ L) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+    for (; i < nnz; i += st) {
+        long long m = amap[i];
+        if (m >= 0) L[m] = val[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: extend-add.  One CTA per (front, column slab): zero the slab of the update matrix, then add every
+// child's update matrix entries that fall into the slab, children in ascending order.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_extend_add(const EAItem* __restrict__ items, const FrontD* __restrict__ F,
+                                                    const int* __restrict__ child_idx, const int* __restrict__ rel,
+                                                    double* __restrict__ L, double* __restrict__ W) {
+    const EAItem it = items[blockIdx.x];
+    const FrontD fp = F[it.front];
+    const int nc = fp.nc, nr = fp.nr, uo = nc & 1;
+    const int ldu = ((nr - nc + uo) + 1) & ~1;
+    double* Wp = W + fp.uoff;
+    double* Lp = L + fp.loff;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = max(it.c0, nc) + warp; c < it.c1; c += 8) {
+        double* col = Wp + (long long)(c - nc + uo) * ldu + (uo - nc);
+        for (int r = c + lane; r < nr; r += 32) col[r] = 0.0;
+    }
+    __syncthreads();
+    for (int q = 0; q < fp.nchild; q++) {
+        const FrontD fc = F[child_idx[fp.childptr + q]];
+        const int mc = fc.nr - fc.nc, uoc = fc.nc & 1;
+        const int ldc = ((mc + uoc) + 1) & ~1;
+        const int* rl = rel + fc.reloff;
+        const double* Wc = W + fc.uoff;
+        const int j0 = lower_bound_dev(rl, mc, it.c0), j1 = lower_bound_dev(rl, mc, it.c1);
+        for (int j = j0 + warp; j < j1; j += 8) {
+            const int pc = rl[j];
+            const double* src = Wc + (long long)(j + uoc) * ldc + uoc;
+            double* dst = (pc < nc) ? Lp + (long long)pc * fp.ld : Wp + (long long)(pc - nc + uo) * ldu + (uo - nc);
+            for (int i = j + lane; i < mc; i += 32) dst[rl[i]] += src[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// right-looking Cholesky of the first nc columns of an nr x nr lower-triangular matrix held in shared
+// memory (column-major, stride lds): potrf + trsm + syrk of a small front in one routine.
+// ---------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ void smem_partial_chol(double* S, int lds, int nr, int nc, int gcol0, int* minor,
+                                                  double dbound, bool record) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    for (int j = 0; j < nc; j++) {
+        __syncthreads();
+        const double d = S[j * lds + j];
+        if (!(d > 0.0) && record && tid == 0) atomicMin(minor, gcol0 + j);
+        double l = sqrt(d);
+        if (dbound > 0.0 && l < dbound) l = dbound;
+        const double inv = 1.0 / l;
+        for (int i = j + 1 + tid; i < nr; i += THREADS) S[j * lds + i] *= inv;
+        __syncthreads();
+        if (tid == 0) S[j * lds + j] = l;
+        for (int c = j + 1 + warp; c < nr; c += NW) {
+            const double lc = S[j * lds + c];
+            if (lc != 0.0)
+                for (int i = c + lane; i < nr; i += 32) S[c * lds + i] -= S[j * lds + i] * lc;
+        }
+    }
+    __syncthreads();
+}
+
+// K6: one CTA per small front (nr <= SMALL_NR): load panel + update matrix, factor, write back.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__ list, const FrontD* __restrict__ F,
+                                                         double* __restrict__ L, double* __restrict__ W, int* minor,
+                                                         double dbound) {
+    extern __shared__ double S[];
+    const FrontD f = F[list[blockIdx.x]];
+    const int nr = f.nr, nc = f.nc, m = nr - nc, uo = nc & 1, lds = nr | 1;
+    const int ldu = ((m + uo) + 1) & ~1;
+    double* P = L + f.loff;
+    double* U = W + f.uoff;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nr * nc; idx += THREADS) {
+        int c = idx / nr, r = idx - c * nr;
+        S[c * lds + r] = (r >= c) ? P[(long long)c * f.ld + r] : 0.0;
+    }
+    for (int idx = tid; idx < m * m; idx += THREADS) {
+        int c = idx / m, r = idx - c * m;
+        if (r >= c) S[(nc + c) * lds + nc + r] = U[(long long)(c + uo) * ldu + r + uo];
+    }
+    smem_partial_chol<THREADS>(S, lds, nr, nc, f.col0, minor, dbound, true);
+    for (int idx = tid; idx < nr * nc; idx += THREADS) {
+        int c = idx / nr, r = idx - c * nr;
+        if (r >= c) P[(long long)c * f.ld + r] = S[c * lds + r];
+    }
+    for (int idx = tid; idx < m * m; idx += THREADS) {
+        int c = idx / m, r = idx - c * m;
+        if (r >= c) U[(long long)(c + uo) * ldu + r + uo] = S[(nc + c) * lds + nc + r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2+K3: panel kernel for block column kb of large fronts.  CTA 0 of a front factors the diagonal block
+// and writes it back; every other CTA factors the same block redundantly in shared memory (no
+// inter-CTA dependency, no extra launch) and solves X L11^T = B for its 64-row tile.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront, const int* __restrict__ gprefix,
+                                                  int ngroups, int kb, const FrontD* __restrict__ F,
+                                                  double* __restrict__ L, double* __restrict__ diag_scratch,
+                                                  int* minor, double dbound) {
+    extern __shared__ double sm[];
+    double* Ls = sm;
+    double* Xs = Ls + NB * LDL;
+    double* rinv = Xs + NB * LDX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = find_group(gprefix, ngroups, blockIdx.x);
+    const int r = blockIdx.x - gprefix[g];
+    const FrontD f = F[gfront[g]];
+    const int k0 = kb * NB;
+    const int w = min(NB, f.nc - k0);
+    const int wpad = (w + 15) & ~15;
+    const int ld = f.ld;
+    double* P = L + f.loff;
+    for (int idx = tid; idx < wpad * wpad; idx += 256) {
+        int c = idx / wpad, rr = idx - c * wpad;
+        double v = 0.0;
+        if (c < w && rr < w) { if (rr >= c) v = P[(long long)(k0 + c) * ld + k0 + rr]; }
+        else if (rr == c) v = 1.0;
+        Ls[c * LDL + rr] = v;
+    }
+    const int row0 = k0 + w + (r - 1) * TR;
+    const int nrows = (r > 0) ? min(TR, f.nr - row0) : 0;
+    if (r > 0) {
+        for (int idx = tid; idx < wpad * TR; idx += 256) {
+            int c = idx / TR, i = idx - c * TR;
+            Xs[c * LDX + i] = (c < w && i < nrows) ? P[(long long)(k0 + c) * ld + row0 + i] : 0.0;
+        }
+    }
+    smem_partial_chol<256>(Ls, LDL, w, w, f.col0 + k0, minor, dbound, r == 0);
+    if (r == 0) {
+        // The factored block goes to scratch, not to the panel: CTAs of this launch that start later still
+        // have to read the UNfactored block.  k_diag_writeback copies it into the panel after this launch.
+        double* dst = diag_scratch + (size_t)g * NB * NB;
+        for (int idx = tid; idx < w * w; idx += 256) {
+            int c = idx / w, rr = idx - c * w;
+            if (rr >= c) dst[c * NB + rr] = Ls[c * LDL + rr];
+        }
+        return;
+    }
+    if (tid < wpad) rinv[tid] = 1.0 / Ls[tid * LDL + tid];
+    __syncthreads();
+    // ---- X L11^T = B, 16 columns at a time; warp owns rows [8*warp, 8*warp+8), 4 lanes per row
+    const int q = lane & 3, rw = warp * 8 + (lane >> 2);
+    for (int c0 = 0; c0 < wpad; c0 += 16) {
+        double b00 = Xs[(c0 + 2 * q) * LDX + rw], b01 = Xs[(c0 + 2 * q + 1) * LDX + rw];
+        double b10 = Xs[(c0 + 8 + 2 * q) * LDX + rw], b11 = Xs[(c0 + 8 + 2 * q + 1) * LDX + rw];
+        for (int k4 = 0; k4 < c0; k4 += 4) {
+            const double a = -Xs[(k4 + q) * LDX + rw];
+            const double l0 = Ls[(k4 + q) * LDL + c0 + (lane >> 2)];
+            const double l1 = Ls[(k4 + q) * LDL + c0 + 8 + (lane >> 2)];
+            dmma884(b00, b01, a, l0);
+            dmma884(b10, b11, a, l1);
+        }
+        // substitution against the 16x16 diagonal chunk, values stay in registers
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            const int owner = (p & 7) >> 1;
+            double cand = (p < 8) ? ((p & 1) ? b01 : b00) : ((p & 1) ? b11 : b10);
+            cand *= rinv[c0 + p];
+            const double xp = __shfl_sync(0xffffffffu, cand, (lane & ~3) | owner);
+            if (q == owner) { if (p < 8) { if (p & 1) b01 = xp; else b00 = xp; } else { if (p & 1) b11 = xp; else b10 = xp; } }
+            const double* lp = Ls + (c0 + p) * LDL + c0;
+            if (2 * q > p) b00 -= xp * lp[2 * q];
+            if (2 * q + 1 > p) b01 -= xp * lp[2 * q + 1];
+            if (8 + 2 * q > p) b10 -= xp * lp[8 + 2 * q];
+            if (8 + 2 * q + 1 > p) b11 -= xp * lp[8 + 2 * q + 1];
+        }
+        Xs[(c0 + 2 * q) * LDX + rw] = b00;
+        Xs[(c0 + 2 * q + 1) * LDX + rw] = b01;
+        Xs[(c0 + 8 + 2 * q) * LDX + rw] = b10;
+        Xs[(c0 + 8 + 2 * q + 1) * LDX + rw] = b11;
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * TR; idx += 256) {
+        int c = idx / TR, i = idx - c * TR;
+        if (i < nrows) P[(long long)(k0 + c) * ld + row0 + i] = Xs[c * LDX + i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_diag_writeback(const int* __restrict__ gfront, int kb,
+                                                        const FrontD* __restrict__ F, double* __restrict__ L,
+                                                        const double* __restrict__ diag_scratch) {
+    const FrontD f = F[gfront[blockIdx.x]];
+    const int k0 = kb * NB, w = min(NB, f.nc - k0);
+    double* P = L + f.loff;
+    const double* src = diag_scratch + (size_t)blockIdx.x * NB * NB;
+    for (int idx = threadIdx.x; idx < w * w; idx += 256) {
+        int c = idx / w, rr = idx - c * w;
+        if (rr >= c) P[(long long)(k0 + c) * f.ld + k0 + rr] = src[c * NB + rr];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: C(128x128 tile) -= A_i A_j^T with FP64 DMMA.  A_i, A_j are 128-row slices of the front's panel
+// (column-major, leading dimension ld), K columns starting at k0.
+//   mode 0: in-panel trailing update after block column kb (target columns inside the panel)
+//   mode 1: Schur complement into the update matrix (K = nc)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_tile_async(double* dst, const double* __restrict__ src, int ld, int rows_valid,
+                                                int kcols_valid, int tid) {
+    // BT rows x BK columns, 16-byte chunks: 64 chunks per column, 1024 chunks, 4 per thread
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int ch = tid + i * 256;
+        const int c = ch >> 6, r = (ch & 63) * 2;
+        int bytes = 0;
+        if (c < kcols_valid) bytes = (r + 1 < rows_valid) ? 16 : ((r < rows_valid) ? 8 : 0);
+        const double* s = (bytes > 0) ? src + (long long)c * ld + r : src;
+        cp_async16(dst + c * LDT + r, s, bytes);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfront, const int* __restrict__ gprefix,
+                                                   int ngroups, int mode, int kb, const FrontD* __restrict__ F,
+                                                   double* __restrict__ L, double* __restrict__ W) {
+    extern __shared__ double sm[];
+    double* As = sm;                          // [STAGES][BK][LDT]   rows of the tile's row block
+    double* Bs = sm + STAGES * BK * LDT;      // [STAGES][BK][LDT]   rows of the tile's column block
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = find_group(gprefix, ngroups, blockIdx.x);
+    int t = blockIdx.x - gprefix[g];
+    const FrontD f = F[gfront[g]];
+    const int nr = f.nr, nc = f.nc, ld = f.ld;
+    const double* P = L + f.loff;
+    int rowI, rowJ, k0, K, ldc, crows, ccols, lo;
+    double* C;
+    bool diag;
+    if (mode == 0) {
+        const int nrt = (nr + BT - 1) / BT;
+        int tj = kb + 1;
+        while (t >= nrt - tj) { t -= nrt - tj; tj++; }
+        const int ti = tj + t;
+        rowI = ti * BT; rowJ = tj * BT;
+        k0 = kb * NB; K = min(NB, nc - k0);
+        C = L + f.loff + rowI + (long long)rowJ * ld; ldc = ld;
+        crows = min(BT, nr - rowI); ccols = min(BT, nc - rowJ);
+        lo = 0; diag = (ti == tj);
+    } else {
+        const int r0 = nc - (nc & 1);
+        const int mu = nr - r0, T = (mu + BT - 1) / BT;
+        const int ldu = (mu + 1) & ~1;
+        int tj = 0;
+        while (t >= T - tj) { t -= T - tj; tj++; }
+        const int ti = tj + t;
+        rowI = r0 + ti * BT; rowJ = r0 + tj * BT;
+        k0 = 0; K = nc;
+        C = W + f.uoff + (long long)ti * BT + (long long)tj * BT * ldu; ldc = ldu;
+        crows = min(BT, nr - rowI); ccols = min(BT, nr - rowJ);
+        lo = nc; diag = (ti == tj);
+    }
+    const double* A = P + rowI + (long long)k0 * ld;
+    const double* B = P + rowJ + (long long)k0 * ld;
+    const int brows = ccols;
+
+    // warp tile: 64 C-rows (MMA N dimension, 8 tiles) x 32 C-columns (MMA M dimension, 4 tiles)
+    const int wr = (warp >> 2) * 64, wc = (warp & 3) * 32;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int nkt = (K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nkt) {
+            load_tile_async(As + s * BK * LDT, A + (long long)s * BK * ld, ld, crows, K - s * BK, tid);
+            load_tile_async(Bs + s * BK * LDT, B + (long long)s * BK * ld, ld, brows, K - s * BK, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nkt; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nk = kt + STAGES - 1;
+        if (nk < nkt) {
+            const int s = nk % STAGES;
+            load_tile_async(As + s * BK * LDT, A + (long long)nk * BK * ld, ld, crows, K - nk * BK, tid);
+            load_tile_async(Bs + s * BK * LDT, B + (long long)nk * BK * ld, ld, brows, K - nk * BK, tid);
+        }
+        cp_async_commit();
+        const double* as = As + (kt % STAGES) * BK * LDT;
+        const double* bs = Bs + (kt % STAGES) * BK * LDT;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double am[4], bn[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) am[i] = bs[(kk + (lane & 3)) * LDT + wc + i * 8 + (lane >> 2)];
+#pragma unroll
+            for (int j = 0; j < 8; j++) bn[j] = as[(kk + (lane & 3)) * LDT + wr + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], am[i], bn[j]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: thread holds C rows (r, r+1) of one column per accumulator pair
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int c = wc + i * 8 + (lane >> 2);
+        if (c >= ccols || rowJ + c < lo) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = wr + j * 8 + 2 * (lane & 3);
+            double* p = C + (long long)c * ldc + r;
+            const bool v0 = r < crows && rowI + r >= lo && (!diag || r >= c);
+            const bool v1 = r + 1 < crows && rowI + r + 1 >= lo && (!diag || r + 1 >= c);
+            if (v0 && v1) {
+                double2 x = *reinterpret_cast<double2*>(p);
+                x.x -= acc[i][j][0]; x.y -= acc[i][j][1];
+                *reinterpret_cast<double2*>(p) = x;
+            } else if (v0) p[0] -= acc[i][j][0];
+            else if (v1) p[1] -= acc[i][j][1];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7: supernodal triangular solves, one CTA per (front, right-hand side), level by level.
+// Work vector of a front: T[rowptr .. rowptr+nr) (first nc entries = solution block, rest = the update
+// vector handed to the parent through the same relative indices as the factorization).
+// ---------------------------------------------------------------------------------------------------
+constexpr int CB = 32;
+__global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const FrontD* __restrict__ F,
+                                             const int* __restrict__ child_idx, const int* __restrict__ rel,
+                                             const double* __restrict__ L, double* __restrict__ T, long long tstride,
+                                             double* __restrict__ X, long long xstride) {
+    __shared__ double D[CB][CB + 1];
+    __shared__ double xs[CB];
+    const FrontD f = F[list[blockIdx.x]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    double* x = X + blockIdx.y * xstride + f.col0;
+    const double* P = L + f.loff;
+    const int nr = f.nr, nc = f.nc, ld = f.ld, tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < nr; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
+    __syncthreads();
+    for (int q = 0; q < f.nchild; q++) {
+        const FrontD fc = F[child_idx[f.childptr + q]];
+        const int mc = fc.nr - fc.nc;
+        const int* rl = rel + fc.reloff;
+        const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
+        for (int i = tid; i < mc; i += 256) t[rl[i]] += tc[i];
+        __syncthreads();
+    }
+    for (int b0 = 0; b0 < nc; b0 += CB) {
+        const int wb = min(CB, nc - b0);
+        for (int idx = tid; idx < wb * wb; idx += 256) {
+            int c = idx / wb, r = idx - c * wb;
+            D[r][c] = (r >= c) ? P[(long long)(b0 + c) * ld + b0 + r] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double v = (lane < wb) ? t[b0 + lane] : 0.0;
+            for (int qq = 0; qq < wb; qq++) {
+                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
+                if (lane == qq) v = xq;
+                else if (lane > qq && lane < wb) v -= xq * D[lane][qq];
+            }
+            if (lane < wb) { xs[lane] = v; t[b0 + lane] = v; x[b0 + lane] = v; }
+        }
+        __syncthreads();
+        for (int r = b0 + wb + tid; r < nr; r += 256) {
+            double acc = t[r];
+            const double* col = P + (long long)b0 * ld + r;
+            for (int qq = 0; qq < wb; qq++) acc -= col[(long long)qq * ld] * xs[qq];
+            t[r] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const FrontD* __restrict__ F,
+                                             const int* __restrict__ rows, const double* __restrict__ L,
+                                             double* __restrict__ T, long long tstride, double* __restrict__ X,
+                                             long long xstride) {
+    __shared__ double D[CB][CB + 1];
+    __shared__ double zs[CB];
+    const FrontD f = F[list[blockIdx.x]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    double* xg = X + blockIdx.y * xstride;
+    const double* P = L + f.loff;
+    const int* rw = rows + f.rowptr;
+    const int nr = f.nr, nc = f.nc, ld = f.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < nr; i += 256) t[i] = xg[rw[i]];
+    __syncthreads();
+    const int nblk = (nc + CB - 1) / CB;
+    for (int b = nblk - 1; b >= 0; b--) {
+        const int b0 = b * CB, wb = min(CB, nc - b0);
+        for (int idx = tid; idx < wb * wb; idx += 256) {
+            int c = idx / wb, r = idx - c * wb;
+            D[r][c] = (r >= c) ? P[(long long)(b0 + c) * ld + b0 + r] : 0.0;
+        }
+        for (int qq = warp; qq < wb; qq += 8) {
+            const double* col = P + (long long)(b0 + qq) * ld;
+            double s = 0.0;
+            for (int r = b0 + wb + lane; r < nr; r += 32) s += col[r] * t[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) zs[qq] = t[b0 + qq] - s;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double v = (lane < wb) ? zs[lane] : 0.0;
+            for (int qq = wb - 1; qq >= 0; qq--) {
+                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
+                if (lane == qq) v = xq;
+                else if (lane < qq) v -= xq * D[qq][lane];
+            }
+            if (lane < wb) { t[b0 + lane] = v; xg[f.col0 + b0 + lane] = v; }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_perm_gather(const double* __restrict__ B, long long ldB, const int* __restrict__ perm, int n,
+                              double* __restrict__ X, long long ldX) {
+    const double* b = B + blockIdx.y * ldB;
+    double* x = X + blockIdx.y * ldX;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) x[k] = b[perm[k]];
+}
+__global__ void k_perm_scatter(double* __restrict__ B, long long ldB, const int* __restrict__ perm, int n,
+                               const double* __restrict__ X, long long ldX) {
+    double* b = B + blockIdx.y * ldB;
+    const double* x = X + blockIdx.y * ldX;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) b[perm[k]] = x[k];
+}
+__global__ void k_copy_cols(const double* __restrict__ S, long long lds, double* __restrict__ Dst, long long ldd, int n) {
+    const double* s = S + blockIdx.y * lds;
+    double* d = Dst + blockIdx.y * ldd;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) d[k] = s[k];
+}
+__global__ void k_diag(const FrontD* __restrict__ F, int ns, const double* __restrict__ L, double* __restrict__ d) {
+    for (int s = blockIdx.x; s < ns; s += gridDim.x) {
+        const FrontD f = F[s];
+        for (int c = threadIdx.x; c < f.nc; c += blockDim.x) d[f.col0 + c] = L[f.loff + (long long)c * f.ld + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side driver
+// ---------------------------------------------------------------------------------------------------
+struct Launch {            // one grouped launch: groups [goff, goff+ng) in the schedule arrays, `ctas` CTAs
+    int goff = 0, ng = 0, ctas = 0;
+};
+struct LevelSched {
+    int ea_off = 0, ea_cnt = 0;
+    int small_off[3] = {0, 0, 0}, small_cnt[3] = {0, 0, 0}, small_maxnr[3] = {0, 0, 0};
+    std::vector<Launch> panel, upd;   // per block step kb
+    Launch syrk;
+};
+
+class CholDevice {
+public:
+    const CholPlan* plan = nullptr;
+    CholOpts opts;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    double *dL = nullptr, *dW = nullptr, *dval = nullptr, *dT = nullptr, *dX = nullptr, *dBstage = nullptr;
+    i64 bstage_cap = 0;            // doubles
+    long long* damap = nullptr;
+    FrontD* dF = nullptr;
+    int *drows = nullptr, *drel = nullptr, *dchild = nullptr, *dperm = nullptr, *dlevel_fronts = nullptr;
+    int *dsched = nullptr, *dminor = nullptr;
+    double* ddiag = nullptr;       // scratch for factored diagonal blocks of one panel launch
+    EAItem* dea = nullptr;
+    std::vector<LevelSched> levels;
+    i64 solve_cols = 0;            // capacity (columns) of dT / dX
+    bool numeric = false, profiling = false;
+    cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> pev;  // profiling event pool
+    i64 total_bytes = 0;
+
+    ~CholDevice() {
+        cudaSetDevice(device);
+        cudaFree(dL); cudaFree(dW); cudaFree(dval); cudaFree(dT); cudaFree(dX); cudaFree(dBstage); cudaFree(damap); cudaFree(dF);
+        cudaFree(drows); cudaFree(drel); cudaFree(dchild); cudaFree(dperm); cudaFree(dlevel_fronts);
+        cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : pev) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    template <class T> int upload(T** dst, const T* src, size_t count) {
+        size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        CUDA_TRY(cudaMalloc((void**)dst, bytes));
+        total_bytes += bytes;
+        if (count) CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        return ST_OK;
+    }
+    int init();
+    int factorize(const double* val, bool on_device, i64* minor, CholTimes* times);
+    int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times);
+    int ensure_solve_ws(i64 cols);
+};
+
+static constexpr size_t SMEM_PANEL = (size_t)(NB * LDL + NB * LDX + NB) * sizeof(double);
+static constexpr size_t SMEM_UPDATE = (size_t)(2 * STAGES * BK * LDT) * sizeof(double);
+
+int CholDevice::init() {
+    const CholPlan& P = *plan;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    const int ns = (int)P.fronts.size();
+    std::vector<FrontD> hf(ns);
+    for (int s = 0; s < ns; s++) {
+        const Front& f = P.fronts[s];
+        FrontD d;
+        d.loff = f.loff; d.uoff = f.uoff; d.reloff = f.reloff; d.rowptr = f.rowptr;
+        d.col0 = f.col0; d.nc = f.nc; d.nr = f.nr; d.ld = f.ld;
+        d.nchild = P.child_ptr[s + 1] - P.child_ptr[s]; d.childptr = P.child_ptr[s];
+        d.parent = f.parent; d.level = f.level;
+        hf[s] = d;
+    }
+    int rc;
+    if ((rc = upload(&dF, hf.data(), hf.size()))) return rc;
+    if ((rc = upload(&drows, P.rows.data(), P.rows.size()))) return rc;
+    if ((rc = upload(&drel, P.rel.data(), P.rel.size()))) return rc;
+    if ((rc = upload(&dchild, P.child_idx.data(), P.child_idx.size()))) return rc;
+    if ((rc = upload(&dperm, P.perm.data(), P.perm.size()))) return rc;
+    if ((rc = upload(&dlevel_fronts, P.level_fronts.data(), P.level_fronts.size()))) return rc;
+    {
+        std::vector<long long> am(P.amap.begin(), P.amap.end());
+        if ((rc = upload(&damap, am.data(), am.size()))) return rc;
+    }
+    CUDA_TRY(cudaMalloc((void**)&dL, std::max<i64>(P.lsize, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dW, std::max<i64>(P.wsize, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dval, std::max<i64>(P.nnzA, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dminor, sizeof(int)));
+    total_bytes += (P.lsize + P.wsize + P.nnzA) * sizeof(double);
+
+    // ---- schedule
+    std::vector<int> sched;          // group arrays: [front ids...][prefix...]
+    std::vector<EAItem> ea;
+    levels.resize(P.nlevels);
+    const long long EA_TARGET = 16384;
+    for (int l = 0; l < P.nlevels; l++) {
+        LevelSched& LS = levels[l];
+        std::vector<int> smalls[3], bigs;
+        LS.ea_off = (int)ea.size();
+        for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; q++) {
+            const int s = P.level_fronts[q];
+            const Front& f = P.fronts[s];
+            const int nchild = P.child_ptr[s + 1] - P.child_ptr[s];
+            // extend-add items
+            int cbeg = nchild > 0 ? 0 : f.nc;
+            long long acc = 0;
+            int c0 = cbeg;
+            for (int c = cbeg; c < f.nr; c++) {
+                acc += f.nr - c;
+                if (acc >= EA_TARGET || c == f.nr - 1) { ea.push_back({s, c0, c + 1}); c0 = c + 1; acc = 0; }
+            }
+            if (f.nr <= SMALL_NR) {
+                int cls = f.nr <= 32 ? 0 : (f.nr <= 64 ? 1 : 2);
+                smalls[cls].push_back(s);
+                LS.small_maxnr[cls] = std::max(LS.small_maxnr[cls], f.nr);
+            } else bigs.push_back(s);
+        }
+        LS.ea_cnt = (int)ea.size() - LS.ea_off;
+        for (int c = 0; c < 3; c++) {
+            LS.small_off[c] = (int)sched.size();
+            LS.small_cnt[c] = (int)smalls[c].size();
+            sched.insert(sched.end(), smalls[c].begin(), smalls[c].end());
+        }
+        int maxblk = 0;
+        for (int s : bigs) maxblk = std::max(maxblk, (P.fronts[s].nc + NB - 1) / NB);
+        LS.panel.resize(maxblk);
+        LS.upd.resize(maxblk);
+        auto emit = [&](Launch& la, const std::vector<int>& fr, const std::vector<int>& cnt) {
+            la.goff = (int)sched.size();
+            la.ng = (int)fr.size();
+            sched.insert(sched.end(), fr.begin(), fr.end());
+            int run = 0;
+            for (int c : cnt) { sched.push_back(run); run += c; }
+            sched.push_back(run);
+            la.ctas = run;
+        };
+        for (int kb = 0; kb < maxblk; kb++) {
+            std::vector<int> fr, cp, fu, cu;
+            for (int s : bigs) {
+                const Front& f = P.fronts[s];
+                const int nblk = (f.nc + NB - 1) / NB;
+                if (kb >= nblk) continue;
+                const int w = std::min(NB, f.nc - kb * NB);
+                const int below = f.nr - (kb * NB + w);
+                fr.push_back(s);
+                cp.push_back(1 + (below + TR - 1) / TR);
+                const int nrt = (f.nr + BT - 1) / BT;
+                long long tiles = 0;
+                for (int tj = kb + 1; tj < nblk; tj++) tiles += nrt - tj;
+                if (tiles > 0) { fu.push_back(s); cu.push_back((int)tiles); }
+            }
+            emit(LS.panel[kb], fr, cp);
+            emit(LS.upd[kb], fu, cu);
+        }
+        {
+            std::vector<int> fr, cnt;
+            for (int s : bigs) {
+                const Front& f = P.fronts[s];
+                if (f.nr == f.nc) continue;
+                const int r0 = f.nc - (f.nc & 1);
+                const long long T = (f.nr - r0 + BT - 1) / BT;
+                fr.push_back(s);
+                cnt.push_back((int)(T * (T + 1) / 2));
+            }
+            emit(LS.syrk, fr, cnt);
+        }
+    }
+    {
+        int maxng = 1;
+        for (auto& LS : levels) for (auto& la : LS.panel) maxng = std::max(maxng, la.ng);
+        CUDA_TRY(cudaMalloc((void**)&ddiag, (size_t)maxng * NB * NB * sizeof(double)));
+        total_bytes += (size_t)maxng * NB * NB * sizeof(double);
+    }
+    if ((rc = upload(&dsched, sched.data(), sched.size()))) return rc;
+    if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
+    CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_small_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((SMALL_NR | 1) * SMALL_NR * sizeof(double))));
+    CUDA_TRY(cudaFuncSetAttribute(k_small_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
+    return ST_OK;
+}
+
+int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTimes* times) {
+    const CholPlan& P = *plan;
+    CUDA_TRY(cudaSetDevice(device));
+    numeric = false;
+    const int ns = (int)P.fronts.size();
+    CUDA_TRY(cudaEventRecord(ev[0], stream));
+    const double* dv = val;
+    if (!on_device) {
+        if (P.nnzA) CUDA_TRY(cudaMemcpyAsync(dval, val, P.nnzA * sizeof(double), cudaMemcpyHostToDevice, stream));
+        dv = dval;
+    }
+    CUDA_TRY(cudaEventRecord(ev[1], stream));
+    const int big = 0x7fffffff;
+    CUDA_TRY(cudaMemcpyAsync(dminor, &big, sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (P.lsize) CUDA_TRY(cudaMemsetAsync(dL, 0, P.lsize * sizeof(double), stream));
+    if (P.nnzA) {
+        int blocks = (int)std::min<i64>((P.nnzA + 255) / 256, 148 * 16);
+        k_scatter_A<<<blocks, 256, 0, stream>>>(dv, damap, P.nnzA, dL);
+    }
+    CUDA_TRY(cudaEventRecord(ev[2], stream));
+    size_t pe = 0;
+    struct Span { int cls; size_t e0, e1; };
+    std::vector<Span> spans;
+    auto prof_begin = [&](int cls) -> int {
+        if (!profiling) return 0;
+        while (pev.size() < pe + 2) { cudaEvent_t e; cudaEventCreate(&e); pev.push_back(e); }
+        cudaEventRecord(pev[pe], stream);
+        spans.push_back({cls, pe, pe + 1});
+        pe += 2;
+        return 0;
+    };
+    auto prof_end = [&]() { if (profiling) cudaEventRecord(pev[spans.back().e1], stream); };
+    for (int l = 0; l < P.nlevels; l++) {
+        const LevelSched& LS = levels[l];
+        if (LS.ea_cnt) {
+            prof_begin(0);
+            k_extend_add<<<LS.ea_cnt, 256, 0, stream>>>(dea + LS.ea_off, dF, dchild, drel, dL, dW);
+            prof_end();
+        }
+        prof_begin(1);
+        if (LS.small_cnt[0])
+            k_small_front<64><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(
+                dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound);
+        if (LS.small_cnt[1])
+            k_small_front<128><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(
+                dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound);
+        if (LS.small_cnt[2])
+            k_small_front<256><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(
+                dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound);
+        prof_end();
+        for (size_t kb = 0; kb < LS.panel.size(); kb++) {
+            const Launch& lp = LS.panel[kb];
+            if (lp.ctas) {
+                prof_begin(2);
+                k_panel<<<lp.ctas, 256, SMEM_PANEL, stream>>>(dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
+                                                              dF, dL, ddiag, dminor, opts.dbound);
+                k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag);
+                prof_end();
+            }
+            const Launch& lu = LS.upd[kb];
+            if (lu.ctas) {
+                prof_begin(3);
+                k_update<<<lu.ctas, 256, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                                                                (int)kb, dF, dL, dW);
+                prof_end();
+            }
+        }
+        if (LS.syrk.ctas) {
+            prof_begin(3);
+            k_update<<<LS.syrk.ctas, 256, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+                                                                 LS.syrk.ng, 1, 0, dF, dL, dW);
+            prof_end();
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    int hminor = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hminor, dminor, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(ev[3], stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    (void)ns;
+    if (times) {
+        float ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); times->ms_h2d = ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); times->ms_assemble = ms;
+        cudaEventElapsedTime(&ms, ev[2], ev[3]); times->ms_factor = ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[3]); times->ms_total = ms;
+        times->ms_extend = times->ms_potrf = times->ms_trsm = times->ms_dense_update = 0;
+        for (auto& sp : spans) {
+            cudaEventElapsedTime(&ms, pev[sp.e0], pev[sp.e1]);
+            if (sp.cls == 0) times->ms_extend += ms;
+            else if (sp.cls == 1) times->ms_potrf += ms;       // small fronts (all three phases fused)
+            else if (sp.cls == 2) times->ms_trsm += ms;        // panel kernels (diag block + triangular solves)
+            else times->ms_dense_update += ms;
+        }
+    }
+    if (hminor != big) {
+        if (minor) *minor = hminor;
+        return ST_NOT_POSDEF;
+    }
+    if (minor) *minor = P.n;
+    numeric = true;
+    return ST_OK;
+}
+
+int CholDevice::ensure_solve_ws(i64 cols) {
+    if (cols <= solve_cols) return ST_OK;
+    cudaFree(dT); cudaFree(dX); dT = dX = nullptr; solve_cols = 0;
+    const CholPlan& P = *plan;
+    CUDA_TRY(cudaMalloc((void**)&dT, std::max<i64>((i64)P.rows.size() * cols, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dX, std::max<i64>((i64)P.n * cols, 1) * sizeof(double)));
+    solve_cols = cols;
+    return ST_OK;
+}
+
+int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times) {
+    const CholPlan& P = *plan;
+    const int n = P.n;
+    if (n == 0 || nrhs == 0) return ST_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    // chunk of right-hand sides processed per pass (bounded workspace)
+    const i64 maxcols = std::max<i64>(1, std::min<i64>(nrhs, (i64)(256ll << 20) / std::max<i64>(1, (i64)P.rows.size() * 8)));
+    int rc = ensure_solve_ws(std::min<i64>(maxcols, 64));
+    if (rc) return rc;
+    const i64 chunk = solve_cols;
+    CUDA_TRY(cudaEventRecord(ev[4], stream));
+    double* dB = B;
+    if (!on_device) {
+        if ((i64)n * nrhs > bstage_cap) {
+            cudaFree(dBstage); dBstage = nullptr; bstage_cap = 0;
+            CUDA_TRY(cudaMalloc((void**)&dBstage, (size_t)n * nrhs * sizeof(double)));
+            bstage_cap = (i64)n * nrhs;
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(dBstage, (size_t)n * 8, B, (size_t)ldB * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, stream));
+        dB = dBstage;
+    }
+    const i64 ldd = on_device ? ldB : n;
+    const bool do_perm = (sys == 0), do_fwd = (sys == 0 || sys == 1 || sys == 2 || sys == 4),
+               do_bwd = (sys == 0 || sys == 1 || sys == 3 || sys == 5);
+    const int gx = std::min((n + 255) / 256, 148 * 8);
+    const i64 tstride = (i64)P.rows.size();
+    for (i64 j0 = 0; j0 < nrhs; j0 += chunk) {
+        const int nc = (int)std::min<i64>(chunk, nrhs - j0);
+        double* b = dB + j0 * ldd;
+        if (sys == 7) {          // x = P b
+            k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
+            k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
+            continue;
+        }
+        if (sys == 8) {          // x = P' b
+            k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, dperm, n, b, ldd);
+            k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
+            continue;
+        }
+        if (sys == 6) continue;  // D x = b with D = I
+        if (do_perm) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
+        else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dX, n, n);
+        if (do_fwd)
+            for (int l = 0; l < P.nlevels; l++) {
+                const int cnt = P.level_ptr[l + 1] - P.level_ptr[l];
+                k_fwd<<<dim3(cnt, nc), 256, 0, stream>>>(dlevel_fronts + P.level_ptr[l], dF, dchild, drel, dL, dT, tstride, dX, n);
+            }
+        if (do_bwd)
+            for (int l = P.nlevels - 1; l >= 0; l--) {
+                const int cnt = P.level_ptr[l + 1] - P.level_ptr[l];
+                k_bwd<<<dim3(cnt, nc), 256, 0, stream>>>(dlevel_fronts + P.level_ptr[l], dF, drows, dL, dT, tstride, dX, n);
+            }
+        if (do_perm) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
+        else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
+    }
+    cudaError_t le = cudaGetLastError();
+    if (!on_device && le == cudaSuccess)
+        le = cudaMemcpy2DAsync(B, (size_t)ldB * 8, dBstage, (size_t)n * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, stream);
+    cudaEventRecord(ev[5], stream);
+    cudaError_t se = cudaStreamSynchronize(stream);
+    CUDA_TRY(le);
+    CUDA_TRY(se);
+    if (times) { float ms; cudaEventElapsedTime(&ms, ev[4], ev[5]); times->ms_solve = ms; }
+    return ST_OK;
+}
+
+CholDevice* chol_device_create(const CholPlan& plan, const CholOpts& opts, int device, int* status) {
+    if (device_count() <= 0) { *status = ST_NO_DEVICE; set_last_error("no CUDA device available"); return nullptr; }
+    CholDevice* d = new CholDevice();
+    d->plan = &plan;
+    d->opts = opts;
+    d->device = device;
+    *status = d->init();
+    if (*status != ST_OK) { delete d; return nullptr; }
+    return d;
+}
+void chol_device_destroy(CholDevice* d) { delete d; }
+int chol_device_factorize(CholDevice* d, const double* val, bool val_on_device, i64* minor, CholTimes* times) {
+    return d->factorize(val, val_on_device, minor, times);
+}
+int chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times) {
+    return d->solve(sys, B, nrhs, ldB, on_device, times);
+}
+int chol_device_diag(CholDevice* d, double* diag_host) {
+    const CholPlan& P = *d->plan;
+    if (P.n == 0) return ST_OK;
+    CUDA_TRY(cudaSetDevice(d->device));
+    int rc = d->ensure_solve_ws(1);
+    if (rc) return rc;
+    k_diag<<<std::min<int>((int)P.fronts.size(), 148 * 8), 128, 0, d->stream>>>(d->dF, (int)P.fronts.size(), d->dL, d->dX);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(diag_host, d->dX, P.n * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return ST_OK;
+}
+int chol_device_download_L(CholDevice* d, double* L_host) {
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    if (d->plan->lsize) CUDA_TRY(cudaMemcpy(L_host, d->dL, d->plan->lsize * sizeof(double), cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+void chol_device_set_profiling(CholDevice* d, bool on) { d->profiling = on; }
+i64 chol_device_workspace_bytes(const CholDevice* d) { return d->total_bytes; }
+
+}  // namespace b200s

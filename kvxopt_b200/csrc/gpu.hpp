@@ -1,0 +1,33 @@
+// Device side of the engine as seen by the C ABI (capi.cu).  Implemented in chol_gpu.cu / klu_gpu.cu.
+#pragma once
+#include "host.hpp"
+#include <string>
+
+namespace b200s {
+
+// status codes shared with include/b200sparse.h (kept numerically identical)
+enum : int { ST_OK = 0, ST_NOT_POSDEF = 1, ST_SINGULAR = 2, ST_OOM = -2, ST_TOO_LARGE = -3, ST_INVALID = -4,
+             ST_NO_DEVICE = -5, ST_CUDA = -6 };
+
+void set_last_error(const std::string& s);
+const char* get_last_error();
+int  current_device();          // device chosen with b200s_set_device (default 0)
+void set_current_device(int d);
+int  device_count();
+
+struct CholTimes {
+    double ms_h2d = 0, ms_assemble = 0, ms_factor = 0, ms_total = 0, ms_solve = 0;
+    double ms_dense_update = 0, ms_potrf = 0, ms_trsm = 0, ms_extend = 0;
+};
+
+class CholDevice;   // device-resident plan + numeric factor
+CholDevice* chol_device_create(const CholPlan& plan, const CholOpts& opts, int device, int* status);
+void chol_device_destroy(CholDevice* d);
+int  chol_device_factorize(CholDevice* d, const double* val, bool val_on_device, i64* minor, CholTimes* times);
+int  chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times);
+int  chol_device_diag(CholDevice* d, double* diag_host);
+int  chol_device_download_L(CholDevice* d, double* L_host);   // raw panel storage, plan.lsize doubles
+void chol_device_set_profiling(CholDevice* d, bool on);
+i64  chol_device_workspace_bytes(const CholDevice* d);
+
+}  // namespace b200s

@@ -1,0 +1,100 @@
+"""CPU oracle (TEST INFRASTRUCTURE): ctypes access to oracle/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_lib = None
+i64 = C.c_int64
+pi = C.POINTER(C.c_int64)
+pd = C.POINTER(C.c_double)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            from . import build as _b
+            _b.build()
+        _lib = C.CDLL(_LIB)
+        L = _lib
+        L.oracle_chol_analyze.restype = C.c_void_p
+        L.oracle_chol_analyze.argtypes = [i64, pi, pi, C.c_char, pi]
+        L.oracle_chol_free.argtypes = [C.c_void_p]
+        L.oracle_chol_factorize.argtypes = [C.c_void_p, pd]
+        L.oracle_chol_solve.argtypes = [C.c_void_p, C.c_int, pd, i64, i64]
+        L.oracle_chol_diag.argtypes = [C.c_void_p, pd]
+        L.oracle_chol_get_perm.argtypes = [C.c_void_p, pi]
+        L.oracle_chol_dense_L.argtypes = [C.c_void_p, pd]
+        for f in ("oracle_chol_nnzL", "oracle_chol_nsuper", "oracle_chol_minor"):
+            getattr(L, f).restype = i64
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.oracle_chol_flops.restype = C.c_double
+        L.oracle_chol_flops.argtypes = [C.c_void_p]
+        L.oracle_blas_threads.argtypes = [C.c_int]
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class CholOracle:
+    """Supernodal left-looking LL^T of the `uplo` triangle of a CCS matrix (colptr,rowind,values)."""
+
+    def __init__(self, n, colptr, rowind, uplo="L", perm=None):
+        self.n = int(n)
+        self.colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        self.rowind = np.ascontiguousarray(rowind, dtype=np.int64)
+        p = np.ascontiguousarray(perm, dtype=np.int64) if perm is not None else None
+        self.h = lib().oracle_chol_analyze(self.n, _p(self.colptr, pi), _p(self.rowind, pi), uplo.encode(),
+                                           _p(p, pi) if p is not None else None)
+        if not self.h:
+            raise ValueError("oracle: invalid permutation")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_chol_free(self.h)
+            self.h = None
+
+    def factorize(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        st = lib().oracle_chol_factorize(self.h, _p(v, pd))
+        if st:
+            raise ArithmeticError(int(lib().oracle_chol_minor(self.h)))
+
+    def solve(self, B, sys=0):
+        X = np.array(B, dtype=np.float64, order="F", copy=True)
+        X2 = X.reshape(self.n, -1, order="F")
+        st = lib().oracle_chol_solve(self.h, sys, _p(X2, pd), X2.shape[1], max(self.n, 1))
+        if st:
+            raise ValueError("oracle solve failed: %d" % st)
+        return X
+
+    def diag(self):
+        d = np.zeros(self.n)
+        lib().oracle_chol_diag(self.h, _p(d, pd))
+        return d
+
+    def perm(self):
+        p = np.zeros(self.n, dtype=np.int64)
+        lib().oracle_chol_get_perm(self.h, _p(p, pi))
+        return p
+
+    def dense_L(self):
+        L = np.zeros((self.n, self.n), order="F")
+        lib().oracle_chol_dense_L(self.h, _p(L, pd))
+        return L
+
+    @property
+    def nnzL(self):
+        return int(lib().oracle_chol_nnzL(self.h))
+
+    @property
+    def flops(self):
+        return float(lib().oracle_chol_flops(self.h))
