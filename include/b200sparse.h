@@ -149,6 +149,14 @@ b200s_status b200s_klu_analyze(b200s_int n, const b200s_int* colptr, const b200s
 b200s_status b200s_klu_factor(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind,
                               const double* val, b200s_klu_num** out);
 
+/* The pivot search of b200s_klu_factor alone (host only, no device upload): pattern of L, U, F, the pivot
+ * order and the row scaling of ONE matrix.  It exists so that the host logic can be verified without a
+ * GPU and so that tools can inspect the pivot sequence; solves on such an object return B200S_NO_DEVICE.
+ * b200s_klu_extract_host returns the values this pivot search computed as a by-product. */
+b200s_status b200s_klu_pivot_host(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind,
+                                  const double* val, b200s_klu_num** out);
+b200s_status b200s_klu_extract_host(const b200s_klu_num* N, double* Lx, double* Ux, double* Fx, double* Rs);
+
 /* Batched numeric refactorization (klu_refactor semantics: same pattern, same pivot sequence, fresh
  * row scaling) of `batch` matrices whose values are vals[b*ldv + k], k indexing the CCS given to
  * b200s_klu_factor.  Factors stay resident on the device for b200s_klu_solve_batch.
@@ -186,6 +194,21 @@ b200s_status b200s_klu_extract(const b200s_klu_num* N,
 /* download the factor of matrix b of the last batch in the same layout (values only; pattern/P/Q shared) */
 b200s_status b200s_klu_extract_batch(b200s_klu_num* N, b200s_int b, double* Lx, double* Ux,
                                      double* Fx, double* Rs);
+
+/* Read-only view of the static refactorization plan (pattern + pivot order frozen by b200s_klu_factor)
+ * that the batched kernels replay; pointers stay valid while N lives.  For tests and tools.
+ * Value slot v of matrix b lives at LU[v*batch_padded + b]; column k owns slots [cbeg[k], cbeg[k+1]):
+ * U above the diagonal (ascending rows), U(k,k) at udiag_slot[k], L below the diagonal from lslot0[k];
+ * F entries of column k start at fslot0[k].  slot_src[v] indexes the caller's value array (-1 = fill-in),
+ * slot_row[v] is the pivotal row whose scale factor divides it.  Column k applies, for each u in
+ * [upd_ptr[k], upd_ptr[k+1]): LU[dest[upd_dest[u]+t]] -= LU[upd_lslot[u]+t] * LU[upd_uslot[u]], t < upd_cnt[u]. */
+typedef struct {
+    b200s_int n, nlevels, nslots, lu_slots, nnz_A, nupd, ndest;
+    const int64_t *cbeg, *rowptr, *upd_ptr, *upd_dest;
+    const int32_t *udiag_slot, *slot_src, *slot_row, *rowent, *level_ptr, *level_cols, *upd_uslot, *upd_lslot,
+                  *upd_cnt, *dest, *lslot0, *fslot0;
+} b200s_klu_plan_view_t;
+b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* view);
 
 void b200s_klu_free_symbolic(b200s_klu_sym* S);   /* src/C/klu.c:51-61 */
 void b200s_klu_free_numeric(b200s_klu_num* N);    /* src/C/klu.c:63-72 */

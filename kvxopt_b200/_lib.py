@@ -28,7 +28,7 @@ OK, NOT_POSDEF, SINGULAR = 0, 1, 2
 OUT_OF_MEMORY, TOO_LARGE, INVALID, NO_DEVICE, CUDA_ERROR = -2, -3, -4, -5, -6
 
 
-from ._lib_types import CholOpts, CholInfo, KluInfo  # noqa: E402,F401
+from ._lib_types import CholOpts, CholInfo, KluInfo, KluPlanView  # noqa: E402,F401
 
 
 def _sig(name, restype, *argtypes):
@@ -65,6 +65,8 @@ SIGNATURES = {
     "b200s_amd_order": (C.c_int, i64, p_i64, p_i64, C.c_char, p_i64),
     "b200s_klu_analyze": (C.c_int, i64, p_i64, p_i64, C.POINTER(vp)),
     "b200s_klu_factor": (C.c_int, vp, p_i64, p_i64, p_f64, C.POINTER(vp)),
+    "b200s_klu_pivot_host": (C.c_int, vp, p_i64, p_i64, p_f64, C.POINTER(vp)),
+    "b200s_klu_extract_host": (C.c_int, vp, p_f64, p_f64, p_f64, p_f64),
     "b200s_klu_refactor_batch": (C.c_int, vp, p_f64, i64, i64, p_int),
     "b200s_klu_refactor_batch_dev": (C.c_int, vp, vp, i64, i64, p_int),
     "b200s_klu_solve_batch": (C.c_int, vp, C.c_int, p_f64, i64, i64, i64),
@@ -74,6 +76,7 @@ SIGNATURES = {
     "b200s_klu_extract": (C.c_int, vp, p_i64, p_i64, p_f64, p_i64, p_i64, p_f64, p_i64, p_i64, p_f64,
                           p_i64, p_i64, p_f64, p_i64),
     "b200s_klu_extract_batch": (C.c_int, vp, i64, p_f64, p_f64, p_f64, p_f64),
+    "b200s_klu_plan_view": (C.c_int, vp, C.POINTER(KluPlanView)),
     "b200s_klu_free_symbolic": (None, vp),
     "b200s_klu_free_numeric": (None, vp),
 }

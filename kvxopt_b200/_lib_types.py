@@ -29,3 +29,10 @@ class KluInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+
+
+class KluPlanView(C.Structure):
+    _fields_ = [(k, i64) for k in ("n", "nlevels", "nslots", "lu_slots", "nnz_A", "nupd", "ndest")] + \
+               [(k, C.POINTER(C.c_int64)) for k in ("cbeg", "rowptr", "upd_ptr", "upd_dest")] + \
+               [(k, C.POINTER(C.c_int32)) for k in ("udiag_slot", "slot_src", "slot_row", "rowent", "level_ptr", "level_cols",
+                                                    "upd_uslot", "upd_lslot", "upd_cnt", "dest", "lslot0", "fslot0")]

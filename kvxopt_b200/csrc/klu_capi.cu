@@ -1,0 +1,222 @@
+// extern "C" boundary, KLU half (include/b200sparse.h).
+#include "../../include/b200sparse.h"
+#include "gpu.hpp"
+#include "klu_host.hpp"
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <vector>
+
+using namespace b200s;
+
+namespace b200s {
+class KluDevice;
+KluDevice* klu_device_create(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S, int device, int* status);
+void klu_device_destroy(KluDevice* d);
+int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status);
+int klu_device_solve(KluDevice* d, int trans, double* B, long long nrhs, long long ldB, long long batch, bool on_device);
+int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs_host);
+void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve);
+}  // namespace b200s
+
+struct b200s_klu_sym {
+    KluSymbolic S;
+};
+struct b200s_klu_num {
+    const b200s_klu_sym* sym = nullptr;
+    KluSymbolic S;         // copy: the numeric object must outlive nothing but itself
+    KluNumeric N;
+    KluPlan P;
+    KluDevice* dev = nullptr;
+    int device = 0;
+};
+
+extern "C" {
+
+b200s_status b200s_klu_analyze(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, b200s_klu_sym** out) {
+    if (!out) return B200S_INVALID;
+    *out = nullptr;
+    if (n < 0 || (n > 0 && (!colptr || (colptr[n] > 0 && !rowind)))) return B200S_INVALID;
+    b200s_klu_sym* S = new (std::nothrow) b200s_klu_sym();
+    if (!S) return B200S_OUT_OF_MEMORY;
+    try {
+        static const b200s_int zero = 0;
+        klu_analyze(n, n > 0 ? colptr : &zero, rowind, S->S);
+    } catch (const std::bad_alloc&) {
+        delete S; return B200S_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        set_last_error(e.what()); delete S; return B200S_INVALID;
+    }
+    *out = S;
+    return B200S_OK;
+}
+
+static b200s_status factor_impl(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                b200s_klu_num** out, bool with_device) {
+    if (!S || !out) return B200S_INVALID;
+    *out = nullptr;
+    const i32 n = S->S.n;
+    if (n > 0) {
+        if (!colptr || !val) return B200S_INVALID;
+        if (colptr[n] != S->S.nnz) { set_last_error("matrix pattern differs from the analysed pattern"); return B200S_INVALID; }
+        for (i32 j = 0; j <= n; j++) if (colptr[j] != S->S.Ap[j]) { set_last_error("matrix pattern differs from the analysed pattern"); return B200S_INVALID; }
+        for (i64 p = 0; p < S->S.nnz; p++) if (rowind[p] != S->S.Ai[p]) { set_last_error("matrix pattern differs from the analysed pattern"); return B200S_INVALID; }
+    }
+    b200s_klu_num* N = new (std::nothrow) b200s_klu_num();
+    if (!N) return B200S_OUT_OF_MEMORY;
+    N->S = S->S;
+    N->device = current_device();
+    try {
+        int st = klu_factor(N->S, val, N->N);
+        if (st != ST_OK) { delete N; return (b200s_status)st; }
+        klu_build_plan(N->S, N->N, N->P);
+    } catch (const std::bad_alloc&) {
+        delete N; return B200S_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        set_last_error(e.what()); delete N; return B200S_INVALID;
+    }
+    if (n > 0 && with_device) {
+        // the numeric values used by solve/extract come from the device refactorization (batch of one)
+        int st = ST_OK;
+        N->dev = klu_device_create(N->P, N->N, N->S, N->device, &st);
+        if (!N->dev) { delete N; return (b200s_status)st; }
+        int mst = 0;
+        st = klu_device_refactor(N->dev, val, false, 1, S->S.nnz, &mst);
+        if (st == ST_OK && mst != 0) st = mst;
+        if (st != ST_OK) { klu_device_destroy(N->dev); delete N; return (b200s_status)st; }
+    }
+    *out = N;
+    return B200S_OK;
+}
+
+b200s_status b200s_klu_factor(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                              b200s_klu_num** out) {
+    return factor_impl(S, colptr, rowind, val, out, true);
+}
+b200s_status b200s_klu_pivot_host(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                  b200s_klu_num** out) {
+    return factor_impl(S, colptr, rowind, val, out, false);
+}
+b200s_status b200s_klu_extract_host(const b200s_klu_num* N, double* Lx, double* Ux, double* Fx, double* Rs) {
+    if (!N) return B200S_INVALID;
+    if (Lx) for (size_t p = 0; p < N->N.Lx.size(); p++) Lx[p] = N->N.Lx[p];
+    if (Ux) for (size_t p = 0; p < N->N.Ux.size(); p++) Ux[p] = N->N.Ux[p];
+    if (Fx) for (size_t p = 0; p < N->N.Fx.size(); p++) Fx[p] = N->N.Fx[p];
+    if (Rs) for (size_t p = 0; p < N->N.Rs.size(); p++) Rs[p] = N->N.Rs[p];
+    return B200S_OK;
+}
+
+static b200s_status refactor_impl(b200s_klu_num* N, const double* vals, bool on_device, b200s_int batch, b200s_int ldv,
+                                  int* status_per_matrix) {
+    if (!N || batch < 0) return B200S_INVALID;
+    if (N->N.n == 0 || batch == 0) return B200S_OK;
+    if (!vals || ldv < N->S.nnz || batch > 0x7fffff00) return B200S_INVALID;
+    if (!N->dev) return B200S_NO_DEVICE;
+    return (b200s_status)klu_device_refactor(N->dev, vals, on_device, batch, ldv, status_per_matrix);
+}
+b200s_status b200s_klu_refactor_batch(b200s_klu_num* N, const double* vals, b200s_int batch, b200s_int ldv, int* status_per_matrix) {
+    return refactor_impl(N, vals, false, batch, ldv, status_per_matrix);
+}
+b200s_status b200s_klu_refactor_batch_dev(b200s_klu_num* N, const double* vals_dev, b200s_int batch, b200s_int ldv, int* status_per_matrix) {
+    return refactor_impl(N, vals_dev, true, batch, ldv, status_per_matrix);
+}
+
+static b200s_status solve_impl(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB, b200s_int batch, bool on_device) {
+    if (!N || nrhs < 0 || batch < 0 || (trans != 0 && trans != 1)) return B200S_INVALID;
+    if (N->N.n == 0 || nrhs == 0 || batch == 0) return B200S_OK;
+    if (!B || ldB < N->N.n) return B200S_INVALID;
+    if (!N->dev) return B200S_NO_DEVICE;
+    return (b200s_status)klu_device_solve(N->dev, trans, B, nrhs, ldB, batch, on_device);
+}
+b200s_status b200s_klu_solve_batch(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB, b200s_int batch) {
+    return solve_impl(N, trans, B, nrhs, ldB, batch, false);
+}
+b200s_status b200s_klu_solve_batch_dev(b200s_klu_num* N, int trans, double* B_dev, b200s_int nrhs, b200s_int ldB, b200s_int batch) {
+    return solve_impl(N, trans, B_dev, nrhs, ldB, batch, true);
+}
+b200s_status b200s_klu_solve(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB) {
+    return solve_impl(N, trans, B, nrhs, ldB, 1, false);
+}
+
+b200s_status b200s_klu_info(const b200s_klu_num* N, b200s_klu_info_t* info) {
+    if (!N || !info) return B200S_INVALID;
+    memset(info, 0, sizeof *info);
+    const i32 n = N->N.n;
+    info->n = n; info->nblocks = N->S.nblocks; info->nnz_A = N->S.nnz;
+    info->nnz_L = N->N.Lp[n]; info->nnz_U = N->N.Up[n]; info->nnz_F = N->N.Fp[n];
+    info->nlevels = N->P.nlevels; info->max_block = N->S.maxblock;
+    info->flops = N->N.flops;
+    info->bytes_per_refactor = 8 * (info->nnz_A + info->nnz_L + info->nnz_U + info->nnz_F + 2 * (i64)n);
+    if (N->dev) klu_device_times(N->dev, &info->ms_h2d, &info->ms_refactor, &info->ms_solve);
+    return B200S_OK;
+}
+
+static b200s_status extract_values(b200s_klu_num* N, b200s_int b, double* Lx, double* Ux, double* Fx, double* Rs) {
+    const i32 n = N->N.n;
+    if (n == 0) return B200S_OK;
+    if (!N->dev) return B200S_NO_DEVICE;
+    std::vector<double> slots((size_t)N->P.nslots);
+    std::vector<double> rs((size_t)n);
+    int st = klu_device_extract(N->dev, b, slots.data(), rs.data());
+    if (st != ST_OK) return (b200s_status)st;
+    for (i32 k = 0; k < n; k++) {
+        const i64 nu = N->N.Up[k + 1] - N->N.Up[k];
+        if (Ux) for (i64 p = 0; p < nu; p++) Ux[N->N.Up[k] + p] = slots[N->P.cbeg[k] + p];
+        if (Lx) {
+            Lx[N->N.Lp[k]] = 1.0;
+            for (i64 p = N->N.Lp[k] + 1; p < N->N.Lp[k + 1]; p++) Lx[p] = slots[N->P.lslot0[k] + (p - N->N.Lp[k] - 1)];
+        }
+        if (Fx) for (i64 p = N->N.Fp[k]; p < N->N.Fp[k + 1]; p++) Fx[p] = slots[N->P.fslot0[k] + (p - N->N.Fp[k])];
+    }
+    if (Rs) for (i32 k = 0; k < n; k++) Rs[k] = rs[k];
+    return B200S_OK;
+}
+
+b200s_status b200s_klu_extract(const b200s_klu_num* Nc, b200s_int* Lp, b200s_int* Li, double* Lx, b200s_int* Up, b200s_int* Ui,
+                               double* Ux, b200s_int* Fp, b200s_int* Fi, double* Fx, b200s_int* P, b200s_int* Q, double* Rs,
+                               b200s_int* R) {
+    if (!Nc) return B200S_INVALID;
+    b200s_klu_num* N = const_cast<b200s_klu_num*>(Nc);
+    const i32 n = N->N.n;
+    for (i32 k = 0; k <= n; k++) {
+        if (Lp) Lp[k] = N->N.Lp[k];
+        if (Up) Up[k] = N->N.Up[k];
+        if (Fp) Fp[k] = N->N.Fp[k];
+    }
+    if (Li) for (size_t p = 0; p < N->N.Li.size(); p++) Li[p] = N->N.Li[p];
+    if (Ui) for (size_t p = 0; p < N->N.Ui.size(); p++) Ui[p] = N->N.Ui[p];
+    if (Fi) for (size_t p = 0; p < N->N.Fi.size(); p++) Fi[p] = N->N.Fi[p];
+    for (i32 k = 0; k < n; k++) {
+        if (P) P[k] = N->N.Pnum[k];
+        if (Q) Q[k] = N->S.Q[k];
+    }
+    if (R) for (i32 b = 0; b <= N->S.nblocks; b++) R[b] = N->S.R[b];
+    if (Lx || Ux || Fx || Rs) return extract_values(N, 0, Lx, Ux, Fx, Rs);
+    return B200S_OK;
+}
+b200s_status b200s_klu_extract_batch(b200s_klu_num* N, b200s_int b, double* Lx, double* Ux, double* Fx, double* Rs) {
+    if (!N) return B200S_INVALID;
+    return extract_values(N, b, Lx, Ux, Fx, Rs);
+}
+
+b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* v) {
+    if (!N || !v) return B200S_INVALID;
+    const KluPlan& P = N->P;
+    v->n = P.n; v->nlevels = P.nlevels; v->nslots = P.nslots; v->lu_slots = P.lu_slots; v->nnz_A = P.nnzA;
+    v->nupd = (b200s_int)P.upd_uslot.size(); v->ndest = (b200s_int)P.dest.size();
+    v->cbeg = P.cbeg.data(); v->udiag_slot = P.udiag_slot.data(); v->slot_src = P.slot_src.data();
+    v->slot_row = P.slot_row.data(); v->rowptr = P.rowptr.data(); v->rowent = P.rowent.data();
+    v->level_ptr = P.level_ptr.data(); v->level_cols = P.level_cols.data(); v->upd_ptr = P.upd_ptr.data();
+    v->upd_uslot = P.upd_uslot.data(); v->upd_lslot = P.upd_lslot.data(); v->upd_cnt = P.upd_cnt.data();
+    v->upd_dest = P.upd_dest.data(); v->dest = P.dest.data(); v->lslot0 = P.lslot0.data(); v->fslot0 = P.fslot0.data();
+    return B200S_OK;
+}
+
+void b200s_klu_free_symbolic(b200s_klu_sym* S) { delete S; }
+void b200s_klu_free_numeric(b200s_klu_num* N) {
+    if (!N) return;
+    if (N->dev) klu_device_destroy(N->dev);
+    delete N;
+}
+
+}  // extern "C"

@@ -1,0 +1,407 @@
+// Batched KLU numeric refactorization and solves on B200 (sm_100a).
+// Replaces klu_l_factor on same-pattern inputs (reference src/C/klu.c:337, klu_refactor semantics) and
+// klu_l_solve / klu_l_tsolve (src/C/klu.c:651-657) for a batch of matrices that share one sparsity
+// pattern and one pivot sequence.
+//
+// Layout in HBM: every per-matrix quantity is batch-interleaved, value v of matrix b at [v*Bp + b]
+// (Bp = batch rounded up to 32), so that the 32 lanes of a warp -- 32 different matrices executing the
+// same static schedule -- read and write 256 contiguous bytes.  No divergence: the pattern, the pivot
+// order and therefore the instruction stream are identical for all matrices.
+//   Axt [nnzA ][Bp]  transposed copy of the caller's values
+//   Rs  [n    ][Bp]  row scale factors (max |row|), pivotal row order
+//   LU  [slots][Bp]  per column: U above the diagonal, U diagonal, L below the diagonal; then F
+// Kernels: k_klu_transpose (tiled), k_klu_rowscale, k_klu_scatter, k_klu_refactor (one CTA per group of
+// 32 matrices walks the column level schedule, 16 warps share the columns of a level), k_klu_solve.
+#include "gpu.hpp"
+#include "klu_host.hpp"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+namespace b200s {
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,       \
+                     cudaGetErrorString(e__));                                                       \
+            set_last_error(buf__);                                                                   \
+            return e__ == cudaErrorMemoryAllocation ? ST_OOM : ST_CUDA;                              \
+        }                                                                                            \
+    } while (0)
+
+// in[b*ldv + k] -> out[k*Bp + b]
+__global__ void k_klu_transpose(const double* __restrict__ in, long long ldv, long long nnz, int batch, int Bp,
+                                double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const long long k0 = (long long)blockIdx.x * 32;
+    const int b0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int b = b0 + r;
+        const long long k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (b < batch && k < nnz) ? in[(long long)b * ldv + k] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const long long k = k0 + r;
+        const int b = b0 + threadIdx.x;
+        if (k < nnz) out[k * Bp + b] = tile[threadIdx.x][r];
+    }
+}
+
+// Rs[i][b] = max_k |A(i,k)| (1 when the row is empty or zero)
+__global__ void k_klu_rowscale(const long long* __restrict__ rowptr, const int* __restrict__ rowent, int n, int Bp,
+                               const double* __restrict__ Axt, double* __restrict__ Rs) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ngroups = Bp >> 5;
+    const long long total = (long long)n * ngroups;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp; w < total; w += nwarps) {
+        const int i = (int)(w / ngroups), g = (int)(w - (long long)i * ngroups);
+        const int b = g * 32 + lane;
+        double m = 0.0;
+        for (long long p = rowptr[i]; p < rowptr[i + 1]; p++) m = fmax(m, fabs(Axt[(long long)rowent[p] * Bp + b]));
+        Rs[(long long)i * Bp + b] = (m > 0.0) ? m : 1.0;
+    }
+}
+
+// LU[v][b] = A(src(v))[b] / Rs[row(v)][b], zero for fill-in slots
+__global__ void k_klu_scatter(const int* __restrict__ slot_src, const int* __restrict__ slot_row, long long nslots, int Bp,
+                              const double* __restrict__ Axt, const double* __restrict__ Rs, double* __restrict__ LU) {
+    const long long total = nslots * Bp;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long v = t / Bp;
+        const int b = (int)(t - v * Bp);
+        const int src = slot_src[v];
+        LU[t] = (src >= 0) ? Axt[(long long)src * Bp + b] / Rs[(long long)slot_row[v] * Bp + b] : 0.0;
+    }
+}
+
+struct KluPlanD {
+    int n, nlevels;
+    const int *level_ptr, *level_cols, *udiag_slot, *lslot0, *upd_uslot, *upd_lslot, *upd_cnt, *dest;
+    const long long *cbeg, *upd_ptr, *upd_dest;
+};
+
+// One CTA per group of 32 matrices.  Levels of the column dependency graph are separated by
+// __syncthreads(); inside a level each warp takes whole columns.
+constexpr int KLU_WARPS = 16;
+__global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, int Bp, double* __restrict__ LU,
+                                                                 int* __restrict__ status) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    double* lu = LU + b;
+    int bad = 0;
+    for (int l = 0; l < P.nlevels; l++) {
+        for (int c = P.level_ptr[l] + warp; c < P.level_ptr[l + 1]; c += KLU_WARPS) {
+            const int k = P.level_cols[c];
+            for (long long u = P.upd_ptr[k]; u < P.upd_ptr[k + 1]; u++) {
+                const double ujk = lu[(long long)P.upd_uslot[u] * Bp];
+                const int cnt = P.upd_cnt[u];
+                const double* lcol = lu + (long long)P.upd_lslot[u] * Bp;
+                const int* d = P.dest + P.upd_dest[u];
+                int t = 0;
+                for (; t + 4 <= cnt; t += 4) {
+                    const double l0 = lcol[(long long)t * Bp], l1 = lcol[(long long)(t + 1) * Bp];
+                    const double l2 = lcol[(long long)(t + 2) * Bp], l3 = lcol[(long long)(t + 3) * Bp];
+                    double* p0 = lu + (long long)d[t] * Bp; double* p1 = lu + (long long)d[t + 1] * Bp;
+                    double* p2 = lu + (long long)d[t + 2] * Bp; double* p3 = lu + (long long)d[t + 3] * Bp;
+                    const double x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+                    *p0 = x0 - l0 * ujk; *p1 = x1 - l1 * ujk; *p2 = x2 - l2 * ujk; *p3 = x3 - l3 * ujk;
+                }
+                for (; t < cnt; t++) {
+                    double* p0 = lu + (long long)d[t] * Bp;
+                    *p0 -= lcol[(long long)t * Bp] * ujk;
+                }
+            }
+            const double piv = lu[(long long)P.udiag_slot[k] * Bp];
+            if (!(fabs(piv) > 0.0)) bad = 1;            // zero or NaN pivot
+            const long long l0 = P.lslot0[k], l1 = P.cbeg[k + 1];
+            for (long long s = l0; s < l1; s++) lu[s * Bp] /= piv;
+        }
+        __syncthreads();
+    }
+    if (bad) status[b] = ST_SINGULAR;
+}
+
+struct KluSolveD {
+    int n, nblocks;
+    const long long *Lp, *Up, *Fp, *cbeg;
+    const int *Li, *Ui, *Fi, *lslot0, *fslot0, *Pnum, *Q, *R;
+};
+
+// One thread per (matrix, right-hand side).  X[n][Bp] work vectors (one set per right-hand side).
+// trans = 0:  x = Q (U+F)^-1 L^-1 Rs^-1 P b        trans = 1:  x = P' Rs^-1 L^-T (U+F)^-T Q' b
+__global__ void k_klu_solve(KluSolveD S, int trans, int batch, int Bp, const double* __restrict__ LU,
+                            const double* __restrict__ Rs, double* __restrict__ B, long long ldB, long long bstride,
+                            double* __restrict__ X) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int rhs = blockIdx.y;
+    double* bb = B + (long long)b * bstride + (long long)rhs * ldB;
+    double* x = X + (long long)rhs * S.n * Bp + b;
+    const double* lu = LU + b;
+    const int n = S.n;
+    if (!trans) {
+        // (L U + F) z = Rs^-1 P b by block back-substitution, last block first (klu_solve)
+        for (int k = 0; k < n; k++) x[(long long)k * Bp] = bb[S.Pnum[k]] / Rs[(long long)k * Bp + b];
+        for (int blk = S.nblocks - 1; blk >= 0; blk--) {
+            const int k0 = S.R[blk], k1 = S.R[blk + 1];
+            for (int k = k0; k < k1; k++) {                       // L_k y = b_k (unit diagonal)
+                const double xk = x[(long long)k * Bp];
+                const long long p0 = S.Lp[k] + 1, p1 = S.Lp[k + 1];
+                const long long s0 = S.lslot0[k];
+                for (long long p = p0; p < p1; p++) x[(long long)S.Li[p] * Bp] -= lu[(s0 + p - p0) * Bp] * xk;
+            }
+            for (int k = k1 - 1; k >= k0; k--) {                  // U_k z_k = y, then rows above: b -= F(:,k) z_k
+                const long long u0 = S.Up[k], u1 = S.Up[k + 1] - 1, s0 = S.cbeg[k];
+                const double xk = x[(long long)k * Bp] / lu[(s0 + (u1 - u0)) * Bp];
+                x[(long long)k * Bp] = xk;
+                for (long long p = u0; p < u1; p++) x[(long long)S.Ui[p] * Bp] -= lu[(s0 + p - u0) * Bp] * xk;
+                const long long f0 = S.Fp[k], f1 = S.Fp[k + 1], fs = S.fslot0[k];
+                for (long long p = f0; p < f1; p++) x[(long long)S.Fi[p] * Bp] -= lu[(fs + p - f0) * Bp] * xk;
+            }
+        }
+        for (int k = 0; k < n; k++) bb[S.Q[k]] = x[(long long)k * Bp];
+    } else {
+        // (L U + F)^T z = Q^T b by block forward substitution, first block first (klu_tsolve)
+        for (int k = 0; k < n; k++) x[(long long)k * Bp] = bb[S.Q[k]];
+        for (int blk = 0; blk < S.nblocks; blk++) {
+            const int k0 = S.R[blk], k1 = S.R[blk + 1];
+            for (int k = k0; k < k1; k++) {                       // b_k -= F(:,k)^T z_above ;  U_k^T y = b_k
+                const long long u0 = S.Up[k], u1 = S.Up[k + 1] - 1, s0 = S.cbeg[k];
+                double acc = x[(long long)k * Bp];
+                const long long f0 = S.Fp[k], f1 = S.Fp[k + 1], fs = S.fslot0[k];
+                for (long long p = f0; p < f1; p++) acc -= lu[(fs + p - f0) * Bp] * x[(long long)S.Fi[p] * Bp];
+                for (long long p = u0; p < u1; p++) acc -= lu[(s0 + p - u0) * Bp] * x[(long long)S.Ui[p] * Bp];
+                x[(long long)k * Bp] = acc / lu[(s0 + (u1 - u0)) * Bp];
+            }
+            for (int k = k1 - 1; k >= k0; k--) {                  // L_k^T z_k = y
+                const long long p0 = S.Lp[k] + 1, p1 = S.Lp[k + 1], s0 = S.lslot0[k];
+                double acc = x[(long long)k * Bp];
+                for (long long p = p0; p < p1; p++) acc -= lu[(s0 + p - p0) * Bp] * x[(long long)S.Li[p] * Bp];
+                x[(long long)k * Bp] = acc;
+            }
+        }
+        for (int k = 0; k < n; k++) bb[S.Pnum[k]] = x[(long long)k * Bp] / Rs[(long long)k * Bp + b];
+    }
+}
+
+__global__ void k_klu_gather_slots(const double* __restrict__ LU, int Bp, int b, long long nslots, double* __restrict__ out) {
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nslots; v += (long long)gridDim.x * blockDim.x)
+        out[v] = LU[v * Bp + b];
+}
+
+class KluDevice {
+public:
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {};
+    KluPlanD PD{};
+    KluSolveD SD{};
+    std::vector<void*> owned;
+    int *d_slot_src = nullptr, *d_slot_row = nullptr, *d_rowent = nullptr, *d_status = nullptr;
+    long long* d_rowptr = nullptr;
+    long long nslots = 0, nnzA = 0;
+    int n = 0;
+    // batch buffers
+    int Bp = 0, batch = 0;
+    double *dA = nullptr, *dAxt = nullptr, *dRs = nullptr, *dLU = nullptr, *dX = nullptr, *dB = nullptr;
+    long long capA = 0, capX = 0, capB = 0;
+    double ms_h2d = 0, ms_refactor = 0, ms_solve = 0;
+
+    ~KluDevice() {
+        cudaSetDevice(device);
+        for (void* p : owned) cudaFree(p);
+        cudaFree(dA); cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(dX); cudaFree(dB); cudaFree(d_status);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    template <class T> int up(const T** dst, const std::vector<T>& src) {
+        T* p = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&p, std::max<size_t>(src.size(), 1) * sizeof(T)));
+        owned.push_back(p);
+        if (!src.empty()) CUDA_TRY(cudaMemcpy(p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+        *dst = p;
+        return ST_OK;
+    }
+    int init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S);
+    int ensure_batch(int b);
+    int refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host);
+    int solve(int trans, double* B, long long nrhs, long long ldB, long long batch_, bool on_device);
+};
+
+int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    n = P.n; nslots = P.nslots; nnzA = P.nnzA;
+    int rc;
+    PD.n = P.n; PD.nlevels = P.nlevels;
+    std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
+        updd(P.upd_dest.begin(), P.upd_dest.end()), rowptr(P.rowptr.begin(), P.rowptr.end());
+    if ((rc = up(&PD.level_ptr, P.level_ptr))) return rc;
+    if ((rc = up(&PD.level_cols, P.level_cols))) return rc;
+    if ((rc = up(&PD.udiag_slot, P.udiag_slot))) return rc;
+    if ((rc = up(&PD.lslot0, P.lslot0))) return rc;
+    if ((rc = up(&PD.upd_uslot, P.upd_uslot))) return rc;
+    if ((rc = up(&PD.upd_lslot, P.upd_lslot))) return rc;
+    if ((rc = up(&PD.upd_cnt, P.upd_cnt))) return rc;
+    if ((rc = up(&PD.dest, P.dest))) return rc;
+    if ((rc = up(&PD.cbeg, cbeg))) return rc;
+    if ((rc = up(&PD.upd_ptr, updp))) return rc;
+    if ((rc = up(&PD.upd_dest, updd))) return rc;
+    const int* tmp_i; const long long* tmp_l;
+    if ((rc = up(&tmp_i, P.slot_src))) return rc; d_slot_src = (int*)tmp_i;
+    if ((rc = up(&tmp_i, P.slot_row))) return rc; d_slot_row = (int*)tmp_i;
+    if ((rc = up(&tmp_i, P.rowent))) return rc; d_rowent = (int*)tmp_i;
+    if ((rc = up(&tmp_l, rowptr))) return rc; d_rowptr = (long long*)tmp_l;
+    SD.n = P.n;
+    std::vector<long long> Lp(N.Lp.begin(), N.Lp.end()), Up(N.Up.begin(), N.Up.end()), Fp(N.Fp.begin(), N.Fp.end());
+    if ((rc = up(&SD.Lp, Lp))) return rc;
+    if ((rc = up(&SD.Up, Up))) return rc;
+    if ((rc = up(&SD.Fp, Fp))) return rc;
+    SD.cbeg = PD.cbeg;
+    if ((rc = up(&SD.Li, N.Li))) return rc;
+    if ((rc = up(&SD.Ui, N.Ui))) return rc;
+    if ((rc = up(&SD.Fi, N.Fi))) return rc;
+    SD.lslot0 = PD.lslot0;
+    if ((rc = up(&SD.fslot0, P.fslot0))) return rc;
+    if ((rc = up(&SD.Pnum, N.Pnum))) return rc;
+    if ((rc = up(&SD.Q, S.Q))) return rc;
+    if ((rc = up(&SD.R, S.R))) return rc;
+    SD.nblocks = S.nblocks;
+    return ST_OK;
+}
+
+int KluDevice::ensure_batch(int b) {
+    const int bp = (b + 31) & ~31;
+    if (bp <= Bp) { batch = b; return ST_OK; }
+    cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(d_status);
+    dAxt = dRs = dLU = nullptr; d_status = nullptr; Bp = 0;
+    CUDA_TRY(cudaMalloc((void**)&dAxt, std::max<long long>(nnzA, 1) * bp * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dRs, std::max<long long>(n, 1) * (long long)bp * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dLU, std::max<long long>(nslots, 1) * bp * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&d_status, bp * sizeof(int)));
+    Bp = bp; batch = b;
+    return ST_OK;
+}
+
+int KluDevice::refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (batch_ <= 0 || n == 0) return ST_OK;
+    int rc = ensure_batch((int)batch_);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev[0], stream));
+    const double* dv = vals;
+    if (!on_device) {
+        const long long need = (batch_ - 1) * ldv + nnzA;
+        if (need > capA) {
+            cudaFree(dA); dA = nullptr; capA = 0;
+            CUDA_TRY(cudaMalloc((void**)&dA, need * sizeof(double)));
+            capA = need;
+        }
+        CUDA_TRY(cudaMemcpyAsync(dA, vals, need * sizeof(double), cudaMemcpyHostToDevice, stream));
+        dv = dA;
+    }
+    CUDA_TRY(cudaEventRecord(ev[1], stream));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, Bp * sizeof(int), stream));
+    {
+        dim3 grid((unsigned)((nnzA + 31) / 32), (unsigned)(Bp / 32)), block(32, 8);
+        k_klu_transpose<<<grid, block, 0, stream>>>(dv, ldv, nnzA, batch, Bp, dAxt);
+    }
+    k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs);
+    k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, nslots, Bp, dAxt, dRs, dLU);
+    k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, Bp, dLU, d_status);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev[2], stream));
+    std::vector<int> st;
+    if (status_host) {
+        st.resize(Bp);
+        CUDA_TRY(cudaMemcpyAsync(st.data(), d_status, Bp * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (status_host) for (long long b = 0; b < batch_; b++) status_host[b] = st[b];
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_h2d = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_refactor = ms;
+    return ST_OK;
+}
+
+int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long long batch_, bool on_device) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (batch_ <= 0 || n == 0 || nrhs <= 0) return ST_OK;
+    if (batch_ > batch) { set_last_error("solve_batch: batch larger than the last refactored batch"); return ST_INVALID; }
+    const long long bstride = ldB * nrhs;
+    const long long needX = (long long)n * Bp * nrhs;
+    if (needX > capX) {
+        cudaFree(dX); dX = nullptr; capX = 0;
+        CUDA_TRY(cudaMalloc((void**)&dX, needX * sizeof(double)));
+        capX = needX;
+    }
+    CUDA_TRY(cudaEventRecord(ev[0], stream));
+    double* db = B;
+    const long long totalB = bstride * batch_;
+    if (!on_device) {
+        if (totalB > capB) {
+            cudaFree(dB); dB = nullptr; capB = 0;
+            CUDA_TRY(cudaMalloc((void**)&dB, totalB * sizeof(double)));
+            capB = totalB;
+        }
+        CUDA_TRY(cudaMemcpyAsync(dB, B, totalB * sizeof(double), cudaMemcpyHostToDevice, stream));
+        db = dB;
+    }
+    dim3 grid((unsigned)((batch_ + 63) / 64), (unsigned)nrhs);
+    k_klu_solve<<<grid, 64, 0, stream>>>(SD, trans, (int)batch_, Bp, dLU, dRs, db, ldB, bstride, dX);
+    CUDA_TRY(cudaGetLastError());
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(B, dB, totalB * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(ev[1], stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_solve = ms;
+    return ST_OK;
+}
+
+// ---- entry points used by klu_capi.cu ---------------------------------------------------------------
+KluDevice* klu_device_create(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S, int device, int* status) {
+    if (device_count() <= 0) { *status = ST_NO_DEVICE; set_last_error("no CUDA device available"); return nullptr; }
+    KluDevice* d = new KluDevice();
+    d->device = device;
+    *status = d->init(P, N, S);
+    if (*status != ST_OK) { delete d; return nullptr; }
+    return d;
+}
+void klu_device_destroy(KluDevice* d) { delete d; }
+int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status) {
+    return d->refactor(vals, on_device, batch, ldv, status);
+}
+int klu_device_solve(KluDevice* d, int trans, double* B, long long nrhs, long long ldB, long long batch, bool on_device) {
+    return d->solve(trans, B, nrhs, ldB, batch, on_device);
+}
+int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs_host) {
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (b < 0 || b >= d->batch) { set_last_error("extract_batch: matrix index out of range"); return ST_INVALID; }
+    double* tmp = nullptr;
+    const long long cnt = std::max<long long>(d->nslots, d->n);
+    CUDA_TRY(cudaMalloc((void**)&tmp, std::max<long long>(cnt, 1) * sizeof(double)));
+    k_klu_gather_slots<<<148 * 4, 256, 0, d->stream>>>(d->dLU, d->Bp, (int)b, d->nslots, tmp);
+    cudaError_t e = cudaMemcpyAsync(slots_host, tmp, d->nslots * sizeof(double), cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e == cudaSuccess && rs_host) {
+        k_klu_gather_slots<<<148, 256, 0, d->stream>>>(d->dRs, d->Bp, (int)b, d->n, tmp);
+        e = cudaMemcpyAsync(rs_host, tmp, d->n * sizeof(double), cudaMemcpyDeviceToHost, d->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    }
+    cudaFree(tmp);
+    CUDA_TRY(e);
+    return ST_OK;
+}
+void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve) {
+    *h2d = d->ms_h2d; *refactor = d->ms_refactor; *solve = d->ms_solve;
+}
+
+}  // namespace b200s

@@ -1,0 +1,413 @@
+// KLU replacement, host part (reference call sites: src/C/klu.c:136,264 klu_l_analyze; :142,337
+// klu_l_factor).  SuiteSparse KLU is not in the reference tree; the published algorithm is restated
+// (Davis & Palamadai Natarajan, "Algorithm 907: KLU", ACM TOMS 2010): permutation to block upper
+// triangular form (maximum transversal + strongly connected components), AMD on A+A' inside every
+// block, then per block a left-looking Gilbert-Peierls LU with threshold partial pivoting that
+// prefers the diagonal (tol = 1e-3) on the row-scaled matrix (scale = 2: max |row|).
+// The pivoting factorization runs here once per pattern; its pattern and pivot sequence are frozen
+// into a KluPlan that the batched CUDA refactorization (klu_gpu.cu) replays for every matrix.
+#include "klu_host.hpp"
+#include "gpu.hpp"
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+
+namespace b200s {
+
+namespace {
+
+// maximum transversal: match[i] = column matched to row i (or -1)
+std::vector<i32> max_transversal(i32 n, const i64* Ap, const i32* Ai, i32& nmatch) {
+    std::vector<i32> match(n, -1), cheap(n), visited(n, -1), jstack, pstack_col;
+    std::vector<i64> pos(n);
+    for (i32 j = 0; j < n; j++) cheap[j] = 0;
+    nmatch = 0;
+    std::vector<i32> colstack(n), rowstack(n);
+    std::vector<i64> posstack(n);
+    for (i32 j0 = 0; j0 < n; j0++) {
+        // iterative DFS for an augmenting path starting at column j0
+        i32 head = 0;
+        colstack[0] = j0;
+        posstack[0] = -1;          // -1: cheap phase not done yet
+        bool found = false;
+        while (head >= 0) {
+            const i32 j = colstack[head];
+            if (posstack[head] == -1) {
+                // cheap assignment: first unmatched row of column j
+                bool got = false;
+                for (i64& p = pos[j] = Ap[j] + cheap[j]; p < Ap[j + 1]; p++) {
+                    i32 i = Ai[p];
+                    if (match[i] == -1) { cheap[j] = (i32)(p - Ap[j]) + 1; rowstack[head] = i; got = true; break; }
+                }
+                if (got) { found = true; break; }
+                cheap[j] = (i32)(Ap[j + 1] - Ap[j]);
+                visited[j] = j0;
+                posstack[head] = Ap[j];
+            }
+            bool descended = false;
+            for (i64 p = posstack[head]; p < Ap[j + 1]; p++) {
+                i32 i = Ai[p];
+                i32 jn = match[i];
+                if (jn >= 0 && visited[jn] != j0) {
+                    posstack[head] = p + 1;
+                    rowstack[head] = i;
+                    head++;
+                    colstack[head] = jn;
+                    posstack[head] = -1;
+                    descended = true;
+                    break;
+                }
+            }
+            if (!descended) head--;
+        }
+        if (found) {
+            for (i32 h = head; h >= 0; h--) match[rowstack[h]] = colstack[h];
+            nmatch++;
+        }
+    }
+    return match;
+}
+
+}  // namespace
+
+void klu_analyze(i64 n64, const i64* Ap, const i64* Ai64, KluSymbolic& S) {
+    if (n64 < 0 || n64 > 0x7fffffff - 16) throw std::invalid_argument("matrix order out of range");
+    const i32 n = (i32)n64;
+    S = KluSymbolic();
+    S.n = n;
+    if (n == 0) { S.R.assign(1, 0); S.Ap.assign(1, 0); return; }
+    if (Ap[0] != 0) throw std::invalid_argument("colptr[0] must be 0");
+    for (i32 j = 0; j < n; j++) {
+        if (Ap[j + 1] < Ap[j]) throw std::invalid_argument("colptr must be nondecreasing");
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
+            if (Ai64[p] < 0 || Ai64[p] >= n) throw std::invalid_argument("row index out of range");
+            if (p > Ap[j] && Ai64[p] <= Ai64[p - 1]) throw std::invalid_argument("row indices must be strictly increasing within a column");
+        }
+    }
+    S.nnz = Ap[n];
+    if (S.nnz > 0x7fffffff - 16) throw std::invalid_argument("too many entries");
+    S.Ap.assign(Ap, Ap + n + 1);
+    S.Ai.resize(S.nnz);
+    for (i64 p = 0; p < S.nnz; p++) S.Ai[p] = (i32)Ai64[p];
+    const i32* Ai = S.Ai.data();
+
+    i32 nmatch = 0;
+    std::vector<i32> match = max_transversal(n, Ap, Ai, nmatch);
+    S.structural_rank = nmatch;
+    if (nmatch < n) {
+        // structurally singular: complete the matching arbitrarily so that the permutations stay valid;
+        // the numeric factorization will report the zero pivot.
+        std::vector<char> used(n, 0);
+        for (i32 i = 0; i < n; i++) if (match[i] >= 0) used[match[i]] = 1;
+        i32 j = 0;
+        for (i32 i = 0; i < n; i++)
+            if (match[i] < 0) { while (used[j]) j++; match[i] = j; used[j] = 1; }
+    }
+    // C(:,i) = A(:,match[i]) has a zero-free diagonal.  Tarjan SCC on the graph i -> r for C(r,i) != 0.
+    std::vector<i32> index(n, -1), low(n), onstack(n, 0), stack, blockof(n, -1), order;
+    std::vector<i32> cs(n);
+    std::vector<i64> ps(n);
+    order.reserve(n);
+    std::vector<i32> bstart;
+    i32 counter = 0, nb = 0;
+    for (i32 root = 0; root < n; root++) {
+        if (index[root] != -1) continue;
+        i32 head = 0;
+        cs[0] = root; ps[0] = Ap[match[root]];
+        index[root] = low[root] = counter++;
+        stack.push_back(root); onstack[root] = 1;
+        while (head >= 0) {
+            const i32 v = cs[head];
+            const i32 col = match[v];
+            bool descended = false;
+            for (i64& p = ps[head]; p < Ap[col + 1]; p++) {
+                const i32 w = Ai[p];
+                if (index[w] == -1) {
+                    p++;
+                    head++;
+                    cs[head] = w; ps[head] = Ap[match[w]];
+                    index[w] = low[w] = counter++;
+                    stack.push_back(w); onstack[w] = 1;
+                    descended = true;
+                    break;
+                } else if (onstack[w]) low[v] = std::min(low[v], index[w]);
+            }
+            if (descended) continue;
+            if (low[v] == index[v]) {
+                bstart.push_back((i32)order.size());
+                while (true) {
+                    i32 w = stack.back(); stack.pop_back(); onstack[w] = 0;
+                    blockof[w] = nb;
+                    order.push_back(w);
+                    if (w == v) break;
+                }
+                nb++;
+            }
+            head--;
+            if (head >= 0) low[cs[head]] = std::min(low[cs[head]], low[v]);
+        }
+    }
+    bstart.push_back(n);
+    S.nblocks = nb;
+    S.R.assign(bstart.begin(), bstart.end());
+    // per-block AMD on B + B' (B = diagonal block of C), applied symmetrically
+    std::vector<i32> local(n, -1);
+    for (i32 b = 0; b < nb; b++) {
+        const i32 k0 = S.R[b], nk = S.R[b + 1] - k0;
+        S.maxblock = std::max(S.maxblock, nk);
+        if (nk <= 2) continue;
+        for (i32 t = 0; t < nk; t++) local[order[k0 + t]] = t;
+        SymPattern G;
+        G.n = nk;
+        std::vector<std::vector<i32>> adj(nk);
+        for (i32 t = 0; t < nk; t++) {
+            const i32 v = order[k0 + t], col = match[v];
+            for (i64 p = Ap[col]; p < Ap[col + 1]; p++) {
+                const i32 w = Ai[p];
+                if (w == v || blockof[w] != b) continue;
+                adj[t].push_back(local[w]);
+                adj[local[w]].push_back(t);
+            }
+        }
+        G.ptr.assign(nk + 1, 0);
+        for (i32 t = 0; t < nk; t++) {
+            std::sort(adj[t].begin(), adj[t].end());
+            adj[t].erase(std::unique(adj[t].begin(), adj[t].end()), adj[t].end());
+            G.ptr[t + 1] = G.ptr[t] + (i64)adj[t].size();
+        }
+        G.idx.reserve(G.ptr[nk]);
+        for (i32 t = 0; t < nk; t++) G.idx.insert(G.idx.end(), adj[t].begin(), adj[t].end());
+        std::vector<i32> pl = amd_order(G);
+        std::vector<i32> neworder(nk);
+        for (i32 t = 0; t < nk; t++) neworder[t] = order[k0 + pl[t]];
+        std::copy(neworder.begin(), neworder.end(), order.begin() + k0);
+    }
+    S.P = order;
+    S.Q.resize(n);
+    for (i32 k = 0; k < n; k++) S.Q[k] = match[order[k]];
+}
+
+int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
+    const i32 n = S.n;
+    N = KluNumeric();
+    N.n = n;
+    N.Lp.assign(n + 1, 0); N.Up.assign(n + 1, 0); N.Fp.assign(n + 1, 0);
+    N.Pnum.assign(n, -1); N.Rs.assign(n, 1.0);
+    if (n == 0) return ST_OK;
+    const i64* Ap = S.Ap.data();
+    const i32* Ai = S.Ai.data();
+    const double tol = 1e-3;
+    // row scaling by max |row| (scale = 2); a zero row is left unscaled and will produce a zero pivot
+    std::vector<double> rs(n, 0.0);
+    for (i32 j = 0; j < n; j++)
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) rs[Ai[p]] = std::max(rs[Ai[p]], std::fabs(Ax[p]));
+    for (i32 i = 0; i < n; i++) if (!(rs[i] > 0.0)) rs[i] = 1.0;
+    std::vector<i32> pinvP(n);                    // row (original) -> position after the symbolic permutation
+    for (i32 k = 0; k < n; k++) pinvP[S.P[k]] = k;
+    std::vector<i32> pivpos(n, -1);               // symbolic row position -> final pivotal position
+    std::vector<i32> rowat(n, -1);                // final pivotal position -> symbolic row position
+    std::vector<double> x(n, 0.0);
+    std::vector<i32> mark(n, -1), reach, dstack, lcol_of(n, -1);
+    std::vector<i64> pstack;
+    reach.reserve(n); dstack.reserve(n); pstack.reserve(n);
+    // L is built with symbolic row positions and remapped to pivotal positions at the end
+    std::vector<i32> Li_tmp; std::vector<double> Lx_tmp;
+    std::vector<i32> xi;
+    double fl = 0;
+    int status = ST_OK;
+    for (i32 b = 0; b < S.nblocks; b++) {
+        const i32 k0 = S.R[b], k1 = S.R[b + 1];
+        for (i32 k = k0; k < k1; k++) {
+            const i32 col = S.Q[k];
+            // scatter the scaled column: rows above the block go to F, rows inside the block into x
+            xi.clear();
+            reach.clear();
+            for (i64 p = Ap[col]; p < Ap[col + 1]; p++) {
+                const i32 r = pinvP[Ai[p]];
+                const double v = Ax[p] / rs[Ai[p]];
+                if (r < k0) { N.Fi.push_back(r); N.Fx.push_back(v); }        // r is remapped to pivotal later
+                else if (r >= k1) throw std::logic_error("klu: entry below the block diagonal");
+                else { x[r] = v; if (mark[r] != k) { mark[r] = k; xi.push_back(r); } }
+            }
+            // reach of the column pattern in the graph of L (DFS over already-pivotal rows)
+            for (size_t q = 0, q_end = xi.size(); q < q_end; q++) {
+                const i32 r0 = xi[q];
+                if (pivpos[r0] < 0 || lcol_of[r0] == k) continue;
+                dstack.clear(); pstack.clear();
+                dstack.push_back(r0); pstack.push_back(N.Lp[pivpos[r0]] + 1);
+                lcol_of[r0] = k;
+                while (!dstack.empty()) {
+                    const i32 r = dstack.back();
+                    const i32 jc = pivpos[r];
+                    bool desc = false;
+                    i64& pp = pstack.back();
+                    const i64 pend = (i64)Li_tmp.size() < N.Lp[jc + 1] ? (i64)Li_tmp.size() : N.Lp[jc + 1];
+                    for (; pp < pend; pp++) {
+                        const i32 rr = Li_tmp[pp];
+                        if (mark[rr] != k) { mark[rr] = k; xi.push_back(rr); x[rr] = 0.0; }
+                        if (pivpos[rr] >= 0 && lcol_of[rr] != k) {
+                            lcol_of[rr] = k;
+                            pp++;
+                            dstack.push_back(rr); pstack.push_back(N.Lp[pivpos[rr]] + 1);
+                            desc = true;
+                            break;
+                        }
+                    }
+                    if (!desc) { reach.push_back(r); dstack.pop_back(); pstack.pop_back(); }
+                }
+            }
+            // numeric sparse triangular solve in topological order (reverse of the DFS finish order)
+            for (i32 t = (i32)reach.size() - 1; t >= 0; t--) {
+                const i32 r = reach[t], jc = pivpos[r];
+                const double xj = x[r];
+                for (i64 pp = N.Lp[jc] + 1; pp < N.Lp[jc + 1]; pp++) x[Li_tmp[pp]] -= Lx_tmp[pp] * xj;
+                fl += 2.0 * (double)(N.Lp[jc + 1] - N.Lp[jc] - 1);
+            }
+            // pivot search among the non-pivotal rows; prefer the diagonal (symbolic row position k)
+            double amax = -1.0; i32 prow = -1;
+            for (i32 r : xi)
+                if (pivpos[r] < 0) { double a = std::fabs(x[r]); if (a > amax) { amax = a; prow = r; } }
+            if (pivpos[k] < 0 && mark[k] == k && std::fabs(x[k]) >= tol * amax && x[k] != 0.0) prow = k;
+            if (prow < 0 || !(amax > 0.0) || x[prow] == 0.0) {
+                // numerically (or structurally) singular column: KLU with halt_if_singular stops here
+                N.singular_col = k;
+                status = ST_SINGULAR;
+                for (i32 r : xi) x[r] = 0.0;
+                return status;
+            }
+            const double piv = x[prow];
+            pivpos[prow] = k;
+            rowat[k] = prow;
+            // U(:,k): pivotal rows (stored with pivotal positions), diagonal last
+            for (i32 r : xi)
+                if (pivpos[r] >= 0 && r != prow) { N.Ui.push_back(pivpos[r]); N.Ux.push_back(x[r]); }
+            N.Ui.push_back(k); N.Ux.push_back(piv);
+            N.Up[k + 1] = (i64)N.Ui.size();
+            // L(:,k): unit diagonal first, then non-pivotal rows divided by the pivot
+            Li_tmp.push_back(prow); Lx_tmp.push_back(1.0);
+            for (i32 r : xi)
+                if (pivpos[r] < 0) { Li_tmp.push_back(r); Lx_tmp.push_back(x[r] / piv); }
+            N.Lp[k + 1] = (i64)Li_tmp.size();
+            N.Fp[k + 1] = (i64)N.Fi.size();
+            for (i32 r : xi) x[r] = 0.0;
+        }
+    }
+    // remap rows to pivotal positions, sort columns by row
+    N.Li.resize(Li_tmp.size()); N.Lx = Lx_tmp;
+    for (size_t p = 0; p < Li_tmp.size(); p++) N.Li[p] = pivpos[Li_tmp[p]];
+    for (size_t p = 0; p < N.Fi.size(); p++) N.Fi[p] = pivpos[N.Fi[p]];
+    auto sort_cols = [&](std::vector<i64>& Cp, std::vector<i32>& Ci, std::vector<double>& Cx) {
+        std::vector<std::pair<i32, double>> tmp;
+        for (i32 k = 0; k < n; k++) {
+            tmp.clear();
+            for (i64 p = Cp[k]; p < Cp[k + 1]; p++) tmp.emplace_back(Ci[p], Cx[p]);
+            std::sort(tmp.begin(), tmp.end(), [](const std::pair<i32, double>& a, const std::pair<i32, double>& b) { return a.first < b.first; });
+            for (i64 p = Cp[k]; p < Cp[k + 1]; p++) { Ci[p] = tmp[p - Cp[k]].first; Cx[p] = tmp[p - Cp[k]].second; }
+        }
+    };
+    sort_cols(N.Lp, N.Li, N.Lx);
+    sort_cols(N.Up, N.Ui, N.Ux);
+    sort_cols(N.Fp, N.Fi, N.Fx);
+    for (i32 k = 0; k < n; k++) { N.Pnum[k] = S.P[rowat[k]]; N.Rs[k] = rs[N.Pnum[k]]; }
+    N.flops = fl;
+    return status;
+}
+
+void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
+    const i32 n = S.n;
+    P = KluPlan();
+    P.n = n;
+    P.nnzA = S.nnz;
+    P.cbeg.assign(n + 1, 0);
+    P.udiag_slot.assign(n, 0);
+    P.lslot0.assign(n, 0);
+    P.fslot0.assign(n, 0);
+    // slots: per column [U above diag..., U diag, L below diag...]
+    i64 s = 0;
+    std::vector<i64> uslot0(n);
+    for (i32 k = 0; k < n; k++) {
+        P.cbeg[k] = s;
+        uslot0[k] = s;
+        s += N.Up[k + 1] - N.Up[k];
+        P.udiag_slot[k] = (i32)(s - 1);
+        P.lslot0[k] = (i32)s;
+        s += N.Lp[k + 1] - N.Lp[k] - 1;
+    }
+    P.cbeg[n] = s;
+    P.lu_slots = s;
+    for (i32 k = 0; k < n; k++) { P.fslot0[k] = (i32)s; s += N.Fp[k + 1] - N.Fp[k]; }
+    P.nslots = s;
+    if (s > 0x7fffffff - 16) throw std::invalid_argument("klu plan too large");
+    P.slot_src.assign(s, -1);
+    P.slot_row.assign(s, 0);
+    // row position (pivotal) -> slot inside the current column
+    std::vector<i32> slot_of_row(n, -1), pinvnum(n);
+    for (i32 k = 0; k < n; k++) pinvnum[N.Pnum[k]] = k;
+    for (i32 k = 0; k < n; k++) {
+        for (i64 p = N.Up[k]; p < N.Up[k + 1]; p++) { i32 sl = (i32)(uslot0[k] + (p - N.Up[k])); P.slot_row[sl] = N.Ui[p]; slot_of_row[N.Ui[p]] = sl; }
+        for (i64 p = N.Lp[k] + 1; p < N.Lp[k + 1]; p++) { i32 sl = (i32)(P.lslot0[k] + (p - N.Lp[k] - 1)); P.slot_row[sl] = N.Li[p]; slot_of_row[N.Li[p]] = sl; }
+        // F slots are looked up separately (rows above the block)
+        const i32 col = S.Q[k];
+        for (i64 p = S.Ap[col]; p < S.Ap[col + 1]; p++) {
+            const i32 r = pinvnum[S.Ai[p]];
+            // F entry?
+            const i32* fb = N.Fi.data() + N.Fp[k];
+            const i32* fe = N.Fi.data() + N.Fp[k + 1];
+            const i32* it = std::lower_bound(fb, fe, r);
+            if (it != fe && *it == r) {
+                i32 sl = P.fslot0[k] + (i32)(it - fb);
+                P.slot_src[sl] = (i32)p; P.slot_row[sl] = r;
+            } else {
+                i32 sl = slot_of_row[r];
+                if (sl < P.cbeg[k] || sl >= P.cbeg[k + 1] || P.slot_row[sl] != r) throw std::logic_error("klu plan: entry outside the LU pattern");
+                P.slot_src[sl] = (i32)p;
+            }
+        }
+        // updates of column k: for each U entry (j,k), j < k ascending, L(:,j) below the diagonal
+        P.upd_ptr.push_back((i64)P.upd_uslot.size());
+        for (i64 p = N.Up[k]; p < N.Up[k + 1] - 1; p++) {
+            const i32 j = N.Ui[p];
+            const i64 cnt = N.Lp[j + 1] - N.Lp[j] - 1;
+            if (cnt == 0) continue;
+            P.upd_uslot.push_back((i32)(uslot0[k] + (p - N.Up[k])));
+            P.upd_lslot.push_back(P.lslot0[j]);
+            P.upd_cnt.push_back((i32)cnt);
+            P.upd_dest.push_back((i64)P.dest.size());
+            for (i64 q = N.Lp[j] + 1; q < N.Lp[j + 1]; q++) {
+                const i32 sl = slot_of_row[N.Li[q]];
+                if (sl < P.cbeg[k] || sl >= P.cbeg[k + 1] || P.slot_row[sl] != N.Li[q]) throw std::logic_error("klu plan: fill entry missing");
+                P.dest.push_back(sl);
+            }
+        }
+    }
+    P.upd_ptr.push_back((i64)P.upd_uslot.size());
+    // F entries' scaling rows were set above; entries of F with no source cannot exist
+    // row lists for the scaling pass
+    P.rowptr.assign(n + 1, 0);
+    for (i64 p = 0; p < S.nnz; p++) P.rowptr[pinvnum[S.Ai[p]] + 1]++;
+    for (i32 i = 0; i < n; i++) P.rowptr[i + 1] += P.rowptr[i];
+    P.rowent.resize(S.nnz);
+    {
+        std::vector<i64> pos(P.rowptr.begin(), P.rowptr.end() - 1);
+        for (i64 p = 0; p < S.nnz; p++) P.rowent[pos[pinvnum[S.Ai[p]]]++] = (i32)p;
+    }
+    // level schedule: column k depends on every column j with U(j,k) != 0
+    std::vector<i32> level(n, 0);
+    P.nlevels = 0;
+    for (i32 k = 0; k < n; k++) {
+        i32 lv = 0;
+        for (i64 p = N.Up[k]; p < N.Up[k + 1] - 1; p++) lv = std::max(lv, level[N.Ui[p]] + 1);
+        level[k] = lv;
+        P.nlevels = std::max(P.nlevels, lv + 1);
+    }
+    P.level_ptr.assign(P.nlevels + 1, 0);
+    for (i32 k = 0; k < n; k++) P.level_ptr[level[k] + 1]++;
+    for (i32 l = 0; l < P.nlevels; l++) P.level_ptr[l + 1] += P.level_ptr[l];
+    P.level_cols.resize(n);
+    {
+        std::vector<i32> pos(P.level_ptr.begin(), P.level_ptr.end() - 1);
+        for (i32 k = 0; k < n; k++) P.level_cols[pos[level[k]]++] = k;
+    }
+}
+
+}  // namespace b200s
