@@ -37,12 +37,17 @@ _py.PyCapsule_IsValid.restype = C.c_int
 _py.PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
 
 
+# Raw-address variants for use inside capsule destructors: the capsule is being deallocated there
+# (refcount 0), so it must not be wrapped in a py_object (that would resurrect and re-free it).
+_raw_GetPointer = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p)(("PyCapsule_GetPointer", _py))
+_raw_GetName = C.CFUNCTYPE(C.c_char_p, C.c_void_p)(("PyCapsule_GetName", _py))
+
+
 @C.CFUNCTYPE(None, C.c_void_p)
 def _capsule_destructor(capsule_addr):        # kvxopt_free_cholmod_factor, cholmod.c:210-214
     try:
-        cap = C.cast(capsule_addr, C.py_object).value
-        name = _py.PyCapsule_GetName(cap)
-        ptr = _py.PyCapsule_GetPointer(cap, name)
+        name = _raw_GetName(capsule_addr)
+        ptr = _raw_GetPointer(capsule_addr, name)
         if ptr:
             fn["b200s_chol_free"](ptr)
     except Exception:   # never raise from a destructor

@@ -70,6 +70,8 @@ class CholOracle:
 
     def solve(self, B, sys=0):
         X = np.array(B, dtype=np.float64, order="F", copy=True)
+        if self.n == 0 or X.size == 0:
+            return X
         X2 = X.reshape(self.n, -1, order="F")
         st = lib().oracle_chol_solve(self.h, sys, _p(X2, pd), X2.shape[1], max(self.n, 1))
         if st:
@@ -98,3 +100,75 @@ class CholOracle:
     @property
     def flops(self):
         return float(lib().oracle_chol_flops(self.h))
+
+
+def _klu_sigs():
+    L = lib()
+    if getattr(L, "_klu_ready", False):
+        return L
+    L.oracle_klu_factor.restype = C.c_void_p
+    L.oracle_klu_factor.argtypes = [i64, pi, pi, pd, pi, pi, C.c_double, pi]
+    L.oracle_klu_free.argtypes = [C.c_void_p]
+    L.oracle_klu_refactor.argtypes = [C.c_void_p, pi, pi, pd]
+    L.oracle_klu_solve.argtypes = [C.c_void_p, C.c_int, pd, i64, i64]
+    L.oracle_klu_det.restype = C.c_double
+    L.oracle_klu_det.argtypes = [C.c_void_p]
+    L.oracle_klu_nnz.restype = i64
+    L.oracle_klu_nnz.argtypes = [C.c_void_p, C.c_int]
+    L.oracle_klu_flops.restype = C.c_double
+    L.oracle_klu_flops.argtypes = [C.c_void_p]
+    L._klu_ready = True
+    return L
+
+
+class KluOracle:
+    """Gilbert-Peierls LU with KLU's scaling and pivot rule on a CCS matrix; optional row/column pre-ordering."""
+
+    def __init__(self, n, colptr, rowind, values, P0=None, Q=None, tol=1e-3):
+        L = _klu_sigs()
+        self.n = int(n)
+        self.colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        self.rowind = np.ascontiguousarray(rowind, dtype=np.int64)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        p0 = np.ascontiguousarray(P0, dtype=np.int64) if P0 is not None else None
+        q = np.ascontiguousarray(Q, dtype=np.int64) if Q is not None else None
+        sing = i64(-1)
+        self.h = L.oracle_klu_factor(self.n, _p(self.colptr, pi), _p(self.rowind, pi), _p(v, pd),
+                                     _p(p0, pi) if p0 is not None else None, _p(q, pi) if q is not None else None,
+                                     tol, C.byref(sing))
+        if not self.h:
+            raise ArithmeticError("singular matrix")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_klu_free(self.h)
+            self.h = None
+
+    def refactor(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        st = lib().oracle_klu_refactor(self.h, _p(self.colptr, pi), _p(self.rowind, pi), _p(v, pd))
+        if st:
+            raise ArithmeticError("singular matrix")
+
+    def solve(self, B, trans="N"):
+        X = np.array(B, dtype=np.float64, order="F", copy=True)
+        if self.n == 0 or X.size == 0:
+            return X
+        X2 = X.reshape(self.n, -1, order="F")
+        lib().oracle_klu_solve(self.h, 0 if trans == "N" else 1, _p(X2, pd), X2.shape[1], max(self.n, 1))
+        return X
+
+    def det(self):
+        return float(lib().oracle_klu_det(self.h))
+
+    @property
+    def nnz_L(self):
+        return int(lib().oracle_klu_nnz(self.h, 0))
+
+    @property
+    def nnz_U(self):
+        return int(lib().oracle_klu_nnz(self.h, 1))
+
+    @property
+    def flops(self):
+        return float(lib().oracle_klu_flops(self.h))

@@ -1,0 +1,278 @@
+"""Parity of the CUDA sparse Cholesky (through the kvxopt.cholmod-compatible API and the C ABI) against the
+CPU oracle, the reference's LAPACK golden vectors and the reference's documented known answers.
+Tolerances are BASELINE.json's: relative backward error <= 1e-12, solution relative difference <= 1e-10."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import GOLD, lap3d, load_matrix, lower_ccs, rand_spd, sym_from_lower
+
+pytestmark = pytest.mark.gpu
+
+BERR_TOL = 1e-12
+XREL_TOL = 1e-10
+
+
+def berr(A, X, B):
+    X = X.reshape(A.shape[0], -1); B = B.reshape(A.shape[0], -1)
+    return (np.linalg.norm(A @ X - B, axis=0) / (spla.norm(A, 1) * np.linalg.norm(X, axis=0) + np.linalg.norm(B, axis=0))).max()
+
+
+@pytest.fixture(scope="module")
+def cholmod():
+    from kvxopt_b200 import cholmod as m, _lib
+    assert _lib.device_count() > 0, "GPU tests need a CUDA device; there is no CPU fallback"
+    return m
+
+
+def test_doc_example_linsolve_numpy_types(cholmod):
+    # reference doc/source/spsolvers.rst:555-563
+    A = sp.csc_matrix(([10.0, 3, 5, -2, 5, 2], ([0, 2, 1, 3, 2, 3], [0, 0, 1, 1, 2, 3])), shape=(4, 4))
+    X = np.arange(8, dtype=float).reshape(4, 2, order="F")
+    cholmod.linsolve(A, X)
+    ref = np.array([[-0.146341463414634, 0.048780487804878], [1.333333333333333, 4.0],
+                    [0.487804878048781, 1.170731707317073], [2.833333333333333, 7.5]])
+    np.testing.assert_allclose(X, ref, rtol=1e-13)
+
+
+def test_doc_examples_with_reference_types(cholmod, kvx):
+    """the reference's own documentation examples, typed exactly as in the docs (kvxopt matrix/spmatrix)"""
+    from kvxopt import matrix, spmatrix, cholmod as kc, log
+    assert kc is cholmod
+    A = spmatrix([10, 3, 5, -2, 5, 2], [0, 2, 1, 3, 2, 3], [0, 0, 1, 1, 2, 3])
+    X = matrix(range(8), (4, 2), "d")
+    kc.linsolve(A, X)
+    np.testing.assert_allclose(np.array(X), [[-0.146341463414634, 0.048780487804878], [1.333333333333333, 4.0],
+                                             [0.487804878048781, 1.170731707317073], [2.833333333333333, 7.5]], rtol=1e-13)
+    # spsolvers.rst:580-585: splinsolve with sparse identity gives the inverse
+    I4 = spmatrix(1.0, range(4), range(4))
+    Xs = kc.splinsolve(A, I4)
+    Ad = np.array(matrix(A)); Ad = np.tril(Ad) + np.tril(Ad, -1).T
+    np.testing.assert_allclose(np.array(matrix(Xs)), np.linalg.inv(Ad), rtol=1e-12, atol=1e-15)
+    # spsolvers.rst:759-772: log det through diag()
+    F = kc.symbolic(A)
+    kc.numeric(A, F)
+    assert abs(2.0 * sum(log(kc.diag(F))) - 5.505331535932363) < 1e-12
+    # spsolvers.rst: solve with the systems used by kkt_chol2 (misc.py:1531-1558): P, L, L', P'
+    b = matrix([1.0, 2.0, 3.0, 4.0])
+    x = +b
+    for s in (7, 4, 5, 8):
+        kc.solve(F, x, sys=s)
+    np.testing.assert_allclose(np.array(x).ravel(), np.linalg.solve(Ad, np.array(b).ravel()), rtol=1e-13)
+    Lf = kc.getfactor(F)
+    Ld = np.array(matrix(Lf))
+    p = cholmod.factor_perm(F)
+    np.testing.assert_allclose(Ld @ Ld.T, Ad[np.ix_(p, p)], rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["bcsstk13", "bcsstk24"])
+def test_reference_matrices_vs_reference_lapack_and_oracle(cholmod, name):
+    """BASELINE config 1: cholmod.linsolve on tests/bcsstk24.mtx (lower triangle as stored), random RHS"""
+    from oracle import CholOracle
+    Al = load_matrix(name)
+    n = Al.shape[0]
+    A = sym_from_lower(Al)
+    B = np.random.default_rng(0).standard_normal((n, 3))
+    X = np.asfortranarray(B.copy())
+    cholmod.linsolve(Al, X)
+    assert berr(A, X, B) <= BERR_TOL
+    Xref = np.load(GOLD + "/posv_%s.npz" % name)["X"]            # reference lapack.posv
+    assert np.linalg.norm(X - Xref) / np.linalg.norm(Xref) <= XREL_TOL
+    F = cholmod.symbolic(Al)
+    cholmod.numeric(Al, F)
+    O = CholOracle(n, Al.indptr, Al.indices, "L", cholmod.factor_perm(F))   # same P A P' on the CPU
+    O.factorize(Al.data)
+    Xo = O.solve(B)
+    assert np.linalg.norm(X - Xo) / np.linalg.norm(Xo) <= XREL_TOL
+    d = cholmod.diag(F)
+    np.testing.assert_allclose(np.asarray(d).ravel(), O.diag(), rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,dens,seed", [(1, 1.0, 0), (2, 1.0, 1), (33, 0.2, 2), (129, 0.05, 3), (700, 0.01, 4), (1500, 0.004, 5)])
+def test_random_spd_all_systems_vs_oracle(cholmod, n, dens, seed):
+    from oracle import CholOracle
+    A = rand_spd(n, dens, seed)
+    Al = lower_ccs(A)
+    F = cholmod.symbolic(Al)
+    cholmod.numeric(Al, F)
+    p = cholmod.factor_perm(F)
+    O = CholOracle(n, Al.indptr, Al.indices, "L", p)
+    O.factorize(Al.data)
+    rng = np.random.default_rng(seed)
+    B = rng.standard_normal((n, 3))
+    for s in range(9):
+        X = np.asfortranarray(B.copy())
+        cholmod.solve(F, X, sys=s)
+        Xo = O.solve(B, s)
+        assert np.linalg.norm(X - Xo) <= XREL_TOL * max(np.linalg.norm(Xo), 1e-300), "sys=%d" % s
+    X = np.asfortranarray(B.copy()); cholmod.solve(F, X)
+    assert berr(A, X, B) <= BERR_TOL
+    Lg = cholmod.getfactor(F).toarray()
+    np.testing.assert_allclose(Lg, O.dense_L(), atol=1e-11 * np.abs(Lg).max())
+    # refactorization with new values on the same pattern (what the IPM does every iteration)
+    Al2 = Al.copy(); Al2.data = Al.data * (1 + 0.1 * rng.uniform(0, 1, Al.nnz)); Al2 = Al2 + sp.identity(n) * n
+    Al2 = lower_ccs(Al2)
+    assert np.array_equal(Al2.indices, Al.indices)
+    cholmod.numeric(Al2, F)
+    X = np.asfortranarray(B.copy()); cholmod.solve(F, X)
+    assert berr(sym_from_lower(Al2), X, B) <= BERR_TOL
+
+
+def test_upper_storage_user_perm_ldB_offset_nrhs(cholmod):
+    n = 200
+    A = rand_spd(n, 0.03, 11)
+    Au = sp.triu(A).tocsc(); Au.sort_indices()
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(n)
+    F = cholmod.symbolic(Au, p=perm, uplo="U")
+    cholmod.numeric(Au, F)
+    ldB, off = n + 7, 5
+    buf = rng.standard_normal(off + 3 * ldB)
+    keep = buf.copy()
+    cholmod.solve(F, buf, sys=0, nrhs=2, ldB=ldB, offsetB=off)
+    for j in range(2):
+        b = keep[off + j * ldB: off + j * ldB + n]
+        x = buf[off + j * ldB: off + j * ldB + n]
+        assert berr(A, x, b) <= BERR_TOL
+    # everything outside the two solved columns is untouched
+    mask = np.ones_like(buf, dtype=bool)
+    for j in range(2):
+        mask[off + j * ldB: off + j * ldB + n] = False
+    assert np.array_equal(buf[mask], keep[mask])
+    with pytest.raises(ValueError):
+        cholmod.solve(F, buf, ldB=n - 1, nrhs=1)
+    with pytest.raises(TypeError):
+        cholmod.solve(F, buf, nrhs=4, ldB=ldB, offsetB=off)
+    with pytest.raises(ValueError):
+        cholmod.solve(F, buf, sys=9)
+
+
+def test_not_positive_definite_reports_the_oracles_column(cholmod):
+    from oracle import CholOracle
+    n = 300
+    A = rand_spd(n, 0.02, 21).tolil()
+    A[150, 150] = -1.0
+    A = A.tocsc()
+    Al = lower_ccs(A)
+    F = cholmod.symbolic(Al)
+    with pytest.raises(ArithmeticError) as e:
+        cholmod.numeric(Al, F)
+    O = CholOracle(n, Al.indptr, Al.indices, "L", cholmod.factor_perm(F))
+    with pytest.raises(ArithmeticError) as eo:
+        O.factorize(Al.data)
+    assert e.value.args[0] == eo.value.args[0]
+    with pytest.raises(ArithmeticError):
+        cholmod.solve(F, np.ones((n, 1), order="F"))
+    with pytest.raises(ArithmeticError):
+        cholmod.linsolve(Al, np.ones((n, 1), order="F"))
+    # a later successful numeric() on the same factor object recovers (kkt_chol2's retry path, misc.py:1433-1447)
+    A2 = lower_ccs(rand_spd(n, 0.02, 21))
+    if np.array_equal(A2.indices, Al.indices):
+        cholmod.numeric(A2, F)
+        X = np.ones((n, 1), order="F"); cholmod.solve(F, X)
+        assert berr(sym_from_lower(A2), X, np.ones((n, 1))) <= BERR_TOL
+
+
+def test_error_contract(cholmod):
+    A = lower_ccs(rand_spd(20, 0.2, 3))
+    F = cholmod.symbolic(A)
+    with pytest.raises(ValueError, match="symbolic factor"):
+        cholmod.solve(F, np.ones((20, 1), order="F"))
+    with pytest.raises(TypeError):
+        cholmod.solve("not a capsule", np.ones((20, 1), order="F"))
+    with pytest.raises(TypeError):
+        cholmod.symbolic(sp.csc_matrix(np.ones((3, 4))))
+    with pytest.raises(TypeError):
+        cholmod.linsolve(A.astype(np.complex128), np.ones((20, 1), order="F"))
+    with pytest.raises(ValueError):
+        cholmod.symbolic(A, uplo="X")
+    cholmod.options["nope"] = 1
+    try:
+        with pytest.raises(ValueError, match="invalid value for CHOLMOD parameter"):
+            cholmod.symbolic(A)
+    finally:
+        del cholmod.options["nope"]
+    cholmod.options["supernodal"] = 0
+    try:
+        with pytest.raises(ValueError):
+            cholmod.symbolic(A)           # simplicial LDL' is refused, never emulated on the CPU
+    finally:
+        del cholmod.options["supernodal"]
+
+
+def test_zero_size_inputs(cholmod):
+    """0x0 A, n x 0 sparse RHS and 0 x 1 B occur in kkt_chol2 when there are no equality constraints"""
+    E = sp.csc_matrix((0, 0))
+    F = cholmod.symbolic(E)
+    cholmod.numeric(E, F)
+    cholmod.solve(F, np.zeros((0, 1), order="F"))
+    A = lower_ccs(rand_spd(10, 0.3, 1))
+    F = cholmod.symbolic(A); cholmod.numeric(A, F)
+    X = cholmod.spsolve(F, sp.csc_matrix((10, 0)), sys=7)
+    assert X.shape == (10, 0)
+    cholmod.linsolve(A, np.zeros((10, 0), order="F"))
+
+
+def test_spsolve_matches_dense(cholmod):
+    n = 120
+    A = rand_spd(n, 0.04, 8)
+    Al = lower_ccs(A)
+    F = cholmod.symbolic(Al); cholmod.numeric(Al, F)
+    Bs = sp.random(n, 6, density=0.05, random_state=np.random.default_rng(2), format="csc")
+    for s in (0, 4, 7):
+        Xs = cholmod.spsolve(F, Bs, sys=s)
+        Xd = np.asfortranarray(Bs.toarray()); cholmod.solve(F, Xd, sys=s)
+        np.testing.assert_allclose(Xs.toarray(), Xd, rtol=1e-13, atol=1e-300)
+    Xl = cholmod.splinsolve(Al, Bs)
+    np.testing.assert_allclose(A @ Xl.toarray(), Bs.toarray(), atol=1e-12)
+
+
+@pytest.mark.parametrize("dims,order", [((24, 24, 24), "nd"), ((40, 40, 40), "nd"), ((30, 30, 30), "amd"), ((300, 300, 1), "amd")])
+def test_laplacians_large_fronts(cholmod, dims, order):
+    """fronts wider than one 128-column block, many CTAs per panel launch (the shape of BASELINE config 4)"""
+    from kvxopt_b200 import _lib as L
+    nx, ny, nz = dims
+    A = lap3d(nx, ny, nz)
+    Al = lower_ccs(A)
+    n = A.shape[0]
+    perm = None
+    if order == "nd":
+        perm = np.zeros(n, np.int64)
+        assert L.fn["b200s_grid_nd_perm"](nx, ny, nz, 64, L.ptr_i64(perm)) == 0
+    F = cholmod.symbolic(Al, p=perm)
+    cholmod.numeric(Al, F)
+    B = np.random.default_rng(0).standard_normal((n, 2))
+    X = np.asfortranarray(B.copy())
+    cholmod.solve(F, X)
+    assert berr(A, X, B) <= BERR_TOL
+    # determinism: a second factorization + solve gives bit-identical results (no atomics in the extend-add)
+    cholmod.numeric(Al, F)
+    X2 = np.asfortranarray(B.copy()); cholmod.solve(F, X2)
+    assert np.array_equal(X, X2)
+    # size-independent property: linearity of the solve
+    Y = np.asfortranarray(2.5 * B[:, :1] - 0.5 * B[:, 1:2]); cholmod.solve(F, Y)
+    np.testing.assert_allclose(Y[:, 0], 2.5 * X[:, 0] - 0.5 * X[:, 1], rtol=1e-9, atol=1e-12 * np.abs(X).max())
+
+
+def test_device_resident_entry_points(cholmod):
+    """b200s_chol_factorize_dev / solve_dev (values and right-hand sides already in HBM) match the host-pointer calls"""
+    import torch
+    from kvxopt_b200 import _lib as L
+    A = lap3d(16, 16, 16); Al = lower_ccs(A); n = A.shape[0]
+    F = cholmod.symbolic(Al)
+    h, _ = cholmod._factor_handle(F)
+    vals = torch.from_numpy(Al.data.copy()).cuda()
+    minor = C.c_int64()
+    torch.cuda.synchronize()
+    assert L.fn["b200s_chol_factorize_dev"](h, vals.data_ptr(), C.byref(minor)) == 0
+    B = np.random.default_rng(0).standard_normal((n, 2))
+    Xd = torch.from_numpy(np.asfortranarray(B).T.copy()).cuda()       # (2, n) C-order == n x 2 column-major
+    torch.cuda.synchronize()
+    assert L.fn["b200s_chol_solve_dev"](h, 0, Xd.data_ptr(), 2, n) == 0
+    X = Xd.cpu().numpy().T
+    assert berr(A, X, B) <= BERR_TOL
+    Xh = np.asfortranarray(B.copy()); cholmod.solve(F, Xh)
+    assert np.array_equal(Xh, X)

@@ -1,0 +1,130 @@
+"""Parity of the CUDA KLU path against the reference's own test criteria (reference
+tests/test_sparse_solvers.py:216-323), its documented known answers, the CPU oracle and SuperLU."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import load_matrix
+
+pytestmark = pytest.mark.gpu
+MATRICES = ["ACTIVSg2000", "bcsstk13", "bcsstk24", "bp_800"]      # reference tests/test_sparse_solvers.py:29-30
+
+KLU_V = [2, 3, 3, -1, 4, 4, -3, 1, 2, 2, 6, 1]
+KLU_I = [0, 1, 0, 2, 4, 1, 2, 3, 4, 2, 1, 4]
+KLU_J = [0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 4, 4]
+
+
+@pytest.fixture(scope="module")
+def klu():
+    from kvxopt_b200 import klu as m, _lib
+    assert _lib.device_count() > 0, "GPU tests need a CUDA device; there is no CPU fallback"
+    return m
+
+
+@pytest.mark.parametrize("name", MATRICES)
+def test_lu_identity(klu, name):
+    """TestKLU.test_lu: || R P A Q - (L U + F) ||_1 == 0 to 7 places"""
+    A = load_matrix(name)
+    Fs = klu.symbolic(A)
+    Fn = klu.numeric(A, Fs)
+    Lm, Um, P, Q, R, Fm, r = klu.get_numeric(A, Fs, Fn)
+    err = abs(R @ P @ A @ Q - (Lm @ Um + Fm)).sum(axis=0).max()
+    assert round(err, 7) == 0
+    assert r[0] == 0 and r[-1] == A.shape[0]
+
+
+@pytest.mark.parametrize("name", MATRICES)
+@pytest.mark.parametrize("trans", ["N", "T"])
+def test_linsolve_and_solve(klu, name, trans):
+    """TestKLU.test_linsolve / test_solve: A x == b elementwise to 7 places, 3 random columns"""
+    A = load_matrix(name)
+    n = A.shape[0]
+    B = np.random.default_rng(0).standard_normal((n, 3))
+    M = A if trans == "N" else A.T
+    X = np.asfortranarray(B.copy())
+    assert klu.linsolve(A, X, trans=trans) is None
+    np.testing.assert_array_almost_equal(M @ X, B, decimal=7)
+    Fs = klu.symbolic(A); Fn = klu.numeric(A, Fs)
+    X2 = np.asfortranarray(B.copy())
+    klu.solve(A, Fs, Fn, X2, trans=trans)
+    assert np.array_equal(X, X2)
+    Xref = spla.splu(M.tocsc()).solve(B)
+    assert np.linalg.norm(X - Xref) / np.linalg.norm(Xref) < 1e-10
+
+
+def test_doc_known_answers_and_det(klu, kvx):
+    """reference doc/source/spsolvers.rst:333-345, 420-439 and tests/test_sparse_solvers.py:288-323, reference types"""
+    from kvxopt import matrix, spmatrix, klu as kk
+    assert kk is klu
+    A = spmatrix(KLU_V, KLU_I, KLU_J)
+    B = matrix(1.0, (5, 1))
+    kk.linsolve(A, B)
+    np.testing.assert_allclose(np.array(B).ravel(), [0.57894737, -0.05263158, 1.0, 1.97368421, -0.78947368], rtol=1e-7)
+    VB = [4, 3, 3, -1, 4, 4, -3, 1, 2, 2, 6, 2]
+    Bm = spmatrix(VB, KLU_I, KLU_J)
+    x = matrix(1.0, (5, 1))
+    Fa = kk.symbolic(A); FA = kk.numeric(A, Fa)
+    Fb = kk.symbolic(Bm); FB = kk.numeric(Bm, Fb)
+    kk.solve(A, Fa, FA, x)
+    kk.solve(Bm, Fb, FB, x)
+    kk.solve(A, Fa, FA, x, trans="T")
+    np.testing.assert_allclose(np.array(x).ravel(), [0.580654371385528, -0.236595065688228, 1.628000923361034,
+                                                     8.06557280782751, -0.13075278223259], rtol=1e-12)
+    assert abs(kk.get_det(A, Fa, FA) - 114.0) < 1e-9
+    Lm, Um, P, Q, R, Fm, r = kk.get_numeric(A, Fa, FA)
+    assert type(Lm).__name__ == "spmatrix" and isinstance(r, list)
+    assert max(abs(R * P * A * Q - (Lm * Um + Fm))) < 1e-12          # spsolvers.rst:462-484
+    assert kk.linsolve(spmatrix([], [], [], (0, 0)), matrix(0.0, (0, 1))) == 0      # klu.c:126
+
+
+def test_singular_and_type_errors(klu):
+    with pytest.raises(ArithmeticError, match="singular"):
+        klu.linsolve(sp.csc_matrix(np.array([[1.0, 2], [2, 4]])), np.ones((2, 1), order="F"))
+    with pytest.raises(TypeError):
+        klu.symbolic(sp.csc_matrix(np.ones((2, 3))))
+    A = load_matrix("bp_800")
+    Fs = klu.symbolic(A)
+    with pytest.raises(TypeError):
+        klu.solve(A, Fs, Fs, np.ones((822, 1), order="F"))
+    with pytest.raises(ValueError):
+        klu.linsolve(A, np.ones((822, 1), order="F"), trans="X")
+
+
+@pytest.mark.parametrize("name,batch", [("bp_800", 70), ("ACTIVSg2000", 96)])
+def test_batched_refactor_vs_oracle(klu, name, batch):
+    """BASELINE config 2 at test size: same-pattern value perturbations a_k (1 + 1e-3 u_k); every matrix of the
+    batch is compared with the CPU oracle's refactorization (same pivot order) and with SuperLU"""
+    from oracle import KluOracle
+    A = load_matrix(name)
+    n = A.shape[0]
+    Fs = klu.symbolic(A); Fn = klu.numeric(A, Fs)
+    rng = np.random.default_rng(0)
+    vals = A.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(batch, A.nnz)))
+    status = klu.refactor_batch(Fn, vals)
+    assert not status.any()
+    B = rng.standard_normal((batch, 2, n))
+    X = B.copy()
+    klu.solve_batch(Fn, X)
+    Lm, Um, P, Q, R, Fm, r = klu.get_numeric(A, Fs, Fn)
+    Pnum = np.asarray(P.tocsc().indices)                  # P[i, Pnum[i]] = 1 -> column of the single entry in row i
+    Pnum = np.asarray(P.tocsr().indices)
+    Qv = np.asarray(Q.tocsc().indices)
+    O = KluOracle(n, A.indptr, A.indices, A.data, P0=Pnum, Q=Qv)
+    for b in list(range(0, batch, max(1, batch // 6))) + [batch - 1]:
+        Ab = sp.csc_matrix((vals[b], A.indices, A.indptr), shape=(n, n))
+        O.refactor(vals[b])
+        Xo = O.solve(B[b].T)
+        assert np.linalg.norm(X[b].T - Xo) / np.linalg.norm(Xo) < 1e-10
+        assert np.abs(Ab @ X[b].T - B[b].T).max() < 1e-7
+    XT = B.copy()
+    klu.solve_batch(Fn, XT, trans="T")
+    b = batch // 2
+    Ab = sp.csc_matrix((vals[b], A.indices, A.indptr), shape=(n, n))
+    assert np.abs(Ab.T @ XT[b].T - B[b].T).max() < 1e-7
+    # a matrix with a zeroed pivot column is flagged, the others are unaffected
+    vals2 = vals.copy(); vals2[3, :] = 0.0
+    st = klu.refactor_batch(Fn, vals2, check=False)
+    assert st[3] != 0 and st[:3].sum() == 0 and st[4:].sum() == 0
+    with pytest.raises(ArithmeticError):
+        klu.refactor_batch(Fn, vals2)

@@ -1,0 +1,251 @@
+"""Host (CPU, integer) logic of the engine through the C ABI: orderings, supernode plan, KLU pivot search
+and the static refactorization plan.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import lap3d, load_matrix, lower_ccs, rand_spd
+from kvxopt_b200 import _lib as L
+from oracle import CholOracle
+
+fn = L.fn
+
+
+def analyze(A, perm=None, uplo="L", opts=None):
+    cp, ri = A.indptr.astype(np.int64), A.indices.astype(np.int64)
+    F = L.vp()
+    p = np.ascontiguousarray(perm, dtype=np.int64) if perm is not None else None
+    st = fn["b200s_chol_analyze"](A.shape[0], L.ptr_i64(cp), L.ptr_i64(ri), uplo.encode(), L.ptr_i64(p),
+                                  C.byref(opts) if opts is not None else None, C.byref(F))
+    return st, F
+
+
+def plan_of(F):
+    inf = L.CholInfo(); fn["b200s_chol_info"](F, C.byref(inf))
+    n, ns = inf.n, inf.nsuper
+    perm = np.zeros(n, np.int64); fn["b200s_chol_get_perm"](F, L.ptr_i64(perm))
+    sup = np.zeros(ns + 1, np.int64); rp = np.zeros(ns + 1, np.int64)
+    fn["b200s_chol_get_super"](F, L.ptr_i64(sup), L.ptr_i64(rp), None)
+    rows = np.zeros(max(int(rp[-1]), 1), np.int64)
+    fn["b200s_chol_get_super"](F, L.ptr_i64(sup), L.ptr_i64(rp), L.ptr_i64(rows))
+    return inf, perm, sup, rp, rows
+
+
+@pytest.mark.parametrize("n,dens,seed", [(1, 1.0, 0), (9, 0.4, 1), (80, 0.06, 2), (500, 0.01, 3)])
+def test_supernode_structure_covers_exact_fill(n, dens, seed):
+    A = rand_spd(n, dens, seed)
+    Al = lower_ccs(A)
+    st, F = analyze(Al)
+    assert st == 0
+    inf, perm, sup, rp, rows = plan_of(F)
+    assert sorted(perm) == list(range(n))
+    # exact fill pattern from a dense Cholesky of the permuted matrix
+    Ad = A.toarray()[np.ix_(perm, perm)] + n * np.eye(n)
+    Lc = np.linalg.cholesky(Ad)
+    covered = np.zeros((n, n), dtype=bool)
+    for s in range(inf.nsuper):
+        c0, c1 = sup[s], sup[s + 1]
+        r = rows[rp[s]:rp[s + 1]]
+        assert list(r[:c1 - c0]) == list(range(c0, c1))
+        assert np.all(np.diff(r) > 0)
+        for j in range(c0, c1):
+            covered[r[r >= j], j] = True
+    assert np.all(covered[np.abs(Lc) > 1e-14])
+    assert inf.nnz_L == covered.sum()
+    # the independent oracle symbolic with the same permutation predicts the same exact fill count or less
+    O = CholOracle(n, Al.indptr, Al.indices, "L", perm)
+    assert O.nnzL <= inf.nnz_L
+    fn["b200s_chol_free"](F)
+
+
+def test_no_relaxation_gives_exact_fill():
+    A = lap3d(8, 8, 4)
+    Al = lower_ccs(A)
+    o = L.CholOpts(); fn["b200s_chol_default_opts"](C.byref(o))
+    for i in range(3):
+        o.nrelax[i] = 0; o.zrelax[i] = 0.0
+    st, F = analyze(Al, opts=o)
+    inf, perm, *_ = plan_of(F)
+    O = CholOracle(A.shape[0], Al.indptr, Al.indices, "L", perm)
+    # oracle counts exact fill; with relaxation off the plan may only add 'free' merges (no explicit zeros)
+    assert inf.nnz_L == O.nnzL
+    fn["b200s_chol_free"](F)
+
+
+def test_amd_reduces_fill_on_grid():
+    A = lap3d(30, 30, 1)
+    Al = lower_ccs(A)
+    st, F = analyze(Al)
+    inf_amd = plan_of(F)[0]
+    o = L.CholOpts(); fn["b200s_chol_default_opts"](C.byref(o)); o.ordering = 1
+    st, F2 = analyze(Al, opts=o)
+    inf_nat = plan_of(F2)[0]
+    assert inf_amd.nnz_L < 0.6 * inf_nat.nnz_L
+    assert inf_amd.flops < inf_nat.flops
+    fn["b200s_chol_free"](F); fn["b200s_chol_free"](F2)
+
+
+def test_grid_nd_and_user_perm():
+    nx, ny, nz = 12, 10, 7
+    p = np.zeros(nx * ny * nz, np.int64)
+    assert fn["b200s_grid_nd_perm"](nx, ny, nz, 16, L.ptr_i64(p)) == 0
+    assert sorted(p) == list(range(nx * ny * nz))
+    Al = lower_ccs(lap3d(nx, ny, nz))
+    st, F = analyze(Al, perm=p)
+    assert st == 0
+    inf, perm, *_ = plan_of(F)
+    assert sorted(perm) == list(range(nx * ny * nz))
+    assert inf.nlevels >= 3
+    fn["b200s_chol_free"](F)
+    bad = p.copy(); bad[0] = bad[1]
+    st, F = analyze(Al, perm=bad)
+    assert st == L.INVALID and "permutation" in L.last_error()
+
+
+def test_invalid_inputs():
+    A = lower_ccs(rand_spd(10, 0.3, 0))
+    st, _ = analyze(A, uplo="X")
+    assert st == L.INVALID
+    cp, ri = A.indptr.astype(np.int64), A.indices.astype(np.int64)
+    ri2 = ri.copy(); ri2[0] = 99
+    F = L.vp()
+    assert fn["b200s_chol_analyze"](10, L.ptr_i64(cp), L.ptr_i64(ri2), b"L", None, None, C.byref(F)) == L.INVALID
+    o = L.CholOpts(); fn["b200s_chol_default_opts"](C.byref(o)); o.supernodal = 0
+    st, _ = analyze(A, opts=o)
+    assert st == L.INVALID         # simplicial LDL^T mode is not implemented and is refused, not emulated
+
+
+def test_zero_size_and_upper():
+    E = sp.csc_matrix((0, 0))
+    st, F = analyze(E)
+    assert st == 0
+    assert fn["b200s_chol_factorize"](F, None, None) == 0          # n = 0 succeeds without a device
+    assert fn["b200s_chol_solve"](F, 0, None, 0, 1) == 0
+    fn["b200s_chol_free"](F)
+    A = rand_spd(40, 0.1, 4)
+    Au = sp.triu(A).tocsc(); Au.sort_indices()
+    stU, FU = analyze(Au, uplo="U")
+    stL, FL = analyze(lower_ccs(A))
+    assert stU == 0 and stL == 0
+    assert plan_of(FU)[0].nnz_L == plan_of(FL)[0].nnz_L
+    fn["b200s_chol_free"](FU); fn["b200s_chol_free"](FL)
+
+
+# ---- KLU host ----------------------------------------------------------------------------------------
+
+def klu_pivot(A):
+    A = A.tocsc(); A.sort_indices()
+    n = A.shape[0]
+    cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+    S = L.vp()
+    assert fn["b200s_klu_analyze"](n, L.ptr_i64(cp), L.ptr_i64(ri), C.byref(S)) == 0
+    N = L.vp()
+    st = fn["b200s_klu_pivot_host"](S, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(N))
+    return st, S, N, A
+
+
+def klu_pattern(N, n):
+    inf = L.KluInfo(); fn["b200s_klu_info"](N, C.byref(inf))
+    Lp = np.zeros(n + 1, np.int64); Up = np.zeros(n + 1, np.int64); Fp = np.zeros(n + 1, np.int64)
+    Li = np.zeros(max(inf.nnz_L, 1), np.int64); Ui = np.zeros(max(inf.nnz_U, 1), np.int64); Fi = np.zeros(max(inf.nnz_F, 1), np.int64)
+    P = np.zeros(max(n, 1), np.int64); Q = np.zeros(max(n, 1), np.int64); R = np.zeros(inf.nblocks + 1, np.int64)
+    assert fn["b200s_klu_extract"](N, L.ptr_i64(Lp), L.ptr_i64(Li), None, L.ptr_i64(Up), L.ptr_i64(Ui), None,
+                                   L.ptr_i64(Fp), L.ptr_i64(Fi), None, L.ptr_i64(P), L.ptr_i64(Q), None, L.ptr_i64(R)) == 0
+    return inf, Lp, Li[:inf.nnz_L], Up, Ui[:inf.nnz_U], Fp, Fi[:inf.nnz_F], P[:n], Q[:n], R
+
+
+def identity_error(A, vals, Rs, pat, Lx, Ux, Fx):
+    inf, Lp, Li, Up, Ui, Fp, Fi, P, Q, R = pat
+    n = A.shape[0]
+    Lm = sp.csc_matrix((Lx, Li, Lp), shape=(n, n)); Um = sp.csc_matrix((Ux, Ui, Up), shape=(n, n))
+    Fm = sp.csc_matrix((Fx, Fi, Fp), shape=(n, n))
+    A2 = sp.csc_matrix((vals, A.indices, A.indptr), shape=(n, n))
+    return abs(sp.diags(1.0 / Rs) @ A2[P, :][:, Q] - (Lm @ Um + Fm)).sum(axis=0).max()
+
+
+@pytest.mark.parametrize("name", ["bp_800", "bcsstk13", "bcsstk24", "ACTIVSg2000"])
+def test_klu_pivot_identity_on_reference_matrices(name):
+    """R P A Q = L U + F, the check of reference tests/test_sparse_solvers.py:216-237, on the pivot search"""
+    st, S, N, A = klu_pivot(load_matrix(name))
+    assert st == 0
+    n = A.shape[0]
+    pat = klu_pattern(N, n)
+    inf = pat[0]
+    Lx = np.zeros(max(inf.nnz_L, 1)); Ux = np.zeros(max(inf.nnz_U, 1)); Fx = np.zeros(max(inf.nnz_F, 1)); Rs = np.zeros(n)
+    fn["b200s_klu_extract_host"](N, L.ptr_f64(Lx), L.ptr_f64(Ux), L.ptr_f64(Fx), L.ptr_f64(Rs))
+    assert identity_error(A, A.data, Rs, pat, Lx[:inf.nnz_L], Ux[:inf.nnz_U], Fx[:inf.nnz_F]) < 1e-7
+    assert sorted(pat[7]) == list(range(n)) and sorted(pat[8]) == list(range(n))
+    if name == "ACTIVSg2000":
+        assert inf.nblocks == 1                     # irreducible
+    if name.startswith("bcsstk"):
+        assert inf.nblocks == n                     # stored lower triangle => n singleton blocks
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
+def emulate_plan(N, A, vals):
+    """replays the static refactorization plan with numpy exactly as the CUDA kernels do"""
+    n = A.shape[0]
+    v = L.KluPlanView(); assert fn["b200s_klu_plan_view"](N, C.byref(v)) == 0
+    arr = lambda p, m: np.ctypeslib.as_array(p, shape=(m,)).copy() if m > 0 else np.zeros(0, np.int64)
+    cbeg = arr(v.cbeg, n + 1); rowptr = arr(v.rowptr, n + 1); upd_ptr = arr(v.upd_ptr, n + 1); upd_dest = arr(v.upd_dest, v.nupd)
+    udiag = arr(v.udiag_slot, n); ssrc = arr(v.slot_src, v.nslots); srow = arr(v.slot_row, v.nslots); rowent = arr(v.rowent, v.nnz_A)
+    lp = arr(v.level_ptr, v.nlevels + 1); lc = arr(v.level_cols, n)
+    uus = arr(v.upd_uslot, v.nupd); uls = arr(v.upd_lslot, v.nupd); ucnt = arr(v.upd_cnt, v.nupd)
+    dest = arr(v.dest, v.ndest); lslot0 = arr(v.lslot0, n); fslot0 = arr(v.fslot0, n)
+    Rs = np.ones(n)
+    for i in range(n):
+        e = rowent[rowptr[i]:rowptr[i + 1]]
+        if len(e):
+            Rs[i] = np.abs(vals[e]).max()
+    LU = np.where(ssrc >= 0, vals[np.maximum(ssrc, 0)] / Rs[srow], 0.0)
+    done_level = np.full(n, -1)
+    for l in range(v.nlevels):
+        for k in lc[lp[l]:lp[l + 1]]:
+            for u in range(upd_ptr[k], upd_ptr[k + 1]):
+                for t in range(ucnt[u]):
+                    LU[dest[upd_dest[u] + t]] -= LU[uls[u] + t] * LU[uus[u]]
+            LU[lslot0[k]:cbeg[k + 1]] /= LU[udiag[k]]
+            done_level[k] = l
+    return LU, Rs, cbeg, lslot0, fslot0
+
+
+@pytest.mark.parametrize("case", ["rand60", "rand300", "bp_800"])
+def test_klu_static_plan_reproduces_factorization_of_perturbed_values(case):
+    if case.startswith("rand"):
+        n = int(case[4:])
+        rng = np.random.default_rng(n)
+        A = sp.random(n, n, density=3.0 / n, random_state=rng, format="csc") + sp.identity(n) * 0.5
+    else:
+        A = load_matrix(case)
+    st, S, N, A = klu_pivot(A)
+    assert st == 0
+    n = A.shape[0]
+    pat = klu_pattern(N, n)
+    inf, Lp, Li, Up, Ui, Fp, Fi, P, Q, R = pat
+    vals = A.data * (1 + 1e-3 * np.random.default_rng(7).uniform(-1, 1, A.nnz))
+    LU, Rs, cbeg, lslot0, fslot0 = emulate_plan(N, A, vals)
+    Lx = np.zeros(inf.nnz_L); Ux = np.zeros(inf.nnz_U); Fx = np.zeros(inf.nnz_F)
+    for k in range(n):
+        nu = Up[k + 1] - Up[k]
+        Ux[Up[k]:Up[k + 1]] = LU[cbeg[k]:cbeg[k] + nu]
+        Lx[Lp[k]] = 1.0
+        Lx[Lp[k] + 1:Lp[k + 1]] = LU[lslot0[k]:lslot0[k] + (Lp[k + 1] - Lp[k] - 1)]
+        Fx[Fp[k]:Fp[k + 1]] = LU[fslot0[k]:fslot0[k] + Fp[k + 1] - Fp[k]]
+    assert identity_error(A, vals, Rs, pat, Lx, Ux, Fx) < 1e-9
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
+def test_klu_structurally_and_numerically_singular():
+    st, S, N, _ = klu_pivot(sp.csc_matrix(np.array([[1.0, 2], [2, 4]])))
+    assert st == L.SINGULAR
+    st, S, N, _ = klu_pivot(sp.csc_matrix(np.array([[1.0, 0, 0], [0, 0, 0], [0, 3, 1]])))
+    assert st == L.SINGULAR
+
+
+def test_klu_zero_diagonal_is_permuted_away():
+    A = sp.csc_matrix(np.array([[0, 2.0, 0, 0], [3, 0, 0, 1], [0, 0, 0, 5], [1, 0, 4, 0]]))
+    st, S, N, A = klu_pivot(A)
+    assert st == 0
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
