@@ -110,6 +110,7 @@ typedef struct {
     double    ms_analyze;     /* host wall time of analyze                                          */
     double    ms_dense_update; /* device time inside the SYRK/GEMM update kernels of the last factorize */
     double    ms_potrf, ms_trsm, ms_extend;
+    double    flops_update;   /* flops executed by the tiled DMMA update kernel (numerator of its roofline) */
 } b200s_chol_info_t;
 b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info);
 /* when on, factorize records per-kernel-class CUDA events (adds launch gaps; for profiling only) */
@@ -179,6 +180,7 @@ typedef struct {
     double    flops;             /* multiply-adds x2 of one refactorization                        */
     b200s_int bytes_per_refactor;/* 8*(nnz_A + nnz_L + nnz_U + nnz_F + 2n): compulsory traffic      */
     double    ms_h2d, ms_refactor, ms_solve;  /* device-event times of the last batch call          */
+    double    ms_kernel;         /* of which: the refactorization kernel alone (k_klu_refactor)     */
 } b200s_klu_info_t;
 b200s_status b200s_klu_info(const b200s_klu_num* N, b200s_klu_info_t* info);
 

@@ -14,7 +14,7 @@ class CholInfo(C.Structure):
                [(k, C.c_double) for k in ("flops", "flops_potrf", "flops_trsm", "flops_syrk")] + \
                [("is_numeric", C.c_int), ("minor", i64)] + \
                [(k, C.c_double) for k in ("ms_h2d", "ms_assemble", "ms_factor", "ms_total", "ms_solve", "ms_analyze",
-                                          "ms_dense_update", "ms_potrf", "ms_trsm", "ms_extend")]
+                                          "ms_dense_update", "ms_potrf", "ms_trsm", "ms_extend", "flops_update")]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -23,7 +23,7 @@ class CholInfo(C.Structure):
 class KluInfo(C.Structure):
     _fields_ = [(k, i64) for k in ("n", "nblocks", "nnz_A", "nnz_L", "nnz_U", "nnz_F", "nlevels", "max_block")] + \
                [("flops", C.c_double), ("bytes_per_refactor", i64)] + \
-               [(k, C.c_double) for k in ("ms_h2d", "ms_refactor", "ms_solve")]
+               [(k, C.c_double) for k in ("ms_h2d", "ms_refactor", "ms_solve", "ms_kernel")]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

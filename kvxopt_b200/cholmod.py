@@ -49,6 +49,7 @@ def _capsule_destructor(capsule_addr):        # kvxopt_free_cholmod_factor, chol
         name = _raw_GetName(capsule_addr)
         ptr = _raw_GetPointer(capsule_addr, name)
         if ptr:
+            _FAMILY.pop(ptr, None)
             fn["b200s_chol_free"](ptr)
     except Exception:   # never raise from a destructor
         pass
@@ -150,15 +151,24 @@ def _dense_view(B):
         if not a.flags.f_contiguous:
             raise TypeError("B must be stored column-major (Fortran order)")
         flat = a.reshape(-1, order="F")
-    if not np.shares_memory(flat, a) or not flat.flags.writeable:
+    if a.size and (not np.shares_memory(flat, a) or not flat.flags.writeable):
         raise TypeError("B must be a writable column-major array")
     return flat, nrows, ncols
 
 
+def _kv_module(like):
+    """the kvxopt package `like` belongs to (an object of it, or its name), else None"""
+    import importlib
+    if isinstance(like, str):
+        return importlib.import_module(like)
+    if like is not None and _is_kvx(like):
+        return importlib.import_module(type(like).__module__.split(".")[0])
+    return None
+
+
 def _make_spmatrix(like, values, rowind, colptr, size):
-    if _is_kvx(like):
-        import importlib
-        kv = importlib.import_module(type(like).__module__.split(".")[0])
+    kv = _kv_module(like)
+    if kv is not None:
         cols = np.repeat(np.arange(size[1], dtype=np.int64), np.diff(colptr))
         return kv.spmatrix(kv.matrix(values, (len(values), 1), "d") if len(values) else [],
                            kv.matrix(rowind, (len(rowind), 1), "i") if len(rowind) else [],
@@ -168,9 +178,8 @@ def _make_spmatrix(like, values, rowind, colptr, size):
 
 
 def _make_matrix(like, values, size):
-    if _is_kvx(like):
-        import importlib
-        kv = importlib.import_module(type(like).__module__.split(".")[0])
+    kv = _kv_module(like)
+    if kv is not None:
         return kv.matrix(values, size, "d")
     return np.asarray(values, dtype=np.float64).reshape(size, order="F")
 
@@ -238,6 +247,7 @@ def symbolic(A, p=None, uplo="L"):
     """F = symbolic(A, p=None, uplo='L')  -- cholmod.c:244-291"""
     o = _set_options()
     h, _ = _analyze(A, p, uplo, o)
+    _FAMILY[h.value] = type(A).__module__.split(".")[0] if _is_kvx(A) else None   # family diag()/getfactor() return
     return _py.PyCapsule_New(h, _NAME_L if uplo == "L" else _NAME_U, C.cast(_capsule_destructor, C.c_void_p))
 
 
@@ -383,7 +393,7 @@ def diag(F):
     st = fn["b200s_chol_diag"](h, L.ptr_f64(d))
     if st != L.OK:
         _raise_status(st, "diag failed")
-    return _make_matrix(_LIKE[0], d, (inf.n, 1))
+    return _make_matrix(_FAMILY.get(h), d, (inf.n, 1))
 
 
 def getfactor(F):
@@ -401,16 +411,12 @@ def getfactor(F):
     nnz = int(colptr[-1]) if inf.n else 0
     rowind = L.take_array(li, max(nnz, 1), np.int64)[:nnz]
     values = L.take_array(lx, max(nnz, 1), np.float64)[:nnz]
-    return _make_spmatrix(_LIKE[0], values, rowind, colptr, (inf.n, inf.n))
+    return _make_spmatrix(_FAMILY.get(h), values, rowind, colptr, (inf.n, inf.n))
 
 
-# diag/getfactor have no matrix argument to copy the container type from: they return kvxopt types
-# once install() has bound a kvxopt package, scipy/numpy types otherwise.
-class _NumpyLike:
-    pass
-
-
-_LIKE = [_NumpyLike()]
+# diag/getfactor have no matrix argument: they return the container family (kvxopt or scipy/numpy) of the
+# matrix that was given to symbolic().  Keyed by factor handle, cleared by the capsule destructor.
+_FAMILY = {}
 
 
 def factor_info(F):
@@ -434,5 +440,4 @@ def install(kvxopt_module=None):
     name = kvxopt_module.__name__
     sys.modules[name + ".cholmod"] = sys.modules[__name__]
     setattr(kvxopt_module, "cholmod", sys.modules[__name__])
-    _LIKE[0] = kvxopt_module.matrix(0.0, (1, 1))
     return sys.modules[__name__]

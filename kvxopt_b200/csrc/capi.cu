@@ -226,6 +226,7 @@ b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info) {
     info->ms_total = F->times.ms_total; info->ms_solve = F->times.ms_solve; info->ms_analyze = P.ms_analyze;
     info->ms_dense_update = F->times.ms_dense_update; info->ms_potrf = F->times.ms_potrf;
     info->ms_trsm = F->times.ms_trsm; info->ms_extend = F->times.ms_extend;
+    info->flops_update = P.flops_update;
     return B200S_OK;
 }
 b200s_status b200s_chol_set_profiling(b200s_chol* F, int on) {

@@ -62,11 +62,11 @@ struct FrontD {
 };
 struct EAItem { int front, c0, c1; };
 
-constexpr int NB = 128;        // block-column width inside large fronts
+constexpr int NB = PLAN_NB;    // block-column width inside large fronts
 constexpr int TR = 64;         // rows per CTA in the panel triangular solve
 constexpr int LDL = NB + 4;    // smem stride of the diagonal block   (stride % 16 == 4 -> conflict-free DMMA fragment loads)
 constexpr int LDX = TR + 4;    // smem stride of the row tile
-constexpr int SMALL_NR = 128;  // fronts with nr <= SMALL_NR are factored by one CTA in shared memory
+constexpr int SMALL_NR = PLAN_SMALL_NR;  // fronts with nr <= SMALL_NR are factored by one CTA in shared memory
 constexpr int BT = 128;        // update tile is BT x BT
 constexpr int BK = 16;         // k-depth per pipeline stage
 constexpr int STAGES = 4;

@@ -26,6 +26,10 @@ std::vector<i32> amd_order(const SymPattern& G);
 std::vector<i32> grid_nd(i64 nx, i64 ny, i64 nz, i64 leaf);
 
 // ---- symbolic.cpp -------------------------------------------------------------------------------
+// tiling constants shared by the plan statistics and the CUDA schedule (chol_gpu.cu)
+constexpr int PLAN_NB = 128;        // block-column width inside large fronts
+constexpr int PLAN_SMALL_NR = 128;  // fronts with nr <= this are factored by one CTA in shared memory
+
 struct CholOpts {
     int supernodal = 2, nmethods = 0, postorder = 1, ordering = 0;
     double dbound = 0.0;
@@ -68,6 +72,7 @@ struct CholPlan {
     i64 nnzL = 0;                 // structural nonzeros of L (trapezoids, incl. relaxed zeros)
     i32 nlevels = 0, max_nr = 0, max_nc = 0;
     double flops = 0, flops_potrf = 0, flops_trsm = 0, flops_syrk = 0;
+    double flops_update = 0;      // flops executed by the tiled DMMA update kernel (fronts with nr > PLAN_SMALL_NR)
     double ms_analyze = 0;
 };
 

@@ -200,7 +200,7 @@ class KluDevice {
 public:
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {};
+    cudaEvent_t ev[6] = {};
     KluPlanD PD{};
     KluSolveD SD{};
     std::vector<void*> owned;
@@ -212,7 +212,7 @@ public:
     int Bp = 0, batch = 0;
     double *dA = nullptr, *dAxt = nullptr, *dRs = nullptr, *dLU = nullptr, *dX = nullptr, *dB = nullptr;
     long long capA = 0, capX = 0, capB = 0;
-    double ms_h2d = 0, ms_refactor = 0, ms_solve = 0;
+    double ms_h2d = 0, ms_refactor = 0, ms_solve = 0, ms_kernel = 0;
 
     ~KluDevice() {
         cudaSetDevice(device);
@@ -316,7 +316,9 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     }
     k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs);
     k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, nslots, Bp, dAxt, dRs, dLU);
+    CUDA_TRY(cudaEventRecord(ev[4], stream));
     k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, Bp, dLU, d_status);
+    CUDA_TRY(cudaEventRecord(ev[5], stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[2], stream));
     std::vector<int> st;
@@ -329,6 +331,7 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_h2d = ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_refactor = ms;
+    cudaEventElapsedTime(&ms, ev[4], ev[5]); ms_kernel = ms;
     return ST_OK;
 }
 
@@ -400,8 +403,8 @@ int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs
     CUDA_TRY(e);
     return ST_OK;
 }
-void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve) {
-    *h2d = d->ms_h2d; *refactor = d->ms_refactor; *solve = d->ms_solve;
+void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel) {
+    *h2d = d->ms_h2d; *refactor = d->ms_refactor; *solve = d->ms_solve; *kernel = d->ms_kernel;
 }
 
 }  // namespace b200s

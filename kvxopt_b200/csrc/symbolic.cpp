@@ -384,6 +384,14 @@ void chol_analyze(i64 n64, const i64* colptr, const i64* rowind, char uplo, cons
         plan.flops_potrf += c * c * c / 3.0;
         plan.flops_trsm += c * c * r;
         plan.flops_syrk += c * r * r;
+        if (f.nr > PLAN_SMALL_NR) {
+            double panel = 0;
+            for (i32 k0 = 0; k0 < f.nc; k0 += PLAN_NB) {
+                const double w = std::min(PLAN_NB, f.nc - k0), below = f.nr - (k0 + w);
+                panel += w * w * w / 3.0 + w * w * below;
+            }
+            plan.flops_update += (c * c * c / 3.0 + c * c * r + c * r * r) - panel;
+        }
     }
     plan.flops = plan.flops_potrf + plan.flops_trsm + plan.flops_syrk;
     plan.lsize = loff;
