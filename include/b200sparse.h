@@ -209,6 +209,8 @@ typedef struct {
     const int64_t *cbeg, *rowptr, *upd_ptr, *upd_dest;
     const int32_t *udiag_slot, *slot_src, *slot_row, *rowent, *level_ptr, *level_cols, *upd_uslot, *upd_lslot,
                   *upd_cnt, *dest, *lslot0, *fslot0;
+    /* wave schedule of the fast kernel (klu_gpu.cu): statistics */
+    b200s_int nwaves, nwaves_with_deps, nbatches, nsegments, staged_rows;
 } b200s_klu_plan_view_t;
 b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* view);
 

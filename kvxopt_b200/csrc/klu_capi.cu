@@ -209,6 +209,10 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
     v->level_ptr = P.level_ptr.data(); v->level_cols = P.level_cols.data(); v->upd_ptr = P.upd_ptr.data();
     v->upd_uslot = P.upd_uslot.data(); v->upd_lslot = P.upd_lslot.data(); v->upd_cnt = P.upd_cnt.data();
     v->upd_dest = P.upd_dest.data(); v->dest = P.dest.data(); v->lslot0 = P.lslot0.data(); v->fslot0 = P.fslot0.data();
+    v->nwaves = (b200s_int)P.wave_col0.size() - 1; v->nwaves_with_deps = 0;
+    for (int d : P.wave_hasdep) v->nwaves_with_deps += d;
+    v->nbatches = (b200s_int)P.bseg_ptr.size() - 1; v->nsegments = (b200s_int)P.seg_src.size(); v->staged_rows = 0;
+    for (int c : P.seg_cnt) v->staged_rows += c;
     return B200S_OK;
 }
 

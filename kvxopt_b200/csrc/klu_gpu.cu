@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace b200s {
@@ -70,14 +71,15 @@ __global__ void k_klu_rowscale(const long long* __restrict__ rowptr, const int* 
 }
 
 // LU[v][b] = A(src(v))[b] / Rs[row(v)][b], zero for fill-in slots
-__global__ void k_klu_scatter(const int* __restrict__ slot_src, const int* __restrict__ slot_row, long long nslots, int Bp,
-                              const double* __restrict__ Axt, const double* __restrict__ Rs, double* __restrict__ LU) {
-    const long long total = nslots * Bp;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+__global__ void k_klu_scatter(const int* __restrict__ slot_src, const int* __restrict__ slot_row, long long slot0,
+                              long long nslots, int Bp, const double* __restrict__ Axt, const double* __restrict__ Rs,
+                              double* __restrict__ LU, int prescaled) {
+    const long long total = nslots * Bp, first = slot0 * Bp;
+    for (long long t = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long v = t / Bp;
         const int b = (int)(t - v * Bp);
         const int src = slot_src[v];
-        LU[t] = (src >= 0) ? Axt[(long long)src * Bp + b] / Rs[(long long)slot_row[v] * Bp + b] : 0.0;
+        LU[t] = (src >= 0) ? (prescaled ? Axt[(long long)src * Bp + b] : Axt[(long long)src * Bp + b] / Rs[(long long)slot_row[v] * Bp + b]) : 0.0;
     }
 }
 
@@ -126,6 +128,212 @@ __global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, int
         __syncthreads();
     }
     if (bad) status[b] = ST_SINGULAR;
+}
+
+// Fast path: wave schedule.  One CTA per group of 32 matrices, one warp per column of the current wave.  The
+// column's slots live in shared memory ([row][32 matrices], every lane touches only its own matrix, so no
+// intra-warp synchronisation is needed); L columns of finished columns stream from global memory; the scatter of
+// the scaled input values is fused into the column initialisation.
+struct KluWaveD {
+    int nwaves;
+    const int *wave_col0, *col_roff, *batch_rowslot, *wave_rowsrc;
+    const unsigned* bentry;     // per batch [KLU_WAVE_WARPS][KLU_CHUNK_ROWS] staged-row actions
+    const unsigned* wblob;      // in-wave update blobs
+    const long long *wbatch_ptr, *wblob_ptr;
+};
+
+__device__ __forceinline__ void klu_cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void klu_cp_async16_zfill(void* smem, const void* gmem, int bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
+constexpr int KLU_ENTRY_DOUBLES = (KLU_WAVE_WARPS * KLU_REC_U32 + KLU_CHUNK_ROWS) / 2;   // column records + next row->slot table (uint32), in doubles
+constexpr int KLU_STAGE_DOUBLES = KLU_CHUNK_ROWS * 32 + KLU_ENTRY_DOUBLES;      // L rows + per-warp row actions
+constexpr size_t KLU_WAVE_SMEM =
+    (size_t)(KLU_WAVE_ROWS * 32 + KLU_STAGES * KLU_STAGE_DOUBLES) * sizeof(double) + KLU_BLOB_BYTES;
+
+// Fast path: wave schedule.  One CTA per group of 32 matrices (lane = matrix), one warp per column of the wave.
+//   xs    : the columns of the wave, [row][32 matrices] doubles -- every lane touches only its own matrix
+//   stage : KLU_STAGES-deep cp.async ring; a batch = 64 rows of finished L columns (read once from HBM/L2 and
+//           consumed by every column of the wave) + for each warp and row what to do with it (destination row, row
+//           holding u_jk) so that the update loop reads NO metadata from global memory
+//   blob  : the updates between columns of the same wave (applied in rounds from the source's xs region)
+// The input values arrive pre-scaled (k_klu_prescale), gathered straight into xs by cp.async with zero fill.
+__global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(KluPlanD P, KluWaveD W, int Bp,
+                                                                              const double* __restrict__ Axs,
+                                                                              double* __restrict__ LU, int* __restrict__ status,
+                                                                              long long* __restrict__ dbg) {
+    extern __shared__ double smem_klu[];
+    double* xs = smem_klu;
+    double* stage = smem_klu + KLU_WAVE_ROWS * 32;
+    double* blob = stage + KLU_STAGES * KLU_STAGE_DOUBLES;
+    __shared__ int done_round[KLU_WAVE_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    double* lu = LU + b;
+    const double* lug = LU + (long long)blockIdx.x * 32;          // group base for the cooperative copies
+    const double* axg = Axs + (long long)blockIdx.x * 32;
+    int bad = 0;
+    const int srow = tid >> 4, spc = (tid & 15) * 2;
+    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0, t_wait = 0, t_bar = 0, t_issue = 0, t_apply = 0, tC = 0;
+    auto stage_batch = [&](long long bi, int ls0, int ls1, int buf) {
+        double* dst = stage + (long long)buf * KLU_STAGE_DOUBLES;
+        if (ls0 >= 0) klu_cp_async16(dst + srow * 32 + spc, lug + (long long)ls0 * Bp + spc);
+        if (ls1 >= 0) klu_cp_async16(dst + (srow + 32) * 32 + spc, lug + (long long)ls1 * Bp + spc);
+        if (tid < KLU_ENTRY_DOUBLES / 2)
+            klu_cp_async16(dst + KLU_CHUNK_ROWS * 32 + tid * 2, W.bentry + (bi * KLU_ENTRY_DOUBLES + tid * 2) * 2);
+    };
+    for (int w = 0; w < W.nwaves; w++) {
+        if (dbg) tA = clock64();
+        const int k0 = W.wave_col0[w], wc = W.wave_col0[w + 1] - k0;
+        // team = the warps that share one column: 16 / (wc rounded up to a power of two) warps
+        const int tshift = (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
+        const int T = 1 << tshift, col = warp >> tshift, sub = warp & (T - 1);
+        const bool active = col < wc;
+        const int k = k0 + (active ? col : 0);
+        const int cb = (int)P.cbeg[k];
+        const int len = (int)P.cbeg[k + 1] - cb;
+        double* x = xs + W.col_roff[k] * 32 + lane;
+        const int diag = P.udiag_slot[k] - cb, l0 = P.lslot0[k] - cb;
+        const long long c0 = W.wbatch_ptr[w];
+        const int nb = (int)(W.wbatch_ptr[w + 1] - c0);
+        auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
+        // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
+        {
+            const int klast = k0 + wc - 1;
+            const int wrows = W.col_roff[klast] + (int)(P.cbeg[klast + 1] - P.cbeg[klast]);
+            const int* rsrc = W.wave_rowsrc + (long long)w * KLU_WAVE_ROWS;
+            for (int row = srow; row < wrows; row += 32) {
+                const int src = rsrc[row];
+                klu_cp_async16_zfill(xs + row * 32 + spc, src >= 0 ? axg + (long long)src * Bp + spc : axg, src >= 0 ? 16 : 0);
+            }
+            const long long bp0 = W.wblob_ptr[w];
+            const int pieces = (int)(W.wblob_ptr[w + 1] - bp0);
+            for (int q = tid; q < pieces; q += KLU_WAVE_WARPS * 32) klu_cp_async16(blob + q * 2, W.wblob + (bp0 + q) * 4);
+            asm volatile("cp.async.commit_group;");
+        }
+        // ---- prologue of the batch pipeline
+        for (int st = 0; st < KLU_STAGES - 1; st++) {
+            if (st < nb) {
+                const int* rs = W.batch_rowslot + (c0 + st) * KLU_CHUNK_ROWS;
+                stage_batch(c0 + st, rs[srow], rs[srow + 32], st);
+            }
+            asm volatile("cp.async.commit_group;");
+        }
+        if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
+        int buf = 0;
+        for (int c = 0; c < nb; c++) {
+            if (dbg) tC = clock64();
+            asm volatile("cp.async.wait_group %0;" ::"n"(KLU_STAGES - 2));
+            if (dbg) { long long tD = clock64(); t_wait += tD - tC; tC = tD; }
+            __syncthreads();
+            if (dbg) { long long tD = clock64(); t_bar += tD - tC; tC = tD; }
+            const int nc = c + KLU_STAGES - 1;
+            int nbuf = buf + KLU_STAGES - 1; if (nbuf >= KLU_STAGES) nbuf -= KLU_STAGES;
+            if (nc < nb) {
+                // the row -> slot table of batch nc travelled with batch c (the one being consumed): no global load here
+                const int* rsn = reinterpret_cast<const int*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
+                                 KLU_WAVE_WARPS * KLU_REC_U32;
+                stage_batch(c0 + nc, rsn[srow], rsn[srow + 32], nbuf);
+            }
+            asm volatile("cp.async.commit_group;");
+            if (dbg) { long long tD = clock64(); t_issue += tD - tC; tC = tD; }
+            if (active) {
+                const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
+                const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
+                                      col * KLU_REC_U32;
+                const unsigned short* dd = reinterpret_cast<const unsigned short*>(rec + 16);
+                const int nseg = (int)rec[0];
+                // per matched segment: team barrier (the previous segment may have written u_jk or the same rows from
+                // another warp of the team), then the segment's rows are split over the team in chunks of four
+                for (int sgi = 1; sgi <= nseg; sgi++) {
+                    const unsigned sd = rec[sgi];
+                    const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
+                    team_sync();
+                    const double ujk = x[(sd >> 16) * 32];
+                    int t = r0 + 4 * sub;
+                    for (; t + 4 <= r1; t += 4 * T) {
+                        const int d0 = dd[t] * 32, d1 = dd[t + 1] * 32, d2 = dd[t + 2] * 32, d3 = dd[t + 3] * 32;
+                        const double l0v = sb[t * 32], l1v = sb[(t + 1) * 32], l2v = sb[(t + 2) * 32], l3v = sb[(t + 3) * 32];
+                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
+                        x[d0] = x0 - l0v * ujk; x[d1] = x1 - l1v * ujk; x[d2] = x2 - l2v * ujk; x[d3] = x3 - l3v * ujk;
+                    }
+                    for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;      // tail (< 4 rows) of the warp that owns it
+                }
+            }
+            if (dbg) { long long tD = clock64(); t_apply += tD - tC; }
+            if (++buf == KLU_STAGES) buf = 0;
+        }
+        asm volatile("cp.async.wait_group 0;");
+        if (tid < KLU_WAVE_WARPS) done_round[tid] = 0x7fffffff;
+        __syncthreads();
+        if (dbg) { long long tB = clock64(); t_p1 += tB - tA; tA = tB; }
+        // ---- sources inside the wave: rounds.  In round r a column consumes (in pivot order) the in-wave sources
+        // finalized in rounds < r from their xs regions, and finalizes itself once all its updates are applied.
+        const unsigned* bl = reinterpret_cast<const unsigned*>(blob);
+        int ui = active ? (int)bl[2 * col] : 0;
+        const int ue = active ? ui + (int)bl[2 * col + 1] : 0;
+        const int nupd_wave = (int)(bl[2 * (wc - 1)] + bl[2 * (wc - 1) + 1]);
+        const unsigned* updl = bl + 2 * KLU_WAVE_WARPS;
+        const unsigned short* bdst = reinterpret_cast<const unsigned short*>(updl + 4 * nupd_wave);
+        bool fin = !active;
+        for (int r = 0;; r++) {
+            if (!fin) {
+                while (ui < ue) {
+                    const unsigned w0 = updl[4 * ui];
+                    if (done_round[w0 & 0xffu] >= r) break;
+                    team_sync();                  // the previous update (or the staged phase) of every team warp is done
+                    const double uj = x[updl[4 * ui + 1] * 32];
+                    const int cnt = (int)updl[4 * ui + 2];
+                    const unsigned short* d = bdst + updl[4 * ui + 3];
+                    const double* lsrc = xs + (w0 >> 8) * 32 + lane;
+                    int t = sub * 4;
+                    for (; t + 4 <= cnt; t += 4 * T) {
+                        const int d0 = d[t] * 32, d1 = d[t + 1] * 32, d2 = d[t + 2] * 32, d3 = d[t + 3] * 32;
+                        const double l0v = lsrc[t * 32], l1v = lsrc[(t + 1) * 32], l2v = lsrc[(t + 2) * 32], l3v = lsrc[(t + 3) * 32];
+                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
+                        x[d0] = x0 - l0v * uj; x[d1] = x1 - l1v * uj; x[d2] = x2 - l2v * uj; x[d3] = x3 - l3v * uj;
+                    }
+                    for (; t < cnt; t++) x[d[t] * 32] -= lsrc[t * 32] * uj;     // tail (< 4 rows) of the warp that owns it
+                    ui++;
+                }
+                if (ui == ue) {
+                    team_sync();
+                    const double piv = x[diag * 32];
+                    if (!(fabs(piv) > 0.0)) bad = 1;
+                    team_sync();                  // everyone has read the pivot before the column is rewritten
+                    const double rpiv = 1.0 / piv;    // one division per column; L(:,k) = x * (1/pivot)
+#pragma unroll 4
+                    for (int sl = l0 + sub; sl < len; sl += T) x[sl * 32] *= rpiv;
+                    team_sync();
+#pragma unroll 4
+                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
+                    fin = true;
+                    if (lane == 0 && sub == 0) done_round[col] = r;
+                }
+            }
+            n_rounds++;
+            if (__syncthreads_count(!fin) == 0) break;
+        }
+        if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; }
+    }
+    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = t_wait; dbg[5] = t_bar; dbg[6] = t_issue; dbg[7] = t_apply; }
+    if (bad) status[b] = ST_SINGULAR;
+}
+
+// Axt[e][b] /= Rs[row(e)][b]: the row scaling of klu_factor applied to the transposed input once
+__global__ void k_klu_prescale(const int* __restrict__ ent_row, long long nnz, int Bp, const double* __restrict__ Rs,
+                               double* __restrict__ Axt) {
+    const long long total = nnz * Bp;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long e = t / Bp;
+        const int b = (int)(t - e * Bp);
+        Axt[t] = Axt[t] / Rs[(long long)ent_row[e] * Bp + b];
+    }
 }
 
 struct KluSolveD {
@@ -202,9 +410,14 @@ public:
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     KluPlanD PD{};
+    KluWaveD WD{};
     KluSolveD SD{};
+    bool use_wave = false;
+    long long lu_slots = 0;
     std::vector<void*> owned;
     int *d_slot_src = nullptr, *d_slot_row = nullptr, *d_rowent = nullptr, *d_status = nullptr;
+    int* d_ent_row = nullptr;
+    long long* ddbg = nullptr;     // optional phase timers of the wave kernel (B200S_KLU_DEBUG=1)
     long long* d_rowptr = nullptr;
     long long nslots = 0, nnzA = 0;
     int n = 0;
@@ -240,6 +453,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     n = P.n; nslots = P.nslots; nnzA = P.nnzA;
+    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(cudaMalloc((void**)&ddbg, 8 * sizeof(long long))); owned.push_back(ddbg); }
     int rc;
     PD.n = P.n; PD.nlevels = P.nlevels;
     std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
@@ -255,6 +469,29 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     if ((rc = up(&PD.cbeg, cbeg))) return rc;
     if ((rc = up(&PD.upd_ptr, updp))) return rc;
     if ((rc = up(&PD.upd_dest, updd))) return rc;
+    lu_slots = P.lu_slots;
+    {
+        WD.nwaves = (int)P.wave_col0.size() - 1;
+        if ((rc = up(&WD.wave_col0, P.wave_col0))) return rc;
+        if ((rc = up(&WD.col_roff, P.col_roff))) return rc;
+        std::vector<long long> wbp(P.wbatch_ptr.begin(), P.wbatch_ptr.end()), wlp(P.wblob_ptr.begin(), P.wblob_ptr.end());
+        if ((rc = up(&WD.wbatch_ptr, wbp))) return rc;
+        if ((rc = up(&WD.wblob_ptr, wlp))) return rc;
+        if ((rc = up(&WD.batch_rowslot, P.batch_rowslot))) return rc;
+        if ((rc = up(&WD.wave_rowsrc, P.wave_rowsrc))) return rc;
+        std::vector<unsigned> be(P.bentry.begin(), P.bentry.end()), wb(P.wblob.begin(), P.wblob.end());
+        if ((rc = up(&WD.bentry, be))) return rc;
+        if ((rc = up(&WD.wblob, wb))) return rc;
+        std::vector<int> ent_row(P.nnzA, 0);
+        for (int i = 0; i < P.n; i++)
+            for (long long q = P.rowptr[i]; q < P.rowptr[i + 1]; q++) ent_row[P.rowent[q]] = i;
+        const int* er;
+        if ((rc = up(&er, ent_row))) return rc;
+        d_ent_row = (int*)er;
+        use_wave = P.max_col_len <= KLU_WAVE_ROWS;
+        if (use_wave)
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
+    }
     const int* tmp_i; const long long* tmp_l;
     if ((rc = up(&tmp_i, P.slot_src))) return rc; d_slot_src = (int*)tmp_i;
     if ((rc = up(&tmp_i, P.slot_row))) return rc; d_slot_row = (int*)tmp_i;
@@ -315,10 +552,20 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
         k_klu_transpose<<<grid, block, 0, stream>>>(dv, ldv, nnzA, batch, Bp, dAxt);
     }
     k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs);
-    k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, nslots, Bp, dAxt, dRs, dLU);
-    CUDA_TRY(cudaEventRecord(ev[4], stream));
-    k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, Bp, dLU, d_status);
-    CUDA_TRY(cudaEventRecord(ev[5], stream));
+    if (use_wave) {
+        k_klu_prescale<<<148 * 16, 256, 0, stream>>>(d_ent_row, nnzA, Bp, dRs, dAxt);
+        // only the off-diagonal-block entries F need a separate scatter; L/U columns are gathered inside the kernel
+        if (nslots > lu_slots)
+            k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1);
+        CUDA_TRY(cudaEventRecord(ev[4], stream));
+        k_klu_refactor_wave<<<Bp / 32, KLU_WAVE_WARPS * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
+        CUDA_TRY(cudaEventRecord(ev[5], stream));
+    } else {
+        k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, 0, nslots, Bp, dAxt, dRs, dLU, 0);
+        CUDA_TRY(cudaEventRecord(ev[4], stream));
+        k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, Bp, dLU, d_status);
+        CUDA_TRY(cudaEventRecord(ev[5], stream));
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[2], stream));
     std::vector<int> st;
@@ -328,6 +575,11 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     if (status_host) for (long long b = 0; b < batch_; b++) status_host[b] = st[b];
+    if (ddbg) {
+        long long h[8] = {0};
+        cudaMemcpy(h, ddbg, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld) | warp 0: wait %lld barrier %lld issue %lld apply %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_h2d = ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_refactor = ms;

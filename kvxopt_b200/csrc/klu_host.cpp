@@ -10,6 +10,7 @@
 #include "gpu.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <stdexcept>
 
 namespace b200s {
@@ -369,6 +370,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             const i32 j = N.Ui[p];
             const i64 cnt = N.Lp[j + 1] - N.Lp[j] - 1;
             if (cnt == 0) continue;
+            P.upd_src.push_back(j);
             P.upd_uslot.push_back((i32)(uslot0[k] + (p - N.Up[k])));
             P.upd_lslot.push_back(P.lslot0[j]);
             P.upd_cnt.push_back((i32)cnt);
@@ -390,6 +392,156 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
     {
         std::vector<i64> pos(P.rowptr.begin(), P.rowptr.end() - 1);
         for (i64 p = 0; p < S.nnz; p++) P.rowent[pos[pinvnum[S.Ai[p]]]++] = (i32)p;
+    }
+    // wave schedule
+    P.col_roff.assign(n, 0);
+    P.upd_split.assign(n, 0);
+    P.wave_col0.clear();
+    P.max_col_len = 0;
+    for (i32 k = 0; k < n; k++) P.max_col_len = std::max<i32>(P.max_col_len, (i32)(P.cbeg[k + 1] - P.cbeg[k]));
+    {
+        // in-wave blob size if the wave [k0, k1) were closed: header + updates + dest lists
+        auto blob_bytes = [&](i32 k0, i32 k1) {
+            i64 nu = 0, nd = 0;
+            for (i32 c = k0; c < k1; c++)
+                for (i64 u = P.upd_ptr[c]; u < P.upd_ptr[c + 1]; u++)
+                    if (P.upd_src[u] >= k0) { nu++; nd += P.upd_cnt[u]; }
+            return (i64)(2 * KLU_WAVE_WARPS) * 4 + nu * 16 + ((nd * 2 + 15) / 16) * 16;
+        };
+        i32 k = 0;
+        while (k < n) {
+            P.wave_col0.push_back(k);
+            const i32 k0 = k;
+            i32 rows = 0, cnt = 0;
+            while (k < n && cnt < KLU_WAVE_WARPS) {
+                const i32 len = (i32)(P.cbeg[k + 1] - P.cbeg[k]);
+                if (cnt > 0 && rows + len > KLU_WAVE_ROWS) break;
+                if (cnt > 0 && blob_bytes(k0, k + 1) > KLU_BLOB_BYTES) break;
+                P.col_roff[k] = rows;
+                rows += len;
+                cnt++;
+                k++;
+            }
+        }
+        P.wave_col0.push_back(n);
+        const i32 nw = (i32)P.wave_col0.size() - 1;
+        P.wave_hasdep.assign(nw, 0);
+        P.wbatch_ptr.assign(1, 0);
+        P.bseg_ptr.assign(1, 0);
+        std::vector<i32> srcs;
+        for (i32 w = 0; w < nw; w++) {
+            const i32 k0 = P.wave_col0[w];
+            srcs.clear();
+            for (i32 c = k0; c < P.wave_col0[w + 1]; c++) {
+                i64 u = P.upd_ptr[c];
+                while (u < P.upd_ptr[c + 1] && P.upd_src[u] < k0) { srcs.push_back(P.upd_src[u]); u++; }
+                P.upd_split[c] = u;
+                if (u < P.upd_ptr[c + 1]) P.wave_hasdep[w] = 1;
+            }
+            std::sort(srcs.begin(), srcs.end());
+            srcs.erase(std::unique(srcs.begin(), srcs.end()), srcs.end());
+            i32 fill = KLU_CHUNK_ROWS;      // rows used in the open batch (full => start a new one)
+            std::vector<i32> matched(P.wave_col0[w + 1] - k0, 0);      // segments of the open batch used by each column
+            std::vector<i64> ucur(P.wave_col0[w + 1] - k0);
+            for (i32 c = k0; c < P.wave_col0[w + 1]; c++) ucur[c - k0] = P.upd_ptr[c];
+            for (i32 j : srcs) {
+                const i32 total = (i32)(N.Lp[j + 1] - N.Lp[j] - 1);
+                // columns of the wave that use source j
+                std::vector<i32> users;
+                for (i32 c = k0; c < P.wave_col0[w + 1]; c++) {
+                    i64& u = ucur[c - k0];
+                    if (u < P.upd_split[c] && P.upd_src[u] == j) { users.push_back(c - k0); u++; }
+                }
+                i32 off = 0;
+                while (off < total) {
+                    bool overflow = false;
+                    for (i32 q : users) if (matched[q] >= KLU_MAXSEG) overflow = true;
+                    if (overflow) fill = KLU_CHUNK_ROWS;
+                    if (fill == KLU_CHUNK_ROWS) {          // open a new batch
+                        std::fill(matched.begin(), matched.end(), 0);
+                        if (!P.seg_src.empty() && P.bseg_ptr.back() != (i64)P.seg_src.size()) P.bseg_ptr.push_back((i64)P.seg_src.size());
+                        P.batch_rowslot.insert(P.batch_rowslot.end(), KLU_CHUNK_ROWS, -1);
+                        fill = 0;
+                    }
+                    const i32 cnt = std::min(KLU_CHUNK_ROWS - fill, total - off);
+                    P.seg_src.push_back(j); P.seg_off.push_back(off); P.seg_cnt.push_back(cnt); P.seg_row.push_back(fill);
+                    for (i32 q : users) matched[q]++;
+                    i32* rs = P.batch_rowslot.data() + P.batch_rowslot.size() - KLU_CHUNK_ROWS;
+                    for (i32 r = 0; r < cnt; r++) rs[fill + r] = P.lslot0[j] + off + r;
+                    fill += cnt;
+                    off += cnt;
+                }
+            }
+            if (P.bseg_ptr.back() != (i64)P.seg_src.size()) P.bseg_ptr.push_back((i64)P.seg_src.size());
+            P.wbatch_ptr.push_back((i64)P.bseg_ptr.size() - 1);
+        }
+    }
+    // ---- staged tables of the wave kernel
+    {
+        const i32 nw = (i32)P.wave_col0.size() - 1;
+        const size_t nbatch = P.bseg_ptr.size() - 1;
+        const size_t BST = (size_t)KLU_WAVE_WARPS * KLU_REC_U32 + KLU_CHUNK_ROWS;
+        P.bentry.assign(nbatch * BST, 0u);
+        for (i32 w = 0; w < nw; w++)
+            for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1]; bi++) {
+                const i64 nx = bi + KLU_STAGES - 1;
+                for (i32 r = 0; r < KLU_CHUNK_ROWS; r++)
+                    P.bentry[bi * BST + (size_t)KLU_WAVE_WARPS * KLU_REC_U32 + r] =
+                        (nx < P.wbatch_ptr[w + 1]) ? (uint32_t)P.batch_rowslot[nx * KLU_CHUNK_ROWS + r] : 0xffffffffu;
+            }
+        P.wave_rowsrc.assign((size_t)nw * KLU_WAVE_ROWS, -1);
+        P.wblob_ptr.assign(1, 0);
+        for (i32 w = 0; w < nw; w++) {
+            const i32 k0 = P.wave_col0[w], k1 = P.wave_col0[w + 1];
+            for (i32 c = k0; c < k1; c++) {
+                const i64 cb = P.cbeg[c];
+                const i32 len = (i32)(P.cbeg[c + 1] - cb);
+                if (P.col_roff[c] + len > KLU_WAVE_ROWS) continue;      // oversized single column: fallback kernel
+                for (i32 sl = 0; sl < len; sl++) P.wave_rowsrc[(size_t)w * KLU_WAVE_ROWS + P.col_roff[c] + sl] = P.slot_src[cb + sl];
+                // entries of the staged (earlier-wave) updates of column c
+                i64 u = P.upd_ptr[c];
+                for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1] && u < P.upd_split[c]; bi++)
+                    for (i64 sg = P.bseg_ptr[bi]; sg < P.bseg_ptr[bi + 1] && u < P.upd_split[c]; sg++) {
+                        if (P.seg_src[sg] != P.upd_src[u]) continue;
+                        const i32 uloc = (i32)(P.upd_uslot[u] - cb);
+                        uint32_t* rec = P.bentry.data() + (size_t)bi * BST + (size_t)(c - k0) * KLU_REC_U32;
+                        if (rec[0] >= (uint32_t)KLU_MAXSEG) throw std::logic_error("klu plan: too many segments in a batch record");
+                        rec[0]++;
+                        rec[rec[0]] = (uint32_t)P.seg_row[sg] | ((uint32_t)P.seg_cnt[sg] << 8) | ((uint32_t)uloc << 16);
+                        uint16_t* dd = reinterpret_cast<uint16_t*>(rec + 16);
+                        for (i32 r = 0; r < P.seg_cnt[sg]; r++)
+                            dd[P.seg_row[sg] + r] = (uint16_t)(P.dest[P.upd_dest[u] + P.seg_off[sg] + r] - cb);
+                        if (P.seg_off[sg] + P.seg_cnt[sg] == P.upd_cnt[u]) u++;
+                    }
+                if (u != P.upd_split[c]) throw std::logic_error("klu plan: staged updates do not cover a column");
+            }
+            // in-wave blob
+            std::vector<uint32_t> hdr(2 * KLU_WAVE_WARPS, 0), upd;
+            std::vector<uint16_t> dst;
+            for (i32 c = k0; c < k1; c++) {
+                const i64 cb = P.cbeg[c];
+                hdr[2 * (c - k0)] = (uint32_t)(upd.size() / 4);
+                for (i64 u = P.upd_split[c]; u < P.upd_ptr[c + 1]; u++) {
+                    {
+                        const i32 j = P.upd_src[u];
+                        const uint32_t srcrow0 = (uint32_t)(P.col_roff[j] + (P.lslot0[j] - P.cbeg[j]));   // first L row of the source in xs
+                        upd.push_back((uint32_t)(j - k0) | (srcrow0 << 8));
+                    }
+                    upd.push_back((uint32_t)(P.upd_uslot[u] - cb));
+                    upd.push_back((uint32_t)P.upd_cnt[u]);
+                    upd.push_back((uint32_t)dst.size());
+                    for (i32 r = 0; r < P.upd_cnt[u]; r++) dst.push_back((uint16_t)(P.dest[P.upd_dest[u] + r] - cb));
+                }
+                hdr[2 * (c - k0) + 1] = (uint32_t)(upd.size() / 4) - hdr[2 * (c - k0)];
+            }
+            while (dst.size() % 8) dst.push_back(0);
+            const size_t before = P.wblob.size();
+            P.wblob.insert(P.wblob.end(), hdr.begin(), hdr.end());
+            P.wblob.insert(P.wblob.end(), upd.begin(), upd.end());
+            for (size_t q = 0; q < dst.size(); q += 2) P.wblob.push_back((uint32_t)dst[q] | ((uint32_t)dst[q + 1] << 16));
+            if ((P.wblob.size() - before) * 4 > (size_t)KLU_BLOB_BYTES && k1 - k0 > 1) throw std::logic_error("klu plan: in-wave blob too large");
+            P.wblob_ptr.push_back((i64)(P.wblob.size() / 4));
+        }
     }
     // level schedule: column k depends on every column j with U(j,k) != 0
     std::vector<i32> level(n, 0);

@@ -3,6 +3,7 @@
 // that the batched CUDA kernels execute.
 #pragma once
 #include "host.hpp"
+#include <cstdint>
 
 namespace b200s {
 
@@ -54,10 +55,47 @@ struct KluPlan {
     std::vector<i32> upd_uslot, upd_lslot, upd_cnt;
     std::vector<i64> upd_dest;        // offset into dest[]
     std::vector<i32> dest;
+    // wave schedule (the fast kernel): columns 0..n-1 in order, grouped into waves of consecutive columns, one
+    // warp per column, the column's slots held in shared memory (rows x 32 matrices).  A wave is bounded by the
+    // warp count and by the shared-memory rows.  Updates of column k split at upd_split[k]: sources in earlier
+    // waves (applied independently by every warp) / sources inside the wave (applied in pivot order).
+    std::vector<i32> wave_col0;       // nwaves+1
+    std::vector<i32> wave_hasdep;     // nwaves: 1 when some column of the wave depends on another column of it
+    std::vector<i32> col_roff;        // n: first shared-memory row of the column inside its wave
+    std::vector<i64> upd_split;       // n
+    std::vector<i32> upd_src;         // per update: source column j
+    // per wave: the union of the earlier-wave source columns its columns need, cut into segments (source column,
+    // row range) and packed into batches of at most KLU_CHUNK_ROWS L entries; the CTA stages each batch in shared
+    // memory once (cp.async, KLU_STAGES deep) and every column of the wave consumes it from there
+    std::vector<i64> wbatch_ptr;      // nwaves+1 -> batches
+    std::vector<i64> bseg_ptr;        // nbatches+1 -> segments
+    std::vector<i32> seg_src, seg_off, seg_cnt, seg_row;   // source column, first L row, rows, first row in the stage
+    std::vector<i32> batch_rowslot;   // nbatches * KLU_CHUNK_ROWS: global slot staged into each row (-1 = unused)
+    // per batch: KLU_WAVE_WARPS records of KLU_REC_U32 words -- {nseg, then per matched segment (first stage row) |
+    // (rows << 8) | (row of u_jk << 16)}, the destination row (uint16) of every staged row -- followed by the row -> slot
+    // table (KLU_CHUNK_ROWS words) of the batch issued while this one is consumed
+    std::vector<uint32_t> bentry;
+    std::vector<i32> wave_rowsrc;     // nwaves * KLU_WAVE_ROWS: value-array index gathered into each shared-memory row
+                                      // (-1 = fill-in slot, zero)
+    // per wave: blob with the updates whose source column is inside the wave (16-byte units):
+    // ints [2q],[2q+1] = first update / count of warp q; updates {source warp, row of u_jk, rows, dest offset};
+    // then the destination rows as uint16
+    std::vector<i64> wblob_ptr;       // nwaves+1, in 16-byte units
+    std::vector<uint32_t> wblob;
+    i32 max_col_len = 0;
     // solve schedule uses Lp/Li/Up/Ui/Fp/Fi of the numeric object with slots: L(i,k) at lslot, etc.
     std::vector<i32> lslot0;          // per column: first L slot (below diagonal)
     std::vector<i32> fslot0;          // per column: first F slot
 };
+constexpr int KLU_WAVE_WARPS = 16;   // columns (warps) per wave
+constexpr int KLU_WAVE_ROWS = 464;   // shared-memory rows for the columns of a wave (x 32 matrices x 8 B = 116 KiB)
+constexpr int KLU_META_INT4 = 72;    // per batch: header {nseg} + up to 64 segment descriptors, padded to 1152 B
+constexpr int KLU_CHUNK_ROWS = 64;   // L entries staged per chunk (16 KiB per stage)
+constexpr int KLU_STAGES = 5;
+constexpr uint32_t KLU_SKIP = 0xffffffffu;
+constexpr int KLU_MAXSEG = 15;        // matched segments per (batch, column); the host closes a batch before it overflows
+constexpr int KLU_REC_U32 = 16 + KLU_CHUNK_ROWS / 2;   // per (batch, column): {nseg, segs[15]} + 64 uint16 destination rows
+constexpr int KLU_BLOB_BYTES = 8192;  // cap of the in-wave update blob
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan);
 
 }  // namespace b200s
