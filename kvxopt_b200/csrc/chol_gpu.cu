@@ -171,6 +171,72 @@ __device__ __forceinline__ void smem_partial_chol(double* S, int lds, int nr, in
     __syncthreads();
 }
 
+// Blocked Cholesky of a w x w (w <= 128, padded to wpad = multiple of 16 with an identity tail) lower-triangular
+// block held in shared memory with stride LDL, 256 threads: per 16-column chunk (1) warp 0 factors the 16x16
+// diagonal chunk, one lane per row; (2) one thread per row solves the rows below against it; (3) all warps apply the
+// rank-16 update to the trailing lower triangle with FP64 DMMA on 8x8 tiles.  6 block barriers per chunk instead
+// of 2 per column.
+__device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, int gcol0, int* minor, double dbound,
+                                                   bool record, double* rdiag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c0 = 0; c0 < wpad; c0 += 16) {
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = 0; j < 16; j++) {
+                const double d = S[(c0 + j) * LDL + c0 + j];
+                if (!(d > 0.0) && record && lane == 0 && c0 + j < w) atomicMin(minor, gcol0 + c0 + j);
+                double l = sqrt(d);
+                if (dbound > 0.0 && l < dbound) l = dbound;
+                const double inv = 1.0 / l;
+                __syncwarp();
+                double lij = 0.0;
+                if (lane > j && lane < 16) { lij = S[(c0 + j) * LDL + c0 + lane] * inv; S[(c0 + j) * LDL + c0 + lane] = lij; }
+                if (lane == j) { S[(c0 + j) * LDL + c0 + j] = l; rdiag[j] = inv; }
+                __syncwarp();
+                if (lane > j && lane < 16)
+                    for (int c = j + 1; c <= lane; c++) S[(c0 + c) * LDL + c0 + lane] -= lij * S[(c0 + j) * LDL + c0 + c];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const int t0 = c0 + 16;
+        for (int r = t0 + tid; r < wpad; r += 256) {
+            double xv[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) xv[q] = S[(c0 + q) * LDL + r];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                double v = xv[q];
+#pragma unroll
+                for (int p = 0; p < q; p++) v -= xv[p] * S[(c0 + p) * LDL + c0 + q];
+                xv[q] = v * rdiag[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) S[(c0 + q) * LDL + r] = xv[q];
+        }
+        __syncthreads();
+        const int nt = (wpad - t0) >> 3;
+        const int ntiles = nt * (nt + 1) / 2;
+        for (int tile = warp; tile < ntiles; tile += 8) {
+            int ti = (int)((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > tile) ti--;
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+            const int tj = tile - ti * (ti + 1) / 2;
+            const int row = t0 + 8 * ti + (lane >> 2), col = t0 + 8 * tj + 2 * (lane & 3);
+            double c0v = S[col * LDL + row], c1v = S[(col + 1) * LDL + row];
+#pragma unroll
+            for (int k4 = 0; k4 < 16; k4 += 4) {
+                const double a = -S[(c0 + k4 + (lane & 3)) * LDL + t0 + 8 * ti + (lane >> 2)];
+                const double bq = S[(c0 + k4 + (lane & 3)) * LDL + t0 + 8 * tj + (lane >> 2)];
+                dmma884(c0v, c1v, a, bq);
+            }
+            S[col * LDL + row] = c0v;
+            S[(col + 1) * LDL + row] = c1v;
+        }
+    }
+    __syncthreads();
+}
+
 // K6: one CTA per small front (nr <= SMALL_NR): load panel + update matrix, factor, write back.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__ list, const FrontD* __restrict__ F,
@@ -231,15 +297,8 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
         else if (rr == c) v = 1.0;
         Ls[c * LDL + rr] = v;
     }
-    const int row0 = k0 + w + (r - 1) * TR;
-    const int nrows = (r > 0) ? min(TR, f.nr - row0) : 0;
-    if (r > 0) {
-        for (int idx = tid; idx < wpad * TR; idx += 256) {
-            int c = idx / TR, i = idx - c * TR;
-            Xs[c * LDX + i] = (c < w && i < nrows) ? P[(long long)(k0 + c) * ld + row0 + i] : 0.0;
-        }
-    }
-    smem_partial_chol<256>(Ls, LDL, w, w, f.col0 + k0, minor, dbound, r == 0);
+    __shared__ double rdiag16[16];
+    smem_potrf_blocked(Ls, w, wpad, f.col0 + k0, minor, dbound, r == 0, rdiag16);
     if (r == 0) {
         // The factored block goes to scratch, not to the panel: CTAs of this launch that start later still
         // have to read the UNfactored block.  k_diag_writeback copies it into the panel after this launch.
@@ -251,43 +310,56 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
         return;
     }
     if (tid < wpad) rinv[tid] = 1.0 / Ls[tid * LDL + tid];
-    __syncthreads();
-    // ---- X L11^T = B, 16 columns at a time; warp owns rows [8*warp, 8*warp+8), 4 lanes per row
+    // this CTA solves the 64-row tiles r-1, r-1+nsolve, ... of the rows below the diagonal block with the factor
+    // it holds in shared memory (the redundant diagonal factorization is paid once per CTA, not once per tile)
+    const int nsolve = gprefix[g + 1] - gprefix[g] - 1;
+    const int ntiles = (f.nr - (k0 + w) + TR - 1) / TR;
     const int q = lane & 3, rw = warp * 8 + (lane >> 2);
-    for (int c0 = 0; c0 < wpad; c0 += 16) {
-        double b00 = Xs[(c0 + 2 * q) * LDX + rw], b01 = Xs[(c0 + 2 * q + 1) * LDX + rw];
-        double b10 = Xs[(c0 + 8 + 2 * q) * LDX + rw], b11 = Xs[(c0 + 8 + 2 * q + 1) * LDX + rw];
-        for (int k4 = 0; k4 < c0; k4 += 4) {
-            const double a = -Xs[(k4 + q) * LDX + rw];
-            const double l0 = Ls[(k4 + q) * LDL + c0 + (lane >> 2)];
-            const double l1 = Ls[(k4 + q) * LDL + c0 + 8 + (lane >> 2)];
-            dmma884(b00, b01, a, l0);
-            dmma884(b10, b11, a, l1);
+    for (int tile = r - 1; tile < ntiles; tile += nsolve) {
+        const int row0 = k0 + w + tile * TR;
+        const int nrows = min(TR, f.nr - row0);
+        __syncthreads();                 // previous tile fully written back / rinv visible
+        for (int idx = tid; idx < wpad * TR; idx += 256) {
+            int c = idx / TR, i = idx - c * TR;
+            Xs[c * LDX + i] = (c < w && i < nrows) ? P[(long long)(k0 + c) * ld + row0 + i] : 0.0;
         }
-        // substitution against the 16x16 diagonal chunk, values stay in registers
+        __syncthreads();
+        // ---- X L11^T = B, 16 columns at a time; warp owns rows [8*warp, 8*warp+8), 4 lanes per row
+        for (int c0 = 0; c0 < wpad; c0 += 16) {
+            double b00 = Xs[(c0 + 2 * q) * LDX + rw], b01 = Xs[(c0 + 2 * q + 1) * LDX + rw];
+            double b10 = Xs[(c0 + 8 + 2 * q) * LDX + rw], b11 = Xs[(c0 + 8 + 2 * q + 1) * LDX + rw];
+            for (int k4 = 0; k4 < c0; k4 += 4) {
+                const double a = -Xs[(k4 + q) * LDX + rw];
+                const double l0 = Ls[(k4 + q) * LDL + c0 + (lane >> 2)];
+                const double l1 = Ls[(k4 + q) * LDL + c0 + 8 + (lane >> 2)];
+                dmma884(b00, b01, a, l0);
+                dmma884(b10, b11, a, l1);
+            }
+            // substitution against the 16x16 diagonal chunk, values stay in registers
 #pragma unroll
-        for (int p = 0; p < 16; p++) {
-            const int owner = (p & 7) >> 1;
-            double cand = (p < 8) ? ((p & 1) ? b01 : b00) : ((p & 1) ? b11 : b10);
-            cand *= rinv[c0 + p];
-            const double xp = __shfl_sync(0xffffffffu, cand, (lane & ~3) | owner);
-            if (q == owner) { if (p < 8) { if (p & 1) b01 = xp; else b00 = xp; } else { if (p & 1) b11 = xp; else b10 = xp; } }
-            const double* lp = Ls + (c0 + p) * LDL + c0;
-            if (2 * q > p) b00 -= xp * lp[2 * q];
-            if (2 * q + 1 > p) b01 -= xp * lp[2 * q + 1];
-            if (8 + 2 * q > p) b10 -= xp * lp[8 + 2 * q];
-            if (8 + 2 * q + 1 > p) b11 -= xp * lp[8 + 2 * q + 1];
+            for (int p = 0; p < 16; p++) {
+                const int owner = (p & 7) >> 1;
+                double cand = (p < 8) ? ((p & 1) ? b01 : b00) : ((p & 1) ? b11 : b10);
+                cand *= rinv[c0 + p];
+                const double xp = __shfl_sync(0xffffffffu, cand, (lane & ~3) | owner);
+                if (q == owner) { if (p < 8) { if (p & 1) b01 = xp; else b00 = xp; } else { if (p & 1) b11 = xp; else b10 = xp; } }
+                const double* lp = Ls + (c0 + p) * LDL + c0;
+                if (2 * q > p) b00 -= xp * lp[2 * q];
+                if (2 * q + 1 > p) b01 -= xp * lp[2 * q + 1];
+                if (8 + 2 * q > p) b10 -= xp * lp[8 + 2 * q];
+                if (8 + 2 * q + 1 > p) b11 -= xp * lp[8 + 2 * q + 1];
+            }
+            Xs[(c0 + 2 * q) * LDX + rw] = b00;
+            Xs[(c0 + 2 * q + 1) * LDX + rw] = b01;
+            Xs[(c0 + 8 + 2 * q) * LDX + rw] = b10;
+            Xs[(c0 + 8 + 2 * q + 1) * LDX + rw] = b11;
+            __syncwarp();
         }
-        Xs[(c0 + 2 * q) * LDX + rw] = b00;
-        Xs[(c0 + 2 * q + 1) * LDX + rw] = b01;
-        Xs[(c0 + 8 + 2 * q) * LDX + rw] = b10;
-        Xs[(c0 + 8 + 2 * q + 1) * LDX + rw] = b11;
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int idx = tid; idx < w * TR; idx += 256) {
-        int c = idx / TR, i = idx - c * TR;
-        if (i < nrows) P[(long long)(k0 + c) * ld + row0 + i] = Xs[c * LDX + i];
+        __syncthreads();
+        for (int idx = tid; idx < w * TR; idx += 256) {
+            int c = idx / TR, i = idx - c * TR;
+            if (i < nrows) P[(long long)(k0 + c) * ld + row0 + i] = Xs[c * LDX + i];
+        }
     }
 }
 
@@ -527,6 +599,202 @@ __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const
     }
 }
 
+// ---- large fronts: the same solves split over many CTAs, one 128-column block step at a time ------------------
+constexpr int SOLVE_FT = 256;    // rows per CTA in the forward update
+constexpr int SOLVE_BT = 1024;   // rows per CTA in the backward (transposed) update
+
+// forward: t = [x(cols); 0] + children's update vectors
+__global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list, const FrontD* __restrict__ F,
+                                                    const int* __restrict__ child_idx, const int* __restrict__ rel,
+                                                    double* __restrict__ T, long long tstride, const double* __restrict__ X,
+                                                    long long xstride) {
+    const FrontD f = F[list[blockIdx.x]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    const double* x = X + blockIdx.y * xstride + f.col0;
+    const int nr = f.nr, nc = f.nc, tid = threadIdx.x;
+    for (int i = tid; i < nr; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
+    __syncthreads();
+    for (int q = 0; q < f.nchild; q++) {
+        const FrontD fc = F[child_idx[f.childptr + q]];
+        const int mc = fc.nr - fc.nc;
+        const int* rl = rel + fc.reloff;
+        const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
+        for (int i = tid; i < mc; i += 256) t[rl[i]] += tc[i];
+        __syncthreads();
+    }
+}
+// backward: t = x(rows of the front)
+__global__ void __launch_bounds__(256) k_bwd_gather(const int* __restrict__ list, const FrontD* __restrict__ F,
+                                                    const int* __restrict__ rows, double* __restrict__ T, long long tstride,
+                                                    const double* __restrict__ X, long long xstride) {
+    const FrontD f = F[list[blockIdx.x]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    const double* xg = X + blockIdx.y * xstride;
+    const int* rw = rows + f.rowptr;
+    for (int i = threadIdx.x; i < f.nr; i += 256) t[i] = xg[rw[i]];
+}
+
+// forward, block kb: solve the (<=128)^2 diagonal block for t[k0..k0+w)
+__global__ void __launch_bounds__(256) k_fwd_diag(const int* __restrict__ gfront, int kb, const FrontD* __restrict__ F,
+                                                  const double* __restrict__ L, double* __restrict__ T, long long tstride,
+                                                  double* __restrict__ X, long long xstride) {
+    __shared__ double D[CB][CB + 1];
+    __shared__ double ts[NB];
+    const FrontD f = F[gfront[blockIdx.x]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    double* x = X + blockIdx.y * xstride + f.col0;
+    const double* P = L + f.loff;
+    const int ld = f.ld, tid = threadIdx.x, lane = tid & 31;
+    const int k0 = kb * NB, w = min(NB, f.nc - k0);
+    if (tid < w) ts[tid] = t[k0 + tid];
+    __syncthreads();
+    for (int b0 = 0; b0 < w; b0 += CB) {
+        const int wb = min(CB, w - b0);
+        for (int idx = tid; idx < wb * wb; idx += 256) {
+            int c = idx / wb, r = idx - c * wb;
+            D[r][c] = (r >= c) ? P[(long long)(k0 + b0 + c) * ld + k0 + b0 + r] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double v = (lane < wb) ? ts[b0 + lane] : 0.0;
+            for (int qq = 0; qq < wb; qq++) {
+                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
+                if (lane == qq) v = xq;
+                else if (lane > qq && lane < wb) v -= xq * D[lane][qq];
+            }
+            if (lane < wb) ts[b0 + lane] = v;
+        }
+        __syncthreads();
+        // rows of this 128-block below the sub-block
+        for (int r = b0 + wb + tid; r < w; r += 256) {
+            double acc = ts[r];
+            const double* col = P + (long long)(k0 + b0) * ld + k0 + r;
+            for (int qq = 0; qq < wb; qq++) acc -= col[(long long)qq * ld] * ts[b0 + qq];
+            ts[r] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid < w) { t[k0 + tid] = ts[tid]; x[k0 + tid] = ts[tid]; }
+}
+// forward, block kb: t[r] -= L[r, blk] * x_blk for a 256-row tile of the rows below the block
+__global__ void __launch_bounds__(256) k_fwd_upd(const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
+                                                 int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
+                                                 double* __restrict__ T, long long tstride) {
+    __shared__ double xs[NB];
+    const int g = find_group(gprefix, ngroups, blockIdx.x);
+    const int tile = blockIdx.x - gprefix[g];
+    const FrontD f = F[gfront[g]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    const double* P = L + f.loff;
+    const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x;
+    if (tid < w) xs[tid] = t[k0 + tid];
+    __syncthreads();
+    const int r = k0 + w + tile * SOLVE_FT + tid;
+    if (r < f.nr) {
+        const double* col = P + (long long)k0 * f.ld + r;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int q = 0;
+        for (; q + 16 <= w; q += 16) {          // 16 independent loads in flight per thread
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = col[(long long)(q + j) * f.ld];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                a0 += v[j] * xs[q + j]; a1 += v[j + 1] * xs[q + j + 1];
+                a2 += v[j + 2] * xs[q + j + 2]; a3 += v[j + 3] * xs[q + j + 3];
+            }
+        }
+        for (; q < w; q++) a0 += col[(long long)q * f.ld] * xs[q];
+        t[r] -= (a0 + a1) + (a2 + a3);
+    }
+}
+// backward, block kb: partial[q] = sum over a 1024-row tile of the rows below the block of L[r, k0+q] * t[r]
+__global__ void __launch_bounds__(256) k_bwd_upd(const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
+                                                 int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
+                                                 const double* __restrict__ T, long long tstride, double* __restrict__ part,
+                                                 long long pstride) {
+    __shared__ double tsm[SOLVE_BT];
+    const int g = find_group(gprefix, ngroups, blockIdx.x);
+    const int tile = blockIdx.x - gprefix[g];
+    const FrontD f = F[gfront[g]];
+    const double* t = T + blockIdx.y * tstride + f.rowptr;
+    const double* P = L + f.loff;
+    const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = k0 + w + tile * SOLVE_BT, r1 = min(f.nr, r0 + SOLVE_BT);
+    for (int i = tid; i < r1 - r0; i += 256) tsm[i] = t[r0 + i];
+    __syncthreads();
+    double* out = part + blockIdx.y * pstride + (long long)blockIdx.x * NB;
+    for (int q = warp; q < w; q += 8) {
+        const double* col = P + (long long)(k0 + q) * f.ld + r0;
+        double s0 = 0, s1 = 0;
+        int i = lane;
+        const int nrow = r1 - r0;
+        for (; i + 224 < nrow; i += 256) {      // 8 independent loads in flight per lane
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = col[i + 32 * j];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) { s0 += v[j] * tsm[i + 32 * j]; s1 += v[j + 1] * tsm[i + 32 * (j + 1)]; }
+        }
+        for (; i < nrow; i += 32) s0 += col[i] * tsm[i];
+        double sv = s0 + s1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (lane == 0) out[q] = sv;
+    }
+}
+// backward, block kb: z = t_blk - sum of the tile partials (fixed order), then solve L11^T x = z
+__global__ void __launch_bounds__(256) k_bwd_diag(const int* __restrict__ gfront, const int* __restrict__ gprefix, int kb,
+                                                  const FrontD* __restrict__ F, const double* __restrict__ L,
+                                                  double* __restrict__ T, long long tstride, double* __restrict__ X,
+                                                  long long xstride, const double* __restrict__ part, long long pstride) {
+    __shared__ double D[CB][CB + 1];
+    __shared__ double zs[NB];
+    const FrontD f = F[gfront[blockIdx.x]];
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    double* x = X + blockIdx.y * xstride + f.col0;
+    const double* P = L + f.loff;
+    const int ld = f.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = kb * NB, w = min(NB, f.nc - k0);
+    const int tile0 = gprefix[blockIdx.x], tile1 = gprefix[blockIdx.x + 1];
+    if (tid < w) {
+        double z = t[k0 + tid];
+        const double* pp = part + blockIdx.y * pstride + tid;
+        for (int tl = tile0; tl < tile1; tl++) z -= pp[(long long)tl * NB];
+        zs[tid] = z;
+    }
+    __syncthreads();
+    const int nsb = (w + CB - 1) / CB;
+    for (int sbk = nsb - 1; sbk >= 0; sbk--) {
+        const int b0 = sbk * CB, wb = min(CB, w - b0);
+        for (int idx = tid; idx < wb * wb; idx += 256) {
+            int c = idx / wb, r = idx - c * wb;
+            D[r][c] = (r >= c) ? P[(long long)(k0 + b0 + c) * ld + k0 + b0 + r] : 0.0;
+        }
+        // contributions of the already solved rows of this 128-block (below the sub-block)
+        for (int qq = warp; qq < wb; qq += 8) {
+            const double* col = P + (long long)(k0 + b0 + qq) * ld + k0;
+            double sv = 0.0;
+            for (int r = b0 + wb + lane; r < w; r += 32) sv += col[r] * zs[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            if (lane == 0) zs[b0 + qq] -= sv;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double v = (lane < wb) ? zs[b0 + lane] : 0.0;
+            for (int qq = wb - 1; qq >= 0; qq--) {
+                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
+                if (lane == qq) v = xq;
+                else if (lane < qq) v -= xq * D[qq][lane];
+            }
+            if (lane < wb) zs[b0 + lane] = v;
+        }
+        __syncthreads();
+    }
+    if (tid < w) { t[k0 + tid] = zs[tid]; x[k0 + tid] = zs[tid]; }
+}
+
 __global__ void k_perm_gather(const double* __restrict__ B, long long ldB, const int* __restrict__ perm, int n,
                               double* __restrict__ X, long long ldX) {
     const double* b = B + blockIdx.y * ldB;
@@ -562,6 +830,8 @@ struct LevelSched {
     int small_off[3] = {0, 0, 0}, small_cnt[3] = {0, 0, 0}, small_maxnr[3] = {0, 0, 0};
     std::vector<Launch> panel, upd;   // per block step kb
     Launch syrk;
+    std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
+    int small_all_off = 0, small_all_cnt = 0;
 };
 
 class CholDevice {
@@ -580,6 +850,8 @@ public:
     EAItem* dea = nullptr;
     std::vector<LevelSched> levels;
     i64 solve_cols = 0;            // capacity (columns) of dT / dX
+    int max_solve_ctas = 1;        // most CTAs of one backward-update launch (sizes the partial-sum buffer)
+    double* dpart = nullptr;
     bool numeric = false, profiling = false;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> pev;  // profiling event pool
@@ -589,7 +861,7 @@ public:
         cudaSetDevice(device);
         cudaFree(dL); cudaFree(dW); cudaFree(dval); cudaFree(dT); cudaFree(dX); cudaFree(dBstage); cudaFree(damap); cudaFree(dF);
         cudaFree(drows); cudaFree(drel); cudaFree(dchild); cudaFree(dperm); cudaFree(dlevel_fronts);
-        cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag);
+        cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag); cudaFree(dpart);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -689,16 +961,52 @@ int CholDevice::init() {
             sched.push_back(run);
             la.ctas = run;
         };
+        LS.small_all_off = LS.small_off[0];
+        LS.small_all_cnt = LS.small_cnt[0] + LS.small_cnt[1] + LS.small_cnt[2];
+        LS.sfwd.resize(maxblk);
+        LS.sbwd.resize(maxblk);
         for (int kb = 0; kb < maxblk; kb++) {
-            std::vector<int> fr, cp, fu, cu;
+            std::vector<int> fs, cf, cb2;
             for (int s : bigs) {
                 const Front& f = P.fronts[s];
                 const int nblk = (f.nc + NB - 1) / NB;
                 if (kb >= nblk) continue;
                 const int w = std::min(NB, f.nc - kb * NB);
                 const int below = f.nr - (kb * NB + w);
+                fs.push_back(s);
+                cf.push_back((below + SOLVE_FT - 1) / SOLVE_FT);
+                cb2.push_back((below + SOLVE_BT - 1) / SOLVE_BT);
+            }
+            emit(LS.sfwd[kb], fs, cf);
+            emit(LS.sbwd[kb], fs, cb2);
+            max_solve_ctas = std::max(max_solve_ctas, LS.sbwd[kb].ctas);
+        }
+        for (int kb = 0; kb < maxblk; kb++) {
+            std::vector<int> fr, cp, fu, cu;
+            // panel CTAs: one per front for the diagonal block + solver CTAs that each factor the block redundantly
+            // and then walk over several 64-row tiles; the solver CTAs of a launch are capped near one wave (148 SMs)
+            long long tiles_total = 0;
+            int nact = 0;
+            for (int s : bigs) {
+                const Front& f = P.fronts[s];
+                if (kb >= (f.nc + NB - 1) / NB) continue;
+                const int w = std::min(NB, f.nc - kb * NB);
+                tiles_total += (f.nr - (kb * NB + w) + TR - 1) / TR;
+                nact++;
+            }
+            const long long budget = std::max<long long>(148 - nact, nact);
+            for (int s : bigs) {
+                const Front& f = P.fronts[s];
+                const int nblk = (f.nc + NB - 1) / NB;
+                if (kb >= nblk) continue;
+                const int w = std::min(NB, f.nc - kb * NB);
+                const int below = f.nr - (kb * NB + w);
+                const int ntiles = (below + TR - 1) / TR;
+                int nsolve = ntiles;
+                if (tiles_total > budget && ntiles > 0)
+                    nsolve = (int)std::min<long long>(ntiles, std::max<long long>(1, (budget * ntiles + tiles_total - 1) / tiles_total));
                 fr.push_back(s);
-                cp.push_back(1 + (below + TR - 1) / TR);
+                cp.push_back(1 + nsolve);
                 const int nrt = (f.nr + BT - 1) / BT;
                 long long tiles = 0;
                 for (int tj = kb + 1; tj < nblk; tj++) tiles += nrt - tj;
@@ -846,6 +1154,8 @@ int CholDevice::ensure_solve_ws(i64 cols) {
     const CholPlan& P = *plan;
     CUDA_TRY(cudaMalloc((void**)&dT, std::max<i64>((i64)P.rows.size() * cols, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dX, std::max<i64>((i64)P.n * cols, 1) * sizeof(double)));
+    cudaFree(dpart); dpart = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dpart, (size_t)max_solve_ctas * NB * cols * sizeof(double)));
     solve_cols = cols;
     return ST_OK;
 }
@@ -892,15 +1202,36 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         if (sys == 6) continue;  // D x = b with D = I
         if (do_perm) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dX, n, n);
+        const long long pstride = (long long)max_solve_ctas * NB;
         if (do_fwd)
             for (int l = 0; l < P.nlevels; l++) {
-                const int cnt = P.level_ptr[l + 1] - P.level_ptr[l];
-                k_fwd<<<dim3(cnt, nc), 256, 0, stream>>>(dlevel_fronts + P.level_ptr[l], dF, dchild, drel, dL, dT, tstride, dX, n);
+                const LevelSched& LS = levels[l];
+                if (LS.small_all_cnt)
+                    k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
+                if (!LS.panel.empty() && LS.panel[0].ng) {
+                    k_fwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, dchild, drel, dT, tstride, dX, n);
+                    for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
+                        const Launch& la = LS.sfwd[kb];
+                        k_fwd_diag<<<dim3(la.ng, nc), 256, 0, stream>>>(dsched + la.goff, (int)kb, dF, dL, dT, tstride, dX, n);
+                        if (la.ctas)
+                            k_fwd_upd<<<dim3(la.ctas, nc), 256, 0, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride);
+                    }
+                }
             }
         if (do_bwd)
             for (int l = P.nlevels - 1; l >= 0; l--) {
-                const int cnt = P.level_ptr[l + 1] - P.level_ptr[l];
-                k_bwd<<<dim3(cnt, nc), 256, 0, stream>>>(dlevel_fronts + P.level_ptr[l], dF, drows, dL, dT, tstride, dX, n);
+                const LevelSched& LS = levels[l];
+                if (!LS.panel.empty() && LS.panel[0].ng) {
+                    k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
+                    for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
+                        const Launch& la = LS.sbwd[kb];
+                        if (la.ctas)
+                            k_bwd_upd<<<dim3(la.ctas, nc), 256, 0, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride);
+                        k_bwd_diag<<<dim3(la.ng, nc), 256, 0, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dT, tstride, dX, n, dpart, pstride);
+                    }
+                }
+                if (LS.small_all_cnt)
+                    k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
             }
         if (do_perm) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
