@@ -440,11 +440,29 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
 
     // warp tile: 64 C-rows (MMA N dimension, 8 tiles) x 32 C-columns (MMA M dimension, 4 tiles)
     const int wr = (warp >> 2) * 64, wc = (warp & 3) * 32;
+    // Accumulators start from C (all loads issued up front, they land while the cp.async prologue runs) and the MMA
+    // adds (-A_j)(A_i)^T, so the epilogue is stores only: a load-subtract-store epilogue serialises 32 dependent
+    // global round trips per thread (64 % of the stall samples of the first version, profiles/r01_ncu_k_update.txt).
     double acc[4][8][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 4; i++) {
+        const int c = wc + i * 8 + (lane >> 2);
+        const bool cv = c < ccols && rowJ + c >= lo;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < 8; j++) {
+            const int r = wr + j * 8 + 2 * (lane & 3);
+            const double* p = C + (long long)c * ldc + r;
+            const bool v0 = cv && r < crows && rowI + r >= lo && (!diag || r >= c);
+            const bool v1 = cv && r + 1 < crows && rowI + r + 1 >= lo && (!diag || r + 1 >= c);
+            if (v0 && v1) {
+                const double2 x = *reinterpret_cast<const double2*>(p);
+                acc[i][j][0] = x.x; acc[i][j][1] = x.y;
+            } else {
+                acc[i][j][0] = v0 ? p[0] : 0.0;
+                acc[i][j][1] = v1 ? p[1] : 0.0;
+            }
+        }
+    }
 
     const int nkt = (K + BK - 1) / BK;
 #pragma unroll
@@ -471,7 +489,7 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
         for (int kk = 0; kk < BK; kk += 4) {
             double am[4], bn[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++) am[i] = bs[(kk + (lane & 3)) * LDT + wc + i * 8 + (lane >> 2)];
+            for (int i = 0; i < 4; i++) am[i] = -bs[(kk + (lane & 3)) * LDT + wc + i * 8 + (lane >> 2)];
 #pragma unroll
             for (int j = 0; j < 8; j++) bn[j] = as[(kk + (lane & 3)) * LDT + wr + j * 8 + (lane >> 2)];
 #pragma unroll
@@ -492,12 +510,9 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
             double* p = C + (long long)c * ldc + r;
             const bool v0 = r < crows && rowI + r >= lo && (!diag || r >= c);
             const bool v1 = r + 1 < crows && rowI + r + 1 >= lo && (!diag || r + 1 >= c);
-            if (v0 && v1) {
-                double2 x = *reinterpret_cast<double2*>(p);
-                x.x -= acc[i][j][0]; x.y -= acc[i][j][1];
-                *reinterpret_cast<double2*>(p) = x;
-            } else if (v0) p[0] -= acc[i][j][0];
-            else if (v1) p[1] -= acc[i][j][1];
+            if (v0 && v1) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+            else if (v0) p[0] = acc[i][j][0];
+            else if (v1) p[1] = acc[i][j][1];
         }
     }
 }
