@@ -382,26 +382,34 @@ __global__ void __launch_bounds__(256) k_diag_writeback(const int* __restrict__ 
 //   mode 0: in-panel trailing update after block column kb (target columns inside the panel)
 //   mode 1: Schur complement into the update matrix (K = nc)
 // ---------------------------------------------------------------------------------------------------
+constexpr int UPD_THREADS = 256;   // 8 warps (4 x 2), each a 32 x 32 piece of a 128 x 64 tile; 2 CTAs per SM
+constexpr int BTN = 64;            // tile columns
+constexpr int LDTB = BTN + 4;      // smem stride of the column-block operand
+
+template <int ROWS, int LDS_>
 __device__ __forceinline__ void load_tile_async(double* dst, const double* __restrict__ src, int ld, int rows_valid,
                                                 int kcols_valid, int tid) {
-    // BT rows x BK columns, 16-byte chunks: 64 chunks per column, 1024 chunks, 4 per thread
+    // ROWS rows x BK columns in 16-byte chunks
+    constexpr int CPC = ROWS / 2;                      // chunks per column
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int ch = tid + i * 256;
-        const int c = ch >> 6, r = (ch & 63) * 2;
+    for (int i = 0; i < CPC * BK / UPD_THREADS; i++) {
+        const int ch = tid + i * UPD_THREADS;
+        const int c = ch / CPC, r = (ch % CPC) * 2;
         int bytes = 0;
         if (c < kcols_valid) bytes = (r + 1 < rows_valid) ? 16 : ((r < rows_valid) ? 8 : 0);
         const double* s = (bytes > 0) ? src + (long long)c * ld + r : src;
-        cp_async16(dst + c * LDT + r, s, bytes);
+        cp_async16(dst + c * LDS_ + r, s, bytes);
     }
 }
 
-__global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfront, const int* __restrict__ gprefix,
-                                                   int ngroups, int mode, int kb, const FrontD* __restrict__ F,
-                                                   double* __restrict__ L, double* __restrict__ W) {
+// tile decode shared by host counting and the kernel: column tiles of 64, row tiles of 128, lower triangle only:
+// column tile cj pairs with row tiles ti >= cj/2
+__global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const int* __restrict__ gfront, const int* __restrict__ gprefix,
+                                                           int ngroups, int mode, int kb, const FrontD* __restrict__ F,
+                                                           double* __restrict__ L, double* __restrict__ W) {
     extern __shared__ double sm[];
-    double* As = sm;                          // [STAGES][BK][LDT]   rows of the tile's row block
-    double* Bs = sm + STAGES * BK * LDT;      // [STAGES][BK][LDT]   rows of the tile's column block
+    double* As = sm;                          // [STAGES][BK][LDT]    rows of the tile's row block (128)
+    double* Bs = sm + STAGES * BK * LDT;      // [STAGES][BK][LDTB]   rows of the tile's column block (64)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = find_group(gprefix, ngroups, blockIdx.x);
     int t = blockIdx.x - gprefix[g];
@@ -410,50 +418,50 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
     const double* P = L + f.loff;
     int rowI, rowJ, k0, K, ldc, crows, ccols, lo;
     double* C;
-    bool diag;
     if (mode == 0) {
         const int nrt = (nr + BT - 1) / BT;
-        int tj = kb + 1;
-        while (t >= nrt - tj) { t -= nrt - tj; tj++; }
-        const int ti = tj + t;
-        rowI = ti * BT; rowJ = tj * BT;
+        int cj = 2 * (kb + 1);
+        while (t >= nrt - (cj >> 1)) { t -= nrt - (cj >> 1); cj++; }
+        const int ti = (cj >> 1) + t;
+        rowI = ti * BT; rowJ = cj * BTN;
         k0 = kb * NB; K = min(NB, nc - k0);
         C = L + f.loff + rowI + (long long)rowJ * ld; ldc = ld;
-        crows = min(BT, nr - rowI); ccols = min(BT, nc - rowJ);
-        lo = 0; diag = (ti == tj);
+        crows = min(BT, nr - rowI); ccols = min(BTN, nc - rowJ);
+        lo = 0;
     } else {
         const int r0 = nc - (nc & 1);
         const int mu = nr - r0, T = (mu + BT - 1) / BT;
         const int ldu = (mu + 1) & ~1;
-        int tj = 0;
-        while (t >= T - tj) { t -= T - tj; tj++; }
-        const int ti = tj + t;
-        rowI = r0 + ti * BT; rowJ = r0 + tj * BT;
+        int cj = 0;
+        while (t >= T - (cj >> 1)) { t -= T - (cj >> 1); cj++; }
+        const int ti = (cj >> 1) + t;
+        rowI = r0 + ti * BT; rowJ = r0 + cj * BTN;
         k0 = 0; K = nc;
-        C = W + f.uoff + (long long)ti * BT + (long long)tj * BT * ldu; ldc = ldu;
-        crows = min(BT, nr - rowI); ccols = min(BT, nr - rowJ);
-        lo = nc; diag = (ti == tj);
+        C = W + f.uoff + (long long)ti * BT + (long long)cj * BTN * ldu; ldc = ldu;
+        crows = min(BT, nr - rowI); ccols = min(BTN, nr - rowJ);
+        lo = nc;
     }
+    const int dshift = rowJ - rowI;            // entry (r, c) of the tile is on/below the diagonal iff r >= c + dshift
     const double* A = P + rowI + (long long)k0 * ld;
     const double* B = P + rowJ + (long long)k0 * ld;
     const int brows = ccols;
 
-    // warp tile: 64 C-rows (MMA N dimension, 8 tiles) x 32 C-columns (MMA M dimension, 4 tiles)
-    const int wr = (warp >> 2) * 64, wc = (warp & 3) * 32;
+    // warp tile: 32 C-rows (MMA N dimension, 4 tiles) x 32 C-columns (MMA M dimension, 4 tiles)
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
     // Accumulators start from C (all loads issued up front, they land while the cp.async prologue runs) and the MMA
-    // adds (-A_j)(A_i)^T, so the epilogue is stores only: a load-subtract-store epilogue serialises 32 dependent
-    // global round trips per thread (64 % of the stall samples of the first version, profiles/r01_ncu_k_update.txt).
-    double acc[4][8][2];
+    // adds (-A_j)(A_i)^T, so the epilogue is stores only: a load-subtract-store epilogue serialises dependent
+    // global round trips (64 % of the stall samples of the first version, profiles/).
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int c = wc + i * 8 + (lane >> 2);
         const bool cv = c < ccols && rowJ + c >= lo;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
             const int r = wr + j * 8 + 2 * (lane & 3);
             const double* p = C + (long long)c * ldc + r;
-            const bool v0 = cv && r < crows && rowI + r >= lo && (!diag || r >= c);
-            const bool v1 = cv && r + 1 < crows && rowI + r + 1 >= lo && (!diag || r + 1 >= c);
+            const bool v0 = cv && r < crows && rowI + r >= lo && r >= c + dshift;
+            const bool v1 = cv && r + 1 < crows && rowI + r + 1 >= lo && r + 1 >= c + dshift;
             if (v0 && v1) {
                 const double2 x = *reinterpret_cast<const double2*>(p);
                 acc[i][j][0] = x.x; acc[i][j][1] = x.y;
@@ -468,8 +476,8 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < nkt) {
-            load_tile_async(As + s * BK * LDT, A + (long long)s * BK * ld, ld, crows, K - s * BK, tid);
-            load_tile_async(Bs + s * BK * LDT, B + (long long)s * BK * ld, ld, brows, K - s * BK, tid);
+            load_tile_async<BT, LDT>(As + s * BK * LDT, A + (long long)s * BK * ld, ld, crows, K - s * BK, tid);
+            load_tile_async<BTN, LDTB>(Bs + s * BK * LDTB, B + (long long)s * BK * ld, ld, brows, K - s * BK, tid);
         }
         cp_async_commit();
     }
@@ -479,23 +487,23 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
         const int nk = kt + STAGES - 1;
         if (nk < nkt) {
             const int s = nk % STAGES;
-            load_tile_async(As + s * BK * LDT, A + (long long)nk * BK * ld, ld, crows, K - nk * BK, tid);
-            load_tile_async(Bs + s * BK * LDT, B + (long long)nk * BK * ld, ld, brows, K - nk * BK, tid);
+            load_tile_async<BT, LDT>(As + s * BK * LDT, A + (long long)nk * BK * ld, ld, crows, K - nk * BK, tid);
+            load_tile_async<BTN, LDTB>(Bs + s * BK * LDTB, B + (long long)nk * BK * ld, ld, brows, K - nk * BK, tid);
         }
         cp_async_commit();
         const double* as = As + (kt % STAGES) * BK * LDT;
-        const double* bs = Bs + (kt % STAGES) * BK * LDT;
+        const double* bs = Bs + (kt % STAGES) * BK * LDTB;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double am[4], bn[8];
+            double am[4], bn[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) am[i] = -bs[(kk + (lane & 3)) * LDT + wc + i * 8 + (lane >> 2)];
+            for (int i = 0; i < 4; i++) am[i] = -bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)];
 #pragma unroll
-            for (int j = 0; j < 8; j++) bn[j] = as[(kk + (lane & 3)) * LDT + wr + j * 8 + (lane >> 2)];
+            for (int j = 0; j < 4; j++) bn[j] = as[(kk + (lane & 3)) * LDT + wr + j * 8 + (lane >> 2)];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], am[i], bn[j]);
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], am[i], bn[j]);
         }
     }
     cp_async_wait<0>();
@@ -505,11 +513,11 @@ __global__ void __launch_bounds__(256, 1) k_update(const int* __restrict__ gfron
         const int c = wc + i * 8 + (lane >> 2);
         if (c >= ccols || rowJ + c < lo) continue;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
             const int r = wr + j * 8 + 2 * (lane & 3);
             double* p = C + (long long)c * ldc + r;
-            const bool v0 = r < crows && rowI + r >= lo && (!diag || r >= c);
-            const bool v1 = r + 1 < crows && rowI + r + 1 >= lo && (!diag || r + 1 >= c);
+            const bool v0 = r < crows && rowI + r >= lo && r >= c + dshift;
+            const bool v1 = r + 1 < crows && rowI + r + 1 >= lo && r + 1 >= c + dshift;
             if (v0 && v1) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
             else if (v0) p[0] = acc[i][j][0];
             else if (v1) p[1] = acc[i][j][1];
@@ -895,7 +903,7 @@ public:
 };
 
 static constexpr size_t SMEM_PANEL = (size_t)(NB * LDL + NB * LDX + NB) * sizeof(double);
-static constexpr size_t SMEM_UPDATE = (size_t)(2 * STAGES * BK * LDT) * sizeof(double);
+static constexpr size_t SMEM_UPDATE = (size_t)(STAGES * BK * (LDT + LDTB)) * sizeof(double);
 
 int CholDevice::init() {
     const CholPlan& P = *plan;
@@ -1022,9 +1030,9 @@ int CholDevice::init() {
                     nsolve = (int)std::min<long long>(ntiles, std::max<long long>(1, (budget * ntiles + tiles_total - 1) / tiles_total));
                 fr.push_back(s);
                 cp.push_back(1 + nsolve);
-                const int nrt = (f.nr + BT - 1) / BT;
+                const int nrt = (f.nr + BT - 1) / BT, ncolt = (f.nc + BTN - 1) / BTN;
                 long long tiles = 0;
-                for (int tj = kb + 1; tj < nblk; tj++) tiles += nrt - tj;
+                for (int cj = 2 * (kb + 1); cj < ncolt; cj++) tiles += nrt - (cj >> 1);
                 if (tiles > 0) { fu.push_back(s); cu.push_back((int)tiles); }
             }
             emit(LS.panel[kb], fr, cp);
@@ -1035,10 +1043,12 @@ int CholDevice::init() {
             for (int s : bigs) {
                 const Front& f = P.fronts[s];
                 if (f.nr == f.nc) continue;
-                const int r0 = f.nc - (f.nc & 1);
-                const long long T = (f.nr - r0 + BT - 1) / BT;
+                const int r0 = f.nc - (f.nc & 1), mu = f.nr - r0;
+                const int T = (mu + BT - 1) / BT, ncolt = (mu + BTN - 1) / BTN;
+                long long tiles = 0;
+                for (int cj = 0; cj < ncolt; cj++) tiles += T - (cj >> 1);
                 fr.push_back(s);
-                cnt.push_back((int)(T * (T + 1) / 2));
+                cnt.push_back((int)tiles);
             }
             emit(LS.syrk, fr, cnt);
         }
@@ -1121,14 +1131,14 @@ int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTim
             const Launch& lu = LS.upd[kb];
             if (lu.ctas) {
                 prof_begin(3);
-                k_update<<<lu.ctas, 256, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
                                                                 (int)kb, dF, dL, dW);
                 prof_end();
             }
         }
         if (LS.syrk.ctas) {
             prof_begin(3);
-            k_update<<<LS.syrk.ctas, 256, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+            k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
                                                                  LS.syrk.ng, 1, 0, dF, dL, dW);
             prof_end();
         }
