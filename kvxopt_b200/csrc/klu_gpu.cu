@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
     const double* axg = Axs + (long long)blockIdx.x * 32;
     int bad = 0;
     const int srow = tid >> 4, spc = (tid & 15) * 2;
-    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0, t_wait = 0, t_bar = 0, t_issue = 0, t_apply = 0, tC = 0;
+    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0;
     auto stage_batch = [&](long long bi, int ls0, int ls1, int buf) {
         double* dst = stage + (long long)buf * KLU_STAGE_DOUBLES;
         if (ls0 >= 0) klu_cp_async16(dst + srow * 32 + spc, lug + (long long)ls0 * Bp + spc);
@@ -227,11 +227,8 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
         if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
         int buf = 0;
         for (int c = 0; c < nb; c++) {
-            if (dbg) tC = clock64();
             asm volatile("cp.async.wait_group %0;" ::"n"(KLU_STAGES - 2));
-            if (dbg) { long long tD = clock64(); t_wait += tD - tC; tC = tD; }
             __syncthreads();
-            if (dbg) { long long tD = clock64(); t_bar += tD - tC; tC = tD; }
             const int nc = c + KLU_STAGES - 1;
             int nbuf = buf + KLU_STAGES - 1; if (nbuf >= KLU_STAGES) nbuf -= KLU_STAGES;
             if (nc < nb) {
@@ -241,7 +238,6 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
                 stage_batch(c0 + nc, rsn[srow], rsn[srow + 32], nbuf);
             }
             asm volatile("cp.async.commit_group;");
-            if (dbg) { long long tD = clock64(); t_issue += tD - tC; tC = tD; }
             if (active) {
                 const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
                 const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
@@ -253,19 +249,31 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
                 for (int sgi = 1; sgi <= nseg; sgi++) {
                     const unsigned sd = rec[sgi];
                     const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
+                    int t = r0 + 4 * sub;
+                    // operands of the first chunk are fetched before the team barrier (they do not depend on it)
+                    const bool first = t + 4 <= r1;
+                    int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+                    double l0v = 0, l1v = 0, l2v = 0, l3v = 0;
+                    if (first) {
+                        d0 = dd[t] * 32; d1 = dd[t + 1] * 32; d2 = dd[t + 2] * 32; d3 = dd[t + 3] * 32;
+                        l0v = sb[t * 32]; l1v = sb[(t + 1) * 32]; l2v = sb[(t + 2) * 32]; l3v = sb[(t + 3) * 32];
+                    }
                     team_sync();
                     const double ujk = x[(sd >> 16) * 32];
-                    int t = r0 + 4 * sub;
-                    for (; t + 4 <= r1; t += 4 * T) {
-                        const int d0 = dd[t] * 32, d1 = dd[t + 1] * 32, d2 = dd[t + 2] * 32, d3 = dd[t + 3] * 32;
-                        const double l0v = sb[t * 32], l1v = sb[(t + 1) * 32], l2v = sb[(t + 2) * 32], l3v = sb[(t + 3) * 32];
+                    if (first) {
                         const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
                         x[d0] = x0 - l0v * ujk; x[d1] = x1 - l1v * ujk; x[d2] = x2 - l2v * ujk; x[d3] = x3 - l3v * ujk;
+                        t += 4 * T;
+                    }
+                    for (; t + 4 <= r1; t += 4 * T) {
+                        const int e0 = dd[t] * 32, e1 = dd[t + 1] * 32, e2 = dd[t + 2] * 32, e3 = dd[t + 3] * 32;
+                        const double m0 = sb[t * 32], m1 = sb[(t + 1) * 32], m2 = sb[(t + 2) * 32], m3 = sb[(t + 3) * 32];
+                        const double x0 = x[e0], x1 = x[e1], x2 = x[e2], x3 = x[e3];
+                        x[e0] = x0 - m0 * ujk; x[e1] = x1 - m1 * ujk; x[e2] = x2 - m2 * ujk; x[e3] = x3 - m3 * ujk;
                     }
                     for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;      // tail (< 4 rows) of the warp that owns it
                 }
             }
-            if (dbg) { long long tD = clock64(); t_apply += tD - tC; }
             if (++buf == KLU_STAGES) buf = 0;
         }
         asm volatile("cp.async.wait_group 0;");
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
         }
         if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; }
     }
-    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = t_wait; dbg[5] = t_bar; dbg[6] = t_issue; dbg[7] = t_apply; }
+    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; }
     if (bad) status[b] = ST_SINGULAR;
 }
 
@@ -578,7 +586,7 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     if (ddbg) {
         long long h[8] = {0};
         cudaMemcpy(h, ddbg, sizeof h, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld) | warp 0: wait %lld barrier %lld issue %lld apply %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld)\n", h[0], h[1], h[2], h[3]);
     }
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_h2d = ms;
