@@ -122,6 +122,26 @@ b200s_status b200s_chol_get_perm(const b200s_chol* F, b200s_int* perm_out);
 b200s_status b200s_chol_get_super(const b200s_chol* F, b200s_int* super_out, b200s_int* rowptr_out,
                                   b200s_int* rows_out /* may be NULL to query sizes only */);
 
+/* ---- building blocks of the multi-GPU (subtree-to-subcube) factorization; no reference counterpart ----------
+ * One process per GPU holds the same plan.  b200s_chol_set_owned marks the fronts this process factors (bytes,
+ * nsuper of them; NULL = all).  The factorization is stepped level by level: begin (upload + assemble), one call
+ * per level (kernels are enqueued on the handle's stream; non-owned fronts are skipped), end (synchronise, minor).
+ * Between levels the caller moves update matrices of fronts whose parent lives on another GPU: they sit at
+ * W_dev[uoff[s] .. uoff[s]+usize[s]) on every process (identical layout), panels at L_dev[loff[s] .. +lsize[s]).
+ * kvxopt_b200/dist.py drives this with torch.distributed (NCCL send/recv over NVLink). */
+b200s_status b200s_chol_set_owned(b200s_chol* F, const unsigned char* owned);
+b200s_status b200s_chol_factor_begin(b200s_chol* F, const double* val, int val_on_device);
+b200s_status b200s_chol_factor_level(b200s_chol* F, b200s_int level);
+b200s_status b200s_chol_factor_end(b200s_chol* F, b200s_int* minor_out);
+b200s_status b200s_chol_sync(b200s_chol* F);             /* wait for the handle's stream */
+/* per front (arrays of nsuper, any may be NULL); offsets and sizes in doubles */
+b200s_status b200s_chol_front_layout(const b200s_chol* F, b200s_int* parent, b200s_int* level, b200s_int* ncols,
+                                     b200s_int* nrows, b200s_int* loff, b200s_int* lsize, b200s_int* uoff,
+                                     b200s_int* usize);
+b200s_status b200s_chol_device_buffers(b200s_chol* F, double** L_dev, double** W_dev);
+/* after the panels of all fronts have been gathered into L_dev: declare the factor numeric so that solves run */
+b200s_status b200s_chol_set_numeric(b200s_chol* F, int numeric, b200s_int minor);
+
 void b200s_chol_free(b200s_chol* F);     /* capsule destructor (src/C/cholmod.c:210-214) */
 void b200s_free(void* p);
 

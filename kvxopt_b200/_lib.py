@@ -59,6 +59,14 @@ SIGNATURES = {
     "b200s_chol_set_profiling": (C.c_int, vp, C.c_int),
     "b200s_chol_get_perm": (C.c_int, vp, p_i64),
     "b200s_chol_get_super": (C.c_int, vp, p_i64, p_i64, p_i64),
+    "b200s_chol_set_owned": (C.c_int, vp, C.c_char_p),
+    "b200s_chol_factor_begin": (C.c_int, vp, vp, C.c_int),
+    "b200s_chol_factor_level": (C.c_int, vp, i64),
+    "b200s_chol_factor_end": (C.c_int, vp, p_i64),
+    "b200s_chol_sync": (C.c_int, vp),
+    "b200s_chol_front_layout": (C.c_int, vp, p_i64, p_i64, p_i64, p_i64, p_i64, p_i64, p_i64, p_i64),
+    "b200s_chol_device_buffers": (C.c_int, vp, C.POINTER(vp), C.POINTER(vp)),
+    "b200s_chol_set_numeric": (C.c_int, vp, C.c_int, i64),
     "b200s_chol_free": (None, vp),
     "b200s_free": (None, vp),
     "b200s_grid_nd_perm": (C.c_int, i64, i64, i64, i64, p_i64),

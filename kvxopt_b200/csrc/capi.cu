@@ -95,17 +95,22 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
     return B200S_OK;
 }
 
-static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_device, b200s_int* minor_out) {
-    if (!F) return B200S_INVALID;
-    F->numeric = false;
-    if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
-    if (!val && F->plan.nnzA > 0) return B200S_INVALID;
+static b200s_status ensure_device(b200s_chol* F) {
     if (!F->dev) {
         int st = ST_OK;
         F->dev = chol_device_create(F->plan, F->opts, F->device, &st);
         if (!F->dev) return (b200s_status)st;
         chol_device_set_profiling(F->dev, F->profiling);
     }
+    return B200S_OK;
+}
+
+static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_device, b200s_int* minor_out) {
+    if (!F) return B200S_INVALID;
+    F->numeric = false;
+    if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
+    if (!val && F->plan.nnzA > 0) return B200S_INVALID;
+    { b200s_status es = ensure_device(F); if (es != B200S_OK) return es; }
     i64 minor = F->plan.n;
     int st = chol_device_factorize(F->dev, val, on_device, &minor, &F->times);
     F->minor = minor;
@@ -118,6 +123,76 @@ b200s_status b200s_chol_factorize(b200s_chol* F, const double* val, b200s_int* m
 }
 b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200s_int* minor_out) {
     return factorize_impl(F, val_dev, true, minor_out);
+}
+
+// ---- level-stepped factorization and front ownership (multi-GPU subtree-to-subcube building blocks) ----------
+b200s_status b200s_chol_set_owned(b200s_chol* F, const unsigned char* owned) {
+    if (!F) return B200S_INVALID;
+    if (F->plan.n == 0) return B200S_OK;
+    b200s_status es = ensure_device(F);
+    if (es != B200S_OK) return es;
+    return (b200s_status)chol_device_set_owned(F->dev, owned);
+}
+b200s_status b200s_chol_factor_begin(b200s_chol* F, const double* val, int val_on_device) {
+    if (!F) return B200S_INVALID;
+    F->numeric = false;
+    if (F->plan.n == 0) return B200S_OK;
+    if (!val && F->plan.nnzA > 0) return B200S_INVALID;
+    b200s_status es = ensure_device(F);
+    if (es != B200S_OK) return es;
+    return (b200s_status)chol_device_factor_begin(F->dev, val, val_on_device != 0);
+}
+b200s_status b200s_chol_factor_level(b200s_chol* F, b200s_int level) {
+    if (!F || !F->dev) return B200S_INVALID;
+    return (b200s_status)chol_device_factor_level(F->dev, (int)level);
+}
+b200s_status b200s_chol_factor_end(b200s_chol* F, b200s_int* minor_out) {
+    if (!F) return B200S_INVALID;
+    if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
+    if (!F->dev) return B200S_INVALID;
+    i64 minor = F->plan.n;
+    int st = chol_device_factor_end(F->dev, &minor, &F->times);
+    F->minor = minor;
+    if (minor_out) *minor_out = minor;
+    F->numeric = (st == ST_OK);
+    return (b200s_status)st;
+}
+b200s_status b200s_chol_sync(b200s_chol* F) {
+    if (!F) return B200S_INVALID;
+    if (!F->dev) return B200S_OK;
+    return (b200s_status)chol_device_sync(F->dev);
+}
+b200s_status b200s_chol_front_layout(const b200s_chol* F, b200s_int* parent, b200s_int* level, b200s_int* ncols, b200s_int* nrows,
+                                     b200s_int* loff, b200s_int* lsize, b200s_int* uoff, b200s_int* usize) {
+    if (!F) return B200S_INVALID;
+    const CholPlan& P = F->plan;
+    for (size_t s = 0; s < P.fronts.size(); s++) {
+        const Front& f = P.fronts[s];
+        const i64 m = f.nr - f.nc, mu = m + (f.nc & 1), ldu = (mu + 1) & ~(i64)1;
+        if (parent) parent[s] = f.parent;
+        if (level) level[s] = f.level;
+        if (ncols) ncols[s] = f.nc;
+        if (nrows) nrows[s] = f.nr;
+        if (loff) loff[s] = f.loff;
+        if (lsize) lsize[s] = (i64)f.ld * f.nc;
+        if (uoff) uoff[s] = f.uoff;
+        if (usize) usize[s] = m > 0 ? ldu * mu : 0;
+    }
+    return B200S_OK;
+}
+b200s_status b200s_chol_device_buffers(b200s_chol* F, double** L_dev, double** W_dev) {
+    if (!F || !L_dev || !W_dev) return B200S_INVALID;
+    b200s_status es = ensure_device(F);
+    if (es != B200S_OK) return es;
+    chol_device_buffers(F->dev, L_dev, W_dev);
+    return B200S_OK;
+}
+b200s_status b200s_chol_set_numeric(b200s_chol* F, int numeric, b200s_int minor) {
+    if (!F || !F->dev) return B200S_INVALID;
+    F->numeric = numeric != 0;
+    F->minor = minor;
+    chol_device_mark_numeric(F->dev, F->numeric);
+    return B200S_OK;
 }
 
 static b200s_status solve_impl(b200s_chol* F, int sys, double* B, b200s_int nrhs, b200s_int ldB, bool on_device) {

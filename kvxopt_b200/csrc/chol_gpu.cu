@@ -113,8 +113,10 @@ __global__ void k_scatter_A(const double* __restrict__ val, const long long* __r
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_extend_add(const EAItem* __restrict__ items, const FrontD* __restrict__ F,
                                                     const int* __restrict__ child_idx, const int* __restrict__ rel,
-                                                    double* __restrict__ L, double* __restrict__ W) {
+                                                    double* __restrict__ L, double* __restrict__ W,
+                                                    const unsigned char* __restrict__ owned) {
     const EAItem it = items[blockIdx.x];
+    if (!owned[it.front]) return;
     const FrontD fp = F[it.front];
     const int nc = fp.nc, nr = fp.nr, uo = nc & 1;
     const int ldu = ((nr - nc + uo) + 1) & ~1;
@@ -241,8 +243,9 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__ list, const FrontD* __restrict__ F,
                                                          double* __restrict__ L, double* __restrict__ W, int* minor,
-                                                         double dbound) {
+                                                         double dbound, const unsigned char* __restrict__ owned) {
     extern __shared__ double S[];
+    if (!owned[list[blockIdx.x]]) return;
     const FrontD f = F[list[blockIdx.x]];
     const int nr = f.nr, nc = f.nc, m = nr - nc, uo = nc & 1, lds = nr | 1;
     const int ldu = ((m + uo) + 1) & ~1;
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__
 __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                   int ngroups, int kb, const FrontD* __restrict__ F,
                                                   double* __restrict__ L, double* __restrict__ diag_scratch,
-                                                  int* minor, double dbound) {
+                                                  int* minor, double dbound, const unsigned char* __restrict__ owned) {
     extern __shared__ double sm[];
     double* Ls = sm;
     double* Xs = Ls + NB * LDL;
@@ -284,6 +287,7 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = find_group(gprefix, ngroups, blockIdx.x);
     const int r = blockIdx.x - gprefix[g];
+    if (!owned[gfront[g]]) return;
     const FrontD f = F[gfront[g]];
     const int k0 = kb * NB;
     const int w = min(NB, f.nc - k0);
@@ -365,7 +369,9 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
 
 __global__ void __launch_bounds__(256) k_diag_writeback(const int* __restrict__ gfront, int kb,
                                                         const FrontD* __restrict__ F, double* __restrict__ L,
-                                                        const double* __restrict__ diag_scratch) {
+                                                        const double* __restrict__ diag_scratch,
+                                                        const unsigned char* __restrict__ owned) {
+    if (!owned[gfront[blockIdx.x]]) return;
     const FrontD f = F[gfront[blockIdx.x]];
     const int k0 = kb * NB, w = min(NB, f.nc - k0);
     double* P = L + f.loff;
@@ -406,13 +412,15 @@ __device__ __forceinline__ void load_tile_async(double* dst, const double* __res
 // column tile cj pairs with row tiles ti >= cj/2
 __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                            int ngroups, int mode, int kb, const FrontD* __restrict__ F,
-                                                           double* __restrict__ L, double* __restrict__ W) {
+                                                           double* __restrict__ L, double* __restrict__ W,
+                                                           const unsigned char* __restrict__ owned) {
     extern __shared__ double sm[];
     double* As = sm;                          // [STAGES][BK][LDT]    rows of the tile's row block (128)
     double* Bs = sm + STAGES * BK * LDT;      // [STAGES][BK][LDTB]   rows of the tile's column block (64)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = find_group(gprefix, ngroups, blockIdx.x);
     int t = blockIdx.x - gprefix[g];
+    if (!owned[gfront[g]]) return;
     const FrontD f = F[gfront[g]];
     const int nr = f.nr, nc = f.nc, ld = f.ld;
     const double* P = L + f.loff;
@@ -878,13 +886,17 @@ public:
     bool numeric = false, profiling = false;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> pev;  // profiling event pool
+    struct Span { int cls; size_t e0, e1; };
+    std::vector<Span> spans;
+    size_t pe = 0;
+    unsigned char* downed = nullptr;   // per front: 1 = this device factors it (multi-GPU subtree ownership)
     i64 total_bytes = 0;
 
     ~CholDevice() {
         cudaSetDevice(device);
         cudaFree(dL); cudaFree(dW); cudaFree(dval); cudaFree(dT); cudaFree(dX); cudaFree(dBstage); cudaFree(damap); cudaFree(dF);
         cudaFree(drows); cudaFree(drel); cudaFree(dchild); cudaFree(dperm); cudaFree(dlevel_fronts);
-        cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag); cudaFree(dpart);
+        cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag); cudaFree(dpart); cudaFree(downed);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -898,6 +910,10 @@ public:
     }
     int init();
     int factorize(const double* val, bool on_device, i64* minor, CholTimes* times);
+    int factor_begin(const double* val, bool on_device);
+    int factor_level(int l);
+    int factor_end(i64* minor, CholTimes* times);
+    int set_owned(const unsigned char* owned_host);
     int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times);
     int ensure_solve_ws(i64 cols);
 };
@@ -936,6 +952,8 @@ int CholDevice::init() {
     CUDA_TRY(cudaMalloc((void**)&dW, std::max<i64>(P.wsize, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dval, std::max<i64>(P.nnzA, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dminor, sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&downed, std::max<size_t>(hf.size(), 1)));
+    CUDA_TRY(cudaMemset(downed, 1, std::max<size_t>(hf.size(), 1)));
     total_bytes += (P.lsize + P.wsize + P.nnzA) * sizeof(double);
 
     // ---- schedule
@@ -1069,11 +1087,10 @@ int CholDevice::init() {
     return ST_OK;
 }
 
-int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTimes* times) {
+int CholDevice::factor_begin(const double* val, bool on_device) {
     const CholPlan& P = *plan;
     CUDA_TRY(cudaSetDevice(device));
     numeric = false;
-    const int ns = (int)P.fronts.size();
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     const double* dv = val;
     if (!on_device) {
@@ -1089,66 +1106,75 @@ int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTim
         k_scatter_A<<<blocks, 256, 0, stream>>>(dv, damap, P.nnzA, dL);
     }
     CUDA_TRY(cudaEventRecord(ev[2], stream));
-    size_t pe = 0;
-    struct Span { int cls; size_t e0, e1; };
-    std::vector<Span> spans;
-    auto prof_begin = [&](int cls) -> int {
-        if (!profiling) return 0;
+    pe = 0;
+    spans.clear();
+    return ST_OK;
+}
+
+int CholDevice::factor_level(int l) {
+    const CholPlan& P = *plan;
+    if (l < 0 || l >= P.nlevels) return ST_INVALID;
+    CUDA_TRY(cudaSetDevice(device));
+    auto prof_begin = [&](int cls) {
+        if (!profiling) return;
         while (pev.size() < pe + 2) { cudaEvent_t e; cudaEventCreate(&e); pev.push_back(e); }
         cudaEventRecord(pev[pe], stream);
         spans.push_back({cls, pe, pe + 1});
         pe += 2;
-        return 0;
     };
     auto prof_end = [&]() { if (profiling) cudaEventRecord(pev[spans.back().e1], stream); };
-    for (int l = 0; l < P.nlevels; l++) {
-        const LevelSched& LS = levels[l];
-        if (LS.ea_cnt) {
-            prof_begin(0);
-            k_extend_add<<<LS.ea_cnt, 256, 0, stream>>>(dea + LS.ea_off, dF, dchild, drel, dL, dW);
+    const LevelSched& LS = levels[l];
+    if (LS.ea_cnt) {
+        prof_begin(0);
+        k_extend_add<<<LS.ea_cnt, 256, 0, stream>>>(dea + LS.ea_off, dF, dchild, drel, dL, dW, downed);
+        prof_end();
+    }
+    prof_begin(1);
+    if (LS.small_cnt[0])
+        k_small_front<64><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(
+            dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed);
+    if (LS.small_cnt[1])
+        k_small_front<128><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(
+            dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed);
+    if (LS.small_cnt[2])
+        k_small_front<256><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(
+            dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed);
+    prof_end();
+    for (size_t kb = 0; kb < LS.panel.size(); kb++) {
+        const Launch& lp = LS.panel[kb];
+        if (lp.ctas) {
+            prof_begin(2);
+            k_panel<<<lp.ctas, 256, SMEM_PANEL, stream>>>(dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
+                                                          dF, dL, ddiag, dminor, opts.dbound, downed);
+            k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag, downed);
             prof_end();
         }
-        prof_begin(1);
-        if (LS.small_cnt[0])
-            k_small_front<64><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(
-                dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound);
-        if (LS.small_cnt[1])
-            k_small_front<128><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(
-                dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound);
-        if (LS.small_cnt[2])
-            k_small_front<256><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(
-                dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound);
-        prof_end();
-        for (size_t kb = 0; kb < LS.panel.size(); kb++) {
-            const Launch& lp = LS.panel[kb];
-            if (lp.ctas) {
-                prof_begin(2);
-                k_panel<<<lp.ctas, 256, SMEM_PANEL, stream>>>(dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
-                                                              dF, dL, ddiag, dminor, opts.dbound);
-                k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag);
-                prof_end();
-            }
-            const Launch& lu = LS.upd[kb];
-            if (lu.ctas) {
-                prof_begin(3);
-                k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
-                                                                (int)kb, dF, dL, dW);
-                prof_end();
-            }
-        }
-        if (LS.syrk.ctas) {
+        const Launch& lu = LS.upd[kb];
+        if (lu.ctas) {
             prof_begin(3);
-            k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
-                                                                 LS.syrk.ng, 1, 0, dF, dL, dW);
+            k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                                                                    (int)kb, dF, dL, dW, downed);
             prof_end();
         }
     }
+    if (LS.syrk.ctas) {
+        prof_begin(3);
+        k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+                                                                     LS.syrk.ng, 1, 0, dF, dL, dW, downed);
+        prof_end();
+    }
     CUDA_TRY(cudaGetLastError());
+    return ST_OK;
+}
+
+int CholDevice::factor_end(i64* minor, CholTimes* times) {
+    const CholPlan& P = *plan;
+    CUDA_TRY(cudaSetDevice(device));
+    const int big = 0x7fffffff;
     int hminor = 0;
     CUDA_TRY(cudaMemcpyAsync(&hminor, dminor, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaEventRecord(ev[3], stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    (void)ns;
     if (times) {
         float ms;
         cudaEventElapsedTime(&ms, ev[0], ev[1]); times->ms_h2d = ms;
@@ -1170,6 +1196,22 @@ int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTim
     }
     if (minor) *minor = P.n;
     numeric = true;
+    return ST_OK;
+}
+
+int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTimes* times) {
+    int rc = factor_begin(val, on_device);
+    if (rc) return rc;
+    for (int l = 0; l < plan->nlevels; l++)
+        if ((rc = factor_level(l))) return rc;
+    return factor_end(minor, times);
+}
+
+int CholDevice::set_owned(const unsigned char* owned_host) {
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t ns = plan->fronts.size();
+    std::vector<unsigned char> all(std::max<size_t>(ns, 1), 1);
+    CUDA_TRY(cudaMemcpy(downed, owned_host ? owned_host : all.data(), ns, cudaMemcpyHostToDevice));
     return ST_OK;
 }
 
@@ -1308,6 +1350,17 @@ int chol_device_download_L(CholDevice* d, double* L_host) {
     return ST_OK;
 }
 void chol_device_set_profiling(CholDevice* d, bool on) { d->profiling = on; }
+int chol_device_set_owned(CholDevice* d, const unsigned char* owned) { return d->set_owned(owned); }
+int chol_device_factor_begin(CholDevice* d, const double* val, bool on_device) { return d->factor_begin(val, on_device); }
+int chol_device_factor_level(CholDevice* d, int level) { return d->factor_level(level); }
+int chol_device_factor_end(CholDevice* d, i64* minor, CholTimes* times) { return d->factor_end(minor, times); }
+int chol_device_sync(CholDevice* d) {
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return ST_OK;
+}
+void chol_device_buffers(CholDevice* d, double** L, double** W) { *L = d->dL; *W = d->dW; }
+void chol_device_mark_numeric(CholDevice* d, bool numeric) { d->numeric = numeric; }
 i64 chol_device_workspace_bytes(const CholDevice* d) { return d->total_bytes; }
 
 }  // namespace b200s

@@ -28,6 +28,14 @@ int  chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, boo
 int  chol_device_diag(CholDevice* d, double* diag_host);
 int  chol_device_download_L(CholDevice* d, double* L_host);   // raw panel storage, plan.lsize doubles
 void chol_device_set_profiling(CholDevice* d, bool on);
+// level-stepped factorization + front ownership: building blocks of the multi-GPU subtree-to-subcube driver
+int  chol_device_set_owned(CholDevice* d, const unsigned char* owned);
+int  chol_device_factor_begin(CholDevice* d, const double* val, bool on_device);
+int  chol_device_factor_level(CholDevice* d, int level);
+int  chol_device_factor_end(CholDevice* d, i64* minor, CholTimes* times);
+int  chol_device_sync(CholDevice* d);
+void chol_device_buffers(CholDevice* d, double** L, double** W);
+void chol_device_mark_numeric(CholDevice* d, bool numeric);
 i64  chol_device_workspace_bytes(const CholDevice* d);
 
 }  // namespace b200s

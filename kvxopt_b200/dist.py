@@ -1,0 +1,250 @@
+"""Multi-GPU sparse Cholesky: subtree-to-subcube mapping of the supernodal elimination tree over the GPUs of one box.
+
+No counterpart in the reference (single process, no GPU); this is SURVEY section 8(e), BASELINE config 4.
+Every process (one per GPU, `torchrun`) analyses the same matrix and therefore holds the identical plan.  The tree is
+cut top-down: the root front goes to the first rank of the group, its children are split over the two halves of the
+group by subtree work, and so on until a group is a single rank, which then owns the whole subtree.  The
+factorization is stepped level by level through the C ABI (b200s_chol_factor_begin/level/end); before a level runs,
+the update matrices of children that live on another GPU are moved GPU-to-GPU with NCCL send/recv straight between
+the W buffers (identical layout on every rank).  Afterwards the panels are gathered on rank 0, which serves the
+solves.  Round-1 limitation: a front is never split over several GPUs, so the top log2(G) levels are sequential.
+
+`ownership()` and `exchange_plan()` are pure functions of the plan and are tested on the CPU; `VirtualRanks` runs the
+same protocol with several handles on ONE GPU (device-to-device copies instead of NCCL) for single-GPU testing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+fn = L.fn
+
+
+def front_layout(h):
+    inf = L.CholInfo()
+    fn["b200s_chol_info"](h, C.byref(inf))
+    ns = inf.nsuper
+    a = {k: np.zeros(max(ns, 1), dtype=np.int64) for k in ("parent", "level", "nc", "nr", "loff", "lsize", "uoff", "usize")}
+    st = fn["b200s_chol_front_layout"](h, *[L.ptr_i64(a[k]) for k in ("parent", "level", "nc", "nr", "loff", "lsize", "uoff", "usize")])
+    assert st == 0
+    lay = {k: v[:ns] for k, v in a.items()}
+    lay["nlevels"] = int(inf.nlevels)
+    lay["n"] = int(inf.n)
+    return lay
+
+
+def front_work(lay):
+    c = lay["nc"].astype(np.float64)
+    r = (lay["nr"] - lay["nc"]).astype(np.float64)
+    return c ** 3 / 3.0 + c * c * r + c * r * r
+
+
+def ownership(lay, world):
+    """subtree-to-subcube: owner[s] in [0, world) for every front"""
+    ns = len(lay["parent"])
+    parent = lay["parent"]
+    work = front_work(lay)
+    sub = work.copy()
+    for s in range(ns):                       # fronts are postordered: children before parents
+        if parent[s] >= 0:
+            sub[parent[s]] += sub[s]
+    kids = [[] for _ in range(ns)]
+    roots = []
+    for s in range(ns):
+        (kids[parent[s]] if parent[s] >= 0 else roots).append(s)
+    owner = np.zeros(ns, dtype=np.int64)
+    first = np.zeros(ns, dtype=np.int64)      # first descendant of s in postorder (subtree = [first[s], s])
+    for s in range(ns):
+        first[s] = first[kids[s][0]] if kids[s] else s
+
+    stack = [(roots, 0, world)]
+    while stack:
+        nodes, r0, r1 = stack.pop()
+        if not nodes:
+            continue
+        if r1 - r0 == 1:
+            for s in nodes:
+                owner[first[s]:s + 1] = r0
+            continue
+        if len(nodes) == 1:
+            s = nodes[0]
+            owner[s] = r0
+            stack.append((kids[s], r0, r1))
+            continue
+        # split the set of subtrees into two bins of similar work, the rank group into two halves
+        order = sorted(nodes, key=lambda q: -sub[q])
+        bins, load = ([], []), [0.0, 0.0]
+        for q in order:
+            b = 0 if load[0] <= load[1] else 1
+            bins[b].append(q)
+            load[b] += sub[q]
+        mid = r0 + max(1, min(r1 - r0 - 1, int(round((r1 - r0) * load[0] / max(load[0] + load[1], 1e-300)))))
+        stack.append((bins[0], r0, mid))
+        stack.append((bins[1], mid, r1))
+    return owner
+
+
+def exchange_plan(lay, owner):
+    """per level l: list of (child, src_rank, dst_rank) transfers that must complete before level l runs"""
+    parent, level = lay["parent"], lay["level"]
+    plan = [[] for _ in range(lay["nlevels"])]
+    for s in range(len(parent)):
+        p = parent[s]
+        if p >= 0 and owner[p] != owner[s] and lay["usize"][s] > 0:
+            plan[level[p]].append((s, int(owner[s]), int(owner[p])))
+    return plan
+
+
+def gather_plan(lay, owner, root=0):
+    """contiguous runs of fronts owned by the same rank != root: (rank, first front, last front) for the panel gather"""
+    runs = []
+    ns = len(owner)
+    s = 0
+    while s < ns:
+        e = s
+        while e + 1 < ns and owner[e + 1] == owner[s]:
+            e += 1
+        if owner[s] != root:
+            runs.append((int(owner[s]), s, e))
+        s = e + 1
+    return runs
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def _device_views(h, lay):
+    import torch
+    Lp, Wp = L.vp(), L.vp()
+    st = fn["b200s_chol_device_buffers"](h, C.byref(Lp), C.byref(Wp))
+    if st != 0:
+        raise RuntimeError("device buffers: %s (%s)" % (L.strerror(st), L.last_error()))
+    inf = L.CholInfo()
+    fn["b200s_chol_info"](h, C.byref(inf))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Lt = torch.as_tensor(_DevArray(Lp.value, max(inf.factor_bytes // 8, 1)), device=dev)
+    Wt = torch.as_tensor(_DevArray(Wp.value, max(inf.workspace_bytes // 8, 1)), device=dev)
+    return Lt, Wt
+
+
+def _check(st, what):
+    if st not in (0, 1):
+        raise RuntimeError("%s: %s (%s)" % (what, L.strerror(st), L.last_error()))
+    return st
+
+
+class DistCholesky:
+    """one instance per rank; `F` is the capsule from kvxopt_b200.cholmod.symbolic on this rank's GPU"""
+
+    def __init__(self, F, world, rank, group=None):
+        from . import cholmod
+        self.h, _ = cholmod._factor_handle(F)
+        self.F = F
+        self.world, self.rank, self.group = world, rank, group
+        self.lay = front_layout(self.h)
+        self.owner = ownership(self.lay, world)
+        self.xplan = exchange_plan(self.lay, self.owner)
+        self.gplan = gather_plan(self.lay, self.owner)
+        mine = (self.owner == rank).astype(np.uint8)
+        _check(fn["b200s_chol_set_owned"](self.h, mine.tobytes()), "set_owned")
+        self.Lt, self.Wt = _device_views(self.h, self.lay)
+        self.work_share = float(front_work(self.lay)[self.owner == rank].sum())
+
+    def factorize(self, values_ptr, on_device):
+        """level-stepped factorization with NCCL exchange of the update matrices; returns (status, minor)"""
+        import torch
+        import torch.distributed as dist
+        lay = self.lay
+        _check(fn["b200s_chol_factor_begin"](self.h, values_ptr, 1 if on_device else 0), "factor_begin")
+        for l in range(lay["nlevels"]):
+            moves = self.xplan[l]
+            mine = [m for m in moves if self.rank in (m[1], m[2])]
+            if mine:
+                fn["b200s_chol_sync"](self.h)                 # my update matrices of earlier levels are complete
+                ops = []
+                for s, src, dst in mine:
+                    t = self.Wt[lay["uoff"][s]: lay["uoff"][s] + lay["usize"][s]]
+                    if src == self.rank:
+                        ops.append(dist.P2POp(dist.isend, t, dst, group=self.group))
+                    else:
+                        ops.append(dist.P2POp(dist.irecv, t, src, group=self.group))
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                torch.cuda.current_stream().synchronize()      # received data visible to the handle's stream
+            _check(fn["b200s_chol_factor_level"](self.h, l), "factor_level")
+        minor = C.c_int64()
+        st = _check(fn["b200s_chol_factor_end"](self.h, C.byref(minor)), "factor_end")
+        m = torch.tensor([int(minor.value) if st == 1 else lay["n"]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(m, op=dist.ReduceOp.MIN, group=self.group)
+        self.minor = int(m.item())
+        return (1 if self.minor < lay["n"] else 0), self.minor
+
+    def gather_factor(self, root=0):
+        """collect all panels on `root` (contiguous runs of fronts per owner) and mark its factor numeric"""
+        import torch
+        import torch.distributed as dist
+        lay = self.lay
+        ops = []
+        for rk, s0, s1 in self.gplan:
+            a, b = lay["loff"][s0], lay["loff"][s1] + lay["lsize"][s1]
+            t = self.Lt[a:b]
+            if self.rank == rk:
+                ops.append(dist.P2POp(dist.isend, t, root, group=self.group))
+            elif self.rank == root:
+                ops.append(dist.P2POp(dist.irecv, t, rk, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        torch.cuda.current_stream().synchronize()
+        if self.rank == root:
+            _check(fn["b200s_chol_set_numeric"](self.h, 1 if self.minor >= lay["n"] else 0, self.minor), "set_numeric")
+
+
+class VirtualRanks:
+    """The same protocol with `world` handles on ONE GPU (device-to-device copies instead of NCCL): lets the ownership
+    split, the exchange plan and the level-stepped kernels be verified on a single-GPU box."""
+
+    def __init__(self, capsules):
+        from . import cholmod
+        self.hs = [cholmod._factor_handle(F)[0] for F in capsules]
+        self.world = len(self.hs)
+        self.lay = front_layout(self.hs[0])
+        self.owner = ownership(self.lay, self.world)
+        self.xplan = exchange_plan(self.lay, self.owner)
+        self.gplan = gather_plan(self.lay, self.owner)
+        self.views = []
+        for r, h in enumerate(self.hs):
+            _check(fn["b200s_chol_set_owned"](h, (self.owner == r).astype(np.uint8).tobytes()), "set_owned")
+            self.views.append(_device_views(h, self.lay))
+
+    def factorize(self, values):
+        import torch
+        lay = self.lay
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        for h in self.hs:
+            _check(fn["b200s_chol_factor_begin"](h, v.ctypes.data_as(C.c_void_p), 0), "factor_begin")
+        for l in range(lay["nlevels"]):
+            if self.xplan[l]:
+                for h in self.hs:
+                    fn["b200s_chol_sync"](h)
+                for s, src, dst in self.xplan[l]:
+                    a, b = lay["uoff"][s], lay["uoff"][s] + lay["usize"][s]
+                    self.views[dst][1][a:b].copy_(self.views[src][1][a:b])
+                torch.cuda.synchronize()
+            for h in self.hs:
+                _check(fn["b200s_chol_factor_level"](h, l), "factor_level")
+        minors = []
+        for h in self.hs:
+            m = C.c_int64()
+            st = _check(fn["b200s_chol_factor_end"](h, C.byref(m)), "factor_end")
+            minors.append(int(m.value) if st == 1 else lay["n"])
+        self.minor = min(minors)
+        for rk, s0, s1 in self.gplan:
+            a, b = lay["loff"][s0], lay["loff"][s1] + lay["lsize"][s1]
+            self.views[0][0][a:b].copy_(self.views[rk][0][a:b])
+        torch.cuda.synchronize()
+        _check(fn["b200s_chol_set_numeric"](self.hs[0], 1 if self.minor >= lay["n"] else 0, self.minor), "set_numeric")
+        return self.minor
