@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -306,6 +306,50 @@ def cpu_cholesky_sample(nx):
             "factor_tflops": O.flops / tf / 1e12, "cores": threads, "kind": "port"}
 
 
+def bench_cholesky_multi(nx, steps, rank, world):
+    """BASELINE configs[3] over N GPUs: subtree-to-subcube (kvxopt_b200/dist.py), update matrices over NCCL/NVLink"""
+    import torch
+    import torch.distributed as dist
+    from kvxopt_b200 import _lib as L, cholmod, dist as D
+    Al = lap3d_lower(nx)
+    n = Al.shape[0]
+    perm = np.zeros(n, np.int64)
+    L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm))
+    F = cholmod.symbolic(Al, p=perm)
+    dc = D.DistCholesky(F, world, rank)
+    vals = torch.from_numpy(Al.data.copy()).cuda()
+    times, gtimes = [], []
+    for rep in range(steps + 1):
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st, minor = dc.factorize(vals.data_ptr(), True)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        dc.gather_factor(0)
+        torch.cuda.synchronize(); dist.barrier()
+        t2 = time.perf_counter()
+        if rep > 0:
+            times.append((t1 - t0) * 1e3); gtimes.append((t2 - t1) * 1e3)
+    out = None
+    if rank == 0:
+        d = cholmod.factor_info(F)
+        b = np.random.default_rng(0).standard_normal((n, 1)); x = np.asfortranarray(b.copy())
+        cholmod.solve(F, x)
+        A = (Al + sp.tril(Al, -1).T).tocsr()
+        berr = float(np.linalg.norm(A @ x - b) / (12.0 * np.linalg.norm(x) + np.linalg.norm(b)))
+        w = D.front_work(dc.lay)
+        out = {"workload": "7-point Laplacian %d^3, nested dissection, subtree-to-subcube over %d GPUs" % (nx, world),
+               "factor_ms": float(np.min(times)), "gather_panels_ms": float(np.min(gtimes)),
+               "factor_tflops": d["flops"] / (float(np.min(times)) * 1e-3) / 1e12, "solve_ms_rank0": d["ms_solve"],
+               "backward_error": berr, "timing": "host clock between barrier+synchronize pairs, max over ranks by construction",
+               "work_share_per_rank": [round(float(w[dc.owner == r].sum() / w.sum()), 3) for r in range(world)],
+               "nccl_transfers": int(sum(len(l) for l in dc.xplan)),
+               "nccl_bytes": int(sum(int(dc.lay["usize"][m[0]]) for l in dc.xplan for m in l) * 8),
+               "limitation": "fronts are not split across GPUs in round 1: the top log2(N) levels run on one GPU each"}
+    del dc, F
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -440,6 +484,14 @@ def main():
                 line["cholesky"]["cpu_baseline"] = cpu_cholesky_sample(48)
         except Exception as e:  # the headline line must still be printed
             line["cholesky"] = {"error": repr(e)}
+    if world > 1 and args.workload in ("all", "chol"):
+        try:
+            res = bench_cholesky_multi(args.chol_grid, 2, rank, world)
+            if rank == 0:
+                line["cholesky_subtree"] = res
+        except Exception as e:
+            if rank == 0:
+                line["cholesky_subtree"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
