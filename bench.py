@@ -332,9 +332,9 @@ def bench_cholesky_multi(nx, steps, rank, world):
             times.append((t1 - t0) * 1e3); gtimes.append((t2 - t1) * 1e3)
     out = None
     if rank == 0:
-        d = cholmod.factor_info(F)
         b = np.random.default_rng(0).standard_normal((n, 1)); x = np.asfortranarray(b.copy())
         cholmod.solve(F, x)
+        d = cholmod.factor_info(F)
         A = (Al + sp.tril(Al, -1).T).tocsr()
         berr = float(np.linalg.norm(A @ x - b) / (12.0 * np.linalg.norm(x) + np.linalg.norm(b)))
         w = D.front_work(dc.lay)
