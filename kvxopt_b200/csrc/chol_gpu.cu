@@ -426,9 +426,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const int* __restrict
     const double* P = L + f.loff;
     int rowI, rowJ, k0, K, ldc, crows, ccols, lo;
     double* C;
-    if (mode == 0) {
+    if (mode != 1) {
+        // mode 0: every column tile right of block kb; mode 2: only the next block column (lookahead part A);
+        // mode 3: the column tiles right of the next block column (part B, overlapped with the next panel kernel)
         const int nrt = (nr + BT - 1) / BT;
-        int cj = 2 * (kb + 1);
+        int cj = 2 * (kb + 1) + (mode == 3 ? 2 : 0);
         while (t >= nrt - (cj >> 1)) { t -= nrt - (cj >> 1); cj++; }
         const int ti = (cj >> 1) + t;
         rowI = ti * BT; rowJ = cj * BTN;
@@ -859,7 +861,8 @@ struct Launch {            // one grouped launch: groups [goff, goff+ng) in the 
 struct LevelSched {
     int ea_off = 0, ea_cnt = 0;
     int small_off[3] = {0, 0, 0}, small_cnt[3] = {0, 0, 0}, small_maxnr[3] = {0, 0, 0};
-    std::vector<Launch> panel, upd;   // per block step kb
+    std::vector<Launch> panel, upd;   // per block step kb (upd = all trailing column tiles)
+    std::vector<Launch> updA, updB;   // lookahead split of upd: next block column / the rest
     Launch syrk;
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
     int small_all_off = 0, small_all_cnt = 0;
@@ -870,7 +873,8 @@ public:
     const CholPlan* plan = nullptr;
     CholOpts opts;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: lookahead (trailing update overlapped with the next panel)
+    cudaEvent_t evP = nullptr, evB = nullptr;
     double *dL = nullptr, *dW = nullptr, *dval = nullptr, *dT = nullptr, *dX = nullptr, *dBstage = nullptr;
     i64 bstage_cap = 0;            // doubles
     long long* damap = nullptr;
@@ -899,6 +903,9 @@ public:
         cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag); cudaFree(dpart); cudaFree(downed);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
+        if (evP) cudaEventDestroy(evP);
+        if (evB) cudaEventDestroy(evB);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
     template <class T> int upload(T** dst, const T* src, size_t count) {
@@ -925,6 +932,9 @@ int CholDevice::init() {
     const CholPlan& P = *plan;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&evP, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     const int ns = (int)P.fronts.size();
     std::vector<FrontD> hf(ns);
@@ -993,6 +1003,8 @@ int CholDevice::init() {
         for (int s : bigs) maxblk = std::max(maxblk, (P.fronts[s].nc + NB - 1) / NB);
         LS.panel.resize(maxblk);
         LS.upd.resize(maxblk);
+        LS.updA.resize(maxblk);
+        LS.updB.resize(maxblk);
         auto emit = [&](Launch& la, const std::vector<int>& fr, const std::vector<int>& cnt) {
             la.goff = (int)sched.size();
             la.ng = (int)fr.size();
@@ -1023,7 +1035,7 @@ int CholDevice::init() {
             max_solve_ctas = std::max(max_solve_ctas, LS.sbwd[kb].ctas);
         }
         for (int kb = 0; kb < maxblk; kb++) {
-            std::vector<int> fr, cp, fu, cu;
+            std::vector<int> fr, cp, fu, cu, fuA, cuA, fuB, cuB;
             // panel CTAs: one per front for the diagonal block + solver CTAs that each factor the block redundantly
             // and then walk over several 64-row tiles; the solver CTAs of a launch are capped near one wave (148 SMs)
             long long tiles_total = 0;
@@ -1049,12 +1061,19 @@ int CholDevice::init() {
                 fr.push_back(s);
                 cp.push_back(1 + nsolve);
                 const int nrt = (f.nr + BT - 1) / BT, ncolt = (f.nc + BTN - 1) / BTN;
-                long long tiles = 0;
-                for (int cj = 2 * (kb + 1); cj < ncolt; cj++) tiles += nrt - (cj >> 1);
+                long long tiles = 0, tilesA = 0;
+                for (int cj = 2 * (kb + 1); cj < ncolt; cj++) {
+                    tiles += nrt - (cj >> 1);
+                    if (cj < 2 * (kb + 1) + 2) tilesA += nrt - (cj >> 1);
+                }
                 if (tiles > 0) { fu.push_back(s); cu.push_back((int)tiles); }
+                if (tilesA > 0) { fuA.push_back(s); cuA.push_back((int)tilesA); }
+                if (tiles - tilesA > 0) { fuB.push_back(s); cuB.push_back((int)(tiles - tilesA)); }
             }
             emit(LS.panel[kb], fr, cp);
             emit(LS.upd[kb], fu, cu);
+            emit(LS.updA[kb], fuA, cuA);
+            emit(LS.updB[kb], fuB, cuB);
         }
         {
             std::vector<int> fr, cnt;
@@ -1140,6 +1159,12 @@ int CholDevice::factor_level(int l) {
         k_small_front<256><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(
             dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed);
     prof_end();
+    // Lookahead of depth one: after panel kb, part A of its trailing update (the next block column only) runs on
+    // the main stream, then panel kb+1; part B (all other column tiles) runs on stream2 concurrently with panel
+    // kb+1, whose few latency-bound CTAs would otherwise leave the GPU idle.  Part A of step kb+1 waits for part B
+    // of step kb (same C tiles).  With profiling on everything is serialised on the main stream.
+    const bool lookahead = !profiling;
+    bool pendingB = false;
     for (size_t kb = 0; kb < LS.panel.size(); kb++) {
         const Launch& lp = LS.panel[kb];
         if (lp.ctas) {
@@ -1149,14 +1174,32 @@ int CholDevice::factor_level(int l) {
             k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag, downed);
             prof_end();
         }
-        const Launch& lu = LS.upd[kb];
-        if (lu.ctas) {
-            prof_begin(3);
-            k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+        if (!lookahead) {
+            const Launch& lu = LS.upd[kb];
+            if (lu.ctas) {
+                prof_begin(3);
+                k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                                                                        (int)kb, dF, dL, dW, downed);
+                prof_end();
+            }
+            continue;
+        }
+        const Launch& la = LS.updA[kb];
+        const Launch& lb = LS.updB[kb];
+        if (lb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));             // panel kb is complete
+        if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }   // part B of step kb-1
+        if (la.ctas)
+            k_update<<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
                                                                     (int)kb, dF, dL, dW, downed);
-            prof_end();
+        if (lb.ctas) {
+            CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
+            k_update<<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
+                                                                     (int)kb, dF, dL, dW, downed);
+            CUDA_TRY(cudaEventRecord(evB, stream2));
+            pendingB = true;
         }
     }
+    if (pendingB) CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0));
     if (LS.syrk.ctas) {
         prof_begin(3);
         k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
