@@ -1,0 +1,33 @@
+"""BASELINE config 5: synthetic sparse QP through the reference coneqp (probe build oracle/_ref) with the B200 cholmod
+module as kvxopt.cholmod.  usage: run_qp.py nx ny nrand   (config 5: 500 400 5000; small: 500 400 2000)"""
+import os, sys, time
+import numpy as np, scipy.sparse as sp
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import kvxopt
+from kvxopt_b200 import cholmod, klu
+cholmod.install(kvxopt)
+from kvxopt import matrix, spmatrix, solvers
+from generators import qp_instance
+nx, ny, nrand = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (100, 80, 200)
+P, q, G, h = qp_instance(nx, ny, nrand)
+def tosp(M):
+    M = sp.coo_matrix(M); return spmatrix(M.data.tolist(), M.row.tolist(), M.col.tolist(), M.shape)
+t_num = [0.0]; t_sol = [0.0]; n_num = [0]; n_sol = [0]; t_sym = [0.0]
+on, osv, osy = cholmod.numeric, cholmod.solve, cholmod.symbolic
+def numeric(*a, **k):
+    t = time.perf_counter(); r = on(*a, **k); t_num[0] += time.perf_counter() - t; n_num[0] += 1; return r
+def solve(*a, **k):
+    t = time.perf_counter(); r = osv(*a, **k); t_sol[0] += time.perf_counter() - t; n_sol[0] += 1; return r
+def symbolic(*a, **k):
+    t = time.perf_counter(); r = osy(*a, **k); t_sym[0] += time.perf_counter() - t
+    if cholmod.factor_info(r)["n"] > 0: print("symbolic: %s" % {k2: v for k2, v in cholmod.factor_info(r).items() if k2 in ("n", "nnz_L", "flops", "nsuper", "max_front_rows", "ms_analyze")}, flush=True)
+    return r
+cholmod.numeric, cholmod.solve, cholmod.symbolic = numeric, solve, symbolic
+solvers.options["show_progress"] = True
+t0 = time.perf_counter()
+sol = solvers.qp(tosp(sp.tril(P)), matrix(q), tosp(G), matrix(h))
+wall = time.perf_counter() - t0
+print("status %s iterations %d objective %.10f wall %.2f s => %.2f IPM iterations/s" % (sol["status"], sol["iterations"], sol["primal objective"], wall, sol["iterations"] / wall))
+print("cholmod: symbolic %.2f s | numeric %d calls %.3f s | solve %d calls %.3f s | everything else (reference Python IPM, host S assembly) %.2f s" % (
+    t_sym[0], n_num[0], t_num[0], n_sol[0], t_sol[0], wall - t_sym[0] - t_num[0] - t_sol[0]))
