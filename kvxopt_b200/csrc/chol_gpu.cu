@@ -19,7 +19,9 @@
 #include "gpu.hpp"
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -930,7 +932,17 @@ static constexpr size_t SMEM_UPDATE = (size_t)(STAGES * BK * (LDT + LDTB)) * siz
 
 int CholDevice::init() {
     const CholPlan& P = *plan;
+    const bool dbg = getenv("B200S_DEBUG") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200s chol init] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+        t_start = now;
+    };
     CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(0));
+    lap("context");
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&evP, cudaEventDisableTiming));
@@ -958,6 +970,7 @@ int CholDevice::init() {
         std::vector<long long> am(P.amap.begin(), P.amap.end());
         if ((rc = upload(&damap, am.data(), am.size()))) return rc;
     }
+    lap("plan upload");
     CUDA_TRY(cudaMalloc((void**)&dL, std::max<i64>(P.lsize, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dW, std::max<i64>(P.wsize, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dval, std::max<i64>(P.nnzA, 1) * sizeof(double)));
@@ -966,6 +979,7 @@ int CholDevice::init() {
     CUDA_TRY(cudaMemset(downed, 1, std::max<size_t>(hf.size(), 1)));
     total_bytes += (P.lsize + P.wsize + P.nnzA) * sizeof(double);
 
+    lap("cudaMalloc L/W/val");
     // ---- schedule
     std::vector<int> sched;          // group arrays: [front ids...][prefix...]
     std::vector<EAItem> ea;
@@ -1096,6 +1110,7 @@ int CholDevice::init() {
         CUDA_TRY(cudaMalloc((void**)&ddiag, (size_t)maxng * NB * NB * sizeof(double)));
         total_bytes += (size_t)maxng * NB * NB * sizeof(double);
     }
+    lap("schedule build");
     if ((rc = upload(&dsched, sched.data(), sched.size()))) return rc;
     if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
@@ -1103,6 +1118,7 @@ int CholDevice::init() {
     CUDA_TRY(cudaFuncSetAttribute(k_small_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((SMALL_NR | 1) * SMALL_NR * sizeof(double))));
     CUDA_TRY(cudaFuncSetAttribute(k_small_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
+    lap("schedule upload + attributes");
     return ST_OK;
 }
 

@@ -1,7 +1,12 @@
 """BASELINE config 5: synthetic sparse QP through the reference coneqp (probe build oracle/_ref) with the B200 cholmod
 module as kvxopt.cholmod.  usage: run_qp.py nx ny nrand   (config 5: 500 400 5000; small: 500 400 2000)"""
-import os, sys, time
+import os, sys, time, functools, faulthandler
+faulthandler.enable()
+faulthandler.dump_traceback_later(int(os.environ.get("QP_DUMP_AFTER", "100000")), exit=True)
+print = functools.partial(print, flush=True)
 import numpy as np, scipy.sparse as sp
+# the reference's own host code (misc_solvers.scale -> BLAS) crashes inside multi-threaded OpenBLAS at m >= 4e5 on this image
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import kvxopt
@@ -16,9 +21,13 @@ def tosp(M):
 t_num = [0.0]; t_sol = [0.0]; n_num = [0]; n_sol = [0]; t_sym = [0.0]
 on, osv, osy = cholmod.numeric, cholmod.solve, cholmod.symbolic
 def numeric(*a, **k):
-    t = time.perf_counter(); r = on(*a, **k); t_num[0] += time.perf_counter() - t; n_num[0] += 1; return r
+    t = time.perf_counter(); r = on(*a, **k); dt = time.perf_counter() - t; t_num[0] += dt; n_num[0] += 1
+    if dt > 0.05: print("  [numeric call %d took %.3f s, n=%d]" % (n_num[0], dt, a[0].size[0]), flush=True)
+    return r
 def solve(*a, **k):
-    t = time.perf_counter(); r = osv(*a, **k); t_sol[0] += time.perf_counter() - t; n_sol[0] += 1; return r
+    t = time.perf_counter(); r = osv(*a, **k); dt = time.perf_counter() - t; t_sol[0] += dt; n_sol[0] += 1
+    if dt > 0.05: print("  [solve call %d took %.3f s]" % (n_sol[0], dt), flush=True)
+    return r
 def symbolic(*a, **k):
     t = time.perf_counter(); r = osy(*a, **k); t_sym[0] += time.perf_counter() - t
     if cholmod.factor_info(r)["n"] > 0: print("symbolic: %s" % {k2: v for k2, v in cholmod.factor_info(r).items() if k2 in ("n", "nnz_L", "flops", "nsuper", "max_front_rows", "ms_analyze")}, flush=True)
