@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, int
 // intra-warp synchronisation is needed); L columns of finished columns stream from global memory; the scatter of
 // the scaled input values is fused into the column initialisation.
 struct KluWaveD {
-    int nwaves;
+    int nwaves, spine0;
     const int *wave_col0, *col_roff, *batch_rowslot, *wave_rowsrc;
     const unsigned* bentry;     // per batch [KLU_WAVE_WARPS][KLU_CHUNK_ROWS] staged-row actions
     const unsigned* wblob;      // in-wave update blobs
@@ -309,7 +309,15 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
                     for (; t < cnt; t++) x[d[t] * 32] -= lsrc[t * 32] * uj;     // tail (< 4 rows) of the warp that owns it
                     ui++;
                 }
-                if (ui == ue) {
+                if (ui == ue && k >= W.spine0) {
+                    // column of the dense trailing block: only the updates from columns < spine0 were applied here;
+                    // store it unfinished, k_klu_dense_lu factors the block
+                    team_sync();
+#pragma unroll 4
+                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
+                    fin = true;
+                    if (lane == 0 && sub == 0) done_round[col] = r;
+                } else if (ui == ue) {
                     team_sync();
                     const double piv = x[diag * 32];
                     if (!(fabs(piv) > 0.0)) bad = 1;
@@ -331,6 +339,217 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
     }
     if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; }
     if (bad) status[b] = ST_SINGULAR;
+}
+
+// Dense trailing block: one CTA per matrix gathers the nd x nd block (pattern entries from the LU slots, zeros
+// elsewhere) into shared memory, factors it without pivoting (the pivot order is the frozen one) by 16-column
+// chunks -- diagonal chunk by one warp, L21 = A21 U11^-1 and U12 = L11^-1 A12 one thread per row / column, trailing
+// update with FP64 DMMA on 8x8 tiles -- and scatters the pattern entries back.  Entries outside the symbolic
+// pattern stay exactly zero (the pattern is closed under fill).
+__device__ __forceinline__ void klu_dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// diagonal 16 x 16 chunk at (d0, d0) factored in registers by one warp: lane r (and r + 16) owns row d0 + r
+__device__ __forceinline__ int klu_dense_diag(double* S, int lds, int d0, int lane, double* rdiag) {
+    const int r = lane & 15;
+    double a[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) a[c] = S[(d0 + c) * lds + d0 + r];
+    int flag = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const double piv = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(fabs(piv) > 0.0)) flag = 1;
+        const double rp = __drcp_rn(piv);
+        const bool below = r > j;
+        const double lij = a[j] * rp;
+        if (below) a[j] = lij;
+#pragma unroll
+        for (int c = 0; c < 16; c++)
+            if (c > j) {                 // static after unrolling: keeps a[] in registers
+                const double u = __shfl_sync(0xffffffffu, a[c], j);
+                const double t = fma(-lij, u, a[c]);
+                a[c] = below ? t : a[c];
+            }
+        if (lane == j) rdiag[j] = rp;
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) S[(d0 + c) * lds + d0 + r] = a[c];
+    }
+    return flag;
+}
+
+// C(8 x 32 strip at tile row ti, tile columns tj0..tj0+3, those in qmask) -= L(:, c0..c0+15) U(c0..c0+15, :)
+template <bool FULL>
+__device__ __forceinline__ void klu_dense_strip(double* S, int lds, int c0, int t0, int ti, int tj0, int qmask, int lane) {
+    double* Cp = S + (t0 + 8 * tj0 + 2 * (lane & 3)) * lds + t0 + 8 * ti + (lane >> 2);      // C(row, col), col += 8 per q
+    const double* Ap = S + (c0 + (lane & 3)) * lds + t0 + 8 * ti + (lane >> 2);               // L(row, c0 + k)
+    const double* Bp = S + (t0 + 8 * tj0 + (lane >> 2)) * lds + c0 + (lane & 3);              // U(c0 + k, col)
+    const int q8 = 8 * lds;
+    double acc[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (FULL || (qmask >> q & 1)) {
+            acc[q][0] = Cp[q * q8];
+            acc[q][1] = Cp[q * q8 + lds];
+        }
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+        const double av = -Ap[k4 * lds];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (FULL || (qmask >> q & 1)) klu_dmma884(acc[q][0], acc[q][1], av, Bp[q * q8 + k4]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (FULL || (qmask >> q & 1)) {
+            Cp[q * q8] = acc[q][0];
+            Cp[q * q8 + lds] = acc[q][1];
+        }
+}
+
+// LU[slot][matrix] (dir 0) -> D[matrix][entry] for the entries of the dense trailing block, and back (dir 1): 32 x 32
+// tiles through shared memory so both sides move full 256-byte rows
+__global__ void __launch_bounds__(256) k_klu_dense_pack(const int* __restrict__ dslot, int ndmap, int ndp, int Bp, double* __restrict__ LU,
+                                                        double* __restrict__ D, int dir) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    if (dir == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + ty + 8 * i;
+            if (e < ndmap) tile[ty + 8 * i][tx] = LU[(long long)dslot[e] * Bp + b0 + tx];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (e0 + tx < ndmap) D[(long long)(b0 + ty + 8 * i) * ndp + e0 + tx] = tile[tx][ty + 8 * i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (e0 + tx < ndmap) tile[tx][ty + 8 * i] = D[(long long)(b0 + ty + 8 * i) * ndp + e0 + tx];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + ty + 8 * i;
+            if (e < ndmap) LU[(long long)dslot[e] * Bp + b0 + tx] = tile[ty + 8 * i][tx];
+        }
+    }
+}
+
+// D[matrix][entry]: the block entries of one matrix, contiguous (k_klu_dense_pack), so gather and scatter are coalesced.
+// dmeta: per column of the block KLU_DENSE_META ints = {index of its first entry, row bitmap (160 bits)}
+constexpr int KLU_DENSE_THREADS = 512;
+__global__ void __launch_bounds__(KLU_DENSE_THREADS, 1) k_klu_dense_lu(int nd, const int* __restrict__ dmeta, int ndp, int batch,
+                                                         double* __restrict__ D, int* __restrict__ status) {
+    extern __shared__ double S[];
+    __shared__ double rdiag[16];
+    __shared__ int bad, tctr;
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int lds = nd + 4, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* meta = reinterpret_cast<int*>(S + nd * lds);
+    double* dm = D + (long long)b * ndp;      // this matrix' block entries, column by column, rows ascending
+    {
+        double2* S2 = reinterpret_cast<double2*>(S);
+        for (int i = tid; i < (nd * lds) >> 1; i += KLU_DENSE_THREADS) S2[i] = make_double2(0.0, 0.0);
+        for (int i = tid; i < nd * KLU_DENSE_META; i += KLU_DENSE_THREADS) meta[i] = dmeta[i];
+    }
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    {   // gather straight into shared memory (LDGSTS): every request of the CTA is in flight at once
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(S);
+        for (int c = warp; c < nd; c += KLU_DENSE_THREADS / 32) {
+            const int* m = meta + c * KLU_DENSE_META;
+            int slot = m[0];
+#pragma unroll
+            for (int w = 0; w < KLU_DENSE_META - 1; w++) {
+                const unsigned bits = (unsigned)m[1 + w];
+                if (bits >> lane & 1) {
+                    const double* src = dm + slot + __popc(bits & ((1u << lane) - 1u));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * (unsigned)(c * lds + 32 * w + lane)), "l"(src));
+                }
+                slot += __popc(bits);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0 && klu_dense_diag(S, lds, 0, lane, rdiag)) bad = 1;
+    for (int c0 = 0; c0 < nd; c0 += 16) {
+        __syncthreads();                       // diagonal chunk c0 factored, trailing update of the previous chunk done
+        const int t0 = c0 + 16, rem = nd - t0;
+        if (tid == 0) tctr = 0;
+        for (int idx = tid; idx < 2 * rem; idx += KLU_DENSE_THREADS) {
+            double v[16];
+            if (idx < rem) {                   // row r of L21: x U11 = a
+                const int r = t0 + idx;
+#pragma unroll
+                for (int q = 0; q < 16; q++) v[q] = S[(c0 + q) * lds + r];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    double acc = v[q];
+#pragma unroll
+                    for (int pp = 0; pp < q; pp++) acc = fma(-v[pp], S[(c0 + q) * lds + c0 + pp], acc);
+                    v[q] = acc * rdiag[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 16; q++) S[(c0 + q) * lds + r] = v[q];
+            } else {                           // column c of U12: L11 u = a (unit lower)
+                const int c = t0 + idx - rem;
+#pragma unroll
+                for (int q = 0; q < 16; q++) v[q] = S[c * lds + c0 + q];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    double acc = v[q];
+#pragma unroll
+                    for (int pp = 0; pp < q; pp++) acc = fma(-S[(c0 + pp) * lds + c0 + q], v[pp], acc);
+                    v[q] = acc;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; q++) S[c * lds + c0 + q] = v[q];
+            }
+        }
+        __syncthreads();
+        // trailing update by 8 x 32 strips handed out through a counter; warp 0 first updates the next diagonal chunk
+        // and factors it while the other warps work on the rest (look-ahead)
+        const int nt = rem >> 3, ntj = (nt + 3) >> 2;
+        if (warp == 0 && rem > 0) {
+            klu_dense_strip<false>(S, lds, c0, t0, 0, 0, 3, lane);
+            klu_dense_strip<false>(S, lds, c0, t0, 1, 0, 3, lane);
+            __syncwarp();
+            if (klu_dense_diag(S, lds, t0, lane, rdiag)) bad = 1;
+        }
+        const int nstrips = nt * ntj, rcp = (65536 + ntj - 1) / max(ntj, 1);
+        int mt = 0;
+        if (lane == 0) mt = atomicAdd(&tctr, 1);
+        mt = __shfl_sync(0xffffffffu, mt, 0);
+        while (mt < nstrips) {
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&tctr, 1);      // next ticket fetched under the DMMA work of this strip
+            const int ti = (mt * rcp) >> 16, tj0 = (mt - ti * ntj) * 4;
+            int qmask = (nt - tj0 >= 4) ? 15 : ((1 << (nt - tj0)) - 1);
+            if (ti < 2 && tj0 == 0) qmask &= ~3;
+            if (qmask == 15) klu_dense_strip<true>(S, lds, c0, t0, ti, tj0, 15, lane);
+            else if (qmask) klu_dense_strip<false>(S, lds, c0, t0, ti, tj0, qmask, lane);
+            mt = __shfl_sync(0xffffffffu, nxt, 0);
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c < nd; c += KLU_DENSE_THREADS / 32) {
+        const int* m = meta + c * KLU_DENSE_META;
+        int slot = m[0];
+#pragma unroll
+        for (int w = 0; w < KLU_DENSE_META - 1; w++) {
+            const unsigned bits = (unsigned)m[1 + w];
+            if (bits >> lane & 1) dm[slot + __popc(bits & ((1u << lane) - 1u))] = S[c * lds + 32 * w + lane];
+            slot += __popc(bits);
+        }
+    }
+    if (tid == 0 && bad) status[b] = ST_SINGULAR;
 }
 
 // Axt[e][b] /= Rs[row(e)][b]: the row scaling of klu_factor applied to the transposed input once
@@ -425,6 +644,10 @@ public:
     std::vector<void*> owned;
     int *d_slot_src = nullptr, *d_slot_row = nullptr, *d_rowent = nullptr, *d_status = nullptr;
     int* d_ent_row = nullptr;
+    const int *d_dense_meta = nullptr, *d_dense_slot = nullptr;
+    double* dD = nullptr;
+    int spine_nd = 0, ndmap = 0, ndp = 0;
+    size_t dense_smem = 0;
     long long* ddbg = nullptr;     // optional phase timers of the wave kernel (B200S_KLU_DEBUG=1)
     long long* d_rowptr = nullptr;
     long long nslots = 0, nnzA = 0;
@@ -438,7 +661,7 @@ public:
     ~KluDevice() {
         cudaSetDevice(device);
         for (void* p : owned) cudaFree(p);
-        cudaFree(dA); cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(dX); cudaFree(dB); cudaFree(d_status);
+        cudaFree(dA); cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(dX); cudaFree(dB); cudaFree(d_status); cudaFree(dD);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -497,6 +720,16 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         if ((rc = up(&er, ent_row))) return rc;
         d_ent_row = (int*)er;
         use_wave = P.max_col_len <= KLU_WAVE_ROWS;
+        WD.spine0 = use_wave ? P.spine0 : P.n;
+        spine_nd = use_wave ? P.spine_nd : 0;
+        if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;
+        if ((rc = up(&d_dense_slot, P.dense_slot))) return rc;
+        ndmap = (int)P.dense_slot.size();
+        ndp = (ndmap + 31) & ~31;
+        dense_smem = (size_t)spine_nd * (spine_nd + 4) * sizeof(double) + (size_t)spine_nd * KLU_DENSE_META * sizeof(int);
+        if (spine_nd > 0)
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_dense_lu, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)dense_smem));
         if (use_wave)
             CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
     }
@@ -526,11 +759,12 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
 int KluDevice::ensure_batch(int b) {
     const int bp = (b + 31) & ~31;
     if (bp <= Bp) { batch = b; return ST_OK; }
-    cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(d_status);
-    dAxt = dRs = dLU = nullptr; d_status = nullptr; Bp = 0;
+    cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(d_status); cudaFree(dD);
+    dAxt = dRs = dLU = dD = nullptr; d_status = nullptr; Bp = 0;
     CUDA_TRY(cudaMalloc((void**)&dAxt, std::max<long long>(nnzA, 1) * bp * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dRs, std::max<long long>(n, 1) * (long long)bp * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dLU, std::max<long long>(nslots, 1) * bp * sizeof(double)));
+    if (spine_nd > 0) CUDA_TRY(cudaMalloc((void**)&dD, (size_t)ndp * bp * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&d_status, bp * sizeof(int)));
     Bp = bp; batch = b;
     return ST_OK;
@@ -567,6 +801,13 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
             k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
         k_klu_refactor_wave<<<Bp / 32, KLU_WAVE_WARPS * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
+        if (spine_nd > 0)
+        {
+            const dim3 tg(ndp / 32, Bp / 32);
+            k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, Bp, dLU, dD, 0);
+            k_klu_dense_lu<<<batch, KLU_DENSE_THREADS, dense_smem, stream>>>(spine_nd, d_dense_meta, ndp, batch, dD, d_status);
+            k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, Bp, dLU, dD, 1);
+        }
         CUDA_TRY(cudaEventRecord(ev[5], stream));
     } else {
         k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, 0, nslots, Bp, dAxt, dRs, dLU, 0);

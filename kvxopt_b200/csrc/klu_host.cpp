@@ -393,6 +393,42 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         std::vector<i64> pos(P.rowptr.begin(), P.rowptr.end() - 1);
         for (i64 p = 0; p < S.nnz; p++) P.rowent[pos[pinvnum[S.Ai[p]]]++] = (i32)p;
     }
+    // ---- dense trailing block: the largest nd <= KLU_DENSE_MAX (multiple of 16) inside the last BTF block whose
+    // L+U pattern restricted to the last nd rows/columns is at least 30 % dense
+    P.upd_end.assign(n, 0);
+    for (i32 k = 0; k < n; k++) P.upd_end[k] = P.upd_ptr[k + 1];
+    P.spine0 = n; P.spine_nd = 0;
+    {
+        const i32 lastblk = S.nblocks > 0 ? S.R[S.nblocks] - S.R[S.nblocks - 1] : 0;
+        for (i32 nd = std::min<i32>(KLU_DENSE_MAX, (lastblk / 16) * 16); nd >= 48; nd -= 16) {
+            const i32 s0 = n - nd;
+            i64 cnt = 0;
+            for (i32 k = s0; k < n; k++)
+                for (i64 sl = P.cbeg[k]; sl < P.cbeg[k + 1]; sl++) if (P.slot_row[sl] >= s0) cnt++;
+            if ((double)cnt >= 0.30 * nd * nd) { P.spine0 = s0; P.spine_nd = nd; break; }
+        }
+        if (P.spine_nd > 0) {
+            const i32 s0 = P.spine0;
+            P.dense_meta.assign((size_t)P.spine_nd * KLU_DENSE_META, 0);
+            for (i32 k = s0; k < n; k++) {
+                i64 u = P.upd_ptr[k];
+                while (u < P.upd_ptr[k + 1] && P.upd_src[u] < s0) u++;
+                P.upd_end[k] = u;
+                // slots of a column ascend by row: the block entries are its tail
+                i32* m = P.dense_meta.data() + (size_t)(k - s0) * KLU_DENSE_META;
+                i64 sl = P.cbeg[k];
+                while (sl < P.cbeg[k + 1] && P.slot_row[sl] < s0) sl++;
+                m[0] = (i32)P.dense_slot.size();
+                const i64 first = sl;
+                for (; sl < P.cbeg[k + 1]; sl++) {
+                    const i32 r = P.slot_row[sl] - s0;
+                    P.dense_slot.push_back((i32)sl);
+                    if (r < 0 || (sl > first && P.slot_row[sl] <= P.slot_row[sl - 1])) throw std::logic_error("klu plan: column slots not ascending by row");
+                    m[1 + (r >> 5)] |= (i32)(1u << (r & 31));
+                }
+            }
+        }
+    }
     // wave schedule
     P.col_roff.assign(n, 0);
     P.upd_split.assign(n, 0);
@@ -404,7 +440,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         auto blob_bytes = [&](i32 k0, i32 k1) {
             i64 nu = 0, nd = 0;
             for (i32 c = k0; c < k1; c++)
-                for (i64 u = P.upd_ptr[c]; u < P.upd_ptr[c + 1]; u++)
+                for (i64 u = P.upd_ptr[c]; u < P.upd_end[c]; u++)
                     if (P.upd_src[u] >= k0) { nu++; nd += P.upd_cnt[u]; }
             return (i64)(2 * KLU_WAVE_WARPS) * 4 + nu * 16 + ((nd * 2 + 15) / 16) * 16;
         };
@@ -434,9 +470,9 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             srcs.clear();
             for (i32 c = k0; c < P.wave_col0[w + 1]; c++) {
                 i64 u = P.upd_ptr[c];
-                while (u < P.upd_ptr[c + 1] && P.upd_src[u] < k0) { srcs.push_back(P.upd_src[u]); u++; }
+                while (u < P.upd_end[c] && P.upd_src[u] < k0) { srcs.push_back(P.upd_src[u]); u++; }
                 P.upd_split[c] = u;
-                if (u < P.upd_ptr[c + 1]) P.wave_hasdep[w] = 1;
+                if (u < P.upd_end[c]) P.wave_hasdep[w] = 1;
             }
             std::sort(srcs.begin(), srcs.end());
             srcs.erase(std::unique(srcs.begin(), srcs.end()), srcs.end());
@@ -521,7 +557,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             for (i32 c = k0; c < k1; c++) {
                 const i64 cb = P.cbeg[c];
                 hdr[2 * (c - k0)] = (uint32_t)(upd.size() / 4);
-                for (i64 u = P.upd_split[c]; u < P.upd_ptr[c + 1]; u++) {
+                for (i64 u = P.upd_split[c]; u < P.upd_end[c]; u++) {
                     {
                         const i32 j = P.upd_src[u];
                         const uint32_t srcrow0 = (uint32_t)(P.col_roff[j] + (P.lslot0[j] - P.cbeg[j]));   // first L row of the source in xs

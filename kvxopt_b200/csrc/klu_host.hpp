@@ -83,6 +83,13 @@ struct KluPlan {
     std::vector<i64> wblob_ptr;       // nwaves+1, in 16-byte units
     std::vector<uint32_t> wblob;
     i32 max_col_len = 0;
+    // dense trailing block ("spine"): the last spine_nd columns are nearly dense after fill (76 % of the work of a
+    // power-flow Jacobian).  The wave kernel applies to them only the updates from columns < spine0; the block itself
+    // is then factored per matrix by a dense tensor-core LU (k_klu_dense_lu).  spine_nd = 0: disabled.
+    i32 spine0 = 0, spine_nd = 0;
+    std::vector<i64> upd_end;         // n: end of the updates the wave kernel applies to column k
+    std::vector<i32> dense_meta;            // per block column KLU_DENSE_META ints: index of its first block entry, row bitmap
+    std::vector<i32> dense_slot;            // value slot of every block entry (column by column, rows ascending)
     // solve schedule uses Lp/Li/Up/Ui/Fp/Fi of the numeric object with slots: L(i,k) at lslot, etc.
     std::vector<i32> lslot0;          // per column: first L slot (below diagonal)
     std::vector<i32> fslot0;          // per column: first F slot
@@ -96,6 +103,7 @@ constexpr uint32_t KLU_SKIP = 0xffffffffu;
 constexpr int KLU_MAXSEG = 15;        // matched segments per (batch, column); the host closes a batch before it overflows
 constexpr int KLU_REC_U32 = 16 + KLU_CHUNK_ROWS / 2;   // per (batch, column): {nseg, segs[15]} + 64 uint16 destination rows
 constexpr int KLU_BLOB_BYTES = 8192;  // cap of the in-wave update blob
+constexpr int KLU_DENSE_MAX = 160, KLU_DENSE_META = 1 + KLU_DENSE_MAX / 32;    // largest dense trailing block (shared memory: 160 x 164 doubles)
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan);
 
 }  // namespace b200s

@@ -1,0 +1,32 @@
+"""Small end-to-end pass over every kernel for compute-sanitizer (memcheck): Cholesky (small + tiled fronts, solves,
+sys modes, diag, getfactor) and KLU (factor, batch refactor wave kernel, solves)."""
+import os, sys
+import numpy as np, scipy.sparse as sp
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from kvxopt_b200 import _lib as L, cholmod, klu
+from bench import lap3d_lower
+def lap(nx):
+    Al = lap3d_lower(nx); perm = np.zeros(Al.shape[0], np.int64); L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm)); return Al, perm
+for nx in (6, 14):
+    Al, perm = lap(nx); n = Al.shape[0]
+    F = cholmod.symbolic(Al, p=perm); cholmod.numeric(Al, F)
+    for s in (0, 4, 5, 7, 8):
+        X = np.ones((n, 3), order="F"); cholmod.solve(F, X, sys=s)
+    cholmod.diag(F); cholmod.getfactor(F)
+    print("chol", nx, cholmod.factor_info(F)["max_front_rows"], "ok", flush=True)
+rng = np.random.default_rng(0)
+M = sp.random(700, 700, density=0.01, random_state=rng, format="csc"); A = (M + M.T + sp.identity(700) * 20).tocsc()
+Al = sp.tril(A).tocsc(); Al.sort_indices(); F = cholmod.symbolic(Al); cholmod.numeric(Al, F); X = np.ones((700, 2), order="F"); cholmod.solve(F, X)
+print("chol rand ok", flush=True)
+z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "bp_800.npz"))
+K = sp.csc_matrix((z["values"], z["rowind"].astype(np.int64), z["colptr"]), shape=(int(z["n"]),) * 2)
+Fs = klu.symbolic(K); Fn = klu.numeric(K, Fs)
+vals = K.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(40, K.nnz)))
+klu.refactor_batch(Fn, vals); B = rng.standard_normal((40, 2, K.shape[0])); klu.solve_batch(Fn, B); klu.solve_batch(Fn, B, trans="T")
+klu.get_numeric(K, Fs, Fn)
+z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ACTIVSg2000.npz"))
+K = sp.csc_matrix((z["values"], z["rowind"].astype(np.int64), z["colptr"]), shape=(int(z["n"]),) * 2)
+Fs = klu.symbolic(K); Fn = klu.numeric(K, Fs)
+vals = K.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(33, K.nnz)))
+klu.refactor_batch(Fn, vals); B = rng.standard_normal((33, 1, K.shape[0])); klu.solve_batch(Fn, B)
+print("klu ok", flush=True)
