@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace b200s {
@@ -59,6 +60,7 @@ int device_count() {
 // ---------------------------------------------------------------------------------------------------
 struct FrontD {
     long long loff, uoff, reloff, rowptr;
+    long long ioff;               // large fronts: offset of the inverted diagonal sub-blocks in Minv (MINV_BLK per block column)
     int col0, nc, nr, ld;
     int nchild, childptr, parent, level;
 };
@@ -95,6 +97,31 @@ __device__ __forceinline__ int find_group(const int* prefix, int ng, int b) {
     int lo = 0, hi = ng;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= b) lo = mid; else hi = mid; }
     return lo;
+}
+
+// Launch metadata of the solve kernels passed BY VALUE (constant bank) when a block step covers few fronts -- which is
+// every step of the top levels, where the steps are many and short: no dependent global loads (group prefix -> front id
+// -> front record) ahead of the first data access.  ng == 0: read the schedule arrays in global memory instead.
+struct FrontS { long long loff, rowptr, ioff; int nc, nr, ld, col0; };
+constexpr int MAXG = 32;
+struct SolveGroups { int ng; int prefix[MAXG + 1]; FrontS fr[MAXG]; };
+__device__ __forceinline__ FrontS load_front(const SolveGroups& sg, const int* gfront, const FrontD* F, int g) {
+    if (sg.ng) return sg.fr[g];
+    const FrontD fd = F[gfront[g]];
+    FrontS f;
+    f.loff = fd.loff; f.rowptr = fd.rowptr; f.ioff = fd.ioff; f.nc = fd.nc; f.nr = fd.nr; f.ld = fd.ld; f.col0 = fd.col0;
+    return f;
+}
+__device__ __forceinline__ int locate_group(const SolveGroups& sg, const int* gprefix, int ngroups, int b, int& tile) {
+    if (sg.ng) {
+        int g = 0;
+        while (g + 1 < sg.ng && sg.prefix[g + 1] <= b) g++;
+        tile = b - sg.prefix[g];
+        return g;
+    }
+    const int g = find_group(gprefix, ngroups, b);
+    tile = b - gprefix[g];
+    return g;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -635,8 +662,49 @@ __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const
 }
 
 // ---- large fronts: the same solves split over many CTAs, one 128-column block step at a time ------------------
-constexpr int SOLVE_FT = 256;    // rows per CTA in the forward update
-constexpr int SOLVE_BT = 1024;   // rows per CTA in the backward (transposed) update
+// The 32 x 32 diagonal sub-blocks of every 128-column block are inverted once per factorization (k_diag_inverse), so
+// a block step is four small matrix-vector products instead of a 128-step substitution chain.
+constexpr int SOLVE_FT = 64;     // rows per CTA in the forward update  (256 threads = 64 rows x 4 column quarters)
+constexpr int SOLVE_BT = 256;    // rows per CTA in the backward (transposed) update
+constexpr int SB = 32;           // inverted diagonal sub-block
+constexpr int MINV_HALF = (NB / SB) * SB * SB;  // the four inverse sub-blocks of a 128-column block, column-major
+constexpr int MINV_BLK = 2 * MINV_HALF;         // ... followed by their transposes (backward solve)
+constexpr int LDD = NB + 2;      // smem stride of the staged diagonal block (even: 16-byte LDGSTS rows)
+constexpr int LDM = SB;          // smem stride of a staged inverse sub-block (always read column-wise)
+static constexpr size_t SMEM_SDIAG = (size_t)(NB * LDD + MINV_HALF + NB) * sizeof(double);
+
+// inverse of the SB x SB lower-triangular diagonal sub-blocks: one CTA per 128-column block, one warp per sub-block,
+// lane j solves L x = e_j by substitution
+__global__ void __launch_bounds__(128) k_diag_inverse(const int* __restrict__ blkfront, const int* __restrict__ blkkb,
+                                                      const FrontD* __restrict__ F, const double* __restrict__ L,
+                                                      double* __restrict__ Minv) {
+    __shared__ double D[NB / SB][SB][SB + 1];
+    const FrontD f = F[blkfront[blockIdx.x]];
+    const int kb = blkkb[blockIdx.x], k0 = kb * NB, w = min(NB, f.nc - k0);
+    const int s = threadIdx.x >> 5, lane = threadIdx.x & 31, b0 = s * SB, wb = min(SB, w - b0);
+    if (wb <= 0) return;
+    const double* P = L + f.loff + (long long)(k0 + b0) * f.ld + k0 + b0;
+    for (int c = 0; c < SB; c++) {
+        double v = (lane == c) ? 1.0 : 0.0;
+        if (c < wb && lane < wb && lane >= c) v = P[(long long)c * f.ld + lane];
+        D[s][lane][c] = v;
+    }
+    __syncwarp();
+    double x[SB];
+#pragma unroll
+    for (int i = 0; i < SB; i++) {
+        double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k++) acc = fma(-D[s][i][k], x[k], acc);
+        x[i] = acc / D[s][i][i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < SB; i++) D[s][i][lane] = x[i];      // element (i, lane) of the inverse
+    __syncwarp();
+    double* out = Minv + f.ioff + (long long)kb * MINV_BLK + s * SB * SB;
+    for (int c = 0; c < SB; c++) { out[c * SB + lane] = D[s][lane][c]; out[MINV_HALF + c * SB + lane] = D[s][c][lane]; }
+}
 
 // forward: t = [x(cols); 0] + children's update vectors
 __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list, const FrontD* __restrict__ F,
@@ -669,162 +737,240 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const int* __restrict__ list
     for (int i = threadIdx.x; i < f.nr; i += 256) t[i] = xg[rw[i]];
 }
 
+// stage the inverse sub-blocks (or their transposes) and the part of the 128-block below them in shared memory:
+// 16-byte LDGSTS, all in flight.  Row pairs may reach one row past w (w odd): inside the padded panel, never used.
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void stage_diag_block(const double* __restrict__ P, int ld, int k0, int w,
+                                                 const double* __restrict__ minv, double* Ls, double* Ms, int tid) {
+    const unsigned lbase = (unsigned)__cvta_generic_to_shared(Ls), mbase = (unsigned)__cvta_generic_to_shared(Ms);
+    const int nm = min(NB / SB, (w + SB - 1) / SB) * SB * SB;
+    for (int i = tid * 2; i < nm; i += 512) cp_async16(mbase + 8u * (unsigned)i, minv + i);
+    for (int idx = tid; idx < NB * (NB / 2); idx += 256) {
+        const int c = idx >> 6, r = (idx & 63) * 2;
+        if (c < w && r < w && r >= ((c >> 5) + 1) * SB) cp_async16(lbase + 8u * (unsigned)(c * LDD + r), P + (long long)(k0 + c) * ld + k0 + r);
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
 // forward, block kb: solve the (<=128)^2 diagonal block for t[k0..k0+w)
-__global__ void __launch_bounds__(256) k_fwd_diag(const int* __restrict__ gfront, int kb, const FrontD* __restrict__ F,
-                                                  const double* __restrict__ L, double* __restrict__ T, long long tstride,
+__global__ void __launch_bounds__(256) k_fwd_diag(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, int kb, const FrontD* __restrict__ F,
+                                                  const double* __restrict__ L, const double* __restrict__ Minv,
+                                                  double* __restrict__ T, long long tstride,
                                                   double* __restrict__ X, long long xstride) {
-    __shared__ double D[CB][CB + 1];
-    __shared__ double ts[NB];
-    const FrontD f = F[gfront[blockIdx.x]];
+    extern __shared__ double sm[];
+    double* Ls = sm;                       // [col][row], stride LDD
+    double* Ms = Ls + NB * LDD;            // [sub-block][col][row], stride LDM
+    double* ts = Ms + MINV_HALF;
+    const FrontS f = load_front(sg, gfront, F, blockIdx.x);
     double* t = T + blockIdx.y * tstride + f.rowptr;
     double* x = X + blockIdx.y * xstride + f.col0;
-    const double* P = L + f.loff;
-    const int ld = f.ld, tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int k0 = kb * NB, w = min(NB, f.nc - k0);
-    if (tid < w) ts[tid] = t[k0 + tid];
+    stage_diag_block(L + f.loff, f.ld, k0, w, Minv + f.ioff + (long long)kb * MINV_BLK, Ls, Ms, tid);
+    if (tid < NB) ts[tid] = (tid < w) ? t[k0 + tid] : 0.0;
     __syncthreads();
-    for (int b0 = 0; b0 < w; b0 += CB) {
-        const int wb = min(CB, w - b0);
-        for (int idx = tid; idx < wb * wb; idx += 256) {
-            int c = idx / wb, r = idx - c * wb;
-            D[r][c] = (r >= c) ? P[(long long)(k0 + b0 + c) * ld + k0 + b0 + r] : 0.0;
+    for (int b0 = 0; b0 < w; b0 += SB) {
+        const double* M = Ms + (b0 / SB) * SB * SB;
+        double xv = 0.0;
+        if (tid < 32) {                    // x_sub = inv(L_sub) t_sub
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int c = 0; c < SB; c += 2) { a0 = fma(M[c * LDM + lane], ts[b0 + c], a0); a1 = fma(M[(c + 1) * LDM + lane], ts[b0 + c + 1], a1); }
+            xv = a0 + a1;
         }
         __syncthreads();
-        if (tid < 32) {
-            double v = (lane < wb) ? ts[b0 + lane] : 0.0;
-            for (int qq = 0; qq < wb; qq++) {
-                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
-                if (lane == qq) v = xq;
-                else if (lane > qq && lane < wb) v -= xq * D[lane][qq];
-            }
-            if (lane < wb) ts[b0 + lane] = v;
-        }
+        if (tid < 32) ts[b0 + lane] = xv;
         __syncthreads();
-        // rows of this 128-block below the sub-block
-        for (int r = b0 + wb + tid; r < w; r += 256) {
-            double acc = ts[r];
-            const double* col = P + (long long)(k0 + b0) * ld + k0 + r;
-            for (int qq = 0; qq < wb; qq++) acc -= col[(long long)qq * ld] * ts[b0 + qq];
-            ts[r] = acc;
+        const int r = b0 + SB + tid;       // rows of this 128-block below the sub-block
+        if (r < w) {
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int c = 0; c < SB; c += 2) { a0 = fma(Ls[(b0 + c) * LDD + r], ts[b0 + c], a0); a1 = fma(Ls[(b0 + c + 1) * LDD + r], ts[b0 + c + 1], a1); }
+            ts[r] -= a0 + a1;
         }
         __syncthreads();
     }
     if (tid < w) { t[k0 + tid] = ts[tid]; x[k0 + tid] = ts[tid]; }
 }
-// forward, block kb: t[r] -= L[r, blk] * x_blk for a 256-row tile of the rows below the block
-__global__ void __launch_bounds__(256) k_fwd_upd(const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
+// stage a 64-row x w-column slice of the panel (rows r0.. with r0 even, columns k0..) in shared memory as S[col][64]:
+// thread = (row pair, group of 16 columns) issues its 16 16-byte LDGSTS back to back, so the whole 64 KB slice is in
+// flight at once.  A pair may reach row nr (nr odd): inside the padded panel (ld even), masked by the callers.
+__device__ __forceinline__ void stage_rows64(const double* __restrict__ P, int ld, int nr, int k0, int w, int r0, double* S, int tid) {
+    const int rp = tid & 31, cg = tid >> 5, r = r0 + 2 * rp;
+    if (r >= nr) return;
+    const int wq = min(16, w - cg * 16);
+    const double* col = P + (long long)(k0 + cg * 16) * ld + r;
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(S) + 8u * (unsigned)(cg * 16 * 64 + 2 * rp);
+#pragma unroll 8
+    for (int j = 0; j < wq; j++) cp_async16(sb + 8u * 64u * (unsigned)j, col + (long long)j * ld);
+}
+
+// forward, block kb: t[r] -= L[r, blk] * x_blk for a 64-row tile of the rows below the block
+__global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
                                                  double* __restrict__ T, long long tstride) {
+    extern __shared__ double sm[];
+    double* S = sm;                        // [128 columns][64 rows]
     __shared__ double xs[NB];
-    const int g = find_group(gprefix, ngroups, blockIdx.x);
-    const int tile = blockIdx.x - gprefix[g];
-    const FrontD f = F[gfront[g]];
+    __shared__ double red[4][SOLVE_FT];
+    int tile;
+    const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
+    const FrontS f = load_front(sg, gfront, F, g);
     double* t = T + blockIdx.y * tstride + f.rowptr;
-    const double* P = L + f.loff;
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x;
-    if (tid < w) xs[tid] = t[k0 + tid];
+    const int rr = tid & (SOLVE_FT - 1), cq = tid >> 6;
+    const int rb = k0 + w, r0 = (rb & ~1) + tile * SOLVE_FT;      // tiles start at an even row (16-byte LDGSTS)
+    stage_rows64(L + f.loff, f.ld, f.nr, k0, w, r0, S, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid < NB) xs[tid] = (tid < w) ? t[k0 + tid] : 0.0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const int r = k0 + w + tile * SOLVE_FT + tid;
-    if (r < f.nr) {
-        const double* col = P + (long long)k0 * f.ld + r;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        int q = 0;
-        for (; q + 16 <= w; q += 16) {          // 16 independent loads in flight per thread
-            double v[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = col[(long long)(q + j) * f.ld];
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                a0 += v[j] * xs[q + j]; a1 += v[j + 1] * xs[q + j + 1];
-                a2 += v[j + 2] * xs[q + j + 2]; a3 += v[j + 3] * xs[q + j + 3];
-            }
-        }
-        for (; q < w; q++) a0 += col[(long long)q * f.ld] * xs[q];
-        t[r] -= (a0 + a1) + (a2 + a3);
+    double a0 = 0, a1 = 0;
+    if (r0 + rr < f.nr && r0 + rr >= rb) {
+        const int wq = min(32, w - cq * 32);
+        const double* sp = S + cq * 32 * 64 + rr;
+        int j = 0;
+        for (; j + 1 < wq; j += 2) { a0 = fma(sp[j * 64], xs[cq * 32 + j], a0); a1 = fma(sp[(j + 1) * 64], xs[cq * 32 + j + 1], a1); }
+        if (j < wq) a0 = fma(sp[j * 64], xs[cq * 32 + j], a0);
     }
+    red[cq][rr] = a0 + a1;
+    __syncthreads();
+    if (tid < SOLVE_FT && r0 + tid < f.nr && r0 + tid >= rb) t[r0 + tid] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
 }
-// backward, block kb: partial[q] = sum over a 1024-row tile of the rows below the block of L[r, k0+q] * t[r]
-__global__ void __launch_bounds__(256) k_bwd_upd(const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
+// backward, block kb: partial[q] = sum over a 256-row tile of the rows below the block of L[r, k0+q] * t[r].
+// Four 64-row slices go through three shared-memory buffers (>= 128 KB in flight); thread = (row, column quarter);
+// the 32 per-lane column sums of a warp are combined by a halving butterfly
+__global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
                                                  const double* __restrict__ T, long long tstride, double* __restrict__ part,
                                                  long long pstride) {
-    __shared__ double tsm[SOLVE_BT];
-    const int g = find_group(gprefix, ngroups, blockIdx.x);
-    const int tile = blockIdx.x - gprefix[g];
-    const FrontD f = F[gfront[g]];
+    extern __shared__ double sm[];         // 3 buffers of [128 columns][64 rows]
+    __shared__ double red[8][32];
+    int tile;
+    const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
+    const FrontS f = load_front(sg, gfront, F, g);
     const double* t = T + blockIdx.y * tstride + f.rowptr;
     const double* P = L + f.loff;
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = k0 + w + tile * SOLVE_BT, r1 = min(f.nr, r0 + SOLVE_BT);
-    for (int i = tid; i < r1 - r0; i += 256) tsm[i] = t[r0 + i];
-    __syncthreads();
-    double* out = part + blockIdx.y * pstride + (long long)blockIdx.x * NB;
-    for (int q = warp; q < w; q += 8) {
-        const double* col = P + (long long)(k0 + q) * f.ld + r0;
-        double s0 = 0, s1 = 0;
-        int i = lane;
-        const int nrow = r1 - r0;
-        for (; i + 224 < nrow; i += 256) {      // 8 independent loads in flight per lane
-            double v[8];
+    const int rr = tid & 63, cq = tid >> 6;
+    const int wq = min(32, w - cq * 32);
+    const int rb = k0 + w, r0 = (rb & ~1) + tile * SOLVE_BT;
+    constexpr int NSUB = SOLVE_BT / 64;
+    double p[32];
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = col[i + 32 * j];
+    for (int j = 0; j < 32; j++) p[j] = 0.0;
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) { s0 += v[j] * tsm[i + 32 * j]; s1 += v[j + 1] * tsm[i + 32 * (j + 1)]; }
-        }
-        for (; i < nrow; i += 32) s0 += col[i] * tsm[i];
-        double sv = s0 + s1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        if (lane == 0) out[q] = sv;
+    for (int sub = 0; sub < 3; sub++) {
+        stage_rows64(P, f.ld, f.nr, k0, w, r0 + sub * 64, sm + sub * NB * 64, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-}
-// backward, block kb: z = t_blk - sum of the tile partials (fixed order), then solve L11^T x = z
-__global__ void __launch_bounds__(256) k_bwd_diag(const int* __restrict__ gfront, const int* __restrict__ gprefix, int kb,
-                                                  const FrontD* __restrict__ F, const double* __restrict__ L,
-                                                  double* __restrict__ T, long long tstride, double* __restrict__ X,
-                                                  long long xstride, const double* __restrict__ part, long long pstride) {
-    __shared__ double D[CB][CB + 1];
-    __shared__ double zs[NB];
-    const FrontD f = F[gfront[blockIdx.x]];
-    double* t = T + blockIdx.y * tstride + f.rowptr;
-    double* x = X + blockIdx.y * xstride + f.col0;
-    const double* P = L + f.loff;
-    const int ld = f.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k0 = kb * NB, w = min(NB, f.nc - k0);
-    const int tile0 = gprefix[blockIdx.x], tile1 = gprefix[blockIdx.x + 1];
-    if (tid < w) {
-        double z = t[k0 + tid];
-        const double* pp = part + blockIdx.y * pstride + tid;
-        for (int tl = tile0; tl < tile1; tl++) z -= pp[(long long)tl * NB];
-        zs[tid] = z;
-    }
-    __syncthreads();
-    const int nsb = (w + CB - 1) / CB;
-    for (int sbk = nsb - 1; sbk >= 0; sbk--) {
-        const int b0 = sbk * CB, wb = min(CB, w - b0);
-        for (int idx = tid; idx < wb * wb; idx += 256) {
-            int c = idx / wb, r = idx - c * wb;
-            D[r][c] = (r >= c) ? P[(long long)(k0 + b0 + c) * ld + k0 + b0 + r] : 0.0;
-        }
-        // contributions of the already solved rows of this 128-block (below the sub-block)
-        for (int qq = warp; qq < wb; qq += 8) {
-            const double* col = P + (long long)(k0 + b0 + qq) * ld + k0;
-            double sv = 0.0;
-            for (int r = b0 + wb + lane; r < w; r += 32) sv += col[r] * zs[r];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-            if (lane == 0) zs[b0 + qq] -= sv;
+    for (int sub = 0; sub < NSUB; sub++) {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncthreads();
+        const int r = r0 + sub * 64 + rr;
+        if (r < f.nr && r >= rb) {
+            const double tv = t[r];
+            const double* sp = sm + (sub % 3) * NB * 64 + cq * 32 * 64 + rr;
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (j < wq) p[j] = fma(sp[j * 64], tv, p[j]);
         }
         __syncthreads();
-        if (tid < 32) {
-            double v = (lane < wb) ? zs[b0 + lane] : 0.0;
-            for (int qq = wb - 1; qq >= 0; qq--) {
-                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
-                if (lane == qq) v = xq;
-                else if (lane < qq) v -= xq * D[qq][lane];
-            }
-            if (lane < wb) zs[b0 + lane] = v;
+        if (sub + 3 < NSUB) stage_rows64(P, f.ld, f.nr, k0, w, r0 + (sub + 3) * 64, sm + (sub % 3) * NB * 64, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // after the step with offset o the lanes with bit o set hold the upper half of the surviving columns: lane l ends
+    // with the sum of column l
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; j++) {
+            const double send = up ? p[j] : p[j + o];
+            const double keep = up ? p[j + o] : p[j];
+            p[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
+    }
+    red[warp][lane] = p[0];
+    __syncthreads();
+    if (tid < NB) part[blockIdx.y * pstride + (long long)blockIdx.x * NB + tid] = red[2 * (tid >> 5)][tid & 31] + red[2 * (tid >> 5) + 1][tid & 31];
+}
+// backward, block kb: z = t_blk - sum of the tile partials (fixed order), then solve L11^T x = z
+constexpr int PT_CHUNK = 48;     // partial rows staged per pass
+static constexpr size_t SMEM_FUPD = (size_t)NB * 64 * sizeof(double), SMEM_BUPD = 3 * SMEM_FUPD;
+static constexpr size_t SMEM_BDIAG = SMEM_SDIAG + (size_t)PT_CHUNK * NB * sizeof(double);
+__global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int kb,
+                                                  const FrontD* __restrict__ F, const double* __restrict__ L,
+                                                  const double* __restrict__ Minv,
+                                                  double* __restrict__ T, long long tstride, double* __restrict__ X,
+                                                  long long xstride, const double* __restrict__ part, long long pstride) {
+    extern __shared__ double sm[];
+    double* Ls = sm;
+    double* Ms = Ls + NB * LDD;
+    double* zs = Ms + MINV_HALF;
+    double* Ps = zs + NB;                  // [PT_CHUNK][128] staged partial sums
+    __shared__ double zh[NB];
+    const FrontS f = load_front(sg, gfront, F, blockIdx.x);
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    double* x = X + blockIdx.y * xstride + f.col0;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int k0 = kb * NB, w = min(NB, f.nc - k0);
+    const int tile0 = sg.ng ? sg.prefix[blockIdx.x] : gprefix[blockIdx.x], tile1 = sg.ng ? sg.prefix[blockIdx.x + 1] : gprefix[blockIdx.x + 1];
+    const double* pp = part + blockIdx.y * pstride + (long long)tile0 * NB;
+    const unsigned pbase = (unsigned)__cvta_generic_to_shared(Ps);
+    {
+        const int cnt = min(PT_CHUNK, tile1 - tile0) * NB;
+        for (int i = tid * 2; i < cnt; i += 512)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pbase + 8u * (unsigned)i), "l"(pp + i));
+    }
+    stage_diag_block(L + f.loff, f.ld, k0, w, Minv + f.ioff + (long long)kb * MINV_BLK + MINV_HALF, Ls, Ms, tid);   // commits + waits for all
+    __syncthreads();
+    {   // two threads per column sum alternate partial rows; combined in a fixed order
+        const int q = tid & (NB - 1), h = tid >> 7;
+        double z = 0.0;
+        for (int c0 = 0; c0 < tile1 - tile0; c0 += PT_CHUNK) {
+            const int cnt = min(PT_CHUNK, tile1 - tile0 - c0);
+            if (c0 > 0) {
+                __syncthreads();
+                for (int i = tid * 2; i < cnt * NB; i += 512)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pbase + 8u * (unsigned)i), "l"(pp + (long long)c0 * NB + i));
+                asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+            }
+            for (int tl = h; tl < cnt; tl += 2) z += Ps[tl * NB + q];
+        }
+        if (h == 1) zh[q] = z;
+        __syncthreads();
+        if (h == 0) zs[q] = (q < w) ? t[k0 + q] - (z + zh[q]) : 0.0;
+    }
+    __syncthreads();
+    const int nsb = (w + SB - 1) / SB;
+    for (int sbk = nsb - 1; sbk >= 0; sbk--) {
+        const int b0 = sbk * SB;
+        // contributions of the already solved rows of this 128-block (below the sub-block): 8 threads per column
+        {
+            const int q = tid >> 3, gq = tid & 7;
+            double sv = 0.0;
+            for (int r = b0 + SB + gq; r < w; r += 8) sv = fma(Ls[(b0 + q) * LDD + r], zs[r], sv);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+            if (gq == 0) zs[b0 + q] -= sv;
+        }
+        __syncthreads();
+        double xv = 0.0;
+        if (tid < 32) {                    // x_sub = inv(L_sub)^T z_sub
+            const double* M = Ms + sbk * SB * SB;          // transposed inverse, column-major
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int c = 0; c < SB; c += 2) { a0 = fma(M[c * LDM + lane], zs[b0 + c], a0); a1 = fma(M[(c + 1) * LDM + lane], zs[b0 + c + 1], a1); }
+            xv = a0 + a1;
+        }
+        __syncthreads();
+        if (tid < 32) zs[b0 + lane] = xv;
         __syncthreads();
     }
     if (tid < w) { t[k0 + tid] = zs[tid]; x[k0 + tid] = zs[tid]; }
@@ -859,6 +1005,7 @@ __global__ void k_diag(const FrontD* __restrict__ F, int ns, const double* __res
 // ---------------------------------------------------------------------------------------------------
 struct Launch {            // one grouped launch: groups [goff, goff+ng) in the schedule arrays, `ctas` CTAs
     int goff = 0, ng = 0, ctas = 0;
+    int sgi = -1;          // solve launches with few groups: index of the by-value metadata in CholDevice::sgroups
 };
 struct LevelSched {
     int ea_off = 0, ea_cnt = 0;
@@ -886,9 +1033,17 @@ public:
     double* ddiag = nullptr;       // scratch for factored diagonal blocks of one panel launch
     EAItem* dea = nullptr;
     std::vector<LevelSched> levels;
+    std::vector<SolveGroups> sgroups;   // sgroups[0] = empty (use the schedule arrays)
+    std::map<int, cudaGraphExec_t> solve_graphs;   // key: columns * 4 + forward * 2 + backward
+    bool use_graphs = true;
+    void drop_graphs() { for (auto& kv : solve_graphs) cudaGraphExecDestroy(kv.second); solve_graphs.clear(); }
     i64 solve_cols = 0;            // capacity (columns) of dT / dX
     int max_solve_ctas = 1;        // most CTAs of one backward-update launch (sizes the partial-sum buffer)
     double* dpart = nullptr;
+    double* dMinv = nullptr;       // inverted 32 x 32 diagonal sub-blocks of the large fronts (solve phase)
+    int *dinv_front = nullptr, *dinv_kb = nullptr;
+    int ninvblk = 0;
+    bool minv_valid = false;
     bool numeric = false, profiling = false;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> pev;  // profiling event pool
@@ -900,9 +1055,11 @@ public:
 
     ~CholDevice() {
         cudaSetDevice(device);
+        drop_graphs();
         cudaFree(dL); cudaFree(dW); cudaFree(dval); cudaFree(dT); cudaFree(dX); cudaFree(dBstage); cudaFree(damap); cudaFree(dF);
         cudaFree(drows); cudaFree(drel); cudaFree(dchild); cudaFree(dperm); cudaFree(dlevel_fronts);
         cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag); cudaFree(dpart); cudaFree(downed);
+        cudaFree(dMinv); cudaFree(dinv_front); cudaFree(dinv_kb);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -943,6 +1100,7 @@ int CholDevice::init() {
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaFree(0));
     lap("context");
+    use_graphs = getenv("B200S_NO_GRAPH") == nullptr;
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&evP, cudaEventDisableTiming));
@@ -950,6 +1108,7 @@ int CholDevice::init() {
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     const int ns = (int)P.fronts.size();
     std::vector<FrontD> hf(ns);
+    std::vector<int> inv_front, inv_kb;
     for (int s = 0; s < ns; s++) {
         const Front& f = P.fronts[s];
         FrontD d;
@@ -957,10 +1116,18 @@ int CholDevice::init() {
         d.col0 = f.col0; d.nc = f.nc; d.nr = f.nr; d.ld = f.ld;
         d.nchild = P.child_ptr[s + 1] - P.child_ptr[s]; d.childptr = P.child_ptr[s];
         d.parent = f.parent; d.level = f.level;
+        d.ioff = -1;
+        if (f.nr > SMALL_NR) {
+            d.ioff = (long long)inv_front.size() * MINV_BLK;
+            for (int kb = 0; kb < (f.nc + NB - 1) / NB; kb++) { inv_front.push_back(s); inv_kb.push_back(kb); }
+        }
         hf[s] = d;
     }
+    ninvblk = (int)inv_front.size();
     int rc;
     if ((rc = upload(&dF, hf.data(), hf.size()))) return rc;
+    if ((rc = upload(&dinv_front, inv_front.data(), inv_front.size()))) return rc;
+    if ((rc = upload(&dinv_kb, inv_kb.data(), inv_kb.size()))) return rc;
     if ((rc = upload(&drows, P.rows.data(), P.rows.size()))) return rc;
     if ((rc = upload(&drel, P.rel.data(), P.rel.size()))) return rc;
     if ((rc = upload(&dchild, P.child_idx.data(), P.child_idx.size()))) return rc;
@@ -975,6 +1142,8 @@ int CholDevice::init() {
     CUDA_TRY(cudaMalloc((void**)&dW, std::max<i64>(P.wsize, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dval, std::max<i64>(P.nnzA, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&dminor, sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&dMinv, std::max<size_t>((size_t)ninvblk * MINV_BLK, 1) * sizeof(double)));
+    total_bytes += (i64)ninvblk * MINV_BLK * sizeof(double);
     CUDA_TRY(cudaMalloc((void**)&downed, std::max<size_t>(hf.size(), 1)));
     CUDA_TRY(cudaMemset(downed, 1, std::max<size_t>(hf.size(), 1)));
     total_bytes += (P.lsize + P.wsize + P.nnzA) * sizeof(double);
@@ -984,6 +1153,8 @@ int CholDevice::init() {
     std::vector<int> sched;          // group arrays: [front ids...][prefix...]
     std::vector<EAItem> ea;
     levels.resize(P.nlevels);
+    sgroups.assign(1, SolveGroups());
+    memset(&sgroups[0], 0, sizeof(SolveGroups));
     const long long EA_TARGET = 16384;
     for (int l = 0; l < P.nlevels; l++) {
         LevelSched& LS = levels[l];
@@ -1039,13 +1210,29 @@ int CholDevice::init() {
                 const int nblk = (f.nc + NB - 1) / NB;
                 if (kb >= nblk) continue;
                 const int w = std::min(NB, f.nc - kb * NB);
-                const int below = f.nr - (kb * NB + w);
+                const int below = f.nr - ((kb * NB + w) & ~1);      // row tiles of the solve start at an even row
                 fs.push_back(s);
                 cf.push_back((below + SOLVE_FT - 1) / SOLVE_FT);
                 cb2.push_back((below + SOLVE_BT - 1) / SOLVE_BT);
             }
             emit(LS.sfwd[kb], fs, cf);
             emit(LS.sbwd[kb], fs, cb2);
+            if (!fs.empty() && (int)fs.size() <= MAXG)
+                for (int dir = 0; dir < 2; dir++) {
+                    SolveGroups G;
+                    memset(&G, 0, sizeof(G));
+                    G.ng = (int)fs.size();
+                    const std::vector<int>& cnt = dir ? cb2 : cf;
+                    int run = 0;
+                    for (int i = 0; i < G.ng; i++) {
+                        const FrontD& d = hf[fs[i]];
+                        G.prefix[i] = run; run += cnt[i];
+                        G.fr[i] = FrontS{d.loff, d.rowptr, d.ioff, d.nc, d.nr, d.ld, d.col0};
+                    }
+                    G.prefix[G.ng] = run;
+                    (dir ? LS.sbwd[kb] : LS.sfwd[kb]).sgi = (int)sgroups.size();
+                    sgroups.push_back(G);
+                }
             max_solve_ctas = std::max(max_solve_ctas, LS.sbwd[kb].ctas);
         }
         for (int kb = 0; kb < maxblk; kb++) {
@@ -1115,6 +1302,10 @@ int CholDevice::init() {
     if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
     CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SDIAG));
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BDIAG));
+    CUDA_TRY(cudaFuncSetAttribute(k_fwd_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FUPD));
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUPD));
     CUDA_TRY(cudaFuncSetAttribute(k_small_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((SMALL_NR | 1) * SMALL_NR * sizeof(double))));
     CUDA_TRY(cudaFuncSetAttribute(k_small_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
@@ -1126,6 +1317,7 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
     const CholPlan& P = *plan;
     CUDA_TRY(cudaSetDevice(device));
     numeric = false;
+    minv_valid = false;
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     const double* dv = val;
     if (!on_device) {
@@ -1276,6 +1468,7 @@ int CholDevice::set_owned(const unsigned char* owned_host) {
 
 int CholDevice::ensure_solve_ws(i64 cols) {
     if (cols <= solve_cols) return ST_OK;
+    drop_graphs();                 // the captured sweeps hold the old workspace pointers
     cudaFree(dT); cudaFree(dX); dT = dX = nullptr; solve_cols = 0;
     const CholPlan& P = *plan;
     CUDA_TRY(cudaMalloc((void**)&dT, std::max<i64>((i64)P.rows.size() * cols, 1) * sizeof(double)));
@@ -1297,6 +1490,10 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     if (rc) return rc;
     const i64 chunk = solve_cols;
     CUDA_TRY(cudaEventRecord(ev[4], stream));
+    if (!minv_valid && ninvblk > 0) {
+        k_diag_inverse<<<ninvblk, 128, 0, stream>>>(dinv_front, dinv_kb, dF, dL, dMinv);
+        minv_valid = true;
+    }
     double* dB = B;
     if (!on_device) {
         if ((i64)n * nrhs > bstage_cap) {
@@ -1329,36 +1526,57 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         if (do_perm) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dX, n, n);
         const long long pstride = (long long)max_solve_ctas * NB;
+        // the level sweeps are a fixed launch sequence (hundreds of short dependent kernels): captured once per
+        // (columns, directions) into a CUDA graph and replayed
+        auto sweeps = [&]() {
         if (do_fwd)
-            for (int l = 0; l < P.nlevels; l++) {
-                const LevelSched& LS = levels[l];
-                if (LS.small_all_cnt)
-                    k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
-                if (!LS.panel.empty() && LS.panel[0].ng) {
-                    k_fwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, dchild, drel, dT, tstride, dX, n);
-                    for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
-                        const Launch& la = LS.sfwd[kb];
-                        k_fwd_diag<<<dim3(la.ng, nc), 256, 0, stream>>>(dsched + la.goff, (int)kb, dF, dL, dT, tstride, dX, n);
-                        if (la.ctas)
-                            k_fwd_upd<<<dim3(la.ctas, nc), 256, 0, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride);
+                for (int l = 0; l < P.nlevels; l++) {
+                    const LevelSched& LS = levels[l];
+                    if (LS.small_all_cnt)
+                        k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
+                    if (!LS.panel.empty() && LS.panel[0].ng) {
+                        k_fwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, dchild, drel, dT, tstride, dX, n);
+                        for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
+                            const Launch& la = LS.sfwd[kb];
+                            k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n);
+                            if (la.ctas)
+                                k_fwd_upd<<<dim3(la.ctas, nc), 256, SMEM_FUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride);
+                        }
                     }
                 }
-            }
-        if (do_bwd)
-            for (int l = P.nlevels - 1; l >= 0; l--) {
-                const LevelSched& LS = levels[l];
-                if (!LS.panel.empty() && LS.panel[0].ng) {
-                    k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
-                    for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
-                        const Launch& la = LS.sbwd[kb];
-                        if (la.ctas)
-                            k_bwd_upd<<<dim3(la.ctas, nc), 256, 0, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride);
-                        k_bwd_diag<<<dim3(la.ng, nc), 256, 0, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dT, tstride, dX, n, dpart, pstride);
+            if (do_bwd)
+                for (int l = P.nlevels - 1; l >= 0; l--) {
+                    const LevelSched& LS = levels[l];
+                    if (!LS.panel.empty() && LS.panel[0].ng) {
+                        k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
+                        for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
+                            const Launch& la = LS.sbwd[kb];
+                            if (la.ctas)
+                                k_bwd_upd<<<dim3(la.ctas, nc), 256, SMEM_BUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride);
+                            k_bwd_diag<<<dim3(la.ng, nc), 256, SMEM_BDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dMinv, dT, tstride, dX, n, dpart, pstride);
+                        }
                     }
+                    if (LS.small_all_cnt)
+                        k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
                 }
-                if (LS.small_all_cnt)
-                    k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
+        };
+        const int gkey = nc * 4 + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
+        if (!use_graphs) sweeps();
+        else {
+            auto it = solve_graphs.find(gkey);
+            if (it == solve_graphs.end()) {
+                cudaGraph_t gr = nullptr;
+                cudaGraphExec_t ge = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                sweeps();
+                CUDA_TRY(cudaStreamEndCapture(stream, &gr));
+                cudaError_t ie = cudaGraphInstantiate(&ge, gr, 0);
+                cudaGraphDestroy(gr);
+                CUDA_TRY(ie);
+                it = solve_graphs.emplace(gkey, ge).first;
             }
+            CUDA_TRY(cudaGraphLaunch(it->second, stream));
+        }
         if (do_perm) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
     }
@@ -1419,7 +1637,7 @@ int chol_device_sync(CholDevice* d) {
     return ST_OK;
 }
 void chol_device_buffers(CholDevice* d, double** L, double** W) { *L = d->dL; *W = d->dW; }
-void chol_device_mark_numeric(CholDevice* d, bool numeric) { d->numeric = numeric; }
+void chol_device_mark_numeric(CholDevice* d, bool numeric) { d->numeric = numeric; d->minv_valid = false; }
 i64 chol_device_workspace_bytes(const CholDevice* d) { return d->total_bytes; }
 
 }  // namespace b200s
