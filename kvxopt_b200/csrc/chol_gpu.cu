@@ -203,34 +203,84 @@ __device__ __forceinline__ void smem_partial_chol(double* S, int lds, int nr, in
 }
 
 // Blocked Cholesky of a w x w (w <= 128, padded to wpad = multiple of 16 with an identity tail) lower-triangular
-// block held in shared memory with stride LDL, 256 threads: per 16-column chunk (1) warp 0 factors the 16x16
-// diagonal chunk, one lane per row; (2) one thread per row solves the rows below against it; (3) all warps apply the
-// rank-16 update to the trailing lower triangle with FP64 DMMA on 8x8 tiles.  6 block barriers per chunk instead
-// of 2 per column.
+// block held in shared memory with stride LDL, 256 threads, 16 columns per step:
+//  (1) the 16 x 16 diagonal chunk is factored by warp 0 in registers (one lane per row, pivot column broadcast by
+//      shuffles, rsqrt instead of sqrt + divide);
+//  (2) one thread per row solves the rows below against it;
+//  (3) all warps apply the rank-16 update to the trailing lower triangle with FP64 DMMA, 8 x 32 strips of tiles handed
+//      out through a counter; warp 0 first updates the next diagonal chunk and factors it while the others work on the
+//      rest (look-ahead), so step (1) is off the critical path after the first chunk.
+// Only the lower triangle of S is meaningful afterwards.
+__device__ __forceinline__ void chol_diag16(double* S, int d0, int lane, double* rdiag, double dbound, int w, int gcol0,
+                                            int* minor, bool record) {
+    const int r = lane & 15;
+    double a[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) a[c] = S[(d0 + c) * LDL + d0 + r];
+    int bad = 16;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0) && j < bad) bad = j;
+        double inv = rsqrt(d);
+        double l = d * inv;
+        if (dbound > 0.0 && l < dbound) { l = dbound; inv = 1.0 / dbound; }
+        const double lij = (r == j) ? l : a[j] * inv;
+        if (r >= j) a[j] = lij;
+#pragma unroll
+        for (int c = 0; c < 16; c++)
+            if (c > j) {                 // static after unrolling: keeps a[] in registers
+                const double u = __shfl_sync(0xffffffffu, lij, c);
+                const double t = fma(-lij, u, a[c]);
+                a[c] = (r >= c) ? t : a[c];
+            }
+        if (lane == j) rdiag[j] = inv;
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; c++)
+            if (r >= c) S[(d0 + c) * LDL + d0 + r] = a[c];
+    }
+    if (record && lane == 0 && bad < 16 && d0 + bad < w) atomicMin(minor, gcol0 + d0 + bad);
+}
+
+// C(8 x 32 strip: tile row ti, tile columns tj0..tj0+3, those in qmask) -= L(rows, c0..c0+15) L(cols, c0..c0+15)^T
+__device__ __forceinline__ void chol_strip(double* S, int c0, int t0, int ti, int tj0, int qmask, int lane) {
+    double* Cp = S + (t0 + 8 * tj0 + 2 * (lane & 3)) * LDL + t0 + 8 * ti + (lane >> 2);
+    const double* Ap = S + (c0 + (lane & 3)) * LDL + t0 + 8 * ti + (lane >> 2);
+    const double* Bp = S + (c0 + (lane & 3)) * LDL + t0 + 8 * tj0 + (lane >> 2);
+    double acc[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (qmask >> q & 1) { acc[q][0] = Cp[q * 8 * LDL]; acc[q][1] = Cp[q * 8 * LDL + LDL]; }
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+        const double av = -Ap[k4 * LDL];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (qmask >> q & 1) dmma884(acc[q][0], acc[q][1], av, Bp[k4 * LDL + 8 * q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (qmask >> q & 1) { Cp[q * 8 * LDL] = acc[q][0]; Cp[q * 8 * LDL + LDL] = acc[q][1]; }
+}
+
 __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, int gcol0, int* minor, double dbound,
                                                    bool record, double* rdiag) {
+    __shared__ int tctr;
+    __shared__ unsigned char strip_ti[32], strip_tj[32];      // strips of the lower triangle of <= 14 x 14 tiles, by row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        int n = 0;
+        for (int ti = 0; ti < 14; ti++)
+            for (int tj0 = 0; tj0 <= ti; tj0 += 4) { strip_ti[n] = (unsigned char)ti; strip_tj[n] = (unsigned char)tj0; n++; }
+    }
+    __syncthreads();
+    if (warp == 0) chol_diag16(S, 0, lane, rdiag, dbound, w, gcol0, minor, record);
     for (int c0 = 0; c0 < wpad; c0 += 16) {
-        __syncthreads();
-        if (warp == 0) {
-            for (int j = 0; j < 16; j++) {
-                const double d = S[(c0 + j) * LDL + c0 + j];
-                if (!(d > 0.0) && record && lane == 0 && c0 + j < w) atomicMin(minor, gcol0 + c0 + j);
-                double l = sqrt(d);
-                if (dbound > 0.0 && l < dbound) l = dbound;
-                const double inv = 1.0 / l;
-                __syncwarp();
-                double lij = 0.0;
-                if (lane > j && lane < 16) { lij = S[(c0 + j) * LDL + c0 + lane] * inv; S[(c0 + j) * LDL + c0 + lane] = lij; }
-                if (lane == j) { S[(c0 + j) * LDL + c0 + j] = l; rdiag[j] = inv; }
-                __syncwarp();
-                if (lane > j && lane < 16)
-                    for (int c = j + 1; c <= lane; c++) S[(c0 + c) * LDL + c0 + lane] -= lij * S[(c0 + j) * LDL + c0 + c];
-                __syncwarp();
-            }
-        }
-        __syncthreads();
+        __syncthreads();                       // diagonal chunk c0 factored, trailing update of the previous chunk done
         const int t0 = c0 + 16;
+        if (tid == 0) tctr = 0;
         for (int r = t0 + tid; r < wpad; r += 256) {
             double xv[16];
 #pragma unroll
@@ -239,7 +289,7 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
             for (int q = 0; q < 16; q++) {
                 double v = xv[q];
 #pragma unroll
-                for (int p = 0; p < q; p++) v -= xv[p] * S[(c0 + p) * LDL + c0 + q];
+                for (int p = 0; p < q; p++) v = fma(-xv[p], S[(c0 + p) * LDL + c0 + q], v);
                 xv[q] = v * rdiag[q];
             }
 #pragma unroll
@@ -247,22 +297,26 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
         }
         __syncthreads();
         const int nt = (wpad - t0) >> 3;
-        const int ntiles = nt * (nt + 1) / 2;
-        for (int tile = warp; tile < ntiles; tile += 8) {
-            int ti = (int)((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
-            while (ti * (ti + 1) / 2 > tile) ti--;
-            while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-            const int tj = tile - ti * (ti + 1) / 2;
-            const int row = t0 + 8 * ti + (lane >> 2), col = t0 + 8 * tj + 2 * (lane & 3);
-            double c0v = S[col * LDL + row], c1v = S[(col + 1) * LDL + row];
-#pragma unroll
-            for (int k4 = 0; k4 < 16; k4 += 4) {
-                const double a = -S[(c0 + k4 + (lane & 3)) * LDL + t0 + 8 * ti + (lane >> 2)];
-                const double bq = S[(c0 + k4 + (lane & 3)) * LDL + t0 + 8 * tj + (lane >> 2)];
-                dmma884(c0v, c1v, a, bq);
-            }
-            S[col * LDL + row] = c0v;
-            S[(col + 1) * LDL + row] = c1v;
+        if (nt == 0) break;
+        int nstrips = 0;                       // strips with ti < nt: a prefix of the table
+        for (int ti = 0; ti < nt; ti++) nstrips += (ti >> 2) + 1;
+        if (warp == 0) {
+            chol_strip(S, c0, t0, 0, 0, 1, lane);
+            chol_strip(S, c0, t0, 1, 0, 3, lane);
+            __syncwarp();
+            chol_diag16(S, t0, lane, rdiag, dbound, w, gcol0, minor, record);
+        }
+        int mt = 0;
+        if (lane == 0) mt = atomicAdd(&tctr, 1);
+        mt = __shfl_sync(0xffffffffu, mt, 0);
+        while (mt < nstrips) {
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&tctr, 1);      // next ticket fetched under the DMMA work of this strip
+            const int ti = strip_ti[mt], tj0 = strip_tj[mt];
+            int qmask = (ti - tj0 >= 3) ? 15 : ((1 << (ti - tj0 + 1)) - 1);
+            if (ti < 2 && tj0 == 0) qmask = 0;             // the next diagonal chunk: done by warp 0 above
+            if (qmask) chol_strip(S, c0, t0, ti, tj0, qmask, lane);
+            mt = __shfl_sync(0xffffffffu, nxt, 0);
         }
     }
     __syncthreads();
@@ -323,12 +377,15 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
     const int wpad = (w + 15) & ~15;
     const int ld = f.ld;
     double* P = L + f.loff;
-    for (int idx = tid; idx < wpad * wpad; idx += 256) {
-        int c = idx / wpad, rr = idx - c * wpad;
-        double v = 0.0;
-        if (c < w && rr < w) { if (rr >= c) v = P[(long long)(k0 + c) * ld + k0 + rr]; }
-        else if (rr == c) v = 1.0;
-        Ls[c * LDL + rr] = v;
+#pragma unroll 4
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int c = idx >> 7, rr = idx & (NB - 1);
+        if (c < wpad && rr < wpad) {
+            double v = 0.0;
+            if (c < w && rr < w) { if (rr >= c) v = P[(long long)(k0 + c) * ld + k0 + rr]; }
+            else if (rr == c) v = 1.0;
+            Ls[c * LDL + rr] = v;
+        }
     }
     __shared__ double rdiag16[16];
     smem_potrf_blocked(Ls, w, wpad, f.col0 + k0, minor, dbound, r == 0, rdiag16);
@@ -665,7 +722,7 @@ __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const
 // The 32 x 32 diagonal sub-blocks of every 128-column block are inverted once per factorization (k_diag_inverse), so
 // a block step is four small matrix-vector products instead of a 128-step substitution chain.
 constexpr int SOLVE_FT = 64;     // rows per CTA in the forward update  (256 threads = 64 rows x 4 column quarters)
-constexpr int SOLVE_BT = 256;    // rows per CTA in the backward (transposed) update
+constexpr int SOLVE_BT = 192;    // rows per CTA in the backward (transposed) update: three 64-row slices, all in flight
 constexpr int SB = 32;           // inverted diagonal sub-block
 constexpr int MINV_HALF = (NB / SB) * SB * SB;  // the four inverse sub-blocks of a 128-column block, column-major
 constexpr int MINV_BLK = 2 * MINV_HALF;         // ... followed by their transposes (backward solve)
@@ -706,23 +763,35 @@ __global__ void __launch_bounds__(128) k_diag_inverse(const int* __restrict__ bl
     for (int c = 0; c < SB; c++) { out[c * SB + lane] = D[s][lane][c]; out[MINV_HALF + c * SB + lane] = D[s][c][lane]; }
 }
 
-// forward: t = [x(cols); 0] + children's update vectors
-__global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list, const FrontD* __restrict__ F,
+// forward: t = [x(cols); 0] + children's update vectors.  One CTA per 2048-row chunk of a front: a child's relative
+// indices ascend, so the entries that fall into the chunk are a contiguous run found by binary search; children are
+// applied one after the other (deterministic sums).
+constexpr int GATHER_ROWS = 2048;
+__global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list, const int* __restrict__ cprefix, int nfronts,
+                                                    const FrontD* __restrict__ F,
                                                     const int* __restrict__ child_idx, const int* __restrict__ rel,
                                                     double* __restrict__ T, long long tstride, const double* __restrict__ X,
                                                     long long xstride) {
-    const FrontD f = F[list[blockIdx.x]];
+    const int g = find_group(cprefix, nfronts, blockIdx.x);
+    const FrontD f = F[list[g]];
+    const int a = (blockIdx.x - cprefix[g]) * GATHER_ROWS, b = min(f.nr, a + GATHER_ROWS);
     double* t = T + blockIdx.y * tstride + f.rowptr;
     const double* x = X + blockIdx.y * xstride + f.col0;
-    const int nr = f.nr, nc = f.nc, tid = threadIdx.x;
-    for (int i = tid; i < nr; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
+    const int nc = f.nc, tid = threadIdx.x;
+    for (int i = a + tid; i < b; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
     __syncthreads();
     for (int q = 0; q < f.nchild; q++) {
         const FrontD fc = F[child_idx[f.childptr + q]];
         const int mc = fc.nr - fc.nc;
         const int* rl = rel + fc.reloff;
         const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
-        for (int i = tid; i < mc; i += 256) t[rl[i]] += tc[i];
+        int lo = 0, hi = mc;                       // first entry with rl >= a
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < a) lo = mid + 1; else hi = mid; }
+        for (int i = lo + tid; i < mc; i += 256) {
+            const int d = rl[i];
+            if (d >= b) break;
+            t[d] += tc[i];
+        }
         __syncthreads();
     }
 }
@@ -839,8 +908,8 @@ __global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGr
     __syncthreads();
     if (tid < SOLVE_FT && r0 + tid < f.nr && r0 + tid >= rb) t[r0 + tid] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
 }
-// backward, block kb: partial[q] = sum over a 256-row tile of the rows below the block of L[r, k0+q] * t[r].
-// Four 64-row slices go through three shared-memory buffers (>= 128 KB in flight); thread = (row, column quarter);
+// backward, block kb: partial[q] = sum over a 192-row tile of the rows below the block of L[r, k0+q] * t[r].
+// Three 64-row slices, one shared-memory buffer each (192 KB in flight); thread = (row, column quarter);
 // the 32 per-lane column sums of a warp are combined by a halving butterfly
 __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
@@ -861,26 +930,28 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
     double p[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) p[j] = 0.0;
+    static_assert(NSUB == 3, "one buffer per slice");
+    double tv[NSUB];
 #pragma unroll
-    for (int sub = 0; sub < 3; sub++) {
+    for (int sub = 0; sub < NSUB; sub++) {
         stage_rows64(P, f.ld, f.nr, k0, w, r0 + sub * 64, sm + sub * NB * 64, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
+        const int r = r0 + sub * 64 + rr;
+        tv[sub] = (r < f.nr && r >= rb) ? t[r] : 0.0;
     }
 #pragma unroll
     for (int sub = 0; sub < NSUB; sub++) {
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        if (sub == 0) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        if (sub == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (sub == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const int r = r0 + sub * 64 + rr;
         if (r < f.nr && r >= rb) {
-            const double tv = t[r];
-            const double* sp = sm + (sub % 3) * NB * 64 + cq * 32 * 64 + rr;
+            const double* sp = sm + sub * NB * 64 + cq * 32 * 64 + rr;
 #pragma unroll
             for (int j = 0; j < 32; j++)
-                if (j < wq) p[j] = fma(sp[j * 64], tv, p[j]);
+                if (j < wq) p[j] = fma(sp[j * 64], tv[sub], p[j]);
         }
-        __syncthreads();
-        if (sub + 3 < NSUB) stage_rows64(P, f.ld, f.nr, k0, w, r0 + (sub + 3) * 64, sm + (sub % 3) * NB * 64, tid);
-        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // after the step with offset o the lanes with bit o set hold the upper half of the surviving columns: lane l ends
     // with the sum of column l
@@ -1014,6 +1085,7 @@ struct LevelSched {
     std::vector<Launch> updA, updB;   // lookahead split of upd: next block column / the rest
     Launch syrk;
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
+    Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
     int small_all_off = 0, small_all_cnt = 0;
 };
 
@@ -1199,6 +1271,11 @@ int CholDevice::init() {
             sched.push_back(run);
             la.ctas = run;
         };
+        if (!bigs.empty()) {
+            std::vector<int> cnt;
+            for (int s : bigs) cnt.push_back((P.fronts[s].nr + GATHER_ROWS - 1) / GATHER_ROWS);
+            emit(LS.gfwd, bigs, cnt);
+        }
         LS.small_all_off = LS.small_off[0];
         LS.small_all_cnt = LS.small_cnt[0] + LS.small_cnt[1] + LS.small_cnt[2];
         LS.sfwd.resize(maxblk);
@@ -1535,7 +1612,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     if (LS.small_all_cnt)
                         k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
                     if (!LS.panel.empty() && LS.panel[0].ng) {
-                        k_fwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, dchild, drel, dT, tstride, dX, n);
+                        k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
                         for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
                             const Launch& la = LS.sfwd[kb];
                             k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n);
