@@ -99,17 +99,18 @@ __device__ __forceinline__ int find_group(const int* prefix, int ng, int b) {
     return lo;
 }
 
-// Launch metadata of the solve kernels passed BY VALUE (constant bank) when a block step covers few fronts -- which is
+// Launch metadata of the panel / update / solve kernels passed BY VALUE (constant bank) when a block step covers few fronts -- which is
 // every step of the top levels, where the steps are many and short: no dependent global loads (group prefix -> front id
 // -> front record) ahead of the first data access.  ng == 0: read the schedule arrays in global memory instead.
-struct FrontS { long long loff, rowptr, ioff; int nc, nr, ld, col0; };
+struct FrontS { long long loff, rowptr, ioff, uoff; int nc, nr, ld, col0, id, pad_; };
 constexpr int MAXG = 32;
 struct SolveGroups { int ng; int prefix[MAXG + 1]; FrontS fr[MAXG]; };
 __device__ __forceinline__ FrontS load_front(const SolveGroups& sg, const int* gfront, const FrontD* F, int g) {
     if (sg.ng) return sg.fr[g];
     const FrontD fd = F[gfront[g]];
     FrontS f;
-    f.loff = fd.loff; f.rowptr = fd.rowptr; f.ioff = fd.ioff; f.nc = fd.nc; f.nr = fd.nr; f.ld = fd.ld; f.col0 = fd.col0;
+    f.loff = fd.loff; f.rowptr = fd.rowptr; f.ioff = fd.ioff; f.uoff = fd.uoff; f.nc = fd.nc; f.nr = fd.nr; f.ld = fd.ld;
+    f.col0 = fd.col0; f.id = gfront[g]; f.pad_ = 0;
     return f;
 }
 __device__ __forceinline__ int locate_group(const SolveGroups& sg, const int* gprefix, int ngroups, int b, int& tile) {
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__
 // and writes it back; every other CTA factors the same block redundantly in shared memory (no
 // inter-CTA dependency, no extra launch) and solves X L11^T = B for its 64-row tile.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront, const int* __restrict__ gprefix,
+__global__ void __launch_bounds__(256, 1) k_panel(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                   int ngroups, int kb, const FrontD* __restrict__ F,
                                                   double* __restrict__ L, double* __restrict__ diag_scratch,
                                                   int* minor, double dbound, const unsigned char* __restrict__ owned) {
@@ -368,25 +369,31 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
     double* Xs = Ls + NB * LDL;
     double* rinv = Xs + NB * LDX;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = find_group(gprefix, ngroups, blockIdx.x);
-    const int r = blockIdx.x - gprefix[g];
-    if (!owned[gfront[g]]) return;
-    const FrontD f = F[gfront[g]];
+    int r;
+    const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, r);
+    const FrontS f = load_front(sg, gfront, F, g);
+    if (!owned[f.id]) return;
     const int k0 = kb * NB;
     const int w = min(NB, f.nc - k0);
     const int wpad = (w + 15) & ~15;
     const int ld = f.ld;
     double* P = L + f.loff;
-#pragma unroll 4
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int c = idx >> 7, rr = idx & (NB - 1);
-        if (c < wpad && rr < wpad) {
-            double v = 0.0;
-            if (c < w && rr < w) { if (rr >= c) v = P[(long long)(k0 + c) * ld + k0 + rr]; }
-            else if (rr == c) v = 1.0;
-            Ls[c * LDL + rr] = v;
+    // diagonal block -> shared memory, 16-byte LDGSTS all in flight: rows below w and row pairs above the diagonal are
+    // zero-filled (src-size 0 / 8), pad columns get the identity
+    for (int idx = tid; idx < NB * (NB / 2); idx += 256) {
+        const int c = idx >> 6, rr = (idx & 63) * 2;
+        if (c >= wpad || rr >= wpad) continue;
+        if (c < w) {
+            const int bytes = (rr + 1 < c) ? 0 : ((rr + 1 < w) ? 16 : ((rr < w) ? 8 : 0));
+            const double* src = bytes ? P + (long long)(k0 + c) * ld + k0 + rr : P;
+            cp_async16(Ls + c * LDL + rr, src, bytes);
+        } else {
+            Ls[c * LDL + rr] = (rr == c) ? 1.0 : 0.0;
+            Ls[c * LDL + rr + 1] = (rr + 1 == c) ? 1.0 : 0.0;
         }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __shared__ double rdiag16[16];
     smem_potrf_blocked(Ls, w, wpad, f.col0 + k0, minor, dbound, r == 0, rdiag16);
     if (r == 0) {
@@ -402,13 +409,14 @@ __global__ void __launch_bounds__(256, 1) k_panel(const int* __restrict__ gfront
     if (tid < wpad) rinv[tid] = 1.0 / Ls[tid * LDL + tid];
     // this CTA solves the 64-row tiles r-1, r-1+nsolve, ... of the rows below the diagonal block with the factor
     // it holds in shared memory (the redundant diagonal factorization is paid once per CTA, not once per tile)
-    const int nsolve = gprefix[g + 1] - gprefix[g] - 1;
+    const int nsolve = (sg.ng ? sg.prefix[g + 1] - sg.prefix[g] : gprefix[g + 1] - gprefix[g]) - 1;
     const int ntiles = (f.nr - (k0 + w) + TR - 1) / TR;
     const int q = lane & 3, rw = warp * 8 + (lane >> 2);
     for (int tile = r - 1; tile < ntiles; tile += nsolve) {
         const int row0 = k0 + w + tile * TR;
         const int nrows = min(TR, f.nr - row0);
         __syncthreads();                 // previous tile fully written back / rinv visible
+#pragma unroll 8
         for (int idx = tid; idx < wpad * TR; idx += 256) {
             int c = idx / TR, i = idx - c * TR;
             Xs[c * LDX + i] = (c < w && i < nrows) ? P[(long long)(k0 + c) * ld + row0 + i] : 0.0;
@@ -496,7 +504,7 @@ __device__ __forceinline__ void load_tile_async(double* dst, const double* __res
 
 // tile decode shared by host counting and the kernel: column tiles of 64, row tiles of 128, lower triangle only:
 // column tile cj pairs with row tiles ti >= cj/2
-__global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const int* __restrict__ gfront, const int* __restrict__ gprefix,
+__global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                            int ngroups, int mode, int kb, const FrontD* __restrict__ F,
                                                            double* __restrict__ L, double* __restrict__ W,
                                                            const unsigned char* __restrict__ owned) {
@@ -504,10 +512,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const int* __restrict
     double* As = sm;                          // [STAGES][BK][LDT]    rows of the tile's row block (128)
     double* Bs = sm + STAGES * BK * LDT;      // [STAGES][BK][LDTB]   rows of the tile's column block (64)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = find_group(gprefix, ngroups, blockIdx.x);
-    int t = blockIdx.x - gprefix[g];
-    if (!owned[gfront[g]]) return;
-    const FrontD f = F[gfront[g]];
+    int t;
+    const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, t);
+    const FrontS f = load_front(sg, gfront, F, g);
+    if (!owned[f.id]) return;
     const int nr = f.nr, nc = f.nc, ld = f.ld;
     const double* P = L + f.loff;
     int rowI, rowJ, k0, K, ldc, crows, ccols, lo;
@@ -1270,6 +1278,21 @@ int CholDevice::init() {
             for (int c : cnt) { sched.push_back(run); run += c; }
             sched.push_back(run);
             la.ctas = run;
+            la.sgi = -1;
+            if (!fr.empty() && (int)fr.size() <= MAXG) {
+                SolveGroups G;
+                memset(&G, 0, sizeof(G));
+                G.ng = (int)fr.size();
+                int acc = 0;
+                for (int i = 0; i < G.ng; i++) {
+                    const FrontD& d = hf[fr[i]];
+                    G.prefix[i] = acc; acc += cnt[i];
+                    G.fr[i] = FrontS{d.loff, d.rowptr, d.ioff, d.uoff, d.nc, d.nr, d.ld, d.col0, fr[i], 0};
+                }
+                G.prefix[G.ng] = acc;
+                la.sgi = (int)sgroups.size();
+                sgroups.push_back(G);
+            }
         };
         if (!bigs.empty()) {
             std::vector<int> cnt;
@@ -1294,22 +1317,6 @@ int CholDevice::init() {
             }
             emit(LS.sfwd[kb], fs, cf);
             emit(LS.sbwd[kb], fs, cb2);
-            if (!fs.empty() && (int)fs.size() <= MAXG)
-                for (int dir = 0; dir < 2; dir++) {
-                    SolveGroups G;
-                    memset(&G, 0, sizeof(G));
-                    G.ng = (int)fs.size();
-                    const std::vector<int>& cnt = dir ? cb2 : cf;
-                    int run = 0;
-                    for (int i = 0; i < G.ng; i++) {
-                        const FrontD& d = hf[fs[i]];
-                        G.prefix[i] = run; run += cnt[i];
-                        G.fr[i] = FrontS{d.loff, d.rowptr, d.ioff, d.nc, d.nr, d.ld, d.col0};
-                    }
-                    G.prefix[G.ng] = run;
-                    (dir ? LS.sbwd[kb] : LS.sfwd[kb]).sgi = (int)sgroups.size();
-                    sgroups.push_back(G);
-                }
             max_solve_ctas = std::max(max_solve_ctas, LS.sbwd[kb].ctas);
         }
         for (int kb = 0; kb < maxblk; kb++) {
@@ -1454,7 +1461,7 @@ int CholDevice::factor_level(int l) {
         const Launch& lp = LS.panel[kb];
         if (lp.ctas) {
             prof_begin(2);
-            k_panel<<<lp.ctas, 256, SMEM_PANEL, stream>>>(dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
+            k_panel<<<lp.ctas, 256, SMEM_PANEL, stream>>>(sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
                                                           dF, dL, ddiag, dminor, opts.dbound, downed);
             k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag, downed);
             prof_end();
@@ -1463,7 +1470,7 @@ int CholDevice::factor_level(int l) {
             const Launch& lu = LS.upd[kb];
             if (lu.ctas) {
                 prof_begin(3);
-                k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
                                                                         (int)kb, dF, dL, dW, downed);
                 prof_end();
             }
@@ -1474,11 +1481,11 @@ int CholDevice::factor_level(int l) {
         if (lb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));             // panel kb is complete
         if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }   // part B of step kb-1
         if (la.ctas)
-            k_update<<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
+            k_update<<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
                                                                     (int)kb, dF, dL, dW, downed);
         if (lb.ctas) {
             CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-            k_update<<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
+            k_update<<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
                                                                      (int)kb, dF, dL, dW, downed);
             CUDA_TRY(cudaEventRecord(evB, stream2));
             pendingB = true;
@@ -1487,7 +1494,7 @@ int CholDevice::factor_level(int l) {
     if (pendingB) CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0));
     if (LS.syrk.ctas) {
         prof_begin(3);
-        k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+        k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
                                                                      LS.syrk.ng, 1, 0, dF, dL, dW, downed);
         prof_end();
     }
