@@ -563,66 +563,274 @@ __global__ void k_klu_prescale(const int* __restrict__ ent_row, long long nnz, i
     }
 }
 
-struct KluSolveD {
-    int n, nblocks;
-    const long long *Lp, *Up, *Fp, *cbeg;
-    const int *Li, *Ui, *Fi, *lslot0, *fslot0, *Pnum, *Q, *R;
+// ---- batched triangular solves: level-scheduled gather tasks ----------------------------------------
+// klu_solve / klu_tsolve (reference src/C/klu.c:593-690) as a DAG of 2n tasks over the work vector V = [Y; Z]
+// (2n rows, interleaved [row][matrix]):  V[t] = (V[i] - sum_terms LU[slot] * V[src]) / LU[diag]   with i = t mod n.
+//   'N' (row gather):    task i   = row i of L  (Y[i] = b~[i] - L(i,:) Y - F(i,:) Z, F couples to the later BTF blocks)
+//                        task n+i = row i of U  (Z[i] = (Y[i] - U(i,i+1:) Z) / U(i,i))
+//   'T' (column gather): task k   = column k of U and F (Y[k] = (b~[k] - U(:k,k)' Y - F(:,k)' Z) / U(k,k))
+//                        task n+k = column k of L       (Z[k] = Y[k] - L(k+1:,k)' Z)
+// Tasks are sorted by DAG level; one CTA (16 warps) serves 32 matrices (lane = matrix), the tasks of a level are
+// dealt to the warps, one block barrier per level.  Task records and the first 32 terms of a warp's next task are
+// prefetched before the barrier (they are static), so a level costs about one round trip for the values.
+struct KluSolveLvlD {
+    int n, nlev;
+    const int* lvl_ptr;     // nlev + 1
+    const int4* rec;        // per task in level order: {task id t, first term, end term, diagonal slot or -1}
+    const int* tslot;       // value slot of a term
+    const int* tsrc;        // row of V it multiplies
+    const int* extra;       // per part: split levels: head = number of further parts of its task, others = -1
+    const int* mode;        // per level: 1 = split mode
+};
+constexpr int KLU_SOLVE_WARPS = 16;
+constexpr int KLU_SOLVE_PART = 16;        // terms per part of a split level = value pairs in flight per round
+constexpr int KLU_SOLVE_MAXPARTS = 192;   // parts of one split level (shared-memory partial sums: 192 x 32 doubles)
+struct KluSolveLvlH {
+    std::vector<int> lvl_ptr, tslot, tsrc, extra, mode;
+    std::vector<int4> rec;
+    int nlev = 0;
 };
 
-// One thread per (matrix, right-hand side).  X[n][Bp] work vectors (one set per right-hand side).
-// trans = 0:  x = Q (U+F)^-1 L^-1 Rs^-1 P b        trans = 1:  x = P' Rs^-1 L^-T (U+F)^-T Q' b
-__global__ void k_klu_solve(KluSolveD S, int trans, int batch, int Bp, const double* __restrict__ LU,
-                            const double* __restrict__ Rs, double* __restrict__ B, long long ldB, long long bstride,
-                            double* __restrict__ X) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    const int rhs = blockIdx.y;
-    double* bb = B + (long long)b * bstride + (long long)rhs * ldB;
-    double* x = X + (long long)rhs * S.n * Bp + b;
-    const double* lu = LU + b;
-    const int n = S.n;
-    if (!trans) {
-        // (L U + F) z = Rs^-1 P b by block back-substitution, last block first (klu_solve)
-        for (int k = 0; k < n; k++) x[(long long)k * Bp] = bb[S.Pnum[k]] / Rs[(long long)k * Bp + b];
+static void build_solve_levels(const KluSymbolic& S, const KluNumeric& N, const KluPlan& P, bool trans, KluSolveLvlH& H) {
+    const int n = P.n;
+    std::vector<std::vector<std::pair<int, int>>> terms(2 * (size_t)n);     // per task: (slot, src row of V)
+    std::vector<int> diag(2 * (size_t)n, -1);
+    for (int k = 0; k < n; k++) {
+        const long long u0 = N.Up[k], u1 = N.Up[k + 1] - 1, l0 = N.Lp[k] + 1, l1 = N.Lp[k + 1], f0 = N.Fp[k], f1 = N.Fp[k + 1];
+        const int us = (int)P.cbeg[k], ls = P.lslot0[k], fs = P.fslot0[k];
+        if (!trans) {
+            for (long long p = l0; p < l1; p++) terms[N.Li[p]].push_back({ls + (int)(p - l0), k});                  // L(i,k) Y[k]
+            for (long long p = f0; p < f1; p++) terms[N.Fi[p]].push_back({fs + (int)(p - f0), n + k});              // F(i,k) Z[k]
+            for (long long p = u0; p < u1; p++) terms[(size_t)n + N.Ui[p]].push_back({us + (int)(p - u0), n + k});  // U(i,k) Z[k]
+            diag[(size_t)n + k] = P.udiag_slot[k];
+        } else {
+            for (long long p = u0; p < u1; p++) terms[k].push_back({us + (int)(p - u0), N.Ui[p]});                  // U(p,k) Y[p]
+            for (long long p = f0; p < f1; p++) terms[k].push_back({fs + (int)(p - f0), n + N.Fi[p]});              // F(p,k) Z[p]
+            for (long long p = l0; p < l1; p++) terms[(size_t)n + k].push_back({ls + (int)(p - l0), n + N.Li[p]});  // L(p,k) Z[p]
+            diag[k] = P.udiag_slot[k];
+        }
+    }
+    // levels in a topological order of the sequential algorithm
+    std::vector<int> level(2 * (size_t)n, 0);
+    auto visit = [&](int t) {
+        int lv = 0;
+        if (t >= n) lv = level[t - n] + 1;                        // Z-task of i needs Y[i]
+        for (auto& e : terms[t]) lv = std::max(lv, level[e.second] + 1);
+        level[t] = lv;
+    };
+    if (!trans)
         for (int blk = S.nblocks - 1; blk >= 0; blk--) {
-            const int k0 = S.R[blk], k1 = S.R[blk + 1];
-            for (int k = k0; k < k1; k++) {                       // L_k y = b_k (unit diagonal)
-                const double xk = x[(long long)k * Bp];
-                const long long p0 = S.Lp[k] + 1, p1 = S.Lp[k + 1];
-                const long long s0 = S.lslot0[k];
-                for (long long p = p0; p < p1; p++) x[(long long)S.Li[p] * Bp] -= lu[(s0 + p - p0) * Bp] * xk;
-            }
-            for (int k = k1 - 1; k >= k0; k--) {                  // U_k z_k = y, then rows above: b -= F(:,k) z_k
-                const long long u0 = S.Up[k], u1 = S.Up[k + 1] - 1, s0 = S.cbeg[k];
-                const double xk = x[(long long)k * Bp] / lu[(s0 + (u1 - u0)) * Bp];
-                x[(long long)k * Bp] = xk;
-                for (long long p = u0; p < u1; p++) x[(long long)S.Ui[p] * Bp] -= lu[(s0 + p - u0) * Bp] * xk;
-                const long long f0 = S.Fp[k], f1 = S.Fp[k + 1], fs = S.fslot0[k];
-                for (long long p = f0; p < f1; p++) x[(long long)S.Fi[p] * Bp] -= lu[(fs + p - f0) * Bp] * xk;
-            }
+            for (int i = S.R[blk]; i < S.R[blk + 1]; i++) visit(i);
+            for (int i = S.R[blk + 1] - 1; i >= S.R[blk]; i--) visit(n + i);
         }
-        for (int k = 0; k < n; k++) bb[S.Q[k]] = x[(long long)k * Bp];
-    } else {
-        // (L U + F)^T z = Q^T b by block forward substitution, first block first (klu_tsolve)
-        for (int k = 0; k < n; k++) x[(long long)k * Bp] = bb[S.Q[k]];
+    else
         for (int blk = 0; blk < S.nblocks; blk++) {
-            const int k0 = S.R[blk], k1 = S.R[blk + 1];
-            for (int k = k0; k < k1; k++) {                       // b_k -= F(:,k)^T z_above ;  U_k^T y = b_k
-                const long long u0 = S.Up[k], u1 = S.Up[k + 1] - 1, s0 = S.cbeg[k];
-                double acc = x[(long long)k * Bp];
-                const long long f0 = S.Fp[k], f1 = S.Fp[k + 1], fs = S.fslot0[k];
-                for (long long p = f0; p < f1; p++) acc -= lu[(fs + p - f0) * Bp] * x[(long long)S.Fi[p] * Bp];
-                for (long long p = u0; p < u1; p++) acc -= lu[(s0 + p - u0) * Bp] * x[(long long)S.Ui[p] * Bp];
-                x[(long long)k * Bp] = acc / lu[(s0 + (u1 - u0)) * Bp];
-            }
-            for (int k = k1 - 1; k >= k0; k--) {                  // L_k^T z_k = y
-                const long long p0 = S.Lp[k] + 1, p1 = S.Lp[k + 1], s0 = S.lslot0[k];
-                double acc = x[(long long)k * Bp];
-                for (long long p = p0; p < p1; p++) acc -= lu[(s0 + p - p0) * Bp] * x[(long long)S.Li[p] * Bp];
-                x[(long long)k * Bp] = acc;
+            for (int k = S.R[blk]; k < S.R[blk + 1]; k++) visit(k);
+            for (int k = S.R[blk + 1] - 1; k >= S.R[blk]; k--) visit(n + k);
+        }
+    int nlev = 0;
+    for (int t = 0; t < 2 * n; t++) nlev = std::max(nlev, level[t] + 1);
+    H.nlev = nlev;
+    H.lvl_ptr.assign(nlev + 1, 0);
+    for (int t = 0; t < 2 * n; t++) H.lvl_ptr[level[t] + 1]++;
+    for (int l = 0; l < nlev; l++) H.lvl_ptr[l + 1] += H.lvl_ptr[l];
+    std::vector<int> pos(H.lvl_ptr.begin(), H.lvl_ptr.end() - 1), order(2 * (size_t)n);
+    // long tasks first inside a level: the warps that get them start early
+    std::vector<int> ids(2 * (size_t)n);
+    for (int t = 0; t < 2 * n; t++) ids[t] = t;
+    std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) {
+        if (level[x] != level[y]) return level[x] < level[y];
+        return terms[x].size() > terms[y].size();
+    });
+    // Emit the work items ("parts") level by level.  A level with fewer tasks than warps whose tasks are long is
+    // run in split mode: every task is cut into parts of <= 32 terms that different warps sum concurrently into
+    // shared memory; after a barrier the head part's warp combines them (fixed order) and stores the row.
+    H.rec.clear(); H.extra.clear(); H.mode.assign(nlev, 0);
+    H.tslot.clear(); H.tsrc.clear();
+    std::vector<int> lp2(nlev + 1, 0);
+    for (int l = 0; l < nlev; l++) {
+        const int q0 = H.lvl_ptr[l], q1 = H.lvl_ptr[l + 1];
+        int parts = 0;
+        for (int q = q0; q < q1; q++) parts += std::max<int>(1, ((int)terms[ids[q]].size() + KLU_SOLVE_PART - 1) / KLU_SOLVE_PART);
+        const bool split = (q1 - q0) < KLU_SOLVE_WARPS && parts > (q1 - q0) && parts <= KLU_SOLVE_MAXPARTS;
+        H.mode[l] = split ? 1 : 0;
+        for (int q = q0; q < q1; q++) {
+            const int t = ids[q];
+            const int base = (int)H.tslot.size();
+            for (auto& e : terms[t]) { H.tslot.push_back(e.first); H.tsrc.push_back(e.second); }
+            const int cnt = (int)terms[t].size();
+            if (!split) {
+                H.rec.push_back(make_int4(t, base, base + cnt, diag[t]));
+                H.extra.push_back(0);
+            } else {
+                const int np = std::max(1, (cnt + KLU_SOLVE_PART - 1) / KLU_SOLVE_PART);
+                for (int pi = 0; pi < np; pi++) {
+                    H.rec.push_back(make_int4(t, base + KLU_SOLVE_PART * pi, std::min(base + cnt, base + KLU_SOLVE_PART * (pi + 1)), pi == 0 ? diag[t] : -1));
+                    H.extra.push_back(pi == 0 ? np - 1 : -1);
+                }
             }
         }
-        for (int k = 0; k < n; k++) bb[S.Pnum[k]] = x[(long long)k * Bp] / Rs[(long long)k * Bp + b];
+        lp2[l + 1] = (int)H.rec.size();
+    }
+    H.lvl_ptr = lp2;
+    (void)pos; (void)order;
+}
+
+// V[k][b] <- B_b[perm[k]] (/ Rs[k][b] for 'N'), and back: 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) k_klu_solve_load(int n, int batch, int Bp, const int* __restrict__ perm, const double* __restrict__ Rs,
+                                                        const double* __restrict__ B, long long ldB, long long bstride, double* __restrict__ V) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, k0 = blockIdx.x * 32, b0 = blockIdx.y * 32, rhs = blockIdx.z;
+    double* v = V + (long long)rhs * 2 * n * Bp;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int b = b0 + ty + 8 * i, k = k0 + tx;
+        tile[ty + 8 * i][tx] = (b < batch && k < n) ? B[(long long)b * bstride + (long long)rhs * ldB + perm[k]] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int k = k0 + ty + 8 * i, b = b0 + tx;
+        if (k < n) {
+            double x = tile[tx][ty + 8 * i];
+            if (Rs) x = (b < batch) ? x / Rs[(long long)k * Bp + b] : 0.0;
+            v[(long long)k * Bp + b] = x;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_klu_solve_store(int n, int batch, int Bp, const int* __restrict__ perm, const double* __restrict__ Rs,
+                                                         double* __restrict__ B, long long ldB, long long bstride, const double* __restrict__ V) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, k0 = blockIdx.x * 32, b0 = blockIdx.y * 32, rhs = blockIdx.z;
+    const double* z = V + (long long)rhs * 2 * n * Bp + (long long)n * Bp;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int k = k0 + ty + 8 * i, b = b0 + tx;
+        double x = 0.0;
+        if (k < n && b < batch) { x = z[(long long)k * Bp + b]; if (Rs) x /= Rs[(long long)k * Bp + b]; }
+        tile[ty + 8 * i][tx] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int b = b0 + ty + 8 * i, k = k0 + tx;
+        if (b < batch && k < n) B[(long long)b * bstride + (long long)rhs * ldB + perm[k]] = tile[tx][ty + 8 * i];
+    }
+}
+
+// sum of LU[slot] * V[src] over the terms [p0, p1); have: the metadata of the first 32 terms is already in ps / pj.
+// 16 value pairs are in flight per round (a part of a split level is one round).
+__device__ __forceinline__ double klu_solve_terms(const int* __restrict__ tslot, const int* __restrict__ tsrc, int p0, int p1,
+                                                  int ps, int pj, bool have, int lane,
+                                                  const double* __restrict__ lu, const double* __restrict__ v, int Bp) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = p0; p < p1; p += 32) {
+        if (p != p0 || !have) { ps = 0; pj = 0; if (p + lane < p1) { ps = tslot[p + lane]; pj = tsrc[p + lane]; } }
+        const int cnt = min(32, p1 - p);
+        for (int u = 0; u < cnt; u += KLU_SOLVE_PART) {
+            double a[KLU_SOLVE_PART], x[KLU_SOLVE_PART];
+#pragma unroll
+            for (int j = 0; j < KLU_SOLVE_PART; j++) {
+                const int sl = __shfl_sync(0xffffffffu, ps, (u + j) & 31), sr = __shfl_sync(0xffffffffu, pj, (u + j) & 31);
+                const bool on = u + j < cnt;
+                a[j] = on ? lu[(long long)sl * Bp] : 0.0;
+                x[j] = on ? v[(long long)sr * Bp] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < KLU_SOLVE_PART; j += 2) { s0 = fma(a[j], x[j], s0); s1 = fma(a[j + 1], x[j + 1], s1); }
+        }
+    }
+    return s0 + s1;
+}
+
+__global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolveLvlD S, int Bp, const double* __restrict__ LU,
+                                                                         double* __restrict__ V) {
+    extern __shared__ double smd[];
+    double* part = smd;                                            // [KLU_SOLVE_MAXPARTS][32] partial sums of a split level
+    int* lp = reinterpret_cast<int*>(smd + KLU_SOLVE_MAXPARTS * 32);   // level pointers, then modes
+    int* md = lp + S.nlev + 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = S.n, nlev = S.nlev;
+    const int4* __restrict__ rec = S.rec;
+    const int* __restrict__ tslot = S.tslot;
+    const int* __restrict__ tsrc = S.tsrc;
+    const int* __restrict__ extra = S.extra;
+    for (int i = threadIdx.x; i <= nlev; i += KLU_SOLVE_WARPS * 32) lp[i] = S.lvl_ptr[i];
+    for (int i = threadIdx.x; i < nlev; i += KLU_SOLVE_WARPS * 32) md[i] = S.mode[i];
+    if (threadIdx.x == 0) lp[nlev + 1] = lp[nlev];
+    __syncthreads();
+    const int b = blockIdx.x * 32 + lane;
+    const double* lu = LU + b;
+    double* v = V + (long long)blockIdx.y * 2 * n * Bp + b;
+    // static metadata of this warp's first part of a level is fetched one level ahead (rN..), under the previous level
+    int4 r = make_int4(0, 0, 0, -1), rN = r;
+    int ps = 0, pj = 0, ex = 0, psN = 0, pjN = 0, exN = 0;
+    bool have = false, haveN = false;
+    if (nlev > 0 && lp[0] + warp < lp[1]) {
+        const int q = lp[0] + warp;
+        r = rec[q]; ex = extra[q];
+        if (r.y + lane < r.z) { ps = tslot[r.y + lane]; pj = tsrc[r.y + lane]; }
+        have = true;
+    }
+    for (int lev = 0; lev < nlev; lev++) {
+        const int q0 = lp[lev], qe = lp[lev + 1];
+        haveN = false;
+        if (lev + 1 < nlev && qe + warp < lp[lev + 2]) {
+            const int q = qe + warp;
+            rN = rec[q]; exN = extra[q];
+            psN = 0; pjN = 0;
+            if (rN.y + lane < rN.z) { psN = tslot[rN.y + lane]; pjN = tsrc[rN.y + lane]; }
+            haveN = true;
+        }
+        if (!md[lev]) {
+            for (int q = q0 + warp; q < qe; q += KLU_SOLVE_WARPS) {
+                const bool mine = have && q == q0 + warp;
+                if (!mine) r = rec[q];
+                const int t = r.x, i = (t < n) ? t : t - n;
+                const double y = v[(long long)i * Bp];
+                double dg = 1.0;
+                if (r.w >= 0) dg = lu[(long long)r.w * Bp];
+                double acc = y - klu_solve_terms(tslot, tsrc, r.y, r.z, ps, pj, mine, lane, lu, v, Bp);
+                if (r.w >= 0) acc /= dg;
+                v[(long long)t * Bp] = acc;
+            }
+        } else {
+            // pass 1: every part (<= KLU_SOLVE_PART terms) -> its partial sum; a task's head also fetches V[i], diagonal
+            double y = 0.0, dg = 1.0;
+            int ht = -1, hq = 0, hex = 0, hw = -1;
+            for (int q = q0 + warp; q < qe; q += KLU_SOLVE_WARPS) {
+                const bool mine = have && q == q0 + warp;
+                if (!mine) { r = rec[q]; ex = extra[q]; }
+                if (ex >= 0 && ht < 0) {       // first head of this warp: keep its operands in registers
+                    const int i = (r.x < n) ? r.x : r.x - n;
+                    y = v[(long long)i * Bp];
+                    if (r.w >= 0) dg = lu[(long long)r.w * Bp];
+                    ht = r.x; hq = q; hex = ex; hw = r.w;
+                }
+                part[(q - q0) * 32 + lane] = klu_solve_terms(tslot, tsrc, r.y, r.z, ps, pj, mine, lane, lu, v, Bp);
+            }
+            __syncthreads();
+            // pass 2: heads combine their parts in order and store the row
+            for (int q = q0 + warp; q < qe; q += KLU_SOLVE_WARPS) {
+                int t, e, w;
+                if (q == hq && ht >= 0) { t = ht; e = hex; w = hw; }
+                else {
+                    e = extra[q];
+                    if (e < 0) continue;
+                    const int4 rr = rec[q];
+                    t = rr.x; w = rr.w;
+                    const int i = (t < n) ? t : t - n;
+                    y = v[(long long)i * Bp];
+                    dg = (w >= 0) ? lu[(long long)w * Bp] : 1.0;
+                }
+                double ssum = 0.0;
+                for (int k = 0; k <= e; k++) ssum += part[(q - q0 + k) * 32 + lane];
+                double acc = y - ssum;
+                if (w >= 0) acc /= dg;
+                v[(long long)t * Bp] = acc;
+            }
+        }
+        r = rN; ps = psN; pj = pjN; ex = exN; have = haveN;
+        __syncthreads();
     }
 }
 
@@ -638,7 +846,8 @@ public:
     cudaEvent_t ev[6] = {};
     KluPlanD PD{};
     KluWaveD WD{};
-    KluSolveD SD{};
+    KluSolveLvlD SL[2] = {};          // [0] = 'N', [1] = 'T'
+    const int *d_Pnum = nullptr, *d_Q = nullptr;
     bool use_wave = false;
     long long lu_slots = 0;
     std::vector<void*> owned;
@@ -738,21 +947,19 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     if ((rc = up(&tmp_i, P.slot_row))) return rc; d_slot_row = (int*)tmp_i;
     if ((rc = up(&tmp_i, P.rowent))) return rc; d_rowent = (int*)tmp_i;
     if ((rc = up(&tmp_l, rowptr))) return rc; d_rowptr = (long long*)tmp_l;
-    SD.n = P.n;
-    std::vector<long long> Lp(N.Lp.begin(), N.Lp.end()), Up(N.Up.begin(), N.Up.end()), Fp(N.Fp.begin(), N.Fp.end());
-    if ((rc = up(&SD.Lp, Lp))) return rc;
-    if ((rc = up(&SD.Up, Up))) return rc;
-    if ((rc = up(&SD.Fp, Fp))) return rc;
-    SD.cbeg = PD.cbeg;
-    if ((rc = up(&SD.Li, N.Li))) return rc;
-    if ((rc = up(&SD.Ui, N.Ui))) return rc;
-    if ((rc = up(&SD.Fi, N.Fi))) return rc;
-    SD.lslot0 = PD.lslot0;
-    if ((rc = up(&SD.fslot0, P.fslot0))) return rc;
-    if ((rc = up(&SD.Pnum, N.Pnum))) return rc;
-    if ((rc = up(&SD.Q, S.Q))) return rc;
-    if ((rc = up(&SD.R, S.R))) return rc;
-    SD.nblocks = S.nblocks;
+    if ((rc = up(&d_Pnum, N.Pnum))) return rc;
+    if ((rc = up(&d_Q, S.Q))) return rc;
+    for (int tr = 0; tr < 2; tr++) {
+        KluSolveLvlH H;
+        build_solve_levels(S, N, P, tr != 0, H);
+        SL[tr].n = P.n; SL[tr].nlev = H.nlev;
+        if ((rc = up(&SL[tr].lvl_ptr, H.lvl_ptr))) return rc;
+        if ((rc = up(&SL[tr].rec, H.rec))) return rc;
+        if ((rc = up(&SL[tr].tslot, H.tslot))) return rc;
+        if ((rc = up(&SL[tr].tsrc, H.tsrc))) return rc;
+        if ((rc = up(&SL[tr].extra, H.extra))) return rc;
+        if ((rc = up(&SL[tr].mode, H.mode))) return rc;
+    }
     return ST_OK;
 }
 
@@ -841,7 +1048,7 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
     if (batch_ <= 0 || n == 0 || nrhs <= 0) return ST_OK;
     if (batch_ > batch) { set_last_error("solve_batch: batch larger than the last refactored batch"); return ST_INVALID; }
     const long long bstride = ldB * nrhs;
-    const long long needX = (long long)n * Bp * nrhs;
+    const long long needX = 2ll * n * Bp * nrhs;      // V = [Y; Z] per right-hand side
     if (needX > capX) {
         cudaFree(dX); dX = nullptr; capX = 0;
         CUDA_TRY(cudaMalloc((void**)&dX, needX * sizeof(double)));
@@ -859,8 +1066,18 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
         CUDA_TRY(cudaMemcpyAsync(dB, B, totalB * sizeof(double), cudaMemcpyHostToDevice, stream));
         db = dB;
     }
-    dim3 grid((unsigned)((batch_ + 63) / 64), (unsigned)nrhs);
-    k_klu_solve<<<grid, 64, 0, stream>>>(SD, trans, (int)batch_, Bp, dLU, dRs, db, ldB, bstride, dX);
+    {
+        const KluSolveLvlD& L_ = SL[trans ? 1 : 0];
+        const dim3 tg((unsigned)((n + 31) / 32), (unsigned)(Bp / 32), (unsigned)nrhs);
+        const int nb = (int)batch_;
+        // 'N': V = Rs^-1 P b, result scattered through Q;  'T': V = Q' b, result P' Rs^-1 z
+        k_klu_solve_load<<<tg, 256, 0, stream>>>(n, nb, Bp, trans ? d_Q : d_Pnum, trans ? nullptr : dRs, db, ldB, bstride, dX);
+        const size_t sm = (size_t)KLU_SOLVE_MAXPARTS * 32 * sizeof(double) + (size_t)(2 * L_.nlev + 4) * sizeof(int);
+        if (sm > 220 * 1024) { set_last_error("klu solve: too many levels"); return ST_TOO_LARGE; }
+        if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_klu_solve_lvl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_klu_solve_lvl<<<dim3((unsigned)(Bp / 32), (unsigned)nrhs), KLU_SOLVE_WARPS * 32, sm, stream>>>(L_, Bp, dLU, dX);
+        k_klu_solve_store<<<tg, 256, 0, stream>>>(n, nb, Bp, trans ? d_Pnum : d_Q, trans ? dRs : nullptr, db, ldB, bstride, dX);
+    }
     CUDA_TRY(cudaGetLastError());
     if (!on_device) CUDA_TRY(cudaMemcpyAsync(B, dB, totalB * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaEventRecord(ev[1], stream));

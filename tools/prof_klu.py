@@ -18,3 +18,14 @@ for r in range(reps):
     assert fn["b200s_klu_refactor_batch"](N, L.ptr_f64(vals), batch, nnz, None) == 0
     fn["b200s_klu_info"](N, C.byref(inf))
     print("batch %d: refactor %.3f ms, kernel %.3f ms, h2d %.3f ms" % (batch, inf.ms_refactor, inf.ms_kernel, inf.ms_h2d), flush=True)
+if len(sys.argv) > 3:      # argv[3] = nrhs: also time the batched solve ('N' then 'T')
+    nrhs = int(sys.argv[3])
+    Bb = np.ascontiguousarray(rng.standard_normal((batch, nrhs, n)))
+    for tr in (0, 1):
+        X = Bb.copy()
+        assert fn["b200s_klu_solve_batch"](N, tr, L.ptr_f64(X), nrhs, n, batch) == 0
+        fn["b200s_klu_info"](N, C.byref(inf))
+        Ab = sp.csc_matrix((vals[0], A.indices, A.indptr), shape=(n, n))
+        M = Ab.T if tr else Ab
+        res = np.abs(M @ X[0].T - Bb[0].T).max()
+        print("solve_batch trans=%d nrhs=%d: %.3f ms (host buffers), residual %.2e" % (tr, nrhs, inf.ms_solve, res), flush=True)
