@@ -200,7 +200,9 @@ typedef struct {
     double    flops;             /* multiply-adds x2 of one refactorization                        */
     b200s_int bytes_per_refactor;/* 8*(nnz_A + nnz_L + nnz_U + nnz_F + 2n): compulsory traffic      */
     double    ms_h2d, ms_refactor, ms_solve;  /* device-event times of the last batch call          */
-    double    ms_kernel;         /* of which: the refactorization kernel alone (k_klu_refactor)     */
+    double    ms_kernel;         /* of which: the sparse refactorization kernel (k_klu_refactor_wave) */
+    double    ms_dense;          /* ... and the dense trailing block (pack + k_klu_dense_lu + unpack) */
+    b200s_int launches;          /* kernels launched by the last refactor_batch call                 */
 } b200s_klu_info_t;
 b200s_status b200s_klu_info(const b200s_klu_num* N, b200s_klu_info_t* info);
 

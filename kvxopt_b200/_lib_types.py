@@ -23,7 +23,7 @@ class CholInfo(C.Structure):
 class KluInfo(C.Structure):
     _fields_ = [(k, i64) for k in ("n", "nblocks", "nnz_A", "nnz_L", "nnz_U", "nnz_F", "nlevels", "max_block")] + \
                [("flops", C.c_double), ("bytes_per_refactor", i64)] + \
-               [(k, C.c_double) for k in ("ms_h2d", "ms_refactor", "ms_solve", "ms_kernel")]
+               [(k, C.c_double) for k in ("ms_h2d", "ms_refactor", "ms_solve", "ms_kernel", "ms_dense")] + [("launches", i64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

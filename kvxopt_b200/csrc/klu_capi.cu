@@ -16,7 +16,7 @@ void klu_device_destroy(KluDevice* d);
 int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status);
 int klu_device_solve(KluDevice* d, int trans, double* B, long long nrhs, long long ldB, long long batch, bool on_device);
 int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs_host);
-void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel);
+void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel, double* dense, long long* launches);
 }  // namespace b200s
 
 struct b200s_klu_sym {
@@ -147,7 +147,11 @@ b200s_status b200s_klu_info(const b200s_klu_num* N, b200s_klu_info_t* info) {
     info->nlevels = N->P.nlevels; info->max_block = N->S.maxblock;
     info->flops = N->N.flops;
     info->bytes_per_refactor = 8 * (info->nnz_A + info->nnz_L + info->nnz_U + info->nnz_F + 2 * (i64)n);
-    if (N->dev) klu_device_times(N->dev, &info->ms_h2d, &info->ms_refactor, &info->ms_solve, &info->ms_kernel);
+    if (N->dev) {
+        long long nl = 0;
+        klu_device_times(N->dev, &info->ms_h2d, &info->ms_refactor, &info->ms_solve, &info->ms_kernel, &info->ms_dense, &nl);
+        info->launches = nl;
+    }
     return B200S_OK;
 }
 

@@ -843,7 +843,7 @@ class KluDevice {
 public:
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[7] = {};
     KluPlanD PD{};
     KluWaveD WD{};
     KluSolveLvlD SL[2] = {};          // [0] = 'N', [1] = 'T'
@@ -865,7 +865,8 @@ public:
     int Bp = 0, batch = 0;
     double *dA = nullptr, *dAxt = nullptr, *dRs = nullptr, *dLU = nullptr, *dX = nullptr, *dB = nullptr;
     long long capA = 0, capX = 0, capB = 0;
-    double ms_h2d = 0, ms_refactor = 0, ms_solve = 0, ms_kernel = 0;
+    double ms_h2d = 0, ms_refactor = 0, ms_solve = 0, ms_kernel = 0, ms_dense = 0;
+    long long launches = 0;
 
     ~KluDevice() {
         cudaSetDevice(device);
@@ -1008,8 +1009,9 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
             k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
         k_klu_refactor_wave<<<Bp / 32, KLU_WAVE_WARPS * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
-        if (spine_nd > 0)
-        {
+        CUDA_TRY(cudaEventRecord(ev[6], stream));
+        launches = 4 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
+        if (spine_nd > 0) {
             const dim3 tg(ndp / 32, Bp / 32);
             k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, Bp, dLU, dD, 0);
             k_klu_dense_lu<<<batch, KLU_DENSE_THREADS, dense_smem, stream>>>(spine_nd, d_dense_meta, ndp, batch, dD, d_status);
@@ -1020,7 +1022,9 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
         k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, 0, nslots, Bp, dAxt, dRs, dLU, 0);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
         k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, Bp, dLU, d_status);
+        CUDA_TRY(cudaEventRecord(ev[6], stream));
         CUDA_TRY(cudaEventRecord(ev[5], stream));
+        launches = 4;
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[2], stream));
@@ -1039,7 +1043,8 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_h2d = ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_refactor = ms;
-    cudaEventElapsedTime(&ms, ev[4], ev[5]); ms_kernel = ms;
+    cudaEventElapsedTime(&ms, ev[4], ev[6]); ms_kernel = ms;
+    cudaEventElapsedTime(&ms, ev[6], ev[5]); ms_dense = ms;
     return ST_OK;
 }
 
@@ -1121,8 +1126,8 @@ int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs
     CUDA_TRY(e);
     return ST_OK;
 }
-void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel) {
-    *h2d = d->ms_h2d; *refactor = d->ms_refactor; *solve = d->ms_solve; *kernel = d->ms_kernel;
+void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel, double* dense, long long* launches) {
+    *h2d = d->ms_h2d; *refactor = d->ms_refactor; *solve = d->ms_solve; *kernel = d->ms_kernel; *dense = d->ms_dense; *launches = d->launches;
 }
 
 }  // namespace b200s

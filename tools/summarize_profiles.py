@@ -37,6 +37,7 @@ def report(rep, out_name, traffic_key=None):
     h, units = rows[0], rows[1]
     lines = ["# ncu --set full --clock-control none --import-source on; report %s" % os.path.basename(rep)]
     traffic = None
+    per_kernel = {}
     for row in rows[2:]:
         lines.append("kernel: " + row[h.index("Kernel Name")][:100])
         vals = {}
@@ -50,6 +51,7 @@ def report(rep, out_name, traffic_key=None):
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
             traffic = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
             lines.append("  dram traffic per launch (read+write): %.1f MB" % (traffic / 1e6))
+            per_kernel.setdefault(row[h.index("Kernel Name")].split("(")[0], traffic)
         except Exception:
             pass
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
@@ -76,7 +78,11 @@ def report(rep, out_name, traffic_key=None):
     if traffic_key and traffic is not None:
         tp = os.path.join(OUT, "traffic.json")
         t = json.load(open(tp)) if os.path.exists(tp) else {}
-        t[traffic_key] = traffic
+        if isinstance(traffic_key, dict):          # kernel name -> key, first launch of each kernel
+            for kn, key in traffic_key.items():
+                if kn in per_kernel: t[key] = per_kernel[kn]
+        else:
+            t[traffic_key] = traffic
         json.dump(t, open(tp, "w"), indent=1)
 
 if __name__ == "__main__":
@@ -84,6 +90,8 @@ if __name__ == "__main__":
     for csvf, name in (("r01_launches_bench_klu.csv", "r01_launches_bench_klu_summary.txt"), ("r01_launches_chol64.csv", "r01_launches_chol64_summary.txt")):
         if os.path.exists(os.path.join(g, csvf)):
             launches(os.path.join(g, csvf), name)
-    for rep, name, key in (("r01_klu_wave.ncu-rep", "r01_ncu_k_klu_refactor_wave.txt", "k_klu_refactor"), ("r01_chol_update.ncu-rep", "r01_ncu_k_update.txt", "k_update")):
+    for rep, name, key in (("r01_klu_wave.ncu-rep", "r01_ncu_k_klu_refactor_wave.txt", "k_klu_refactor"), ("r01_chol_update.ncu-rep", "r01_ncu_k_update.txt", "k_update"),
+                           ("r01_klu_refactor_final.ncu-rep", "r01_ncu_klu_refactor_final.txt",
+                            {"k_klu_refactor_wave": "k_klu_refactor_wave", "k_klu_dense_lu": "k_klu_dense_lu", "k_klu_dense_pack": "k_klu_dense_pack"})):
         if os.path.exists(os.path.join(g, rep)):
             report(os.path.join(g, rep), name, key)
