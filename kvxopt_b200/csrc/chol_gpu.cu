@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(256) k_diag_writeback(const int* __restrict__ 
 //   mode 0: in-panel trailing update after block column kb (target columns inside the panel)
 //   mode 1: Schur complement into the update matrix (K = nc)
 // ---------------------------------------------------------------------------------------------------
+constexpr int SUPER_NB = 4;        // block columns per super-block of the two-level trailing update
 constexpr int UPD_THREADS = 256;   // 8 warps (4 x 2), each a 32 x 32 piece of a 128 x 64 tile; 2 CTAs per SM
 constexpr int BTN = 64;            // tile columns
 constexpr int LDTB = BTN + 4;      // smem stride of the column-block operand
@@ -523,12 +524,16 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
     if (mode != 1) {
         // mode 0: every column tile right of block kb; mode 2: only the next block column (lookahead part A);
         // mode 3: the column tiles right of the next block column (part B, overlapped with the next panel kernel)
+        // mode 4: "near" update inside the super-block of SUPER_NB block columns (K = 128, column tiles up to the end
+        // of the super-block); mode 5: "far" update after the last panel of a super-block: all column tiles right of
+        // it with K = the whole super-block (up to 512), so C is read and written once per super-block
         const int nrt = (nr + BT - 1) / BT;
         int cj = 2 * (kb + 1) + (mode == 3 ? 2 : 0);
         while (t >= nrt - (cj >> 1)) { t -= nrt - (cj >> 1); cj++; }
         const int ti = (cj >> 1) + t;
         rowI = ti * BT; rowJ = cj * BTN;
         k0 = kb * NB; K = min(NB, nc - k0);
+        if (mode == 5) { k0 = (kb / SUPER_NB) * SUPER_NB * NB; K = (kb + 1) * NB - k0; }
         C = L + f.loff + rowI + (long long)rowJ * ld; ldc = ld;
         crows = min(BT, nr - rowI); ccols = min(BTN, nc - rowJ);
         lo = 0;
@@ -1091,6 +1096,7 @@ struct LevelSched {
     int small_off[3] = {0, 0, 0}, small_cnt[3] = {0, 0, 0}, small_maxnr[3] = {0, 0, 0};
     std::vector<Launch> panel, upd;   // per block step kb (upd = all trailing column tiles)
     std::vector<Launch> updA, updB;   // lookahead split of upd: next block column / the rest
+    std::vector<Launch> updN, updF;   // two-level update: near (inside the super-block, K = 128) / far (K = super-block)
     Launch syrk;
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
     Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
@@ -1270,6 +1276,8 @@ int CholDevice::init() {
         LS.upd.resize(maxblk);
         LS.updA.resize(maxblk);
         LS.updB.resize(maxblk);
+        LS.updN.resize(maxblk);
+        LS.updF.resize(maxblk);
         auto emit = [&](Launch& la, const std::vector<int>& fr, const std::vector<int>& cnt) {
             la.goff = (int)sched.size();
             la.ng = (int)fr.size();
@@ -1320,7 +1328,7 @@ int CholDevice::init() {
             max_solve_ctas = std::max(max_solve_ctas, LS.sbwd[kb].ctas);
         }
         for (int kb = 0; kb < maxblk; kb++) {
-            std::vector<int> fr, cp, fu, cu, fuA, cuA, fuB, cuB;
+            std::vector<int> fr, cp, fu, cu, fuA, cuA, fuB, cuB, fuN, cuN, fuF, cuF;
             // panel CTAs: one per front for the diagonal block + solver CTAs that each factor the block redundantly
             // and then walk over several 64-row tiles; the solver CTAs of a launch are capped near one wave (148 SMs)
             long long tiles_total = 0;
@@ -1354,11 +1362,22 @@ int CholDevice::init() {
                 if (tiles > 0) { fu.push_back(s); cu.push_back((int)tiles); }
                 if (tilesA > 0) { fuA.push_back(s); cuA.push_back((int)tilesA); }
                 if (tiles - tilesA > 0) { fuB.push_back(s); cuB.push_back((int)(tiles - tilesA)); }
+                // two-level: near = column tiles up to the end of kb's super-block, far (only after the super-block's
+                // last panel) = everything right of the super-block
+                const int sb_end = (kb / SUPER_NB + 1) * SUPER_NB;          // first block column outside
+                long long tilesN = 0, tilesF = 0;
+                for (int cj = 2 * (kb + 1); cj < std::min(ncolt, 2 * sb_end); cj++) tilesN += nrt - (cj >> 1);
+                if (kb + 1 == sb_end)
+                    for (int cj = 2 * sb_end; cj < ncolt; cj++) tilesF += nrt - (cj >> 1);
+                if (tilesN > 0) { fuN.push_back(s); cuN.push_back((int)tilesN); }
+                if (tilesF > 0) { fuF.push_back(s); cuF.push_back((int)tilesF); }
             }
             emit(LS.panel[kb], fr, cp);
             emit(LS.upd[kb], fu, cu);
             emit(LS.updA[kb], fuA, cuA);
             emit(LS.updB[kb], fuB, cuB);
+            emit(LS.updN[kb], fuN, cuN);
+            emit(LS.updF[kb], fuF, cuF);
         }
         {
             std::vector<int> fr, cnt;
@@ -1456,6 +1475,7 @@ int CholDevice::factor_level(int l) {
     // kb+1, whose few latency-bound CTAs would otherwise leave the GPU idle.  Part A of step kb+1 waits for part B
     // of step kb (same C tiles).  With profiling on everything is serialised on the main stream.
     const bool lookahead = !profiling;
+    const bool two_level = getenv("B200S_ONE_LEVEL") == nullptr;
     bool pendingB = false;
     for (size_t kb = 0; kb < LS.panel.size(); kb++) {
         const Launch& lp = LS.panel[kb];
@@ -1465,6 +1485,19 @@ int CholDevice::factor_level(int l) {
                                                           dF, dL, ddiag, dminor, opts.dbound, downed);
             k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag, downed);
             prof_end();
+        }
+        if (two_level) {
+            const Launch& ln = LS.updN[kb];
+            const Launch& lf = LS.updF[kb];
+            prof_begin(3);
+            if (ln.ctas)
+                k_update<<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
+                                                                        (int)kb, dF, dL, dW, downed);
+            if (lf.ctas)
+                k_update<<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
+                                                                        (int)kb, dF, dL, dW, downed);
+            prof_end();
+            continue;
         }
         if (!lookahead) {
             const Launch& lu = LS.upd[kb];
