@@ -166,7 +166,7 @@ constexpr size_t KLU_WAVE_SMEM =
 __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(KluPlanD P, KluWaveD W, int Bp,
                                                                               const double* __restrict__ Axs,
                                                                               double* __restrict__ LU, int* __restrict__ status,
-                                                                              long long* __restrict__ dbg) {
+                                                                              long long* __restrict__ dbg, int tmode) {
     extern __shared__ double smem_klu[];
     double* xs = smem_klu;
     double* stage = smem_klu + KLU_WAVE_ROWS * 32;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
     const double* axg = Axs + (long long)blockIdx.x * 32;
     int bad = 0;
     const int srow = tid >> 4, spc = (tid & 15) * 2;
-    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0;
+    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0, t_w = 0, t_b = 0, t_i = 0;
     auto stage_batch = [&](long long bi, int ls0, int ls1, int buf) {
         double* dst = stage + (long long)buf * KLU_STAGE_DOUBLES;
         if (ls0 >= 0) klu_cp_async16(dst + srow * 32 + spc, lug + (long long)ls0 * Bp + spc);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
         if (dbg) tA = clock64();
         const int k0 = W.wave_col0[w], wc = W.wave_col0[w + 1] - k0;
         // team = the warps that share one column: 16 / (wc rounded up to a power of two) warps
-        const int tshift = (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
+        const int tshift = tmode ? 0 : (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
         const int T = 1 << tshift, col = warp >> tshift, sub = warp & (T - 1);
         const bool active = col < wc;
         const int k = k0 + (active ? col : 0);
@@ -227,8 +227,12 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
         if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
         int buf = 0;
         for (int c = 0; c < nb; c++) {
+            long long q0 = 0, q1 = 0, q2 = 0;
+            if (dbg) q0 = clock64();
             asm volatile("cp.async.wait_group %0;" ::"n"(KLU_STAGES - 2));
+            if (dbg) q1 = clock64();
             __syncthreads();
+            if (dbg) { q2 = clock64(); t_w += q1 - q0; t_b += q2 - q1; }
             const int nc = c + KLU_STAGES - 1;
             int nbuf = buf + KLU_STAGES - 1; if (nbuf >= KLU_STAGES) nbuf -= KLU_STAGES;
             if (nc < nb) {
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
                 stage_batch(c0 + nc, rsn[srow], rsn[srow + 32], nbuf);
             }
             asm volatile("cp.async.commit_group;");
+            if (dbg) { long long q3 = clock64(); t_i += q3 - q2; }
             if (active) {
                 const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
                 const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
@@ -246,6 +251,34 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
                 const int nseg = (int)rec[0];
                 // per matched segment: team barrier (the previous segment may have written u_jk or the same rows from
                 // another warp of the team), then the segment's rows are split over the team in chunks of four
+                if (tmode) {
+                    for (int sgi = 1; sgi <= nseg; sgi++) {
+                        const unsigned sd = rec[sgi];
+                        const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
+                        const double ujk = x[(sd >> 16) * 32];
+                        int t = r0;
+                        for (; t + 8 <= r1; t += 8) {
+                            int e[8]; double m[8], xv[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
+#pragma unroll
+                            for (int q = 0; q < 8; q++) xv[q] = x[e[q]];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) x[e[q]] = xv[q] - m[q] * ujk;
+                        }
+                        if (t + 4 <= r1) {
+                            int e[4]; double m[4], xv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) x[e[q]] = xv[q] - m[q] * ujk;
+                            t += 4;
+                        }
+                        for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;
+                    }
+                } else
                 for (int sgi = 1; sgi <= nseg; sgi++) {
                     const unsigned sd = rec[sgi];
                     const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
@@ -335,9 +368,271 @@ __global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(Kl
             n_rounds++;
             if (__syncthreads_count(!fin) == 0) break;
         }
-        if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; }
+        if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; if (tid == 0 && blockIdx.x == 0) { dbg[8 + 2 * w] = t_init + t_p1; dbg[9 + 2 * w] = t_p2; } }
     }
-    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; }
+    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = t_w; dbg[5] = t_b; dbg[6] = t_i; }
+    if (bad) status[b] = ST_SINGULAR;
+}
+
+// mbarrier / TMA-bulk helpers (shared::cta addresses)
+__device__ __forceinline__ void klu_mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count));
+}
+__device__ __forceinline__ void klu_mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void klu_mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void klu_mbar_wait(unsigned long long* b, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void klu_bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                 "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+constexpr int KLU_CONS_BAR = 9;      // named barrier of the 16 consumer warps (team barriers use 1..8)
+
+// Fast path (TMA variant): wave schedule.  One CTA per group of 32 matrices (lane = matrix), one warp per column of
+// the wave, plus ONE PRODUCER WARP that streams the staged batches with cp.async.bulk (256-byte rows + the batch's
+// records) into a KLU_STAGES-deep ring guarded by full/empty mbarriers: the consumer warps never issue a copy and
+// there is no CTA-wide barrier per batch.
+//   xs    : the columns of the wave, [row][32 matrices] doubles -- every lane touches only its own matrix
+//   stage : KLU_STAGES-deep cp.async ring; a batch = 64 rows of finished L columns (read once from HBM/L2 and
+//           consumed by every column of the wave) + for each warp and row what to do with it (destination row, row
+//           holding u_jk) so that the update loop reads NO metadata from global memory
+//   blob  : the updates between columns of the same wave (applied in rounds from the source's xs region)
+// The input values arrive pre-scaled (k_klu_prescale), gathered straight into xs by cp.async with zero fill.
+__global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_wave_tma(KluPlanD P, KluWaveD W, int Bp,
+                                                                              const double* __restrict__ Axs,
+                                                                              double* __restrict__ LU, int* __restrict__ status,
+                                                                              long long* __restrict__ dbg, int tmode) {
+    extern __shared__ double smem_klu[];
+    double* xs = smem_klu;
+    double* stage = smem_klu + KLU_WAVE_ROWS * 32;
+    double* blob = stage + KLU_STAGES * KLU_STAGE_DOUBLES;
+    __shared__ int done_round[KLU_WAVE_WARPS];
+    __shared__ unsigned long long full_bar[KLU_STAGES], empty_bar[KLU_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    double* lu = LU + b;
+    const double* lug = LU + (long long)blockIdx.x * 32;          // group base for the cooperative copies
+    const double* axg = Axs + (long long)blockIdx.x * 32;
+    int bad = 0;
+    const int srow = tid >> 4, spc = (tid & 15) * 2;
+    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0;
+    if (tid == 0) {
+        for (int s = 0; s < KLU_STAGES; s++) { klu_mbar_init(&full_bar[s], 1); klu_mbar_init(&empty_bar[s], KLU_WAVE_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == KLU_WAVE_WARPS) {
+        // ---------------- producer warp: lane r issues staged rows r and r + 32 of every batch
+        constexpr unsigned META_BYTES = KLU_WAVE_WARPS * KLU_REC_U32 * 4;
+        for (int w = 0; w < W.nwaves; w++) {
+            const long long c0 = W.wbatch_ptr[w], c1 = W.wbatch_ptr[w + 1];
+            int ls0 = 0, ls1 = 0;
+            if (c0 < c1) { ls0 = W.batch_rowslot[c0 * KLU_CHUNK_ROWS + lane]; ls1 = W.batch_rowslot[c0 * KLU_CHUNK_ROWS + 32 + lane]; }
+            for (long long g = c0; g < c1; g++) {
+                const int slot = (int)(g % KLU_STAGES);
+                const unsigned par = (unsigned)((g / KLU_STAGES) & 1);
+                const int a0 = ls0, a1 = ls1;
+                if (g + 1 < c1) { ls0 = W.batch_rowslot[(g + 1) * KLU_CHUNK_ROWS + lane]; ls1 = W.batch_rowslot[(g + 1) * KLU_CHUNK_ROWS + 32 + lane]; }
+                klu_mbar_wait(&empty_bar[slot], par ^ 1u);
+                const int nrows = __popc(__ballot_sync(0xffffffffu, a0 >= 0)) + __popc(__ballot_sync(0xffffffffu, a1 >= 0));
+                double* dst = stage + (long long)slot * KLU_STAGE_DOUBLES;
+                if (lane == 0) klu_mbar_expect_tx(&full_bar[slot], (unsigned)nrows * 256u + META_BYTES);
+                __syncwarp();
+                if (a0 >= 0) klu_bulk_g2s(dst + lane * 32, lug + (long long)a0 * Bp, 256u, &full_bar[slot]);
+                if (a1 >= 0) klu_bulk_g2s(dst + (lane + 32) * 32, lug + (long long)a1 * Bp, 256u, &full_bar[slot]);
+                if (lane == 0) klu_bulk_g2s(dst + KLU_CHUNK_ROWS * 32, W.bentry + g * KLU_ENTRY_DOUBLES * 2, META_BYTES, &full_bar[slot]);
+            }
+            asm volatile("bar.sync 0;" ::: "memory");       // end of wave: the consumers stored (and fenced) the wave's columns
+        }
+        return;
+    }
+    for (int w = 0; w < W.nwaves; w++) {
+        if (dbg) tA = clock64();
+        const int k0 = W.wave_col0[w], wc = W.wave_col0[w + 1] - k0;
+        // team = the warps that share one column: 16 / (wc rounded up to a power of two) warps
+        const int tshift = tmode ? 0 : (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
+        const int T = 1 << tshift, col = warp >> tshift, sub = warp & (T - 1);
+        const bool active = col < wc;
+        const int k = k0 + (active ? col : 0);
+        const int cb = (int)P.cbeg[k];
+        const int len = (int)P.cbeg[k + 1] - cb;
+        double* x = xs + W.col_roff[k] * 32 + lane;
+        const int diag = P.udiag_slot[k] - cb, l0 = P.lslot0[k] - cb;
+        const long long c0 = W.wbatch_ptr[w];
+        const int nb = (int)(W.wbatch_ptr[w + 1] - c0);
+        auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
+        // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
+        {
+            const int klast = k0 + wc - 1;
+            const int wrows = W.col_roff[klast] + (int)(P.cbeg[klast + 1] - P.cbeg[klast]);
+            const int* rsrc = W.wave_rowsrc + (long long)w * KLU_WAVE_ROWS;
+            for (int row = srow; row < wrows; row += 32) {
+                const int src = rsrc[row];
+                klu_cp_async16_zfill(xs + row * 32 + spc, src >= 0 ? axg + (long long)src * Bp + spc : axg, src >= 0 ? 16 : 0);
+            }
+            const long long bp0 = W.wblob_ptr[w];
+            const int pieces = (int)(W.wblob_ptr[w + 1] - bp0);
+            for (int q = tid; q < pieces; q += KLU_WAVE_WARPS * 32) klu_cp_async16(blob + q * 2, W.wblob + (bp0 + q) * 4);
+            asm volatile("cp.async.commit_group;");
+        }
+        asm volatile("cp.async.wait_group 0;");
+        asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
+        if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
+        for (int c = 0; c < nb; c++) {
+            const long long g = c0 + c;
+            const int buf = (int)(g % KLU_STAGES);
+            klu_mbar_wait(&full_bar[buf], (unsigned)((g / KLU_STAGES) & 1));
+            if (active) {
+                const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
+                const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
+                                      col * KLU_REC_U32;
+                const unsigned short* dd = reinterpret_cast<const unsigned short*>(rec + 16);
+                const int nseg = (int)rec[0];
+                // per matched segment: team barrier (the previous segment may have written u_jk or the same rows from
+                // another warp of the team), then the segment's rows are split over the team in chunks of four
+                if (tmode) {
+                    for (int sgi = 1; sgi <= nseg; sgi++) {
+                        const unsigned sd = rec[sgi];
+                        const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
+                        const double ujk = x[(sd >> 16) * 32];
+                        int t = r0;
+                        for (; t + 8 <= r1; t += 8) {
+                            int e[8]; double m[8], xv[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
+#pragma unroll
+                            for (int q = 0; q < 8; q++) xv[q] = x[e[q]];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) x[e[q]] = xv[q] - m[q] * ujk;
+                        }
+                        if (t + 4 <= r1) {
+                            int e[4]; double m[4], xv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) x[e[q]] = xv[q] - m[q] * ujk;
+                            t += 4;
+                        }
+                        for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;
+                    }
+                } else
+                for (int sgi = 1; sgi <= nseg; sgi++) {
+                    const unsigned sd = rec[sgi];
+                    const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
+                    int t = r0 + 4 * sub;
+                    // operands of the first chunk are fetched before the team barrier (they do not depend on it)
+                    const bool first = t + 4 <= r1;
+                    int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+                    double l0v = 0, l1v = 0, l2v = 0, l3v = 0;
+                    if (first) {
+                        d0 = dd[t] * 32; d1 = dd[t + 1] * 32; d2 = dd[t + 2] * 32; d3 = dd[t + 3] * 32;
+                        l0v = sb[t * 32]; l1v = sb[(t + 1) * 32]; l2v = sb[(t + 2) * 32]; l3v = sb[(t + 3) * 32];
+                    }
+                    team_sync();
+                    const double ujk = x[(sd >> 16) * 32];
+                    if (first) {
+                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
+                        x[d0] = x0 - l0v * ujk; x[d1] = x1 - l1v * ujk; x[d2] = x2 - l2v * ujk; x[d3] = x3 - l3v * ujk;
+                        t += 4 * T;
+                    }
+                    for (; t + 4 <= r1; t += 4 * T) {
+                        const int e0 = dd[t] * 32, e1 = dd[t + 1] * 32, e2 = dd[t + 2] * 32, e3 = dd[t + 3] * 32;
+                        const double m0 = sb[t * 32], m1 = sb[(t + 1) * 32], m2 = sb[(t + 2) * 32], m3 = sb[(t + 3) * 32];
+                        const double x0 = x[e0], x1 = x[e1], x2 = x[e2], x3 = x[e3];
+                        x[e0] = x0 - m0 * ujk; x[e1] = x1 - m1 * ujk; x[e2] = x2 - m2 * ujk; x[e3] = x3 - m3 * ujk;
+                    }
+                    for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;      // tail (< 4 rows) of the warp that owns it
+                }
+            }
+            __syncwarp();
+            if (lane == 0) klu_mbar_arrive(&empty_bar[buf]);
+        }
+        if (tid < KLU_WAVE_WARPS) done_round[tid] = 0x7fffffff;
+        asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
+        if (dbg) { long long tB = clock64(); t_p1 += tB - tA; tA = tB; }
+        // ---- sources inside the wave: rounds.  In round r a column consumes (in pivot order) the in-wave sources
+        // finalized in rounds < r from their xs regions, and finalizes itself once all its updates are applied.
+        const unsigned* bl = reinterpret_cast<const unsigned*>(blob);
+        int ui = active ? (int)bl[2 * col] : 0;
+        const int ue = active ? ui + (int)bl[2 * col + 1] : 0;
+        const int nupd_wave = (int)(bl[2 * (wc - 1)] + bl[2 * (wc - 1) + 1]);
+        const unsigned* updl = bl + 2 * KLU_WAVE_WARPS;
+        const unsigned short* bdst = reinterpret_cast<const unsigned short*>(updl + 4 * nupd_wave);
+        bool fin = !active;
+        for (int r = 0;; r++) {
+            if (!fin) {
+                while (ui < ue) {
+                    const unsigned w0 = updl[4 * ui];
+                    if (done_round[w0 & 0xffu] >= r) break;
+                    team_sync();                  // the previous update (or the staged phase) of every team warp is done
+                    const double uj = x[updl[4 * ui + 1] * 32];
+                    const int cnt = (int)updl[4 * ui + 2];
+                    const unsigned short* d = bdst + updl[4 * ui + 3];
+                    const double* lsrc = xs + (w0 >> 8) * 32 + lane;
+                    int t = sub * 4;
+                    for (; t + 4 <= cnt; t += 4 * T) {
+                        const int d0 = d[t] * 32, d1 = d[t + 1] * 32, d2 = d[t + 2] * 32, d3 = d[t + 3] * 32;
+                        const double l0v = lsrc[t * 32], l1v = lsrc[(t + 1) * 32], l2v = lsrc[(t + 2) * 32], l3v = lsrc[(t + 3) * 32];
+                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
+                        x[d0] = x0 - l0v * uj; x[d1] = x1 - l1v * uj; x[d2] = x2 - l2v * uj; x[d3] = x3 - l3v * uj;
+                    }
+                    for (; t < cnt; t++) x[d[t] * 32] -= lsrc[t * 32] * uj;     // tail (< 4 rows) of the warp that owns it
+                    ui++;
+                }
+                if (ui == ue && k >= W.spine0) {
+                    // column of the dense trailing block: only the updates from columns < spine0 were applied here;
+                    // store it unfinished, k_klu_dense_lu factors the block
+                    team_sync();
+#pragma unroll 4
+                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
+                    fin = true;
+                    if (lane == 0 && sub == 0) done_round[col] = r;
+                } else if (ui == ue) {
+                    team_sync();
+                    const double piv = x[diag * 32];
+                    if (!(fabs(piv) > 0.0)) bad = 1;
+                    team_sync();                  // everyone has read the pivot before the column is rewritten
+                    const double rpiv = 1.0 / piv;    // one division per column; L(:,k) = x * (1/pivot)
+#pragma unroll 4
+                    for (int sl = l0 + sub; sl < len; sl += T) x[sl * 32] *= rpiv;
+                    team_sync();
+#pragma unroll 4
+                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
+                    fin = true;
+                    if (lane == 0 && sub == 0) done_round[col] = r;
+                }
+            }
+            n_rounds++;
+            {
+                unsigned left;
+                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nbar.red.popc.u32 %0, %2, %3, p;\n}\n"
+                             : "=r"(left) : "r"((unsigned)!fin), "n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
+                if (left == 0) break;
+            }
+        }
+        if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; if (tid == 0 && blockIdx.x == 0) { dbg[8 + 2 * w] = t_init + t_p1; dbg[9 + 2 * w] = t_p2; } }
+        // the wave's columns are in global memory: make them visible to the producer's bulk (async-proxy) reads
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("bar.sync 0;" ::: "memory");
+    }
+    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = dbg[5] = dbg[6] = 0; }
     if (bad) status[b] = ST_SINGULAR;
 }
 
@@ -857,6 +1152,7 @@ public:
     double* dD = nullptr;
     int spine_nd = 0, ndmap = 0, ndp = 0;
     size_t dense_smem = 0;
+    std::vector<int> h_wave_col0;
     long long* ddbg = nullptr;     // optional phase timers of the wave kernel (B200S_KLU_DEBUG=1)
     long long* d_rowptr = nullptr;
     long long nslots = 0, nnzA = 0;
@@ -894,7 +1190,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     n = P.n; nslots = P.nslots; nnzA = P.nnzA;
-    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(cudaMalloc((void**)&ddbg, 8 * sizeof(long long))); owned.push_back(ddbg); }
+    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(cudaMalloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; }
     int rc;
     PD.n = P.n; PD.nlevels = P.nlevels;
     std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
@@ -941,7 +1237,10 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
             CUDA_TRY(cudaFuncSetAttribute(k_klu_dense_lu, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)dense_smem));
         if (use_wave)
+        {
             CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
+        }
     }
     const int* tmp_i; const long long* tmp_l;
     if ((rc = up(&tmp_i, P.slot_src))) return rc; d_slot_src = (int*)tmp_i;
@@ -1008,7 +1307,10 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
         if (nslots > lu_slots)
             k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
-        k_klu_refactor_wave<<<Bp / 32, KLU_WAVE_WARPS * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
+        if (!getenv("B200S_KLU_TMA"))
+            k_klu_refactor_wave<<<Bp / 32, KLU_WAVE_WARPS * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg, getenv("B200S_KLU_T1") ? 1 : 0);
+        else
+            k_klu_refactor_wave_tma<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg, getenv("B200S_KLU_T1") ? 1 : 0);
         CUDA_TRY(cudaEventRecord(ev[6], stream));
         launches = 4 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
         if (spine_nd > 0) {
@@ -1038,7 +1340,15 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     if (ddbg) {
         long long h[8] = {0};
         cudaMemcpy(h, ddbg, sizeof h, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld)\n", h[0], h[1], h[2], h[3]);
+        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld) | warp0 p1: wait_group %lld barrier %lld issue %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+        if (const char* f = getenv("B200S_KLU_DEBUG_FILE")) {
+            std::vector<long long> hw(8 + 2 * (size_t)WD.nwaves);
+            cudaMemcpy(hw.data(), ddbg, hw.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            if (FILE* fp = fopen(f, "w")) {
+                for (int w = 0; w < WD.nwaves; w++) fprintf(fp, "%d %d %lld %lld\n", w, h_wave_col0[w], hw[8 + 2 * w], hw[9 + 2 * w]);
+                fclose(fp);
+            }
+        }
     }
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); ms_h2d = ms;
