@@ -186,6 +186,13 @@ b200s_status b200s_klu_refactor_batch(b200s_klu_num* N, const double* vals, b200
                                       b200s_int ldv, int* status_per_matrix);
 b200s_status b200s_klu_refactor_batch_dev(b200s_klu_num* N, const double* vals_dev, b200s_int batch,
                                           b200s_int ldv, int* status_per_matrix);
+/* Pipelined form of b200s_klu_refactor_batch for callers that stream many batches: _begin enqueues the upload of
+ * `vals` (host memory, ideally pinned; it must stay valid until the matching _end) and the refactorization kernels
+ * and returns at once; _end waits for the OLDEST batch in flight and returns its per-matrix status.  Up to two
+ * batches may be in flight: the upload of batch i+1 then overlaps the kernels of batch i.  The device factors
+ * always hold the most recently begun batch (solve after the matching _end and before the next _begin). */
+b200s_status b200s_klu_refactor_batch_begin(b200s_klu_num* N, const double* vals, b200s_int batch, b200s_int ldv);
+b200s_status b200s_klu_refactor_batch_end(b200s_klu_num* N, int* status_per_matrix);
 /* klu.solve (src/C/klu.c:593-690) for every matrix of the last refactored batch:
  * B is batch blocks of n x nrhs column-major (block stride ldB*nrhs), overwritten.  trans 0 = 'N', 1 = 'T'. */
 b200s_status b200s_klu_solve_batch(b200s_klu_num* N, int trans, double* B, b200s_int nrhs,

@@ -77,6 +77,8 @@ SIGNATURES = {
     "b200s_klu_extract_host": (C.c_int, vp, p_f64, p_f64, p_f64, p_f64),
     "b200s_klu_refactor_batch": (C.c_int, vp, p_f64, i64, i64, p_int),
     "b200s_klu_refactor_batch_dev": (C.c_int, vp, vp, i64, i64, p_int),
+    "b200s_klu_refactor_batch_begin": (C.c_int, vp, p_f64, i64, i64),
+    "b200s_klu_refactor_batch_end": (C.c_int, vp, p_int),
     "b200s_klu_solve_batch": (C.c_int, vp, C.c_int, p_f64, i64, i64, i64),
     "b200s_klu_solve_batch_dev": (C.c_int, vp, C.c_int, vp, i64, i64, i64),
     "b200s_klu_solve": (C.c_int, vp, C.c_int, p_f64, i64, i64),

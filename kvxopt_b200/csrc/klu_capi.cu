@@ -14,6 +14,8 @@ class KluDevice;
 KluDevice* klu_device_create(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S, int device, int* status);
 void klu_device_destroy(KluDevice* d);
 int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status);
+int klu_device_refactor_begin(KluDevice* d, const double* vals, long long batch, long long ldv);
+int klu_device_refactor_end(KluDevice* d, int* status);
 int klu_device_solve(KluDevice* d, int trans, double* B, long long nrhs, long long ldB, long long batch, bool on_device);
 int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs_host);
 void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel, double* dense, long long* launches);
@@ -119,6 +121,20 @@ b200s_status b200s_klu_refactor_batch(b200s_klu_num* N, const double* vals, b200
 }
 b200s_status b200s_klu_refactor_batch_dev(b200s_klu_num* N, const double* vals_dev, b200s_int batch, b200s_int ldv, int* status_per_matrix) {
     return refactor_impl(N, vals_dev, true, batch, ldv, status_per_matrix);
+}
+
+b200s_status b200s_klu_refactor_batch_begin(b200s_klu_num* N, const double* vals, b200s_int batch, b200s_int ldv) {
+    if (!N || batch < 0) return B200S_INVALID;
+    if (N->N.n == 0 || batch == 0) return B200S_OK;
+    if (!vals || ldv < N->S.nnz || batch > 0x7fffff00) return B200S_INVALID;
+    if (!N->dev) return B200S_NO_DEVICE;
+    return (b200s_status)klu_device_refactor_begin(N->dev, vals, batch, ldv);
+}
+b200s_status b200s_klu_refactor_batch_end(b200s_klu_num* N, int* status_per_matrix) {
+    if (!N) return B200S_INVALID;
+    if (N->N.n == 0) return B200S_OK;
+    if (!N->dev) return B200S_NO_DEVICE;
+    return (b200s_status)klu_device_refactor_end(N->dev, status_per_matrix);
 }
 
 static b200s_status solve_impl(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB, b200s_int batch, bool on_device) {

@@ -9,7 +9,9 @@
 // order and therefore the instruction stream are identical for all matrices.
 //   Axt [nnzA ][Bp]  transposed copy of the caller's values
 //   Rs  [n    ][Bp]  row scale factors (max |row|), pivotal row order
-//   LU  [slots][Bp]  per column: U above the diagonal, U diagonal, L below the diagonal; then F
+//   LU  [Bp/32][slots][32]  GROUP-MAJOR: the slots of a group of 32 matrices are contiguous (value v of matrix b at
+//       (b/32)*slots*32 + v*32 + b%32), so a run of consecutive slots -- the L part of a column -- is ONE contiguous
+//       block that a single cp.async.bulk (TMA) moves.  Per column: U above the diagonal, U diagonal, L below; then F
 // Kernels: k_klu_transpose (tiled), k_klu_rowscale, k_klu_scatter, k_klu_refactor (one CTA per group of
 // 32 matrices walks the column level schedule, 16 warps share the columns of a level), k_klu_solve.
 #include "gpu.hpp"
@@ -73,18 +75,19 @@ __global__ void k_klu_rowscale(const long long* __restrict__ rowptr, const int* 
 // LU[v][b] = A(src(v))[b] / Rs[row(v)][b], zero for fill-in slots
 __global__ void k_klu_scatter(const int* __restrict__ slot_src, const int* __restrict__ slot_row, long long slot0,
                               long long nslots, int Bp, const double* __restrict__ Axt, const double* __restrict__ Rs,
-                              double* __restrict__ LU, int prescaled) {
+                              double* __restrict__ LU, int prescaled, long long gstride) {
     const long long total = nslots * Bp, first = slot0 * Bp;
     for (long long t = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long v = t / Bp;
         const int b = (int)(t - v * Bp);
         const int src = slot_src[v];
-        LU[t] = (src >= 0) ? (prescaled ? Axt[(long long)src * Bp + b] : Axt[(long long)src * Bp + b] / Rs[(long long)slot_row[v] * Bp + b]) : 0.0;
+        LU[(long long)(b >> 5) * gstride + v * 32 + (b & 31)] = (src >= 0) ? (prescaled ? Axt[(long long)src * Bp + b] : Axt[(long long)src * Bp + b] / Rs[(long long)slot_row[v] * Bp + b]) : 0.0;
     }
 }
 
 struct KluPlanD {
     int n, nlevels;
+    long long gstride;          // doubles between the LU blocks of consecutive groups of 32 matrices (= slots * 32)
     const int *level_ptr, *level_cols, *udiag_slot, *lslot0, *upd_uslot, *upd_lslot, *upd_cnt, *dest;
     const long long *cbeg, *upd_ptr, *upd_dest;
 };
@@ -92,38 +95,38 @@ struct KluPlanD {
 // One CTA per group of 32 matrices.  Levels of the column dependency graph are separated by
 // __syncthreads(); inside a level each warp takes whole columns.
 constexpr int KLU_WARPS = 16;
-__global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, int Bp, double* __restrict__ LU,
+__global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, long long gstride, double* __restrict__ LU,
                                                                  int* __restrict__ status) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
-    double* lu = LU + b;
+    double* lu = LU + (long long)blockIdx.x * gstride + lane;
     int bad = 0;
     for (int l = 0; l < P.nlevels; l++) {
         for (int c = P.level_ptr[l] + warp; c < P.level_ptr[l + 1]; c += KLU_WARPS) {
             const int k = P.level_cols[c];
             for (long long u = P.upd_ptr[k]; u < P.upd_ptr[k + 1]; u++) {
-                const double ujk = lu[(long long)P.upd_uslot[u] * Bp];
+                const double ujk = lu[(long long)P.upd_uslot[u] * 32];
                 const int cnt = P.upd_cnt[u];
-                const double* lcol = lu + (long long)P.upd_lslot[u] * Bp;
+                const double* lcol = lu + (long long)P.upd_lslot[u] * 32;
                 const int* d = P.dest + P.upd_dest[u];
                 int t = 0;
                 for (; t + 4 <= cnt; t += 4) {
-                    const double l0 = lcol[(long long)t * Bp], l1 = lcol[(long long)(t + 1) * Bp];
-                    const double l2 = lcol[(long long)(t + 2) * Bp], l3 = lcol[(long long)(t + 3) * Bp];
-                    double* p0 = lu + (long long)d[t] * Bp; double* p1 = lu + (long long)d[t + 1] * Bp;
-                    double* p2 = lu + (long long)d[t + 2] * Bp; double* p3 = lu + (long long)d[t + 3] * Bp;
+                    const double l0 = lcol[(long long)t * 32], l1 = lcol[(long long)(t + 1) * 32];
+                    const double l2 = lcol[(long long)(t + 2) * 32], l3 = lcol[(long long)(t + 3) * 32];
+                    double* p0 = lu + (long long)d[t] * 32; double* p1 = lu + (long long)d[t + 1] * 32;
+                    double* p2 = lu + (long long)d[t + 2] * 32; double* p3 = lu + (long long)d[t + 3] * 32;
                     const double x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
                     *p0 = x0 - l0 * ujk; *p1 = x1 - l1 * ujk; *p2 = x2 - l2 * ujk; *p3 = x3 - l3 * ujk;
                 }
                 for (; t < cnt; t++) {
-                    double* p0 = lu + (long long)d[t] * Bp;
-                    *p0 -= lcol[(long long)t * Bp] * ujk;
+                    double* p0 = lu + (long long)d[t] * 32;
+                    *p0 -= lcol[(long long)t * 32] * ujk;
                 }
             }
-            const double piv = lu[(long long)P.udiag_slot[k] * Bp];
+            const double piv = lu[(long long)P.udiag_slot[k] * 32];
             if (!(fabs(piv) > 0.0)) bad = 1;            // zero or NaN pivot
             const long long l0 = P.lslot0[k], l1 = P.cbeg[k + 1];
-            for (long long s = l0; s < l1; s++) lu[s * Bp] /= piv;
+            for (long long s = l0; s < l1; s++) lu[s * 32] /= piv;
         }
         __syncthreads();
     }
@@ -140,6 +143,8 @@ struct KluWaveD {
     const unsigned* bentry;     // per batch [KLU_WAVE_WARPS][KLU_CHUNK_ROWS] staged-row actions
     const unsigned* wblob;      // in-wave update blobs
     const long long *wbatch_ptr, *wblob_ptr;
+    const int* bseg_ptr;        // per batch: its staged segments [bseg_ptr[g], bseg_ptr[g+1])
+    const int2* segd;           // per segment: {first LU slot, first stage row | rows << 8}: rows consecutive slots = one bulk copy
 };
 
 __device__ __forceinline__ void klu_cp_async16(void* smem, const void* gmem) {
@@ -155,224 +160,6 @@ constexpr int KLU_ENTRY_DOUBLES = (KLU_WAVE_WARPS * KLU_REC_U32 + KLU_CHUNK_ROWS
 constexpr int KLU_STAGE_DOUBLES = KLU_CHUNK_ROWS * 32 + KLU_ENTRY_DOUBLES;      // L rows + per-warp row actions
 constexpr size_t KLU_WAVE_SMEM =
     (size_t)(KLU_WAVE_ROWS * 32 + KLU_STAGES * KLU_STAGE_DOUBLES) * sizeof(double) + KLU_BLOB_BYTES;
-
-// Fast path: wave schedule.  One CTA per group of 32 matrices (lane = matrix), one warp per column of the wave.
-//   xs    : the columns of the wave, [row][32 matrices] doubles -- every lane touches only its own matrix
-//   stage : KLU_STAGES-deep cp.async ring; a batch = 64 rows of finished L columns (read once from HBM/L2 and
-//           consumed by every column of the wave) + for each warp and row what to do with it (destination row, row
-//           holding u_jk) so that the update loop reads NO metadata from global memory
-//   blob  : the updates between columns of the same wave (applied in rounds from the source's xs region)
-// The input values arrive pre-scaled (k_klu_prescale), gathered straight into xs by cp.async with zero fill.
-__global__ void __launch_bounds__(KLU_WAVE_WARPS * 32, 1) k_klu_refactor_wave(KluPlanD P, KluWaveD W, int Bp,
-                                                                              const double* __restrict__ Axs,
-                                                                              double* __restrict__ LU, int* __restrict__ status,
-                                                                              long long* __restrict__ dbg, int tmode) {
-    extern __shared__ double smem_klu[];
-    double* xs = smem_klu;
-    double* stage = smem_klu + KLU_WAVE_ROWS * 32;
-    double* blob = stage + KLU_STAGES * KLU_STAGE_DOUBLES;
-    __shared__ int done_round[KLU_WAVE_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x * 32 + lane;
-    double* lu = LU + b;
-    const double* lug = LU + (long long)blockIdx.x * 32;          // group base for the cooperative copies
-    const double* axg = Axs + (long long)blockIdx.x * 32;
-    int bad = 0;
-    const int srow = tid >> 4, spc = (tid & 15) * 2;
-    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0, t_w = 0, t_b = 0, t_i = 0;
-    auto stage_batch = [&](long long bi, int ls0, int ls1, int buf) {
-        double* dst = stage + (long long)buf * KLU_STAGE_DOUBLES;
-        if (ls0 >= 0) klu_cp_async16(dst + srow * 32 + spc, lug + (long long)ls0 * Bp + spc);
-        if (ls1 >= 0) klu_cp_async16(dst + (srow + 32) * 32 + spc, lug + (long long)ls1 * Bp + spc);
-        if (tid < KLU_ENTRY_DOUBLES / 2)
-            klu_cp_async16(dst + KLU_CHUNK_ROWS * 32 + tid * 2, W.bentry + (bi * KLU_ENTRY_DOUBLES + tid * 2) * 2);
-    };
-    for (int w = 0; w < W.nwaves; w++) {
-        if (dbg) tA = clock64();
-        const int k0 = W.wave_col0[w], wc = W.wave_col0[w + 1] - k0;
-        // team = the warps that share one column: 16 / (wc rounded up to a power of two) warps
-        const int tshift = tmode ? 0 : (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
-        const int T = 1 << tshift, col = warp >> tshift, sub = warp & (T - 1);
-        const bool active = col < wc;
-        const int k = k0 + (active ? col : 0);
-        const int cb = (int)P.cbeg[k];
-        const int len = (int)P.cbeg[k + 1] - cb;
-        double* x = xs + W.col_roff[k] * 32 + lane;
-        const int diag = P.udiag_slot[k] - cb, l0 = P.lslot0[k] - cb;
-        const long long c0 = W.wbatch_ptr[w];
-        const int nb = (int)(W.wbatch_ptr[w + 1] - c0);
-        auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
-        // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
-        {
-            const int klast = k0 + wc - 1;
-            const int wrows = W.col_roff[klast] + (int)(P.cbeg[klast + 1] - P.cbeg[klast]);
-            const int* rsrc = W.wave_rowsrc + (long long)w * KLU_WAVE_ROWS;
-            for (int row = srow; row < wrows; row += 32) {
-                const int src = rsrc[row];
-                klu_cp_async16_zfill(xs + row * 32 + spc, src >= 0 ? axg + (long long)src * Bp + spc : axg, src >= 0 ? 16 : 0);
-            }
-            const long long bp0 = W.wblob_ptr[w];
-            const int pieces = (int)(W.wblob_ptr[w + 1] - bp0);
-            for (int q = tid; q < pieces; q += KLU_WAVE_WARPS * 32) klu_cp_async16(blob + q * 2, W.wblob + (bp0 + q) * 4);
-            asm volatile("cp.async.commit_group;");
-        }
-        // ---- prologue of the batch pipeline
-        for (int st = 0; st < KLU_STAGES - 1; st++) {
-            if (st < nb) {
-                const int* rs = W.batch_rowslot + (c0 + st) * KLU_CHUNK_ROWS;
-                stage_batch(c0 + st, rs[srow], rs[srow + 32], st);
-            }
-            asm volatile("cp.async.commit_group;");
-        }
-        if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
-        int buf = 0;
-        for (int c = 0; c < nb; c++) {
-            long long q0 = 0, q1 = 0, q2 = 0;
-            if (dbg) q0 = clock64();
-            asm volatile("cp.async.wait_group %0;" ::"n"(KLU_STAGES - 2));
-            if (dbg) q1 = clock64();
-            __syncthreads();
-            if (dbg) { q2 = clock64(); t_w += q1 - q0; t_b += q2 - q1; }
-            const int nc = c + KLU_STAGES - 1;
-            int nbuf = buf + KLU_STAGES - 1; if (nbuf >= KLU_STAGES) nbuf -= KLU_STAGES;
-            if (nc < nb) {
-                // the row -> slot table of batch nc travelled with batch c (the one being consumed): no global load here
-                const int* rsn = reinterpret_cast<const int*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
-                                 KLU_WAVE_WARPS * KLU_REC_U32;
-                stage_batch(c0 + nc, rsn[srow], rsn[srow + 32], nbuf);
-            }
-            asm volatile("cp.async.commit_group;");
-            if (dbg) { long long q3 = clock64(); t_i += q3 - q2; }
-            if (active) {
-                const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
-                const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
-                                      col * KLU_REC_U32;
-                const unsigned short* dd = reinterpret_cast<const unsigned short*>(rec + 16);
-                const int nseg = (int)rec[0];
-                // per matched segment: team barrier (the previous segment may have written u_jk or the same rows from
-                // another warp of the team), then the segment's rows are split over the team in chunks of four
-                if (tmode) {
-                    for (int sgi = 1; sgi <= nseg; sgi++) {
-                        const unsigned sd = rec[sgi];
-                        const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
-                        const double ujk = x[(sd >> 16) * 32];
-                        int t = r0;
-                        for (; t + 8 <= r1; t += 8) {
-                            int e[8]; double m[8], xv[8];
-#pragma unroll
-                            for (int q = 0; q < 8; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
-#pragma unroll
-                            for (int q = 0; q < 8; q++) xv[q] = x[e[q]];
-#pragma unroll
-                            for (int q = 0; q < 8; q++) x[e[q]] = xv[q] - m[q] * ujk;
-                        }
-                        if (t + 4 <= r1) {
-                            int e[4]; double m[4], xv[4];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
-#pragma unroll
-                            for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) x[e[q]] = xv[q] - m[q] * ujk;
-                            t += 4;
-                        }
-                        for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;
-                    }
-                } else
-                for (int sgi = 1; sgi <= nseg; sgi++) {
-                    const unsigned sd = rec[sgi];
-                    const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
-                    int t = r0 + 4 * sub;
-                    // operands of the first chunk are fetched before the team barrier (they do not depend on it)
-                    const bool first = t + 4 <= r1;
-                    int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-                    double l0v = 0, l1v = 0, l2v = 0, l3v = 0;
-                    if (first) {
-                        d0 = dd[t] * 32; d1 = dd[t + 1] * 32; d2 = dd[t + 2] * 32; d3 = dd[t + 3] * 32;
-                        l0v = sb[t * 32]; l1v = sb[(t + 1) * 32]; l2v = sb[(t + 2) * 32]; l3v = sb[(t + 3) * 32];
-                    }
-                    team_sync();
-                    const double ujk = x[(sd >> 16) * 32];
-                    if (first) {
-                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
-                        x[d0] = x0 - l0v * ujk; x[d1] = x1 - l1v * ujk; x[d2] = x2 - l2v * ujk; x[d3] = x3 - l3v * ujk;
-                        t += 4 * T;
-                    }
-                    for (; t + 4 <= r1; t += 4 * T) {
-                        const int e0 = dd[t] * 32, e1 = dd[t + 1] * 32, e2 = dd[t + 2] * 32, e3 = dd[t + 3] * 32;
-                        const double m0 = sb[t * 32], m1 = sb[(t + 1) * 32], m2 = sb[(t + 2) * 32], m3 = sb[(t + 3) * 32];
-                        const double x0 = x[e0], x1 = x[e1], x2 = x[e2], x3 = x[e3];
-                        x[e0] = x0 - m0 * ujk; x[e1] = x1 - m1 * ujk; x[e2] = x2 - m2 * ujk; x[e3] = x3 - m3 * ujk;
-                    }
-                    for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;      // tail (< 4 rows) of the warp that owns it
-                }
-            }
-            if (++buf == KLU_STAGES) buf = 0;
-        }
-        asm volatile("cp.async.wait_group 0;");
-        if (tid < KLU_WAVE_WARPS) done_round[tid] = 0x7fffffff;
-        __syncthreads();
-        if (dbg) { long long tB = clock64(); t_p1 += tB - tA; tA = tB; }
-        // ---- sources inside the wave: rounds.  In round r a column consumes (in pivot order) the in-wave sources
-        // finalized in rounds < r from their xs regions, and finalizes itself once all its updates are applied.
-        const unsigned* bl = reinterpret_cast<const unsigned*>(blob);
-        int ui = active ? (int)bl[2 * col] : 0;
-        const int ue = active ? ui + (int)bl[2 * col + 1] : 0;
-        const int nupd_wave = (int)(bl[2 * (wc - 1)] + bl[2 * (wc - 1) + 1]);
-        const unsigned* updl = bl + 2 * KLU_WAVE_WARPS;
-        const unsigned short* bdst = reinterpret_cast<const unsigned short*>(updl + 4 * nupd_wave);
-        bool fin = !active;
-        for (int r = 0;; r++) {
-            if (!fin) {
-                while (ui < ue) {
-                    const unsigned w0 = updl[4 * ui];
-                    if (done_round[w0 & 0xffu] >= r) break;
-                    team_sync();                  // the previous update (or the staged phase) of every team warp is done
-                    const double uj = x[updl[4 * ui + 1] * 32];
-                    const int cnt = (int)updl[4 * ui + 2];
-                    const unsigned short* d = bdst + updl[4 * ui + 3];
-                    const double* lsrc = xs + (w0 >> 8) * 32 + lane;
-                    int t = sub * 4;
-                    for (; t + 4 <= cnt; t += 4 * T) {
-                        const int d0 = d[t] * 32, d1 = d[t + 1] * 32, d2 = d[t + 2] * 32, d3 = d[t + 3] * 32;
-                        const double l0v = lsrc[t * 32], l1v = lsrc[(t + 1) * 32], l2v = lsrc[(t + 2) * 32], l3v = lsrc[(t + 3) * 32];
-                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
-                        x[d0] = x0 - l0v * uj; x[d1] = x1 - l1v * uj; x[d2] = x2 - l2v * uj; x[d3] = x3 - l3v * uj;
-                    }
-                    for (; t < cnt; t++) x[d[t] * 32] -= lsrc[t * 32] * uj;     // tail (< 4 rows) of the warp that owns it
-                    ui++;
-                }
-                if (ui == ue && k >= W.spine0) {
-                    // column of the dense trailing block: only the updates from columns < spine0 were applied here;
-                    // store it unfinished, k_klu_dense_lu factors the block
-                    team_sync();
-#pragma unroll 4
-                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
-                    fin = true;
-                    if (lane == 0 && sub == 0) done_round[col] = r;
-                } else if (ui == ue) {
-                    team_sync();
-                    const double piv = x[diag * 32];
-                    if (!(fabs(piv) > 0.0)) bad = 1;
-                    team_sync();                  // everyone has read the pivot before the column is rewritten
-                    const double rpiv = 1.0 / piv;    // one division per column; L(:,k) = x * (1/pivot)
-#pragma unroll 4
-                    for (int sl = l0 + sub; sl < len; sl += T) x[sl * 32] *= rpiv;
-                    team_sync();
-#pragma unroll 4
-                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
-                    fin = true;
-                    if (lane == 0 && sub == 0) done_round[col] = r;
-                }
-            }
-            n_rounds++;
-            if (__syncthreads_count(!fin) == 0) break;
-        }
-        if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; if (tid == 0 && blockIdx.x == 0) { dbg[8 + 2 * w] = t_init + t_p1; dbg[9 + 2 * w] = t_p2; } }
-    }
-    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = t_w; dbg[5] = t_b; dbg[6] = t_i; }
-    if (bad) status[b] = ST_SINGULAR;
-}
 
 // mbarrier / TMA-bulk helpers (shared::cta addresses)
 __device__ __forceinline__ void klu_mbar_init(unsigned long long* b, int count) {
@@ -402,7 +189,7 @@ __device__ __forceinline__ void klu_bulk_g2s(void* smem, const void* gmem, unsig
 }
 constexpr int KLU_CONS_BAR = 9;      // named barrier of the 16 consumer warps (team barriers use 1..8)
 
-// Fast path (TMA variant): wave schedule.  One CTA per group of 32 matrices (lane = matrix), one warp per column of
+// Fast path: wave schedule.  One CTA per group of 32 matrices (lane = matrix), one warp per column of
 // the wave, plus ONE PRODUCER WARP that streams the staged batches with cp.async.bulk (256-byte rows + the batch's
 // records) into a KLU_STAGES-deep ring guarded by full/empty mbarriers: the consumer warps never issue a copy and
 // there is no CTA-wide barrier per batch.
@@ -412,10 +199,10 @@ constexpr int KLU_CONS_BAR = 9;      // named barrier of the 16 consumer warps (
 //           holding u_jk) so that the update loop reads NO metadata from global memory
 //   blob  : the updates between columns of the same wave (applied in rounds from the source's xs region)
 // The input values arrive pre-scaled (k_klu_prescale), gathered straight into xs by cp.async with zero fill.
-__global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_wave_tma(KluPlanD P, KluWaveD W, int Bp,
+__global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_wave(KluPlanD P, KluWaveD W, int Bp,
                                                                               const double* __restrict__ Axs,
                                                                               double* __restrict__ LU, int* __restrict__ status,
-                                                                              long long* __restrict__ dbg, int tmode) {
+                                                                              long long* __restrict__ dbg) {
     extern __shared__ double smem_klu[];
     double* xs = smem_klu;
     double* stage = smem_klu + KLU_WAVE_ROWS * 32;
@@ -424,12 +211,12 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     __shared__ unsigned long long full_bar[KLU_STAGES], empty_bar[KLU_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x * 32 + lane;
-    double* lu = LU + b;
-    const double* lug = LU + (long long)blockIdx.x * 32;          // group base for the cooperative copies
+    double* lu = LU + (long long)blockIdx.x * P.gstride + lane;
+    const double* lug = LU + (long long)blockIdx.x * P.gstride;   // group base for the cooperative copies
     const double* axg = Axs + (long long)blockIdx.x * 32;
     int bad = 0;
     const int srow = tid >> 4, spc = (tid & 15) * 2;
-    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0;
+    long long t_init = 0, t_p1 = 0, t_p2 = 0, n_rounds = 0, tA = 0, t_w = 0, t_w0 = 0;
     if (tid == 0) {
         for (int s = 0; s < KLU_STAGES; s++) { klu_mbar_init(&full_bar[s], 1); klu_mbar_init(&empty_bar[s], KLU_WAVE_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -440,20 +227,33 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         constexpr unsigned META_BYTES = KLU_WAVE_WARPS * KLU_REC_U32 * 4;
         for (int w = 0; w < W.nwaves; w++) {
             const long long c0 = W.wbatch_ptr[w], c1 = W.wbatch_ptr[w + 1];
-            int ls0 = 0, ls1 = 0;
-            if (c0 < c1) { ls0 = W.batch_rowslot[c0 * KLU_CHUNK_ROWS + lane]; ls1 = W.batch_rowslot[c0 * KLU_CHUNK_ROWS + 32 + lane]; }
+            int s0 = 0, s1 = 0;
+            int2 sd = make_int2(0, 0);
+            if (c0 < c1) { s0 = W.bseg_ptr[c0]; s1 = W.bseg_ptr[c0 + 1]; if (s0 + lane < s1) sd = W.segd[s0 + lane]; }
             for (long long g = c0; g < c1; g++) {
                 const int slot = (int)(g % KLU_STAGES);
                 const unsigned par = (unsigned)((g / KLU_STAGES) & 1);
-                const int a0 = ls0, a1 = ls1;
-                if (g + 1 < c1) { ls0 = W.batch_rowslot[(g + 1) * KLU_CHUNK_ROWS + lane]; ls1 = W.batch_rowslot[(g + 1) * KLU_CHUNK_ROWS + 32 + lane]; }
+                const int a0 = s0, a1 = s1;
+                const int2 cur = sd;
+                if (g + 1 < c1) {           // the next batch's descriptors are fetched while this one waits for its slot
+                    s0 = a1; s1 = W.bseg_ptr[g + 2];
+                    sd = make_int2(0, 0);
+                    if (s0 + lane < s1) sd = W.segd[s0 + lane];
+                }
                 klu_mbar_wait(&empty_bar[slot], par ^ 1u);
-                const int nrows = __popc(__ballot_sync(0xffffffffu, a0 >= 0)) + __popc(__ballot_sync(0xffffffffu, a1 >= 0));
                 double* dst = stage + (long long)slot * KLU_STAGE_DOUBLES;
-                if (lane == 0) klu_mbar_expect_tx(&full_bar[slot], (unsigned)nrows * 256u + META_BYTES);
+                // a batch holds at most KLU_CHUNK_ROWS (64) one-row segments: lane q takes segments q and q + 32
+                int2 ex = make_int2(0, 0);
+                if (a0 + 32 + lane < a1) ex = W.segd[a0 + 32 + lane];
+                int rows = (a0 + lane < a1 ? (cur.y >> 8) : 0) + (a0 + 32 + lane < a1 ? (ex.y >> 8) : 0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+                if (lane == 0) klu_mbar_expect_tx(&full_bar[slot], (unsigned)rows * 256u + META_BYTES);
                 __syncwarp();
-                if (a0 >= 0) klu_bulk_g2s(dst + lane * 32, lug + (long long)a0 * Bp, 256u, &full_bar[slot]);
-                if (a1 >= 0) klu_bulk_g2s(dst + (lane + 32) * 32, lug + (long long)a1 * Bp, 256u, &full_bar[slot]);
+                if (a0 + lane < a1)
+                    klu_bulk_g2s(dst + (cur.y & 0xff) * 32, lug + (long long)cur.x * 32, (unsigned)(cur.y >> 8) * 256u, &full_bar[slot]);
+                if (a0 + 32 + lane < a1)
+                    klu_bulk_g2s(dst + (ex.y & 0xff) * 32, lug + (long long)ex.x * 32, (unsigned)(ex.y >> 8) * 256u, &full_bar[slot]);
                 if (lane == 0) klu_bulk_g2s(dst + KLU_CHUNK_ROWS * 32, W.bentry + g * KLU_ENTRY_DOUBLES * 2, META_BYTES, &full_bar[slot]);
             }
             asm volatile("bar.sync 0;" ::: "memory");       // end of wave: the consumers stored (and fenced) the wave's columns
@@ -464,7 +264,7 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         if (dbg) tA = clock64();
         const int k0 = W.wave_col0[w], wc = W.wave_col0[w + 1] - k0;
         // team = the warps that share one column: 16 / (wc rounded up to a power of two) warps
-        const int tshift = tmode ? 0 : (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
+        const int tshift = (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
         const int T = 1 << tshift, col = warp >> tshift, sub = warp & (T - 1);
         const bool active = col < wc;
         const int k = k0 + (active ? col : 0);
@@ -476,13 +276,13 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         const int nb = (int)(W.wbatch_ptr[w + 1] - c0);
         auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
         // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
+        const int wrows = (int)(P.cbeg[k0 + wc] - P.cbeg[k0]);
         {
-            const int klast = k0 + wc - 1;
-            const int wrows = W.col_roff[klast] + (int)(P.cbeg[klast + 1] - P.cbeg[klast]);
             const int* rsrc = W.wave_rowsrc + (long long)w * KLU_WAVE_ROWS;
             for (int row = srow; row < wrows; row += 32) {
                 const int src = rsrc[row];
-                klu_cp_async16_zfill(xs + row * 32 + spc, src >= 0 ? axg + (long long)src * Bp + spc : axg, src >= 0 ? 16 : 0);
+                if (src >= 0) klu_cp_async16(xs + row * 32 + spc, axg + (long long)src * Bp + spc);
+                else *reinterpret_cast<double2*>(xs + row * 32 + spc) = make_double2(0.0, 0.0);      // fill-in slot
             }
             const long long bp0 = W.wblob_ptr[w];
             const int pieces = (int)(W.wblob_ptr[w + 1] - bp0);
@@ -495,7 +295,10 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         for (int c = 0; c < nb; c++) {
             const long long g = c0 + c;
             const int buf = (int)(g % KLU_STAGES);
+            long long q0 = 0;
+            if (dbg) q0 = clock64();
             klu_mbar_wait(&full_bar[buf], (unsigned)((g / KLU_STAGES) & 1));
+            if (dbg) { t_w += clock64() - q0; if (c == 0) t_w0 += clock64() - q0; }
             if (active) {
                 const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
                 const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
@@ -504,60 +307,37 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                 const int nseg = (int)rec[0];
                 // per matched segment: team barrier (the previous segment may have written u_jk or the same rows from
                 // another warp of the team), then the segment's rows are split over the team in chunks of four
-                if (tmode) {
-                    for (int sgi = 1; sgi <= nseg; sgi++) {
-                        const unsigned sd = rec[sgi];
-                        const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
-                        const double ujk = x[(sd >> 16) * 32];
-                        int t = r0;
-                        for (; t + 8 <= r1; t += 8) {
-                            int e[8]; double m[8], xv[8];
-#pragma unroll
-                            for (int q = 0; q < 8; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
-#pragma unroll
-                            for (int q = 0; q < 8; q++) xv[q] = x[e[q]];
-#pragma unroll
-                            for (int q = 0; q < 8; q++) x[e[q]] = xv[q] - m[q] * ujk;
-                        }
-                        if (t + 4 <= r1) {
-                            int e[4]; double m[4], xv[4];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) { e[q] = dd[t + q] * 32; m[q] = sb[(t + q) * 32]; }
-#pragma unroll
-                            for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) x[e[q]] = xv[q] - m[q] * ujk;
-                            t += 4;
-                        }
-                        for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;
-                    }
-                } else
                 for (int sgi = 1; sgi <= nseg; sgi++) {
                     const unsigned sd = rec[sgi];
                     const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
                     int t = r0 + 4 * sub;
-                    // operands of the first chunk are fetched before the team barrier (they do not depend on it)
-                    const bool first = t + 4 <= r1;
-                    int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-                    double l0v = 0, l1v = 0, l2v = 0, l3v = 0;
-                    if (first) {
-                        d0 = dd[t] * 32; d1 = dd[t + 1] * 32; d2 = dd[t + 2] * 32; d3 = dd[t + 3] * 32;
-                        l0v = sb[t * 32]; l1v = sb[(t + 1) * 32]; l2v = sb[(t + 2) * 32]; l3v = sb[(t + 3) * 32];
+                    // every chunk is four PREDICATED rows (a partial chunk costs one pass, not one dependent
+                    // load-update-store chain per row); the operands of the first chunk are fetched before the team
+                    // barrier (they do not depend on it)
+                    int e[4]; double m[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const bool on = t + q < r1;
+                        e[q] = on ? dd[t + q] * 32 : 0;
+                        m[q] = on ? sb[(t + q) * 32] : 0.0;
                     }
                     team_sync();
                     const double ujk = x[(sd >> 16) * 32];
-                    if (first) {
-                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
-                        x[d0] = x0 - l0v * ujk; x[d1] = x1 - l1v * ujk; x[d2] = x2 - l2v * ujk; x[d3] = x3 - l3v * ujk;
+                    for (;;) {
+                        double xv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (t + q < r1) x[e[q]] = xv[q] - m[q] * ujk;
                         t += 4 * T;
+                        if (t >= r1) break;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const bool on = t + q < r1;
+                            e[q] = on ? dd[t + q] * 32 : 0;
+                            m[q] = on ? sb[(t + q) * 32] : 0.0;
+                        }
                     }
-                    for (; t + 4 <= r1; t += 4 * T) {
-                        const int e0 = dd[t] * 32, e1 = dd[t + 1] * 32, e2 = dd[t + 2] * 32, e3 = dd[t + 3] * 32;
-                        const double m0 = sb[t * 32], m1 = sb[(t + 1) * 32], m2 = sb[(t + 2) * 32], m3 = sb[(t + 3) * 32];
-                        const double x0 = x[e0], x1 = x[e1], x2 = x[e2], x3 = x[e3];
-                        x[e0] = x0 - m0 * ujk; x[e1] = x1 - m1 * ujk; x[e2] = x2 - m2 * ujk; x[e3] = x3 - m3 * ujk;
-                    }
-                    for (; t < r1; t++) x[dd[t] * 32] -= sb[t * 32] * ujk;      // tail (< 4 rows) of the warp that owns it
                 }
             }
             __syncwarp();
@@ -585,22 +365,24 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                     const int cnt = (int)updl[4 * ui + 2];
                     const unsigned short* d = bdst + updl[4 * ui + 3];
                     const double* lsrc = xs + (w0 >> 8) * 32 + lane;
-                    int t = sub * 4;
-                    for (; t + 4 <= cnt; t += 4 * T) {
-                        const int d0 = d[t] * 32, d1 = d[t + 1] * 32, d2 = d[t + 2] * 32, d3 = d[t + 3] * 32;
-                        const double l0v = lsrc[t * 32], l1v = lsrc[(t + 1) * 32], l2v = lsrc[(t + 2) * 32], l3v = lsrc[(t + 3) * 32];
-                        const double x0 = x[d0], x1 = x[d1], x2 = x[d2], x3 = x[d3];
-                        x[d0] = x0 - l0v * uj; x[d1] = x1 - l1v * uj; x[d2] = x2 - l2v * uj; x[d3] = x3 - l3v * uj;
+                    for (int t = sub * 4; t < cnt; t += 4 * T) {
+                        int e[4]; double m[4], xv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const bool on = t + q < cnt;
+                            e[q] = on ? d[t + q] * 32 : 0;
+                            m[q] = on ? lsrc[(t + q) * 32] : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (t + q < cnt) x[e[q]] = xv[q] - m[q] * uj;
                     }
-                    for (; t < cnt; t++) x[d[t] * 32] -= lsrc[t * 32] * uj;     // tail (< 4 rows) of the warp that owns it
                     ui++;
                 }
                 if (ui == ue && k >= W.spine0) {
                     // column of the dense trailing block: only the updates from columns < spine0 were applied here;
                     // store it unfinished, k_klu_dense_lu factors the block
-                    team_sync();
-#pragma unroll 4
-                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
                     fin = true;
                     if (lane == 0 && sub == 0) done_round[col] = r;
                 } else if (ui == ue) {
@@ -611,9 +393,6 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                     const double rpiv = 1.0 / piv;    // one division per column; L(:,k) = x * (1/pivot)
 #pragma unroll 4
                     for (int sl = l0 + sub; sl < len; sl += T) x[sl * 32] *= rpiv;
-                    team_sync();
-#pragma unroll 4
-                    for (int sl = sub; sl < len; sl += T) lu[(long long)(cb + sl) * Bp] = x[sl * 32];
                     fin = true;
                     if (lane == 0 && sub == 0) done_round[col] = r;
                 }
@@ -627,12 +406,18 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
             }
         }
         if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; if (tid == 0 && blockIdx.x == 0) { dbg[8 + 2 * w] = t_init + t_p1; dbg[9 + 2 * w] = t_p2; } }
-        // the wave's columns are in global memory: make them visible to the producer's bulk (async-proxy) reads
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        asm volatile("bar.sync 0;" ::: "memory");
+        // the columns of a wave own consecutive slots and consecutive xs rows: ONE bulk store (TMA) writes the wave
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(lu + (long long)cb * 32),
+                         "r"((unsigned)__cvta_generic_to_shared(xs)), "r"((unsigned)wrows * 256u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        asm volatile("bar.sync 0;" ::: "memory");      // the producer may now read the wave's columns; xs is free
     }
-    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = dbg[5] = dbg[6] = 0; }
+    if (dbg && tid == 0 && blockIdx.x == 0) { dbg[0] = t_init; dbg[1] = t_p1; dbg[2] = t_p2; dbg[3] = n_rounds; dbg[4] = t_w; dbg[5] = t_w0; dbg[6] = 0; }
     if (bad) status[b] = ST_SINGULAR;
 }
 
@@ -707,7 +492,7 @@ __device__ __forceinline__ void klu_dense_strip(double* S, int lds, int c0, int 
 
 // LU[slot][matrix] (dir 0) -> D[matrix][entry] for the entries of the dense trailing block, and back (dir 1): 32 x 32
 // tiles through shared memory so both sides move full 256-byte rows
-__global__ void __launch_bounds__(256) k_klu_dense_pack(const int* __restrict__ dslot, int ndmap, int ndp, int Bp, double* __restrict__ LU,
+__global__ void __launch_bounds__(256) k_klu_dense_pack(const int* __restrict__ dslot, int ndmap, int ndp, long long gstride, double* __restrict__ LU,
                                                         double* __restrict__ D, int dir) {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -716,7 +501,7 @@ __global__ void __launch_bounds__(256) k_klu_dense_pack(const int* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int e = e0 + ty + 8 * i;
-            if (e < ndmap) tile[ty + 8 * i][tx] = LU[(long long)dslot[e] * Bp + b0 + tx];
+            if (e < ndmap) tile[ty + 8 * i][tx] = LU[(long long)(b0 >> 5) * gstride + (long long)dslot[e] * 32 + tx];
         }
         __syncthreads();
 #pragma unroll
@@ -730,7 +515,7 @@ __global__ void __launch_bounds__(256) k_klu_dense_pack(const int* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int e = e0 + ty + 8 * i;
-            if (e < ndmap) LU[(long long)dslot[e] * Bp + b0 + tx] = tile[ty + 8 * i][tx];
+            if (e < ndmap) LU[(long long)(b0 >> 5) * gstride + (long long)dslot[e] * 32 + tx] = tile[ty + 8 * i][tx];
         }
     }
 }
@@ -1028,7 +813,7 @@ __device__ __forceinline__ double klu_solve_terms(const int* __restrict__ tslot,
             for (int j = 0; j < KLU_SOLVE_PART; j++) {
                 const int sl = __shfl_sync(0xffffffffu, ps, (u + j) & 31), sr = __shfl_sync(0xffffffffu, pj, (u + j) & 31);
                 const bool on = u + j < cnt;
-                a[j] = on ? lu[(long long)sl * Bp] : 0.0;
+                a[j] = on ? lu[(long long)sl * 32] : 0.0;
                 x[j] = on ? v[(long long)sr * Bp] : 0.0;
             }
 #pragma unroll
@@ -1038,7 +823,7 @@ __device__ __forceinline__ double klu_solve_terms(const int* __restrict__ tslot,
     return s0 + s1;
 }
 
-__global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolveLvlD S, int Bp, const double* __restrict__ LU,
+__global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolveLvlD S, int Bp, long long gstride, const double* __restrict__ LU,
                                                                          double* __restrict__ V) {
     extern __shared__ double smd[];
     double* part = smd;                                            // [KLU_SOLVE_MAXPARTS][32] partial sums of a split level
@@ -1054,7 +839,7 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
     if (threadIdx.x == 0) lp[nlev + 1] = lp[nlev];
     __syncthreads();
     const int b = blockIdx.x * 32 + lane;
-    const double* lu = LU + b;
+    const double* lu = LU + (long long)blockIdx.x * gstride + lane;
     double* v = V + (long long)blockIdx.y * 2 * n * Bp + b;
     // static metadata of this warp's first part of a level is fetched one level ahead (rN..), under the previous level
     int4 r = make_int4(0, 0, 0, -1), rN = r;
@@ -1083,7 +868,7 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
                 const int t = r.x, i = (t < n) ? t : t - n;
                 const double y = v[(long long)i * Bp];
                 double dg = 1.0;
-                if (r.w >= 0) dg = lu[(long long)r.w * Bp];
+                if (r.w >= 0) dg = lu[(long long)r.w * 32];
                 double acc = y - klu_solve_terms(tslot, tsrc, r.y, r.z, ps, pj, mine, lane, lu, v, Bp);
                 if (r.w >= 0) acc /= dg;
                 v[(long long)t * Bp] = acc;
@@ -1098,7 +883,7 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
                 if (ex >= 0 && ht < 0) {       // first head of this warp: keep its operands in registers
                     const int i = (r.x < n) ? r.x : r.x - n;
                     y = v[(long long)i * Bp];
-                    if (r.w >= 0) dg = lu[(long long)r.w * Bp];
+                    if (r.w >= 0) dg = lu[(long long)r.w * 32];
                     ht = r.x; hq = q; hex = ex; hw = r.w;
                 }
                 part[(q - q0) * 32 + lane] = klu_solve_terms(tslot, tsrc, r.y, r.z, ps, pj, mine, lane, lu, v, Bp);
@@ -1115,7 +900,7 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
                     t = rr.x; w = rr.w;
                     const int i = (t < n) ? t : t - n;
                     y = v[(long long)i * Bp];
-                    dg = (w >= 0) ? lu[(long long)w * Bp] : 1.0;
+                    dg = (w >= 0) ? lu[(long long)w * 32] : 1.0;
                 }
                 double ssum = 0.0;
                 for (int k = 0; k <= e; k++) ssum += part[(q - q0 + k) * 32 + lane];
@@ -1131,7 +916,7 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
 
 __global__ void k_klu_gather_slots(const double* __restrict__ LU, int Bp, int b, long long nslots, double* __restrict__ out) {
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nslots; v += (long long)gridDim.x * blockDim.x)
-        out[v] = LU[v * Bp + b];
+        out[v] = LU[(long long)(b >> 5) * nslots * 32 + v * 32 + (b & 31)];
 }
 
 class KluDevice {
@@ -1153,6 +938,15 @@ public:
     int spine_nd = 0, ndmap = 0, ndp = 0;
     size_t dense_smem = 0;
     std::vector<int> h_wave_col0;
+    // pipelined host-buffer path (refactor_begin / refactor_end)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_free[2] = {}, ev_done[2] = {};
+    double* dAp[2] = {nullptr, nullptr};
+    long long capAp[2] = {0, 0}, pend_batch[2] = {0, 0};
+    int* h_status_pinned[2] = {nullptr, nullptr};
+    std::vector<int> h_status[2];
+    bool buf_used[2] = {false, false};
+    int npending = 0, next_buf = 0;
     long long* ddbg = nullptr;     // optional phase timers of the wave kernel (B200S_KLU_DEBUG=1)
     long long* d_rowptr = nullptr;
     long long nslots = 0, nnzA = 0;
@@ -1169,6 +963,14 @@ public:
         for (void* p : owned) cudaFree(p);
         cudaFree(dA); cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(dX); cudaFree(dB); cudaFree(d_status); cudaFree(dD);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (int q = 0; q < 2; q++) {
+            cudaFree(dAp[q]);
+            if (h_status_pinned[q]) cudaFreeHost(h_status_pinned[q]);
+            if (ev_h2d[q]) cudaEventDestroy(ev_h2d[q]);
+            if (ev_free[q]) cudaEventDestroy(ev_free[q]);
+            if (ev_done[q]) cudaEventDestroy(ev_done[q]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
     template <class T> int up(const T** dst, const std::vector<T>& src) {
@@ -1181,7 +983,10 @@ public:
     }
     int init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S);
     int ensure_batch(int b);
+    int enqueue_refactor(const double* dv, long long ldv, cudaEvent_t after_transpose);
     int refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host);
+    int refactor_begin(const double* vals, long long batch_, long long ldv);
+    int refactor_end(int* status_host);
     int solve(int trans, double* B, long long nrhs, long long ldB, long long batch_, bool on_device);
 };
 
@@ -1192,7 +997,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     n = P.n; nslots = P.nslots; nnzA = P.nnzA;
     if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(cudaMalloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; }
     int rc;
-    PD.n = P.n; PD.nlevels = P.nlevels;
+    PD.n = P.n; PD.nlevels = P.nlevels; PD.gstride = (long long)P.nslots * 32;
     std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
         updd(P.upd_dest.begin(), P.upd_dest.end()), rowptr(P.rowptr.begin(), P.rowptr.end());
     if ((rc = up(&PD.level_ptr, P.level_ptr))) return rc;
@@ -1216,6 +1021,15 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         if ((rc = up(&WD.wblob_ptr, wlp))) return rc;
         if ((rc = up(&WD.batch_rowslot, P.batch_rowslot))) return rc;
         if ((rc = up(&WD.wave_rowsrc, P.wave_rowsrc))) return rc;
+        {
+            std::vector<int> bsp(P.bseg_ptr.begin(), P.bseg_ptr.end());
+            std::vector<int2> sgd(P.seg_src.size());
+            for (size_t q = 0; q < sgd.size(); q++)
+                sgd[q] = make_int2(P.lslot0[P.seg_src[q]] + P.seg_off[q], P.seg_row[q] | (P.seg_cnt[q] << 8));
+            bsp.push_back(bsp.back());       // the producer reads bseg_ptr[g + 2] one batch ahead
+            if ((rc = up(&WD.bseg_ptr, bsp))) return rc;
+            if ((rc = up(&WD.segd, sgd))) return rc;
+        }
         std::vector<unsigned> be(P.bentry.begin(), P.bentry.end()), wb(P.wblob.begin(), P.wblob.end());
         if ((rc = up(&WD.bentry, be))) return rc;
         if ((rc = up(&WD.wblob, wb))) return rc;
@@ -1239,7 +1053,6 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         if (use_wave)
         {
             CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
-            CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
         }
     }
     const int* tmp_i; const long long* tmp_l;
@@ -1277,6 +1090,43 @@ int KluDevice::ensure_batch(int b) {
     return ST_OK;
 }
 
+// the kernels of one refactorization, enqueued on `stream`; dv = device copy of the caller's [batch][ldv] values
+int KluDevice::enqueue_refactor(const double* dv, long long ldv, cudaEvent_t after_transpose) {
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, Bp * sizeof(int), stream));
+    {
+        dim3 grid((unsigned)((nnzA + 31) / 32), (unsigned)(Bp / 32)), block(32, 8);
+        k_klu_transpose<<<grid, block, 0, stream>>>(dv, ldv, nnzA, batch, Bp, dAxt);
+    }
+    if (after_transpose) CUDA_TRY(cudaEventRecord(after_transpose, stream));       // the caller's value buffer is free again
+    k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs);
+    if (use_wave) {
+        k_klu_prescale<<<148 * 16, 256, 0, stream>>>(d_ent_row, nnzA, Bp, dRs, dAxt);
+        // only the off-diagonal-block entries F need a separate scatter; L/U columns are gathered inside the kernel
+        if (nslots > lu_slots)
+            k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1, nslots * 32);
+        CUDA_TRY(cudaEventRecord(ev[4], stream));
+        k_klu_refactor_wave<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
+        CUDA_TRY(cudaEventRecord(ev[6], stream));
+        launches = 4 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
+        if (spine_nd > 0) {
+            const dim3 tg(ndp / 32, Bp / 32);
+            k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, nslots * 32, dLU, dD, 0);
+            k_klu_dense_lu<<<batch, KLU_DENSE_THREADS, dense_smem, stream>>>(spine_nd, d_dense_meta, ndp, batch, dD, d_status);
+            k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, nslots * 32, dLU, dD, 1);
+        }
+        CUDA_TRY(cudaEventRecord(ev[5], stream));
+    } else {
+        k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, 0, nslots, Bp, dAxt, dRs, dLU, 0, nslots * 32);
+        CUDA_TRY(cudaEventRecord(ev[4], stream));
+        k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, nslots * 32, dLU, d_status);
+        CUDA_TRY(cudaEventRecord(ev[6], stream));
+        CUDA_TRY(cudaEventRecord(ev[5], stream));
+        launches = 4;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ST_OK;
+}
+
 int KluDevice::refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host) {
     CUDA_TRY(cudaSetDevice(device));
     if (batch_ <= 0 || n == 0) return ST_OK;
@@ -1295,39 +1145,7 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
         dv = dA;
     }
     CUDA_TRY(cudaEventRecord(ev[1], stream));
-    CUDA_TRY(cudaMemsetAsync(d_status, 0, Bp * sizeof(int), stream));
-    {
-        dim3 grid((unsigned)((nnzA + 31) / 32), (unsigned)(Bp / 32)), block(32, 8);
-        k_klu_transpose<<<grid, block, 0, stream>>>(dv, ldv, nnzA, batch, Bp, dAxt);
-    }
-    k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs);
-    if (use_wave) {
-        k_klu_prescale<<<148 * 16, 256, 0, stream>>>(d_ent_row, nnzA, Bp, dRs, dAxt);
-        // only the off-diagonal-block entries F need a separate scatter; L/U columns are gathered inside the kernel
-        if (nslots > lu_slots)
-            k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1);
-        CUDA_TRY(cudaEventRecord(ev[4], stream));
-        if (!getenv("B200S_KLU_TMA"))
-            k_klu_refactor_wave<<<Bp / 32, KLU_WAVE_WARPS * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg, getenv("B200S_KLU_T1") ? 1 : 0);
-        else
-            k_klu_refactor_wave_tma<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg, getenv("B200S_KLU_T1") ? 1 : 0);
-        CUDA_TRY(cudaEventRecord(ev[6], stream));
-        launches = 4 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
-        if (spine_nd > 0) {
-            const dim3 tg(ndp / 32, Bp / 32);
-            k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, Bp, dLU, dD, 0);
-            k_klu_dense_lu<<<batch, KLU_DENSE_THREADS, dense_smem, stream>>>(spine_nd, d_dense_meta, ndp, batch, dD, d_status);
-            k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, Bp, dLU, dD, 1);
-        }
-        CUDA_TRY(cudaEventRecord(ev[5], stream));
-    } else {
-        k_klu_scatter<<<148 * 16, 256, 0, stream>>>(d_slot_src, d_slot_row, 0, nslots, Bp, dAxt, dRs, dLU, 0);
-        CUDA_TRY(cudaEventRecord(ev[4], stream));
-        k_klu_refactor<<<Bp / 32, KLU_WARPS * 32, 0, stream>>>(PD, Bp, dLU, d_status);
-        CUDA_TRY(cudaEventRecord(ev[6], stream));
-        CUDA_TRY(cudaEventRecord(ev[5], stream));
-        launches = 4;
-    }
+    if ((rc = enqueue_refactor(dv, ldv, nullptr))) return rc;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[2], stream));
     std::vector<int> st;
@@ -1340,7 +1158,7 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     if (ddbg) {
         long long h[8] = {0};
         cudaMemcpy(h, ddbg, sizeof h, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld) | warp0 p1: wait_group %lld barrier %lld issue %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+        fprintf(stderr, "[klu wave kernel, CTA 0] cycles: gather+prologue %lld  staged-updates %lld  in-wave rounds %lld  (rounds %lld) | warp0 waits for staged data %lld (first batch of a wave %lld)\n", h[0], h[1], h[2], h[3], h[4], h[5]);
         if (const char* f = getenv("B200S_KLU_DEBUG_FILE")) {
             std::vector<long long> hw(8 + 2 * (size_t)WD.nwaves);
             cudaMemcpy(hw.data(), ddbg, hw.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1355,6 +1173,63 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_refactor = ms;
     cudaEventElapsedTime(&ms, ev[4], ev[6]); ms_kernel = ms;
     cudaEventElapsedTime(&ms, ev[6], ev[5]); ms_dense = ms;
+    return ST_OK;
+}
+
+// Pipelined host-buffer refactorization: begin() enqueues the H2D copy on a copy stream and the kernels on the compute
+// stream and returns; end() waits for the oldest batch in flight.  With two batches in flight the upload of batch i+1
+// overlaps the kernels of batch i (two device staging buffers; a staging buffer is free again as soon as the transpose
+// kernel has consumed it).
+int KluDevice::refactor_begin(const double* vals, long long batch_, long long ldv) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (batch_ <= 0 || n == 0) return ST_OK;
+    if (npending >= 2) { set_last_error("refactor_batch_begin: two batches already in flight, call refactor_batch_end first"); return ST_INVALID; }
+    const int bp = ((int)batch_ + 31) & ~31;
+    if (npending > 0 && bp > Bp) { set_last_error("refactor_batch_begin: a larger batch needs the batches in flight to finish first"); return ST_INVALID; }
+    int rc = ensure_batch((int)batch_);
+    if (rc) return rc;
+    if (!copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; q++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_h2d[q], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_free[q], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_done[q], cudaEventDisableTiming));
+        }
+    }
+    const int q = next_buf;
+    const long long need = (batch_ - 1) * ldv + nnzA;
+    if (need > capAp[q]) {
+        if (buf_used[q]) CUDA_TRY(cudaEventSynchronize(ev_free[q]));
+        cudaFree(dAp[q]); dAp[q] = nullptr; capAp[q] = 0;
+        CUDA_TRY(cudaMalloc((void**)&dAp[q], need * sizeof(double)));
+        capAp[q] = need;
+    }
+    if ((long long)h_status[q].size() < Bp) {
+        if (h_status_pinned[q]) cudaFreeHost(h_status_pinned[q]);
+        CUDA_TRY(cudaMallocHost((void**)&h_status_pinned[q], Bp * sizeof(int)));
+        h_status[q].resize(Bp);
+    }
+    if (buf_used[q]) CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_free[q], 0));
+    CUDA_TRY(cudaMemcpyAsync(dAp[q], vals, need * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+    CUDA_TRY(cudaEventRecord(ev_h2d[q], copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_h2d[q], 0));
+    if ((rc = enqueue_refactor(dAp[q], ldv, ev_free[q]))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_status_pinned[q], d_status, Bp * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(ev_done[q], stream));
+    buf_used[q] = true;
+    pend_batch[q] = batch_;
+    npending++;
+    next_buf ^= 1;
+    return ST_OK;
+}
+
+int KluDevice::refactor_end(int* status_host) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (npending == 0) return ST_OK;
+    const int q = (npending == 2) ? next_buf : (next_buf ^ 1);     // the oldest batch in flight
+    CUDA_TRY(cudaEventSynchronize(ev_done[q]));
+    if (status_host) for (long long b = 0; b < pend_batch[q]; b++) status_host[b] = h_status_pinned[q][b];
+    npending--;
     return ST_OK;
 }
 
@@ -1390,7 +1265,7 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
         const size_t sm = (size_t)KLU_SOLVE_MAXPARTS * 32 * sizeof(double) + (size_t)(2 * L_.nlev + 4) * sizeof(int);
         if (sm > 220 * 1024) { set_last_error("klu solve: too many levels"); return ST_TOO_LARGE; }
         if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_klu_solve_lvl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_klu_solve_lvl<<<dim3((unsigned)(Bp / 32), (unsigned)nrhs), KLU_SOLVE_WARPS * 32, sm, stream>>>(L_, Bp, dLU, dX);
+        k_klu_solve_lvl<<<dim3((unsigned)(Bp / 32), (unsigned)nrhs), KLU_SOLVE_WARPS * 32, sm, stream>>>(L_, Bp, nslots * 32, dLU, dX);
         k_klu_solve_store<<<tg, 256, 0, stream>>>(n, nb, Bp, trans ? d_Pnum : d_Q, trans ? dRs : nullptr, db, ldB, bstride, dX);
     }
     CUDA_TRY(cudaGetLastError());
@@ -1415,6 +1290,8 @@ void klu_device_destroy(KluDevice* d) { delete d; }
 int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status) {
     return d->refactor(vals, on_device, batch, ldv, status);
 }
+int klu_device_refactor_begin(KluDevice* d, const double* vals, long long batch, long long ldv) { return d->refactor_begin(vals, batch, ldv); }
+int klu_device_refactor_end(KluDevice* d, int* status) { return d->refactor_end(status); }
 int klu_device_solve(KluDevice* d, int trans, double* B, long long nrhs, long long ldB, long long batch, bool on_device) {
     return d->solve(trans, B, nrhs, ldB, batch, on_device);
 }

@@ -262,6 +262,43 @@ def refactor_batch(Fn, values, check=True):
     return status
 
 
+def refactor_batch_begin(Fn, values):
+    """Pipelined form of refactor_batch: enqueue the upload of `values` (float64, shape (batch, nnz), C-contiguous,
+    ideally pinned host memory; keep it alive and unmodified until the matching refactor_batch_end) and the
+    refactorization kernels, and return at once.  Up to two batches may be in flight; the upload of the second
+    overlaps the kernels of the first."""
+    hn = _capsule_ptr(Fn, _NAME_NUM, "F is not the KLU numeric factor of a 'd' matrix", "F")
+    if not isinstance(values, np.ndarray) or values.dtype != np.float64 or values.ndim != 2 or not values.flags.c_contiguous:
+        raise TypeError("values must be a C-contiguous float64 array of shape (batch, nnz)")
+    inf = L.KluInfo()
+    fn["b200s_klu_info"](hn, C.byref(inf))
+    if values.shape[1] != inf.nnz_A:
+        raise ValueError("values must have nnz(A) = %d columns" % inf.nnz_A)
+    st = fn["b200s_klu_refactor_batch_begin"](hn, L.ptr_f64(values), values.shape[0], values.shape[1])
+    if st != L.OK:
+        _raise_status(st)
+    _pending.setdefault(hn.value if hasattr(hn, "value") else int(hn), []).append(values.shape[0])
+
+
+def refactor_batch_end(Fn, check=True):
+    """Wait for the oldest batch begun with refactor_batch_begin; returns its per-matrix status array."""
+    hn = _capsule_ptr(Fn, _NAME_NUM, "F is not the KLU numeric factor of a 'd' matrix", "F")
+    q = _pending.get(hn.value if hasattr(hn, "value") else int(hn), [])
+    if not q:
+        raise ValueError("no batch in flight")
+    batch = q.pop(0)
+    status = np.zeros(batch, dtype=np.int32)
+    st = fn["b200s_klu_refactor_batch_end"](hn, status.ctypes.data_as(L.p_int))
+    if st != L.OK:
+        _raise_status(st)
+    if check and status.any():
+        raise ArithmeticError("singular matrix")
+    return status
+
+
+_pending = {}
+
+
 def solve_batch(Fn, B, trans="N"):
     """Solve with every matrix of the last refactored batch.  B: float64 array (batch, nrhs, n) or
     (batch, n), overwritten in place (must be C-contiguous)."""

@@ -128,3 +128,37 @@ def test_batched_refactor_vs_oracle(klu, name, batch):
     assert st[3] != 0 and st[:3].sum() == 0 and st[4:].sum() == 0
     with pytest.raises(ArithmeticError):
         klu.refactor_batch(Fn, vals2)
+
+
+def test_pipelined_refactor_matches_synchronous_call(klu):
+    """refactor_batch_begin / refactor_batch_end (two batches in flight) leave the same factors and status as the
+    synchronous refactor_batch, in order, also with a singular matrix in one of the batches."""
+    A = load_matrix("bp_800")
+    Fs = klu.symbolic(A)
+    Fn = klu.numeric(A, Fs)
+    rng = np.random.default_rng(11)
+    n = A.shape[0]
+    batches = [np.ascontiguousarray(A.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(bsz, A.nnz)))) for bsz in (70, 33, 70)]
+    batches[1][5, :] = 0.0                       # singular matrix in the middle batch
+    B = rng.standard_normal((70, 1, n))
+    ref = []
+    for v in batches:
+        st = klu.refactor_batch(Fn, v, check=False)
+        X = B[:v.shape[0]].copy()
+        klu.solve_batch(Fn, X)
+        ref.append((st.copy(), X))
+    assert ref[1][0][5] != 0 and not ref[0][0].any()
+    klu.refactor_batch_begin(Fn, batches[0])
+    klu.refactor_batch_begin(Fn, batches[1])
+    with pytest.raises(ValueError):
+        klu.refactor_batch_begin(Fn, batches[2])           # at most two in flight
+    st0 = klu.refactor_batch_end(Fn, check=False)
+    st1 = klu.refactor_batch_end(Fn, check=False)
+    assert (st0 == ref[0][0]).all() and (st1 == ref[1][0]).all()
+    klu.refactor_batch_begin(Fn, batches[2])
+    st2 = klu.refactor_batch_end(Fn)
+    X = B.copy()
+    klu.solve_batch(Fn, X)                                 # factors of the most recently begun batch
+    assert (st2 == ref[2][0]).all() and np.array_equal(X, ref[2][1])
+    with pytest.raises(ValueError):
+        klu.refactor_batch_end(Fn)
