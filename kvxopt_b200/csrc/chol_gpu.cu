@@ -17,6 +17,7 @@
 //                 operands staged by a 4-stage cp.async pipeline; used for the in-panel trailing update
 //                 (K = 128) and for the Schur complement (K = nc).
 #include "gpu.hpp"
+#include "devpool.hpp"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
@@ -1141,11 +1142,13 @@ public:
 
     ~CholDevice() {
         cudaSetDevice(device);
+        if (stream2) cudaStreamSynchronize(stream2);
+        if (stream) cudaStreamSynchronize(stream);      // blocks go back to the caching allocator: nothing may still use them
         drop_graphs();
-        cudaFree(dL); cudaFree(dW); cudaFree(dval); cudaFree(dT); cudaFree(dX); cudaFree(dBstage); cudaFree(damap); cudaFree(dF);
-        cudaFree(drows); cudaFree(drel); cudaFree(dchild); cudaFree(dperm); cudaFree(dlevel_fronts);
-        cudaFree(dsched); cudaFree(dminor); cudaFree(dea); cudaFree(ddiag); cudaFree(dpart); cudaFree(downed);
-        cudaFree(dMinv); cudaFree(dinv_front); cudaFree(dinv_kb);
+        pool_free(dL); pool_free(dW); pool_free(dval); pool_free(dT); pool_free(dX); pool_free(dBstage); pool_free(damap); pool_free(dF);
+        pool_free(drows); pool_free(drel); pool_free(dchild); pool_free(dperm); pool_free(dlevel_fronts);
+        pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(ddiag); pool_free(dpart); pool_free(downed);
+        pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -1155,7 +1158,7 @@ public:
     }
     template <class T> int upload(T** dst, const T* src, size_t count) {
         size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-        CUDA_TRY(cudaMalloc((void**)dst, bytes));
+        CUDA_TRY(pool_malloc((void**)dst, bytes));
         total_bytes += bytes;
         if (count) CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
         return ST_OK;
@@ -1224,13 +1227,13 @@ int CholDevice::init() {
         if ((rc = upload(&damap, am.data(), am.size()))) return rc;
     }
     lap("plan upload");
-    CUDA_TRY(cudaMalloc((void**)&dL, std::max<i64>(P.lsize, 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&dW, std::max<i64>(P.wsize, 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&dval, std::max<i64>(P.nnzA, 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&dminor, sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&dMinv, std::max<size_t>((size_t)ninvblk * MINV_BLK, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dL, std::max<i64>(P.lsize, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dW, std::max<i64>(P.wsize, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dval, std::max<i64>(P.nnzA, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dminor, sizeof(int)));
+    CUDA_TRY(pool_malloc((void**)&dMinv, std::max<size_t>((size_t)ninvblk * MINV_BLK, 1) * sizeof(double)));
     total_bytes += (i64)ninvblk * MINV_BLK * sizeof(double);
-    CUDA_TRY(cudaMalloc((void**)&downed, std::max<size_t>(hf.size(), 1)));
+    CUDA_TRY(pool_malloc((void**)&downed, std::max<size_t>(hf.size(), 1)));
     CUDA_TRY(cudaMemset(downed, 1, std::max<size_t>(hf.size(), 1)));
     total_bytes += (P.lsize + P.wsize + P.nnzA) * sizeof(double);
 
@@ -1397,7 +1400,7 @@ int CholDevice::init() {
     {
         int maxng = 1;
         for (auto& LS : levels) for (auto& la : LS.panel) maxng = std::max(maxng, la.ng);
-        CUDA_TRY(cudaMalloc((void**)&ddiag, (size_t)maxng * NB * NB * sizeof(double)));
+        CUDA_TRY(pool_malloc((void**)&ddiag, (size_t)maxng * NB * NB * sizeof(double)));
         total_bytes += (size_t)maxng * NB * NB * sizeof(double);
     }
     lap("schedule build");
@@ -1586,12 +1589,12 @@ int CholDevice::set_owned(const unsigned char* owned_host) {
 int CholDevice::ensure_solve_ws(i64 cols) {
     if (cols <= solve_cols) return ST_OK;
     drop_graphs();                 // the captured sweeps hold the old workspace pointers
-    cudaFree(dT); cudaFree(dX); dT = dX = nullptr; solve_cols = 0;
+    pool_free(dT); pool_free(dX); dT = dX = nullptr; solve_cols = 0;
     const CholPlan& P = *plan;
-    CUDA_TRY(cudaMalloc((void**)&dT, std::max<i64>((i64)P.rows.size() * cols, 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&dX, std::max<i64>((i64)P.n * cols, 1) * sizeof(double)));
-    cudaFree(dpart); dpart = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&dpart, (size_t)max_solve_ctas * NB * cols * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dT, std::max<i64>((i64)P.rows.size() * cols, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dX, std::max<i64>((i64)P.n * cols, 1) * sizeof(double)));
+    pool_free(dpart); dpart = nullptr;
+    CUDA_TRY(pool_malloc((void**)&dpart, (size_t)max_solve_ctas * NB * cols * sizeof(double)));
     solve_cols = cols;
     return ST_OK;
 }
@@ -1614,8 +1617,8 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     double* dB = B;
     if (!on_device) {
         if ((i64)n * nrhs > bstage_cap) {
-            cudaFree(dBstage); dBstage = nullptr; bstage_cap = 0;
-            CUDA_TRY(cudaMalloc((void**)&dBstage, (size_t)n * nrhs * sizeof(double)));
+            pool_free(dBstage); dBstage = nullptr; bstage_cap = 0;
+            CUDA_TRY(pool_malloc((void**)&dBstage, (size_t)n * nrhs * sizeof(double)));
             bstage_cap = (i64)n * nrhs;
         }
         CUDA_TRY(cudaMemcpy2DAsync(dBstage, (size_t)n * 8, B, (size_t)ldB * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, stream));

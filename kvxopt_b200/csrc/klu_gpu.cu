@@ -15,6 +15,7 @@
 // Kernels: k_klu_transpose (tiled), k_klu_rowscale, k_klu_scatter, k_klu_refactor (one CTA per group of
 // 32 matrices walks the column level schedule, 16 warps share the columns of a level), k_klu_solve.
 #include "gpu.hpp"
+#include "devpool.hpp"
 #include "klu_host.hpp"
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -960,11 +961,13 @@ public:
 
     ~KluDevice() {
         cudaSetDevice(device);
-        for (void* p : owned) cudaFree(p);
-        cudaFree(dA); cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(dX); cudaFree(dB); cudaFree(d_status); cudaFree(dD);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (stream) cudaStreamSynchronize(stream);      // blocks go back to the caching allocator
+        for (void* p : owned) pool_free(p);
+        pool_free(dA); pool_free(dAxt); pool_free(dRs); pool_free(dLU); pool_free(dX); pool_free(dB); pool_free(d_status); pool_free(dD);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (int q = 0; q < 2; q++) {
-            cudaFree(dAp[q]);
+            pool_free(dAp[q]);
             if (h_status_pinned[q]) cudaFreeHost(h_status_pinned[q]);
             if (ev_h2d[q]) cudaEventDestroy(ev_h2d[q]);
             if (ev_free[q]) cudaEventDestroy(ev_free[q]);
@@ -975,7 +978,7 @@ public:
     }
     template <class T> int up(const T** dst, const std::vector<T>& src) {
         T* p = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&p, std::max<size_t>(src.size(), 1) * sizeof(T)));
+        CUDA_TRY(pool_malloc((void**)&p, std::max<size_t>(src.size(), 1) * sizeof(T)));
         owned.push_back(p);
         if (!src.empty()) CUDA_TRY(cudaMemcpy(p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
         *dst = p;
@@ -995,7 +998,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     n = P.n; nslots = P.nslots; nnzA = P.nnzA;
-    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(cudaMalloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; }
+    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(pool_malloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; }
     int rc;
     PD.n = P.n; PD.nlevels = P.nlevels; PD.gstride = (long long)P.nslots * 32;
     std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
@@ -1079,13 +1082,13 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
 int KluDevice::ensure_batch(int b) {
     const int bp = (b + 31) & ~31;
     if (bp <= Bp) { batch = b; return ST_OK; }
-    cudaFree(dAxt); cudaFree(dRs); cudaFree(dLU); cudaFree(d_status); cudaFree(dD);
+    pool_free(dAxt); pool_free(dRs); pool_free(dLU); pool_free(d_status); pool_free(dD);
     dAxt = dRs = dLU = dD = nullptr; d_status = nullptr; Bp = 0;
-    CUDA_TRY(cudaMalloc((void**)&dAxt, std::max<long long>(nnzA, 1) * bp * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&dRs, std::max<long long>(n, 1) * (long long)bp * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&dLU, std::max<long long>(nslots, 1) * bp * sizeof(double)));
-    if (spine_nd > 0) CUDA_TRY(cudaMalloc((void**)&dD, (size_t)ndp * bp * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&d_status, bp * sizeof(int)));
+    CUDA_TRY(pool_malloc((void**)&dAxt, std::max<long long>(nnzA, 1) * bp * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dRs, std::max<long long>(n, 1) * (long long)bp * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&dLU, std::max<long long>(nslots, 1) * bp * sizeof(double)));
+    if (spine_nd > 0) CUDA_TRY(pool_malloc((void**)&dD, (size_t)ndp * bp * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&d_status, bp * sizeof(int)));
     Bp = bp; batch = b;
     return ST_OK;
 }
@@ -1137,8 +1140,8 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     if (!on_device) {
         const long long need = (batch_ - 1) * ldv + nnzA;
         if (need > capA) {
-            cudaFree(dA); dA = nullptr; capA = 0;
-            CUDA_TRY(cudaMalloc((void**)&dA, need * sizeof(double)));
+            pool_free(dA); dA = nullptr; capA = 0;
+            CUDA_TRY(pool_malloc((void**)&dA, need * sizeof(double)));
             capA = need;
         }
         CUDA_TRY(cudaMemcpyAsync(dA, vals, need * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -1200,8 +1203,8 @@ int KluDevice::refactor_begin(const double* vals, long long batch_, long long ld
     const long long need = (batch_ - 1) * ldv + nnzA;
     if (need > capAp[q]) {
         if (buf_used[q]) CUDA_TRY(cudaEventSynchronize(ev_free[q]));
-        cudaFree(dAp[q]); dAp[q] = nullptr; capAp[q] = 0;
-        CUDA_TRY(cudaMalloc((void**)&dAp[q], need * sizeof(double)));
+        pool_free(dAp[q]); dAp[q] = nullptr; capAp[q] = 0;
+        CUDA_TRY(pool_malloc((void**)&dAp[q], need * sizeof(double)));
         capAp[q] = need;
     }
     if ((long long)h_status[q].size() < Bp) {
@@ -1240,8 +1243,8 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
     const long long bstride = ldB * nrhs;
     const long long needX = 2ll * n * Bp * nrhs;      // V = [Y; Z] per right-hand side
     if (needX > capX) {
-        cudaFree(dX); dX = nullptr; capX = 0;
-        CUDA_TRY(cudaMalloc((void**)&dX, needX * sizeof(double)));
+        pool_free(dX); dX = nullptr; capX = 0;
+        CUDA_TRY(pool_malloc((void**)&dX, needX * sizeof(double)));
         capX = needX;
     }
     CUDA_TRY(cudaEventRecord(ev[0], stream));
@@ -1249,8 +1252,8 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
     const long long totalB = bstride * batch_;
     if (!on_device) {
         if (totalB > capB) {
-            cudaFree(dB); dB = nullptr; capB = 0;
-            CUDA_TRY(cudaMalloc((void**)&dB, totalB * sizeof(double)));
+            pool_free(dB); dB = nullptr; capB = 0;
+            CUDA_TRY(pool_malloc((void**)&dB, totalB * sizeof(double)));
             capB = totalB;
         }
         CUDA_TRY(cudaMemcpyAsync(dB, B, totalB * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -1300,7 +1303,7 @@ int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs
     if (b < 0 || b >= d->batch) { set_last_error("extract_batch: matrix index out of range"); return ST_INVALID; }
     double* tmp = nullptr;
     const long long cnt = std::max<long long>(d->nslots, d->n);
-    CUDA_TRY(cudaMalloc((void**)&tmp, std::max<long long>(cnt, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&tmp, std::max<long long>(cnt, 1) * sizeof(double)));
     k_klu_gather_slots<<<148 * 4, 256, 0, d->stream>>>(d->dLU, d->Bp, (int)b, d->nslots, tmp);
     cudaError_t e = cudaMemcpyAsync(slots_host, tmp, d->nslots * sizeof(double), cudaMemcpyDeviceToHost, d->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
@@ -1309,7 +1312,7 @@ int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs
         e = cudaMemcpyAsync(rs_host, tmp, d->n * sizeof(double), cudaMemcpyDeviceToHost, d->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
     }
-    cudaFree(tmp);
+    pool_free(tmp);
     CUDA_TRY(e);
     return ST_OK;
 }
