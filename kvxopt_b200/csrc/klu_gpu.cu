@@ -261,37 +261,64 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         }
         return;
     }
+    // Per-wave parameters and the row -> input-entry table of the NEXT wave are fetched while the current wave runs
+    // (part 1 right after the gather is issued, the dependent part 2 after the staged phase), so that a wave starts
+    // without a chain of dependent global loads.
+    __shared__ int rs_tab[KLU_WAVE_ROWS];
+    int n_k0 = W.wave_col0[0], n_wc = W.wave_col0[1] - n_k0;
+    long long n_c0 = W.wbatch_ptr[0], n_bp0 = W.wblob_ptr[0];
+    int n_nb = (int)(W.wbatch_ptr[1] - n_c0), n_pieces = (int)(W.wblob_ptr[1] - n_bp0);
+    int n_cb = 0, n_len = 0, n_roff = 0, n_diag = 0, n_l0 = 0, n_wrows = 0;
+    auto team_size = [](int wc) { return wc <= 8 ? KLU_WAVE_WARPS / wc : 1; };      // warps per column (any size, not only 2^k)
+    auto load_part2 = [&]() {
+        const int c = warp / team_size(n_wc);
+        const int k = n_k0 + (c < n_wc ? c : 0);
+        n_cb = (int)P.cbeg[k];
+        n_len = (int)P.cbeg[k + 1] - n_cb;
+        n_roff = W.col_roff[k];
+        n_diag = P.udiag_slot[k] - n_cb;
+        n_l0 = P.lslot0[k] - n_cb;
+        n_wrows = (int)(P.cbeg[n_k0 + n_wc] - P.cbeg[n_k0]);
+    };
+    load_part2();
+    if (tid < KLU_WAVE_ROWS) rs_tab[tid] = W.wave_rowsrc[tid];
+    asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
     for (int w = 0; w < W.nwaves; w++) {
         if (dbg) tA = clock64();
-        const int k0 = W.wave_col0[w], wc = W.wave_col0[w + 1] - k0;
-        // team = the warps that share one column: 16 / (wc rounded up to a power of two) warps
-        const int tshift = (wc <= 1) ? 4 : (wc <= 2) ? 3 : (wc <= 4) ? 2 : (wc <= 8) ? 1 : 0;
-        const int T = 1 << tshift, col = warp >> tshift, sub = warp & (T - 1);
+        const int k0 = n_k0, wc = n_wc;
+        // team = the warps that share one column: floor(16 / wc) warps
+        const int T = team_size(wc), col = warp / T, sub = warp - col * T;
         const bool active = col < wc;
         const int k = k0 + (active ? col : 0);
-        const int cb = (int)P.cbeg[k];
-        const int len = (int)P.cbeg[k + 1] - cb;
-        double* x = xs + W.col_roff[k] * 32 + lane;
-        const int diag = P.udiag_slot[k] - cb, l0 = P.lslot0[k] - cb;
-        const long long c0 = W.wbatch_ptr[w];
-        const int nb = (int)(W.wbatch_ptr[w + 1] - c0);
+        const int cb = n_cb, len = n_len;
+        double* x = xs + n_roff * 32 + lane;
+        const int diag = n_diag, l0 = n_l0;
+        const long long c0 = n_c0;
+        const int nb = n_nb;
         auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
         // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
-        const int wrows = (int)(P.cbeg[k0 + wc] - P.cbeg[k0]);
+        const int wrows = n_wrows;
+        int rs_next = -1;
         {
-            const int* rsrc = W.wave_rowsrc + (long long)w * KLU_WAVE_ROWS;
             for (int row = srow; row < wrows; row += 32) {
-                const int src = rsrc[row];
+                const int src = rs_tab[row];
                 if (src >= 0) klu_cp_async16(xs + row * 32 + spc, axg + (long long)src * Bp + spc);
                 else *reinterpret_cast<double2*>(xs + row * 32 + spc) = make_double2(0.0, 0.0);      // fill-in slot
             }
-            const long long bp0 = W.wblob_ptr[w];
-            const int pieces = (int)(W.wblob_ptr[w + 1] - bp0);
+            const long long bp0 = n_bp0;
+            const int pieces = n_pieces;
             for (int q = tid; q < pieces; q += KLU_WAVE_WARPS * 32) klu_cp_async16(blob + q * 2, W.wblob + (bp0 + q) * 4);
             asm volatile("cp.async.commit_group;");
+            if (w + 1 < W.nwaves) {          // part 1 of the next wave's parameters
+                n_k0 = W.wave_col0[w + 1]; n_wc = W.wave_col0[w + 2] - n_k0;
+                n_c0 = W.wbatch_ptr[w + 1]; n_nb = (int)(W.wbatch_ptr[w + 2] - n_c0);
+                n_bp0 = W.wblob_ptr[w + 1]; n_pieces = (int)(W.wblob_ptr[w + 2] - n_bp0);
+                if (tid < KLU_WAVE_ROWS) rs_next = W.wave_rowsrc[(long long)(w + 1) * KLU_WAVE_ROWS + tid];
+            }
         }
         asm volatile("cp.async.wait_group 0;");
         asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
+        if (tid < KLU_WAVE_ROWS) rs_tab[tid] = rs_next;        // every thread is done with this wave's table
         if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
         for (int c = 0; c < nb; c++) {
             const long long g = c0 + c;
@@ -345,6 +372,7 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
             if (lane == 0) klu_mbar_arrive(&empty_bar[buf]);
         }
         if (tid < KLU_WAVE_WARPS) done_round[tid] = 0x7fffffff;
+        if (w + 1 < W.nwaves) load_part2();      // part 2 of the next wave's parameters (depends on part 1)
         asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
         if (dbg) { long long tB = clock64(); t_p1 += tB - tA; tA = tB; }
         // ---- sources inside the wave: rounds.  In round r a column consumes (in pivot order) the in-wave sources
