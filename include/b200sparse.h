@@ -246,6 +246,31 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
 void b200s_klu_free_symbolic(b200s_klu_sym* S);   /* src/C/klu.c:51-61 */
 void b200s_klu_free_numeric(b200s_klu_num* N);    /* src/C/klu.c:63-72 */
 
+/* ---- device-side reduced KKT solver for LP/QP cones (the GPU counterpart of misc.kkt_chol2, -----------------------
+ * reference src/python/misc.py:1352-1567; plugged in through the reference's kktsolver callable API,
+ * src/python/coneprog.py:323-345).  G: ml x n, A: p x n (p may be 0, then Ap/Ai/Ax may be NULL), both CCS with sorted
+ * row indices; Hp/Hi: pattern of the n x n matrix H whose lower triangle enters S (NULL: no H, an LP).
+ * b200s_kkt_factor(di, Hx): S = H + G' diag(di)^2 G (+ A'A in singular mode) is assembled on the device in a fixed
+ * pattern and factored there; K = A S^-1 A' as well.  NOT_POSDEF with *minor = failing column (of S, or of K).
+ * b200s_kkt_solve(x, y, z): misc.py:1489-1565 in place on host vectors (one upload, one download):
+ *   on entry bx, by, bz; on exit ux, uy, W*uz. */
+typedef struct b200s_kkt b200s_kkt;
+b200s_status b200s_kkt_create(b200s_int n, b200s_int ml, b200s_int p, const b200s_int* Gp, const b200s_int* Gi,
+                              const double* Gx, const b200s_int* Ap, const b200s_int* Ai, const double* Ax,
+                              const b200s_int* Hp, const b200s_int* Hi, b200s_kkt** out);
+b200s_status b200s_kkt_set_singular(b200s_kkt* K, int on);    /* misc.py:1427-1447: S += A'A from now on */
+b200s_status b200s_kkt_factor(b200s_kkt* K, const double* di, const double* Hx, b200s_int* minor);
+b200s_status b200s_kkt_solve(b200s_kkt* K, double* x, double* y, double* z);
+typedef struct {
+    b200s_int n, ml, p, nnz_S, nterms, nnz_L, singular_mode;
+    double flops, ms_assemble, ms_factor, ms_solve;
+    const b200s_int *Sp, *Si;       /* lower-triangle pattern of S (valid while K lives) */
+} b200s_kkt_info_t;
+b200s_status b200s_kkt_info(const b200s_kkt* K, b200s_kkt_info_t* info);
+/* evaluates the assembly term lists on the host (verification of the host-built plan in CPU tests; not a solve path) */
+b200s_status b200s_kkt_plan_check_host(const b200s_kkt* K, const double* di, const double* Hx, double* Sx);
+void b200s_kkt_free(b200s_kkt* K);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,12 @@ class KluInfo(C.Structure):
 
 
 
+class KktInfo(C.Structure):
+    _fields_ = [(k, i64) for k in ("n", "ml", "p", "nnz_S", "nterms", "nnz_L", "singular_mode")] + \
+               [(k, C.c_double) for k in ("flops", "ms_assemble", "ms_factor", "ms_solve")] + \
+               [("Sp", C.POINTER(C.c_int64)), ("Si", C.POINTER(C.c_int64))]
+
+
 class KluPlanView(C.Structure):
     _fields_ = [(k, i64) for k in ("n", "nlevels", "nslots", "lu_slots", "nnz_A", "nupd", "ndest")] + \
                [(k, C.POINTER(C.c_int64)) for k in ("cbeg", "rowptr", "upd_ptr", "upd_dest")] + \

@@ -1169,7 +1169,7 @@ public:
     int factor_level(int l);
     int factor_end(i64* minor, CholTimes* times);
     int set_owned(const unsigned char* owned_host);
-    int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times);
+    int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false);
     int ensure_solve_ws(i64 cols);
 };
 
@@ -1599,7 +1599,7 @@ int CholDevice::ensure_solve_ws(i64 cols) {
     return ST_OK;
 }
 
-int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times) {
+int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async) {
     const CholPlan& P = *plan;
     const int n = P.n;
     if (n == 0 || nrhs == 0) return ST_OK;
@@ -1625,8 +1625,12 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         dB = dBstage;
     }
     const i64 ldd = on_device ? ldB : n;
-    const bool do_perm = (sys == 0), do_fwd = (sys == 0 || sys == 1 || sys == 2 || sys == 4),
-               do_bwd = (sys == 0 || sys == 1 || sys == 3 || sys == 5);
+    // sys 0..8: reference numbering (src/C/cholmod.c:437-439).  Internal extras for the device-side KKT solver
+    // (kkt_gpu.cu): 9 = L x = P b (sys 7 then 4 in one pass), 10 = x = P' L^-T b (sys 5 then 8); with `async` the
+    // call returns without synchronising the stream.
+    const bool perm_in = (sys == 0 || sys == 9), perm_out = (sys == 0 || sys == 10),
+               do_fwd = (sys == 0 || sys == 1 || sys == 2 || sys == 4 || sys == 9),
+               do_bwd = (sys == 0 || sys == 1 || sys == 3 || sys == 5 || sys == 10);
     const int gx = std::min((n + 255) / 256, 148 * 8);
     const i64 tstride = (i64)P.rows.size();
     for (i64 j0 = 0; j0 < nrhs; j0 += chunk) {
@@ -1643,7 +1647,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             continue;
         }
         if (sys == 6) continue;  // D x = b with D = I
-        if (do_perm) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
+        if (perm_in) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dX, n, n);
         const long long pstride = (long long)max_solve_ctas * NB;
         // the level sweeps are a fixed launch sequence (hundreds of short dependent kernels): captured once per
@@ -1697,13 +1701,14 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             }
             CUDA_TRY(cudaGraphLaunch(it->second, stream));
         }
-        if (do_perm) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
+        if (perm_out) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
     }
     cudaError_t le = cudaGetLastError();
     if (!on_device && le == cudaSuccess)
         le = cudaMemcpy2DAsync(B, (size_t)ldB * 8, dBstage, (size_t)n * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, stream);
     cudaEventRecord(ev[5], stream);
+    if (async && on_device) { CUDA_TRY(le); return ST_OK; }
     cudaError_t se = cudaStreamSynchronize(stream);
     CUDA_TRY(le);
     CUDA_TRY(se);
@@ -1726,8 +1731,12 @@ int chol_device_factorize(CholDevice* d, const double* val, bool val_on_device, 
     return d->factorize(val, val_on_device, minor, times);
 }
 int chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times) {
-    return d->solve(sys, B, nrhs, ldB, on_device, times);
+    return d->solve(sys, B, nrhs, ldB, on_device, times, false);
 }
+int chol_device_solve_async(CholDevice* d, int sys, double* B_dev, i64 nrhs, i64 ldB) {
+    return d->solve(sys, B_dev, nrhs, ldB, true, nullptr, true);
+}
+void* chol_device_stream(CholDevice* d) { return (void*)d->stream; }
 int chol_device_diag(CholDevice* d, double* diag_host) {
     const CholPlan& P = *d->plan;
     if (P.n == 0) return ST_OK;

@@ -25,6 +25,9 @@ CholDevice* chol_device_create(const CholPlan& plan, const CholOpts& opts, int d
 void chol_device_destroy(CholDevice* d);
 int  chol_device_factorize(CholDevice* d, const double* val, bool val_on_device, i64* minor, CholTimes* times);
 int  chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times);
+// device-resident right-hand sides on the handle's stream, no synchronisation; sys 9 = L x = P b, 10 = x = P' L^-T b
+int  chol_device_solve_async(CholDevice* d, int sys, double* B_dev, i64 nrhs, i64 ldB);
+void* chol_device_stream(CholDevice* d);      // cudaStream_t
 int  chol_device_diag(CholDevice* d, double* diag_host);
 int  chol_device_download_L(CholDevice* d, double* L_host);   // raw panel storage, plan.lsize doubles
 void chol_device_set_profiling(CholDevice* d, bool on);

@@ -249,3 +249,53 @@ def test_klu_zero_diagonal_is_permuted_away():
     st, S, N, A = klu_pivot(A)
     assert st == 0
     fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
+# ---- device-side KKT solver: host-built pattern of S and assembly term lists (kkt_gpu.cu build_plan) ----------------
+
+@pytest.mark.parametrize("seed,n,ml,p", [(0, 40, 90, 3), (1, 25, 25, 0), (2, 60, 200, 10)])
+def test_kkt_assembly_plan_reproduces_H_plus_GtDG(seed, n, ml, p):
+    """S = tril(H + G' diag(di)^2 G [+ A'A]) entry by entry from the constant term lists (misc.py:1418-1455 restated
+    as one fixed-pattern weighted sum)"""
+    rng = np.random.default_rng(seed)
+    G = sp.random(ml, n, density=0.08, random_state=rng, format="csc"); G.sort_indices()
+    A = sp.random(p, n, density=0.3, random_state=rng, format="csc"); A.sort_indices()
+    H = sp.random(n, n, density=0.05, random_state=rng); H = (H + H.T + sp.identity(n)).tocsc()
+    Hl = sp.tril(H).tocsc(); Hl.sort_indices()
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    arrs = [i64(G.indptr), i64(G.indices), G.data.copy(), i64(A.indptr), i64(A.indices), A.data.copy(), i64(Hl.indptr), i64(Hl.indices)]
+    h = C.c_void_p()
+    st = fn["b200s_kkt_create"](n, ml, p, L.ptr_i64(arrs[0]), L.ptr_i64(arrs[1]), L.ptr_f64(arrs[2]), L.ptr_i64(arrs[3]),
+                                L.ptr_i64(arrs[4]), L.ptr_f64(arrs[5]), L.ptr_i64(arrs[6]), L.ptr_i64(arrs[7]), C.byref(h))
+    assert st == 0, L.last_error()
+    for sing in (0, 1):
+        assert fn["b200s_kkt_set_singular"](h, sing) == 0
+        inf = L.KktInfo(); fn["b200s_kkt_info"](h, C.byref(inf))
+        assert inf.singular_mode == sing and inf.n == n and inf.ml == ml and inf.p == p
+        Sp = np.ctypeslib.as_array(inf.Sp, shape=(n + 1,)).copy()
+        Si = np.ctypeslib.as_array(inf.Si, shape=(inf.nnz_S,)).copy()
+        di = rng.uniform(0.5, 2, ml); Sx = np.zeros(inf.nnz_S)
+        assert fn["b200s_kkt_plan_check_host"](h, L.ptr_f64(di), L.ptr_f64(Hl.data.copy()), L.ptr_f64(Sx)) == 0
+        S = sp.csc_matrix((Sx, Si, Sp), shape=(n, n))
+        ref = H + G.T @ sp.diags(di ** 2) @ G
+        if sing and p:
+            ref = ref + A.T @ A
+        assert abs(S - sp.tril(ref)).max() < 1e-13
+        assert all(np.all(np.diff(Si[Sp[j]:Sp[j + 1]]) > 0) and (Sp[j] == Sp[j + 1] or Si[Sp[j]] >= j) for j in range(n))
+    fn["b200s_kkt_free"](h)
+
+
+def test_kkt_rejects_bad_input_and_needs_a_device_for_numeric_work():
+    h = C.c_void_p()
+    cp = np.array([0, 1, 2], dtype=np.int64); ri = np.array([0, 5], dtype=np.int64); vx = np.ones(2)
+    st = fn["b200s_kkt_create"](2, 2, 0, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), None, None, None, None, None, C.byref(h))
+    assert st == L.INVALID and "out of range" in L.last_error()
+    ri = np.array([0, 1], dtype=np.int64)
+    st = fn["b200s_kkt_create"](2, 2, 0, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), None, None, None, None, None, C.byref(h))
+    assert st == 0
+    if L.device_count() == 0:
+        di = np.ones(2); minor = C.c_int64(0)
+        assert fn["b200s_kkt_factor"](h, L.ptr_f64(di), None, C.byref(minor)) == L.NO_DEVICE       # no CPU fallback
+        x = np.ones(2)
+        assert fn["b200s_kkt_solve"](h, L.ptr_f64(x), None, L.ptr_f64(x)) == L.INVALID           # not factored
+    fn["b200s_kkt_free"](h)

@@ -69,6 +69,12 @@ gcholmod.install(kvxopt)
 run_lp(tosp(G), tosp(Aeq))
 dt = min(run_lp(tosp(G), tosp(Aeq))[0] for _ in range(3)); _, sol = run_lp(tosp(G), tosp(Aeq))
 arms["gpu_chol2_sparse_cuda_cholmod"] = {"ms": dt, "iterations": sol["iterations"], "pobj": sol["primal objective"]}
+from kvxopt_b200 import kkt as gkkt
+Gk, Ak = tosp(G), tosp(Aeq)
+run_lp(Gk, Ak, gkkt.lp_kktsolver(Gk, Ak))
+dt = min(run_lp(Gk, Ak, gkkt.lp_kktsolver(Gk, Ak))[0] for _ in range(3)); _, sol = run_lp(Gk, Ak, gkkt.lp_kktsolver(Gk, Ak))
+arms["gpu_device_kkt_solver"] = {"ms": dt, "iterations": sol["iterations"], "pobj": sol["primal objective"],
+                                 "api": "solvers.lp(..., kktsolver=kvxopt_b200.kkt.lp_kktsolver(G, A))"}
 sys.modules["kvxopt.cholmod"] = cholmod_cpu; kvxopt.cholmod = cholmod_cpu
 import kvxopt.misc as misc
 misc.cholmod = cholmod_cpu

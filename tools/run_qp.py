@@ -1,5 +1,6 @@
 """BASELINE config 5: synthetic sparse QP through the reference coneqp (probe build oracle/_ref) with the B200 cholmod
-module as kvxopt.cholmod.  usage: run_qp.py nx ny nrand   (config 5: 500 400 5000; small: 500 400 2000)"""
+module as kvxopt.cholmod.  usage: run_qp.py nx ny nrand [kkt]  (config 5: 500 400 5000; small: 500 400 2000)
+With a 4th argument `kkt` the device-side KKT solver (kvxopt_b200.kkt) is plugged in through the kktsolver callable."""
 import os, sys, time, functools, faulthandler
 faulthandler.enable()
 faulthandler.dump_traceback_later(int(os.environ.get("QP_DUMP_AFTER", "100000")), exit=True)
@@ -35,7 +36,16 @@ def symbolic(*a, **k):
 cholmod.numeric, cholmod.solve, cholmod.symbolic = numeric, solve, symbolic
 solvers.options["show_progress"] = True
 t0 = time.perf_counter()
-sol = solvers.qp(tosp(sp.tril(P)), matrix(q), tosp(G), matrix(h))
+use_kkt = len(sys.argv) > 4 and sys.argv[4] == "kkt"
+if use_kkt:
+    from kvxopt_b200 import kkt
+    Pk, Gk = tosp(sp.tril(P)), tosp(G)
+    t0 = time.perf_counter()
+    ks = kkt.qp_kktsolver(Pk, Gk)
+    sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=ks)
+    print("device KKT solver:", ks.info())
+else:
+    sol = solvers.qp(tosp(sp.tril(P)), matrix(q), tosp(G), matrix(h))
 wall = time.perf_counter() - t0
 print("status %s iterations %d objective %.10f wall %.2f s => %.2f IPM iterations/s" % (sol["status"], sol["iterations"], sol["primal objective"], wall, sol["iterations"] / wall))
 print("cholmod: symbolic %.2f s | numeric %d calls %.3f s | solve %d calls %.3f s | everything else (reference Python IPM, host S assembly) %.2f s" % (
