@@ -12,7 +12,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import kvxopt
 from kvxopt_b200 import cholmod, klu
-cholmod.install(kvxopt)
+mode = sys.argv[4] if len(sys.argv) > 4 else "chol2"
+if mode == "cpu":
+    # CPU arm: the oracle restatement behind kvxopt.cholmod (kind "port"; SuiteSparse is not installable here)
+    from oracle import cholmod_cpu as cholmod
+    sys.modules["kvxopt.cholmod"] = cholmod; kvxopt.cholmod = cholmod
+    os.environ["OPENBLAS_NUM_THREADS"] = os.environ.get("QP_CPU_THREADS", "16")
+else:
+    cholmod.install(kvxopt)
+    # the CUDA context (1-2 s, once per process) is created before the timed region
+    import scipy.sparse as _sp
+    cholmod.linsolve(_sp.identity(2, format="csc"), np.ones((2, 1), order="F"))
 from kvxopt import matrix, spmatrix, solvers
 from generators import qp_instance
 nx, ny, nrand = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (100, 80, 200)
@@ -31,12 +41,12 @@ def solve(*a, **k):
     return r
 def symbolic(*a, **k):
     t = time.perf_counter(); r = osy(*a, **k); t_sym[0] += time.perf_counter() - t
-    if cholmod.factor_info(r)["n"] > 0: print("symbolic: %s" % {k2: v for k2, v in cholmod.factor_info(r).items() if k2 in ("n", "nnz_L", "flops", "nsuper", "max_front_rows", "ms_analyze")}, flush=True)
+    if mode != "cpu" and cholmod.factor_info(r)["n"] > 0: print("symbolic: %s" % {k2: v for k2, v in cholmod.factor_info(r).items() if k2 in ("n", "nnz_L", "flops", "nsuper", "max_front_rows", "ms_analyze")}, flush=True)
     return r
 cholmod.numeric, cholmod.solve, cholmod.symbolic = numeric, solve, symbolic
 solvers.options["show_progress"] = True
 t0 = time.perf_counter()
-use_kkt = len(sys.argv) > 4 and sys.argv[4] == "kkt"
+use_kkt = mode == "kkt"
 if use_kkt:
     from kvxopt_b200 import kkt
     Pk, Gk = tosp(sp.tril(P)), tosp(G)
@@ -47,6 +57,6 @@ if use_kkt:
 else:
     sol = solvers.qp(tosp(sp.tril(P)), matrix(q), tosp(G), matrix(h))
 wall = time.perf_counter() - t0
-print("status %s iterations %d objective %.10f wall %.2f s => %.2f IPM iterations/s" % (sol["status"], sol["iterations"], sol["primal objective"], wall, sol["iterations"] / wall))
+print("mode %s: status %s iterations %d objective %.10f wall %.2f s => %.2f IPM iterations/s%s" % (mode, sol["status"], sol["iterations"], sol["primal objective"], wall, sol["iterations"] / wall, "" if mode == "cpu" else " (CUDA context created before the timed region)"))
 print("cholmod: symbolic %.2f s | numeric %d calls %.3f s | solve %d calls %.3f s | everything else (reference Python IPM, host S assembly) %.2f s" % (
     t_sym[0], n_num[0], t_num[0], n_sol[0], t_sol[0], wall - t_sym[0] - t_num[0] - t_sol[0]))
