@@ -6,6 +6,8 @@
 #include <new>
 #include <stdexcept>
 #include <vector>
+#include <chrono>
+#include <cstdio>
 
 using namespace b200s;
 
@@ -69,7 +71,10 @@ static b200s_status factor_impl(b200s_klu_sym* S, const b200s_int* colptr, const
     N->S = S->S;
     N->device = current_device();
     try {
+        const bool tdbg = getenv("B200S_DEBUG") != nullptr;
+        auto tk0 = std::chrono::steady_clock::now();
         int st = klu_factor(N->S, val, N->N);
+        if (tdbg) fprintf(stderr, "[b200s klu] pivoting factorization (host) %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
         if (st != ST_OK) { delete N; return (b200s_status)st; }
         klu_build_plan(N->S, N->N, N->P);
     } catch (const std::bad_alloc&) {

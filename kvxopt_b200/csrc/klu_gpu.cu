@@ -1070,7 +1070,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         const int* er;
         if ((rc = up(&er, ent_row))) return rc;
         d_ent_row = (int*)er;
-        use_wave = P.max_col_len <= KLU_WAVE_ROWS;
+        use_wave = P.wave_ok && P.max_col_len <= KLU_WAVE_ROWS;
         WD.spine0 = use_wave ? P.spine0 : P.n;
         spine_nd = use_wave ? P.spine_nd : 0;
         if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;

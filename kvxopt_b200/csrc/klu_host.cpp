@@ -12,6 +12,9 @@
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace b200s {
 
@@ -316,6 +319,14 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
 
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
     const i32 n = S.n;
+    const bool tdbg = getenv("B200S_DEBUG") != nullptr;
+    auto tlast = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!tdbg) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200s klu plan] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tlast).count());
+        tlast = now;
+    };
     P = KluPlan();
     P.n = n;
     P.nnzA = S.nnz;
@@ -393,6 +404,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         std::vector<i64> pos(P.rowptr.begin(), P.rowptr.end() - 1);
         for (i64 p = 0; p < S.nnz; p++) P.rowent[pos[pinvnum[S.Ai[p]]]++] = (i32)p;
     }
+    lap("slots + update lists");
     // ---- dense trailing block: the largest nd <= KLU_DENSE_MAX (multiple of 16) inside the last BTF block whose
     // L+U pattern restricted to the last nd rows/columns is at least 30 % dense
     P.upd_end.assign(n, 0);
@@ -429,6 +441,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             }
         }
     }
+    lap("dense block");
     // wave schedule
     P.col_roff.assign(n, 0);
     P.upd_split.assign(n, 0);
@@ -460,6 +473,26 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             }
         }
         P.wave_col0.push_back(n);
+        // Budget: every wave re-streams the earlier L columns its columns need, with ~52 bytes of records per staged row.
+        // With heavy fill (columns longer than the shared-memory wave, or narrow waves over a dense factor) the tables
+        // grow like the flop count; such patterns go to the level-schedule kernel instead and no wave tables are built.
+        {
+            i64 staged = 0;
+            std::vector<i32> mark(n, -1);
+            for (i32 w = 0; w + 1 < (i32)P.wave_col0.size() && staged <= KLU_WAVE_MAX_STAGED; w++) {
+                const i32 k0 = P.wave_col0[w];
+                for (i32 c = k0; c < P.wave_col0[w + 1]; c++)
+                    for (i64 u = P.upd_ptr[c]; u < P.upd_end[c] && P.upd_src[u] < k0; u++)
+                        if (mark[P.upd_src[u]] != w) { mark[P.upd_src[u]] = w; staged += P.upd_cnt[u]; }
+            }
+            P.wave_ok = P.max_col_len <= KLU_WAVE_ROWS && staged <= KLU_WAVE_MAX_STAGED;
+            if (!P.wave_ok) {
+                P.wave_col0.assign(1, 0);
+                P.spine0 = n; P.spine_nd = 0;
+                P.dense_meta.clear(); P.dense_slot.clear();
+                for (i32 k = 0; k < n; k++) P.upd_end[k] = P.upd_ptr[k + 1];
+            }
+        }
         const i32 nw = (i32)P.wave_col0.size() - 1;
         P.wave_hasdep.assign(nw, 0);
         P.wbatch_ptr.assign(1, 0);
@@ -512,6 +545,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             P.wbatch_ptr.push_back((i64)P.bseg_ptr.size() - 1);
         }
     }
+    lap("waves + batches");
     // ---- staged tables of the wave kernel
     {
         const i32 nw = (i32)P.wave_col0.size() - 1;
@@ -579,6 +613,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             P.wblob_ptr.push_back((i64)(P.wblob.size() / 4));
         }
     }
+    lap("staged tables + blobs");
     // level schedule: column k depends on every column j with U(j,k) != 0
     std::vector<i32> level(n, 0);
     P.nlevels = 0;

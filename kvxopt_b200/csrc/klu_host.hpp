@@ -83,6 +83,7 @@ struct KluPlan {
     std::vector<i64> wblob_ptr;       // nwaves+1, in 16-byte units
     std::vector<uint32_t> wblob;
     i32 max_col_len = 0;
+    bool wave_ok = true;              // false: pattern outside the wave kernel's budget (level-schedule kernel instead)
     // dense trailing block ("spine"): the last spine_nd columns are nearly dense after fill (76 % of the work of a
     // power-flow Jacobian).  The wave kernel applies to them only the updates from columns < spine0; the block itself
     // is then factored per matrix by a dense tensor-core LU (k_klu_dense_lu).  spine_nd = 0: disabled.
@@ -103,6 +104,7 @@ constexpr uint32_t KLU_SKIP = 0xffffffffu;
 constexpr int KLU_MAXSEG = 15;        // matched segments per (batch, column); the host closes a batch before it overflows
 constexpr int KLU_REC_U32 = 16 + KLU_CHUNK_ROWS / 2;   // per (batch, column): {nseg, segs[15]} + 64 uint16 destination rows
 constexpr int KLU_BLOB_BYTES = 8192;  // cap of the in-wave update blob
+constexpr long long KLU_WAVE_MAX_STAGED = 8ll << 20;   // staged rows over all waves (x ~52 B of tables): 8 M rows ~ 440 MB
 constexpr int KLU_DENSE_MAX = 160, KLU_DENSE_META = 1 + KLU_DENSE_MAX / 32;    // largest dense trailing block (shared memory: 160 x 164 doubles)
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan);
 

@@ -162,3 +162,69 @@ def test_pipelined_refactor_matches_synchronous_call(klu):
     assert (st2 == ref[2][0]).all() and np.array_equal(X, ref[2][1])
     with pytest.raises(ValueError):
         klu.refactor_batch_end(Fn)
+
+
+def _variety(case):
+    rng = np.random.default_rng(100 + case)
+    if case == 0:                      # block upper triangular: several BTF blocks with off-diagonal (F) entries
+        blocks = [sp.random(m, m, density=0.3, random_state=rng) + 3 * sp.identity(m) for m in (7, 1, 12, 30, 1, 5)]
+        A = sp.block_diag(blocks).tolil()
+        n = A.shape[0]
+        for _ in range(60):
+            i, j = sorted(rng.integers(0, n, 2))
+            if i != j:
+                A[i, j] = rng.standard_normal()
+        perm = rng.permutation(n)
+        return A.tocsc()[perm][:, rng.permutation(n)].tocsc()
+    if case == 1:                      # fully dense: every column of the factor is longer than a wave's shared memory
+        n = 480
+        return sp.csc_matrix(rng.standard_normal((n, n)) + n * np.eye(n))
+    if case == 2:                      # wide band + random fill: long dense tail, many waves
+        n = 900
+        return (sp.diags([rng.standard_normal(n - abs(k)) for k in range(-6, 7)], list(range(-6, 7))) +
+                sp.random(n, n, density=0.001, random_state=rng) + 8 * sp.identity(n)).tocsc()
+    if case == 3:                      # diagonal and 1 x 1
+        return sp.csc_matrix(np.array([[2.5]]))
+    if case == 4:                      # unsymmetric pattern, zero diagonal entries that need the row permutation
+        n = 300
+        A = sp.random(n, n, density=0.02, random_state=rng).tolil()
+        p = rng.permutation(n)
+        for i in range(n):
+            A[i, p[i]] = 4 + rng.uniform()
+        return A.tocsc()
+    n = 64                             # arrow matrix: one dense row and column
+    A = sp.identity(n).tolil() * 3
+    A[0, :] = 1.0; A[:, 0] = 1.0; A[0, 0] = n
+    return A.tocsc()
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_structure_variety_single_and_batched(klu, case):
+    """patterns the reference matrices do not cover: many BTF blocks with F entries, columns longer than the shared-memory
+    wave (level-schedule kernel), long dense tails, 1 x 1, permuted diagonals, arrow -- LU identity, both solves, and a
+    perturbed batch against SuperLU"""
+    A = _variety(case)
+    A.sort_indices()
+    n = A.shape[0]
+    Fs = klu.symbolic(A); Fn = klu.numeric(A, Fs)
+    Lm, Um, P, Q, R, Fm, r = klu.get_numeric(A, Fs, Fn)
+    scale = abs(A).sum(axis=0).max()
+    assert round(abs(R @ P @ A @ Q - (Lm @ Um + Fm)).sum(axis=0).max() / scale, 7) == 0          # the reference's criterion
+    if case == 0:
+        assert len(r) - 1 >= 6 and Fm.nnz > 0
+    rng = np.random.default_rng(case)
+    B = rng.standard_normal((n, 2))
+    for trans, M in (("N", A), ("T", A.T)):
+        X = np.asfortranarray(B.copy())
+        klu.solve(A, Fs, Fn, X, trans=trans)
+        assert np.abs(M @ X - B).max() <= 1e-9 * max(1.0, np.abs(X).max()) * scale
+    batch = 37
+    vals = A.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(batch, A.nnz)))
+    assert not klu.refactor_batch(Fn, vals).any()
+    Bb = rng.standard_normal((batch, 1, n))
+    Xb = Bb.copy()
+    klu.solve_batch(Fn, Xb)
+    for b in (0, 18, 36):
+        Ab = sp.csc_matrix((vals[b], A.indices, A.indptr), shape=(n, n))
+        xref = spla.splu(Ab.tocsc()).solve(Bb[b, 0])
+        assert np.linalg.norm(Xb[b, 0] - xref) <= 1e-9 * np.linalg.norm(xref)
