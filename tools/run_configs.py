@@ -47,6 +47,28 @@ for nrhs in (1, 3):
         "cpu_port_ms": {"numeric": ms_onum, "solve": ms_osol, "kind": "port (oracle/chol_oracle.c, OpenBLAS, same ordering)"},
         "backward_error": res, "rel_diff_vs_oracle": float(np.linalg.norm(X - Xo) / np.linalg.norm(Xo))}
 
+# ---- config 2, single-matrix part: klu.linsolve / symbolic / numeric / solve on ACTIVSg2000 (the batched part is bench.py)
+from oracle import KluOracle
+Aj = load_matrix("ACTIVSg2000"); Aj.sort_indices(); nj = Aj.shape[0]
+Bj = np.asfortranarray(np.random.default_rng(0).standard_normal((nj, 1)))
+gklu.linsolve(Aj, Bj.copy(order="F"))
+ms_lin, _ = best(lambda: gklu.linsolve(Aj, Bj.copy(order="F")))
+ms_sym, Fs = best(lambda: gklu.symbolic(Aj))
+ms_num, Fn = best(lambda: gklu.numeric(Aj, Fs))
+Xj = Bj.copy(order="F")
+ms_sol, _ = best(lambda: gklu.solve(Aj, Fs, Fn, Xj))
+Xj = Bj.copy(order="F"); gklu.solve(Aj, Fs, Fn, Xj)
+resj = float(np.abs(Aj @ Xj - Bj).max())
+_Lm, _Um, _P, _Q, _R, _Fm, _r = gklu.get_numeric(Aj, Fs, Fn)
+_P0, _Qv = np.asarray(_P.tocsr().indices), np.asarray(_Q.tocsc().indices)
+ms_ofac, Oj = best(lambda: KluOracle(nj, Aj.indptr, Aj.indices, Aj.data, P0=_P0, Q=_Qv), 3)
+ms_osol, _ = best(lambda: Oj.solve(Bj[:, 0]), 3)
+out["config2_ACTIVSg2000_single"] = {
+    "n": nj, "nnz": int(Aj.nnz),
+    "gpu_ms": {"linsolve_total": ms_lin, "symbolic_host": ms_sym, "numeric (host pivot search + plan + upload + device refactor)": ms_num, "solve": ms_sol},
+    "cpu_port_ms": {"factor (pivoting Gilbert-Peierls, same ordering)": ms_ofac, "solve": ms_osol, "kind": "port (oracle/klu_oracle.c: BTF + AMD + Gilbert-Peierls)"},
+    "max_residual": resj}
+
 # ---- config 3: solvers.lp on boeing2
 z = np.load(GOLD + "/boeing2_lp.npz")
 G = sp.csc_matrix((z["Gx"], z["Gi"], z["Gp"]), shape=tuple(z["G_size"]))
