@@ -370,6 +370,11 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    # one process per GPU: stay on the cores (and the NUMA node) next to this rank's GPU before any pinned buffer exists
+    numa_cores = 0
+    if world > 1 and not os.environ.get("B200S_NO_NUMA_BIND"):
+        from kvxopt_b200.dist import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local)
     import torch
     import torch.distributed as dist
     from kvxopt_b200 import _lib as L, klu
@@ -482,7 +487,8 @@ def main():
         "config": {"workload": "klu_refactor_batch ACTIVSg2000 (n=4000, nnz=29336) same-pattern perturbations 1e-3",
                    "batch_per_gpu": batch, "global_batch": batch * world, "l2": "inputs_larger_than_l2 (961 MB values per GPU per step)",
                    "nnz_L": d["nnz_L"], "nnz_U": d["nnz_U"], "levels": d["nlevels"], "flops_per_refactor": d["flops"],
-                   "parallelism": "independent matrices sharded by rank, no collective"},
+                   "parallelism": "independent matrices sharded by rank, no collective",
+                   "host_cores_bound_per_rank": numa_cores},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "e2e": {"value": e2e_value, "unit": "refactors/s", "h2d_bytes_per_step": int(batch * nnz * 8),
                 "d2h_bytes_per_step": int(batch * 4), "ms_per_step": e2e_ms / args.steps,

@@ -12,8 +12,9 @@
 //   LU  [Bp/32][slots][32]  GROUP-MAJOR: the slots of a group of 32 matrices are contiguous (value v of matrix b at
 //       (b/32)*slots*32 + v*32 + b%32), so a run of consecutive slots -- the L part of a column -- is ONE contiguous
 //       block that a single cp.async.bulk (TMA) moves.  Per column: U above the diagonal, U diagonal, L below; then F
-// Kernels: k_klu_transpose (tiled), k_klu_rowscale, k_klu_scatter, k_klu_refactor (one CTA per group of
-// 32 matrices walks the column level schedule, 16 warps share the columns of a level), k_klu_solve.
+// Kernels: k_klu_transpose (tiled), k_klu_rowscale, k_klu_prescale, k_klu_scatter, k_klu_refactor_wave (fast path: TMA
+// producer warp + 16 consumer warps per group of 32 matrices), k_klu_dense_pack / k_klu_dense_lu (dense trailing block),
+// k_klu_refactor (level-schedule kernel for patterns outside the wave kernel's budget), k_klu_solve_lvl.
 #include "gpu.hpp"
 #include "devpool.hpp"
 #include "klu_host.hpp"
@@ -152,11 +153,6 @@ __device__ __forceinline__ void klu_cp_async16(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
 }
-__device__ __forceinline__ void klu_cp_async16_zfill(void* smem, const void* gmem, int bytes) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes));
-}
-
 constexpr int KLU_ENTRY_DOUBLES = (KLU_WAVE_WARPS * KLU_REC_U32 + KLU_CHUNK_ROWS) / 2;   // column records + next row->slot table (uint32), in doubles
 constexpr int KLU_STAGE_DOUBLES = KLU_CHUNK_ROWS * 32 + KLU_ENTRY_DOUBLES;      // L rows + per-warp row actions
 constexpr size_t KLU_WAVE_SMEM =

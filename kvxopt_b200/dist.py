@@ -21,6 +21,29 @@ from . import _lib as L
 fn = L.fn
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin the calling process to the CPU cores next to GPU `local_rank` (NVML's ideal CPU affinity), so that pinned
+    host buffers allocated afterwards are first-touched on the GPU's own NUMA node.  With one process per GPU on an
+    8-GPU box, the 961 MB-per-step uploads of the batched KLU path otherwise cross the socket interconnect.  Returns
+    the number of cores bound, 0 when NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def front_layout(h):
     inf = L.CholInfo()
     fn["b200s_chol_info"](h, C.byref(inf))
