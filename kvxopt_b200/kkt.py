@@ -120,7 +120,8 @@ def chol2(G, dims, A, mnl=0):
             raise ValueError("H was given in the first call and is missing now")
         di = _vec(W["di"], ml, "W['di']") if ml else np.zeros(0)
         di = np.ascontiguousarray(di, dtype=np.float64)
-        h = state["handle"].h
+        handle = state["handle"]          # kept alive by the returned solve() even when the caller drops factor()
+        h = handle.h
         minor = C.c_int64(0)
         st = fn["b200s_kkt_factor"](h, L.ptr_f64(di), L.ptr_f64(Hx) if Hx is not None else None, C.byref(minor))
         if st == L.NOT_POSDEF and state["firstcall"] and not state["singular"]:
@@ -138,7 +139,7 @@ def chol2(G, dims, A, mnl=0):
             xf = _vec(x, n, "x")
             yf = _vec(y, p, "y") if p else None
             zf = _vec(z, ml, "z") if ml else None
-            st2 = fn["b200s_kkt_solve"](h, L.ptr_f64(xf), L.ptr_f64(yf) if p else None, L.ptr_f64(zf) if ml else None)
+            st2 = fn["b200s_kkt_solve"](handle.h, L.ptr_f64(xf), L.ptr_f64(yf) if p else None, L.ptr_f64(zf) if ml else None)
             if st2 != L.OK:
                 _raise(st2)
 

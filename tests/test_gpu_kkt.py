@@ -142,3 +142,19 @@ def test_errors_follow_the_reference(kvx):
     Hneg = kvx.spmatrix([-5.0, -5.0, -5.0], [0, 1, 2], [0, 1, 2], (3, 3))
     with pytest.raises(ArithmeticError):
         factor(W, Hneg)                                             # S = -5 I + I: not positive definite, A is empty
+
+
+def test_solve_outlives_the_factor_closure(kvx):
+    """kkt.chol2(...)(W) used as a temporary: the returned solve() must keep the device object alive"""
+    import gc
+    from kvxopt import matrix
+    from kvxopt_b200 import kkt
+    G = to_spmatrix(kvx, sp.identity(4).tocsc() * 2.0)
+    A = kvx.spmatrix([], [], [], (0, 4), "d")
+    W = {"d": matrix([1.0] * 4), "di": matrix([1.0] * 4)}
+    solve = kkt.chol2(G, {"l": 4, "q": [], "s": []}, A)(W)
+    gc.collect()
+    x, y, z = matrix([1.0, 2.0, 3.0, 4.0]), matrix(0.0, (0, 1)), matrix([0.0] * 4)
+    solve(x, y, z)                                    # S = 4 I, bz = 0  =>  ux = bx / 4, W uz = G ux
+    np.testing.assert_allclose(np.array(x).ravel(), [0.25, 0.5, 0.75, 1.0], rtol=1e-14)
+    np.testing.assert_allclose(np.array(z).ravel(), [0.5, 1.0, 1.5, 2.0], rtol=1e-14)
