@@ -391,6 +391,8 @@ def diag(F):
         raise ValueError("F must be a numeric Cholesky factor")
     d = np.zeros(inf.n, dtype=np.float64)
     st = fn["b200s_chol_diag"](h, L.ptr_f64(d))
+    if st == L.INVALID:       # LDL' semantics (options['supernodal'] = 0): cholmod.c:919-922
+        raise ValueError("F must be a nonsingular supernodal Cholesky factor")
     if st != L.OK:
         _raise_status(st, "diag failed")
     return _make_matrix(_FAMILY.get(h), d, (inf.n, 1))

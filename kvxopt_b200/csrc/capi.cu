@@ -17,7 +17,7 @@ struct b200s_chol {
     int device = 0;
     CholTimes times;
     i64 minor = 0;
-    bool numeric = false, profiling = false;
+    bool numeric = false, profiling = false, ldl = false;
 };
 
 static_assert(B200S_OK == ST_OK && B200S_NOT_POSDEF == ST_NOT_POSDEF && B200S_SINGULAR == ST_SINGULAR &&
@@ -69,11 +69,15 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
         if (opts->block > 0) F->opts.block = opts->block;
         for (int i = 0; i < 3; i++) { F->opts.nrelax[i] = opts->nrelax[i]; F->opts.zrelax[i] = opts->zrelax[i]; }
     }
-    if (F->opts.supernodal != 2 && F->opts.supernodal != 1) {
-        set_last_error("only the supernodal LL^T factorization (cholmod.options['supernodal'] = 2) is implemented");
+    // supernodal = 0 asks CHOLMOD for a simplicial LDL' factorization.  The engine always factors supernodally; for the
+    // positive definite matrices this path serves, L_ldl = L D^-1/2 and D = diag(L)^2, so the factor object answers with
+    // LDL' semantics (sys 2..6 scaled by the diagonal, getfactor with D on the diagonal, diag() refused) -- see chol_gpu.cu.
+    if (F->opts.supernodal < 0 || F->opts.supernodal > 2) {
+        set_last_error("cholmod.options['supernodal'] must be 0, 1 or 2");
         delete F;
         return B200S_INVALID;
     }
+    F->ldl = F->opts.supernodal == 0;
     F->device = current_device();
     try {
         static const b200s_int zero = 0;
@@ -101,6 +105,7 @@ static b200s_status ensure_device(b200s_chol* F) {
         F->dev = chol_device_create(F->plan, F->opts, F->device, &st);
         if (!F->dev) return (b200s_status)st;
         chol_device_set_profiling(F->dev, F->profiling);
+        chol_device_set_ldl(F->dev, F->ldl);
     }
     return B200S_OK;
 }
@@ -250,6 +255,7 @@ b200s_status b200s_chol_diag(b200s_chol* F, double* d_out) {
     if (F->plan.n == 0) return B200S_OK;
     if (!d_out) return B200S_INVALID;
     if (!F->numeric || !F->dev) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
+    if (F->ldl) { set_last_error("F must be a nonsingular supernodal Cholesky factor"); return B200S_INVALID; }    /* cholmod.c:919-922 */
     return (b200s_status)chol_device_diag(F->dev, d_out);
 }
 
@@ -278,9 +284,16 @@ b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, dou
     lp[0] = 0;
     for (const Front& f : P.fronts)
         for (i32 c = 0; c < f.nc; c++) {
+            // LDL' semantics (supernodal = 0): cholmod_factor_to_sparse returns L with D on its diagonal; from the LL'
+            // panels that is L(:,c) / l_cc below the diagonal and l_cc^2 on it
+            const double lcc = raw[f.loff + (i64)c * f.ld + c];
             for (i32 r = c; r < f.nr; r++) {
                 double v = raw[f.loff + (i64)c * f.ld + r];
-                if (r == c || v != 0.0) { li[p] = P.rows[f.rowptr + r]; lx[p] = v; p++; }
+                if (r == c || v != 0.0) {
+                    li[p] = P.rows[f.rowptr + r];
+                    lx[p] = !F->ldl ? v : (r == c ? lcc * lcc : v / lcc);
+                    p++;
+                }
             }
             lp[f.col0 + c + 1] = p;
         }

@@ -1078,6 +1078,17 @@ __global__ void k_copy_cols(const double* __restrict__ S, long long lds, double*
     double* d = Dst + blockIdx.y * ldd;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) d[k] = s[k];
 }
+// LDL' semantics on top of the LL' factor (cholmod.options['supernodal'] = 0, reference src/C/cholmod.c:60-64,437-439):
+// for a positive definite matrix L_ldl = L D^-1/2 and D = diag(L)^2, so the LDL' systems are the LL' sweeps with a
+// diagonal scaling before or after.  mode 1: x *= l, 2: x /= l, 3: x /= l^2   (l = diag of the LL' factor, permuted order)
+__global__ void k_scale_by_diag(double* __restrict__ x, long long ldx, const double* __restrict__ dg, int n, int mode) {
+    double* col = x + (long long)blockIdx.y * ldx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double l = dg[i];
+        col[i] = mode == 1 ? col[i] * l : mode == 2 ? col[i] / l : col[i] / (l * l);
+    }
+}
+
 __global__ void k_diag(const FrontD* __restrict__ F, int ns, const double* __restrict__ L, double* __restrict__ d) {
     for (int s = blockIdx.x; s < ns; s += gridDim.x) {
         const FrontD f = F[s];
@@ -1148,7 +1159,7 @@ public:
         pool_free(dL); pool_free(dW); pool_free(dval); pool_free(dT); pool_free(dX); pool_free(dBstage); pool_free(damap); pool_free(dF);
         pool_free(drows); pool_free(drel); pool_free(dchild); pool_free(dperm); pool_free(dlevel_fronts);
         pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(ddiag); pool_free(dpart); pool_free(downed);
-        pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb);
+        pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -1170,6 +1181,9 @@ public:
     int factor_end(i64* minor, CholTimes* times);
     int set_owned(const unsigned char* owned_host);
     int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false);
+    bool ldl = false;             // LDL' semantics of sys 2..6 (supernodal = 0)
+    double* ddiagL = nullptr;     // diagonal of L (permuted order), valid while diagL_valid
+    bool diagL_valid = false;
     int ensure_solve_ws(i64 cols);
 };
 
@@ -1424,6 +1438,7 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
     CUDA_TRY(cudaSetDevice(device));
     numeric = false;
     minv_valid = false;
+    diagL_valid = false;
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     const double* dv = val;
     if (!on_device) {
@@ -1625,6 +1640,19 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         dB = dBstage;
     }
     const i64 ldd = on_device ? ldB : n;
+    int pre = 0, post = 0;        // LDL' semantics: diagonal scaling before / after the LL' sweeps
+    if (ldl) {
+        if (sys == 2) post = 2;             // L D x = b   : x = D^-1/2 (L_ll^-1 b)
+        else if (sys == 3) pre = 2;         // D L' x = b  : x = L_ll^-T (D^-1/2 b)
+        else if (sys == 4) post = 1;        // L x = b     : x = D^1/2 (L_ll^-1 b)
+        else if (sys == 5) pre = 1;         // L' x = b    : x = L_ll^-T (D^1/2 b)
+        else if (sys == 6) pre = 3;         // D x = b
+        if ((pre || post) && !diagL_valid) {
+            if (!ddiagL) CUDA_TRY(pool_malloc((void**)&ddiagL, (size_t)n * sizeof(double)));
+            k_diag<<<std::min<int>((int)P.fronts.size(), 148 * 8), 128, 0, stream>>>(dF, (int)P.fronts.size(), dL, ddiagL);
+            diagL_valid = true;
+        }
+    }
     // sys 0..8: reference numbering (src/C/cholmod.c:437-439).  Internal extras for the device-side KKT solver
     // (kkt_gpu.cu): 9 = L x = P b (sys 7 then 4 in one pass), 10 = x = P' L^-T b (sys 5 then 8); with `async` the
     // call returns without synchronising the stream.
@@ -1646,9 +1674,13 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
             continue;
         }
-        if (sys == 6) continue;  // D x = b with D = I
+        if (sys == 6) {          // D x = b: D = I for LL', diag(L)^2 with LDL' semantics
+            if (pre) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, ddiagL, n, pre);
+            continue;
+        }
         if (perm_in) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dX, n, n);
+        if (pre) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, ddiagL, n, pre);
         const long long pstride = (long long)max_solve_ctas * NB;
         // the level sweeps are a fixed launch sequence (hundreds of short dependent kernels): captured once per
         // (columns, directions) into a CUDA graph and replayed
@@ -1701,6 +1733,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             }
             CUDA_TRY(cudaGraphLaunch(it->second, stream));
         }
+        if (post) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, ddiagL, n, post);
         if (perm_out) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
     }
@@ -1756,6 +1789,7 @@ int chol_device_download_L(CholDevice* d, double* L_host) {
     return ST_OK;
 }
 void chol_device_set_profiling(CholDevice* d, bool on) { d->profiling = on; }
+void chol_device_set_ldl(CholDevice* d, bool on) { d->ldl = on; }
 int chol_device_set_owned(CholDevice* d, const unsigned char* owned) { return d->set_owned(owned); }
 int chol_device_factor_begin(CholDevice* d, const double* val, bool on_device) { return d->factor_begin(val, on_device); }
 int chol_device_factor_level(CholDevice* d, int level) { return d->factor_level(level); }

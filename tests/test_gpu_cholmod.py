@@ -195,10 +195,47 @@ def test_error_contract(cholmod):
             cholmod.symbolic(A)
     finally:
         del cholmod.options["nope"]
-    cholmod.options["supernodal"] = 0
+    cholmod.options["supernodal"] = 7
     try:
         with pytest.raises(ValueError):
-            cholmod.symbolic(A)           # simplicial LDL' is refused, never emulated on the CPU
+            cholmod.symbolic(A)
+    finally:
+        del cholmod.options["supernodal"]
+
+
+def test_simplicial_ldl_semantics_supernodal_0(cholmod):
+    """cholmod.options['supernodal'] = 0 (reference src/C/cholmod.c:60-64): the factor answers as an LDL' factor --
+    sys 1..6 per cholmod.c:437-439, getfactor with D on the diagonal, diag() refused (cholmod.c:919-922) -- and the
+    documented log-det example (doc/source/spsolvers.rst:759-772) gives 5.505331535932363 through sys=6."""
+    import scipy.linalg as sla
+    A4 = sp.csc_matrix(np.array([[10.0, 0, 3, 0], [0, 5, 0, -2], [3, 0, 5, 0], [0, -2, 0, 2]]))
+    cholmod.options["supernodal"] = 0
+    try:
+        F = cholmod.symbolic(lower_ccs(A4)); cholmod.numeric(lower_ccs(A4), F)
+        Di = np.ones((4, 1), order="F")
+        cholmod.solve(F, Di, sys=6)
+        assert abs(-np.log(Di).sum() - 5.505331535932363) < 1e-12
+        with pytest.raises(ValueError):
+            cholmod.diag(F)
+        A = rand_spd(150, 0.05, 4); Al = lower_ccs(A); n = 150
+        F = cholmod.symbolic(Al); cholmod.numeric(Al, F)
+        perm = cholmod.factor_perm(F)
+        Ap = A.toarray()[np.ix_(perm, perm)]
+        Lc = np.linalg.cholesky(Ap)
+        d = np.diag(Lc) ** 2
+        Ld = Lc / np.diag(Lc)[None, :]
+        Lf = cholmod.getfactor(F).toarray()
+        assert np.abs(np.diag(Lf) - d).max() <= 1e-12 * d.max()
+        assert np.abs(np.tril(Lf, -1) - np.tril(Ld, -1)).max() <= 1e-12
+        B = np.random.default_rng(0).standard_normal((n, 2))
+        Pm = np.eye(n)[perm]
+        ref = {0: np.linalg.solve(A.toarray(), B), 1: np.linalg.solve(Ap, B), 2: np.linalg.solve(Ld @ np.diag(d), B),
+               3: np.linalg.solve(np.diag(d) @ Ld.T, B), 4: sla.solve_triangular(Ld, B, lower=True, unit_diagonal=True),
+               5: sla.solve_triangular(Ld.T, B, lower=False, unit_diagonal=True), 6: B / d[:, None], 7: Pm @ B, 8: Pm.T @ B}
+        for sys_, want in ref.items():
+            X = np.asfortranarray(B.copy())
+            cholmod.solve(F, X, sys=sys_)
+            assert np.linalg.norm(X - want) <= 1e-10 * np.linalg.norm(want), sys_
     finally:
         del cholmod.options["supernodal"]
 

@@ -112,9 +112,12 @@ def test_invalid_inputs():
     ri2 = ri.copy(); ri2[0] = 99
     F = L.vp()
     assert fn["b200s_chol_analyze"](10, L.ptr_i64(cp), L.ptr_i64(ri2), b"L", None, None, C.byref(F)) == L.INVALID
-    o = L.CholOpts(); fn["b200s_chol_default_opts"](C.byref(o)); o.supernodal = 0
+    o = L.CholOpts(); fn["b200s_chol_default_opts"](C.byref(o)); o.supernodal = 3
     st, _ = analyze(A, opts=o)
-    assert st == L.INVALID         # simplicial LDL^T mode is not implemented and is refused, not emulated
+    assert st == L.INVALID         # cholmod.options['supernodal'] is 0 (LDL' semantics), 1 or 2
+    o.supernodal = 0
+    st, F0 = analyze(A, opts=o)
+    assert st == 0
 
 
 def test_zero_size_and_upper():
