@@ -239,18 +239,25 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                 }
                 klu_mbar_wait(&empty_bar[slot], par ^ 1u);
                 double* dst = stage + (long long)slot * KLU_STAGE_DOUBLES;
-                // a batch holds at most KLU_CHUNK_ROWS (64) one-row segments: lane q takes segments q and q + 32
-                int2 ex = make_int2(0, 0);
-                if (a0 + 32 + lane < a1) ex = W.segd[a0 + 32 + lane];
-                int rows = (a0 + lane < a1 ? (cur.y >> 8) : 0) + (a0 + 32 + lane < a1 ? (ex.y >> 8) : 0);
+                // lane q takes segments q (descriptor prefetched), q + 32, ... (a batch holds at most KLU_CHUNK_ROWS one-row segments)
+                constexpr int XSEG = (KLU_CHUNK_ROWS + 31) / 32 - 1;
+                int2 ex[XSEG > 0 ? XSEG : 1];
+                int rows = a0 + lane < a1 ? (cur.y >> 8) : 0;
+#pragma unroll
+                for (int q = 0; q < XSEG; q++) {
+                    ex[q] = make_int2(0, 0);
+                    if (a0 + 32 * (q + 1) + lane < a1) { ex[q] = W.segd[a0 + 32 * (q + 1) + lane]; rows += ex[q].y >> 8; }
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
                 if (lane == 0) klu_mbar_expect_tx(&full_bar[slot], (unsigned)rows * 256u + META_BYTES);
                 __syncwarp();
                 if (a0 + lane < a1)
                     klu_bulk_g2s(dst + (cur.y & 0xff) * 32, lug + (long long)cur.x * 32, (unsigned)(cur.y >> 8) * 256u, &full_bar[slot]);
-                if (a0 + 32 + lane < a1)
-                    klu_bulk_g2s(dst + (ex.y & 0xff) * 32, lug + (long long)ex.x * 32, (unsigned)(ex.y >> 8) * 256u, &full_bar[slot]);
+#pragma unroll
+                for (int q = 0; q < XSEG; q++)
+                    if (a0 + 32 * (q + 1) + lane < a1)
+                        klu_bulk_g2s(dst + (ex[q].y & 0xff) * 32, lug + (long long)ex[q].x * 32, (unsigned)(ex[q].y >> 8) * 256u, &full_bar[slot]);
                 if (lane == 0) klu_bulk_g2s(dst + KLU_CHUNK_ROWS * 32, W.bentry + g * KLU_ENTRY_DOUBLES * 2, META_BYTES, &full_bar[slot]);
             }
             asm volatile("bar.sync 0;" ::: "memory");       // end of wave: the consumers stored (and fenced) the wave's columns
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         n_wrows = (int)(P.cbeg[n_k0 + n_wc] - P.cbeg[n_k0]);
     };
     load_part2();
-    if (tid < KLU_WAVE_ROWS) rs_tab[tid] = W.wave_rowsrc[tid];
+    for (int r = tid; r < KLU_WAVE_ROWS; r += KLU_WAVE_WARPS * 32) rs_tab[r] = W.wave_rowsrc[r];
     asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
     for (int w = 0; w < W.nwaves; w++) {
         if (dbg) tA = clock64();
@@ -294,7 +301,8 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
         // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
         const int wrows = n_wrows;
-        int rs_next = -1;
+        constexpr int RS_PER = (KLU_WAVE_ROWS + KLU_WAVE_WARPS * 32 - 1) / (KLU_WAVE_WARPS * 32);
+        int rs_next[RS_PER];
         {
             for (int row = srow; row < wrows; row += 32) {
                 const int src = rs_tab[row];
@@ -309,12 +317,22 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                 n_k0 = W.wave_col0[w + 1]; n_wc = W.wave_col0[w + 2] - n_k0;
                 n_c0 = W.wbatch_ptr[w + 1]; n_nb = (int)(W.wbatch_ptr[w + 2] - n_c0);
                 n_bp0 = W.wblob_ptr[w + 1]; n_pieces = (int)(W.wblob_ptr[w + 2] - n_bp0);
-                if (tid < KLU_WAVE_ROWS) rs_next = W.wave_rowsrc[(long long)(w + 1) * KLU_WAVE_ROWS + tid];
+#pragma unroll
+                for (int q = 0; q < RS_PER; q++) {
+                    const int r = tid + q * KLU_WAVE_WARPS * 32;
+                    rs_next[q] = r < KLU_WAVE_ROWS ? W.wave_rowsrc[(long long)(w + 1) * KLU_WAVE_ROWS + r] : -1;
+                }
             }
         }
         asm volatile("cp.async.wait_group 0;");
         asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
-        if (tid < KLU_WAVE_ROWS) rs_tab[tid] = rs_next;        // every thread is done with this wave's table
+        if (w + 1 < W.nwaves) {                                // every thread is done with this wave's table
+#pragma unroll
+            for (int q = 0; q < RS_PER; q++) {
+                const int r = tid + q * KLU_WAVE_WARPS * 32;
+                if (r < KLU_WAVE_ROWS) rs_tab[r] = rs_next[q];
+            }
+        }
         if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
         for (int c = 0; c < nb; c++) {
             const long long g = c0 + c;

@@ -96,10 +96,10 @@ struct KluPlan {
     std::vector<i32> fslot0;          // per column: first F slot
 };
 constexpr int KLU_WAVE_WARPS = 16;   // columns (warps) per wave
-constexpr int KLU_WAVE_ROWS = 464;   // shared-memory rows for the columns of a wave (x 32 matrices x 8 B = 116 KiB)
+constexpr int KLU_WAVE_ROWS = 528;   // shared-memory rows for the columns of a wave (x 32 matrices x 8 B = 132 KiB)
 constexpr int KLU_META_INT4 = 72;    // per batch: header {nseg} + up to 64 segment descriptors, padded to 1152 B
-constexpr int KLU_CHUNK_ROWS = 64;   // L entries staged per chunk (16 KiB per stage)
-constexpr int KLU_STAGES = 5;
+constexpr int KLU_CHUNK_ROWS = 128;   // L entries staged per batch (32 KiB per stage)
+constexpr int KLU_STAGES = 2;
 constexpr uint32_t KLU_SKIP = 0xffffffffu;
 constexpr int KLU_MAXSEG = 15;        // matched segments per (batch, column); the host closes a batch before it overflows
 constexpr int KLU_REC_U32 = 16 + KLU_CHUNK_ROWS / 2;   // per (batch, column): {nseg, segs[15]} + 64 uint16 destination rows
