@@ -268,12 +268,13 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     // (part 1 right after the gather is issued, the dependent part 2 after the staged phase), so that a wave starts
     // without a chain of dependent global loads.
     __shared__ int rs_tab[KLU_WAVE_ROWS];
-    int n_k0 = W.wave_col0[0], n_wc = W.wave_col0[1] - n_k0;
-    long long n_c0 = W.wbatch_ptr[0], n_bp0 = W.wblob_ptr[0];
-    int n_nb = (int)(W.wbatch_ptr[1] - n_c0), n_pieces = (int)(W.wblob_ptr[1] - n_bp0);
+    // raw values only: nothing is computed from a prefetched word until the next wave starts (no stall on the loads)
+    int n_k0 = W.wave_col0[0], n_k1 = W.wave_col0[1];
+    long long n_c0 = W.wbatch_ptr[0], n_c1 = W.wbatch_ptr[1], n_bp0 = W.wblob_ptr[0], n_bp1 = W.wblob_ptr[1];
     int n_cb = 0, n_len = 0, n_roff = 0, n_diag = 0, n_l0 = 0, n_wrows = 0;
     auto team_size = [](int wc) { return wc <= 8 ? KLU_WAVE_WARPS / wc : 1; };      // warps per column (any size, not only 2^k)
     auto load_part2 = [&]() {
+        const int n_wc = n_k1 - n_k0;
         const int c = warp / team_size(n_wc);
         const int k = n_k0 + (c < n_wc ? c : 0);
         n_cb = (int)P.cbeg[k];
@@ -281,14 +282,14 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         n_roff = W.col_roff[k];
         n_diag = P.udiag_slot[k] - n_cb;
         n_l0 = P.lslot0[k] - n_cb;
-        n_wrows = (int)(P.cbeg[n_k0 + n_wc] - P.cbeg[n_k0]);
+        n_wrows = (int)(P.cbeg[n_k1] - P.cbeg[n_k0]);
     };
     load_part2();
     for (int r = tid; r < KLU_WAVE_ROWS; r += KLU_WAVE_WARPS * 32) rs_tab[r] = W.wave_rowsrc[r];
     asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
     for (int w = 0; w < W.nwaves; w++) {
         if (dbg) tA = clock64();
-        const int k0 = n_k0, wc = n_wc;
+        const int k0 = n_k0, wc = n_k1 - n_k0;
         // team = the warps that share one column: floor(16 / wc) warps
         const int T = team_size(wc), col = warp / T, sub = warp - col * T;
         const bool active = col < wc;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         double* x = xs + n_roff * 32 + lane;
         const int diag = n_diag, l0 = n_l0;
         const long long c0 = n_c0;
-        const int nb = n_nb;
+        const int nb = (int)(n_c1 - n_c0);
         auto team_sync = [&]() { if (T > 1) asm volatile("bar.sync %0, %1;" ::"r"(col + 1), "r"(T * 32) : "memory"); };
         // ---- group 0: gather the (pre-scaled) input values of the wave's columns into xs, and the in-wave blob
         const int wrows = n_wrows;
@@ -310,13 +311,13 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                 else *reinterpret_cast<double2*>(xs + row * 32 + spc) = make_double2(0.0, 0.0);      // fill-in slot
             }
             const long long bp0 = n_bp0;
-            const int pieces = n_pieces;
+            const int pieces = (int)(n_bp1 - n_bp0);
             for (int q = tid; q < pieces; q += KLU_WAVE_WARPS * 32) klu_cp_async16(blob + q * 2, W.wblob + (bp0 + q) * 4);
             asm volatile("cp.async.commit_group;");
             if (w + 1 < W.nwaves) {          // part 1 of the next wave's parameters
-                n_k0 = W.wave_col0[w + 1]; n_wc = W.wave_col0[w + 2] - n_k0;
-                n_c0 = W.wbatch_ptr[w + 1]; n_nb = (int)(W.wbatch_ptr[w + 2] - n_c0);
-                n_bp0 = W.wblob_ptr[w + 1]; n_pieces = (int)(W.wblob_ptr[w + 2] - n_bp0);
+                n_k0 = W.wave_col0[w + 1]; n_k1 = W.wave_col0[w + 2];
+                n_c0 = W.wbatch_ptr[w + 1]; n_c1 = W.wbatch_ptr[w + 2];
+                n_bp0 = W.wblob_ptr[w + 1]; n_bp1 = W.wblob_ptr[w + 2];
 #pragma unroll
                 for (int q = 0; q < RS_PER; q++) {
                     const int r = tid + q * KLU_WAVE_WARPS * 32;
