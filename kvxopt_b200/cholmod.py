@@ -130,6 +130,19 @@ def _ccs(A):
             np.ascontiguousarray(A.data, dtype=np.float64))
 
 
+def _values(A):
+    """float64 value array of a sparse matrix in CCS order (a view when the container already stores it that way)"""
+    if _is_kvx(A):
+        return np.array(A.V, dtype=np.float64).reshape(-1)
+    import scipy.sparse as sp
+    if not sp.isspmatrix_csc(A) and not (hasattr(sp, "csc_array") and isinstance(A, sp.csc_array)):
+        A = A.tocsc()
+    if not A.has_sorted_indices:
+        A = A.copy()
+        A.sort_indices()
+    return np.ascontiguousarray(A.data, dtype=np.float64)
+
+
 def _dense_view(B):
     """flat column-major float64 view that shares memory with B, plus (nrows, ncols)"""
     if _is_kvx(B):
@@ -261,7 +274,7 @@ def numeric(A, F):
     if _typecode(A) != "d":
         raise TypeError("F is not the CHOLMOD factor of a '%s' matrix" % _typecode(A))
     inf = _info(h)
-    cp, ri, vx = _ccs(A)
+    vx = _values(A)               # the pattern was analysed in symbolic(); only the values travel (no index conversion)
     if _size(A)[0] != inf.n or vx.size != inf.nnz_A:
         raise ValueError("factorization failed")
     _factorize(h, vx)

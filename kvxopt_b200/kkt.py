@@ -24,7 +24,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .cholmod import _ccs, _dense_view, _is_kvx, _is_dense, _size
+from .cholmod import _ccs, _dense_view, _is_kvx, _is_dense, _size, _values
 
 fn = L.fn
 
@@ -111,11 +111,11 @@ def chol2(G, dims, A, mnl=0):
         if H is not None:
             if state["Hpattern"] is None:
                 raise ValueError("H was None in the first call and cannot appear later")
-            hc = _sparse_ccs(H, "H")
-            if len(hc[1]) != len(state["Hpattern"][1]) or not np.array_equal(hc[0], state["Hpattern"][0]) or \
-                    not np.array_equal(hc[1], state["Hpattern"][1]):
+            # the pattern of H was fixed by the first call (as the reference's S += H on a fixed F['S'] assumes);
+            # only the values travel -- no index conversion per interior-point iteration
+            Hx = _values(H) if not _is_dense(H) else _sparse_ccs(H, "H")[2]
+            if len(Hx) != len(state["Hpattern"][1]):
                 raise ValueError("the sparsity pattern of H changed between calls")
-            Hx = hc[2]
         elif state["Hpattern"] is not None:
             raise ValueError("H was given in the first call and is missing now")
         di = _vec(W["di"], ml, "W['di']") if ml else np.zeros(0)
