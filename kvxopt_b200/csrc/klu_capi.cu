@@ -85,10 +85,16 @@ static b200s_status factor_impl(b200s_klu_sym* S, const b200s_int* colptr, const
     if (n > 0 && with_device) {
         // the numeric values used by solve/extract come from the device refactorization (batch of one)
         int st = ST_OK;
+        const bool tdbg = getenv("B200S_DEBUG") != nullptr;
+        auto td0 = std::chrono::steady_clock::now();
         N->dev = klu_device_create(N->P, N->N, N->S, N->device, &st);
         if (!N->dev) { delete N; return (b200s_status)st; }
+        auto td1 = std::chrono::steady_clock::now();
         int mst = 0;
         st = klu_device_refactor(N->dev, val, false, 1, S->S.nnz, &mst);
+        if (tdbg) fprintf(stderr, "[b200s klu] device plan upload %.1f ms, refactorization of the batch of one %.1f ms\n",
+                          std::chrono::duration<double, std::milli>(td1 - td0).count(),
+                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td1).count());
         if (st == ST_OK && mst != 0) st = mst;
         if (st != ST_OK) { klu_device_destroy(N->dev); delete N; return (b200s_status)st; }
     }

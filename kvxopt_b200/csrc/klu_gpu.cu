@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <chrono>
 
 namespace b200s {
 
@@ -1028,6 +1029,8 @@ public:
         return ST_OK;
     }
     int init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S);
+    int ensure_solve_levels(int tr);
+    const KluPlan* hP = nullptr; const KluNumeric* hN = nullptr; const KluSymbolic* hS = nullptr;   // owned by the numeric object
     int ensure_batch(int b);
     int enqueue_refactor(const double* dv, long long ldv, cudaEvent_t after_transpose);
     int refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host);
@@ -1046,17 +1049,20 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     PD.n = P.n; PD.nlevels = P.nlevels; PD.gstride = (long long)P.nslots * 32;
     std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
         updd(P.upd_dest.begin(), P.upd_dest.end()), rowptr(P.rowptr.begin(), P.rowptr.end());
-    if ((rc = up(&PD.level_ptr, P.level_ptr))) return rc;
-    if ((rc = up(&PD.level_cols, P.level_cols))) return rc;
+    use_wave = P.wave_ok && P.max_col_len <= KLU_WAVE_ROWS;
     if ((rc = up(&PD.udiag_slot, P.udiag_slot))) return rc;
     if ((rc = up(&PD.lslot0, P.lslot0))) return rc;
-    if ((rc = up(&PD.upd_uslot, P.upd_uslot))) return rc;
-    if ((rc = up(&PD.upd_lslot, P.upd_lslot))) return rc;
-    if ((rc = up(&PD.upd_cnt, P.upd_cnt))) return rc;
-    if ((rc = up(&PD.dest, P.dest))) return rc;
     if ((rc = up(&PD.cbeg, cbeg))) return rc;
-    if ((rc = up(&PD.upd_ptr, updp))) return rc;
-    if ((rc = up(&PD.upd_dest, updd))) return rc;
+    if (!use_wave) {          // update lists and level schedule: only the level-schedule kernel reads them
+        if ((rc = up(&PD.level_ptr, P.level_ptr))) return rc;
+        if ((rc = up(&PD.level_cols, P.level_cols))) return rc;
+        if ((rc = up(&PD.upd_uslot, P.upd_uslot))) return rc;
+        if ((rc = up(&PD.upd_lslot, P.upd_lslot))) return rc;
+        if ((rc = up(&PD.upd_cnt, P.upd_cnt))) return rc;
+        if ((rc = up(&PD.dest, P.dest))) return rc;
+        if ((rc = up(&PD.upd_ptr, updp))) return rc;
+        if ((rc = up(&PD.upd_dest, updd))) return rc;
+    }
     lu_slots = P.lu_slots;
     {
         WD.nwaves = (int)P.wave_col0.size() - 1;
@@ -1065,7 +1071,6 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         std::vector<long long> wbp(P.wbatch_ptr.begin(), P.wbatch_ptr.end()), wlp(P.wblob_ptr.begin(), P.wblob_ptr.end());
         if ((rc = up(&WD.wbatch_ptr, wbp))) return rc;
         if ((rc = up(&WD.wblob_ptr, wlp))) return rc;
-        if ((rc = up(&WD.batch_rowslot, P.batch_rowslot))) return rc;
         if ((rc = up(&WD.wave_rowsrc, P.wave_rowsrc))) return rc;
         {
             std::vector<int> bsp(P.bseg_ptr.begin(), P.bseg_ptr.end());
@@ -1085,7 +1090,6 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         const int* er;
         if ((rc = up(&er, ent_row))) return rc;
         d_ent_row = (int*)er;
-        use_wave = P.wave_ok && P.max_col_len <= KLU_WAVE_ROWS;
         WD.spine0 = use_wave ? P.spine0 : P.n;
         spine_nd = use_wave ? P.spine_nd : 0;
         if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;
@@ -1108,17 +1112,22 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     if ((rc = up(&tmp_l, rowptr))) return rc; d_rowptr = (long long*)tmp_l;
     if ((rc = up(&d_Pnum, N.Pnum))) return rc;
     if ((rc = up(&d_Q, S.Q))) return rc;
-    for (int tr = 0; tr < 2; tr++) {
-        KluSolveLvlH H;
-        build_solve_levels(S, N, P, tr != 0, H);
-        SL[tr].n = P.n; SL[tr].nlev = H.nlev;
-        if ((rc = up(&SL[tr].lvl_ptr, H.lvl_ptr))) return rc;
-        if ((rc = up(&SL[tr].rec, H.rec))) return rc;
-        if ((rc = up(&SL[tr].tslot, H.tslot))) return rc;
-        if ((rc = up(&SL[tr].tsrc, H.tsrc))) return rc;
-        if ((rc = up(&SL[tr].extra, H.extra))) return rc;
-        if ((rc = up(&SL[tr].mode, H.mode))) return rc;
-    }
+    hP = &P; hN = &N; hS = &S;       // the solve schedules are built at the first solve of each kind (ensure_solve_levels)
+    return ST_OK;
+}
+
+int KluDevice::ensure_solve_levels(int tr) {
+    if (SL[tr].n == n && SL[tr].lvl_ptr) return ST_OK;
+    int rc;
+    KluSolveLvlH H;
+    build_solve_levels(*hS, *hN, *hP, tr != 0, H);
+    SL[tr].n = n; SL[tr].nlev = H.nlev;
+    if ((rc = up(&SL[tr].lvl_ptr, H.lvl_ptr))) return rc;
+    if ((rc = up(&SL[tr].rec, H.rec))) return rc;
+    if ((rc = up(&SL[tr].tslot, H.tslot))) return rc;
+    if ((rc = up(&SL[tr].tsrc, H.tsrc))) return rc;
+    if ((rc = up(&SL[tr].extra, H.extra))) return rc;
+    if ((rc = up(&SL[tr].mode, H.mode))) return rc;
     return ST_OK;
 }
 
@@ -1303,6 +1312,7 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
         db = dB;
     }
     {
+        { const int rcl = ensure_solve_levels(trans ? 1 : 0); if (rcl) return rcl; }
         const KluSolveLvlD& L_ = SL[trans ? 1 : 0];
         const dim3 tg((unsigned)((n + 31) / 32), (unsigned)(Bp / 32), (unsigned)nrhs);
         const int nb = (int)batch_;
