@@ -30,3 +30,21 @@ Fs = klu.symbolic(K); Fn = klu.numeric(K, Fs)
 vals = K.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(33, K.nnz)))
 klu.refactor_batch(Fn, vals); B = rng.standard_normal((33, 1, K.shape[0])); klu.solve_batch(Fn, B)
 print("klu ok", flush=True)
+# streaming refactor, LDL' semantics, device KKT solver
+klu.refactor_batch_begin(Fn, vals); klu.refactor_batch_begin(Fn, vals); klu.refactor_batch_end(Fn); klu.refactor_batch_end(Fn)
+cholmod.options["supernodal"] = 0
+Al, perm = lap(8); F = cholmod.symbolic(Al, p=perm); cholmod.numeric(Al, F)
+for s in (2, 3, 4, 5, 6):
+    X = np.ones((Al.shape[0], 2), order="F"); cholmod.solve(F, X, sys=s)
+cholmod.getfactor(F)
+del cholmod.options["supernodal"]
+from kvxopt_b200 import kkt
+nk, mk, pk = 60, 150, 5
+Gk = sp.vstack([sp.identity(nk), sp.random(mk - nk, nk, density=0.1, random_state=rng)]).tocsc()
+Ak = (sp.random(pk, nk, density=0.3, random_state=rng) + sp.csc_matrix((np.ones(pk), (np.arange(pk), np.arange(pk))), shape=(pk, nk))).tocsc()
+Mk = sp.random(nk, nk, density=0.1, random_state=rng); Hk = (Mk @ Mk.T + 0.1 * sp.identity(nk)).tocsc()
+fac = kkt.chol2(Gk, {"l": mk, "q": [], "s": []}, Ak)
+for rep in range(2):
+    sol = fac({"di": 1.0 / rng.uniform(0.3, 3.0, mk)}, sp.tril(Hk).tocsc())
+    x, y, zz = rng.standard_normal(nk), rng.standard_normal(pk), rng.standard_normal(mk); sol(x, y, zz)
+print("streaming + ldl + kkt ok", flush=True)
