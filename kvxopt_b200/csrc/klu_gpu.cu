@@ -954,6 +954,21 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
                 v[(long long)t * Bp] = acc;
             }
         }
+        // the factor rows of this warp's first task of the next level are static: pull them into L2 while the level's
+        // barrier is pending (lane q holds term q's slot), so that the dependent chain of the next level starts from L2
+        if (haveN && rN.y + lane < rN.z) {
+            const double* lrow = lu - lane + (long long)psN * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(lrow));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(lrow + 16));
+            const double* vrow = v - lane + (long long)pjN * Bp;          // the right-hand-side rows the terms read
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + 16));
+        }
+        if (haveN && lane == 0 && rN.w >= 0) {
+            const double* drow = lu + (long long)rN.w * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(drow));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(drow + 16));
+        }
         r = rN; ps = psN; pj = pjN; ex = exN; have = haveN;
         __syncthreads();
     }
