@@ -41,6 +41,7 @@ def _free_numeric(capsule_addr):             # free_klu_d_numeric, klu.c:63-72
     try:
         ptr = _raw_GetPointer(capsule_addr, _NAME_NUM)
         if ptr:
+            _pending.pop(int(ptr), None)         # batches begun and never ended die with the object
             fn["b200s_klu_free_numeric"](ptr)
     except Exception:
         pass
@@ -277,13 +278,13 @@ def refactor_batch_begin(Fn, values):
     st = fn["b200s_klu_refactor_batch_begin"](hn, L.ptr_f64(values), values.shape[0], values.shape[1])
     if st != L.OK:
         _raise_status(st)
-    _pending.setdefault(hn.value if hasattr(hn, "value") else int(hn), []).append(values.shape[0])
+    _pending.setdefault(_key(hn), []).append(values.shape[0])
 
 
 def refactor_batch_end(Fn, check=True):
     """Wait for the oldest batch begun with refactor_batch_begin; returns its per-matrix status array."""
     hn = _capsule_ptr(Fn, _NAME_NUM, "F is not the KLU numeric factor of a 'd' matrix", "F")
-    q = _pending.get(hn.value if hasattr(hn, "value") else int(hn), [])
+    q = _pending.get(_key(hn), [])
     if not q:
         raise ValueError("no batch in flight")
     batch = q.pop(0)
@@ -297,6 +298,10 @@ def refactor_batch_end(Fn, check=True):
 
 
 _pending = {}
+
+
+def _key(h):
+    return int(h.value) if hasattr(h, "value") else int(h)
 
 
 def solve_batch(Fn, B, trans="N"):
