@@ -529,12 +529,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
         // of the super-block); mode 5: "far" update after the last panel of a super-block: all column tiles right of
         // it with K = the whole super-block (up to 512), so C is read and written once per super-block
         const int nrt = (nr + BT - 1) / BT;
-        int cj = 2 * (kb + 1) + (mode == 3 ? 2 : 0);
+        // mode 6: far update without the column tiles of the NEXT super-block (those are mode 5 with a short grid: they
+        // gate the next panels and run first; the rest overlaps the next super-block's latency-bound panel kernels)
+        int cj = 2 * (kb + 1) + (mode == 3 ? 2 : 0) + (mode == 6 ? 2 * SUPER_NB : 0);
         while (t >= nrt - (cj >> 1)) { t -= nrt - (cj >> 1); cj++; }
         const int ti = (cj >> 1) + t;
         rowI = ti * BT; rowJ = cj * BTN;
         k0 = kb * NB; K = min(NB, nc - k0);
-        if (mode == 5) { k0 = (kb / SUPER_NB) * SUPER_NB * NB; K = (kb + 1) * NB - k0; }
+        if (mode == 5 || mode == 6) { k0 = (kb / SUPER_NB) * SUPER_NB * NB; K = (kb + 1) * NB - k0; }
         C = L + f.loff + rowI + (long long)rowJ * ld; ldc = ld;
         crows = min(BT, nr - rowI); ccols = min(BTN, nc - rowJ);
         lo = 0;
@@ -1109,6 +1111,7 @@ struct LevelSched {
     std::vector<Launch> panel, upd;   // per block step kb (upd = all trailing column tiles)
     std::vector<Launch> updA, updB;   // lookahead split of upd: next block column / the rest
     std::vector<Launch> updN, updF;   // two-level update: near (inside the super-block, K = 128) / far (K = super-block)
+    std::vector<Launch> updFA, updFB; // far split: column tiles of the next super-block / the rest (look-ahead)
     Launch syrk;
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
     Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
@@ -1204,8 +1207,13 @@ int CholDevice::init() {
     CUDA_TRY(cudaFree(0));
     lap("context");
     use_graphs = getenv("B200S_NO_GRAPH") == nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    {   // the main stream carries the latency-bound panel chain: its CTAs must get the SM slots that the bulk update
+        // kernels on stream2 free up, ahead of that kernel's own queued CTAs
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&evP, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
@@ -1295,6 +1303,8 @@ int CholDevice::init() {
         LS.updB.resize(maxblk);
         LS.updN.resize(maxblk);
         LS.updF.resize(maxblk);
+        LS.updFA.resize(maxblk);
+        LS.updFB.resize(maxblk);
         auto emit = [&](Launch& la, const std::vector<int>& fr, const std::vector<int>& cnt) {
             la.goff = (int)sched.size();
             la.ng = (int)fr.size();
@@ -1345,7 +1355,7 @@ int CholDevice::init() {
             max_solve_ctas = std::max(max_solve_ctas, LS.sbwd[kb].ctas);
         }
         for (int kb = 0; kb < maxblk; kb++) {
-            std::vector<int> fr, cp, fu, cu, fuA, cuA, fuB, cuB, fuN, cuN, fuF, cuF;
+            std::vector<int> fr, cp, fu, cu, fuA, cuA, fuB, cuB, fuN, cuN, fuF, cuF, fuFA, cuFA, fuFB, cuFB;
             // panel CTAs: one per front for the diagonal block + solver CTAs that each factor the block redundantly
             // and then walk over several 64-row tiles; the solver CTAs of a launch are capped near one wave (148 SMs)
             long long tiles_total = 0;
@@ -1384,10 +1394,16 @@ int CholDevice::init() {
                 const int sb_end = (kb / SUPER_NB + 1) * SUPER_NB;          // first block column outside
                 long long tilesN = 0, tilesF = 0;
                 for (int cj = 2 * (kb + 1); cj < std::min(ncolt, 2 * sb_end); cj++) tilesN += nrt - (cj >> 1);
+                long long tilesFA = 0;
                 if (kb + 1 == sb_end)
-                    for (int cj = 2 * sb_end; cj < ncolt; cj++) tilesF += nrt - (cj >> 1);
+                    for (int cj = 2 * sb_end; cj < ncolt; cj++) {
+                        tilesF += nrt - (cj >> 1);
+                        if (cj < 2 * (sb_end + SUPER_NB)) tilesFA += nrt - (cj >> 1);
+                    }
                 if (tilesN > 0) { fuN.push_back(s); cuN.push_back((int)tilesN); }
                 if (tilesF > 0) { fuF.push_back(s); cuF.push_back((int)tilesF); }
+                if (tilesFA > 0) { fuFA.push_back(s); cuFA.push_back((int)tilesFA); }
+                if (tilesF - tilesFA > 0) { fuFB.push_back(s); cuFB.push_back((int)(tilesF - tilesFA)); }
             }
             emit(LS.panel[kb], fr, cp);
             emit(LS.upd[kb], fu, cu);
@@ -1395,6 +1411,8 @@ int CholDevice::init() {
             emit(LS.updB[kb], fuB, cuB);
             emit(LS.updN[kb], fuN, cuN);
             emit(LS.updF[kb], fuF, cuF);
+            emit(LS.updFA[kb], fuFA, cuFA);
+            emit(LS.updFB[kb], fuFB, cuFB);
         }
         {
             std::vector<int> fr, cnt;
@@ -1511,9 +1529,29 @@ int CholDevice::factor_level(int l) {
             if (ln.ctas)
                 k_update<<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
                                                                         (int)kb, dF, dL, dW, downed);
-            if (lf.ctas)
+            if (lf.ctas && !lookahead)
                 k_update<<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
                                                                         (int)kb, dF, dL, dW, downed);
+            if (lf.ctas && lookahead) {
+                // Far update with look-ahead: the column tiles of the NEXT super-block (part A) run here and gate its
+                // panels; all other column tiles (part B, the bulk of the flops) run on stream2 under the next
+                // super-block's four panel + near-update steps, whose few latency-bound CTAs leave the GPU idle.
+                // Part A of the next far update touches tiles that this part B writes, so it waits for it.
+                const Launch& lfa = LS.updFA[kb];
+                const Launch& lfb = LS.updFB[kb];
+                if (lfb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));            // panels and near updates of this super-block
+                if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }
+                if (lfa.ctas)
+                    k_update<<<lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
+                                                                             (int)kb, dF, dL, dW, downed);
+                if (lfb.ctas) {
+                    CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
+                    k_update<<<lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
+                                                                              (int)kb, dF, dL, dW, downed);
+                    CUDA_TRY(cudaEventRecord(evB, stream2));
+                    pendingB = true;
+                }
+            }
             prof_end();
             continue;
         }
