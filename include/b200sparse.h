@@ -51,7 +51,10 @@ typedef struct b200s_chol b200s_chol;    /* opaque: symbolic plan + device-resid
 /* Mirrors the `cholmod.options` keys read by set_options (src/C/cholmod.c:87-129) plus the relaxed
  * supernode parameters CHOLMOD keeps in its Common object. */
 typedef struct {
-    int    supernodal;   /* only 2 (supernodal LL^T) is implemented; 0/1 are rejected with INVALID  */
+    int    supernodal;   /* 2, 1: supernodal LL^T.  0: LDL^T without pivoting (CHOLMOD's simplicial mode, cholmod.c:60-64):
+                            any symmetric matrix with nonzero pivots (quasi-definite KKT systems); the kernels compute
+                            P A P' = Lt S Lt', S = diag(+-1), and answer sys 1..6 / getfactor with L = Lt diag(Lt)^-1,
+                            D = S diag(Lt)^2; a zero pivot returns NOT_POSDEF with `minor`.  Other values: INVALID */
     int    nmethods;     /* 0: user perm if given else AMD; 1: user perm (must be given); 2: as 0   */
     int    postorder;    /* 1: etree postorder after the fill-reducing ordering (always applied to  */
                          /*    make supernodes contiguous; 0 is accepted and ignored)               */

@@ -69,9 +69,11 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
         if (opts->block > 0) F->opts.block = opts->block;
         for (int i = 0; i < 3; i++) { F->opts.nrelax[i] = opts->nrelax[i]; F->opts.zrelax[i] = opts->zrelax[i]; }
     }
-    // supernodal = 0 asks CHOLMOD for a simplicial LDL' factorization.  The engine always factors supernodally; for the
-    // positive definite matrices this path serves, L_ldl = L D^-1/2 and D = diag(L)^2, so the factor object answers with
-    // LDL' semantics (sys 2..6 scaled by the diagonal, getfactor with D on the diagonal, diag() refused) -- see chol_gpu.cu.
+    // supernodal = 0 asks CHOLMOD for a simplicial LDL' factorization (no pivoting; any symmetric matrix with nonzero
+    // pivots, e.g. quasi-definite KKT systems).  The engine always factors supernodally; in this mode the kernels compute
+    // the signed square-root form P A P' = Lt S Lt', S = diag(+-1), so L_ldl = Lt diag(Lt)^-1 and D = S diag(Lt)^2, and the
+    // factor object answers with LDL' semantics (sys 1..6 scaled by the diagonal, getfactor with D on the diagonal,
+    // diag() refused) -- see chol_gpu.cu.
     if (F->opts.supernodal < 0 || F->opts.supernodal > 2) {
         set_last_error("cholmod.options['supernodal'] must be 0, 1 or 2");
         delete F;
@@ -271,6 +273,12 @@ b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, dou
         int st = chol_device_download_L(F->dev, raw.data());
         if (st != ST_OK) return (b200s_status)st;
     }
+    std::vector<double> sign;
+    if (F->ldl && n > 0) {
+        try { sign.resize((size_t)n); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+        int st = chol_device_download_sign(F->dev, sign.data());
+        if (st != ST_OK) return (b200s_status)st;
+    }
     i64 nnz = 0;
     for (const Front& f : P.fronts)
         for (i32 c = 0; c < f.nc; c++)
@@ -284,14 +292,14 @@ b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, dou
     lp[0] = 0;
     for (const Front& f : P.fronts)
         for (i32 c = 0; c < f.nc; c++) {
-            // LDL' semantics (supernodal = 0): cholmod_factor_to_sparse returns L with D on its diagonal; from the LL'
-            // panels that is L(:,c) / l_cc below the diagonal and l_cc^2 on it
+            // LDL' semantics (supernodal = 0): cholmod_factor_to_sparse returns L with D on its diagonal; from the signed
+            // square-root panels (A = Lt S Lt') that is Lt(:,c) / l_cc below the diagonal and s_c l_cc^2 on it
             const double lcc = raw[f.loff + (i64)c * f.ld + c];
             for (i32 r = c; r < f.nr; r++) {
                 double v = raw[f.loff + (i64)c * f.ld + r];
                 if (r == c || v != 0.0) {
                     li[p] = P.rows[f.rowptr + r];
-                    lx[p] = !F->ldl ? v : (r == c ? lcc * lcc : v / lcc);
+                    lx[p] = !F->ldl ? v : (r == c ? sign[f.col0 + c] * lcc * lcc : v / lcc);
                     p++;
                 }
             }

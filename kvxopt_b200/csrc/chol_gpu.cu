@@ -180,23 +180,27 @@ __global__ void __launch_bounds__(256) k_extend_add(const EAItem* __restrict__ i
 // right-looking Cholesky of the first nc columns of an nr x nr lower-triangular matrix held in shared
 // memory (column-major, stride lds): potrf + trsm + syrk of a small front in one routine.
 // ---------------------------------------------------------------------------------------------------
-template <int THREADS>
+template <int THREADS, bool SGN>
 __device__ __forceinline__ void smem_partial_chol(double* S, int lds, int nr, int nc, int gcol0, int* minor,
-                                                  double dbound, bool record) {
+                                                  double dbound, bool record, double* __restrict__ sgn) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = THREADS / 32;
     for (int j = 0; j < nc; j++) {
         __syncthreads();
         const double d = S[j * lds + j];
-        if (!(d > 0.0) && record && tid == 0) atomicMin(minor, gcol0 + j);
-        double l = sqrt(d);
+        // SGN: signed factorization A = L S L', S = diag(+-1) (LDL' without pivoting: D = S diag(L)^2); only an exactly
+        // zero (or NaN) pivot stops it, as in CHOLMOD's simplicial LDL'
+        const double sj = (SGN && d < 0.0) ? -1.0 : 1.0;
+        const double ad = SGN ? fabs(d) : d;
+        if (!(ad > 0.0) && record && tid == 0) atomicMin(minor, gcol0 + j);
+        double l = sqrt(ad);
         if (dbound > 0.0 && l < dbound) l = dbound;
-        const double inv = 1.0 / l;
+        const double inv = SGN ? sj / l : 1.0 / l;
         for (int i = j + 1 + tid; i < nr; i += THREADS) S[j * lds + i] *= inv;
         __syncthreads();
-        if (tid == 0) S[j * lds + j] = l;
+        if (tid == 0) { S[j * lds + j] = l; if (SGN) sgn[gcol0 + j] = sj; }
         for (int c = j + 1 + warp; c < nr; c += NW) {
-            const double lc = S[j * lds + c];
+            const double lc = SGN ? sj * S[j * lds + c] : S[j * lds + c];
             if (lc != 0.0)
                 for (int i = c + lane; i < nr; i += 32) S[c * lds + i] -= S[j * lds + i] * lc;
         }
@@ -213,8 +217,9 @@ __device__ __forceinline__ void smem_partial_chol(double* S, int lds, int nr, in
 //      out through a counter; warp 0 first updates the next diagonal chunk and factors it while the others work on the
 //      rest (look-ahead), so step (1) is off the critical path after the first chunk.
 // Only the lower triangle of S is meaningful afterwards.
+template <bool SGN>
 __device__ __forceinline__ void chol_diag16(double* S, int d0, int lane, double* rdiag, double dbound, int w, int gcol0,
-                                            int* minor, bool record) {
+                                            int* minor, bool record, double* ssign) {
     const int r = lane & 15;
     double a[16];
 #pragma unroll
@@ -223,20 +228,25 @@ __device__ __forceinline__ void chol_diag16(double* S, int d0, int lane, double*
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         const double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) && j < bad) bad = j;
-        double inv = rsqrt(d);
-        double l = d * inv;
+        // SGN: A = L S L' with S = diag(+-1); rdiag carries the sign (1 / (s_j l_jj)), ssign[] the signs of the block
+        const double sj = (SGN && d < 0.0) ? -1.0 : 1.0;
+        const double ad = SGN ? fabs(d) : d;
+        if (!(ad > 0.0) && j < bad) bad = j;
+        double inv = rsqrt(ad);
+        double l = ad * inv;
         if (dbound > 0.0 && l < dbound) { l = dbound; inv = 1.0 / dbound; }
+        if (SGN) inv *= sj;
         const double lij = (r == j) ? l : a[j] * inv;
         if (r >= j) a[j] = lij;
+        const double mlij = SGN ? sj * lij : lij;
 #pragma unroll
         for (int c = 0; c < 16; c++)
             if (c > j) {                 // static after unrolling: keeps a[] in registers
                 const double u = __shfl_sync(0xffffffffu, lij, c);
-                const double t = fma(-lij, u, a[c]);
+                const double t = fma(-mlij, u, a[c]);
                 a[c] = (r >= c) ? t : a[c];
             }
-        if (lane == j) rdiag[j] = inv;
+        if (lane == j) { rdiag[j] = inv; if (SGN) ssign[d0 + j] = sj; }
     }
     if (lane < 16) {
 #pragma unroll
@@ -247,7 +257,8 @@ __device__ __forceinline__ void chol_diag16(double* S, int d0, int lane, double*
 }
 
 // C(8 x 32 strip: tile row ti, tile columns tj0..tj0+3, those in qmask) -= L(rows, c0..c0+15) L(cols, c0..c0+15)^T
-__device__ __forceinline__ void chol_strip(double* S, int c0, int t0, int ti, int tj0, int qmask, int lane) {
+template <bool SGN>
+__device__ __forceinline__ void chol_strip(double* S, int c0, int t0, int ti, int tj0, int qmask, int lane, const double* ssign) {
     double* Cp = S + (t0 + 8 * tj0 + 2 * (lane & 3)) * LDL + t0 + 8 * ti + (lane >> 2);
     const double* Ap = S + (c0 + (lane & 3)) * LDL + t0 + 8 * ti + (lane >> 2);
     const double* Bp = S + (c0 + (lane & 3)) * LDL + t0 + 8 * tj0 + (lane >> 2);
@@ -257,7 +268,7 @@ __device__ __forceinline__ void chol_strip(double* S, int c0, int t0, int ti, in
         if (qmask >> q & 1) { acc[q][0] = Cp[q * 8 * LDL]; acc[q][1] = Cp[q * 8 * LDL + LDL]; }
 #pragma unroll
     for (int k4 = 0; k4 < 16; k4 += 4) {
-        const double av = -Ap[k4 * LDL];
+        const double av = SGN ? -Ap[k4 * LDL] * ssign[c0 + k4 + (lane & 3)] : -Ap[k4 * LDL];
 #pragma unroll
         for (int q = 0; q < 4; q++)
             if (qmask >> q & 1) dmma884(acc[q][0], acc[q][1], av, Bp[k4 * LDL + 8 * q]);
@@ -267,8 +278,9 @@ __device__ __forceinline__ void chol_strip(double* S, int c0, int t0, int ti, in
         if (qmask >> q & 1) { Cp[q * 8 * LDL] = acc[q][0]; Cp[q * 8 * LDL + LDL] = acc[q][1]; }
 }
 
+template <bool SGN>
 __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, int gcol0, int* minor, double dbound,
-                                                   bool record, double* rdiag) {
+                                                   bool record, double* rdiag, double* ssign) {
     __shared__ int tctr;
     __shared__ unsigned char strip_ti[32], strip_tj[32];      // strips of the lower triangle of <= 14 x 14 tiles, by row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,7 +290,7 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
             for (int tj0 = 0; tj0 <= ti; tj0 += 4) { strip_ti[n] = (unsigned char)ti; strip_tj[n] = (unsigned char)tj0; n++; }
     }
     __syncthreads();
-    if (warp == 0) chol_diag16(S, 0, lane, rdiag, dbound, w, gcol0, minor, record);
+    if (warp == 0) chol_diag16<SGN>(S, 0, lane, rdiag, dbound, w, gcol0, minor, record, ssign);
     for (int c0 = 0; c0 < wpad; c0 += 16) {
         __syncthreads();                       // diagonal chunk c0 factored, trailing update of the previous chunk done
         const int t0 = c0 + 16;
@@ -292,7 +304,11 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
                 double v = xv[q];
 #pragma unroll
                 for (int p = 0; p < q; p++) v = fma(-xv[p], S[(c0 + p) * LDL + c0 + q], v);
-                xv[q] = v * rdiag[q];
+                xv[q] = SGN ? v * fabs(rdiag[q]) : v * rdiag[q];     // SGN: s_q l_rq = v / l_qq, which is what the sums need
+            }
+            if (SGN) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) xv[q] *= ssign[c0 + q];       // back to l_rq
             }
 #pragma unroll
             for (int q = 0; q < 16; q++) S[(c0 + q) * LDL + r] = xv[q];
@@ -303,10 +319,10 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
         int nstrips = 0;                       // strips with ti < nt: a prefix of the table
         for (int ti = 0; ti < nt; ti++) nstrips += (ti >> 2) + 1;
         if (warp == 0) {
-            chol_strip(S, c0, t0, 0, 0, 1, lane);
-            chol_strip(S, c0, t0, 1, 0, 3, lane);
+            chol_strip<SGN>(S, c0, t0, 0, 0, 1, lane, ssign);
+            chol_strip<SGN>(S, c0, t0, 1, 0, 3, lane, ssign);
             __syncwarp();
-            chol_diag16(S, t0, lane, rdiag, dbound, w, gcol0, minor, record);
+            chol_diag16<SGN>(S, t0, lane, rdiag, dbound, w, gcol0, minor, record, ssign);
         }
         int mt = 0;
         if (lane == 0) mt = atomicAdd(&tctr, 1);
@@ -317,7 +333,7 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
             const int ti = strip_ti[mt], tj0 = strip_tj[mt];
             int qmask = (ti - tj0 >= 3) ? 15 : ((1 << (ti - tj0 + 1)) - 1);
             if (ti < 2 && tj0 == 0) qmask = 0;             // the next diagonal chunk: done by warp 0 above
-            if (qmask) chol_strip(S, c0, t0, ti, tj0, qmask, lane);
+            if (qmask) chol_strip<SGN>(S, c0, t0, ti, tj0, qmask, lane, ssign);
             mt = __shfl_sync(0xffffffffu, nxt, 0);
         }
     }
@@ -325,10 +341,11 @@ __device__ __forceinline__ void smem_potrf_blocked(double* S, int w, int wpad, i
 }
 
 // K6: one CTA per small front (nr <= SMALL_NR): load panel + update matrix, factor, write back.
-template <int THREADS>
+template <int THREADS, bool SGN>
 __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__ list, const FrontD* __restrict__ F,
                                                          double* __restrict__ L, double* __restrict__ W, int* minor,
-                                                         double dbound, const unsigned char* __restrict__ owned) {
+                                                         double dbound, const unsigned char* __restrict__ owned,
+                                                         double* __restrict__ sgn) {
     extern __shared__ double S[];
     if (!owned[list[blockIdx.x]]) return;
     const FrontD f = F[list[blockIdx.x]];
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__
         int c = idx / m, r = idx - c * m;
         if (r >= c) S[(nc + c) * lds + nc + r] = U[(long long)(c + uo) * ldu + r + uo];
     }
-    smem_partial_chol<THREADS>(S, lds, nr, nc, f.col0, minor, dbound, true);
+    smem_partial_chol<THREADS, SGN>(S, lds, nr, nc, f.col0, minor, dbound, true, sgn);
     for (int idx = tid; idx < nr * nc; idx += THREADS) {
         int c = idx / nr, r = idx - c * nr;
         if (r >= c) P[(long long)c * f.ld + r] = S[c * lds + r];
@@ -361,10 +378,12 @@ __global__ void __launch_bounds__(THREADS) k_small_front(const int* __restrict__
 // and writes it back; every other CTA factors the same block redundantly in shared memory (no
 // inter-CTA dependency, no extra launch) and solves X L11^T = B for its 64-row tile.
 // ---------------------------------------------------------------------------------------------------
+template <bool SGN>
 __global__ void __launch_bounds__(256, 1) k_panel(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                   int ngroups, int kb, const FrontD* __restrict__ F,
                                                   double* __restrict__ L, double* __restrict__ diag_scratch,
-                                                  int* minor, double dbound, const unsigned char* __restrict__ owned) {
+                                                  int* minor, double dbound, const unsigned char* __restrict__ owned,
+                                                  double* __restrict__ sgn) {
     extern __shared__ double sm[];
     double* Ls = sm;
     double* Xs = Ls + NB * LDL;
@@ -396,8 +415,10 @@ __global__ void __launch_bounds__(256, 1) k_panel(const __grid_constant__ SolveG
     cp_async_commit();
     cp_async_wait<0>();
     __shared__ double rdiag16[16];
-    smem_potrf_blocked(Ls, w, wpad, f.col0 + k0, minor, dbound, r == 0, rdiag16);
+    __shared__ double ssign[NB];
+    smem_potrf_blocked<SGN>(Ls, w, wpad, f.col0 + k0, minor, dbound, r == 0, rdiag16, ssign);
     if (r == 0) {
+        if (SGN && tid < w) sgn[f.col0 + k0 + tid] = ssign[tid];
         // The factored block goes to scratch, not to the panel: CTAs of this launch that start later still
         // have to read the UNfactored block.  k_diag_writeback copies it into the panel after this launch.
         double* dst = diag_scratch + (size_t)g * NB * NB;
@@ -406,6 +427,15 @@ __global__ void __launch_bounds__(256, 1) k_panel(const __grid_constant__ SolveG
             if (rr >= c) dst[c * NB + rr] = Ls[c * LDL + rr];
         }
         return;
+    }
+    if (SGN) {
+        // signed factorization A = L S L': the tile solve is X (L11 S)^T = B, i.e. the same substitution against the
+        // column-signed block
+        for (int idx = tid; idx < wpad * wpad; idx += 256) {
+            const int c = idx / wpad, rr = idx - c * wpad;
+            if (rr >= c) Ls[c * LDL + rr] *= ssign[c];
+        }
+        __syncthreads();
     }
     if (tid < wpad) rinv[tid] = 1.0 / Ls[tid * LDL + tid];
     // this CTA solves the 64-row tiles r-1, r-1+nsolve, ... of the rows below the diagonal block with the factor
@@ -506,10 +536,12 @@ __device__ __forceinline__ void load_tile_async(double* dst, const double* __res
 
 // tile decode shared by host counting and the kernel: column tiles of 64, row tiles of 128, lower triangle only:
 // column tile cj pairs with row tiles ti >= cj/2
+template <bool SGN>
 __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                            int ngroups, int mode, int kb, const FrontD* __restrict__ F,
                                                            double* __restrict__ L, double* __restrict__ W,
-                                                           const unsigned char* __restrict__ owned) {
+                                                           const unsigned char* __restrict__ owned,
+                                                           const double* __restrict__ sgn) {
     extern __shared__ double sm[];
     double* As = sm;                          // [STAGES][BK][LDT]    rows of the tile's row block (128)
     double* Bs = sm + STAGES * BK * LDT;      // [STAGES][BK][LDTB]   rows of the tile's column block (64)
@@ -605,11 +637,20 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
         cp_async_commit();
         const double* as = As + (kt % STAGES) * BK * LDT;
         const double* bs = Bs + (kt % STAGES) * BK * LDTB;
+        // SGN (A = L S L'): C -= A_i S A_j^T, the column signs ride on the negation of the A_j fragment.  The sign array
+        // is padded by BK entries, columns beyond K multiply zero-filled operands.
+        double ns[BK / 4];
+        if (SGN) {
+#pragma unroll
+            for (int kk = 0; kk < BK; kk += 4) ns[kk / 4] = -sgn[f.col0 + k0 + kt * BK + kk + (lane & 3)];
+        }
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             double am[4], bn[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) am[i] = -bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)];
+            for (int i = 0; i < 4; i++)
+                am[i] = SGN ? ns[kk / 4] * bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)]
+                            : -bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)];
 #pragma unroll
             for (int j = 0; j < 4; j++) bn[j] = as[(kk + (lane & 3)) * LDT + wr + j * 8 + (lane >> 2)];
 #pragma unroll
@@ -1081,13 +1122,17 @@ __global__ void k_copy_cols(const double* __restrict__ S, long long lds, double*
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) d[k] = s[k];
 }
 // LDL' semantics on top of the LL' factor (cholmod.options['supernodal'] = 0, reference src/C/cholmod.c:60-64,437-439):
-// for a positive definite matrix L_ldl = L D^-1/2 and D = diag(L)^2, so the LDL' systems are the LL' sweeps with a
-// diagonal scaling before or after.  mode 1: x *= l, 2: x /= l, 3: x /= l^2   (l = diag of the LL' factor, permuted order)
-__global__ void k_scale_by_diag(double* __restrict__ x, long long ldx, const double* __restrict__ dg, int n, int mode) {
+// the engine factors P A P' = Lt S Lt' with S = diag(+-1) (signed square-root form of LDL' without pivoting, any symmetric
+// matrix whose pivots are nonzero: positive definite, quasi-definite KKT systems, ...).  L_ldl = Lt diag(Lt)^-1 and
+// D = S diag(Lt)^2, so the LDL' systems are the Lt sweeps with a diagonal scaling before, between or after.
+// mode 1: x *= l, 2: x *= s / l, 3: x *= s / l^2, 4: x *= s   (l = diag(Lt), s = signs, both in permuted order)
+__global__ void k_scale_by_diag(double* __restrict__ x, long long ldx, const double* __restrict__ dg,
+                                const double* __restrict__ sg, int n, int mode) {
     double* col = x + (long long)blockIdx.y * ldx;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (mode == 4) { col[i] *= sg[i]; continue; }
         const double l = dg[i];
-        col[i] = mode == 1 ? col[i] * l : mode == 2 ? col[i] / l : col[i] / (l * l);
+        col[i] = mode == 1 ? col[i] * l : mode == 2 ? sg[i] * col[i] / l : sg[i] * col[i] / (l * l);
     }
 }
 
@@ -1162,7 +1207,7 @@ public:
         pool_free(dL); pool_free(dW); pool_free(dval); pool_free(dT); pool_free(dX); pool_free(dBstage); pool_free(damap); pool_free(dF);
         pool_free(drows); pool_free(drel); pool_free(dchild); pool_free(dperm); pool_free(dlevel_fronts);
         pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(ddiag); pool_free(dpart); pool_free(downed);
-        pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL);
+        pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -1186,6 +1231,7 @@ public:
     int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false);
     bool ldl = false;             // LDL' semantics of sys 2..6 (supernodal = 0)
     double* ddiagL = nullptr;     // diagonal of L (permuted order), valid while diagL_valid
+    double* dsgn = nullptr;       // ldl: sign of every pivot (+-1, permuted order, padded), written by the factorization kernels
     bool diagL_valid = false;
     int ensure_solve_ws(i64 cols);
 };
@@ -1438,15 +1484,20 @@ int CholDevice::init() {
     lap("schedule build");
     if ((rc = upload(&dsched, sched.data(), sched.size()))) return rc;
     if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
-    CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
-    CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
+    CUDA_TRY(cudaFuncSetAttribute(k_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
+    CUDA_TRY(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
     CUDA_TRY(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SDIAG));
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BDIAG));
     CUDA_TRY(cudaFuncSetAttribute(k_fwd_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FUPD));
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUPD));
-    CUDA_TRY(cudaFuncSetAttribute(k_small_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(k_small_front<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((SMALL_NR | 1) * SMALL_NR * sizeof(double))));
-    CUDA_TRY(cudaFuncSetAttribute(k_small_front<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
+    CUDA_TRY(cudaFuncSetAttribute(k_small_front<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
+    CUDA_TRY(cudaFuncSetAttribute(k_small_front<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((SMALL_NR | 1) * SMALL_NR * sizeof(double))));
+    CUDA_TRY(cudaFuncSetAttribute(k_small_front<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
     lap("schedule upload + attributes");
     return ST_OK;
 }
@@ -1457,6 +1508,12 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
     numeric = false;
     minv_valid = false;
     diagL_valid = false;
+    if (ldl && !dsgn) {
+        const size_t cnt = (size_t)P.n + 2 * NB;          // k_update reads up to BK entries past a front's last column
+        std::vector<double> ones(cnt, 1.0);
+        CUDA_TRY(pool_malloc((void**)&dsgn, cnt * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(dsgn, ones.data(), cnt * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     const double* dv = val;
     if (!on_device) {
@@ -1497,14 +1554,11 @@ int CholDevice::factor_level(int l) {
     }
     prof_begin(1);
     if (LS.small_cnt[0])
-        k_small_front<64><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(
-            dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed);
+        { if (ldl) k_small_front<64, true><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed, dsgn); else k_small_front<64, false><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed, nullptr); }
     if (LS.small_cnt[1])
-        k_small_front<128><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(
-            dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed);
+        { if (ldl) k_small_front<128, true><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed, dsgn); else k_small_front<128, false><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed, nullptr); }
     if (LS.small_cnt[2])
-        k_small_front<256><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(
-            dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed);
+        { if (ldl) k_small_front<256, true><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed, dsgn); else k_small_front<256, false><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed, nullptr); }
     prof_end();
     // Lookahead of depth one: after panel kb, part A of its trailing update (the next block column only) runs on
     // the main stream, then panel kb+1; part B (all other column tiles) runs on stream2 concurrently with panel
@@ -1517,8 +1571,9 @@ int CholDevice::factor_level(int l) {
         const Launch& lp = LS.panel[kb];
         if (lp.ctas) {
             prof_begin(2);
-            k_panel<<<lp.ctas, 256, SMEM_PANEL, stream>>>(sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
-                                                          dF, dL, ddiag, dminor, opts.dbound, downed);
+            { if (ldl) k_panel<true><<<lp.ctas, 256, SMEM_PANEL, stream>>>(sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
+                                                          dF, dL, ddiag, dminor, opts.dbound, downed, dsgn); else k_panel<false><<<lp.ctas, 256, SMEM_PANEL, stream>>>(sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
+                                                          dF, dL, ddiag, dminor, opts.dbound, downed, nullptr); }
             k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag, downed);
             prof_end();
         }
@@ -1527,11 +1582,13 @@ int CholDevice::factor_level(int l) {
             const Launch& lf = LS.updF[kb];
             prof_begin(3);
             if (ln.ctas)
-                k_update<<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
-                                                                        (int)kb, dF, dL, dW, downed);
+                { if (ldl) k_update<true><<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
+                                                                        (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
+                                                                        (int)kb, dF, dL, dW, downed, nullptr); }
             if (lf.ctas && !lookahead)
-                k_update<<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
-                                                                        (int)kb, dF, dL, dW, downed);
+                { if (ldl) k_update<true><<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
+                                                                        (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
+                                                                        (int)kb, dF, dL, dW, downed, nullptr); }
             if (lf.ctas && lookahead) {
                 // Far update with look-ahead: the column tiles of the NEXT super-block (part A) run here and gate its
                 // panels; all other column tiles (part B, the bulk of the flops) run on stream2 under the next
@@ -1542,12 +1599,14 @@ int CholDevice::factor_level(int l) {
                 if (lfb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));            // panels and near updates of this super-block
                 if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }
                 if (lfa.ctas)
-                    k_update<<<lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
-                                                                             (int)kb, dF, dL, dW, downed);
+                    { if (ldl) k_update<true><<<lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
+                                                                             (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
+                                                                             (int)kb, dF, dL, dW, downed, nullptr); }
                 if (lfb.ctas) {
                     CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-                    k_update<<<lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
-                                                                              (int)kb, dF, dL, dW, downed);
+                    { if (ldl) k_update<true><<<lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
+                                                                              (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
+                                                                              (int)kb, dF, dL, dW, downed, nullptr); }
                     CUDA_TRY(cudaEventRecord(evB, stream2));
                     pendingB = true;
                 }
@@ -1559,8 +1618,9 @@ int CholDevice::factor_level(int l) {
             const Launch& lu = LS.upd[kb];
             if (lu.ctas) {
                 prof_begin(3);
-                k_update<<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
-                                                                        (int)kb, dF, dL, dW, downed);
+                { if (ldl) k_update<true><<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                                                                        (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                                                                        (int)kb, dF, dL, dW, downed, nullptr); }
                 prof_end();
             }
             continue;
@@ -1570,12 +1630,14 @@ int CholDevice::factor_level(int l) {
         if (lb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));             // panel kb is complete
         if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }   // part B of step kb-1
         if (la.ctas)
-            k_update<<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
-                                                                    (int)kb, dF, dL, dW, downed);
+            { if (ldl) k_update<true><<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
+                                                                    (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
+                                                                    (int)kb, dF, dL, dW, downed, nullptr); }
         if (lb.ctas) {
             CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-            k_update<<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
-                                                                     (int)kb, dF, dL, dW, downed);
+            { if (ldl) k_update<true><<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
+                                                                     (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
+                                                                     (int)kb, dF, dL, dW, downed, nullptr); }
             CUDA_TRY(cudaEventRecord(evB, stream2));
             pendingB = true;
         }
@@ -1583,8 +1645,9 @@ int CholDevice::factor_level(int l) {
     if (pendingB) CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0));
     if (LS.syrk.ctas) {
         prof_begin(3);
-        k_update<<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
-                                                                     LS.syrk.ng, 1, 0, dF, dL, dW, downed);
+        { if (ldl) k_update<true><<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+                                                                     LS.syrk.ng, 1, 0, dF, dL, dW, downed, dsgn); else k_update<false><<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+                                                                     LS.syrk.ng, 1, 0, dF, dL, dW, downed, nullptr); }
         prof_end();
     }
     CUDA_TRY(cudaGetLastError());
@@ -1713,12 +1776,12 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             continue;
         }
         if (sys == 6) {          // D x = b: D = I for LL', diag(L)^2 with LDL' semantics
-            if (pre) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, ddiagL, n, pre);
+            if (pre) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, ddiagL, dsgn, n, pre);
             continue;
         }
         if (perm_in) k_perm_gather<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dX, n, n);
-        if (pre) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, ddiagL, n, pre);
+        if (pre) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, ddiagL, dsgn, n, pre);
         const long long pstride = (long long)max_solve_ctas * NB;
         // the level sweeps are a fixed launch sequence (hundreds of short dependent kernels): captured once per
         // (columns, directions) into a CUDA graph and replayed
@@ -1738,6 +1801,8 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                         }
                     }
                 }
+            if (ldl && do_fwd && do_bwd)       // Lt S Lt' x = b: the signs sit between the two sweeps
+                k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, nullptr, dsgn, n, 4);
             if (do_bwd)
                 for (int l = P.nlevels - 1; l >= 0; l--) {
                     const LevelSched& LS = levels[l];
@@ -1754,7 +1819,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                         k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
                 }
         };
-        const int gkey = nc * 4 + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
+        const int gkey = nc * 8 + (ldl ? 4 : 0) + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
         if (!use_graphs) sweeps();
         else {
             auto it = solve_graphs.find(gkey);
@@ -1771,7 +1836,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             }
             CUDA_TRY(cudaGraphLaunch(it->second, stream));
         }
-        if (post) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, ddiagL, n, post);
+        if (post) k_scale_by_diag<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, ddiagL, dsgn, n, post);
         if (perm_out) k_perm_scatter<<<dim3(gx, nc), 256, 0, stream>>>(b, ldd, dperm, n, dX, n);
         else k_copy_cols<<<dim3(gx, nc), 256, 0, stream>>>(dX, n, b, ldd, n);
     }
@@ -1828,6 +1893,15 @@ int chol_device_download_L(CholDevice* d, double* L_host) {
 }
 void chol_device_set_profiling(CholDevice* d, bool on) { d->profiling = on; }
 void chol_device_set_ldl(CholDevice* d, bool on) { d->ldl = on; }
+int chol_device_download_sign(CholDevice* d, double* sign_host) {
+    const CholPlan& P = *d->plan;
+    if (P.n == 0) return ST_OK;
+    if (!d->ldl || !d->dsgn) { for (i64 i = 0; i < P.n; i++) sign_host[i] = 1.0; return ST_OK; }
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    CUDA_TRY(cudaMemcpy(sign_host, d->dsgn, P.n * sizeof(double), cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
 int chol_device_set_owned(CholDevice* d, const unsigned char* owned) { return d->set_owned(owned); }
 int chol_device_factor_begin(CholDevice* d, const double* val, bool on_device) { return d->factor_begin(val, on_device); }
 int chol_device_factor_level(CholDevice* d, int level) { return d->factor_level(level); }

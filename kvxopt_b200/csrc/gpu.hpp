@@ -31,6 +31,7 @@ void* chol_device_stream(CholDevice* d);      // cudaStream_t
 int  chol_device_diag(CholDevice* d, double* diag_host);
 int  chol_device_download_L(CholDevice* d, double* L_host);   // raw panel storage, plan.lsize doubles
 void chol_device_set_profiling(CholDevice* d, bool on);
+int chol_device_download_sign(CholDevice* d, double* sign_host);   // ldl: +-1 per pivot (permuted order)
 void chol_device_set_ldl(CholDevice* d, bool on);          // LDL' semantics for sys 2..6 (cholmod.options['supernodal'] = 0)
 // level-stepped factorization + front ownership: building blocks of the multi-GPU subtree-to-subcube driver
 int  chol_device_set_owned(CholDevice* d, const unsigned char* owned);

@@ -28,7 +28,7 @@ from .cholmod import _ccs, _dense_view, _is_kvx, _is_dense, _size, _values
 
 fn = L.fn
 
-__all__ = ["chol2", "qp_kktsolver", "lp_kktsolver"]
+__all__ = ["chol2", "ldl", "qp_kktsolver", "lp_kktsolver"]
 
 
 class _Handle:
@@ -146,6 +146,170 @@ def chol2(G, dims, A, mnl=0):
         return solve
 
     factor.info = lambda: info(state["handle"].h) if state["handle"] else {}
+    return factor
+
+
+class _CholHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            fn["b200s_chol_free"](self.h)
+            self.h = None
+
+
+def ldl(G, dims, A, mnl=0, kktreg=None):
+    """Sparse counterpart of misc.kkt_ldl(G, dims, A, mnl, kktreg) (reference src/python/misc.py:1055-1130): the
+    3 x 3 system
+
+        [ H           A'   G' W^-1 ]   [ ux   ]   [ bx      ]
+        [ A           0    0       ] * [ uy   ] = [ by      ]
+        [ W^-T G      0   -I       ]   [ W uz ]   [ W^-T bz ]
+
+    is factored as ONE sparse symmetric indefinite matrix, P K P' = L D L' without pivoting, by the supernodal engine in
+    its signed mode (the C ABI's `supernodal = 0`: what cholmod.options['supernodal'] = 0 selects), where the reference
+    forms K densely and calls LAPACK sytrf.  Returns factor(W, H=None, Df=None) -> solve(x, y, z) with the reference's
+    in-place contract (x, y, z := ux, uy, W uz).
+
+    Elimination order.  Without `kktreg` the (2,2) block is zero and, for linear programs, so is H: the order is
+    z first (pivots -1), then x by approximate minimum degree on the pattern of S = H + G'G (pivots = those of the
+    Cholesky factorization of H + G' W^-2 G), then y (pivots of -A S^-1 A'): every pivot is nonzero whenever the
+    reduced system of misc.kkt_chol2 is positive definite.  With `kktreg` (coneprog.py:430-434) K is quasi-definite, any
+    symmetric permutation has an LDL' factorization, and the fill-reducing ordering is applied to all of K.
+
+    Componentwise inequalities only (dims['q'], dims['s'] empty, mnl = 0), as kkt.chol2.  The pattern of K is analysed
+    once; each factor() sends only K's values; solve() is one host-buffer call.  No CPU fallback."""
+    import scipy.sparse as sp
+    if dims["q"] or dims["s"]:
+        raise ValueError("kvxopt_b200.kkt.ldl is implemented only for problems with no second-order or semidefinite "
+                         "cone constraints")
+    if mnl:
+        raise ValueError("kvxopt_b200.kkt.ldl does not support nonlinear constraints (mnl > 0)")
+    p, n = _size(A)
+    m = dims["l"]
+    if _size(G) != (m, n):
+        raise TypeError("G must be a %d x %d matrix" % (m, n))
+    Gp, Gi, Gx = _sparse_ccs(G, "G")
+    if p > 0:
+        Ap, Ai, Ax = _sparse_ccs(A, "A")
+    else:
+        Ap, Ai, Ax = np.zeros(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+    N = n + p + m
+    reg = float(kktreg) if kktreg else 0.0
+    state = {"handle": None, "Hnnz": None}
+
+    def _create(H):
+        if H is not None:
+            if _size(H) != (n, n):
+                raise TypeError("H must be a %d x %d matrix" % (n, n))
+            Hp, Hi, Hx = _sparse_ccs(H, "H")
+            Hc = np.repeat(np.arange(n, dtype=np.int64), np.diff(Hp))
+            keep = np.nonzero(Hi >= Hc)[0]                       # lower triangle, as sytrf reads it
+            Hi, Hc = Hi[keep], Hc[keep]
+            # every diagonal entry of the x block has a slot, stored or not (kktreg lands there)
+            have = np.zeros(n, dtype=bool); have[Hi[Hi == Hc]] = True
+        else:
+            keep = np.zeros(0, dtype=np.int64); Hi = Hc = keep; have = np.zeros(n, dtype=bool)
+        xdiag = np.nonzero(~have)[0]
+        Gc = np.repeat(np.arange(n, dtype=np.int64), np.diff(Gp))
+        Ac = np.repeat(np.arange(n, dtype=np.int64), np.diff(Ap))
+        rows = np.concatenate([Hi, xdiag, n + Ai, n + p + Gi, n + np.arange(p), n + p + np.arange(m)])
+        cols = np.concatenate([Hc, xdiag, Ac, Gc, n + np.arange(p), n + p + np.arange(m)])
+        K = sp.csc_matrix((np.arange(1, len(rows) + 1, dtype=np.float64), (rows, cols)), shape=(N, N))
+        K.sort_indices()
+        if K.nnz != len(rows):
+            raise ValueError("H, A and G must not hold duplicate entries")
+        src = K.data.astype(np.int64) - 1                        # CCS slot -> index into the concatenated value list
+        kp = np.ascontiguousarray(K.indptr, dtype=np.int64)
+        ki = np.ascontiguousarray(K.indices, dtype=np.int64)
+        if reg:
+            perm = None
+        else:
+            # fill-reducing order of the x block from the engine's host analysis of S = H + G'G
+            Gm = sp.csc_matrix((np.ones(len(Gi)), Gi, Gp), shape=(m, n))
+            Sp = (Gm.T @ Gm + sp.identity(n)).tocsc()
+            if len(Hi):
+                Hm = sp.csc_matrix((np.ones(len(Hi)), (Hi, Hc)), shape=(n, n))
+                Sp = (Sp + Hm + Hm.T).tocsc()
+            Sl = sp.tril(Sp).tocsc(); Sl.sort_indices()
+            hs = C.c_void_p()
+            st = fn["b200s_chol_analyze"](n, L.ptr_i64(np.ascontiguousarray(Sl.indptr, dtype=np.int64)),
+                                          L.ptr_i64(np.ascontiguousarray(Sl.indices, dtype=np.int64)), b"L", None, None,
+                                          C.byref(hs))
+            if st != L.OK:
+                _raise(st)
+            px = np.zeros(n, dtype=np.int64)
+            fn["b200s_chol_get_perm"](hs, L.ptr_i64(px))
+            fn["b200s_chol_free"](hs)
+            perm = np.ascontiguousarray(np.concatenate([n + p + np.arange(m), px, n + np.arange(p)]), dtype=np.int64)
+        o = L.CholOpts()
+        fn["b200s_chol_default_opts"](C.byref(o))
+        o.supernodal = 0                                         # signed LDL' (no pivoting)
+        h = C.c_void_p()
+        st = fn["b200s_chol_analyze"](N, L.ptr_i64(kp), L.ptr_i64(ki), b"L", L.ptr_i64(perm) if perm is not None else None,
+                                      C.byref(o), C.byref(h))
+        if st != L.OK:
+            _raise(st)
+        state.update(handle=_CholHandle(h), Hnnz=(len(keep) if H is not None else None), keep=keep, src=src, kp=kp, ki=ki,
+                     nxd=len(xdiag), Grow=Gi, vals=np.zeros(len(rows)), kv=np.zeros(len(rows)),
+                     u=np.zeros(N), hdiag=(np.nonzero(Hi == Hc)[0] if H is not None else None))
+
+    def factor(W, H=None, Df=None):
+        if Df is not None:
+            raise ValueError("kvxopt_b200.kkt.ldl does not support nonlinear constraints")
+        if state["handle"] is None:
+            _create(H)
+        if (H is None) != (state["Hnnz"] is None):
+            raise ValueError("H must be given in every call or in none")
+        di = np.ascontiguousarray(_vec(W["di"], m, "W['di']") if m else np.zeros(0), dtype=np.float64)
+        v = state["vals"]
+        k0 = 0
+        if H is not None:
+            Hx = (_values(H) if not _is_dense(H) else _sparse_ccs(H, "H")[2])[state["keep"]]
+            if len(Hx) != state["Hnnz"]:
+                raise ValueError("the sparsity pattern of H changed between calls")
+            v[:len(Hx)] = Hx
+            if reg:
+                v[state["hdiag"]] += reg
+            k0 = len(Hx)
+        v[k0:k0 + state["nxd"]] = reg; k0 += state["nxd"]
+        v[k0:k0 + len(Ax)] = Ax; k0 += len(Ax)
+        v[k0:k0 + len(Gx)] = di[state["Grow"]] * Gx; k0 += len(Gx)         # W^-T G = diag(di) G
+        v[k0:k0 + p] = -reg; k0 += p
+        v[k0:k0 + m] = -1.0 - reg
+        kv = state["kv"]
+        np.take(v, state["src"], out=kv)
+        handle = state["handle"]
+        minor = C.c_int64(0)
+        st = fn["b200s_chol_factorize"](handle.h, L.ptr_f64(kv), C.byref(minor))
+        if st == L.NOT_POSDEF:
+            raise ArithmeticError("zero pivot in the LDL' factorization of the KKT matrix (column %d)" % minor.value)
+        if st != L.OK:
+            _raise(st)
+        u = state["u"]
+
+        def solve(x, y, z):
+            xf = _vec(x, n, "x")
+            yf = _vec(y, p, "y") if p else None
+            zf = _vec(z, m, "z") if m else None
+            u[:n] = xf
+            if p:
+                u[n:n + p] = yf
+            if m:
+                u[n + p:] = di * zf
+            st2 = fn["b200s_chol_solve"](handle.h, 0, L.ptr_f64(u), 1, N)
+            if st2 != L.OK:
+                _raise(st2)
+            xf[:] = u[:n]
+            if p:
+                yf[:] = u[n:n + p]
+            if m:
+                zf[:] = u[n + p:]
+
+        return solve
+
+    factor._state = state          # assembled pattern / values, read by the host-side tests
     return factor
 
 

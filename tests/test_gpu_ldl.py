@@ -1,0 +1,188 @@
+"""Sparse LDL' without pivoting for symmetric indefinite (quasi-definite) matrices -- what
+cholmod.options['supernodal'] = 0 selects in the reference (src/C/cholmod.c:60-64, sys 1..6 at :437-439) -- and the
+sparse counterpart of the 'ldl' KKT solver (src/python/misc.py:1055-1130).  Parity against oracle/ldl_oracle.py with
+the same permutation, numpy, and the reference's own sytrf/sytrs answers (tests/golden/kkt_ldl_ref.npz).
+Tolerances are BASELINE.json's: relative backward error <= 1e-12, solution relative difference <= 1e-10."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import GOLD, lap3d, lower_ccs, rand_spd
+
+pytestmark = pytest.mark.gpu
+
+BERR_TOL = 1e-12
+XREL_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def cholmod():
+    from kvxopt_b200 import cholmod as m, _lib
+    assert _lib.device_count() > 0, "GPU tests need a CUDA device; there is no CPU fallback"
+    m.options["supernodal"] = 0
+    yield m
+    del m.options["supernodal"]
+
+
+def quasi_definite(E, F, dens, seed):
+    """[[E, B'], [B, -F]] with E, F positive definite"""
+    rng = np.random.default_rng(seed)
+    B = sp.random(F.shape[0], E.shape[0], density=dens, random_state=rng, format="csc")
+    return sp.bmat([[E, B.T], [B, -F]]).tocsc()
+
+
+def berr(A, X, B):
+    X = X.reshape(A.shape[0], -1); B = B.reshape(A.shape[0], -1)
+    return (np.linalg.norm(A @ X - B, axis=0) / (spla.norm(A, 1) * np.linalg.norm(X, axis=0) + np.linalg.norm(B, axis=0))).max()
+
+
+CASES = {
+    # small fronts only (one CTA per front in shared memory)
+    "small": lambda: quasi_definite(rand_spd(120, 0.05, 1), rand_spd(80, 0.05, 2), 0.03, 3),
+    # nested-dissection-like fill: fronts above 128 rows => panel kernel + DMMA updates, signs mixed inside blocks
+    "grid": lambda: quasi_definite((lap3d(9, 9, 9) + sp.identity(729)).tocsc(), (lap3d(8, 8, 4) + sp.identity(256)).tocsc(), 0.004, 4),
+    # one dense front of 700 columns: every block-column step, the near (K = 128) and far (K = 512) updates
+    "dense": lambda: quasi_definite(rand_spd(420, 0.6, 5), rand_spd(280, 0.6, 6), 0.5, 7),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_ldl_factor_and_systems_vs_oracle(cholmod, name):
+    from oracle import ldl_oracle
+    K = CASES[name]()
+    n = K.shape[0]
+    Kl = lower_ccs(K)
+    F = cholmod.symbolic(Kl); cholmod.numeric(Kl, F)
+    perm = cholmod.factor_perm(F)
+    Kd = K.toarray()
+    Lo, do, minor = ldl_oracle.ldl_nopivot(Kd[np.ix_(perm, perm)])
+    assert minor == n
+    nneg = int((np.linalg.eigvalsh(Kd) < 0).sum())
+    assert int((do < 0).sum()) == nneg                     # Sylvester: the oracle's inertia is the matrix's
+    Lf = cholmod.getfactor(F).toarray()                    # unit lower triangle with D on the diagonal
+    d = np.diag(Lf).copy()
+    assert int((d < 0).sum()) == nneg and nneg > 0
+    Lg = np.tril(Lf, -1) + np.eye(n)
+    scale = np.abs(do).max()
+    assert np.abs(d - do).max() <= 1e-10 * scale
+    assert np.abs(Lg - Lo).max() <= 1e-10 * max(1.0, np.abs(Lo).max())
+    R = Lg @ np.diag(d) @ Lg.T - Kd[np.ix_(perm, perm)]
+    assert np.abs(R).max() <= 1e-12 * np.abs(Kd).max() * max(1.0, np.abs(Lo).max() ** 2)
+    B = np.random.default_rng(0).standard_normal((n, 3))
+    for sys_ in range(9):
+        X = np.asfortranarray(B.copy())
+        cholmod.solve(F, X, sys=sys_)
+        want = ldl_oracle.solve_sys(Lo, do, perm, B, sys_)
+        assert np.linalg.norm(X - want) <= XREL_TOL * np.linalg.norm(want), (name, sys_)
+    X = np.asfortranarray(B.copy())
+    cholmod.linsolve(Kl, X)
+    assert berr(K, X, B) <= BERR_TOL
+    assert np.linalg.norm(X - np.linalg.solve(Kd, B)) <= XREL_TOL * np.linalg.norm(X)
+    with pytest.raises(ValueError):
+        cholmod.diag(F)                                    # cholmod.c:919-922
+    # refactorization with new values on the same symbolic object, bit-identical repeat
+    cholmod.numeric(Kl, F)
+    X2 = np.asfortranarray(B.copy()); cholmod.solve(F, X2)
+    X3 = np.asfortranarray(B.copy()); cholmod.solve(F, X3)
+    assert np.array_equal(X2, X3)
+
+
+def test_ldl_zero_pivot_raises(cholmod):
+    """a zero pivot is the one failure of LDL' without pivoting: ArithmeticError(k) (cholmod.c:376-380)"""
+    # second pivot 1 - 2 * 2 / 4 = 0 exactly, also in the engine's signed square-root form (sqrt(4) and 1/2 are exact)
+    K = sp.csc_matrix(np.array([[4.0, 2, 0], [2, 1.0, 1], [0, 1, 3.0]]))
+    with pytest.raises(ArithmeticError) as e:
+        F = cholmod.symbolic(lower_ccs(K), p=np.arange(3)); cholmod.numeric(lower_ccs(K), F)
+    assert e.value.args[0] == 1
+
+
+def test_ldl_large_quasi_definite_properties(cholmod):
+    """beyond the dense oracle's reach: 30^3 Laplacian block + constraints (n = 31 000), checked by backward error,
+    linearity and inertia (number of negative pivots = order of the negative block)"""
+    E = (lap3d(30, 30, 30) + 0.5 * sp.identity(27000)).tocsc()
+    Fm = (lap3d(20, 20, 10) + sp.identity(4000)).tocsc()
+    K = quasi_definite(E, Fm, 2e-4, 9)
+    Kl = lower_ccs(K)
+    n = K.shape[0]
+    F = cholmod.symbolic(Kl); cholmod.numeric(Kl, F)
+    B = np.random.default_rng(1).standard_normal((n, 2))
+    X = np.asfortranarray(B.copy()); cholmod.solve(F, X)
+    assert berr(K, X, B) <= BERR_TOL
+    Y = np.asfortranarray((2.0 * B[:, :1] - 3.0 * B[:, 1:2]).copy()); cholmod.solve(F, Y)
+    assert np.linalg.norm(Y - (2.0 * X[:, :1] - 3.0 * X[:, 1:2])) <= 1e-10 * np.linalg.norm(Y)
+    D = np.asfortranarray(np.ones((n, 1))); cholmod.solve(F, D, sys=6)
+    assert int((D < 0).sum()) == 4000
+
+
+def _kkt_case(prefix):
+    z = np.load(os.path.join(GOLD, "kkt_ldl_ref.npz"))
+    g = {k[len(prefix):]: z[k] for k in z.files if k.startswith(prefix)}
+    if prefix == "lp_":
+        b = np.load(os.path.join(GOLD, "boeing2_lp.npz"))
+        G = sp.csc_matrix((b["Gx"], b["Gi"], b["Gp"]), shape=tuple(b["G_size"]))
+        A = sp.csc_matrix((b["Ax"], b["Ai"], b["Ap"]), shape=tuple(b["A_size"]))
+        H = None
+    else:
+        sys.path.insert(0, GOLD)
+        from generators import qp_instance
+        H, _, G, _ = qp_instance(50, 40, 50)
+        A = sp.csc_matrix((0, H.shape[0]))
+    return G, A, H, g
+
+
+@pytest.mark.parametrize("prefix", ["lp_", "qp_"])
+def test_kkt_ldl_matches_reference_sytrf(prefix):
+    """kkt.ldl against the UNMODIFIED reference's misc.kkt_ldl (dense sytrf/sytrs), fixtures made by
+    tests/golden/make_kkt_ldl_fixtures.py"""
+    from kvxopt_b200 import kkt
+    G, A, H, g = _kkt_case(prefix)
+    m, n = G.shape
+    factor = kkt.ldl(G, {"l": m, "q": [], "s": []}, A)
+    W = {"d": g["d"].copy(), "di": 1.0 / g["d"]}
+    for _ in range(2):                                     # second pass: values-only refactorization
+        solve = factor(W, H)
+        x, y, zz = g["bx"].copy(), g["by"].copy(), g["bz"].copy()
+        solve(x, y, zz)
+        for got, want in ((x, g["ux"]), (y, g["uy"]), (zz, g["uz"])):
+            if len(want):
+                assert np.linalg.norm(got - want) <= XREL_TOL * np.linalg.norm(want)
+    # regularised variant (coneprog.py:430-434): unconstrained fill-reducing order on the quasi-definite matrix
+    from oracle import ldl_oracle
+    reg = 1e-6
+    solve = kkt.ldl(G, {"l": m, "q": [], "s": []}, A, kktreg=reg)(W, H)
+    x, y, zz = g["bx"].copy(), g["by"].copy(), g["bz"].copy()
+    solve(x, y, zz)
+    p = A.shape[0]
+    Kd = np.zeros((n + p + m, n + p + m))
+    if H is not None:
+        Kd[:n, :n] = H.toarray()
+    Kd[n:n + p, :n] = A.toarray(); Kd[n + p:, :n] = (1.0 / g["d"])[:, None] * G.toarray()
+    Kd = np.tril(Kd) + np.tril(Kd, -1).T
+    Kd[np.arange(n), np.arange(n)] += reg
+    Kd[np.arange(n, n + p + m), np.arange(n, n + p + m)] -= reg
+    Kd[np.arange(n + p, n + p + m), np.arange(n + p, n + p + m)] -= 1.0
+    want = np.linalg.solve(Kd, np.concatenate([g["bx"], g["by"], g["bz"] / g["d"]]))
+    got = np.concatenate([x, y, zz])
+    assert np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want)
+
+
+def test_boeing2_ipm_with_sparse_ldl(kvx):
+    """BASELINE configs[2] through the 'ldl'-style solver: same iteration count and objective as the reference's
+    dense 'ldl' (tests/golden/boeing2_lp.npz: 29 iterations, objective to 1e-8)"""
+    from kvxopt import matrix, spmatrix, solvers
+    from kvxopt_b200 import kkt
+    z = np.load(os.path.join(GOLD, "boeing2_lp.npz"))
+    def spm(p, i, x, size):
+        cols = np.repeat(np.arange(size[1]), np.diff(p))
+        return spmatrix(x.tolist(), i.tolist(), cols.tolist(), tuple(int(s) for s in size))
+    G = spm(z["Gp"], z["Gi"], z["Gx"], z["G_size"]); A = spm(z["Ap"], z["Ai"], z["Ax"], z["A_size"])
+    c, h, b = matrix(z["c"]), matrix(z["h"]), matrix(z["b"])
+    dims = {"l": G.size[0], "q": [], "s": []}
+    sol = solvers.conelp(c, G, h, dims, A, b, kktsolver=kkt.ldl(G, dims, A))
+    assert sol["status"] == "optimal"
+    assert sol["iterations"] == int(z["iters_ldl"])
+    assert abs(sol["primal objective"] - float(z["pobj_ldl"])) <= 1e-8 * abs(float(z["pobj_ldl"]))

@@ -302,3 +302,36 @@ def test_kkt_rejects_bad_input_and_needs_a_device_for_numeric_work():
         x = np.ones(2)
         assert fn["b200s_kkt_solve"](h, L.ptr_f64(x), None, L.ptr_f64(x)) == L.INVALID           # not factored
     fn["b200s_kkt_free"](h)
+
+
+def test_kkt_ldl_assembles_the_reference_matrix_and_fails_loudly_without_gpu():
+    """kkt.ldl (counterpart of misc.kkt_ldl, misc.py:1055-1130): the CCS values sent to the engine are the lower
+    triangle of [[H + reg, A', G'W^-1], [A, -reg, 0], [W^-T G, 0, -I - reg]]; without a GPU factor() raises (no fallback)"""
+    import scipy.sparse as sp
+    from kvxopt_b200 import kkt, _lib
+    rng = np.random.default_rng(3)
+    n, p, m = 12, 3, 20
+    G = sp.random(m, n, density=0.3, random_state=rng, format="csc")
+    A = sp.random(p, n, density=0.5, random_state=rng, format="csc")
+    Hh = sp.random(n, n, density=0.2, random_state=rng, format="csc"); H = (Hh + Hh.T + 5 * sp.identity(n)).tocsc()
+    di = np.exp(rng.standard_normal(m))
+    for reg in (None, 1e-3):
+        for Hm in (H, None):
+            factor = kkt.ldl(G, {"l": m, "q": [], "s": []}, A, kktreg=reg)
+            try:
+                factor({"di": di.copy()}, Hm)
+                assert _lib.device_count() > 0
+            except RuntimeError:
+                assert _lib.device_count() == 0
+            st = factor._state
+            K = sp.csc_matrix((st["kv"], st["ki"], st["kp"]), shape=(n + p + m, n + p + m)).toarray()
+            r = reg or 0.0
+            want = np.zeros_like(K)
+            if Hm is not None:
+                want[:n, :n] = np.tril(H.toarray())
+            want[np.arange(n), np.arange(n)] += r
+            want[n:n + p, :n] = A.toarray()
+            want[n + p:, :n] = di[:, None] * G.toarray()
+            want[np.arange(n, n + p), np.arange(n, n + p)] = -r
+            want[np.arange(n + p, n + p + m), np.arange(n + p, n + p + m)] = -1.0 - r
+            assert np.abs(K - want).max() == 0.0

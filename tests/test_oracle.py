@@ -1,6 +1,9 @@
 """Pins the CPU oracle (oracle/) to the reference: doc known answers (reference doc/source/spsolvers.rst),
 LAPACK solutions computed by the reference's own lapack.posv (tests/golden/posv_*.npz), the determinant
 of reference tests/test_sparse_solvers.py:298-313, and dense numpy factorizations."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -147,3 +150,35 @@ def test_klu_singular():
     A = sp.csc_matrix(np.array([[1.0, 2], [2, 4]]))
     with pytest.raises(ArithmeticError):
         KluOracle(2, A.indptr, A.indices, A.data)
+
+
+def test_ldl_oracle_against_numpy_and_reference_sytrf():
+    """oracle/ldl_oracle.py (LDL' without pivoting, misc.kkt_ldl for componentwise cones): L D L' = P A P', inertia,
+    numpy solutions, and the UNMODIFIED reference's sytrf/sytrs KKT answers (tests/golden/kkt_ldl_ref.npz)."""
+    from oracle import ldl_oracle
+    sys.path.insert(0, GOLD)
+    from generators import qp_instance
+    rng = np.random.default_rng(5)
+    E = rng.standard_normal((30, 30)); E = E @ E.T + 30 * np.eye(30)
+    Fm = rng.standard_normal((20, 20)); Fm = Fm @ Fm.T + 20 * np.eye(20)
+    B = rng.standard_normal((20, 30))
+    K = np.block([[E, B.T], [B, -Fm]])
+    perm = rng.permutation(50)
+    Lo, d, minor = ldl_oracle.ldl_nopivot(K[np.ix_(perm, perm)])
+    assert minor == 50 and int((d < 0).sum()) == 20
+    assert np.abs(Lo @ np.diag(d) @ Lo.T - K[np.ix_(perm, perm)]).max() <= 1e-12 * np.abs(K).max()
+    rhs = rng.standard_normal((50, 2))
+    assert np.linalg.norm(ldl_oracle.solve_sys(Lo, d, perm, rhs, 0) - np.linalg.solve(K, rhs)) <= 1e-12 * np.linalg.norm(rhs)
+    assert ldl_oracle.ldl_nopivot(np.array([[2.0, 1, 0], [1, 0.5, 1], [0, 1, 3.0]]))[2] == 1
+    z = np.load(os.path.join(GOLD, "kkt_ldl_ref.npz"))
+    b2 = np.load(os.path.join(GOLD, "boeing2_lp.npz"))
+    G = sp.csc_matrix((b2["Gx"], b2["Gi"], b2["Gp"]), shape=tuple(b2["G_size"])).toarray()
+    A = sp.csc_matrix((b2["Ax"], b2["Ai"], b2["Ap"]), shape=tuple(b2["A_size"])).toarray()
+    ux, uy, uz = ldl_oracle.kkt_ldl_lcone(G, A, None, 1.0 / z["lp_d"], z["lp_bx"], z["lp_by"], z["lp_bz"])
+    for got, want in ((ux, z["lp_ux"]), (uy, z["lp_uy"]), (uz, z["lp_uz"])):
+        assert np.linalg.norm(got - want) <= 1e-10 * np.linalg.norm(want)
+    P, _, Gq, _ = qp_instance(50, 40, 50)
+    ux, uy, uz = ldl_oracle.kkt_ldl_lcone(Gq.toarray(), np.zeros((0, 2000)), P.toarray(), 1.0 / z["qp_d"], z["qp_bx"],
+                                          z["qp_by"], z["qp_bz"])
+    for got, want in ((ux, z["qp_ux"]), (uz, z["qp_uz"])):
+        assert np.linalg.norm(got - want) <= 1e-10 * np.linalg.norm(want)
