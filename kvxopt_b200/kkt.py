@@ -283,6 +283,7 @@ def ldl(G, dims, A, mnl=0, kktreg=None):
         handle = state["handle"]
         minor = C.c_int64(0)
         st = fn["b200s_chol_factorize"](handle.h, L.ptr_f64(kv), C.byref(minor))
+        state["factors"] = state.get("factors", 0) + 1
         if st == L.NOT_POSDEF:
             raise ArithmeticError("zero pivot in the LDL' factorization of the KKT matrix (column %d)" % minor.value)
         if st != L.OK:
@@ -309,6 +310,16 @@ def ldl(G, dims, A, mnl=0, kktreg=None):
 
         return solve
 
+    def _info():
+        if state["handle"] is None:
+            return {}
+        inf = L.CholInfo()
+        fn["b200s_chol_info"](state["handle"].h, C.byref(inf))
+        return {"order": N, "nnz_L": inf.nnz_L, "flops": inf.flops, "nsuper": inf.nsuper, "max_front_rows": inf.max_front_rows,
+                "ms_analyze": inf.ms_analyze, "ms_factor_last": inf.ms_factor, "ms_solve_last": inf.ms_solve,
+                "factorizations": state.get("factors", 0)}
+
+    factor.info = _info
     factor._state = state          # assembled pattern / values, read by the host-side tests
     return factor
 

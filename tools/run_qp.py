@@ -54,6 +54,14 @@ if use_kkt:
     ks = kkt.qp_kktsolver(Pk, Gk)
     sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=ks)
     print("device KKT solver:", ks.info())
+elif mode in ("ldl", "ldlreg"):
+    # sparse LDL' of the 3 x 3 KKT system (counterpart of the reference's dense 'ldl'); ldlreg: kktreg = 1e-9, free ordering
+    from kvxopt_b200 import kkt
+    Pk, Gk = tosp(sp.tril(P)), tosp(G)
+    t0 = time.perf_counter()
+    f3 = kkt.ldl(Gk, {"l": Gk.size[0], "q": [], "s": []}, spmatrix([], [], [], (0, Pk.size[0])), kktreg=1e-9 if mode == "ldlreg" else None)
+    sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=lambda W: f3(W, Pk))
+    print("sparse LDL' KKT solver:", f3.info())
 else:
     sol = solvers.qp(tosp(sp.tril(P)), matrix(q), tosp(G), matrix(h))
 wall = time.perf_counter() - t0
