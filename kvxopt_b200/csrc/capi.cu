@@ -136,6 +136,10 @@ b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200
 b200s_status b200s_chol_set_owned(b200s_chol* F, const unsigned char* owned) {
     if (!F) return B200S_INVALID;
     if (F->plan.n == 0) return B200S_OK;
+    if (F->ldl && owned) {   // the pivot signs of fronts factored elsewhere are not exchanged: one GPU per factor in LDL' mode
+        set_last_error("front ownership (subtree-to-subcube) is not available with supernodal = 0 (LDL')");
+        return B200S_INVALID;
+    }
     b200s_status es = ensure_device(F);
     if (es != B200S_OK) return es;
     return (b200s_status)chol_device_set_owned(F->dev, owned);

@@ -1534,6 +1534,18 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
     return ST_OK;
 }
 
+// launch sites shared by the LL' kernels and their signed (LDL') instantiations, which also take the pivot-sign array
+#define LAUNCH_SGN(KERN, GRID, BLOCK, SMEM, STREAM, ...)                                         \
+    do {                                                                                          \
+        if (ldl) KERN<true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn);                    \
+        else KERN<false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr);                    \
+    } while (0)
+#define LAUNCH_SMALL(T, GRID, BLOCK, SMEM, STREAM, ...)                                          \
+    do {                                                                                          \
+        if (ldl) k_small_front<T, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn);        \
+        else k_small_front<T, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr);        \
+    } while (0)
+
 int CholDevice::factor_level(int l) {
     const CholPlan& P = *plan;
     if (l < 0 || l >= P.nlevels) return ST_INVALID;
@@ -1554,11 +1566,14 @@ int CholDevice::factor_level(int l) {
     }
     prof_begin(1);
     if (LS.small_cnt[0])
-        { if (ldl) k_small_front<64, true><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed, dsgn); else k_small_front<64, false><<<LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream>>>(dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed, nullptr); }
+        LAUNCH_SMALL(64, LS.small_cnt[0], 64, (size_t)(LS.small_maxnr[0] | 1) * LS.small_maxnr[0] * 8, stream,
+                         dsched + LS.small_off[0], dF, dL, dW, dminor, opts.dbound, downed);
     if (LS.small_cnt[1])
-        { if (ldl) k_small_front<128, true><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed, dsgn); else k_small_front<128, false><<<LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream>>>(dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed, nullptr); }
+        LAUNCH_SMALL(128, LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream,
+                         dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed);
     if (LS.small_cnt[2])
-        { if (ldl) k_small_front<256, true><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed, dsgn); else k_small_front<256, false><<<LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream>>>(dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed, nullptr); }
+        LAUNCH_SMALL(256, LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream,
+                         dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed);
     prof_end();
     // Lookahead of depth one: after panel kb, part A of its trailing update (the next block column only) runs on
     // the main stream, then panel kb+1; part B (all other column tiles) runs on stream2 concurrently with panel
@@ -1571,9 +1586,9 @@ int CholDevice::factor_level(int l) {
         const Launch& lp = LS.panel[kb];
         if (lp.ctas) {
             prof_begin(2);
-            { if (ldl) k_panel<true><<<lp.ctas, 256, SMEM_PANEL, stream>>>(sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
-                                                          dF, dL, ddiag, dminor, opts.dbound, downed, dsgn); else k_panel<false><<<lp.ctas, 256, SMEM_PANEL, stream>>>(sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
-                                                          dF, dL, ddiag, dminor, opts.dbound, downed, nullptr); }
+            LAUNCH_SGN(k_panel, lp.ctas, 256, SMEM_PANEL, stream,
+                       sgroups[std::max(lp.sgi, 0)], dsched + lp.goff, dsched + lp.goff + lp.ng, lp.ng, (int)kb,
+                       dF, dL, ddiag, dminor, opts.dbound, downed);
             k_diag_writeback<<<lp.ng, 256, 0, stream>>>(dsched + lp.goff, (int)kb, dF, dL, ddiag, downed);
             prof_end();
         }
@@ -1582,13 +1597,13 @@ int CholDevice::factor_level(int l) {
             const Launch& lf = LS.updF[kb];
             prof_begin(3);
             if (ln.ctas)
-                { if (ldl) k_update<true><<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
-                                                                        (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<ln.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
-                                                                        (int)kb, dF, dL, dW, downed, nullptr); }
+                LAUNCH_SGN(k_update, ln.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
+                       (int)kb, dF, dL, dW, downed);
             if (lf.ctas && !lookahead)
-                { if (ldl) k_update<true><<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
-                                                                        (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lf.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
-                                                                        (int)kb, dF, dL, dW, downed, nullptr); }
+                LAUNCH_SGN(k_update, lf.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
+                       (int)kb, dF, dL, dW, downed);
             if (lf.ctas && lookahead) {
                 // Far update with look-ahead: the column tiles of the NEXT super-block (part A) run here and gate its
                 // panels; all other column tiles (part B, the bulk of the flops) run on stream2 under the next
@@ -1599,14 +1614,14 @@ int CholDevice::factor_level(int l) {
                 if (lfb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));            // panels and near updates of this super-block
                 if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }
                 if (lfa.ctas)
-                    { if (ldl) k_update<true><<<lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
-                                                                             (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
-                                                                             (int)kb, dF, dL, dW, downed, nullptr); }
+                    LAUNCH_SGN(k_update, lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
+                       (int)kb, dF, dL, dW, downed);
                 if (lfb.ctas) {
                     CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-                    { if (ldl) k_update<true><<<lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
-                                                                              (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
-                                                                              (int)kb, dF, dL, dW, downed, nullptr); }
+                    LAUNCH_SGN(k_update, lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2,
+                       sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
+                       (int)kb, dF, dL, dW, downed);
                     CUDA_TRY(cudaEventRecord(evB, stream2));
                     pendingB = true;
                 }
@@ -1618,9 +1633,9 @@ int CholDevice::factor_level(int l) {
             const Launch& lu = LS.upd[kb];
             if (lu.ctas) {
                 prof_begin(3);
-                { if (ldl) k_update<true><<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
-                                                                        (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lu.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
-                                                                        (int)kb, dF, dL, dW, downed, nullptr); }
+                LAUNCH_SGN(k_update, lu.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
+                       (int)kb, dF, dL, dW, downed);
                 prof_end();
             }
             continue;
@@ -1630,14 +1645,14 @@ int CholDevice::factor_level(int l) {
         if (lb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));             // panel kb is complete
         if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }   // part B of step kb-1
         if (la.ctas)
-            { if (ldl) k_update<true><<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
-                                                                    (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<la.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
-                                                                    (int)kb, dF, dL, dW, downed, nullptr); }
+            LAUNCH_SGN(k_update, la.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
+                       (int)kb, dF, dL, dW, downed);
         if (lb.ctas) {
             CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-            { if (ldl) k_update<true><<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
-                                                                     (int)kb, dF, dL, dW, downed, dsgn); else k_update<false><<<lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2>>>(sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
-                                                                     (int)kb, dF, dL, dW, downed, nullptr); }
+            LAUNCH_SGN(k_update, lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2,
+                       sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
+                       (int)kb, dF, dL, dW, downed);
             CUDA_TRY(cudaEventRecord(evB, stream2));
             pendingB = true;
         }
@@ -1645,9 +1660,9 @@ int CholDevice::factor_level(int l) {
     if (pendingB) CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0));
     if (LS.syrk.ctas) {
         prof_begin(3);
-        { if (ldl) k_update<true><<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
-                                                                     LS.syrk.ng, 1, 0, dF, dL, dW, downed, dsgn); else k_update<false><<<LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream>>>(sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
-                                                                     LS.syrk.ng, 1, 0, dF, dL, dW, downed, nullptr); }
+        LAUNCH_SGN(k_update, LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
+                       LS.syrk.ng, 1, 0, dF, dL, dW, downed);
         prof_end();
     }
     CUDA_TRY(cudaGetLastError());

@@ -100,6 +100,24 @@ def test_ldl_zero_pivot_raises(cholmod):
     assert e.value.args[0] == 1
 
 
+def test_ldl_sparse_rhs_and_ownership_refused(cholmod):
+    """spsolve / splinsolve go through the same signed sweeps; front ownership (multi-GPU building block) is refused in
+    LDL' mode instead of silently dropping the pivot signs of remote fronts"""
+    import ctypes as C
+    from kvxopt_b200 import _lib as L
+    K = CASES["small"]()
+    n = K.shape[0]
+    Kl = lower_ccs(K)
+    Bs = sp.random(n, 4, density=0.1, random_state=np.random.default_rng(2), format="csc")
+    X = cholmod.splinsolve(Kl, Bs)
+    want = np.linalg.solve(K.toarray(), Bs.toarray())
+    assert np.linalg.norm(X.toarray() - want) <= XREL_TOL * np.linalg.norm(want)
+    F = cholmod.symbolic(Kl)
+    h, _ = cholmod._factor_handle(F)
+    owned = (C.c_ubyte * 100000)(*([1] * 100000))
+    assert L.fn["b200s_chol_set_owned"](h, C.cast(owned, C.c_char_p)) == L.INVALID
+
+
 def test_ldl_large_quasi_definite_properties(cholmod):
     """beyond the dense oracle's reach: 30^3 Laplacian block + constraints (n = 31 000), checked by backward error,
     linearity and inertia (number of negative pivots = order of the negative block)"""
