@@ -933,68 +933,98 @@ __device__ __forceinline__ void stage_rows64(const double* __restrict__ P, int l
     for (int j = 0; j < wq; j++) cp_async16(sb + 8u * 64u * (unsigned)j, col + (long long)j * ld);
 }
 
-// forward, block kb: t[r] -= L[r, blk] * x_blk for a 64-row tile of the rows below the block
+// forward, block kb: t[r] -= L[r, blk] * x_blk for a 64-row tile of the rows below the block.  The tile of L is staged
+// once and applied to all right-hand sides of the call, CG columns at a time (one shared-memory read feeds CG sums).
+template <int CG>
 __global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
-                                                 double* __restrict__ T, long long tstride) {
+                                                 double* __restrict__ T, long long tstride, int ncols) {
     extern __shared__ double sm[];
     double* S = sm;                        // [128 columns][64 rows]
-    __shared__ double xs[NB];
-    __shared__ double red[4][SOLVE_FT];
+    __shared__ double xs[CG][NB];
+    __shared__ double red[CG][4][SOLVE_FT];
     int tile;
     const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
     const FrontS f = load_front(sg, gfront, F, g);
-    double* t = T + blockIdx.y * tstride + f.rowptr;
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x;
     const int rr = tid & (SOLVE_FT - 1), cq = tid >> 6;
     const int rb = k0 + w, r0 = (rb & ~1) + tile * SOLVE_FT;      // tiles start at an even row (16-byte LDGSTS)
     stage_rows64(L + f.loff, f.ld, f.nr, k0, w, r0, S, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if (tid < NB) xs[tid] = (tid < w) ? t[k0 + tid] : 0.0;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    double a0 = 0, a1 = 0;
-    if (r0 + rr < f.nr && r0 + rr >= rb) {
-        const int wq = min(32, w - cq * 32);
-        const double* sp = S + cq * 32 * 64 + rr;
-        int j = 0;
-        for (; j + 1 < wq; j += 2) { a0 = fma(sp[j * 64], xs[cq * 32 + j], a0); a1 = fma(sp[(j + 1) * 64], xs[cq * 32 + j + 1], a1); }
-        if (j < wq) a0 = fma(sp[j * 64], xs[cq * 32 + j], a0);
+    const bool rowok = r0 + rr < f.nr && r0 + rr >= rb;
+    const int wq = min(32, w - cq * 32);
+    const double* sp = S + cq * 32 * 64 + rr;
+    for (int c0 = 0; c0 < ncols; c0 += CG) {
+        const int cn = min(CG, ncols - c0);
+        if (c0) __syncthreads();           // xs / red of the previous column group are consumed
+        for (int i = tid; i < CG * NB; i += 256) {
+            const int c = i / NB, q = i - c * NB;
+            xs[c][q] = (c < cn && q < w) ? T[(c0 + c) * tstride + f.rowptr + k0 + q] : 0.0;
+        }
+        if (c0 == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        double a0[CG], a1[CG];
+#pragma unroll
+        for (int c = 0; c < CG; c++) a0[c] = a1[c] = 0.0;
+        if (rowok) {
+            int j = 0;
+            for (; j + 1 < wq; j += 2) {
+                const double s0 = sp[j * 64], s1 = sp[(j + 1) * 64];
+#pragma unroll
+                for (int c = 0; c < CG; c++) { a0[c] = fma(s0, xs[c][cq * 32 + j], a0[c]); a1[c] = fma(s1, xs[c][cq * 32 + j + 1], a1[c]); }
+            }
+            if (j < wq) {
+                const double s0 = sp[j * 64];
+#pragma unroll
+                for (int c = 0; c < CG; c++) a0[c] = fma(s0, xs[c][cq * 32 + j], a0[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CG; c++) red[c][cq][rr] = a0[c] + a1[c];
+        __syncthreads();
+        for (int i = tid; i < cn * SOLVE_FT; i += 256) {
+            const int c = i / SOLVE_FT, r = i - c * SOLVE_FT;
+            if (r0 + r < f.nr && r0 + r >= rb)
+                T[(c0 + c) * tstride + f.rowptr + r0 + r] -= (red[c][0][r] + red[c][1][r]) + (red[c][2][r] + red[c][3][r]);
+        }
     }
-    red[cq][rr] = a0 + a1;
-    __syncthreads();
-    if (tid < SOLVE_FT && r0 + tid < f.nr && r0 + tid >= rb) t[r0 + tid] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
 }
 // backward, block kb: partial[q] = sum over a 192-row tile of the rows below the block of L[r, k0+q] * t[r].
 // Three 64-row slices, one shared-memory buffer each (192 KB in flight); thread = (row, column quarter);
-// the 32 per-lane column sums of a warp are combined by a halving butterfly
+// the 32 per-lane column sums of a warp are combined by a halving butterfly.  CG right-hand sides share the staged tile
+// (blockIdx.y = group of CG columns): one shared-memory read feeds CG sums.
+template <int CG>
 __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
                                                  const double* __restrict__ T, long long tstride, double* __restrict__ part,
-                                                 long long pstride) {
+                                                 long long pstride, int ncols) {
     extern __shared__ double sm[];         // 3 buffers of [128 columns][64 rows]
-    __shared__ double red[8][32];
+    __shared__ double red[CG][8][32];
     int tile;
     const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
     const FrontS f = load_front(sg, gfront, F, g);
-    const double* t = T + blockIdx.y * tstride + f.rowptr;
+    const int c0 = blockIdx.y * CG, cn = min(CG, ncols - c0);
+    const double* t = T + c0 * tstride + f.rowptr;
     const double* P = L + f.loff;
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rr = tid & 63, cq = tid >> 6;
     const int wq = min(32, w - cq * 32);
     const int rb = k0 + w, r0 = (rb & ~1) + tile * SOLVE_BT;
     constexpr int NSUB = SOLVE_BT / 64;
-    double p[32];
+    double p[CG][32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) p[j] = 0.0;
+    for (int c = 0; c < CG; c++)
+#pragma unroll
+        for (int j = 0; j < 32; j++) p[c][j] = 0.0;
     static_assert(NSUB == 3, "one buffer per slice");
-    double tv[NSUB];
+    double tv[CG][NSUB];
 #pragma unroll
     for (int sub = 0; sub < NSUB; sub++) {
         stage_rows64(P, f.ld, f.nr, k0, w, r0 + sub * 64, sm + sub * NB * 64, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
         const int r = r0 + sub * 64 + rr;
-        tv[sub] = (r < f.nr && r >= rb) ? t[r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < CG; c++) tv[c][sub] = (c < cn && r < f.nr && r >= rb) ? t[c * tstride + r] : 0.0;
     }
 #pragma unroll
     for (int sub = 0; sub < NSUB; sub++) {
@@ -1007,26 +1037,37 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
             const double* sp = sm + sub * NB * 64 + cq * 32 * 64 + rr;
 #pragma unroll
             for (int j = 0; j < 32; j++)
-                if (j < wq) p[j] = fma(sp[j * 64], tv[sub], p[j]);
+                if (j < wq) {
+                    const double lv = sp[j * 64];
+#pragma unroll
+                    for (int c = 0; c < CG; c++) p[c][j] = fma(lv, tv[c][sub], p[c][j]);
+                }
         }
     }
     // after the step with offset o the lanes with bit o set hold the upper half of the surviving columns: lane l ends
     // with the sum of column l
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const bool up = (lane & o) != 0;
+    for (int c = 0; c < CG; c++) {
 #pragma unroll
-        for (int j = 0; j < o; j++) {
-            const double send = up ? p[j] : p[j + o];
-            const double keep = up ? p[j + o] : p[j];
-            p[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; j++) {
+                const double send = up ? p[c][j] : p[c][j + o];
+                const double keep = up ? p[c][j + o] : p[c][j];
+                p[c][j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
         }
+        red[c][warp][lane] = p[c][0];
     }
-    red[warp][lane] = p[0];
     __syncthreads();
-    if (tid < NB) part[blockIdx.y * pstride + (long long)blockIdx.x * NB + tid] = red[2 * (tid >> 5)][tid & 31] + red[2 * (tid >> 5) + 1][tid & 31];
+    for (int i = tid; i < cn * NB; i += 256) {
+        const int c = i / NB, q = i - c * NB;
+        part[(c0 + c) * pstride + (long long)blockIdx.x * NB + q] = red[c][2 * (q >> 5)][q & 31] + red[c][2 * (q >> 5) + 1][q & 31];
+    }
 }
 // backward, block kb: z = t_blk - sum of the tile partials (fixed order), then solve L11^T x = z
+constexpr int BWD_CG = 4;        // right-hand sides per CTA in the backward update (multi-column solves)
 constexpr int PT_CHUNK = 48;     // partial rows staged per pass
 static constexpr size_t SMEM_FUPD = (size_t)NB * 64 * sizeof(double), SMEM_BUPD = 3 * SMEM_FUPD;
 static constexpr size_t SMEM_BDIAG = SMEM_SDIAG + (size_t)PT_CHUNK * NB * sizeof(double);
@@ -1490,8 +1531,10 @@ int CholDevice::init() {
     CUDA_TRY(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
     CUDA_TRY(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SDIAG));
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BDIAG));
-    CUDA_TRY(cudaFuncSetAttribute(k_fwd_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FUPD));
-    CUDA_TRY(cudaFuncSetAttribute(k_bwd_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUPD));
+    CUDA_TRY(cudaFuncSetAttribute(k_fwd_upd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FUPD));
+    CUDA_TRY(cudaFuncSetAttribute(k_fwd_upd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FUPD));
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_upd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUPD));
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_upd<BWD_CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUPD));
     CUDA_TRY(cudaFuncSetAttribute(k_small_front<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((SMALL_NR | 1) * SMALL_NR * sizeof(double))));
     CUDA_TRY(cudaFuncSetAttribute(k_small_front<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 64 * 8));
@@ -1812,7 +1855,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                             const Launch& la = LS.sfwd[kb];
                             k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n);
                             if (la.ctas)
-                                k_fwd_upd<<<dim3(la.ctas, nc), 256, SMEM_FUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride);
+                                (nc == 1 ? k_fwd_upd<1> : k_fwd_upd<4>)<<<la.ctas, 256, SMEM_FUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride, nc);
                         }
                     }
                 }
@@ -1826,7 +1869,8 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                         for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
                             const Launch& la = LS.sbwd[kb];
                             if (la.ctas)
-                                k_bwd_upd<<<dim3(la.ctas, nc), 256, SMEM_BUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride);
+                                (nc == 1 ? k_bwd_upd<1> : k_bwd_upd<BWD_CG>)<<<dim3(la.ctas, nc == 1 ? 1 : (nc + BWD_CG - 1) / BWD_CG), 256, SMEM_BUPD, stream>>>(
+                                    sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride, nc);
                             k_bwd_diag<<<dim3(la.ng, nc), 256, SMEM_BDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dMinv, dT, tstride, dX, n, dpart, pstride);
                         }
                     }

@@ -313,3 +313,28 @@ def test_device_resident_entry_points(cholmod):
     assert berr(A, X, B) <= BERR_TOL
     Xh = np.asfortranarray(B.copy()); cholmod.solve(F, Xh)
     assert np.array_equal(Xh, X)
+
+
+def test_multi_rhs_solve_equals_column_by_column(cholmod):
+    """reference cholmod.c:481-493 solves column by column; the engine stages each tile of L once for all columns
+    of the call (groups of four in the large-front update kernels) -- the result is bit-identical per column"""
+    A = lap3d(22, 22, 22); Al = lower_ccs(A); n = A.shape[0]
+    perm = np.zeros(n, np.int64)
+    from kvxopt_b200 import _lib as L
+    assert L.fn["b200s_grid_nd_perm"](22, 22, 22, 64, L.ptr_i64(perm)) == 0
+    F = cholmod.symbolic(Al, p=perm); cholmod.numeric(Al, F)
+    assert cholmod.factor_info(F)["max_front_rows"] > 256          # large-front (tiled) path
+    B = np.random.default_rng(3).standard_normal((n, 9))
+    cols = []
+    for j in range(9):
+        x = np.asfortranarray(B[:, j:j + 1].copy()); cholmod.solve(F, x); cols.append(x[:, 0])
+    for k in (2, 3, 5, 9):
+        for sys_ in (0, 4, 5):
+            X = np.asfortranarray(B[:, :k].copy()); cholmod.solve(F, X, sys=sys_)
+            if sys_ == 0:
+                for j in range(k):
+                    assert np.array_equal(X[:, j], cols[j]), (k, j)
+                assert berr(A, X, B[:, :k]) <= BERR_TOL
+            else:
+                x1 = np.asfortranarray(B[:, k - 1:k].copy()); cholmod.solve(F, x1, sys=sys_)
+                assert np.array_equal(X[:, k - 1], x1[:, 0]), (k, sys_)
