@@ -637,20 +637,22 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
         cp_async_commit();
         const double* as = As + (kt % STAGES) * BK * LDT;
         const double* bs = Bs + (kt % STAGES) * BK * LDTB;
-        // SGN (A = L S L'): C -= A_i S A_j^T, the column signs ride on the negation of the A_j fragment.  The sign array
-        // is padded by BK entries, columns beyond K multiply zero-filled operands.
-        double ns[BK / 4];
+        // SGN (A = L S L'): C -= A_i S A_j^T, the column signs are applied to the A_j fragment.  The sign array is padded by
+        // BK entries, columns beyond K meet zero-filled operands.
+        int flip[BK / 4];                 // sign bit of s_k: XORed into the fragment on the integer pipe, the FP64 pipe is DMMA's
         if (SGN) {
 #pragma unroll
-            for (int kk = 0; kk < BK; kk += 4) ns[kk / 4] = -sgn[f.col0 + k0 + kt * BK + kk + (lane & 3)];
+            for (int kk = 0; kk < BK; kk += 4) flip[kk / 4] = __double2hiint(sgn[f.col0 + k0 + kt * BK + kk + (lane & 3)]) & 0x80000000;
         }
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             double am[4], bn[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                am[i] = SGN ? ns[kk / 4] * bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)]
-                            : -bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)];
+            for (int i = 0; i < 4; i++) {
+                double v = bs[(kk + (lane & 3)) * LDTB + wc + i * 8 + (lane >> 2)];
+                if (SGN) v = __hiloint2double(__double2hiint(v) ^ flip[kk / 4], __double2loint(v));
+                am[i] = -v;               // the negation is a DMMA operand modifier
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) bn[j] = as[(kk + (lane & 3)) * LDT + wr + j * 8 + (lane >> 2)];
 #pragma unroll

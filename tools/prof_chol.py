@@ -8,6 +8,8 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 Al = lap3d_lower(nx); n = Al.shape[0]
 perm = np.zeros(n, np.int64); L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm))
+if os.environ.get("CHOL_LDL"):
+    cholmod.options["supernodal"] = 0      # signed (LDL') instantiation of the kernels
 F = cholmod.symbolic(Al, p=perm)
 h, _ = cholmod._factor_handle(F)
 prof = 0 if (len(sys.argv) > 3 and sys.argv[3] == "noprof") else 1
