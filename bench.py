@@ -286,6 +286,27 @@ def bench_cholesky(nx, steps, fp64_peak):
                      "traffic": traffic_from_profiles("k_update")},
     }
     del F
+    # the signed instantiation of the same kernels (cholmod.options['supernodal'] = 0: LDL' without pivoting, the mode
+    # kkt.ldl factors quasi-definite KKT systems with) on the same matrix
+    o = L.CholOpts()
+    fn["b200s_chol_default_opts"](C.byref(o))
+    o.supernodal = 0
+    h2 = C.c_void_p()
+    cp_, ri_ = np.ascontiguousarray(Al.indptr, dtype=np.int64), np.ascontiguousarray(Al.indices, dtype=np.int64)
+    assert fn["b200s_chol_analyze"](n, L.ptr_i64(cp_), L.ptr_i64(ri_), b"L", L.ptr_i64(perm), C.byref(o), C.byref(h2)) == 0
+    ms_l = []
+    for _ in range(1 + max(2, steps // 2)):
+        assert fn["b200s_chol_factorize_dev"](h2, vals_dev.data_ptr(), C.byref(minor)) == 0, L.last_error()
+        fn["b200s_chol_info"](h2, C.byref(inf))
+        ms_l.append(inf.ms_total)
+    Xd = Bd.clone()
+    torch.cuda.synchronize()
+    assert fn["b200s_chol_solve_dev"](h2, 0, Xd.data_ptr(), 1, n) == 0
+    x2 = Xd.cpu().numpy()
+    fn["b200s_chol_free"](h2)
+    out["ldl_mode"] = {"what": "same matrix, supernodal = 0 (signed kernels: P A P' = L D L' without pivoting)",
+                       "factor_ms": float(np.min(ms_l[1:])), "factor_tflops": d["flops"] / (float(np.min(ms_l[1:])) * 1e-3) / 1e12,
+                       "backward_error": float(np.linalg.norm(A @ x2 - B[:, 0]) / (12.0 * np.linalg.norm(x2) + np.linalg.norm(B)))}
     return out
 
 

@@ -204,3 +204,21 @@ def test_boeing2_ipm_with_sparse_ldl(kvx):
     assert sol["status"] == "optimal"
     assert sol["iterations"] == int(z["iters_ldl"])
     assert abs(sol["primal objective"] - float(z["pobj_ldl"])) <= 1e-8 * abs(float(z["pobj_ldl"]))
+
+
+def test_ldl_edge_cases(cholmod):
+    """1 x 1 negative matrix, a negative definite matrix (every pivot negative) and an empty one"""
+    K1 = sp.csc_matrix(np.array([[-2.0]]))
+    x = np.array([[3.0]], order="F"); cholmod.linsolve(K1, x)
+    assert abs(x[0, 0] + 1.5) <= 4e-16 * 1.5          # square-root form: l = sqrt(2), x = -(3 / l) / l
+    A = rand_spd(200, 0.05, 8)
+    Kn = (-A).tocsc()
+    B = np.random.default_rng(4).standard_normal((200, 2))
+    X = np.asfortranarray(B.copy()); cholmod.linsolve(lower_ccs(Kn), X)
+    assert berr(Kn, X, B) <= BERR_TOL
+    F = cholmod.symbolic(lower_ccs(Kn)); cholmod.numeric(lower_ccs(Kn), F)
+    D = np.asfortranarray(np.ones((200, 1))); cholmod.solve(F, D, sys=6)
+    assert (D < 0).all()
+    E = sp.csc_matrix((0, 0))
+    F0 = cholmod.symbolic(E); cholmod.numeric(E, F0)
+    cholmod.solve(F0, np.zeros((0, 1), order="F"))
