@@ -566,9 +566,11 @@ __global__ void __launch_bounds__(256) k_klu_dense_pack(const int* __restrict__ 
 }
 
 // D[matrix][entry]: the block entries of one matrix, contiguous (k_klu_dense_pack), so gather and scatter are coalesced.
-// dmeta: per column of the block KLU_DENSE_META ints = {index of its first entry, row bitmap (160 bits)}
-constexpr int KLU_DENSE_THREADS = 512;
-__global__ void __launch_bounds__(KLU_DENSE_THREADS, 1) k_klu_dense_lu(int nd, const int* __restrict__ dmeta, int ndp, int batch,
+// dmeta: per column of the block KLU_DENSE_META ints = {index of its first entry, row bitmap (KLU_DENSE_MAX bits)}
+constexpr int KLU_DENSE_THREADS = 256;
+// two CTAs per SM (64 registers per thread): the latency-bound chunk chains of two matrices overlap
+constexpr int KLU_DENSE_OCC = 2;
+__global__ void __launch_bounds__(KLU_DENSE_THREADS, KLU_DENSE_OCC) k_klu_dense_lu(int nd, const int* __restrict__ dmeta, int ndp, int batch,
                                                          double* __restrict__ D, int* __restrict__ status) {
     extern __shared__ double S[];
     __shared__ double rdiag[16];

@@ -412,7 +412,8 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
     P.spine0 = n; P.spine_nd = 0;
     {
         const i32 lastblk = S.nblocks > 0 ? S.R[S.nblocks] - S.R[S.nblocks - 1] : 0;
-        for (i32 nd = std::min<i32>(KLU_DENSE_MAX, (lastblk / 16) * 16); nd >= 48; nd -= 16) {
+        const i32 dmax = getenv("B200S_KLU_DENSE_MAX") ? std::min<i32>(KLU_DENSE_MAX, atoi(getenv("B200S_KLU_DENSE_MAX"))) : KLU_DENSE_MAX;
+        for (i32 nd = std::min<i32>(dmax, (lastblk / 16) * 16); nd >= 48; nd -= 16) {
             const i32 s0 = n - nd;
             i64 cnt = 0;
             for (i32 k = s0; k < n; k++)

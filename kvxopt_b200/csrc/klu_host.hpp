@@ -105,7 +105,10 @@ constexpr int KLU_MAXSEG = 15;        // matched segments per (batch, column); t
 constexpr int KLU_REC_U32 = 16 + KLU_CHUNK_ROWS / 2;   // per (batch, column): {nseg, segs[15]} + 64 uint16 destination rows
 constexpr int KLU_BLOB_BYTES = 8192;  // cap of the in-wave update blob
 constexpr long long KLU_WAVE_MAX_STAGED = 8ll << 20;   // staged rows over all waves (x ~52 B of tables): 8 M rows ~ 440 MB
-constexpr int KLU_DENSE_MAX = 160, KLU_DENSE_META = 1 + KLU_DENSE_MAX / 32;    // largest dense trailing block (shared memory: 160 x 164 doubles)
+// largest dense trailing block: 112 x 116 doubles of shared memory = two CTAs of k_klu_dense_lu per SM (sweep on the B200 with
+// 4096 x ACTIVSg2000, wave kernel + dense block per batch: 160 columns, one CTA per SM 5.6 + 1.7 ms; 112: 6.1 + 1.05 ms;
+// 96: 6.3 + 0.84 ms; 80: 6.7 + 0.64 ms)
+constexpr int KLU_DENSE_MAX = 112, KLU_DENSE_META = 1 + (KLU_DENSE_MAX + 31) / 32;
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan);
 
 }  // namespace b200s
