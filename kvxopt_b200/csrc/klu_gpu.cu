@@ -12,7 +12,7 @@
 //   LU  [Bp/32][slots][32]  GROUP-MAJOR: the slots of a group of 32 matrices are contiguous (value v of matrix b at
 //       (b/32)*slots*32 + v*32 + b%32), so a run of consecutive slots -- the L part of a column -- is ONE contiguous
 //       block that a single cp.async.bulk (TMA) moves.  Per column: U above the diagonal, U diagonal, L below; then F
-// Kernels: k_klu_transpose (tiled), k_klu_rowscale, k_klu_prescale, k_klu_scatter, k_klu_refactor_wave (fast path: TMA
+// Kernels: k_klu_transpose (tiled), k_klu_rowscale (row maxima + scaling), k_klu_scatter, k_klu_refactor_wave (fast path: TMA
 // producer warp + 16 consumer warps per group of 32 matrices), k_klu_dense_pack / k_klu_dense_lu (dense trailing block),
 // k_klu_refactor (level-schedule kernel for patterns outside the wave kernel's budget), k_klu_solve_lvl.
 #include "gpu.hpp"
@@ -59,8 +59,10 @@ __global__ void k_klu_transpose(const double* __restrict__ in, long long ldv, lo
 }
 
 // Rs[i][b] = max_k |A(i,k)| (1 when the row is empty or zero)
+// prescale != 0: the row's entries are divided by the scale right away (they were just read: the second sweep hits L1/L2), which
+// replaces the separate k_klu_prescale pass over all of A (one 0.96 GB read and the 0.13 GB of scales less per batch of 4096)
 __global__ void k_klu_rowscale(const long long* __restrict__ rowptr, const int* __restrict__ rowent, int n, int Bp,
-                               const double* __restrict__ Axt, double* __restrict__ Rs) {
+                               double* __restrict__ Axt, double* __restrict__ Rs, int prescale) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int ngroups = Bp >> 5;
@@ -70,8 +72,15 @@ __global__ void k_klu_rowscale(const long long* __restrict__ rowptr, const int* 
         const int i = (int)(w / ngroups), g = (int)(w - (long long)i * ngroups);
         const int b = g * 32 + lane;
         double m = 0.0;
-        for (long long p = rowptr[i]; p < rowptr[i + 1]; p++) m = fmax(m, fabs(Axt[(long long)rowent[p] * Bp + b]));
-        Rs[(long long)i * Bp + b] = (m > 0.0) ? m : 1.0;
+        const long long p0 = rowptr[i], p1 = rowptr[i + 1];
+        for (long long p = p0; p < p1; p++) m = fmax(m, fabs(Axt[(long long)rowent[p] * Bp + b]));
+        const double rs = (m > 0.0) ? m : 1.0;
+        Rs[(long long)i * Bp + b] = rs;
+        if (prescale)
+            for (long long p = p0; p < p1; p++) {
+                double* a = Axt + (long long)rowent[p] * Bp + b;
+                *a = *a / rs;
+            }
     }
 }
 
@@ -196,7 +205,7 @@ constexpr int KLU_CONS_BAR = 9;      // named barrier of the 16 consumer warps (
 //           consumed by every column of the wave) + for each warp and row what to do with it (destination row, row
 //           holding u_jk) so that the update loop reads NO metadata from global memory
 //   blob  : the updates between columns of the same wave (applied in rounds from the source's xs region)
-// The input values arrive pre-scaled (k_klu_prescale), gathered straight into xs by cp.async with zero fill.
+// The input values arrive pre-scaled (k_klu_rowscale), gathered straight into xs by cp.async with zero fill.
 __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_wave(KluPlanD P, KluWaveD W, int Bp,
                                                                               const double* __restrict__ Axs,
                                                                               double* __restrict__ LU, int* __restrict__ status,
@@ -679,17 +688,6 @@ __global__ void __launch_bounds__(KLU_DENSE_THREADS, KLU_DENSE_OCC) k_klu_dense_
     if (tid == 0 && bad) status[b] = ST_SINGULAR;
 }
 
-// Axt[e][b] /= Rs[row(e)][b]: the row scaling of klu_factor applied to the transposed input once
-__global__ void k_klu_prescale(const int* __restrict__ ent_row, long long nnz, int Bp, const double* __restrict__ Rs,
-                               double* __restrict__ Axt) {
-    const long long total = nnz * Bp;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long e = t / Bp;
-        const int b = (int)(t - e * Bp);
-        Axt[t] = Axt[t] / Rs[(long long)ent_row[e] * Bp + b];
-    }
-}
-
 // ---- batched triangular solves: level-scheduled gather tasks ----------------------------------------
 // klu_solve / klu_tsolve (reference src/C/klu.c:593-690) as a DAG of 2n tasks over the work vector V = [Y; Z]
 // (2n rows, interleaved [row][matrix]):  V[t] = (V[i] - sum_terms LU[slot] * V[src]) / LU[diag]   with i = t mod n.
@@ -994,7 +992,6 @@ public:
     long long lu_slots = 0;
     std::vector<void*> owned;
     int *d_slot_src = nullptr, *d_slot_row = nullptr, *d_rowent = nullptr, *d_status = nullptr;
-    int* d_ent_row = nullptr;
     const int *d_dense_meta = nullptr, *d_dense_slot = nullptr;
     double* dD = nullptr;
     int spine_nd = 0, ndmap = 0, ndp = 0;
@@ -1101,12 +1098,6 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         std::vector<unsigned> be(P.bentry.begin(), P.bentry.end()), wb(P.wblob.begin(), P.wblob.end());
         if ((rc = up(&WD.bentry, be))) return rc;
         if ((rc = up(&WD.wblob, wb))) return rc;
-        std::vector<int> ent_row(P.nnzA, 0);
-        for (int i = 0; i < P.n; i++)
-            for (long long q = P.rowptr[i]; q < P.rowptr[i + 1]; q++) ent_row[P.rowent[q]] = i;
-        const int* er;
-        if ((rc = up(&er, ent_row))) return rc;
-        d_ent_row = (int*)er;
         WD.spine0 = use_wave ? P.spine0 : P.n;
         spine_nd = use_wave ? P.spine_nd : 0;
         if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;
@@ -1170,16 +1161,15 @@ int KluDevice::enqueue_refactor(const double* dv, long long ldv, cudaEvent_t aft
         k_klu_transpose<<<grid, block, 0, stream>>>(dv, ldv, nnzA, batch, Bp, dAxt);
     }
     if (after_transpose) CUDA_TRY(cudaEventRecord(after_transpose, stream));       // the caller's value buffer is free again
-    k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs);
+    k_klu_rowscale<<<148 * 8, 256, 0, stream>>>(d_rowptr, d_rowent, n, Bp, dAxt, dRs, use_wave ? 1 : 0);
     if (use_wave) {
-        k_klu_prescale<<<148 * 16, 256, 0, stream>>>(d_ent_row, nnzA, Bp, dRs, dAxt);
         // only the off-diagonal-block entries F need a separate scatter; L/U columns are gathered inside the kernel
         if (nslots > lu_slots)
             k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1, nslots * 32);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
         k_klu_refactor_wave<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
         CUDA_TRY(cudaEventRecord(ev[6], stream));
-        launches = 4 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
+        launches = 3 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
         if (spine_nd > 0) {
             const dim3 tg(ndp / 32, Bp / 32);
             k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, nslots * 32, dLU, dD, 0);
