@@ -222,3 +222,26 @@ def test_ldl_edge_cases(cholmod):
     E = sp.csc_matrix((0, 0))
     F0 = cholmod.symbolic(E); cholmod.numeric(E, F0)
     cholmod.solve(F0, np.zeros((0, 1), order="F"))
+
+
+@pytest.mark.parametrize("kktreg", [None, 1e-10])
+def test_qp_mini_coneqp_with_sparse_ldl(kvx, kktreg):
+    """BASELINE config 5 generator at reduced size through the reference coneqp with kkt.ldl: the iteration count and
+    objective of the reference's own run (tests/golden/qp_mini.npz, dense 'chol')"""
+    sys.path.insert(0, GOLD)
+    from generators import qp_instance
+    from kvxopt import matrix, spmatrix, solvers
+    from kvxopt_b200 import kkt
+    z = np.load(os.path.join(GOLD, "qp_mini.npz"))
+    P, q, G, h = qp_instance(int(z["nx"]), int(z["ny"]), int(z["nrand"]))
+    def spm(M):
+        M = sp.coo_matrix(M)
+        return spmatrix(M.data.tolist(), M.row.tolist(), M.col.tolist(), M.shape)
+    Pk, Gk = spm(sp.tril(P)), spm(G)
+    dims = {"l": Gk.size[0], "q": [], "s": []}
+    f3 = kkt.ldl(Gk, dims, spmatrix([], [], [], (0, Pk.size[0])), kktreg=kktreg)
+    sol = solvers.coneqp(Pk, matrix(q), Gk, matrix(h), dims, kktsolver=lambda W: f3(W, Pk))
+    assert sol["status"] == "optimal"
+    assert sol["iterations"] == int(z["iters"])
+    assert abs(sol["primal objective"] - float(z["pobj"])) <= 1e-8 * abs(float(z["pobj"]))
+    assert f3.info()["factorizations"] >= sol["iterations"]
