@@ -28,7 +28,7 @@ from .cholmod import _ccs, _dense_view, _is_kvx, _is_dense, _size, _values
 
 fn = L.fn
 
-__all__ = ["chol2", "ldl", "qp_kktsolver", "lp_kktsolver"]
+__all__ = ["chol2", "ldl", "ldl2", "qp_kktsolver", "lp_kktsolver"]
 
 
 class _Handle:
@@ -321,6 +321,163 @@ def ldl(G, dims, A, mnl=0, kktreg=None):
 
     factor.info = _info
     factor._state = state          # assembled pattern / values, read by the host-side tests
+    return factor
+
+
+def ldl2(G, dims, A, mnl=0):
+    """Sparse counterpart of misc.kkt_ldl2(G, dims, A, mnl) (reference src/python/misc.py:1128-1210): the 2 x 2 system
+
+        [ H + G' W^-1 W^-T G   A' ]   [ ux ]   [ bx + G' W^-1 W^-T bz ]
+        [ A                    0  ] * [ uy ] = [ by                   ],      W uz = W^-T (G ux - bz)
+
+    factored as ONE sparse symmetric quasi-definite matrix, P K P' = L D L' without pivoting, by the engine's signed mode
+    (x columns in approximate-minimum-degree order of the pattern of S = H + G'G, then y: the x pivots are those of the
+    Cholesky factorization of S, the y pivots those of -A S^-1 A').  The reference forms K densely (sytrf, or potrf when
+    there are no equalities).  Unlike kkt.chol2 there is no dense p x p Schur complement, so problems with many equality
+    constraints stay sparse.  Componentwise inequalities only (dims['q'], dims['s'] empty, mnl = 0).  The pattern of K and the
+    list of products g_ki g_kj behind every entry of G'D^2 G are built once; factor() evaluates the values (numpy) and
+    sends them; solve() is two sparse products with G on the host around one host-buffer solve.  No CPU fallback."""
+    import scipy.sparse as sp
+    if dims["q"] or dims["s"]:
+        raise ValueError("kvxopt_b200.kkt.ldl2 is implemented only for problems with no second-order or semidefinite "
+                         "cone constraints")
+    if mnl:
+        raise ValueError("kvxopt_b200.kkt.ldl2 does not support nonlinear constraints (mnl > 0)")
+    p, n = _size(A)
+    m = dims["l"]
+    if _size(G) != (m, n):
+        raise TypeError("G must be a %d x %d matrix" % (m, n))
+    Gp, Gi, Gx = _sparse_ccs(G, "G")
+    Gm = sp.csc_matrix((Gx, Gi, Gp), shape=(m, n))
+    Gr = Gm.tocsr()
+    if p > 0:
+        Ap, Ai, Ax = _sparse_ccs(A, "A")
+    else:
+        Ap, Ai, Ax = np.zeros(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+    N = n + p
+    state = {"handle": None, "Hnnz": None}
+
+    def _create(H):
+        # products behind the lower triangle of G' D^2 G: for every row k of G and every pair i >= j of its columns
+        rp, ci, gv = Gr.indptr, Gr.indices, Gr.data
+        cnt = np.diff(rp)
+        ti, tj, tk, tc = [], [], [], []
+        for r in np.unique(cnt):                    # rows grouped by their number of entries: vectorised pair lists
+            if r == 0:
+                continue
+            rows = np.nonzero(cnt == r)[0]
+            base = rp[rows][:, None] + np.arange(r)[None, :]
+            cols, vals = ci[base], gv[base]
+            a, b = np.tril_indices(r)
+            ii, jj = cols[:, a], cols[:, b]
+            hi, lo = np.maximum(ii, jj), np.minimum(ii, jj)
+            ti.append(hi.ravel()); tj.append(lo.ravel())
+            tk.append(np.repeat(rows, len(a))); tc.append((vals[:, a] * vals[:, b]).ravel())
+        ti = np.concatenate(ti) if ti else np.zeros(0, dtype=np.int64)
+        tj = np.concatenate(tj) if tj else np.zeros(0, dtype=np.int64)
+        tk = np.concatenate(tk) if tk else np.zeros(0, dtype=np.int64)
+        tc = np.concatenate(tc) if tc else np.zeros(0)
+        if H is not None:
+            if _size(H) != (n, n):
+                raise TypeError("H must be a %d x %d matrix" % (n, n))
+            Hp, Hi, Hx = _sparse_ccs(H, "H")
+            Hc = np.repeat(np.arange(n, dtype=np.int64), np.diff(Hp))
+            keep = np.nonzero(Hi >= Hc)[0]
+            Hi, Hc = Hi[keep], Hc[keep]
+        else:
+            keep = np.zeros(0, dtype=np.int64); Hi = Hc = keep
+        Ac = np.repeat(np.arange(n, dtype=np.int64), np.diff(Ap))
+        # pattern of K (lower): S entries (terms and H, merged), diagonal of x, A rows, diagonal of y
+        rows = np.concatenate([ti, Hi, np.arange(n), n + Ai, n + np.arange(p)]).astype(np.int64)
+        cols = np.concatenate([tj, Hc, np.arange(n), Ac, n + np.arange(p)]).astype(np.int64)
+        key = cols * N + rows
+        uniq, slot = np.unique(key, return_inverse=True)           # CCS order: column-major, rows ascending
+        kcol, krow = uniq // N, uniq % N
+        kp = np.zeros(N + 1, dtype=np.int64)
+        np.add.at(kp, kcol + 1, 1)
+        kp = np.cumsum(kp)
+        ki = np.ascontiguousarray(krow, dtype=np.int64)
+        nt, nh = len(ti), len(Hi)
+        Sl = sp.csc_matrix((np.ones(len(uniq)), ki, kp), shape=(N, N))[:n, :n].tocsc()
+        Sl.sort_indices()
+        hs = C.c_void_p()
+        st = fn["b200s_chol_analyze"](n, L.ptr_i64(np.ascontiguousarray(Sl.indptr, dtype=np.int64)),
+                                      L.ptr_i64(np.ascontiguousarray(Sl.indices, dtype=np.int64)), b"L", None, None, C.byref(hs))
+        if st != L.OK:
+            _raise(st)
+        px = np.zeros(n, dtype=np.int64)
+        fn["b200s_chol_get_perm"](hs, L.ptr_i64(px))
+        fn["b200s_chol_free"](hs)
+        perm = np.ascontiguousarray(np.concatenate([px, n + np.arange(p)]), dtype=np.int64)
+        o = L.CholOpts()
+        fn["b200s_chol_default_opts"](C.byref(o))
+        o.supernodal = 0                                            # signed LDL' (no pivoting)
+        h = C.c_void_p()
+        st = fn["b200s_chol_analyze"](N, L.ptr_i64(kp), L.ptr_i64(ki), b"L", L.ptr_i64(perm), C.byref(o), C.byref(h))
+        if st != L.OK:
+            _raise(st)
+        state.update(handle=_CholHandle(h), Hnnz=(nh if H is not None else None), keep=keep, kp=kp, ki=ki,
+                     tslot=slot[:nt], tk=tk, tc=tc, hslot=slot[nt:nt + nh], aslot=slot[nt + nh + n:nt + nh + n + len(Ai)],
+                     nk=len(uniq), kv=np.zeros(len(uniq)), u=np.zeros(N))
+
+    def factor(W, H=None, Df=None):
+        if Df is not None:
+            raise ValueError("kvxopt_b200.kkt.ldl2 does not support nonlinear constraints")
+        if state["handle"] is None:
+            _create(H)
+        if (H is None) != (state["Hnnz"] is None):
+            raise ValueError("H must be given in every call or in none")
+        di = np.ascontiguousarray(_vec(W["di"], m, "W['di']") if m else np.zeros(0), dtype=np.float64)
+        d2 = di * di
+        kv = np.bincount(state["tslot"], weights=state["tc"] * d2[state["tk"]], minlength=state["nk"]) if len(state["tk"]) \
+            else np.zeros(state["nk"])
+        if H is not None:
+            Hx = (_values(H) if not _is_dense(H) else _sparse_ccs(H, "H")[2])[state["keep"]]
+            if len(Hx) != state["Hnnz"]:
+                raise ValueError("the sparsity pattern of H changed between calls")
+            np.add.at(kv, state["hslot"], Hx)
+        kv[state["aslot"]] = Ax
+        kv = np.ascontiguousarray(kv)
+        state["kv"] = kv
+        handle = state["handle"]
+        minor = C.c_int64(0)
+        st = fn["b200s_chol_factorize"](handle.h, L.ptr_f64(kv), C.byref(minor))
+        state["factors"] = state.get("factors", 0) + 1
+        if st == L.NOT_POSDEF:
+            raise ArithmeticError("zero pivot in the LDL' factorization of the KKT matrix (column %d)" % minor.value)
+        if st != L.OK:
+            _raise(st)
+        u = state["u"]
+
+        def solve(x, y, z):
+            xf = _vec(x, n, "x")
+            yf = _vec(y, p, "y") if p else None
+            zf = _vec(z, m, "z") if m else np.zeros(0)
+            u[:n] = xf + Gm.T @ (d2 * zf) if m else xf
+            if p:
+                u[n:] = yf
+            st2 = fn["b200s_chol_solve"](handle.h, 0, L.ptr_f64(u), 1, N)
+            if st2 != L.OK:
+                _raise(st2)
+            xf[:] = u[:n]
+            if p:
+                yf[:] = u[n:]
+            if m:
+                zf[:] = di * (Gm @ u[:n] - zf)
+
+        return solve
+
+    def _info():
+        if state["handle"] is None:
+            return {}
+        inf = L.CholInfo()
+        fn["b200s_chol_info"](state["handle"].h, C.byref(inf))
+        return {"order": N, "nnz_L": inf.nnz_L, "flops": inf.flops, "nsuper": inf.nsuper, "max_front_rows": inf.max_front_rows,
+                "ms_analyze": inf.ms_analyze, "ms_factor_last": inf.ms_factor, "ms_solve_last": inf.ms_solve,
+                "factorizations": state.get("factors", 0)}
+
+    factor.info = _info
+    factor._state = state
     return factor
 
 

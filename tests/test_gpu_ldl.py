@@ -245,3 +245,37 @@ def test_qp_mini_coneqp_with_sparse_ldl(kvx, kktreg):
     assert sol["iterations"] == int(z["iters"])
     assert abs(sol["primal objective"] - float(z["pobj"])) <= 1e-8 * abs(float(z["pobj"]))
     assert f3.info()["factorizations"] >= sol["iterations"]
+
+
+@pytest.mark.parametrize("prefix", ["lp_", "qp_"])
+def test_kkt_ldl2_matches_reference_sytrf(prefix):
+    """kkt.ldl2 (2 x 2 system, misc.py:1128-1210) returns the same (ux, uy, W uz) as the reference's dense solvers: the golden
+    vectors of misc.kkt_ldl, which solves the same KKT system"""
+    from kvxopt_b200 import kkt
+    G, A, H, g = _kkt_case(prefix)
+    m, n = G.shape
+    factor = kkt.ldl2(G, {"l": m, "q": [], "s": []}, A)
+    W = {"d": g["d"].copy(), "di": 1.0 / g["d"]}
+    for _ in range(2):
+        solve = factor(W, H)
+        x, y, zz = g["bx"].copy(), g["by"].copy(), g["bz"].copy()
+        solve(x, y, zz)
+        for got, want in ((x, g["ux"]), (y, g["uy"]), (zz, g["uz"])):
+            if len(want):
+                assert np.linalg.norm(got - want) <= XREL_TOL * np.linalg.norm(want)
+
+
+def test_boeing2_ipm_with_sparse_ldl2(kvx):
+    from kvxopt import matrix, spmatrix, solvers
+    from kvxopt_b200 import kkt
+    z = np.load(os.path.join(GOLD, "boeing2_lp.npz"))
+    def spm(p, i, x, size):
+        cols = np.repeat(np.arange(size[1]), np.diff(p))
+        return spmatrix(x.tolist(), i.tolist(), cols.tolist(), tuple(int(s) for s in size))
+    G = spm(z["Gp"], z["Gi"], z["Gx"], z["G_size"]); A = spm(z["Ap"], z["Ai"], z["Ax"], z["A_size"])
+    c, h, b = matrix(z["c"]), matrix(z["h"]), matrix(z["b"])
+    dims = {"l": G.size[0], "q": [], "s": []}
+    sol = solvers.conelp(c, G, h, dims, A, b, kktsolver=kkt.ldl2(G, dims, A))
+    assert sol["status"] == "optimal"
+    assert sol["iterations"] == int(z["iters_ldl"])
+    assert abs(sol["primal objective"] - float(z["pobj_ldl"])) <= 1e-8 * abs(float(z["pobj_ldl"]))

@@ -335,3 +335,28 @@ def test_kkt_ldl_assembles_the_reference_matrix_and_fails_loudly_without_gpu():
             want[np.arange(n, n + p), np.arange(n, n + p)] = -r
             want[np.arange(n + p, n + p + m), np.arange(n + p, n + p + m)] = -1.0 - r
             assert np.abs(K - want).max() == 0.0
+
+
+def test_kkt_ldl2_assembles_the_reduced_matrix():
+    """kkt.ldl2 (counterpart of misc.kkt_ldl2, misc.py:1128-1210): the values sent to the engine are the lower triangle of
+    [[H + G' W^-2 G, A'], [A, 0]] evaluated from the fixed list of products g_ki g_kj"""
+    import scipy.sparse as sp
+    from kvxopt_b200 import kkt, _lib
+    rng = np.random.default_rng(3)
+    n, p, m = 12, 3, 20
+    G = sp.random(m, n, density=0.3, random_state=rng, format="csc")
+    A = sp.random(p, n, density=0.5, random_state=rng, format="csc")
+    Hh = sp.random(n, n, density=0.2, random_state=rng, format="csc"); H = (Hh + Hh.T + 5 * sp.identity(n)).tocsc()
+    di = np.exp(rng.standard_normal(m))
+    for Hm in (H, None):
+        factor = kkt.ldl2(G, {"l": m, "q": [], "s": []}, A)
+        try:
+            factor({"di": di.copy()}, Hm)
+            assert _lib.device_count() > 0
+        except RuntimeError:
+            assert _lib.device_count() == 0
+        st = factor._state
+        K = sp.csc_matrix((st["kv"], st["ki"], st["kp"]), shape=(n + p, n + p)).toarray()
+        S = (G.T @ sp.diags(di * di) @ G).toarray() + (H.toarray() if Hm is not None else 0.0)
+        want = np.zeros((n + p, n + p)); want[:n, :n] = np.tril(S); want[n:, :n] = A.toarray()
+        assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()

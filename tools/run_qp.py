@@ -62,6 +62,14 @@ elif mode in ("ldl", "ldlreg"):
     f3 = kkt.ldl(Gk, {"l": Gk.size[0], "q": [], "s": []}, spmatrix([], [], [], (0, Pk.size[0])), kktreg=1e-9 if mode == "ldlreg" else None)
     sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=lambda W: f3(W, Pk))
     print("sparse LDL' KKT solver:", f3.info())
+elif mode == "ldl2":
+    # sparse signed LDL' of the reduced 2 x 2 system (counterpart of the reference's dense 'ldl2')
+    from kvxopt_b200 import kkt
+    Pk, Gk = tosp(sp.tril(P)), tosp(G)
+    t0 = time.perf_counter()
+    f2 = kkt.ldl2(Gk, {"l": Gk.size[0], "q": [], "s": []}, spmatrix([], [], [], (0, Pk.size[0])))
+    sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=lambda W: f2(W, Pk))
+    print("sparse LDL' (2 x 2) KKT solver:", f2.info())
 else:
     sol = solvers.qp(tosp(sp.tril(P)), matrix(q), tosp(G), matrix(h))
 wall = time.perf_counter() - t0
