@@ -20,9 +20,9 @@ struct b200s_chol {
     bool numeric = false, profiling = false, ldl = false;
 };
 
-static_assert(B200S_OK == ST_OK && B200S_NOT_POSDEF == ST_NOT_POSDEF && B200S_SINGULAR == ST_SINGULAR &&
-              B200S_OUT_OF_MEMORY == ST_OOM && B200S_TOO_LARGE == ST_TOO_LARGE && B200S_INVALID == ST_INVALID &&
-              B200S_NO_DEVICE == ST_NO_DEVICE && B200S_CUDA_ERROR == ST_CUDA, "status codes out of sync");
+static_assert(int(B200S_OK) == ST_OK && int(B200S_NOT_POSDEF) == ST_NOT_POSDEF && int(B200S_SINGULAR) == ST_SINGULAR &&
+              int(B200S_OUT_OF_MEMORY) == ST_OOM && int(B200S_TOO_LARGE) == ST_TOO_LARGE && int(B200S_INVALID) == ST_INVALID &&
+              int(B200S_NO_DEVICE) == ST_NO_DEVICE && int(B200S_CUDA_ERROR) == ST_CUDA, "status codes out of sync");
 
 extern "C" {
 
