@@ -217,6 +217,12 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
     // L is built with symbolic row positions and remapped to pivotal positions at the end
     std::vector<i32> Li_tmp; std::vector<double> Lx_tmp;
     std::vector<i32> xi;
+    // Symmetric pruning (Eisenstat-Liu, as in KLU's kernel): once some later column k has U(j,k) != 0 and its pivot row in
+    // L(:,j), the rows of L(:,j) that were not pivotal then are all in L(:,k), so the depth-first search only needs the
+    // pivotal head [Lp[j]+1, lpend[j]) of column j.  The reach (as a set) is unchanged; the search drops from ~3x the
+    // cost of the numeric updates to a fraction of it on structurally symmetric patterns (power-flow Jacobians).
+    std::vector<i64> lpend(n, 0);
+    std::vector<char> pruned(n, 0);
     double fl = 0;
     int status = ST_OK;
     for (i32 b = 0; b < S.nblocks; b++) {
@@ -245,7 +251,7 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
                     const i32 jc = pivpos[r];
                     bool desc = false;
                     i64& pp = pstack.back();
-                    const i64 pend = (i64)Li_tmp.size() < N.Lp[jc + 1] ? (i64)Li_tmp.size() : N.Lp[jc + 1];
+                    const i64 pend = lpend[jc];
                     for (; pp < pend; pp++) {
                         const i32 rr = Li_tmp[pp];
                         if (mark[rr] != k) { mark[rr] = k; xi.push_back(rr); x[rr] = 0.0; }
@@ -292,7 +298,24 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
             for (i32 r : xi)
                 if (pivpos[r] < 0) { Li_tmp.push_back(r); Lx_tmp.push_back(x[r] / piv); }
             N.Lp[k + 1] = (i64)Li_tmp.size();
+            lpend[k] = N.Lp[k + 1];
             N.Fp[k + 1] = (i64)N.Fi.size();
+            // prune the columns j with U(j,k) != 0 whose L(:,j) holds this column's pivot row
+            for (i32 r : xi) {
+                const i32 j = pivpos[r];
+                if (j < 0 || r == prow || pruned[j]) continue;
+                const i64 b0 = N.Lp[j] + 1, b1 = N.Lp[j + 1];
+                bool has = false;
+                for (i64 pp = b0; pp < b1; pp++) if (Li_tmp[pp] == prow) { has = true; break; }
+                if (!has) continue;
+                i64 head = b0, tail = b1;
+                while (head < tail) {
+                    if (pivpos[Li_tmp[head]] >= 0) head++;
+                    else { tail--; std::swap(Li_tmp[head], Li_tmp[tail]); std::swap(Lx_tmp[head], Lx_tmp[tail]); }
+                }
+                lpend[j] = head;
+                pruned[j] = 1;
+            }
             for (i32 r : xi) x[r] = 0.0;
         }
     }
@@ -300,14 +323,21 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
     N.Li.resize(Li_tmp.size()); N.Lx = Lx_tmp;
     for (size_t p = 0; p < Li_tmp.size(); p++) N.Li[p] = pivpos[Li_tmp[p]];
     for (size_t p = 0; p < N.Fi.size(); p++) N.Fi[p] = pivpos[N.Fi[p]];
+    // rows ascending inside every column by a double transposition (bucket by row, then read the rows in order):
+    // O(nnz + n) instead of one comparison sort per column
     auto sort_cols = [&](std::vector<i64>& Cp, std::vector<i32>& Ci, std::vector<double>& Cx) {
-        std::vector<std::pair<i32, double>> tmp;
-        for (i32 k = 0; k < n; k++) {
-            tmp.clear();
-            for (i64 p = Cp[k]; p < Cp[k + 1]; p++) tmp.emplace_back(Ci[p], Cx[p]);
-            std::sort(tmp.begin(), tmp.end(), [](const std::pair<i32, double>& a, const std::pair<i32, double>& b) { return a.first < b.first; });
-            for (i64 p = Cp[k]; p < Cp[k + 1]; p++) { Ci[p] = tmp[p - Cp[k]].first; Cx[p] = tmp[p - Cp[k]].second; }
-        }
+        const i64 nz = Cp[n];
+        if (nz == 0) return;
+        std::vector<i64> rp(n + 1, 0), cpos(Cp.begin(), Cp.end() - 1);
+        for (i64 p = 0; p < nz; p++) rp[Ci[p] + 1]++;
+        for (i32 i = 0; i < n; i++) rp[i + 1] += rp[i];
+        std::vector<i32> rc(nz); std::vector<double> rx(nz);
+        for (i32 k = 0; k < n; k++)
+            for (i64 p = Cp[k]; p < Cp[k + 1]; p++) { const i64 q = rp[Ci[p]]++; rc[q] = k; rx[q] = Cx[p]; }
+        // rp[i] is now the end of row i
+        i64 q = 0;
+        for (i32 i = 0; i < n; i++)
+            for (; q < rp[i]; q++) { const i64 d = cpos[rc[q]]++; Ci[d] = i; Cx[d] = rx[q]; }
     };
     sort_cols(N.Lp, N.Li, N.Lx);
     sort_cols(N.Up, N.Ui, N.Ux);
