@@ -385,6 +385,13 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
     // row position (pivotal) -> slot inside the current column
     std::vector<i32> slot_of_row(n, -1), pinvnum(n);
     for (i32 k = 0; k < n; k++) pinvnum[N.Pnum[k]] = k;
+    {
+        // one destination per multiply-add of the factorization, one update per off-diagonal U entry
+        const size_t nupd = (size_t)(N.Up[n] - n);
+        P.dest.reserve((size_t)(N.flops / 2) + 16);
+        P.upd_src.reserve(nupd); P.upd_uslot.reserve(nupd); P.upd_lslot.reserve(nupd); P.upd_cnt.reserve(nupd); P.upd_dest.reserve(nupd);
+        P.upd_ptr.reserve((size_t)n + 1);
+    }
     for (i32 k = 0; k < n; k++) {
         for (i64 p = N.Up[k]; p < N.Up[k + 1]; p++) { i32 sl = (i32)(uslot0[k] + (p - N.Up[k])); P.slot_row[sl] = N.Ui[p]; slot_of_row[N.Ui[p]] = sl; }
         for (i64 p = N.Lp[k] + 1; p < N.Lp[k + 1]; p++) { i32 sl = (i32)(P.lslot0[k] + (p - N.Lp[k] - 1)); P.slot_row[sl] = N.Li[p]; slot_of_row[N.Li[p]] = sl; }
