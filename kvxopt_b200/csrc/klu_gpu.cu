@@ -718,29 +718,40 @@ struct KluSolveLvlH {
 
 static void build_solve_levels(const KluSymbolic& S, const KluNumeric& N, const KluPlan& P, bool trans, KluSolveLvlH& H) {
     const int n = P.n;
-    std::vector<std::vector<std::pair<int, int>>> terms(2 * (size_t)n);     // per task: (slot, src row of V)
+    // per task t (Y rows 0..n-1, Z rows n..2n-1): terms [tp[t], tp[t+1]) = (slot, src row of V), in column order; built
+    // in two passes over the factor (count, fill) -- no per-task containers
+    std::vector<int> tp(2 * (size_t)n + 1, 0), tsl, tsr;
     std::vector<int> diag(2 * (size_t)n, -1);
-    for (int k = 0; k < n; k++) {
-        const long long u0 = N.Up[k], u1 = N.Up[k + 1] - 1, l0 = N.Lp[k] + 1, l1 = N.Lp[k + 1], f0 = N.Fp[k], f1 = N.Fp[k + 1];
-        const int us = (int)P.cbeg[k], ls = P.lslot0[k], fs = P.fslot0[k];
-        if (!trans) {
-            for (long long p = l0; p < l1; p++) terms[N.Li[p]].push_back({ls + (int)(p - l0), k});                  // L(i,k) Y[k]
-            for (long long p = f0; p < f1; p++) terms[N.Fi[p]].push_back({fs + (int)(p - f0), n + k});              // F(i,k) Z[k]
-            for (long long p = u0; p < u1; p++) terms[(size_t)n + N.Ui[p]].push_back({us + (int)(p - u0), n + k});  // U(i,k) Z[k]
-            diag[(size_t)n + k] = P.udiag_slot[k];
-        } else {
-            for (long long p = u0; p < u1; p++) terms[k].push_back({us + (int)(p - u0), N.Ui[p]});                  // U(p,k) Y[p]
-            for (long long p = f0; p < f1; p++) terms[k].push_back({fs + (int)(p - f0), n + N.Fi[p]});              // F(p,k) Z[p]
-            for (long long p = l0; p < l1; p++) terms[(size_t)n + k].push_back({ls + (int)(p - l0), n + N.Li[p]});  // L(p,k) Z[p]
-            diag[k] = P.udiag_slot[k];
+    auto sweep = [&](auto&& emit) {
+        for (int k = 0; k < n; k++) {
+            const long long u0 = N.Up[k], u1 = N.Up[k + 1] - 1, l0 = N.Lp[k] + 1, l1 = N.Lp[k + 1], f0 = N.Fp[k], f1 = N.Fp[k + 1];
+            const int us = (int)P.cbeg[k], ls = P.lslot0[k], fs = P.fslot0[k];
+            if (!trans) {
+                for (long long p = l0; p < l1; p++) emit(N.Li[p], ls + (int)(p - l0), k);                  // L(i,k) Y[k]
+                for (long long p = f0; p < f1; p++) emit(N.Fi[p], fs + (int)(p - f0), n + k);              // F(i,k) Z[k]
+                for (long long p = u0; p < u1; p++) emit(n + N.Ui[p], us + (int)(p - u0), n + k);          // U(i,k) Z[k]
+            } else {
+                for (long long p = u0; p < u1; p++) emit(k, us + (int)(p - u0), N.Ui[p]);                  // U(p,k) Y[p]
+                for (long long p = f0; p < f1; p++) emit(k, fs + (int)(p - f0), n + N.Fi[p]);              // F(p,k) Z[p]
+                for (long long p = l0; p < l1; p++) emit(n + k, ls + (int)(p - l0), n + N.Li[p]);          // L(p,k) Z[p]
+            }
         }
+    };
+    sweep([&](int t, int, int) { tp[t + 1]++; });
+    for (int t = 0; t < 2 * n; t++) tp[t + 1] += tp[t];
+    tsl.resize(tp[2 * (size_t)n]); tsr.resize(tp[2 * (size_t)n]);
+    {
+        std::vector<int> cur(tp.begin(), tp.end() - 1);
+        sweep([&](int t, int slot, int src) { const int q = cur[t]++; tsl[q] = slot; tsr[q] = src; });
     }
+    for (int k = 0; k < n; k++) diag[(trans ? 0 : (size_t)n) + k] = P.udiag_slot[k];
+    auto nterms = [&](int t) { return tp[t + 1] - tp[t]; };
     // levels in a topological order of the sequential algorithm
     std::vector<int> level(2 * (size_t)n, 0);
     auto visit = [&](int t) {
         int lv = 0;
         if (t >= n) lv = level[t - n] + 1;                        // Z-task of i needs Y[i]
-        for (auto& e : terms[t]) lv = std::max(lv, level[e.second] + 1);
+        for (int q = tp[t]; q < tp[t + 1]; q++) lv = std::max(lv, level[tsr[q]] + 1);
         level[t] = lv;
     };
     if (!trans)
@@ -765,7 +776,7 @@ static void build_solve_levels(const KluSymbolic& S, const KluNumeric& N, const 
     for (int t = 0; t < 2 * n; t++) ids[t] = t;
     std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) {
         if (level[x] != level[y]) return level[x] < level[y];
-        return terms[x].size() > terms[y].size();
+        return nterms(x) > nterms(y);
     });
     // Emit the work items ("parts") level by level.  A level with fewer tasks than warps whose tasks are long is
     // run in split mode: every task is cut into parts of <= 32 terms that different warps sum concurrently into
@@ -776,14 +787,15 @@ static void build_solve_levels(const KluSymbolic& S, const KluNumeric& N, const 
     for (int l = 0; l < nlev; l++) {
         const int q0 = H.lvl_ptr[l], q1 = H.lvl_ptr[l + 1];
         int parts = 0;
-        for (int q = q0; q < q1; q++) parts += std::max<int>(1, ((int)terms[ids[q]].size() + KLU_SOLVE_PART - 1) / KLU_SOLVE_PART);
+        for (int q = q0; q < q1; q++) parts += std::max<int>(1, (nterms(ids[q]) + KLU_SOLVE_PART - 1) / KLU_SOLVE_PART);
         const bool split = (q1 - q0) < KLU_SOLVE_WARPS && parts > (q1 - q0) && parts <= KLU_SOLVE_MAXPARTS;
         H.mode[l] = split ? 1 : 0;
         for (int q = q0; q < q1; q++) {
             const int t = ids[q];
             const int base = (int)H.tslot.size();
-            for (auto& e : terms[t]) { H.tslot.push_back(e.first); H.tsrc.push_back(e.second); }
-            const int cnt = (int)terms[t].size();
+            H.tslot.insert(H.tslot.end(), tsl.begin() + tp[t], tsl.begin() + tp[t + 1]);
+            H.tsrc.insert(H.tsrc.end(), tsr.begin() + tp[t], tsr.begin() + tp[t + 1]);
+            const int cnt = nterms(t);
             if (!split) {
                 H.rec.push_back(make_int4(t, base, base + cnt, diag[t]));
                 H.extra.push_back(0);
@@ -1095,9 +1107,9 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
             if ((rc = up(&WD.bseg_ptr, bsp))) return rc;
             if ((rc = up(&WD.segd, sgd))) return rc;
         }
-        std::vector<unsigned> be(P.bentry.begin(), P.bentry.end()), wb(P.wblob.begin(), P.wblob.end());
-        if ((rc = up(&WD.bentry, be))) return rc;
-        if ((rc = up(&WD.wblob, wb))) return rc;
+        static_assert(sizeof(unsigned) == sizeof(uint32_t), "plan tables are uploaded as they are");
+        if ((rc = up(&WD.bentry, P.bentry))) return rc;       // the largest table (11.5 MB on ACTIVSg2000): no staging copy
+        if ((rc = up(&WD.wblob, P.wblob))) return rc;
         WD.spine0 = use_wave ? P.spine0 : P.n;
         spine_nd = use_wave ? P.spine_nd : 0;
         if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;

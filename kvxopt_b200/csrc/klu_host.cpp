@@ -535,7 +535,8 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         P.wave_hasdep.assign(nw, 0);
         P.wbatch_ptr.assign(1, 0);
         P.bseg_ptr.assign(1, 0);
-        std::vector<i32> srcs;
+        std::vector<i32> srcs, matched, users;
+        std::vector<i64> ucur;
         for (i32 w = 0; w < nw; w++) {
             const i32 k0 = P.wave_col0[w];
             srcs.clear();
@@ -548,13 +549,13 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             std::sort(srcs.begin(), srcs.end());
             srcs.erase(std::unique(srcs.begin(), srcs.end()), srcs.end());
             i32 fill = KLU_CHUNK_ROWS;      // rows used in the open batch (full => start a new one)
-            std::vector<i32> matched(P.wave_col0[w + 1] - k0, 0);      // segments of the open batch used by each column
-            std::vector<i64> ucur(P.wave_col0[w + 1] - k0);
+            matched.assign(P.wave_col0[w + 1] - k0, 0);                 // segments of the open batch used by each column
+            ucur.resize(P.wave_col0[w + 1] - k0);
             for (i32 c = k0; c < P.wave_col0[w + 1]; c++) ucur[c - k0] = P.upd_ptr[c];
             for (i32 j : srcs) {
                 const i32 total = (i32)(N.Lp[j + 1] - N.Lp[j] - 1);
                 // columns of the wave that use source j
-                std::vector<i32> users;
+                users.clear();
                 for (i32 c = k0; c < P.wave_col0[w + 1]; c++) {
                     i64& u = ucur[c - k0];
                     if (u < P.upd_split[c] && P.upd_src[u] == j) { users.push_back(c - k0); u++; }
