@@ -187,6 +187,30 @@ def test_klu_pivot_identity_on_reference_matrices(name):
     fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
 
 
+@pytest.mark.parametrize("n,dens,seed", [(200, 0.03, 1), (600, 0.008, 2), (1500, 0.003, 3)])
+def test_klu_pruned_pivot_search_on_unsymmetric_patterns(n, dens, seed):
+    """The host pivot search prunes its depth-first search (Eisenstat-Liu, as KLU's kernel does): on unsymmetric patterns
+    with a weak diagonal (off-diagonal pivots, several BTF blocks) the factors still satisfy R P A Q = L U + F, every column
+    of L and U is sorted by row, L has a unit diagonal and |L| <= 1/tol."""
+    rng = np.random.default_rng(seed)
+    A = sp.random(n, n, dens, random_state=rng, format="csc") + sp.diags(0.05 * rng.standard_normal(n))
+    st, S, N, A = klu_pivot(A)
+    assert st == 0
+    pat = klu_pattern(N, n)
+    inf, Lp, Li, Up, Ui, Fp, Fi, P, Q, R = pat
+    Lx = np.zeros(max(inf.nnz_L, 1)); Ux = np.zeros(max(inf.nnz_U, 1)); Fx = np.zeros(max(inf.nnz_F, 1)); Rs = np.zeros(n)
+    fn["b200s_klu_extract_host"](N, L.ptr_f64(Lx), L.ptr_f64(Ux), L.ptr_f64(Fx), L.ptr_f64(Rs))
+    # threshold pivoting with tol = 1e-3 lets the entries of U grow (1e6 - 1e8 here): the bound is relative to that growth
+    assert identity_error(A, A.data, Rs, pat, Lx[:inf.nnz_L], Ux[:inf.nnz_U], Fx[:inf.nnz_F]) < 1e-13 * max(1.0, np.abs(Ux).max())
+    for k in range(n):
+        li = Li[Lp[k]:Lp[k + 1]]; ui = Ui[Up[k]:Up[k + 1]]
+        assert li[0] == k and Lx[Lp[k]] == 1.0 and np.all(np.diff(li) > 0)
+        assert ui[-1] == k and np.all(np.diff(ui) > 0)
+    assert np.abs(Lx[:inf.nnz_L]).max() <= 1e3 * (1 + 1e-12)
+    assert sorted(P) == list(range(n)) and sorted(Q) == list(range(n))
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
 def emulate_plan(N, A, vals):
     """replays the static refactorization plan with numpy exactly as the CUDA kernels do"""
     n = A.shape[0]
