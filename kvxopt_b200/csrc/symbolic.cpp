@@ -234,7 +234,13 @@ void chol_analyze(i64 n64, const i64* colptr, const i64* rowind, char uplo, cons
         pm.swap(pm2);
         for (i32 k = 0; k < n; k++) ip[pm[k]] = k;
         build_perm_pattern(n, colptr, rowind, use, ip, PP);
-        parent = etree(n, PP);
+        // the elimination tree of the postordered matrix is the first tree relabelled (no second run of Liu's algorithm)
+        {
+            std::vector<i32> ipost(n);
+            for (i32 k = 0; k < n; k++) ipost[post[k]] = k;
+            parent.assign(n, -1);
+            for (i32 k = 0; k < n; k++) { const i32 q = par0[post[k]]; parent[k] = q < 0 ? -1 : ipost[q]; }
+        }
         for (i32 j = 0; j < n; j++)
             if (parent[j] != -1 && parent[j] <= j) throw std::logic_error("etree is not postordered");
         cc = column_counts(n, PP, parent);
@@ -336,6 +342,7 @@ void chol_analyze(i64 n64, const i64* colptr, const i64* rowind, char uplo, cons
     std::vector<std::vector<i32>> kids(ns);
     plan.rows.clear();
     std::vector<i32> tmp;
+    std::vector<size_t> runs;
     for (i32 s = 0; s < ns; s++) {
         Front& f = F[s];
         const i32 c1 = f.col0 + f.nc;
@@ -345,14 +352,29 @@ void chol_analyze(i64 n64, const i64* colptr, const i64* rowind, char uplo, cons
                 i32 i = PP.li[p];
                 if (i >= c1 && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
             }
+        // A's rows are sorted once; every child's update rows arrive sorted (a filtered copy of its sorted row list), so
+        // the list is a sequence of sorted runs that is merged pairwise instead of sorted from scratch
+        std::sort(tmp.begin(), tmp.end());
+        runs.clear();
+        runs.push_back(0);
+        if (!tmp.empty()) runs.push_back(tmp.size());
         for (i32 c : kids[s]) {
             const Front& g = F[c];
             for (i32 k = g.nc; k < g.nr; k++) {
                 i32 i = plan.rows[g.rowptr + k];
                 if (i >= c1 && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
             }
+            if (tmp.size() > runs.back()) runs.push_back(tmp.size());
         }
-        std::sort(tmp.begin(), tmp.end());
+        while (runs.size() > 2) {
+            size_t w = 1;
+            for (size_t r = 0; r + 2 < runs.size(); r += 2) {
+                std::inplace_merge(tmp.begin() + runs[r], tmp.begin() + runs[r + 1], tmp.begin() + runs[r + 2]);
+                runs[w++] = runs[r + 2];
+            }
+            if ((runs.size() - 1) % 2 == 1) runs[w++] = runs.back();      // odd run out: carried to the next round
+            runs.resize(w);
+        }
         f.rowptr = (i64)plan.rows.size();
         f.nr = f.nc + (i32)tmp.size();
         for (i32 j = f.col0; j < c1; j++) plan.rows.push_back(j);
