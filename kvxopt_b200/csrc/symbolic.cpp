@@ -27,9 +27,10 @@ struct PermPattern {
     std::vector<i32> li, ui;   // li: rows below the diagonal of each column; ui: columns left of the diagonal of each row
 };
 
+// ui (row lists) is all the elimination tree needs, li (column lists) all that the column counts and the fronts need
 template <class Sel>
 void build_perm_pattern(i64 n, const i64* colptr, const i64* rowind, Sel use, const std::vector<i32>& iperm,
-                        PermPattern& P) {
+                        PermPattern& P, bool with_li = true, bool with_ui = true) {
     P.lp.assign(n + 1, 0);
     P.up.assign(n + 1, 0);
     for (i64 j = 0; j < n; j++)
@@ -38,8 +39,8 @@ void build_perm_pattern(i64 n, const i64* colptr, const i64* rowind, Sel use, co
             if (i == j || !use(i, j)) continue;
             i32 r = iperm[i], c = iperm[j];
             if (r < c) std::swap(r, c);
-            P.lp[c + 1]++;
-            P.up[r + 1]++;
+            if (with_li) P.lp[c + 1]++;
+            if (with_ui) P.up[r + 1]++;
         }
     for (i64 j = 0; j < n; j++) { P.lp[j + 1] += P.lp[j]; P.up[j + 1] += P.up[j]; }
     P.li.resize(P.lp[n]);
@@ -51,8 +52,8 @@ void build_perm_pattern(i64 n, const i64* colptr, const i64* rowind, Sel use, co
             if (i == j || !use(i, j)) continue;
             i32 r = iperm[i], c = iperm[j];
             if (r < c) std::swap(r, c);
-            P.li[pl[c]++] = r;
-            P.ui[pu[r]++] = c;
+            if (with_li) P.li[pl[c]++] = r;
+            if (with_ui) P.ui[pu[r]++] = c;
         }
 }
 
@@ -226,14 +227,14 @@ void chol_analyze(i64 n64, const i64* colptr, const i64* rowind, char uplo, cons
         std::vector<i32> ip(n);
         for (i32 k = 0; k < n; k++) ip[pm[k]] = k;
         PermPattern P0;
-        build_perm_pattern(n, colptr, rowind, use, ip, P0);
+        build_perm_pattern(n, colptr, rowind, use, ip, P0, false);
         std::vector<i32> par0 = etree(n, P0);
         std::vector<i32> post = postorder(n, par0);
         std::vector<i32> pm2(n);
         for (i32 k = 0; k < n; k++) pm2[k] = pm[post[k]];
         pm.swap(pm2);
         for (i32 k = 0; k < n; k++) ip[pm[k]] = k;
-        build_perm_pattern(n, colptr, rowind, use, ip, PP);
+        build_perm_pattern(n, colptr, rowind, use, ip, PP, true, false);
         // the elimination tree of the postordered matrix is the first tree relabelled (no second run of Liu's algorithm)
         {
             std::vector<i32> ipost(n);
