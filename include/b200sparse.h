@@ -73,11 +73,15 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
                                 char uplo, const b200s_int* perm, const b200s_chol_opts* opts,
                                 b200s_chol** out);
 
-/* cholmod.numeric (src/C/cholmod.c:322-398): cholmod_l_factorize :362 on a matrix with the pattern
- * given to analyze.  val[k] belongs to (rowind[k], column of k) of the SAME colptr/rowind.
+/* cholmod.numeric (src/C/cholmod.c:322-398): cholmod_l_factorize :362.  (colptr, rowind, val) is the caller's matrix as
+ * the reference rebuilds it on every call (pack :132-181).  Its pattern is compared with the one given to analyze (one
+ * memcmp on the fast path); a different pattern is re-mapped through A's own indices: analysed entries A does not have
+ * are zero (a subset pattern is accepted, as by CHOLMOD), an entry of the referenced triangle outside the analysed pattern
+ * returns B200S_INVALID.  colptr = rowind = NULL: the caller guarantees the analysed pattern and order (values only).
  * On B200S_NOT_POSDEF *minor_out is the first non-positive pivot column (in permuted order, like
  * L->minor, cholmod.c:376-380). */
-b200s_status b200s_chol_factorize(b200s_chol* F, const double* val, b200s_int* minor_out);
+b200s_status b200s_chol_factorize(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                  b200s_int* minor_out);
 /* Same with val already resident in device memory (HBM); used by bench `value`. */
 b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200s_int* minor_out);
 

@@ -47,7 +47,7 @@ SIGNATURES = {
     "b200s_set_device": (C.c_int, C.c_int),
     "b200s_chol_default_opts": (None, C.POINTER(CholOpts)),
     "b200s_chol_analyze": (C.c_int, i64, p_i64, p_i64, C.c_char, p_i64, C.POINTER(CholOpts), C.POINTER(vp)),
-    "b200s_chol_factorize": (C.c_int, vp, p_f64, p_i64),
+    "b200s_chol_factorize": (C.c_int, vp, p_i64, p_i64, p_f64, p_i64),
     "b200s_chol_factorize_dev": (C.c_int, vp, vp, p_i64),
     "b200s_chol_solve": (C.c_int, vp, C.c_int, p_f64, i64, i64),
     "b200s_chol_solve_dev": (C.c_int, vp, C.c_int, vp, i64, i64),

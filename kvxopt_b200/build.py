@@ -41,7 +41,7 @@ def build(force=False, verbose=True):
         if p.wait() != 0:
             raise RuntimeError("nvcc failed on " + s)
     if force or procs or _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -39,8 +39,9 @@ _py.PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
 
 # Raw-address variants for use inside capsule destructors: the capsule is being deallocated there
 # (refcount 0), so it must not be wrapped in a py_object (that would resurrect and re-free it).
-_raw_GetPointer = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p)(("PyCapsule_GetPointer", _py))
-_raw_GetName = C.CFUNCTYPE(C.c_char_p, C.c_void_p)(("PyCapsule_GetName", _py))
+# PYFUNCTYPE: these are CPython API functions and must be called with the GIL held (CFUNCTYPE would drop it).
+_raw_GetPointer = C.PYFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p)(("PyCapsule_GetPointer", _py))
+_raw_GetName = C.PYFUNCTYPE(C.c_char_p, C.c_void_p)(("PyCapsule_GetName", _py))
 
 
 @C.CFUNCTYPE(None, C.c_void_p)
@@ -117,9 +118,8 @@ def _size(A):
 def _ccs(A):
     """(colptr int64, rowind int64, values float64) of a sparse matrix without changing its pattern"""
     if _is_kvx(A):
-        cp, ri, vx = A.CCS
-        return (np.array(cp, dtype=np.int64).reshape(-1), np.array(ri, dtype=np.int64).reshape(-1),
-                np.array(vx, dtype=np.float64).reshape(-1))
+        cp, ri, vx = A.CCS        # fresh copies owned by these matrix objects: viewed, not copied again
+        return (_flat_view(cp, np.int64), _flat_view(ri, np.int64), _flat_view(vx, np.float64))
     import scipy.sparse as sp
     if not sp.isspmatrix_csc(A) and not (hasattr(sp, "csc_array") and isinstance(A, sp.csc_array)):
         A = A.tocsc()
@@ -128,6 +128,14 @@ def _ccs(A):
         A.sort_indices()
     return (np.ascontiguousarray(A.indptr, dtype=np.int64), np.ascontiguousarray(A.indices, dtype=np.int64),
             np.ascontiguousarray(A.data, dtype=np.float64))
+
+
+def _flat_view(m, dtype):
+    """1-D numpy view of a kvxopt dense matrix (buffer protocol; the array keeps the matrix alive); a copy only when the
+    element type differs"""
+    if len(m) == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ascontiguousarray(np.asarray(memoryview(m)).reshape(-1), dtype=dtype)
 
 
 def _values(A):
@@ -247,9 +255,9 @@ def _analyze(A, p, uplo, o):
     return h, vx
 
 
-def _factorize(h, vx):
+def _factorize(h, vx, cp=None, ri=None):
     minor = C.c_int64(0)
-    st = fn["b200s_chol_factorize"](h, L.ptr_f64(vx), C.byref(minor))
+    st = fn["b200s_chol_factorize"](h, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(minor))
     if st == L.NOT_POSDEF:
         raise ArithmeticError(int(minor.value))
     if st != L.OK:
@@ -274,10 +282,12 @@ def numeric(A, F):
     if _typecode(A) != "d":
         raise TypeError("F is not the CHOLMOD factor of a '%s' matrix" % _typecode(A))
     inf = _info(h)
-    vx = _values(A)               # the pattern was analysed in symbolic(); only the values travel (no index conversion)
-    if _size(A)[0] != inf.n or vx.size != inf.nnz_A:
+    if _size(A)[0] != inf.n:
         raise ValueError("factorization failed")
-    _factorize(h, vx)
+    # A's own pattern travels with the values (cholmod.c:340-358 rebuilds the cholmod_sparse from A on every call): the
+    # library compares it with the analysed pattern and re-maps the values when A stores a subset of it
+    cp, ri, vx = _ccs(A)
+    _factorize(h, vx, cp, ri)
 
 
 def _check_numeric(h):
@@ -455,4 +465,10 @@ def install(kvxopt_module=None):
     name = kvxopt_module.__name__
     sys.modules[name + ".cholmod"] = sys.modules[__name__]
     setattr(kvxopt_module, "cholmod", sys.modules[__name__])
+    # misc.py:21 binds `cholmod` at import time: rebind it where that already happened, or the KKT solvers of an already
+    # imported kvxopt.misc would silently keep the module they found first
+    for sub in ("misc", "coneprog", "cvxprog", "solvers"):
+        m = sys.modules.get(name + "." + sub)
+        if m is not None and hasattr(m, "cholmod"):
+            setattr(m, "cholmod", sys.modules[__name__])
     return sys.modules[__name__]

@@ -18,6 +18,10 @@ struct b200s_chol {
     CholTimes times;
     i64 minor = 0;
     bool numeric = false, profiling = false, ldl = false;
+    char uplo = 'L';
+    std::vector<i64> Ap, Ai;      // the pattern given to analyze: numeric() compares the caller's pattern with it (cholmod.c:322-398
+                                  // rebuilds the cholmod_sparse from A's own colptr/rowind on every call)
+    std::vector<double> remap;    // scratch of the slow path (pattern differs: values re-mapped through A's own indices)
 };
 
 static_assert(int(B200S_OK) == ST_OK && int(B200S_NOT_POSDEF) == ST_NOT_POSDEF && int(B200S_SINGULAR) == ST_SINGULAR &&
@@ -97,6 +101,10 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
         return B200S_INVALID;
     }
     F->minor = n;
+    F->uplo = uplo;
+    try {
+        if (n > 0) { F->Ap.assign(colptr, colptr + n + 1); F->Ai.assign(rowind, rowind + colptr[n]); }
+    } catch (const std::bad_alloc&) { delete F; return B200S_OUT_OF_MEMORY; }
     *out = F;
     return B200S_OK;
 }
@@ -125,7 +133,44 @@ static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_dev
     F->numeric = (st == ST_OK);
     return (b200s_status)st;
 }
-b200s_status b200s_chol_factorize(b200s_chol* F, const double* val, b200s_int* minor_out) {
+// Values of a matrix whose pattern differs from the analysed one, re-mapped onto the analysed entries: entries of the
+// analysed pattern that A does not have become zero (CHOLMOD accepts a subset pattern); an entry of A inside the
+// referenced triangle that the analysis has not seen is an error.  Row indices must be sorted within each column.
+static b200s_status remap_values(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val) {
+    const i64 n = F->plan.n;
+    try { F->remap.assign((size_t)F->plan.nnzA, 0.0); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    if (colptr[0] != 0) return B200S_INVALID;
+    for (i64 j = 0; j < n; j++) {
+        i64 q = F->Ap[j];
+        const i64 qe = F->Ap[j + 1];
+        i64 last = -1;
+        if (colptr[j + 1] < colptr[j]) return B200S_INVALID;
+        for (i64 k = colptr[j]; k < colptr[j + 1]; k++) {
+            const i64 r = rowind[k];
+            if (r < 0 || r >= n || r <= last) { set_last_error("numeric: row indices of A must be sorted and in range"); return B200S_INVALID; }
+            last = r;
+            const bool referenced = F->uplo == 'L' ? r >= j : r <= j;
+            while (q < qe && F->Ai[q] < r) q++;
+            if (q < qe && F->Ai[q] == r) F->remap[(size_t)q] = val[k];
+            else if (referenced) { set_last_error("numeric: A has an entry outside the pattern analysed by symbolic()"); return B200S_INVALID; }
+        }
+    }
+    return B200S_OK;
+}
+b200s_status b200s_chol_factorize(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                  b200s_int* minor_out) {
+    if (F && colptr && F->plan.n > 0) {
+        const i64 n = F->plan.n, nnz = F->plan.nnzA;
+        const bool same = colptr[n] == nnz && memcmp(colptr, F->Ap.data(), sizeof(i64) * (size_t)(n + 1)) == 0 &&
+                          (nnz == 0 || (rowind && memcmp(rowind, F->Ai.data(), sizeof(i64) * (size_t)nnz) == 0));
+        if (!same) {
+            if (!rowind && colptr[n] > 0) return B200S_INVALID;
+            if (!val && colptr[n] > 0) return B200S_INVALID;
+            b200s_status st = remap_values(F, colptr, rowind, val);
+            if (st != B200S_OK) return st;
+            return factorize_impl(F, F->remap.data(), false, minor_out);
+        }
+    }
     return factorize_impl(F, val, false, minor_out);
 }
 b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200s_int* minor_out) {

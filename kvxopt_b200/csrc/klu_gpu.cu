@@ -1204,6 +1204,9 @@ int KluDevice::enqueue_refactor(const double* dv, long long ldv, cudaEvent_t aft
 int KluDevice::refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host) {
     CUDA_TRY(cudaSetDevice(device));
     if (batch_ <= 0 || n == 0) return ST_OK;
+    // batches begun with refactor_begin still own the staging buffers and the factor storage: the blocking call may
+    // neither grow nor free them (the caching allocator would hand live blocks to another handle)
+    if (npending > 0) { set_last_error("refactor_batch: batches begun with refactor_batch_begin are still in flight, call refactor_batch_end first"); return ST_INVALID; }
     int rc = ensure_batch((int)batch_);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ev[0], stream));

@@ -54,6 +54,17 @@ def _sparse_ccs(M, what):
     return cp, ri, vx
 
 
+def _checked_values(H, pattern):
+    """values of H after checking that it still has the pattern (colptr, rowind) fixed by the first call: the term lists
+    and the scatter maps built then are only valid for that pattern (a same-length, different pattern would be scattered
+    through the old map and factor silently wrong)"""
+    cp, ri, vx = _sparse_ccs(H, "H")
+    if cp.shape != pattern[0].shape or ri.shape != pattern[1].shape or not (np.array_equal(cp, pattern[0]) and
+                                                                            np.array_equal(ri, pattern[1])):
+        raise ValueError("the sparsity pattern of H changed between calls")
+    return vx
+
+
 def _vec(v, n, what):
     flat, nr, nc = _dense_view(v)
     if nr * nc != n:
@@ -113,9 +124,7 @@ def chol2(G, dims, A, mnl=0):
                 raise ValueError("H was None in the first call and cannot appear later")
             # the pattern of H was fixed by the first call (as the reference's S += H on a fixed F['S'] assumes);
             # only the values travel -- no index conversion per interior-point iteration
-            Hx = _values(H) if not _is_dense(H) else _sparse_ccs(H, "H")[2]
-            if len(Hx) != len(state["Hpattern"][1]):
-                raise ValueError("the sparsity pattern of H changed between calls")
+            Hx = _checked_values(H, state["Hpattern"])
         elif state["Hpattern"] is not None:
             raise ValueError("H was given in the first call and is missing now")
         di = _vec(W["di"], ml, "W['di']") if ml else np.zeros(0)
@@ -204,6 +213,7 @@ def ldl(G, dims, A, mnl=0, kktreg=None):
             if _size(H) != (n, n):
                 raise TypeError("H must be a %d x %d matrix" % (n, n))
             Hp, Hi, Hx = _sparse_ccs(H, "H")
+            state["Hpat"] = (Hp.copy(), Hi.copy())
             Hc = np.repeat(np.arange(n, dtype=np.int64), np.diff(Hp))
             keep = np.nonzero(Hi >= Hc)[0]                       # lower triangle, as sytrf reads it
             Hi, Hc = Hi[keep], Hc[keep]
@@ -266,9 +276,7 @@ def ldl(G, dims, A, mnl=0, kktreg=None):
         v = state["vals"]
         k0 = 0
         if H is not None:
-            Hx = (_values(H) if not _is_dense(H) else _sparse_ccs(H, "H")[2])[state["keep"]]
-            if len(Hx) != state["Hnnz"]:
-                raise ValueError("the sparsity pattern of H changed between calls")
+            Hx = _checked_values(H, state["Hpat"])[state["keep"]]
             v[:len(Hx)] = Hx
             if reg:
                 v[state["hdiag"]] += reg
@@ -282,7 +290,7 @@ def ldl(G, dims, A, mnl=0, kktreg=None):
         np.take(v, state["src"], out=kv)
         handle = state["handle"]
         minor = C.c_int64(0)
-        st = fn["b200s_chol_factorize"](handle.h, L.ptr_f64(kv), C.byref(minor))
+        st = fn["b200s_chol_factorize"](handle.h, None, None, L.ptr_f64(kv), C.byref(minor))
         state["factors"] = state.get("factors", 0) + 1
         if st == L.NOT_POSDEF:
             raise ArithmeticError("zero pivot in the LDL' factorization of the KKT matrix (column %d)" % minor.value)
@@ -381,6 +389,7 @@ def ldl2(G, dims, A, mnl=0):
             if _size(H) != (n, n):
                 raise TypeError("H must be a %d x %d matrix" % (n, n))
             Hp, Hi, Hx = _sparse_ccs(H, "H")
+            state["Hpat"] = (Hp.copy(), Hi.copy())
             Hc = np.repeat(np.arange(n, dtype=np.int64), np.diff(Hp))
             keep = np.nonzero(Hi >= Hc)[0]
             Hi, Hc = Hi[keep], Hc[keep]
@@ -432,16 +441,14 @@ def ldl2(G, dims, A, mnl=0):
         kv = np.bincount(state["tslot"], weights=state["tc"] * d2[state["tk"]], minlength=state["nk"]) if len(state["tk"]) \
             else np.zeros(state["nk"])
         if H is not None:
-            Hx = (_values(H) if not _is_dense(H) else _sparse_ccs(H, "H")[2])[state["keep"]]
-            if len(Hx) != state["Hnnz"]:
-                raise ValueError("the sparsity pattern of H changed between calls")
+            Hx = _checked_values(H, state["Hpat"])[state["keep"]]
             np.add.at(kv, state["hslot"], Hx)
         kv[state["aslot"]] = Ax
         kv = np.ascontiguousarray(kv)
         state["kv"] = kv
         handle = state["handle"]
         minor = C.c_int64(0)
-        st = fn["b200s_chol_factorize"](handle.h, L.ptr_f64(kv), C.byref(minor))
+        st = fn["b200s_chol_factorize"](handle.h, None, None, L.ptr_f64(kv), C.byref(minor))
         state["factors"] = state.get("factors", 0) + 1
         if st == L.NOT_POSDEF:
             raise ArithmeticError("zero pivot in the LDL' factorization of the KKT matrix (column %d)" % minor.value)

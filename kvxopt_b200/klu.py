@@ -275,6 +275,8 @@ def refactor_batch_begin(Fn, values):
     fn["b200s_klu_info"](hn, C.byref(inf))
     if values.shape[1] != inf.nnz_A:
         raise ValueError("values must have nnz(A) = %d columns" % inf.nnz_A)
+    if values.shape[0] == 0 or inf.n == 0:
+        return                    # the library queues nothing for an empty batch: nothing to end either
     st = fn["b200s_klu_refactor_batch_begin"](hn, L.ptr_f64(values), values.shape[0], values.shape[1])
     if st != L.OK:
         _raise_status(st)
@@ -331,4 +333,8 @@ def install(kvxopt_module=None):
     name = kvxopt_module.__name__
     sys.modules[name + ".klu"] = sys.modules[__name__]
     setattr(kvxopt_module, "klu", sys.modules[__name__])
+    for sub in ("misc", "coneprog", "cvxprog", "solvers"):       # rebind where `klu` was bound at import time
+        m = sys.modules.get(name + "." + sub)
+        if m is not None and hasattr(m, "klu"):
+            setattr(m, "klu", sys.modules[__name__])
     return sys.modules[__name__]

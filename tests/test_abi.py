@@ -49,7 +49,7 @@ def test_numeric_refuses_without_gpu_or_runs_with_one():
     cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.copy()
     F = _lib.vp()
     assert _lib.fn["b200s_chol_analyze"](2, _lib.ptr_i64(cp), _lib.ptr_i64(ri), b"L", None, None, C.byref(F)) == 0
-    st = _lib.fn["b200s_chol_factorize"](F, _lib.ptr_f64(vx), None)
+    st = _lib.fn["b200s_chol_factorize"](F, None, None, _lib.ptr_f64(vx), None)
     if _lib.device_count() == 0:
         assert st == _lib.NO_DEVICE
     else:

@@ -338,3 +338,35 @@ def test_multi_rhs_solve_equals_column_by_column(cholmod):
             else:
                 x1 = np.asfortranarray(B[:, k - 1:k].copy()); cholmod.solve(F, x1, sys=sys_)
                 assert np.array_equal(X[:, k - 1], x1[:, 0]), (k, sys_)
+
+
+def test_numeric_with_subset_and_changed_pattern(cholmod):
+    """cholmod.numeric rebuilds the matrix from A's own pattern (cholmod.c:340-358): a matrix that stores a SUBSET of the
+    analysed pattern factors correctly (missing entries are zeros); an entry outside the analysed pattern is refused instead
+    of being scattered through the old map"""
+    n = 200
+    A = rand_spd(n, 0.03, 5)
+    Al = lower_ccs(A)
+    F = cholmod.symbolic(Al)
+    # drop a third of the off-diagonal entries: same analysis, subset pattern
+    coo = Al.tocoo()
+    rng = np.random.default_rng(3)
+    keep = (coo.row == coo.col) | (rng.uniform(size=coo.nnz) > 0.33)
+    As = sp.csc_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=(n, n)); As.sort_indices()
+    assert As.nnz < Al.nnz
+    cholmod.numeric(As, F)
+    B = rng.standard_normal((n, 2)); X = np.asfortranarray(B.copy())
+    cholmod.solve(F, X)
+    assert berr(sym_from_lower(As), X, B) <= BERR_TOL
+    # same factor object, full pattern again
+    cholmod.numeric(Al, F)
+    X = np.asfortranarray(B.copy()); cholmod.solve(F, X)
+    assert berr(sym_from_lower(Al), X, B) <= BERR_TOL
+    # an entry the analysis has not seen
+    lil = Al.tolil()
+    free = [(i, j) for j in range(3) for i in range(j + 1, n) if lil[i, j] == 0]
+    i, j = free[0]
+    lil[i, j] = 0.5
+    Ax = lil.tocsc(); Ax.sort_indices()
+    with pytest.raises(ValueError):
+        cholmod.numeric(Ax, F)

@@ -124,7 +124,7 @@ def test_zero_size_and_upper():
     E = sp.csc_matrix((0, 0))
     st, F = analyze(E)
     assert st == 0
-    assert fn["b200s_chol_factorize"](F, None, None) == 0          # n = 0 succeeds without a device
+    assert fn["b200s_chol_factorize"](F, None, None, None, None) == 0          # n = 0 succeeds without a device
     assert fn["b200s_chol_solve"](F, 0, None, 0, 1) == 0
     fn["b200s_chol_free"](F)
     A = rand_spd(40, 0.1, 4)
@@ -134,6 +134,29 @@ def test_zero_size_and_upper():
     assert stU == 0 and stL == 0
     assert plan_of(FU)[0].nnz_L == plan_of(FL)[0].nnz_L
     fn["b200s_chol_free"](FU); fn["b200s_chol_free"](FL)
+
+
+def test_numeric_rejects_entry_outside_analysed_pattern():
+    """cholmod.c:322-398 rebuilds the matrix from A's own pattern; the engine compares it with the analysed one: a
+    same-nnz but different pattern must not be scattered through the old map"""
+    A = lower_ccs(rand_spd(30, 0.15, 7))
+    st, F = analyze(A)
+    assert st == 0
+    cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.copy()
+    # move one off-diagonal entry of column 0 to a row the analysis has not seen (same nnz, different pattern)
+    col0 = ri[cp[0]:cp[1]]
+    free = [r for r in range(1, 30) if r not in set(col0.tolist())]
+    assert len(col0) > 1 and free
+    ri2 = ri.copy()
+    ri2[cp[1] - 1] = max(free)
+    seg = np.sort(ri2[cp[0]:cp[1]]); ri2[cp[0]:cp[1]] = seg
+    st = fn["b200s_chol_factorize"](F, L.ptr_i64(cp), L.ptr_i64(ri2), L.ptr_f64(vx), None)
+    if len(np.unique(seg)) == len(seg):
+        assert st == L.INVALID and "outside the pattern" in L.last_error()
+    # unsorted rows are refused as well
+    ri3 = ri.copy(); ri3[cp[0]], ri3[cp[0] + 1] = ri[cp[0] + 1], ri[cp[0]]
+    assert fn["b200s_chol_factorize"](F, L.ptr_i64(cp), L.ptr_i64(ri3), L.ptr_f64(vx), None) == L.INVALID
+    fn["b200s_chol_free"](F)
 
 
 # ---- KLU host ----------------------------------------------------------------------------------------
