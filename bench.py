@@ -1,19 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the B200 sparse direct-solve hot path.
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload klu|chol|all]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload all|klu|chol|configs]
 
 Headline workload (BASELINE.json configs[1]): batched KLU numeric refactorization of same-pattern value
 perturbations of the ACTIVSg2000 power-flow Jacobian, 4096 matrices per GPU (weak scaling: every rank owns its
 own 4096 matrices, no data-path collective).  metric = refactors/s.
   value : whole-job refactors/s with the value arrays already resident in HBM (b200s_klu_refactor_batch_dev),
           device-event time, max over ranks.
-  e2e   : the same through the public API kvxopt_b200.klu.refactor_batch with HOST (pinned) buffers: H2D of the
-          values and D2H of the per-matrix status inside the timed region.
-At N=1 the same line also carries `cholesky` (BASELINE configs[3]: 100^3 7-point Laplacian, nested dissection,
-supernodal Cholesky factor+solve ms and FP64 TFLOP/s, with the tensor-pipe roofline of the DMMA update kernel).
---impl reference times the CPU restatement of the reference's KLU path (oracle/, klu_refactor semantics) on all
-host cores of this box; SuiteSparse itself is not installable here.
+  e2e   : the same through the public API kvxopt_b200.klu.refactor_batch_begin/_end with HOST (pinned) buffers:
+          H2D of the values and D2H of the per-matrix status inside the timed region.
+At N>1 the line also carries `strong` (the fixed batch of 4096 of configs[1] split across the ranks) and
+`cholesky_subtree` (configs[3] over N GPUs).  At N=1 it carries one object per remaining BASELINE config:
+  config1  cholmod.linsolve on bcsstk24               config3  solvers.lp on boeing2 ('chol' KKT solver on the device)
+  cholesky 100^3 Laplacian supernodal Cholesky        config5  200k-variable QP through coneqp, IPM iterations/s
+each with its CPU baseline timed in the same run (cores stated).  configs 3 and 5 drive the UNMODIFIED reference
+interior-point code (the caller, oracle/_ref probe build) with the B200 KKT solvers plugged in through the reference's
+own kktsolver= API; they run in a child process because the reference's misc_solvers.scale is not safe under
+multi-threaded OpenBLAS at m >= 4e5 rows (OPENBLAS_NUM_THREADS=1 must be set before the BLAS loads).
+
+--impl reference times the CPU restatement of the reference's KLU path (oracle/klu_oracle.c) on all host cores of this
+box, with an ordering computed WITHOUT the product library (SuperLU's minimum degree on A'+A through scipy, then the
+oracle's own threshold-pivoting factorization), and reports both klu_factor (what reference src/C/klu.c:337 calls per
+matrix) and klu_refactor rates; its `cholesky` object times the oracle's supernodal Cholesky (OpenBLAS, all cores) on
+the 64^3 Laplacian that the GPU arm's `cholesky.sample_64` runs as well.  SuiteSparse itself is not installable here
+(DESIGN.md section 4).  libb200sparse.so is never loaded by the reference arm.
 """
 import argparse
 import ctypes as C
@@ -30,14 +41,19 @@ import scipy.sparse as sp
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, "tests", "golden")
+CHOL_SAMPLE_GRID = 64          # the grid both arms factor so that a like-for-like Cholesky ratio exists
 
 
-def load_activsg():
-    z = np.load(os.path.join(GOLD, "ACTIVSg2000.npz"))
+def load_golden(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
     n = int(z["n"])
     A = sp.csc_matrix((z["values"], z["rowind"].astype(np.int64), z["colptr"]), shape=(n, n))
     A.sort_indices()
     return A
+
+
+def load_activsg():
+    return load_golden("ACTIVSg2000")
 
 
 def perturbed_values(base, batch, rank, out=None):
@@ -57,53 +73,58 @@ def perturbed_values(base, batch, rank, out=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions, in-process through NVML every 5 ms (a
+    `nvidia-smi -lms` child needs ~100 ms to deliver its first sample and saw nothing of a 150 ms region in round 1).
+    start()/pause() bracket each timed region; samples taken outside are dropped."""
 
     def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.lines = []
+        self.index, self.samples, self.reasons = index, [], set()
+        self.max_mhz, self.err = None, None
+        self._on, self._stop = False, False
+        self.h = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception as e:      # reported, never fatal
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        masks = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop:
+            if self._on:
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    if self._on:
+                        self.samples.append(float(mhz))
+                        for name, m in masks.items():
+                            if r & m:
+                                self.reasons.add(name)
+                except Exception as e:
+                    self.err = repr(e)
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "25"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        self._on = True
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def pause(self):
+        self._on = False
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 7:
-                continue
-            try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, p[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._on, self._stop = False, True
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "how": "NVML in-process, 5 ms period, timed regions only"}
 
 
 def measured_peaks():
@@ -128,86 +149,6 @@ def traffic_from_profiles(key):
         return None
 
 
-# ------------------------------------------------------------------------------------------------------------
-# reference arm: the CPU restatement of the reference's KLU path on all host cores
-# ------------------------------------------------------------------------------------------------------------
-_W = {}
-
-
-def _worker_init(cp, ri, vx, P0, Q):
-    from oracle import KluOracle
-    _W["o"] = KluOracle(len(cp) - 1, cp, ri, vx, P0=P0, Q=Q)
-    _W["base"] = vx
-
-
-def _worker_run(args):
-    seed, count = args
-    o, base = _W["o"], _W["base"]
-    rng = np.random.default_rng(seed)
-    vals = [base * (1 + 1e-3 * rng.uniform(-1, 1, base.size)) for _ in range(count)]
-    t0 = time.perf_counter()
-    for v in vals:
-        o.refactor(v)
-    return time.perf_counter() - t0
-
-
-def host_pattern(A):
-    """pivot order of the product's host analysis (no GPU involved): gives the CPU port the same ordering"""
-    from kvxopt_b200 import _lib as L
-    fn = L.fn
-    n = A.shape[0]
-    cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
-    S = L.vp(); assert fn["b200s_klu_analyze"](n, L.ptr_i64(cp), L.ptr_i64(ri), C.byref(S)) == 0
-    N = L.vp(); assert fn["b200s_klu_pivot_host"](S, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(N)) == 0
-    P = np.zeros(n, np.int64); Q = np.zeros(n, np.int64)
-    fn["b200s_klu_extract"](N, None, None, None, None, None, None, None, None, None, L.ptr_i64(P), L.ptr_i64(Q), None, None)
-    inf = L.KluInfo(); fn["b200s_klu_info"](N, C.byref(inf))
-    d = inf.asdict()
-    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
-    return cp, ri, vx, P, Q, d
-
-
-def cpu_refactor_rate(A, cores, per_worker, steps, warmup):
-    import multiprocessing as mp
-    cp, ri, vx, P, Q, d = host_pattern(A)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_worker_init, initargs=(cp, ri, vx, P, Q)) as pool:
-        for w in range(warmup):
-            pool.map(_worker_run, [(1000 + w * cores + c, 2) for c in range(cores)])
-        times = []
-        for s in range(steps):
-            t0 = time.perf_counter()
-            pool.map(_worker_run, [(s * cores + c, per_worker) for c in range(cores)])
-            times.append(time.perf_counter() - t0)
-    total = float(np.sum(times))
-    return cores * per_worker * steps / total, total / steps * 1e3, d
-
-
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    A = load_activsg()
-    cores = os.cpu_count() or 1
-    per_worker = 24
-    rate, ms_step, d = cpu_refactor_rate(A, cores, per_worker, args.steps, max(args.warmup, 1))
-    line = {
-        "impl": "reference", "metric": "batched KLU refactors/sec", "value": rate, "unit": "refactors/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "klu_refactor_batch ACTIVSg2000 (n=4000, nnz=29336) same-pattern perturbations 1e-3",
-                   "batch_per_step": cores * per_worker, "ordering": "same BTF+AMD ordering and pivot order as the GPU arm"},
-        "cpu_baseline": {"value": rate, "unit": "refactors/s", "cores": cores, "kind": "port",
-                         "sample": "%d refactorizations per step (%d per core), oracle/klu_oracle.c klu_refactor "
-                                   "restatement; SuiteSparse KLU is not installable in this image" % (cores * per_worker, per_worker)},
-        "e2e": {"value": rate, "unit": "refactors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
-
-
-# ------------------------------------------------------------------------------------------------------------
-# Cholesky (configs[3]) -- reported inside the N=1 line
-# ------------------------------------------------------------------------------------------------------------
 def lap3d_lower(nx):
     """lower triangle of the 7-point Laplacian on an nx^3 grid (diag 6, off-diag -1), x fastest, as CCS"""
     n = nx ** 3
@@ -221,7 +162,140 @@ def lap3d_lower(nx):
     return A
 
 
-def bench_cholesky(nx, steps, fp64_peak):
+# ------------------------------------------------------------------------------------------------------------
+# CPU arms (oracle/, test infrastructure): nothing below this banner and above the next one touches libb200sparse.so
+# ------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def independent_klu_ordering(A):
+    """fill-reducing ordering for the CPU arm computed without the product: SuperLU's multiple-minimum-degree ordering of
+    A'+A (scipy.sparse.linalg.splu, permc_spec='MMD_AT_PLUS_A') -- the same class as KLU's AMD on A+A'; applied
+    symmetrically (P0 = Q), the oracle's factorization then does its own threshold partial pivoting (tol 1e-3)"""
+    import scipy.sparse.linalg as spla
+    lu = spla.splu(A.tocsc(), permc_spec="MMD_AT_PLUS_A")
+    return np.argsort(lu.perm_c).astype(np.int64)
+
+
+def _worker_init(cp, ri, vx, q):
+    from oracle import KluOracle
+    _W["args"] = (len(cp) - 1, cp, ri)
+    _W["q"] = q
+    _W["o"] = KluOracle(len(cp) - 1, cp, ri, vx, P0=q, Q=q)
+    _W["base"] = vx
+
+
+def _worker_run(args):
+    from oracle import KluOracle
+    seed, count, mode = args
+    o, base = _W["o"], _W["base"]
+    rng = np.random.default_rng(seed)
+    vals = [base * (1 + 1e-3 * rng.uniform(-1, 1, base.size)) for _ in range(count)]
+    t0 = time.perf_counter()
+    if mode == "refactor":
+        for v in vals:
+            o.refactor(v)
+    else:       # klu_l_factor: pattern discovery + pivot search per matrix, what klu.numeric (klu.c:337) does
+        n, cp, ri = _W["args"]
+        for v in vals:
+            KluOracle(n, cp, ri, v, P0=_W["q"], Q=_W["q"])
+    return time.perf_counter() - t0
+
+
+def cpu_klu_rates(A, cores, per_worker, steps, warmup):
+    import multiprocessing as mp
+    cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+    q = independent_klu_ordering(A)
+    from oracle import KluOracle
+    o = KluOracle(A.shape[0], cp, ri, vx, P0=q, Q=q)
+    stats = {"nnz_L": o.nnz_L, "nnz_U": o.nnz_U, "flops": o.flops}
+    ctx = mp.get_context("fork")
+    res = {}
+    with ctx.Pool(cores, initializer=_worker_init, initargs=(cp, ri, vx, q)) as pool:
+        for mode, count in (("refactor", per_worker), ("factor", max(per_worker // 4, 2))):
+            for w in range(warmup):
+                pool.map(_worker_run, [(1000 + w * cores + c, 2, mode) for c in range(cores)])
+            times = []
+            for s in range(steps):
+                t0 = time.perf_counter()
+                pool.map(_worker_run, [(s * cores + c, count, mode) for c in range(cores)])
+                times.append(time.perf_counter() - t0)
+            total = float(np.sum(times))
+            res[mode] = (cores * count * steps / total, total / steps * 1e3, cores * count)
+    return res, stats
+
+
+def cpu_cholesky_sample(nx, reps):
+    """the oracle's supernodal left-looking LL^T (OpenBLAS, all cores) on the nx^3 Laplacian with a nested-dissection
+    ordering computed in oracle/grid_nd.py (independent of the product)"""
+    from oracle import CholOracle, lib as olib
+    from oracle.grid_nd import grid_nd_perm
+    Al = lap3d_lower(nx)
+    n = Al.shape[0]
+    perm = grid_nd_perm(nx, nx, nx, 64)
+    threads = olib().oracle_blas_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter(); O = CholOracle(n, Al.indptr, Al.indices, "L", perm); ta = time.perf_counter() - t0
+    b = np.random.default_rng(0).standard_normal(n)
+    tf, ts = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter(); O.factorize(Al.data); tf.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); x = O.solve(b); ts.append(time.perf_counter() - t0)
+    A = (Al + sp.tril(Al, -1).T).tocsr()
+    berr = float(np.linalg.norm(A @ x - b) / (12.0 * np.linalg.norm(x) + np.linalg.norm(b)))
+    return {"workload": "7-point Laplacian %d^3, nested dissection (oracle/grid_nd.py), supernodal LL^T, 1 RHS" % nx,
+            "n": n, "nnz_L": O.nnzL, "flops": O.flops, "analyze_ms_host": ta * 1e3, "factor_ms": min(tf) * 1e3, "solve_ms": min(ts) * 1e3,
+            "factor_plus_solve_ms": (min(tf) + min(ts)) * 1e3, "factor_tflops": O.flops / min(tf) / 1e12, "backward_error": berr,
+            "cores": threads, "kind": "port", "reps": reps,
+            "sample": "oracle/chol_oracle.c (left-looking supernodal LL^T, OpenBLAS dsyrk/dgemm/dpotrf/dtrsm on %d threads)" % threads}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    assert "kvxopt_b200" not in sys.modules
+    A = load_activsg()
+    cores = os.cpu_count() or 1
+    per_worker = 24
+    line = {"impl": "reference", "metric": "batched KLU refactors/sec", "unit": "refactors/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gpu_launches": 0}
+    if args.workload in ("all", "klu", "configs"):
+        res, stats = cpu_klu_rates(A, cores, per_worker, args.steps, max(args.warmup, 1))
+        rate, ms_step, per_step = res["refactor"]
+        frate, fms, fper = res["factor"]
+        line.update({
+            "value": rate, "ms_per_step": ms_step,
+            "config": {"workload": "klu_refactor_batch ACTIVSg2000 (n=4000, nnz=29336) same-pattern perturbations 1e-3",
+                       "batch_per_step": per_step,
+                       "ordering": "independent of the product: SuperLU MMD on A'+A (scipy), oracle's own threshold pivoting; "
+                                   "nnz(L)=%d nnz(U)=%d flops=%.0f" % (stats["nnz_L"], stats["nnz_U"], stats["flops"])},
+            "cpu_baseline": {"value": rate, "unit": "refactors/s", "cores": cores, "kind": "port",
+                             "sample": "%d refactorizations per step (%d per core), oracle/klu_oracle.c klu_refactor restatement; "
+                                       "SuiteSparse KLU is not installable in this image" % (per_step, per_worker)},
+            "klu_factor": {"value": frate, "unit": "factorizations/s", "ms_per_step": fms, "batch_per_step": fper,
+                           "what": "klu_l_factor restatement (pattern discovery + threshold pivot search per matrix): what the reference's "
+                                   "klu.numeric calls for every matrix (src/C/klu.c:337); the reference never calls klu_refactor, so "
+                                   "`value` (refactor, no pivot search) is the KINDER baseline for the GPU arm"},
+            "e2e": {"value": rate, "unit": "refactors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    if args.workload in ("all", "chol"):
+        try:
+            line["cholesky"] = cpu_cholesky_sample(args.chol_sample_grid, max(1, min(args.steps, 2)))
+        except Exception as e:
+            line["cholesky"] = {"error": repr(e)}
+        if "value" not in line:
+            c = line["cholesky"]
+            line.update({"metric": "sparse Cholesky factor+solve ms", "unit": "ms", "higher_is_better": False,
+                         "value": c.get("factor_plus_solve_ms"), "ms_per_step": c.get("factor_plus_solve_ms"), "config": {"workload": c.get("workload")},
+                         "cpu_baseline": {"value": c.get("factor_plus_solve_ms"), "unit": "ms", "cores": c.get("cores"), "kind": "port", "sample": c.get("sample")},
+                         "e2e": {"value": c.get("factor_plus_solve_ms"), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    line["native_so_loaded"] = sorted({os.path.relpath(l.split()[-1], ROOT) for l in open("/proc/self/maps") if ROOT in l and ".so" in l})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def bench_cholesky(nx, steps, fp64_peak, full=True):
     import torch
     from kvxopt_b200 import _lib as L, cholmod
     fn = L.fn
@@ -263,28 +337,34 @@ def bench_cholesky(nx, steps, fp64_peak):
     cholmod.numeric(Al, F)
     cholmod.solve(F, Xh)
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    # one profiled factorization: per-kernel-class device time (events around every launch)
-    fn["b200s_chol_set_profiling"](h, 1)
-    assert fn["b200s_chol_factorize_dev"](h, vals_dev.data_ptr(), C.byref(minor)) == 0
-    fn["b200s_chol_info"](h, C.byref(inf))
-    fn["b200s_chol_set_profiling"](h, 0)
-    d = inf.asdict()
+    d = cholmod.factor_info(F)
     best_f, best_s = float(np.min(ms_f)), float(np.min(ms_s))
-    upd_tf = d["flops_update"] / (d["ms_dense_update"] * 1e-3) / 1e12 if d["ms_dense_update"] > 0 else None
     out = {
         "workload": "7-point Laplacian %d^3, geometric nested dissection (leaf 64), supernodal LL^T, 1 RHS" % nx,
         "n": n, "nnz_L": d["nnz_L"], "nsuper": d["nsuper"], "levels": d["nlevels"], "max_front": [d["max_front_rows"], d["max_front_cols"]],
         "flops": d["flops"], "analyze_ms_host": t_analyze * 1e3,
         "factor_ms": best_f, "solve_ms": best_s, "factor_plus_solve_ms": best_f + best_s,
         "factor_tflops": d["flops"] / (best_f * 1e-3) / 1e12,
+        "solve_gbs": (16.0 * d["nnz_L"] + 16.0 * n) / (best_s * 1e-3) / 1e9,
         "e2e_factor_plus_solve_ms_host_buffers": e2e_ms, "backward_error": berr,
-        "kernel_ms_profiled": {"extend_add": d["ms_extend"], "small_fronts": d["ms_potrf"], "panel": d["ms_trsm"],
-                               "dmma_update": d["ms_dense_update"]},
-        "roofline": {"bound": "tensor", "kernel": "k_update (FP64 DMMA m8n8k4)", "achieved": upd_tf, "peak": fp64_peak,
-                     "unit": "TFLOP/s", "frac": (upd_tf / fp64_peak) if upd_tf else None,
-                     "peak_source": "measured: tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak.json)",
-                     "traffic": traffic_from_profiles("k_update")},
     }
+    if not full:
+        del F
+        return out
+    # one profiled factorization: per-kernel-class device time (events around every launch)
+    fn["b200s_chol_set_profiling"](h, 1)
+    assert fn["b200s_chol_factorize_dev"](h, vals_dev.data_ptr(), C.byref(minor)) == 0
+    fn["b200s_chol_info"](h, C.byref(inf))
+    fn["b200s_chol_set_profiling"](h, 0)
+    d = inf.asdict()
+    upd_tf = d["flops_update"] / (d["ms_dense_update"] * 1e-3) / 1e12 if d["ms_dense_update"] > 0 else None
+    out["kernel_ms_profiled"] = {"extend_add": d["ms_extend"], "small_fronts": d["ms_potrf"], "panel": d["ms_trsm"],
+                                 "dmma_update": d["ms_dense_update"]}
+    out["roofline"] = {"bound": "tensor", "kernel": "k_update (FP64 DMMA m8n8k4)", "achieved": upd_tf, "peak": fp64_peak,
+                       "unit": "TFLOP/s", "frac": (upd_tf / fp64_peak) if upd_tf else None,
+                       "peak_source": "builder-measured: tools/fp64_peak.cu (DMMA m8n8k4 and DFMA issue-rate microbenchmark, "
+                                      "profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 entry",
+                       "traffic": traffic_from_profiles("k_update")}
     del F
     # the signed instantiation of the same kernels (cholmod.options['supernodal'] = 0: LDL' without pivoting, the mode
     # kkt.ldl factors quasi-definite KKT systems with) on the same matrix
@@ -308,23 +388,6 @@ def bench_cholesky(nx, steps, fp64_peak):
                        "factor_ms": float(np.min(ms_l[1:])), "factor_tflops": d["flops"] / (float(np.min(ms_l[1:])) * 1e-3) / 1e12,
                        "backward_error": float(np.linalg.norm(A @ x2 - B[:, 0]) / (12.0 * np.linalg.norm(x2) + np.linalg.norm(B)))}
     return out
-
-
-def cpu_cholesky_sample(nx):
-    """bounded CPU sample of the same workload class: the oracle's supernodal left-looking LL^T (OpenBLAS) on nx^3"""
-    from kvxopt_b200 import _lib as L
-    from oracle import CholOracle, lib as olib
-    Al = lap3d_lower(nx)
-    n = Al.shape[0]
-    perm = np.zeros(n, np.int64)
-    L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm))
-    threads = olib().oracle_blas_threads(os.cpu_count() or 1)
-    O = CholOracle(n, Al.indptr, Al.indices, "L", perm)
-    t0 = time.perf_counter(); O.factorize(Al.data); tf = time.perf_counter() - t0
-    b = np.random.default_rng(0).standard_normal(n)
-    t0 = time.perf_counter(); O.solve(b); ts = time.perf_counter() - t0
-    return {"workload": "same generator at %d^3" % nx, "factor_ms": tf * 1e3, "solve_ms": ts * 1e3, "flops": O.flops,
-            "factor_tflops": O.flops / tf / 1e12, "cores": threads, "kind": "port"}
 
 
 def bench_cholesky_multi(nx, steps, rank, world):
@@ -359,16 +422,217 @@ def bench_cholesky_multi(nx, steps, rank, world):
         A = (Al + sp.tril(Al, -1).T).tocsr()
         berr = float(np.linalg.norm(A @ x - b) / (12.0 * np.linalg.norm(x) + np.linalg.norm(b)))
         w = D.front_work(dc.lay)
+        fm, gm = float(np.min(times)), float(np.min(gtimes))
         out = {"workload": "7-point Laplacian %d^3, nested dissection, subtree-to-subcube over %d GPUs" % (nx, world),
-               "factor_ms": float(np.min(times)), "gather_panels_ms": float(np.min(gtimes)),
-               "factor_tflops": d["flops"] / (float(np.min(times)) * 1e-3) / 1e12, "solve_ms_rank0": d["ms_solve"],
+               "factor_ms": fm, "gather_panels_ms": gm, "solve_ms_rank0": d["ms_solve"],
+               "factor_gather_solve_ms": fm + gm + d["ms_solve"],
+               "factor_tflops": d["flops"] / (fm * 1e-3) / 1e12,
                "backward_error": berr, "timing": "host clock between barrier+synchronize pairs, max over ranks by construction",
                "work_share_per_rank": [round(float(w[dc.owner == r].sum() / w.sum()), 3) for r in range(world)],
                "nccl_transfers": int(sum(len(l) for l in dc.xplan)),
                "nccl_bytes": int(sum(int(dc.lay["usize"][m[0]]) for l in dc.xplan for m in l) * 8),
-               "limitation": "fronts are not split across GPUs in round 1: the top log2(N) levels run on one GPU each"}
+               "limitation": "fronts are not split across GPUs: the top log2(N) levels run on one GPU each; solves on rank 0 after "
+                             "the panel gather (both inside factor_gather_solve_ms)"}
     del dc, F
     return out
+
+
+def bench_config1(steps):
+    """BASELINE configs[0]: cholmod.linsolve on bcsstk24 (lower triangle as stored), random RHS, through the public API with
+    host buffers; CPU baseline = the oracle with its own (SuperLU MMD on A+A') ordering, timed in the same run."""
+    from kvxopt_b200 import cholmod
+    Al = sp.tril(load_golden("bcsstk24")).tocsc(); Al.sort_indices()
+    A = (Al + sp.tril(Al, -1).T).tocsc()
+    n = A.shape[0]
+    B = np.random.default_rng(0).standard_normal((n, 1))
+
+    def best(f, reps):
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter(); r = f(); ts.append((time.perf_counter() - t) * 1e3)
+        return min(ts), r
+
+    reps = max(3, steps)
+    cholmod.linsolve(Al, np.asfortranarray(B.copy()))
+    ms_lin, _ = best(lambda: cholmod.linsolve(Al, np.asfortranarray(B.copy())), reps)
+    ms_sym, F = best(lambda: cholmod.symbolic(Al), reps)
+    ms_num, _ = best(lambda: cholmod.numeric(Al, F), reps)
+    X = np.asfortranarray(B.copy())
+    ms_sol, _ = best(lambda: cholmod.solve(F, X), reps)
+    X = np.asfortranarray(B.copy()); cholmod.solve(F, X)
+    anorm = abs(A).sum(axis=0).max()
+    berr = float(np.linalg.norm(A @ X - B) / (anorm * np.linalg.norm(X) + np.linalg.norm(B)))
+    info = cholmod.factor_info(F)
+    # CPU arm, independent ordering
+    import scipy.sparse.linalg as spla
+    from oracle import CholOracle, lib as olib
+    threads = olib().oracle_blas_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    pat = sp.csc_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape) + sp.identity(n) * (2.0 * A.getnnz(axis=0).max())
+    perm = np.argsort(spla.splu(pat.tocsc(), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0).perm_c).astype(np.int64)
+    ms_ord = (time.perf_counter() - t0) * 1e3
+    ms_oan, O = best(lambda: CholOracle(n, Al.indptr, Al.indices, "L", perm), 2)
+    ms_ofa, _ = best(lambda: O.factorize(Al.data), 3)
+    ms_oso, Xo = best(lambda: O.solve(B), 3)
+    return {"workload": "cholmod.linsolve(A, B) on bcsstk24 (n=3562, lower triangle as stored, 81736 entries), B = n x 1 normal seed 0",
+            "n": n, "nnz_L": info["nnz_L"], "flops": info["flops"],
+            "linsolve_ms": ms_lin, "split_ms": {"symbolic_host": ms_sym, "numeric": ms_num, "solve": ms_sol},
+            "e2e": {"value": ms_lin, "unit": "ms", "h2d_bytes_per_step": int(Al.nnz * 8 + n * 8), "d2h_bytes_per_step": int(n * 8),
+                    "api": "kvxopt_b200.cholmod.linsolve (host buffers in, solution out)"},
+            "backward_error": berr, "rel_diff_vs_oracle": float(np.linalg.norm(X - Xo) / np.linalg.norm(Xo)),
+            "roofline": {"bound": "latency", "note": "3.2e7 flops and 4.5 MB: launch/transfer latency and the host symbolic analysis dominate",
+                         "numeric_gflops": info["flops"] / (ms_num * 1e-3) / 1e9},
+            "cpu_baseline": {"value": ms_oan + ms_ofa + ms_oso, "unit": "ms", "cores": threads, "kind": "port",
+                             "split_ms": {"ordering (SuperLU MMD via scipy, not counted)": ms_ord, "symbolic": ms_oan, "numeric": ms_ofa, "solve": ms_oso},
+                             "sample": "whole workload: oracle/chol_oracle.c analyze + factorize + solve, own ordering"}}
+
+
+def bench_strong(fn, L, hn, dev_vals, batch, nnz, world, steps, barrier, max_over_ranks):
+    """configs[1] as written: ONE batch of `batch` matrices split across the ranks (strong scaling)"""
+    per = batch // world
+    inf = L.KluInfo()
+    for _ in range(3):
+        assert fn["b200s_klu_refactor_batch_dev"](hn, dev_vals.data_ptr(), per, nnz, None) == 0
+    barrier()
+    ms = 0.0
+    for _ in range(steps):
+        assert fn["b200s_klu_refactor_batch_dev"](hn, dev_vals.data_ptr(), per, nnz, None) == 0
+        fn["b200s_klu_info"](hn, C.byref(inf))
+        ms += inf.ms_refactor
+    barrier()
+    ms = max_over_ranks(ms)
+    return {"scaling": "strong", "global_batch": per * world, "batch_per_gpu": per, "value": per * world * steps / (ms * 1e-3),
+            "unit": "refactors/s", "ms_per_step": ms / steps,
+            "note": "one CTA serves 32 matrices and its time is the latency of the column-dependency chain, so a smaller per-GPU batch "
+                    "runs fewer CTAs for about the same time (DESIGN.md section 3.2)"}
+
+
+def ipm_child():
+    """configs 3 and 5 (run as `bench.py --ipm-child`, OPENBLAS_NUM_THREADS=1 in the environment): the unmodified reference
+    IPM (oracle/_ref, the CALLER of the path) with the B200 KKT solvers plugged in through kktsolver=; prints one JSON line"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    sys.path.insert(0, GOLD)
+    out = {}
+    import kvxopt
+    from kvxopt_b200 import cholmod as gcholmod, klu as gklu, kkt as gkkt, _lib as L
+    gcholmod.install(kvxopt); gklu.install(kvxopt)
+    from kvxopt import matrix, spmatrix, solvers
+    solvers.options["show_progress"] = False
+    gcholmod.linsolve(sp.identity(2, format="csc"), np.ones((2, 1), order="F"))      # CUDA context before any timed region
+    cores = os.cpu_count() or 1
+
+    def tosp(M):
+        M = sp.coo_matrix(M)
+        return spmatrix(M.data.tolist(), M.row.tolist(), M.col.tolist(), M.shape)
+
+    # ---- config 3: solvers.lp on boeing2 through conelp
+    try:
+        z = np.load(os.path.join(GOLD, "boeing2_lp.npz"))
+        G = sp.csc_matrix((z["Gx"], z["Gi"], z["Gp"]), shape=tuple(z["G_size"]))
+        Aeq = sp.csc_matrix((z["Ax"], z["Ai"], z["Ap"]), shape=tuple(z["A_size"]))
+        c, h, b = matrix(z["c"]), matrix(z["h"]), matrix(z["b"])
+        Gd, Ad, Gs, As = matrix(G.toarray()), matrix(Aeq.toarray()), tosp(G), tosp(Aeq)
+        dims = {"l": G.shape[0], "q": [], "s": []}
+
+        def run(Gm, Am, mk):
+            best, sol = 1e30, None
+            for _ in range(4):
+                k = mk()
+                t = time.perf_counter(); sol = solvers.conelp(c, Gm, h, dims, Am, b, **({} if k is None else {"kktsolver": k}))
+                best = min(best, (time.perf_counter() - t) * 1e3)
+            return {"ms": best, "iterations": sol["iterations"], "objective": sol["primal objective"], "status": sol["status"]}
+
+        arms = {"device_chol (kvxopt_b200.kkt.chol, dense 'chol' counterpart, misc.py:1213-1349)": run(Gd, Ad, lambda: gkkt.chol(Gd, dims, Ad)),
+                "device_chol2 (kvxopt_b200.kkt.chol2, device-resident sparse reduced system)": run(Gs, As, lambda: gkkt.chol2(Gs, dims, As)),
+                "module_chol2 (reference misc.kkt_chol2 on kvxopt_b200.cholmod)": run(Gs, As, lambda: None)}
+        ref = {"reference_chol (LAPACK, dense)": run(Gd, Ad, lambda: "chol"), "reference_chol2 (LAPACK, dense G)": run(Gd, Ad, lambda: "chol2")}
+        first = arms["device_chol (kvxopt_b200.kkt.chol, dense 'chol' counterpart, misc.py:1213-1349)"]
+        rc = ref["reference_chol (LAPACK, dense)"]
+        out["config3"] = {"workload": "solvers.lp on boeing2 (n=143, G 352x143, A 4x143) via conelp, full IPM, KKT factorization on the GPU each iteration",
+                          "ms": first["ms"], "iterations": first["iterations"], "objective": first["objective"], "arms": arms,
+                          "parity": {"iterations_equal_reference": first["iterations"] == rc["iterations"],
+                                     "objective_rel_diff": abs(first["objective"] - rc["objective"]) / abs(rc["objective"])},
+                          "e2e": {"value": first["ms"], "unit": "ms", "api": "solvers.conelp(..., kktsolver=kvxopt_b200.kkt.chol(G, dims, A)): host vectors in/out every KKT solve"},
+                          "roofline": {"bound": "latency", "note": "143 x 143 dense system: 30 factorizations + ~90 solves of microseconds of work each; "
+                                                                    "per-call launch + PCIe round trips bound it"},
+                          "cpu_baseline": {"value": rc["ms"], "unit": "ms", "cores": 1, "kind": "reference",
+                                           "sample": "whole workload: the reference's own 'chol' kktsolver (LAPACK via oracle/_ref, OPENBLAS_NUM_THREADS=1)",
+                                           "arms": ref}}
+    except Exception as e:
+        out["config3"] = {"error": repr(e)}
+
+    # ---- config 5: 200k-variable QP through coneqp
+    try:
+        from generators import qp_instance
+        nx, ny, nrand = 500, 400, 5000
+        P, q, G, h = qp_instance(nx, ny, nrand)
+        Pk, Gk = tosp(sp.tril(P)), tosp(G)
+        t0 = time.perf_counter()
+        ks = gkkt.qp_kktsolver(Pk, Gk)
+        t_setup = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=ks)
+        wall = time.perf_counter() - t0
+        inf = ks.info()
+        _, _, fp64_peak = measured_peaks()
+        tf = inf["flops"] / (inf["ms_factor"] * 1e-3) / 1e12 if inf.get("ms_factor") else None
+        c5 = {"workload": "synthetic sparse QP n=200000 (500x400 grid Laplacian + 1e-2 I), m=405000 (box + 5000 random 3-nnz rows), coneqp",
+              "iterations": sol["iterations"], "objective": sol["primal objective"], "status": sol["status"],
+              "ipm_iterations_per_s": sol["iterations"] / wall, "wall_s": wall, "setup_s_host_analysis": t_setup,
+              "per_iteration_ms": {"assemble": inf.get("ms_assemble"), "factor": inf.get("ms_factor"), "kkt_solve": inf.get("ms_solve")},
+              "nnz_L": inf.get("nnz_L"), "flops_per_factorization": inf.get("flops"),
+              "e2e": {"value": sol["iterations"] / wall, "unit": "IPM iterations/s",
+                      "api": "solvers.qp(P, q, G, h, kktsolver=kvxopt_b200.kkt.qp_kktsolver(P, G)): W['di'] and x, y, z cross PCIe every call"},
+              "roofline": {"bound": "tensor", "kernel": "k_update (FP64 DMMA) inside the factorization of S", "achieved": tf, "peak": fp64_peak,
+                           "unit": "TFLOP/s", "frac": tf / fp64_peak if tf else None,
+                           "note": "whole-factorization rate (assembly, small fronts and panels included), last iteration"},
+              "parity": {"golden_objective": -43988.5773845128, "golden_iterations": 10,
+                         "objective_rel_diff": abs(sol["primal objective"] + 43988.5773845128) / 43988.5773845128}}
+        # CPU sample: 2 IPM iterations of the reference's own kkt_chol2 with the oracle behind kvxopt.cholmod
+        try:
+            from oracle import cholmod_cpu, lib as olib
+            threads = os.cpu_count() or 1
+            on = cholmod_cpu.numeric
+
+            def numeric_mt(*a, **k):       # BLAS threads only inside the factorization (scale() is not thread-safe here)
+                olib().oracle_blas_threads(threads)
+                try:
+                    return on(*a, **k)
+                finally:
+                    olib().oracle_blas_threads(1)
+            cholmod_cpu.numeric = numeric_mt
+            sys.modules["kvxopt.cholmod"] = cholmod_cpu; kvxopt.cholmod = cholmod_cpu
+            import kvxopt.misc as misc
+            misc.cholmod = cholmod_cpu
+            solvers.options["maxiters"] = 2
+            t0 = time.perf_counter()
+            s2 = solvers.qp(Pk, matrix(q), Gk, matrix(h))
+            w2 = time.perf_counter() - t0
+            c5["cpu_baseline"] = {"value": 2.0 / w2, "unit": "IPM iterations/s", "cores": threads, "kind": "port",
+                                  "sample": "2 iterations (maxiters=2; %.1f s incl. the initial KKT solve) of the reference's coneqp + misc.kkt_chol2 "
+                                            "with oracle/chol_oracle.c behind kvxopt.cholmod (fill-reducing ordering from the engine's host AMD -- "
+                                            "integer work, no GPU --, OpenBLAS %d threads inside the factorization)" % (w2, threads)}
+        except Exception as e:
+            c5["cpu_baseline"] = {"error": repr(e)}
+        out["config5"] = c5
+    except Exception as e:
+        out["config5"] = {"error": repr(e)}
+    print("IPMCHILD " + json.dumps(out), flush=True)
+
+
+def run_ipm_child(timeout=600):
+    env = dict(os.environ)
+    env["OPENBLAS_NUM_THREADS"] = "1"
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--ipm-child"], env=env, capture_output=True, text=True, timeout=timeout)
+        for ln in reversed(p.stdout.splitlines()):
+            if ln.startswith("IPMCHILD "):
+                return json.loads(ln[len("IPMCHILD "):])
+        return {"config3": {"error": "child rc=%d: %s" % (p.returncode, p.stderr[-400:])}, "config5": {"error": "child failed"}}
+    except Exception as e:
+        return {"config3": {"error": repr(e)}, "config5": {"error": repr(e)}}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -378,11 +642,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "klu", "chol"])
+    ap.add_argument("--workload", default="all", choices=["all", "klu", "chol", "configs"])
     ap.add_argument("--batch", type=int, default=4096, help="matrices per GPU")
     ap.add_argument("--chol-grid", type=int, default=100)
+    ap.add_argument("--chol-sample-grid", type=int, default=CHOL_SAMPLE_GRID)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ipm-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.ipm_child:
+        ipm_child()
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -431,14 +700,13 @@ def main():
     host_vals = torch.empty((batch, nnz), dtype=torch.float64, pin_memory=True)
     perturbed_values(A.data, batch, rank, out=host_vals.numpy())
     dev_vals = host_vals.cuda()
-    status = np.zeros(batch, dtype=np.int32)
     inf = L.KluInfo()
+    clocks = ClockSampler(local) if rank == 0 else None
     # ---- warm-up
     for _ in range(args.warmup):
         assert fn["b200s_klu_refactor_batch_dev"](hn, dev_vals.data_ptr(), batch, nnz, None) == 0, L.last_error()
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
+    if clocks:
         clocks.start()
     # ---- timed: device-resident inputs.  Inputs (961 MB per step) are far larger than the 126 MB L2.
     dev_ms, ker_ms, dense_ms, nlaunch = 0.0, 0.0, 0.0, 0
@@ -452,7 +720,8 @@ def main():
         nlaunch += inf.launches
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clk = clocks.stop() if rank == 0 else None
+    if clocks:
+        clocks.pause()
     dev_ms_max = max_over_ranks(dev_ms)
     wall_ms_max = max_over_ranks(wall_ms)
     value = world * batch * args.steps / (dev_ms_max * 1e-3)
@@ -474,6 +743,8 @@ def main():
     klu.refactor_batch_begin(Fn, hbufs[0]); klu.refactor_batch_begin(Fn, hbufs[1])
     klu.refactor_batch_end(Fn); klu.refactor_batch_end(Fn)
     barrier()
+    if clocks:
+        clocks.start()
     t0 = time.perf_counter()
     klu.refactor_batch_begin(Fn, hbufs[0])
     for i in range(1, args.steps):
@@ -483,6 +754,7 @@ def main():
     st = klu.refactor_batch_end(Fn)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    clk = clocks.stop() if clocks else None
     assert not st.any()
     e2e_value = world * batch * args.steps / (e2e_ms * 1e-3)
     e2e_sync_value = world * batch * args.steps / (e2e_sync_ms * 1e-3)
@@ -497,6 +769,7 @@ def main():
     Ab = sp.csc_matrix((host_vals.numpy()[bsel], A.indices, A.indptr), shape=(n, n))
     xref = spla.splu(Ab).solve(Bb[bsel, 0])
     spot = float(np.linalg.norm(Xb[bsel, 0] - xref) / np.linalg.norm(xref))
+    del Bb, Xb
 
     bytes_per = d["bytes_per_refactor"]
     ker_avg_ms = ker_ms / args.steps
@@ -513,6 +786,7 @@ def main():
         "wall_ms_per_step": wall_ms_max / args.steps,
         "e2e": {"value": e2e_value, "unit": "refactors/s", "h2d_bytes_per_step": int(batch * nnz * 8),
                 "d2h_bytes_per_step": int(batch * 4), "ms_per_step": e2e_ms / args.steps,
+                "h2d_gbs": batch * nnz * 8 / (e2e_ms / args.steps * 1e-3) / 1e9,
                 "api": "kvxopt_b200.klu.refactor_batch_begin(Fn, values[batch, nnz]) / refactor_batch_end(Fn) -> status[batch], "
                        "two batches in flight: the pinned-host upload of step i+1 overlaps the kernels of step i; every "
                        "step's H2D and D2H are inside the timed region",
@@ -527,18 +801,33 @@ def main():
         "parity_spot_check_rel_vs_superlu": spot,
         "clocks": clk,
     }
+    if world > 1 and batch % world == 0:
+        try:
+            line["strong"] = bench_strong(fn, L, hn, dev_vals, batch, nnz, world, args.steps, barrier, max_over_ranks)
+        except Exception as e:
+            line["strong"] = {"error": repr(e)}
+    del dev_vals, host_vals, host_vals2, hbufs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = 1
-        rate, _, _ = cpu_refactor_rate(A, cores, 48, 3, 1)
-        line["cpu_baseline"] = {"value": rate, "unit": "refactors/s", "cores": cores, "kind": "port",
-                                "sample": "3 x 48 refactorizations on one core, oracle/klu_oracle.c (klu_refactor restatement, same ordering)"}
+        res, stats = cpu_klu_rates(A, 1, 48, 3, 1)
+        line["cpu_baseline"] = {"value": res["refactor"][0], "unit": "refactors/s", "cores": 1, "kind": "port",
+                                "klu_factor_per_s": res["factor"][0],
+                                "sample": "3 x 48 refactorizations on one core, oracle/klu_oracle.c (klu_refactor restatement; own ordering: "
+                                          "SuperLU MMD on A'+A, own pivoting; nnz(L)=%d)" % stats["nnz_L"]}
     if world == 1 and args.workload in ("all", "chol"):
         try:
             line["cholesky"] = bench_cholesky(args.chol_grid, max(2, min(args.steps, 3)), fp64_peak)
+            line["cholesky"]["sample_64"] = bench_cholesky(args.chol_sample_grid, 3, fp64_peak, full=False)
             if not args.no_cpu_baseline:
-                line["cholesky"]["cpu_baseline"] = cpu_cholesky_sample(48)
+                line["cholesky"]["cpu_baseline"] = cpu_cholesky_sample(args.chol_sample_grid, 1)
+                line["cholesky"]["cpu_baseline"]["note"] = "bounded sample: the %d^3 grid of cholesky.sample_64 (the 100^3 case is ~60 s per CPU factorization)" % args.chol_sample_grid
         except Exception as e:  # the headline line must still be printed
             line["cholesky"] = {"error": repr(e)}
+    if world == 1 and args.workload in ("all", "configs"):
+        try:
+            line["config1"] = bench_config1(args.steps)
+        except Exception as e:
+            line["config1"] = {"error": repr(e)}
+        line.update(run_ipm_child())
     if world > 1 and args.workload in ("all", "chol"):
         try:
             res = bench_cholesky_multi(args.chol_grid, 2, rank, world)

@@ -278,6 +278,24 @@ b200s_status b200s_kkt_info(const b200s_kkt* K, b200s_kkt_info_t* info);
 b200s_status b200s_kkt_plan_check_host(const b200s_kkt* K, const double* di, const double* Hx, double* Sx);
 void b200s_kkt_free(b200s_kkt* K);
 
+/* ---- dense reduced KKT solver: the GPU counterpart of misc.kkt_chol, the 'chol' kktsolver ----------------------------
+ * (reference src/python/misc.py:1213-1349).  G ml x n and A p x n are dense column-major.  create: QR of A' on the host
+ * once per problem (misc.py:1246-1251), kept as compact WY.  factor(di, H): K = [Q1 Q2]'(H + G' diag(di)^2 G)[Q1 Q2] and the
+ * dense Cholesky factorization of its (2,2) block of order n-p on the device (misc.py:1258-1282); H is dense n x n
+ * column-major (lower triangle referenced) or NULL.  solve: misc.py:1284-1345 in place on host vectors. */
+typedef struct b200s_kktd b200s_kktd;
+b200s_status b200s_kktd_create(b200s_int n, b200s_int ml, b200s_int p, const double* G, const double* A, b200s_kktd** out);
+b200s_status b200s_kktd_factor(b200s_kktd* K, const double* di, const double* H, b200s_int* minor);
+b200s_status b200s_kktd_solve(b200s_kktd* K, double* x, double* y, double* z);
+typedef struct {
+    b200s_int n, ml, p, launches;
+    double flops, ms_factor, ms_solve;
+} b200s_kktd_info_t;
+b200s_status b200s_kktd_info(const b200s_kktd* K, b200s_kktd_info_t* info);
+/* the host QR of A' (tests): V n x p unit lower trapezoid, T p x p and R p x p upper triangular; Q = I - V T V' */
+b200s_status b200s_kktd_get_qr(const b200s_kktd* K, double* V, double* T, double* R);
+void b200s_kktd_free(b200s_kktd* K);
+
 #ifdef __cplusplus
 }
 #endif

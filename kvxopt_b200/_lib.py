@@ -28,7 +28,7 @@ OK, NOT_POSDEF, SINGULAR = 0, 1, 2
 OUT_OF_MEMORY, TOO_LARGE, INVALID, NO_DEVICE, CUDA_ERROR = -2, -3, -4, -5, -6
 
 
-from ._lib_types import CholOpts, CholInfo, KluInfo, KluPlanView, KktInfo  # noqa: E402,F401
+from ._lib_types import CholOpts, CholInfo, KluInfo, KluPlanView, KktInfo, KktdInfo  # noqa: E402,F401
 
 
 def _sig(name, restype, *argtypes):
@@ -94,6 +94,12 @@ SIGNATURES = {
     "b200s_kkt_info": (C.c_int, vp, C.POINTER(KktInfo)),
     "b200s_kkt_plan_check_host": (C.c_int, vp, p_f64, p_f64, p_f64),
     "b200s_kkt_free": (None, vp),
+    "b200s_kktd_create": (C.c_int, i64, i64, i64, p_f64, p_f64, C.POINTER(vp)),
+    "b200s_kktd_factor": (C.c_int, vp, p_f64, p_f64, p_i64),
+    "b200s_kktd_solve": (C.c_int, vp, p_f64, p_f64, p_f64),
+    "b200s_kktd_info": (C.c_int, vp, C.POINTER(KktdInfo)),
+    "b200s_kktd_get_qr": (C.c_int, vp, p_f64, p_f64, p_f64),
+    "b200s_kktd_free": (None, vp),
     "b200s_klu_free_symbolic": (None, vp),
     "b200s_klu_free_numeric": (None, vp),
 }

@@ -37,6 +37,13 @@ class KktInfo(C.Structure):
                [("Sp", C.POINTER(C.c_int64)), ("Si", C.POINTER(C.c_int64))]
 
 
+class KktdInfo(C.Structure):
+    _fields_ = [(k, i64) for k in ("n", "ml", "p", "launches")] + [(k, C.c_double) for k in ("flops", "ms_factor", "ms_solve")]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class KluPlanView(C.Structure):
     _fields_ = [(k, i64) for k in ("n", "nlevels", "nslots", "lu_slots", "nnz_A", "nupd", "ndest")] + \
                [(k, C.POINTER(C.c_int64)) for k in ("cbeg", "rowptr", "upd_ptr", "upd_dest")] + \

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200sparse.so")
-SOURCES = ["ordering.cpp", "symbolic.cpp", "klu_host.cpp", "chol_gpu.cu", "klu_gpu.cu", "capi.cu", "klu_capi.cu", "kkt_gpu.cu"]
+SOURCES = ["ordering.cpp", "symbolic.cpp", "klu_host.cpp", "chol_gpu.cu", "klu_gpu.cu", "capi.cu", "klu_capi.cu", "kkt_gpu.cu", "kktd_gpu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC,-O3,", "--expt-relaxed-constexpr"]
 

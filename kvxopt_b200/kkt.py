@@ -28,7 +28,7 @@ from .cholmod import _ccs, _dense_view, _is_kvx, _is_dense, _size, _values
 
 fn = L.fn
 
-__all__ = ["chol2", "ldl", "ldl2", "qp_kktsolver", "lp_kktsolver"]
+__all__ = ["chol", "chol2", "ldl", "ldl2", "qp_kktsolver", "lp_kktsolver"]
 
 
 class _Handle:
@@ -155,6 +155,92 @@ def chol2(G, dims, A, mnl=0):
         return solve
 
     factor.info = lambda: info(state["handle"].h) if state["handle"] else {}
+    return factor
+
+
+def _dense_colmajor(M, shape, what):
+    """dense column-major float64 copy of a dense or sparse kvxopt / numpy / scipy matrix"""
+    if _is_dense(M):
+        if _is_kvx(M):
+            a = np.asarray(memoryview(M)).reshape(tuple(M.size), order="F") if M.size[0] * M.size[1] else np.zeros(tuple(M.size))
+        else:
+            a = np.asarray(M, dtype=np.float64)
+            if a.ndim == 1:
+                a = a.reshape(-1, 1)
+    else:
+        import scipy.sparse as sp
+        cp, ri, vx = _ccs(M)
+        a = sp.csc_matrix((vx, ri, cp), shape=_size(M)).toarray()
+    if tuple(a.shape) != tuple(shape):
+        raise TypeError("%s must be a %d x %d matrix" % ((what,) + tuple(shape)))
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+class _DenseHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            fn["b200s_kktd_free"](self.h)
+            self.h = None
+
+
+def chol(G, dims, A, mnl=0):
+    """Same contract as misc.kkt_chol(G, dims, A, mnl) (reference src/python/misc.py:1213-1349), the 'chol' kktsolver:
+    QR of A' once, then per interior-point iteration the dense K = [Q1 Q2]'(H + G' W^-1 W^-T G)[Q1 Q2] and the dense
+    Cholesky factorization of its (2,2) block of order n-p -- here on the device (csrc/kktd_gpu.cu: register-tiled FP64
+    GEMM for the SYRK and the compact-WY products, the multifrontal engine's one-supernode case for the Cholesky
+    factorization and its solves).  Returns factor(W, H=None, Df=None) -> solve(x, y, z), in place: x, y, z := ux, uy, W uz.
+    Componentwise inequalities only (dims['q'], dims['s'] empty, mnl = 0), like kkt.chol2.  No CPU fallback."""
+    if dims["q"] or dims["s"]:
+        raise ValueError("kvxopt_b200.kkt.chol is implemented only for problems with no second-order or semidefinite "
+                         "cone constraints")
+    if mnl:
+        raise ValueError("kvxopt_b200.kkt.chol does not support nonlinear constraints (mnl > 0)")
+    p, n = _size(A)
+    ml = dims["l"]
+    Gd = _dense_colmajor(G, (ml, n), "G")
+    Ad = _dense_colmajor(A, (p, n), "A") if p else np.zeros((0, n), order="F")
+    h = C.c_void_p()
+    st = fn["b200s_kktd_create"](n, ml, p, L.ptr_f64(Gd.reshape(-1, order="F")), L.ptr_f64(Ad.reshape(-1, order="F")) if p else None,
+                                 C.byref(h))
+    if st == L.SINGULAR:
+        raise ArithmeticError("Rank(A) < p")
+    if st != L.OK:
+        _raise(st)
+    handle = _DenseHandle(h)
+
+    def factor(W, H=None, Df=None):
+        if Df is not None:
+            raise ValueError("kvxopt_b200.kkt.chol does not support nonlinear constraints")
+        di = np.ascontiguousarray(_vec(W["di"], ml, "W['di']") if ml else np.zeros(0), dtype=np.float64)
+        Hd = _dense_colmajor(H, (n, n), "H") if H is not None else None
+        minor = C.c_int64(0)
+        st = fn["b200s_kktd_factor"](handle.h, L.ptr_f64(di), L.ptr_f64(Hd.reshape(-1, order="F")) if Hd is not None else None,
+                                     C.byref(minor))
+        if st == L.NOT_POSDEF:
+            raise ArithmeticError(int(minor.value) + 1)       # lapack.potrf's info (1-based), as the reference raises it
+        if st != L.OK:
+            _raise(st)
+
+        def solve(x, y, z):
+            xf = _vec(x, n, "x")
+            yf = _vec(y, p, "y") if p else None
+            zf = _vec(z, ml, "z") if ml else None
+            st2 = fn["b200s_kktd_solve"](handle.h, L.ptr_f64(xf), L.ptr_f64(yf) if p else None, L.ptr_f64(zf) if ml else None)
+            if st2 != L.OK:
+                _raise(st2)
+
+        return solve
+
+    def _info():
+        inf = L.KktdInfo()
+        fn["b200s_kktd_info"](handle.h, C.byref(inf))
+        return inf.asdict()
+
+    factor.info = _info
+    factor._handle = handle
     return factor
 
 

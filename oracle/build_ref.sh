@@ -27,4 +27,10 @@ gcc $CF -DBASE_MODULE $SRC/C/base.c $SRC/C/dense.c $SRC/C/sparse.c -o $OUT/base$
 for m in blas lapack misc_solvers; do gcc $CF $SRC/C/$m.c -o $OUT/$m$EXT $LD; done
 cp $SRC/python/*.py $OUT/
 printf 'version = "1.3.2.2"\nversion_tuple = (1,3,2,2)\n__version__ = version\n' > $OUT/_version.py
+# the reference's own test-suite and doc examples, so that they can be executed VERBATIM against the B200 modules on the GPU
+# box (where /root/reference does not exist): copied next to the build output only, never into the tracked tree
+REFROOT=$(dirname "$SRC")
+mkdir -p $HERE/_ref/tests $HERE/_ref/examples
+cp $REFROOT/tests/*.py $REFROOT/tests/*.mtx $REFROOT/tests/*.mps $HERE/_ref/tests/
+cp -r $REFROOT/examples/doc $HERE/_ref/examples/
 echo "built reference probe in $OUT"

@@ -35,11 +35,15 @@ typedef struct {
     double* Rs;                 /* row scale factors in pivotal order                      */
     i64 lcap, ucap;
     double flops;
+    double *ws_rs, *ws_x;       /* refactor workspace, allocated once (klu_refactor keeps its workspace in the Numeric object too) */
+    i64* ws_pinv;
+    int usorted;                /* U columns already sorted by row (done by the first refactor) */
 } oracle_klu;
 
 void oracle_klu_free(oracle_klu* F) {
     if (!F) return;
     free(F->Lp); free(F->Li); free(F->Up); free(F->Ui); free(F->Lx); free(F->Ux); free(F->Pnum); free(F->Q); free(F->Rs);
+    free(F->ws_rs); free(F->ws_x); free(F->ws_pinv);
     free(F);
 }
 
@@ -150,9 +154,15 @@ oracle_klu* oracle_klu_factor(i64 n, const i64* Ap, const i64* Ai, const double*
 /* klu_refactor: same pattern and pivot order, new values.  Returns 0, or 2 when a pivot is zero. */
 int oracle_klu_refactor(oracle_klu* F, const i64* Ap, const i64* Ai, const double* Ax) {
     const i64 n = F->n;
-    double* rs = (double*)calloc((size_t)n + 1, sizeof(double));
-    i64* pinv = (i64*)malloc(sizeof(i64) * ((size_t)n + 1));
-    double* x = (double*)calloc((size_t)n + 1, sizeof(double));
+    if (!F->ws_rs) {
+        F->ws_rs = (double*)calloc((size_t)n + 1, sizeof(double));
+        F->ws_pinv = (i64*)malloc(sizeof(i64) * ((size_t)n + 1));
+        F->ws_x = (double*)calloc((size_t)n + 1, sizeof(double));
+    }
+    double* rs = F->ws_rs;
+    i64* pinv = F->ws_pinv;
+    double* x = F->ws_x;          /* all zero on entry and on exit */
+    memset(rs, 0, sizeof(double) * ((size_t)n + 1));
     for (i64 j = 0; j < n; j++)
         for (i64 p = Ap[j]; p < Ap[j + 1]; p++) { double a = fabs(Ax[p]); if (a > rs[Ai[p]]) rs[Ai[p]] = a; }
     for (i64 i = 0; i < n; i++) if (!(rs[i] > 0.0)) rs[i] = 1.0;
@@ -164,7 +174,7 @@ int oracle_klu_refactor(oracle_klu* F, const i64* Ap, const i64* Ai, const doubl
         /* U(:,k) is stored in the order the pivoting factorization produced; the dependency order is by row */
         /* process pivotal rows in ascending order: gather, sort by row index */
         i64 u0 = F->Up[k], u1 = F->Up[k + 1] - 1;
-        for (i64 a = u0 + 1; a < u1; a++) {             /* insertion sort of (Ui,Ux) by Ui, stable pattern */
+        if (!F->usorted) for (i64 a = u0 + 1; a < u1; a++) {             /* insertion sort of (Ui,Ux) by Ui, stable pattern */
             i64 ri = F->Ui[a]; double rx = F->Ux[a]; i64 b = a - 1;
             while (b >= u0 && F->Ui[b] > ri) { F->Ui[b + 1] = F->Ui[b]; F->Ux[b + 1] = F->Ux[b]; b--; }
             F->Ui[b + 1] = ri; F->Ux[b + 1] = rx;
@@ -182,7 +192,7 @@ int oracle_klu_refactor(oracle_klu* F, const i64* Ap, const i64* Ai, const doubl
         if (!(fabs(piv) > 0.0)) status = 2;
         for (i64 q = F->Lp[k] + 1; q < F->Lp[k + 1]; q++) { F->Lx[q] = x[F->Li[q]] / piv; x[F->Li[q]] = 0.0; }
     }
-    free(rs); free(pinv); free(x);
+    F->usorted = 1;
     return status;
 }
 
