@@ -20,6 +20,23 @@ def _free_port():
     return p
 
 
+def host_pattern(A):
+    """pivot order of the product's HOST analysis (no GPU involved)"""
+    import ctypes as C
+    from kvxopt_b200 import _lib as L
+    fn = L.fn
+    n = A.shape[0]
+    cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+    S = L.vp(); assert fn["b200s_klu_analyze"](n, L.ptr_i64(cp), L.ptr_i64(ri), C.byref(S)) == 0
+    N = L.vp(); assert fn["b200s_klu_pivot_host"](S, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(N)) == 0
+    P = np.zeros(n, np.int64); Q = np.zeros(n, np.int64)
+    fn["b200s_klu_extract"](N, None, None, None, None, None, None, None, None, None, L.ptr_i64(P), L.ptr_i64(Q), None, None)
+    inf = L.KluInfo(); fn["b200s_klu_info"](N, C.byref(inf))
+    d = inf.asdict()
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+    return cp, ri, vx, P, Q, d
+
+
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -28,7 +45,9 @@ def _worker(rank, world, port, out):
     import bench
     from oracle import KluOracle
     A = bench.load_activsg()
-    cp, ri, vx, P, Q, info = bench.host_pattern(A)          # host analysis + pivot search, no GPU
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_multi_cpu import host_pattern
+    cp, ri, vx, P, Q, info = host_pattern(A)          # host analysis + pivot search, no GPU
     h = hashlib.sha256(P.tobytes() + Q.tobytes() + np.int64(info["nnz_L"]).tobytes()).digest()
     t = torch.tensor(list(h), dtype=torch.uint8)
     gathered = [torch.zeros_like(t) for _ in range(world)]
@@ -80,7 +99,7 @@ def test_two_rank_sharding_gloo():
 def test_reference_arm_prints_contract_line():
     import json
     import subprocess
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--workload", "klu"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
@@ -88,3 +107,6 @@ def test_reference_arm_prints_contract_line():
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["klu_factor"]["value"] > 0
+    # the reference arm is independent of the product: libb200sparse.so is never mapped into its process
+    assert not any("b200sparse" in s for s in line["native_so_loaded"]), line["native_so_loaded"]
