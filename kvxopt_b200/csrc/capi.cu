@@ -2,6 +2,7 @@
 // torch types.  Cholesky half; the KLU half lives in klu_capi.cu.
 #include "../../include/b200sparse.h"
 #include "gpu.hpp"
+#include "nvtx_range.hpp"
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -62,6 +63,7 @@ void b200s_chol_default_opts(b200s_chol_opts* o) {
 
 b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, char uplo,
                                 const b200s_int* perm, const b200s_chol_opts* opts, b200s_chol** out) {
+    B200S_NVTX("b200s_chol_analyze");
     if (!out) return B200S_INVALID;
     *out = nullptr;
     if (n < 0 || (n > 0 && (!colptr || (colptr[n] > 0 && !rowind)))) return B200S_INVALID;
@@ -121,6 +123,7 @@ static b200s_status ensure_device(b200s_chol* F) {
 }
 
 static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_device, b200s_int* minor_out) {
+    B200S_NVTX("factorize_impl");
     if (!F) return B200S_INVALID;
     F->numeric = false;
     if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
@@ -190,6 +193,7 @@ b200s_status b200s_chol_set_owned(b200s_chol* F, const unsigned char* owned) {
     return (b200s_status)chol_device_set_owned(F->dev, owned);
 }
 b200s_status b200s_chol_factor_begin(b200s_chol* F, const double* val, int val_on_device) {
+    B200S_NVTX("b200s_chol_factor_begin");
     if (!F) return B200S_INVALID;
     F->numeric = false;
     if (F->plan.n == 0) return B200S_OK;
@@ -199,10 +203,12 @@ b200s_status b200s_chol_factor_begin(b200s_chol* F, const double* val, int val_o
     return (b200s_status)chol_device_factor_begin(F->dev, val, val_on_device != 0);
 }
 b200s_status b200s_chol_factor_level(b200s_chol* F, b200s_int level) {
+    B200S_NVTX("b200s_chol_factor_level");
     if (!F || !F->dev) return B200S_INVALID;
     return (b200s_status)chol_device_factor_level(F->dev, (int)level);
 }
 b200s_status b200s_chol_factor_end(b200s_chol* F, b200s_int* minor_out) {
+    B200S_NVTX("b200s_chol_factor_end");
     if (!F) return B200S_INVALID;
     if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
     if (!F->dev) return B200S_INVALID;
@@ -252,6 +258,7 @@ b200s_status b200s_chol_set_numeric(b200s_chol* F, int numeric, b200s_int minor)
 }
 
 static b200s_status solve_impl(b200s_chol* F, int sys, double* B, b200s_int nrhs, b200s_int ldB, bool on_device) {
+    B200S_NVTX("solve_impl");
     if (!F || sys < 0 || sys > 8 || nrhs < 0) return B200S_INVALID;
     if (F->plan.n == 0 || nrhs == 0) return B200S_OK;
     if (!B || ldB < F->plan.n) return B200S_INVALID;
@@ -267,6 +274,7 @@ b200s_status b200s_chol_solve_dev(b200s_chol* F, int sys, double* B_dev, b200s_i
 
 b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_int ncols, const b200s_int* Bp,
                                 const b200s_int* Bi, const double* Bx, b200s_int** Xp, b200s_int** Xi, double** Xx) {
+    B200S_NVTX("b200s_chol_spsolve");
     if (!F || !Xp || !Xi || !Xx || nrows != F->plan.n || ncols < 0) return B200S_INVALID;
     *Xp = nullptr; *Xi = nullptr; *Xx = nullptr;
     const i64 n = nrows;
@@ -302,6 +310,7 @@ b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_i
 }
 
 b200s_status b200s_chol_diag(b200s_chol* F, double* d_out) {
+    B200S_NVTX("b200s_chol_diag");
     if (!F) return B200S_INVALID;
     if (F->plan.n == 0) return B200S_OK;
     if (!d_out) return B200S_INVALID;
@@ -311,6 +320,7 @@ b200s_status b200s_chol_diag(b200s_chol* F, double* d_out) {
 }
 
 b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, double** Lx) {
+    B200S_NVTX("b200s_chol_get_L");
     if (!F || !Lp || !Li || !Lx) return B200S_INVALID;
     *Lp = nullptr; *Li = nullptr; *Lx = nullptr;
     const CholPlan& P = F->plan;

@@ -14,6 +14,7 @@
 // Host pointers at the C ABI (b200s_kkt_*, include/b200sparse.h); everything numeric runs on the device.
 #include "../../include/b200sparse.h"
 #include "gpu.hpp"
+#include "nvtx_range.hpp"
 #include "devpool.hpp"
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -417,6 +418,7 @@ b200s_status b200s_kkt_set_singular(b200s_kkt* K, int on) {
 }
 
 static int kkt_factor_impl(b200s_kkt* K, const double* di, const double* Hx, b200s_int* minor_out) {
+    B200S_NVTX("kkt_factor_impl");
     if (!K || (K->ml > 0 && !di) || (K->hasH && K->nnzH > 0 && !Hx)) return ST_INVALID;
     K->factored = false;
     if (device_count() <= 0) { set_last_error("no CUDA device available"); return ST_NO_DEVICE; }
@@ -460,6 +462,7 @@ static int kkt_factor_impl(b200s_kkt* K, const double* di, const double* Hx, b20
 }
 
 static int kkt_solve_impl(b200s_kkt* K, double* x, double* y, double* z) {
+    B200S_NVTX("kkt_solve_impl");
     if (!K || (K->n > 0 && !x) || (K->p > 0 && !y) || (K->ml > 0 && !z)) return ST_INVALID;
     if (!K->factored) { set_last_error("kkt: solve called before a successful factor"); return ST_INVALID; }
     if (K->n == 0) return ST_OK;

@@ -10,6 +10,7 @@
 // run in k_dgemm (register-tiled FP64).  All device work is on the factor object's stream; no CPU fallback.
 #include "../../include/b200sparse.h"
 #include "gpu.hpp"
+#include "nvtx_range.hpp"
 #include "devpool.hpp"
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -353,6 +354,7 @@ static int kktd_ensure_device(b200s_kktd* K) {
 }
 
 static int kktd_factor_impl(b200s_kktd* K, const double* di, const double* H, b200s_int* minor_out) {
+    B200S_NVTX("kktd_factor_impl");
     if (!K || (K->ml > 0 && !di)) return ST_INVALID;
     K->factored = false;
     const long long n = K->n, ml = K->ml, p = K->p, q = n - p;
@@ -402,6 +404,7 @@ b200s_status b200s_kktd_factor(b200s_kktd* K, const double* di, const double* H,
 }
 
 static int kktd_solve_impl(b200s_kktd* K, double* x, double* y, double* z) {
+    B200S_NVTX("kktd_solve_impl");
     if (!K || (K->n > 0 && !x) || (K->p > 0 && !y) || (K->ml > 0 && !z)) return ST_INVALID;
     if (!K->factored) { set_last_error("kkt 'chol': solve called before a successful factor"); return ST_INVALID; }
     const long long n = K->n, ml = K->ml, p = K->p, q = n - p;

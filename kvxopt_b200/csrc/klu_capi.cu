@@ -1,6 +1,7 @@
 // extern "C" boundary, KLU half (include/b200sparse.h).
 #include "../../include/b200sparse.h"
 #include "gpu.hpp"
+#include "nvtx_range.hpp"
 #include "klu_host.hpp"
 #include <cstring>
 #include <new>
@@ -38,6 +39,7 @@ struct b200s_klu_num {
 extern "C" {
 
 b200s_status b200s_klu_analyze(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, b200s_klu_sym** out) {
+    B200S_NVTX("b200s_klu_analyze");
     if (!out) return B200S_INVALID;
     *out = nullptr;
     if (n < 0 || (n > 0 && (!colptr || (colptr[n] > 0 && !rowind)))) return B200S_INVALID;
@@ -57,6 +59,7 @@ b200s_status b200s_klu_analyze(b200s_int n, const b200s_int* colptr, const b200s
 
 static b200s_status factor_impl(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind, const double* val,
                                 b200s_klu_num** out, bool with_device) {
+    B200S_NVTX("factor_impl");
     if (!S || !out) return B200S_INVALID;
     *out = nullptr;
     const i32 n = S->S.n;
@@ -121,6 +124,7 @@ b200s_status b200s_klu_extract_host(const b200s_klu_num* N, double* Lx, double* 
 
 static b200s_status refactor_impl(b200s_klu_num* N, const double* vals, bool on_device, b200s_int batch, b200s_int ldv,
                                   int* status_per_matrix) {
+    B200S_NVTX("refactor_impl");
     if (!N || batch < 0) return B200S_INVALID;
     if (N->N.n == 0 || batch == 0) return B200S_OK;
     if (!vals || ldv < N->S.nnz || batch > 0x7fffff00) return B200S_INVALID;
@@ -135,6 +139,7 @@ b200s_status b200s_klu_refactor_batch_dev(b200s_klu_num* N, const double* vals_d
 }
 
 b200s_status b200s_klu_refactor_batch_begin(b200s_klu_num* N, const double* vals, b200s_int batch, b200s_int ldv) {
+    B200S_NVTX("b200s_klu_refactor_batch_begin");
     if (!N || batch < 0) return B200S_INVALID;
     if (N->N.n == 0 || batch == 0) return B200S_OK;
     if (!vals || ldv < N->S.nnz || batch > 0x7fffff00) return B200S_INVALID;
@@ -142,6 +147,7 @@ b200s_status b200s_klu_refactor_batch_begin(b200s_klu_num* N, const double* vals
     return (b200s_status)klu_device_refactor_begin(N->dev, vals, batch, ldv);
 }
 b200s_status b200s_klu_refactor_batch_end(b200s_klu_num* N, int* status_per_matrix) {
+    B200S_NVTX("b200s_klu_refactor_batch_end");
     if (!N) return B200S_INVALID;
     if (N->N.n == 0) return B200S_OK;
     if (!N->dev) return B200S_NO_DEVICE;
@@ -149,6 +155,7 @@ b200s_status b200s_klu_refactor_batch_end(b200s_klu_num* N, int* status_per_matr
 }
 
 static b200s_status solve_impl(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB, b200s_int batch, bool on_device) {
+    B200S_NVTX("solve_impl");
     if (!N || nrhs < 0 || batch < 0 || (trans != 0 && trans != 1)) return B200S_INVALID;
     if (N->N.n == 0 || nrhs == 0 || batch == 0) return B200S_OK;
     if (!B || ldB < N->N.n) return B200S_INVALID;

@@ -68,3 +68,42 @@ def test_python_mirror_raises_without_gpu():
         cholmod.linsolve(A, B)
     with pytest.raises(RuntimeError):
         klu.linsolve(A, B)
+
+
+def test_compiled_reference_wrappers_load_and_refuse_to_run_without_a_gpu():
+    """kvxopt.cholmod / kvxopt.klu as compiled extension modules (the reference's src/C/cholmod.c and klu.c against
+    include/suitesparse_shim, tools/build_kvxopt_ext.sh): they import in a fresh interpreter, expose the reference's
+    function table, do the host-side symbolic work, and every numeric call fails loudly when there is no GPU."""
+    import subprocess
+    import sys
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not any(f.startswith("cholmod.") and f.endswith(".so") for f in os.listdir(os.path.join(ref, "kvxopt"))):
+        pytest.fail("oracle/_ref/kvxopt/cholmod*.so is missing: run tools/build_kvxopt_ext.sh in the build container")
+    code = r'''
+import sys, json
+sys.path.insert(0, %r)
+from kvxopt import cholmod, klu, spmatrix, matrix
+from kvxopt_b200 import _lib
+out = {"compiled": cholmod.__file__.endswith(".so") and klu.__file__.endswith(".so"),
+       "funcs": all(hasattr(cholmod, f) for f in ("options", "symbolic", "numeric", "solve", "spsolve", "linsolve", "splinsolve", "diag", "getfactor"))
+                and all(hasattr(klu, f) for f in ("linsolve", "symbolic", "numeric", "solve", "get_numeric", "get_det"))}
+A = spmatrix([10, 3, 5, -2, 5, 2], [0, 2, 1, 3, 2, 3], [0, 0, 1, 1, 2, 3])
+F = cholmod.symbolic(A)
+out["capsule"] = repr(F)
+Fs = klu.symbolic(A)
+if _lib.device_count() == 0:
+    for name, call in (("cholmod.numeric", lambda: cholmod.numeric(A, F)), ("klu.numeric", lambda: klu.numeric(A, Fs)),
+                       ("cholmod.linsolve", lambda: cholmod.linsolve(A, matrix(1.0, (4, 1))))):
+        try:
+            call(); out[name] = "ran"
+        except (ValueError, ArithmeticError) as e:
+            out[name] = "refused"
+print("OUT " + json.dumps(out))
+''' % ref
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    import json
+    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("OUT ")][-1][4:])
+    assert out["compiled"] and out["funcs"] and "CHOLMOD SYM D FACTOR L" in out["capsule"]
+    for k in ("cholmod.numeric", "klu.numeric", "cholmod.linsolve"):
+        assert out.get(k, "refused") == "refused"          # no silent CPU path behind the compiled modules
