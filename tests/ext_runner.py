@@ -79,7 +79,7 @@ V = [2, 3, 3, -1, 4, 4, -3, 1, 2, 2, 6, 1]
 I = [0, 1, 0, 2, 4, 1, 2, 3, 4, 2, 1, 4]
 J = [0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 4, 4]
 Ak = spmatrix(V, I, J)
-Bk = matrix(1.0, (5, 1))
+Bk = matrix(range(5), tc="d")
 klu.linsolve(Ak, Bk)
 out["klu_linsolve_err"] = float(np.abs(np.array(Bk).ravel() - [0.052631578947368, -0.035087719298246, 3.0, 5.482456140350877,
                                                                -1.859649122807017]).max())
