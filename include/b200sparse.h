@@ -247,8 +247,12 @@ typedef struct {
                   *upd_cnt, *dest, *lslot0, *fslot0;
     /* wave schedule of the fast kernel (klu_gpu.cu): statistics */
     b200s_int nwaves, nwaves_with_deps, nbatches, nsegments, staged_rows;
+    b200s_int npieces, npiece_users;     /* staged source blocks (<= 4 columns of one L supernode) x row pieces; (piece, user column) pairs */
 } b200s_klu_plan_view_t;
 b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* view);
+/* Replays the wave-schedule tables of the plan on the HOST for one matrix with the values `val` and returns the factor in the
+ * layout of b200s_klu_extract_host.  Verification of the host-built plan in CPU tests; not a factorization path. */
+b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* val, double* Lx, double* Ux, double* Fx, double* Rs);
 
 void b200s_klu_free_symbolic(b200s_klu_sym* S);   /* src/C/klu.c:51-61 */
 void b200s_klu_free_numeric(b200s_klu_num* N);    /* src/C/klu.c:63-72 */

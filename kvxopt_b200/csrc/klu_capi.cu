@@ -237,6 +237,29 @@ b200s_status b200s_klu_extract_batch(b200s_klu_num* N, b200s_int b, double* Lx, 
     return extract_values(N, b, Lx, Ux, Fx, Rs);
 }
 
+/* Test hook: replays the wave-schedule tables of the refactorization plan on the HOST for one matrix (klu_plan_emulate) and
+ * returns the factor in the layout of b200s_klu_extract_host.  It verifies the host-built plan without a GPU; nothing in
+ * the Python mirrors calls it and it is not a factorization path. */
+b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* val, double* Lx, double* Ux, double* Fx, double* Rs) {
+    if (!N || !val) return B200S_INVALID;
+    const i32 n = N->N.n;
+    std::vector<double> slots((size_t)std::max<i64>(N->P.nslots, 1)), rs((size_t)std::max<i32>(n, 1));
+    int st;
+    try { st = klu_plan_emulate(N->S, N->P, val, slots.data(), rs.data()); }
+    catch (const std::exception& e) { set_last_error(e.what()); return B200S_INVALID; }
+    for (i32 k = 0; k < n; k++) {
+        const i64 nu = N->N.Up[k + 1] - N->N.Up[k];
+        if (Ux) for (i64 p = 0; p < nu; p++) Ux[N->N.Up[k] + p] = slots[N->P.cbeg[k] + p];
+        if (Lx) {
+            Lx[N->N.Lp[k]] = 1.0;
+            for (i64 p = N->N.Lp[k] + 1; p < N->N.Lp[k + 1]; p++) Lx[p] = slots[N->P.lslot0[k] + (p - N->N.Lp[k] - 1)];
+        }
+        if (Fx) for (i64 p = N->N.Fp[k]; p < N->N.Fp[k + 1]; p++) Fx[p] = slots[N->P.fslot0[k] + (p - N->N.Fp[k])];
+        if (Rs) Rs[k] = rs[k];
+    }
+    return (b200s_status)st;
+}
+
 b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* v) {
     if (!N || !v) return B200S_INVALID;
     const KluPlan& P = N->P;
@@ -251,6 +274,7 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
     for (int d : P.wave_hasdep) v->nwaves_with_deps += d;
     v->nbatches = (b200s_int)P.bseg_ptr.size() - 1; v->nsegments = (b200s_int)P.seg_src.size(); v->staged_rows = 0;
     for (int c : P.seg_cnt) v->staged_rows += c;
+    v->npieces = (b200s_int)P.pc_j0.size(); v->npiece_users = (b200s_int)P.pc_user_col.size();
     return B200S_OK;
 }
 

@@ -345,6 +345,12 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
             }
         }
         if (dbg) { long long tB = clock64(); t_init += tB - tA; tA = tB; }
+        double pend[KLU_SN_MAX - 1], u[KLU_SN_MAX];
+        int pend_row = 0, pend_n = 0;
+#pragma unroll
+        for (int a = 0; a < KLU_SN_MAX; a++) u[a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < KLU_SN_MAX - 1; a++) pend[a] = 0.0;
         for (int c = 0; c < nb; c++) {
             const long long g = c0 + c;
             const int buf = (int)(g % KLU_STAGES);
@@ -356,45 +362,88 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                 const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
                 const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
                                       col * KLU_REC_U32;
-                const unsigned short* dd = reinterpret_cast<const unsigned short*>(rec + 16);
+                const unsigned short* dd = reinterpret_cast<const unsigned short*>(rec + KLU_REC_HDR);
                 const int nseg = (int)rec[0];
-                // per matched segment: team barrier (the previous segment may have written u_jk or the same rows from
-                // another warp of the team), then the segment's rows are split over the team in chunks of four
-                for (int sgi = 1; sgi <= nseg; sgi++) {
-                    const unsigned sd = rec[sgi];
-                    const int r0 = sd & 0xffu, r1 = r0 + ((sd >> 8) & 0xffu);
-                    int t = r0 + 4 * sub;
-                    // every chunk is four PREDICATED rows (a partial chunk costs one pass, not one dependent
-                    // load-update-store chain per row); the operands of the first chunk are fetched before the team
-                    // barrier (they do not depend on it)
-                    int e[4]; double m[4];
+                // A piece = rows [i, i + nrows) below a source BLOCK of g <= KLU_SN_MAX consecutive columns of one L supernode, of
+                // which this column uses the last gu = g - s0 (fill closure).  The block's own rows (u_jk, consecutive rows of
+                // x) first go through the block's unit lower triangle in registers; then every destination row is read and
+                // written ONCE for gu multiply-adds (one read-modify-write per multiply-add before: the kernel was bound by
+                // shared-memory wavefronts and by the ~22 instructions it issued per multiply-add).
+                for (int sgi = 0; sgi < nseg; sgi++) {
+                    const unsigned w0 = rec[1 + 2 * sgi], w1 = rec[2 + 2 * sgi];
+                    const int r0 = w0 & 0xffu, nrows = (w0 >> 8) & 0xffu, uloc = (int)(w0 >> 16);
+                    const int g = w1 & 0xfu, s0 = (w1 >> 4) & 0xfu, tri0 = (w1 >> 8) & 0xffu;
+                    const bool hastri = (w1 >> 16) & 1u, cont = (w1 >> 17) & 1u;
+                    const int gu = g - s0;
+                    team_sync();          // the previous piece of every warp of the team is complete
+                    if (pend_n) {         // rows of the previous block's triangle (see below)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const bool on = t + q < r1;
-                        e[q] = on ? dd[t + q] * 32 : 0;
-                        m[q] = on ? sb[(t + q) * 32] : 0.0;
+                        for (int a = 0; a < KLU_SN_MAX - 1; a++) if (a < pend_n) x[(pend_row + a) * 32] = pend[a];
+                        pend_n = 0;
                     }
-                    team_sync();
-                    const double ujk = x[(sd >> 16) * 32];
-                    for (;;) {
-                        double xv[4];
+                    // a continuation piece (more rows below the same block, possibly in a later batch) keeps the u_a every
+                    // warp of the team computed for the block's first piece: they are not re-read (warp 0's deferred write
+                    // of them may still be in flight)
+                    if (!cont) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) xv[q] = x[e[q]];
+                        for (int a = 0; a < KLU_SN_MAX; a++) u[a] = a < gu ? x[(uloc + a) * 32] : 0.0;
+                    }
+                    if (hastri && gu > 1) {
+                        // u_a -= sum_{b < a} L(j0+s0+a, j0+s0+b) u_b: computed by every warp of the team (identical values);
+                        // warp `sub == 0` writes the rows back -- at once when it owns the column alone, else after the team's
+                        // NEXT barrier, so that no warp of the team can read an already updated row (nobody reads these rows
+                        // again before that: each row of U belongs to one source column)
 #pragma unroll
-                        for (int q = 0; q < 4; q++) if (t + q < r1) x[e[q]] = xv[q] - m[q] * ujk;
-                        t += 4 * T;
-                        if (t >= r1) break;
+                        for (int a = 1; a < KLU_SN_MAX; a++)
+                            if (a < gu) {
+                                const int A = s0 + a;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const bool on = t + q < r1;
-                            e[q] = on ? dd[t + q] * 32 : 0;
-                            m[q] = on ? sb[(t + q) * 32] : 0.0;
+                                for (int b = 0; b < KLU_SN_MAX - 1; b++)
+                                    if (b < a) {
+                                        const int B = s0 + b;
+                                        u[a] = fma(-sb[(tri0 + B * (g - 1) - (B * (B - 1)) / 2 + (A - B - 1)) * 32], u[b], u[a]);
+                                    }
+                            }
+                        if (sub == 0) {
+                            if (T == 1) {
+#pragma unroll
+                                for (int a = 1; a < KLU_SN_MAX; a++) if (a < gu) x[(uloc + a) * 32] = u[a];
+                            } else {
+                                pend_row = uloc + 1; pend_n = gu - 1;
+#pragma unroll
+                                for (int a = 1; a < KLU_SN_MAX; a++) pend[a - 1] = u[a];
+                            }
                         }
+                    }
+                    const double* lb = sb + (r0 + s0 * nrows) * 32;
+                    for (int i = 4 * sub; i < nrows; i += 4 * T) {
+                        int e[4]; double acc[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) e[q] = i + q < nrows ? dd[r0 + i + q] * 32 : 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[q] = x[e[q]];
+#pragma unroll
+                        for (int a = 0; a < KLU_SN_MAX; a++)
+                            if (a < gu) {
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    const double m = i + q < nrows ? lb[(a * nrows + i + q) * 32] : 0.0;
+                                    acc[q] = fma(-m, u[a], acc[q]);
+                                }
+                            }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (i + q < nrows) x[e[q]] = acc[q];
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) klu_mbar_arrive(&empty_bar[buf]);
+        }
+        if (active && T > 1) team_sync();      // every warp of the team is past the reads of its last piece
+        if (pend_n) {             // (T > 1, warp sub == 0) the last triangle rows of this wave
+#pragma unroll
+            for (int a = 0; a < KLU_SN_MAX - 1; a++) if (a < pend_n) x[(pend_row + a) * 32] = pend[a];
+            pend_n = 0;
         }
         if (tid < KLU_WAVE_WARPS) done_round[tid] = 0x7fffffff;
         if (w + 1 < W.nwaves) load_part2();      // part 2 of the next wave's parameters (depends on part 1)

@@ -535,12 +535,22 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         P.wave_hasdep.assign(nw, 0);
         P.wbatch_ptr.assign(1, 0);
         P.bseg_ptr.assign(1, 0);
-        std::vector<i32> srcs, matched, users;
+        // nested[j]: Lpattern(j) = {j+1} u Lpattern(j+1) -- columns j and j+1 belong to one supernode of L
+        std::vector<unsigned char> nested(n, 0);
+        for (i32 j = 0; j + 1 < n; j++) {
+            const i64 a0 = N.Lp[j] + 1, a1 = N.Lp[j + 1], b0 = N.Lp[j + 1] + 1, b1 = N.Lp[j + 2];
+            if (a1 - a0 != b1 - b0 + 1 || a1 == a0 || N.Li[a0] != j + 1) continue;
+            bool same = true;
+            for (i64 q = 0; q < b1 - b0 && same; q++) same = N.Li[a0 + 1 + q] == N.Li[b0 + q];
+            nested[j] = same;
+        }
+        const i32 snmax = getenv("B200S_KLU_SN_MAX") ? std::max(1, std::min<i32>(KLU_SN_MAX, atoi(getenv("B200S_KLU_SN_MAX")))) : KLU_SN_MAX;
+        std::vector<i32> srcs, matched, s0of;
         std::vector<i64> ucur;
         for (i32 w = 0; w < nw; w++) {
-            const i32 k0 = P.wave_col0[w];
+            const i32 k0 = P.wave_col0[w], wc = P.wave_col0[w + 1] - k0;
             srcs.clear();
-            for (i32 c = k0; c < P.wave_col0[w + 1]; c++) {
+            for (i32 c = k0; c < k0 + wc; c++) {
                 i64 u = P.upd_ptr[c];
                 while (u < P.upd_end[c] && P.upd_src[u] < k0) { srcs.push_back(P.upd_src[u]); u++; }
                 P.upd_split[c] = u;
@@ -548,40 +558,101 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             }
             std::sort(srcs.begin(), srcs.end());
             srcs.erase(std::unique(srcs.begin(), srcs.end()), srcs.end());
-            i32 fill = KLU_CHUNK_ROWS;      // rows used in the open batch (full => start a new one)
-            matched.assign(P.wave_col0[w + 1] - k0, 0);                 // segments of the open batch used by each column
-            ucur.resize(P.wave_col0[w + 1] - k0);
-            for (i32 c = k0; c < P.wave_col0[w + 1]; c++) ucur[c - k0] = P.upd_ptr[c];
-            for (i32 j : srcs) {
-                const i32 total = (i32)(N.Lp[j + 1] - N.Lp[j] - 1);
-                // columns of the wave that use source j
-                users.clear();
-                for (i32 c = k0; c < P.wave_col0[w + 1]; c++) {
-                    i64& u = ucur[c - k0];
-                    if (u < P.upd_split[c] && P.upd_src[u] == j) { users.push_back(c - k0); u++; }
+            i32 fill = KLU_CHUNK_ROWS;      // row units used in the open batch (full => start a new one)
+            matched.assign(wc, 0);                                      // pieces of the open batch used by each column
+            ucur.resize(wc);
+            s0of.resize(wc);
+            for (i32 q = 0; q < wc; q++) ucur[q] = P.upd_ptr[k0 + q];
+            auto open_batch = [&]() {
+                std::fill(matched.begin(), matched.end(), 0);
+                if (!P.seg_src.empty() && P.bseg_ptr.back() != (i64)P.seg_src.size()) {
+                    P.bseg_ptr.push_back((i64)P.seg_src.size());
+                    P.bpiece_ptr.push_back((i64)P.pc_j0.size());
                 }
-                i32 off = 0;
-                while (off < total) {
-                    bool overflow = false;
-                    for (i32 q : users) if (matched[q] >= KLU_MAXSEG) overflow = true;
-                    if (overflow) fill = KLU_CHUNK_ROWS;
-                    if (fill == KLU_CHUNK_ROWS) {          // open a new batch
-                        std::fill(matched.begin(), matched.end(), 0);
-                        if (!P.seg_src.empty() && P.bseg_ptr.back() != (i64)P.seg_src.size()) P.bseg_ptr.push_back((i64)P.seg_src.size());
-                        P.batch_rowslot.insert(P.batch_rowslot.end(), KLU_CHUNK_ROWS, -1);
-                        fill = 0;
+                P.batch_rowslot.insert(P.batch_rowslot.end(), KLU_CHUNK_ROWS, -1);
+                fill = 0;
+            };
+            auto add_copy = [&](i32 j, i32 off, i32 cnt, i32 row) {
+                P.seg_src.push_back(j); P.seg_off.push_back(off); P.seg_cnt.push_back(cnt); P.seg_row.push_back(row);
+                i32* rs = P.batch_rowslot.data() + P.batch_rowslot.size() - KLU_CHUNK_ROWS;
+                for (i32 r = 0; r < cnt; r++) rs[row + r] = P.lslot0[j] + off + r;
+            };
+            size_t si = 0;
+            while (si < srcs.size()) {
+                // ---- source block: up to snmax consecutive columns of one L supernode, each user column taking a suffix of it
+                const i32 j0 = srcs[si];
+                i32 g = 1;
+                while (g < snmax && si + g < srcs.size() && srcs[si + g] == j0 + g && nested[j0 + g - 1]) g++;
+                // users and their first source inside the block; the block is cut where a user would skip a column
+                // (cannot happen for a structurally closed pattern, checked all the same)
+                for (;;) {
+                    bool ok = true;
+                    for (i32 q = 0; q < wc && ok; q++) {
+                        const i32 c = k0 + q;
+                        i64 u = ucur[q];
+                        s0of[q] = -1;
+                        if (u >= P.upd_split[c] || P.upd_src[u] >= j0 + g) continue;
+                        s0of[q] = P.upd_src[u] - j0;
+                        for (i32 a = s0of[q]; a < g && ok; a++, u++) ok = u < P.upd_split[c] && P.upd_src[u] == j0 + a;
                     }
-                    const i32 cnt = std::min(KLU_CHUNK_ROWS - fill, total - off);
-                    P.seg_src.push_back(j); P.seg_off.push_back(off); P.seg_cnt.push_back(cnt); P.seg_row.push_back(fill);
-                    for (i32 q : users) matched[q]++;
-                    i32* rs = P.batch_rowslot.data() + P.batch_rowslot.size() - KLU_CHUNK_ROWS;
-                    for (i32 r = 0; r < cnt; r++) rs[fill + r] = P.lslot0[j] + off + r;
-                    fill += cnt;
-                    off += cnt;
+                    if (ok || g == 1) break;
+                    g--;
                 }
+                si += g;
+                const i32 R = (i32)(N.Lp[j0 + g] - N.Lp[j0 + g - 1] - 1);       // rows below the block, common to its columns
+                const i32 tri = g * (g - 1) / 2;
+                i32 i0 = 0;
+                bool first = true;
+                while (first || i0 < R) {
+                    bool overflow = false;
+                    for (i32 q = 0; q < wc; q++) if (s0of[q] >= 0 && matched[q] >= KLU_MAXSEG) overflow = true;
+                    const i32 need0 = first ? tri : 0;
+                    i32 avail = KLU_CHUNK_ROWS - fill - need0;
+                    i32 nrows = avail > 0 ? std::min(R - i0, avail / g) : 0;
+                    // a piece that would be cut far below a full batch's worth goes to a fresh batch
+                    if (overflow || fill == KLU_CHUNK_ROWS || avail < 0 || (nrows < R - i0 && nrows < std::min(R - i0, 16)) || (R == 0 && avail < 0)) {
+                        open_batch();
+                        avail = KLU_CHUNK_ROWS - need0;
+                        nrows = std::min(R - i0, avail / g);
+                    }
+                    const i32 tri0 = first && tri > 0 ? fill : -1;
+                    if (first && tri > 0) {
+                        i32 t = fill;
+                        for (i32 b = 0; b + 1 < g; b++) { add_copy(j0 + b, 0, g - 1 - b, t); t += g - 1 - b; }
+                        fill += tri;
+                    }
+                    const i32 r0 = fill;
+                    for (i32 a = 0; a < g && nrows > 0; a++) add_copy(j0 + a, (g - 1 - a) + i0, nrows, r0 + a * nrows);
+                    fill += g * nrows;
+                    P.pc_j0.push_back(j0); P.pc_g.push_back(g); P.pc_i0.push_back(i0); P.pc_nrows.push_back(nrows);
+                    P.pc_r0.push_back(r0); P.pc_tri0.push_back(tri0);
+                    P.pc_user_ptr.push_back((i64)P.pc_user_col.size());
+                    for (i32 q = 0; q < wc; q++)
+                        if (s0of[q] >= 0) {
+                            matched[q]++;
+                            P.pc_user_col.push_back(q); P.pc_user_s0.push_back(s0of[q]); P.pc_user_upd.push_back(ucur[q]);
+                        }
+                    i0 += nrows;
+                    first = false;
+                    if (R == 0) break;
+                }
+                for (i32 q = 0; q < wc; q++) if (s0of[q] >= 0) ucur[q] += g - s0of[q];
             }
-            if (P.bseg_ptr.back() != (i64)P.seg_src.size()) P.bseg_ptr.push_back((i64)P.seg_src.size());
+            for (i32 q = 0; q < wc; q++) if (ucur[q] != P.upd_split[k0 + q]) throw std::logic_error("klu plan: staged blocks do not cover a column");
+            if (P.bseg_ptr.back() != (i64)P.seg_src.size()) { P.bseg_ptr.push_back((i64)P.seg_src.size()); P.bpiece_ptr.push_back((i64)P.pc_j0.size()); }
             P.wbatch_ptr.push_back((i64)P.bseg_ptr.size() - 1);
+        }
+        P.pc_user_ptr.push_back((i64)P.pc_user_col.size());
+        if (tdbg) {
+            // multiply-adds by the number of source columns a (piece, user) pair applies at once
+            double fm[KLU_SN_MAX + 1] = {0};
+            i64 np_[KLU_SN_MAX + 1] = {0};
+            for (size_t pc = 0; pc < P.pc_j0.size(); pc++)
+                for (i64 uq = P.pc_user_ptr[pc]; uq < P.pc_user_ptr[pc + 1]; uq++) {
+                    const i32 gu = P.pc_g[pc] - P.pc_user_s0[uq];
+                    fm[gu] += (double)gu * P.pc_nrows[pc]; np_[gu]++;
+                }
+            for (i32 q = 1; q <= KLU_SN_MAX; q++) fprintf(stderr, "[b200s klu plan] (piece, user) pairs applying %d source columns: %lld, multiply-adds %.0f\n", q, (long long)np_[q], fm[q]);
         }
     }
     lap("waves + batches");
@@ -607,23 +678,31 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
                 const i32 len = (i32)(P.cbeg[c + 1] - cb);
                 if (P.col_roff[c] + len > KLU_WAVE_ROWS) continue;      // oversized single column: fallback kernel
                 for (i32 sl = 0; sl < len; sl++) P.wave_rowsrc[(size_t)w * KLU_WAVE_ROWS + P.col_roff[c] + sl] = P.slot_src[cb + sl];
-                // entries of the staged (earlier-wave) updates of column c
-                i64 u = P.upd_ptr[c];
-                for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1] && u < P.upd_split[c]; bi++)
-                    for (i64 sg = P.bseg_ptr[bi]; sg < P.bseg_ptr[bi + 1] && u < P.upd_split[c]; sg++) {
-                        if (P.seg_src[sg] != P.upd_src[u]) continue;
-                        const i32 uloc = (i32)(P.upd_uslot[u] - cb);
-                        uint32_t* rec = P.bentry.data() + (size_t)bi * BST + (size_t)(c - k0) * KLU_REC_U32;
-                        if (rec[0] >= (uint32_t)KLU_MAXSEG) throw std::logic_error("klu plan: too many segments in a batch record");
-                        rec[0]++;
-                        rec[rec[0]] = (uint32_t)P.seg_row[sg] | ((uint32_t)P.seg_cnt[sg] << 8) | ((uint32_t)uloc << 16);
-                        uint16_t* dd = reinterpret_cast<uint16_t*>(rec + 16);
-                        for (i32 r = 0; r < P.seg_cnt[sg]; r++)
-                            dd[P.seg_row[sg] + r] = (uint16_t)(P.dest[P.upd_dest[u] + P.seg_off[sg] + r] - cb);
-                        if (P.seg_off[sg] + P.seg_cnt[sg] == P.upd_cnt[u]) u++;
-                    }
-                if (u != P.upd_split[c]) throw std::logic_error("klu plan: staged updates do not cover a column");
             }
+            // records of the staged pieces, per (batch, column of the wave): {npieces, then two words per piece:
+            //   w0 = first stage row of the rectangle | rows << 8 | (row of u for the first source used, in the column) << 16
+            //   w1 = block width g | first source used s0 << 4 | first stage row of the triangle << 8 | has-triangle << 16 |
+            //        continuation-of-the-previous-piece's-block << 17},
+            // and for every rectangle row (stage row of the block's first column) the destination row in the column
+            for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1]; bi++)
+                for (i64 pc = P.bpiece_ptr[bi]; pc < P.bpiece_ptr[bi + 1]; pc++)
+                    for (i64 uq = P.pc_user_ptr[pc]; uq < P.pc_user_ptr[pc + 1]; uq++) {
+                        const i32 q = P.pc_user_col[uq], c = k0 + q, s0 = P.pc_user_s0[uq], g = P.pc_g[pc];
+                        const i64 cb = P.cbeg[c], u0 = P.pc_user_upd[uq], ulast = u0 + (g - 1 - s0);
+                        uint32_t* rec = P.bentry.data() + (size_t)bi * BST + (size_t)q * KLU_REC_U32;
+                        if (rec[0] >= (uint32_t)KLU_MAXSEG) throw std::logic_error("klu plan: too many pieces in a batch record");
+                        const uint32_t k = rec[0]++;
+                        const i32 uloc = (i32)(P.upd_uslot[u0] - cb);
+                        for (i32 t = 1; t < g - s0; t++)
+                            if (P.upd_uslot[u0 + t] != P.upd_uslot[u0] + t) throw std::logic_error("klu plan: U rows of a source block are not consecutive");
+                        rec[1 + 2 * k] = (uint32_t)P.pc_r0[pc] | ((uint32_t)P.pc_nrows[pc] << 8) | ((uint32_t)uloc << 16);
+                        rec[2 + 2 * k] = (uint32_t)g | ((uint32_t)s0 << 4) | ((uint32_t)std::max(P.pc_tri0[pc], 0) << 8) |
+                                         ((uint32_t)(P.pc_tri0[pc] >= 0) << 16) | ((uint32_t)(P.pc_i0[pc] > 0) << 17);
+                        uint16_t* dd = reinterpret_cast<uint16_t*>(rec + KLU_REC_HDR);
+                        if (P.upd_src[ulast] != P.pc_j0[pc] + g - 1 || P.upd_cnt[ulast] < P.pc_i0[pc] + P.pc_nrows[pc]) throw std::logic_error("klu plan: piece / update mismatch");
+                        for (i32 r = 0; r < P.pc_nrows[pc]; r++)
+                            dd[P.pc_r0[pc] + r] = (uint16_t)(P.dest[P.upd_dest[ulast] + P.pc_i0[pc] + r] - cb);
+                    }
             // in-wave blob
             std::vector<uint32_t> hdr(2 * KLU_WAVE_WARPS, 0), upd;
             std::vector<uint16_t> dst;
@@ -670,6 +749,101 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         std::vector<i32> pos(P.level_ptr.begin(), P.level_ptr.end() - 1);
         for (i32 k = 0; k < n; k++) P.level_cols[pos[level[k]]++] = k;
     }
+}
+
+// Host interpreter of the wave schedule: executes, for ONE matrix, exactly the tables k_klu_refactor_wave replays (row
+// scaling, gather through wave_rowsrc, TMA copy descriptors seg_*, piece records in bentry, in-wave blobs) followed by the
+// dense trailing block as a plain unpivoted elimination.  Test hook for the host-built plan; never a product path.
+int klu_plan_emulate(const KluSymbolic& S, const KluPlan& P, const double* Ax, double* LU, double* Rs) {
+    const i32 n = P.n;
+    int status = 0;
+    std::vector<double> As((size_t)std::max<i64>(P.nnzA, 1));
+    for (i32 i = 0; i < n; i++) {
+        double m = 0.0;
+        for (i64 p = P.rowptr[i]; p < P.rowptr[i + 1]; p++) m = std::max(m, std::fabs(Ax[P.rowent[p]]));
+        Rs[i] = m > 0.0 ? m : 1.0;
+        for (i64 p = P.rowptr[i]; p < P.rowptr[i + 1]; p++) As[P.rowent[p]] = Ax[P.rowent[p]] / Rs[i];
+    }
+    for (i64 v = 0; v < P.nslots; v++) LU[v] = 0.0;
+    for (i64 v = P.lu_slots; v < P.nslots; v++) LU[v] = P.slot_src[v] >= 0 ? As[P.slot_src[v]] : 0.0;
+    if (!P.wave_ok) return ST_INVALID;
+    std::vector<double> xs(KLU_WAVE_ROWS, 0.0), stage(KLU_CHUNK_ROWS, 0.0);
+    const size_t BST = (size_t)KLU_WAVE_WARPS * KLU_REC_U32 + KLU_CHUNK_ROWS;
+    const i32 nw = (i32)P.wave_col0.size() - 1;
+    (void)S;
+    for (i32 w = 0; w < nw; w++) {
+        const i32 k0 = P.wave_col0[w], k1 = P.wave_col0[w + 1], wc = k1 - k0;
+        const i32 wrows = (i32)(P.cbeg[k1] - P.cbeg[k0]);
+        for (i32 r = 0; r < wrows; r++) {
+            const i32 src = P.wave_rowsrc[(size_t)w * KLU_WAVE_ROWS + r];
+            xs[r] = src >= 0 ? As[src] : 0.0;
+        }
+        for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1]; bi++) {
+            std::fill(stage.begin(), stage.end(), std::nan(""));
+            for (i64 sg = P.bseg_ptr[bi]; sg < P.bseg_ptr[bi + 1]; sg++)
+                for (i32 r = 0; r < P.seg_cnt[sg]; r++) stage[P.seg_row[sg] + r] = LU[P.lslot0[P.seg_src[sg]] + P.seg_off[sg] + r];
+            for (i32 q = 0; q < wc; q++) {
+                const uint32_t* rec = P.bentry.data() + (size_t)bi * BST + (size_t)q * KLU_REC_U32;
+                const uint16_t* dd = reinterpret_cast<const uint16_t*>(rec + KLU_REC_HDR);
+                double* x = xs.data() + P.col_roff[k0 + q];
+                for (uint32_t k = 0; k < rec[0]; k++) {
+                    const uint32_t w0 = rec[1 + 2 * k], w1 = rec[2 + 2 * k];
+                    const i32 r0 = w0 & 0xff, nrows = (w0 >> 8) & 0xff, uloc = w0 >> 16;
+                    const i32 g = w1 & 0xf, s0 = (w1 >> 4) & 0xf, tri0 = (w1 >> 8) & 0xff, hastri = (w1 >> 16) & 1;
+                    const i32 gu = g - s0;
+                    double u[KLU_SN_MAX];
+                    for (i32 a = 0; a < gu; a++) u[a] = x[uloc + a];
+                    if (hastri)
+                        for (i32 a = 1; a < gu; a++) {
+                            for (i32 b = 0; b < a; b++) {
+                                const i32 B = s0 + b, A = s0 + a;
+                                u[a] = std::fma(-stage[tri0 + B * (g - 1) - B * (B - 1) / 2 + (A - B - 1)], u[b], u[a]);
+                            }
+                            x[uloc + a] = u[a];
+                        }
+                    for (i32 i = 0; i < nrows; i++) {
+                        double acc = x[dd[r0 + i]];
+                        for (i32 a = 0; a < gu; a++) acc = std::fma(-stage[r0 + (s0 + a) * nrows + i], u[a], acc);
+                        x[dd[r0 + i]] = acc;
+                    }
+                }
+            }
+        }
+        const uint32_t* bl = P.wblob.data() + P.wblob_ptr[w] * 4;
+        const i32 nupd_wave = (i32)(bl[2 * (wc - 1)] + bl[2 * (wc - 1) + 1]);
+        const uint32_t* updl = bl + 2 * KLU_WAVE_WARPS;
+        const uint16_t* bdst = reinterpret_cast<const uint16_t*>(updl + 4 * nupd_wave);
+        for (i32 q = 0; q < wc; q++) {
+            const i32 c = k0 + q;
+            double* x = xs.data() + P.col_roff[c];
+            for (uint32_t ui = bl[2 * q]; ui < bl[2 * q] + bl[2 * q + 1]; ui++) {
+                const uint32_t w0 = updl[4 * ui];
+                const double uj = x[updl[4 * ui + 1]];
+                const i32 cnt = (i32)updl[4 * ui + 2];
+                const uint16_t* d = bdst + updl[4 * ui + 3];
+                const double* lsrc = xs.data() + (w0 >> 8);
+                for (i32 t = 0; t < cnt; t++) x[d[t]] = std::fma(-lsrc[t], uj, x[d[t]]);
+            }
+            if (c < P.spine0) {
+                const i64 cb = P.cbeg[c];
+                const double piv = x[P.udiag_slot[c] - cb];
+                if (!(std::fabs(piv) > 0.0)) status = ST_SINGULAR;
+                const double rpiv = 1.0 / piv;
+                for (i64 sl = P.lslot0[c] - cb; sl < P.cbeg[c + 1] - cb; sl++) x[sl] *= rpiv;
+            }
+        }
+        for (i32 r = 0; r < wrows; r++) LU[P.cbeg[k0] + r] = xs[r];
+    }
+    for (i32 k = P.spine0; k < n; k++) {          // dense trailing block: the updates the wave kernel left out, then the pivot
+        for (i64 u = P.upd_end[k]; u < P.upd_ptr[k + 1]; u++) {
+            const double ujk = LU[P.upd_uslot[u]];
+            for (i32 t = 0; t < P.upd_cnt[u]; t++) LU[P.dest[P.upd_dest[u] + t]] = std::fma(-LU[P.upd_lslot[u] + t], ujk, LU[P.dest[P.upd_dest[u] + t]]);
+        }
+        const double piv = LU[P.udiag_slot[k]];
+        if (!(std::fabs(piv) > 0.0)) status = ST_SINGULAR;
+        for (i64 sl = P.lslot0[k]; sl < P.cbeg[k + 1]; sl++) LU[sl] /= piv;
+    }
+    return status;
 }
 
 }  // namespace b200s

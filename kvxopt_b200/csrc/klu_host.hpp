@@ -71,6 +71,16 @@ struct KluPlan {
     std::vector<i64> bseg_ptr;        // nbatches+1 -> segments
     std::vector<i32> seg_src, seg_off, seg_cnt, seg_row;   // source column, first L row, rows, first row in the stage
     std::vector<i32> batch_rowslot;   // nbatches * KLU_CHUNK_ROWS: global slot staged into each row (-1 = unused)
+    // staged PIECES: the unit of update.  A source block = up to KLU_SN_MAX consecutive columns j0..j0+g-1 of one supernode of
+    // L (nested patterns); a user column of the wave takes a suffix s0..g-1 of it (fill closure).  The block's common rows
+    // below it (R of them) are cut into pieces of `nrows` rows that fit a batch: stage rows [r0 + a*nrows, +nrows) hold
+    // L(rows i0.., j0+a); the first piece also stages the strictly lower triangle L(j0+a, j0+b) at tri0 (column b's g-1-b
+    // entries consecutively).  seg_* above are the TMA copy descriptors that realise this layout.
+    std::vector<i64> bpiece_ptr = {0};       // nbatches+1 -> pieces
+    std::vector<i32> pc_j0, pc_g, pc_i0, pc_nrows, pc_r0, pc_tri0;
+    std::vector<i64> pc_user_ptr;            // npieces+1 -> users
+    std::vector<i32> pc_user_col, pc_user_s0;  // column of the wave (0-based), first source of the block it uses
+    std::vector<i64> pc_user_upd;            // its update index of source j0+s0
     // per batch: KLU_WAVE_WARPS records of KLU_REC_U32 words -- {nseg, then per matched segment (first stage row) |
     // (rows << 8) | (row of u_jk << 16)}, the destination row (uint16) of every staged row -- followed by the row -> slot
     // table (KLU_CHUNK_ROWS words) of the batch issued while this one is consumed
@@ -102,7 +112,9 @@ constexpr int KLU_CHUNK_ROWS = 128;   // L entries staged per batch (32 KiB per 
 constexpr int KLU_STAGES = 2;
 constexpr uint32_t KLU_SKIP = 0xffffffffu;
 constexpr int KLU_MAXSEG = 15;        // matched segments per (batch, column); the host closes a batch before it overflows
-constexpr int KLU_REC_U32 = 16 + KLU_CHUNK_ROWS / 2;   // per (batch, column): {nseg, segs[15]} + 64 uint16 destination rows
+constexpr int KLU_SN_MAX = 4;         // columns per source block (register-blocked update: one read-modify-write of a destination row per block)
+constexpr int KLU_REC_HDR = 32;       // {npieces, 15 x (w0, w1)} padded
+constexpr int KLU_REC_U32 = KLU_REC_HDR + KLU_CHUNK_ROWS / 2;   // per (batch, column): header + 128 uint16 destination rows
 constexpr int KLU_BLOB_BYTES = 8192;  // cap of the in-wave update blob
 constexpr long long KLU_WAVE_MAX_STAGED = 8ll << 20;   // staged rows over all waves (x ~52 B of tables): 8 M rows ~ 440 MB
 // largest dense trailing block: 112 x 116 doubles of shared memory = two CTAs of k_klu_dense_lu per SM (sweep on the B200 with
@@ -110,5 +122,9 @@ constexpr long long KLU_WAVE_MAX_STAGED = 8ll << 20;   // staged rows over all w
 // 96: 6.3 + 0.84 ms; 80: 6.7 + 0.64 ms)
 constexpr int KLU_DENSE_MAX = 112, KLU_DENSE_META = 1 + (KLU_DENSE_MAX + 31) / 32;
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan);
+// Host interpreter of the WAVE schedule (the tables k_klu_refactor_wave executes: gather, staged pieces, in-wave updates,
+// dense trailing block) for one matrix.  Verification of the host-built plan in CPU tests; not a factorization path of the
+// product.  Ax: the caller's values; out: LU[nslots] (U above diagonal, pivot, L below, then F), Rs[n].  Returns 0 or ST_SINGULAR.
+int klu_plan_emulate(const KluSymbolic& S, const KluPlan& plan, const double* Ax, double* LU, double* Rs);
 
 }  // namespace b200s
