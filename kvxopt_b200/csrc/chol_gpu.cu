@@ -86,6 +86,29 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+// TMA bulk copies (cp.async.bulk, 1-D) completing on an mbarrier: the staging path of k_update's operand tiles
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                 "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __device__ __forceinline__ int lower_bound_dev(const int* a, int n, int v) {
@@ -536,7 +559,11 @@ __device__ __forceinline__ void load_tile_async(double* dst, const double* __res
 
 // tile decode shared by host counting and the kernel: column tiles of 64, row tiles of 128, lower triangle only:
 // column tile cj pairs with row tiles ti >= cj/2
-template <bool SGN>
+// TMA = true: the operand tiles are staged by TMA bulk copies (one cp.async.bulk per tile column: 1 KB of the row block,
+// 512 B of the column block, issued by the lanes of warp 0, completion counted in bytes on one mbarrier per stage) instead of
+// 16-byte LDGSTS from all 256 threads.  Rows past the tile edge are simply not copied (they only feed accumulators that are
+// never stored); k-columns past K are zeroed by plain stores.
+template <bool SGN, bool TMA>
 __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                            int ngroups, int mode, int kb, const FrontD* __restrict__ F,
                                                            double* __restrict__ L, double* __restrict__ W,
@@ -617,24 +644,60 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
     }
 
     const int nkt = (K + BK - 1) / BK;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nkt) {
-            load_tile_async<BT, LDT>(As + s * BK * LDT, A + (long long)s * BK * ld, ld, crows, K - s * BK, tid);
-            load_tile_async<BTN, LDTB>(Bs + s * BK * LDTB, B + (long long)s * BK * ld, ld, brows, K - s * BK, tid);
+    __shared__ unsigned long long full_bar[STAGES];
+    const unsigned abytes = (unsigned)((crows + 1) & ~1) * 8u, bbytes = (unsigned)((brows + 1) & ~1) * 8u;
+    auto issue_tma = [&](int tile, int st) {
+        const int kc = min(BK, K - tile * BK);
+        if (kc < BK) {                 // k-columns beyond K: zeros (generic stores, ordered by the CTA barrier before they are read)
+            for (int idx = tid; idx < (BK - kc) * BT; idx += UPD_THREADS) As[(st * BK + kc + idx / BT) * LDT + idx % BT] = 0.0;
+            for (int idx = tid; idx < (BK - kc) * BTN; idx += UPD_THREADS) Bs[(st * BK + kc + idx / BTN) * LDTB + idx % BTN] = 0.0;
         }
-        cp_async_commit();
+        if (warp == 0) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of this stage precede the async writes
+                mbar_expect_tx(&full_bar[st], (unsigned)kc * (abytes + bbytes));
+            }
+            __syncwarp();
+            if (lane < kc) {
+                bulk_g2s(As + (st * BK + lane) * LDT, A + (long long)(tile * BK + lane) * ld, abytes, &full_bar[st]);
+                bulk_g2s(Bs + (st * BK + lane) * LDTB, B + (long long)(tile * BK + lane) * ld, bbytes, &full_bar[st]);
+            }
+        }
+    };
+    if (TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++) if (s < nkt) issue_tma(s, s);
+    } else {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++) {
+            if (s < nkt) {
+                load_tile_async<BT, LDT>(As + s * BK * LDT, A + (long long)s * BK * ld, ld, crows, K - s * BK, tid);
+                load_tile_async<BTN, LDTB>(Bs + s * BK * LDTB, B + (long long)s * BK * ld, ld, brows, K - s * BK, tid);
+            }
+            cp_async_commit();
+        }
     }
     for (int kt = 0; kt < nkt; kt++) {
-        cp_async_wait<STAGES - 2>();
+        if (TMA) mbar_wait(&full_bar[kt % STAGES], (unsigned)((kt / STAGES) & 1));
+        else cp_async_wait<STAGES - 2>();
         __syncthreads();
         const int nk = kt + STAGES - 1;
-        if (nk < nkt) {
-            const int s = nk % STAGES;
-            load_tile_async<BT, LDT>(As + s * BK * LDT, A + (long long)nk * BK * ld, ld, crows, K - nk * BK, tid);
-            load_tile_async<BTN, LDTB>(Bs + s * BK * LDTB, B + (long long)nk * BK * ld, ld, brows, K - nk * BK, tid);
+        if (TMA) {
+            if (nk < nkt) issue_tma(nk, nk % STAGES);
+        } else {
+            if (nk < nkt) {
+                const int s = nk % STAGES;
+                load_tile_async<BT, LDT>(As + s * BK * LDT, A + (long long)nk * BK * ld, ld, crows, K - nk * BK, tid);
+                load_tile_async<BTN, LDTB>(Bs + s * BK * LDTB, B + (long long)nk * BK * ld, ld, brows, K - nk * BK, tid);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         const double* as = As + (kt % STAGES) * BK * LDT;
         const double* bs = Bs + (kt % STAGES) * BK * LDTB;
         // SGN (A = L S L'): C -= A_i S A_j^T, the column signs are applied to the A_j fragment.  The sign array is padded by
@@ -661,7 +724,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
                 for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], am[i], bn[j]);
         }
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
     // epilogue: thread holds C rows (r, r+1) of one column per accumulator pair
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -1225,6 +1288,7 @@ public:
     std::vector<SolveGroups> sgroups;   // sgroups[0] = empty (use the schedule arrays)
     std::map<int, cudaGraphExec_t> solve_graphs;   // key: columns * 4 + forward * 2 + backward
     bool use_graphs = true;
+    bool upd_tma = false;          // operand tiles of k_update staged by TMA bulk copies (B200S_UPDATE_TMA=0/1 overrides the default)
     void drop_graphs() { for (auto& kv : solve_graphs) cudaGraphExecDestroy(kv.second); solve_graphs.clear(); }
     i64 solve_cols = 0;            // capacity (columns) of dT / dX
     int max_solve_ctas = 1;        // most CTAs of one backward-update launch (sizes the partial-sum buffer)
@@ -1296,6 +1360,7 @@ int CholDevice::init() {
     CUDA_TRY(cudaFree(0));
     lap("context");
     use_graphs = getenv("B200S_NO_GRAPH") == nullptr;
+    if (const char* e = getenv("B200S_UPDATE_TMA")) upd_tma = atoi(e) != 0;
     {   // the main stream carries the latency-bound panel chain: its CTAs must get the SM slots that the bulk update
         // kernels on stream2 free up, ahead of that kernel's own queued CTAs
         int prio_lo = 0, prio_hi = 0;
@@ -1528,9 +1593,11 @@ int CholDevice::init() {
     if ((rc = upload(&dsched, sched.data(), sched.size()))) return rc;
     if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
-    CUDA_TRY(cudaFuncSetAttribute(k_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_update<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_update<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
     CUDA_TRY(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
-    CUDA_TRY(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
+    CUDA_TRY(cudaFuncSetAttribute(k_update<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
     CUDA_TRY(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SDIAG));
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BDIAG));
     CUDA_TRY(cudaFuncSetAttribute(k_fwd_upd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FUPD));
@@ -1584,6 +1651,13 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
     do {                                                                                          \
         if (ldl) KERN<true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn);                    \
         else KERN<false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr);                    \
+    } while (0)
+#define LAUNCH_UPD(GRID, BLOCK, SMEM, STREAM, ...)                                                \
+    do {                                                                                          \
+        if (ldl) { if (upd_tma) k_update<true, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn);       \
+                   else k_update<true, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn); }            \
+        else { if (upd_tma) k_update<false, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr);       \
+               else k_update<false, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr); }            \
     } while (0)
 #define LAUNCH_SMALL(T, GRID, BLOCK, SMEM, STREAM, ...)                                          \
     do {                                                                                          \
@@ -1642,11 +1716,11 @@ int CholDevice::factor_level(int l) {
             const Launch& lf = LS.updF[kb];
             prof_begin(3);
             if (ln.ctas)
-                LAUNCH_SGN(k_update, ln.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                LAUNCH_UPD(ln.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(ln.sgi, 0)], dsched + ln.goff, dsched + ln.goff + ln.ng, ln.ng, 4,
                        (int)kb, dF, dL, dW, downed);
             if (lf.ctas && !lookahead)
-                LAUNCH_SGN(k_update, lf.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                LAUNCH_UPD(lf.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(lf.sgi, 0)], dsched + lf.goff, dsched + lf.goff + lf.ng, lf.ng, 5,
                        (int)kb, dF, dL, dW, downed);
             if (lf.ctas && lookahead) {
@@ -1659,12 +1733,12 @@ int CholDevice::factor_level(int l) {
                 if (lfb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));            // panels and near updates of this super-block
                 if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }
                 if (lfa.ctas)
-                    LAUNCH_SGN(k_update, lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                    LAUNCH_UPD(lfa.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(lfa.sgi, 0)], dsched + lfa.goff, dsched + lfa.goff + lfa.ng, lfa.ng, 5,
                        (int)kb, dF, dL, dW, downed);
                 if (lfb.ctas) {
                     CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-                    LAUNCH_SGN(k_update, lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2,
+                    LAUNCH_UPD(lfb.ctas, UPD_THREADS, SMEM_UPDATE, stream2,
                        sgroups[std::max(lfb.sgi, 0)], dsched + lfb.goff, dsched + lfb.goff + lfb.ng, lfb.ng, 6,
                        (int)kb, dF, dL, dW, downed);
                     CUDA_TRY(cudaEventRecord(evB, stream2));
@@ -1678,7 +1752,7 @@ int CholDevice::factor_level(int l) {
             const Launch& lu = LS.upd[kb];
             if (lu.ctas) {
                 prof_begin(3);
-                LAUNCH_SGN(k_update, lu.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                LAUNCH_UPD(lu.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(lu.sgi, 0)], dsched + lu.goff, dsched + lu.goff + lu.ng, lu.ng, 0,
                        (int)kb, dF, dL, dW, downed);
                 prof_end();
@@ -1690,12 +1764,12 @@ int CholDevice::factor_level(int l) {
         if (lb.ctas) CUDA_TRY(cudaEventRecord(evP, stream));             // panel kb is complete
         if (pendingB) { CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0)); pendingB = false; }   // part B of step kb-1
         if (la.ctas)
-            LAUNCH_SGN(k_update, la.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+            LAUNCH_UPD(la.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, 2,
                        (int)kb, dF, dL, dW, downed);
         if (lb.ctas) {
             CUDA_TRY(cudaStreamWaitEvent(stream2, evP, 0));
-            LAUNCH_SGN(k_update, lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2,
+            LAUNCH_UPD(lb.ctas, UPD_THREADS, SMEM_UPDATE, stream2,
                        sgroups[std::max(lb.sgi, 0)], dsched + lb.goff, dsched + lb.goff + lb.ng, lb.ng, 3,
                        (int)kb, dF, dL, dW, downed);
             CUDA_TRY(cudaEventRecord(evB, stream2));
@@ -1705,7 +1779,7 @@ int CholDevice::factor_level(int l) {
     if (pendingB) CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0));
     if (LS.syrk.ctas) {
         prof_begin(3);
-        LAUNCH_SGN(k_update, LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+        LAUNCH_UPD(LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
                        LS.syrk.ng, 1, 0, dF, dL, dW, downed);
         prof_end();
