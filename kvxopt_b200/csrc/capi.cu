@@ -7,18 +7,26 @@
 #include <cstring>
 #include <new>
 #include <stdexcept>
+#include <algorithm>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 using namespace b200s;
 
 struct b200s_chol {
-    CholPlan plan;
+    // The symbolic plan is immutable after analyze and may be shared by several factor objects: kvxopt re-analyses the same
+    // pattern over and over (cholmod.linsolve frees its factor at the end of every call, cholmod.c:750; misc.kkt_chol2 calls
+    // cholmod.symbolic(K) in every interior-point iteration, misc.py:1486), so analyze keeps the last few small plans keyed
+    // by (n, uplo, options, pattern, user permutation) and hands them out again after comparing the pattern itself.
+    std::shared_ptr<const CholPlan> plan_sp;
+    const CholPlan& plan() const { return *plan_sp; }
     CholOpts opts;
     CholDevice* dev = nullptr;
     int device = 0;
     CholTimes times;
     i64 minor = 0;
-    bool numeric = false, profiling = false, ldl = false;
+    bool numeric = false, profiling = false, ldl = false, custom_owned = false;
     char uplo = 'L';
     std::vector<i64> Ap, Ai;      // the pattern given to analyze: numeric() compares the caller's pattern with it (cholmod.c:322-398
                                   // rebuilds the cholmod_sparse from A's own colptr/rowind on every call)
@@ -28,6 +36,105 @@ struct b200s_chol {
 static_assert(int(B200S_OK) == ST_OK && int(B200S_NOT_POSDEF) == ST_NOT_POSDEF && int(B200S_SINGULAR) == ST_SINGULAR &&
               int(B200S_OUT_OF_MEMORY) == ST_OOM && int(B200S_TOO_LARGE) == ST_TOO_LARGE && int(B200S_INVALID) == ST_INVALID &&
               int(B200S_NO_DEVICE) == ST_NO_DEVICE && int(B200S_CUDA_ERROR) == ST_CUDA, "status codes out of sync");
+
+// ---- plan cache (see b200s_chol::plan_sp) -------------------------------------------------------------------------------
+namespace {
+struct PlanKey {
+    i64 n = 0, nnz = 0;
+    char uplo = 'L';
+    CholOpts opts;
+    bool has_perm = false;
+    unsigned long long hash = 0;
+    std::vector<i64> Ap, Ai, perm;           // the pattern itself: a hit is confirmed by comparing it, not by the hash
+    std::shared_ptr<const CholPlan> plan;
+    unsigned long long stamp = 0;
+    // device objects (uploaded plan tables, schedules, L and W storage, stream) of factor objects that were freed: the next
+    // factor object of this plan on the same GPU takes one over instead of uploading everything again
+    std::vector<std::pair<int, CholDevice*>> idle;
+    ~PlanKey() { for (auto& d : idle) chol_device_destroy(d.second); }
+    PlanKey() = default;
+    PlanKey(PlanKey&&) = default;
+    PlanKey& operator=(PlanKey&& o) {
+        if (this != &o) {
+            for (auto& d : idle) chol_device_destroy(d.second);
+            idle.clear();
+            n = o.n; nnz = o.nnz; uplo = o.uplo; opts = o.opts; has_perm = o.has_perm; hash = o.hash;
+            Ap = std::move(o.Ap); Ai = std::move(o.Ai); perm = std::move(o.perm); plan = std::move(o.plan); stamp = o.stamp;
+            idle = std::move(o.idle); o.idle.clear();
+        }
+        return *this;
+    }
+};
+constexpr size_t PLAN_CACHE_IDLE_DEVS = 2;
+constexpr i64 PLAN_CACHE_IDLE_BYTES = 256ll << 20;
+std::mutex g_plan_mu;
+std::vector<PlanKey>& g_plans = *new std::vector<PlanKey>();      // never destroyed: no CUDA calls during static destruction at exit
+unsigned long long g_plan_stamp = 0;
+constexpr size_t PLAN_CACHE_ENTRIES = 8;
+constexpr i64 PLAN_CACHE_MAX_NNZ = 4 << 20;  // only patterns whose copy is cheap to keep (the 100^3 case re-analyses)
+
+unsigned long long fnv(const void* p, size_t bytes, unsigned long long h) {
+    const unsigned long long* w = (const unsigned long long*)p;
+    for (size_t i = 0; i < bytes / 8; i++) { h ^= w[i]; h *= 1099511628211ull; }
+    return h;
+}
+bool same_opts(const CholOpts& a, const CholOpts& b) {
+    return a.supernodal == b.supernodal && a.nmethods == b.nmethods && a.postorder == b.postorder && a.ordering == b.ordering &&
+           a.dbound == b.dbound && a.block == b.block && !memcmp(a.nrelax, b.nrelax, sizeof a.nrelax) && !memcmp(a.zrelax, b.zrelax, sizeof a.zrelax);
+}
+bool plan_cache_enabled() { static const bool on = getenv("B200S_NO_PLAN_CACHE") == nullptr; return on; }
+unsigned long long pattern_hash(i64 n, const b200s_int* cp, const b200s_int* ri, const b200s_int* perm) {
+    unsigned long long h = 1469598103934665603ull;
+    h = fnv(cp, sizeof(i64) * (size_t)(n + 1), h);
+    h = fnv(ri, sizeof(i64) * (size_t)cp[n], h);
+    if (perm) h = fnv(perm, sizeof(i64) * (size_t)n, h);
+    return h;
+}
+std::shared_ptr<const CholPlan> plan_cache_lookup(i64 n, const b200s_int* cp, const b200s_int* ri, char uplo, const b200s_int* perm,
+                                                  const CholOpts& o) {
+    if (!plan_cache_enabled() || n <= 0 || cp[n] > PLAN_CACHE_MAX_NNZ) return nullptr;
+    const unsigned long long h = pattern_hash(n, cp, ri, perm);
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    for (PlanKey& k : g_plans)
+        if (k.hash == h && k.n == n && k.nnz == cp[n] && k.uplo == uplo && k.has_perm == (perm != nullptr) && same_opts(k.opts, o) &&
+            !memcmp(k.Ap.data(), cp, sizeof(i64) * (size_t)(n + 1)) && !memcmp(k.Ai.data(), ri, sizeof(i64) * (size_t)cp[n]) &&
+            (!perm || !memcmp(k.perm.data(), perm, sizeof(i64) * (size_t)n))) {
+            k.stamp = ++g_plan_stamp;
+            return k.plan;
+        }
+    return nullptr;
+}
+void plan_cache_store(i64 n, const b200s_int* cp, const b200s_int* ri, char uplo, const b200s_int* perm, const CholOpts& o,
+                      const std::shared_ptr<const CholPlan>& plan) {
+    if (!plan_cache_enabled() || n <= 0 || cp[n] > PLAN_CACHE_MAX_NNZ) return;
+    PlanKey k;
+    k.n = n; k.nnz = cp[n]; k.uplo = uplo; k.opts = o; k.has_perm = perm != nullptr; k.hash = pattern_hash(n, cp, ri, perm);
+    k.Ap.assign(cp, cp + n + 1); k.Ai.assign(ri, ri + cp[n]);
+    if (perm) k.perm.assign(perm, perm + n);
+    k.plan = plan;
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    k.stamp = ++g_plan_stamp;
+    if (g_plans.size() < PLAN_CACHE_ENTRIES) { g_plans.push_back(std::move(k)); return; }
+    size_t old = 0;
+    for (size_t i = 1; i < g_plans.size(); i++) if (g_plans[i].stamp < g_plans[old].stamp) old = i;
+    g_plans[old] = std::move(k);
+}
+CholDevice* plan_cache_take_device(const CholPlan* plan, int device) {
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    for (PlanKey& k : g_plans)
+        if (k.plan.get() == plan)
+            for (size_t i = 0; i < k.idle.size(); i++)
+                if (k.idle[i].first == device) { CholDevice* d = k.idle[i].second; k.idle.erase(k.idle.begin() + i); return d; }
+    return nullptr;
+}
+bool plan_cache_park_device(const CholPlan* plan, int device, CholDevice* d) {
+    if ((plan->lsize + plan->wsize) * 8 > PLAN_CACHE_IDLE_BYTES) return false;
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    for (PlanKey& k : g_plans)
+        if (k.plan.get() == plan && k.idle.size() < PLAN_CACHE_IDLE_DEVS) { k.idle.emplace_back(device, d); return true; }
+    return false;
+}
+}  // namespace
 
 extern "C" {
 
@@ -89,7 +196,14 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
     F->device = current_device();
     try {
         static const b200s_int zero = 0;
-        chol_analyze(n, n > 0 ? colptr : &zero, rowind, uplo, perm, F->opts, F->plan);
+        std::shared_ptr<const CholPlan> cached = plan_cache_lookup(n, colptr, rowind, uplo, perm, F->opts);
+        if (cached) F->plan_sp = cached;
+        else {
+            auto fresh = std::make_shared<CholPlan>();
+            chol_analyze(n, n > 0 ? colptr : &zero, rowind, uplo, perm, F->opts, *fresh);
+            F->plan_sp = fresh;
+            plan_cache_store(n, colptr, rowind, uplo, perm, F->opts, F->plan_sp);
+        }
     } catch (const std::bad_alloc&) {
         delete F;
         return B200S_OUT_OF_MEMORY;
@@ -114,7 +228,8 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
 static b200s_status ensure_device(b200s_chol* F) {
     if (!F->dev) {
         int st = ST_OK;
-        F->dev = chol_device_create(F->plan, F->opts, F->device, &st);
+        F->dev = plan_cache_take_device(F->plan_sp.get(), F->device);
+        if (!F->dev) F->dev = chol_device_create(F->plan(), F->opts, F->device, &st);
         if (!F->dev) return (b200s_status)st;
         chol_device_set_profiling(F->dev, F->profiling);
         chol_device_set_ldl(F->dev, F->ldl);
@@ -126,10 +241,10 @@ static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_dev
     B200S_NVTX("factorize_impl");
     if (!F) return B200S_INVALID;
     F->numeric = false;
-    if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
-    if (!val && F->plan.nnzA > 0) return B200S_INVALID;
+    if (F->plan().n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
+    if (!val && F->plan().nnzA > 0) return B200S_INVALID;
     { b200s_status es = ensure_device(F); if (es != B200S_OK) return es; }
-    i64 minor = F->plan.n;
+    i64 minor = F->plan().n;
     int st = chol_device_factorize(F->dev, val, on_device, &minor, &F->times);
     F->minor = minor;
     if (minor_out) *minor_out = minor;
@@ -140,8 +255,8 @@ static b200s_status factorize_impl(b200s_chol* F, const double* val, bool on_dev
 // analysed pattern that A does not have become zero (CHOLMOD accepts a subset pattern); an entry of A inside the
 // referenced triangle that the analysis has not seen is an error.  Row indices must be sorted within each column.
 static b200s_status remap_values(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val) {
-    const i64 n = F->plan.n;
-    try { F->remap.assign((size_t)F->plan.nnzA, 0.0); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    const i64 n = F->plan().n;
+    try { F->remap.assign((size_t)F->plan().nnzA, 0.0); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
     if (colptr[0] != 0) return B200S_INVALID;
     for (i64 j = 0; j < n; j++) {
         i64 q = F->Ap[j];
@@ -162,8 +277,8 @@ static b200s_status remap_values(b200s_chol* F, const b200s_int* colptr, const b
 }
 b200s_status b200s_chol_factorize(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val,
                                   b200s_int* minor_out) {
-    if (F && colptr && F->plan.n > 0) {
-        const i64 n = F->plan.n, nnz = F->plan.nnzA;
+    if (F && colptr && F->plan().n > 0) {
+        const i64 n = F->plan().n, nnz = F->plan().nnzA;
         const bool same = colptr[n] == nnz && memcmp(colptr, F->Ap.data(), sizeof(i64) * (size_t)(n + 1)) == 0 &&
                           (nnz == 0 || (rowind && memcmp(rowind, F->Ai.data(), sizeof(i64) * (size_t)nnz) == 0));
         if (!same) {
@@ -183,21 +298,22 @@ b200s_status b200s_chol_factorize_dev(b200s_chol* F, const double* val_dev, b200
 // ---- level-stepped factorization and front ownership (multi-GPU subtree-to-subcube building blocks) ----------
 b200s_status b200s_chol_set_owned(b200s_chol* F, const unsigned char* owned) {
     if (!F) return B200S_INVALID;
-    if (F->plan.n == 0) return B200S_OK;
+    if (F->plan().n == 0) return B200S_OK;
     if (F->ldl && owned) {   // the pivot signs of fronts factored elsewhere are not exchanged: one GPU per factor in LDL' mode
         set_last_error("front ownership (subtree-to-subcube) is not available with supernodal = 0 (LDL')");
         return B200S_INVALID;
     }
     b200s_status es = ensure_device(F);
     if (es != B200S_OK) return es;
+    F->custom_owned = true;
     return (b200s_status)chol_device_set_owned(F->dev, owned);
 }
 b200s_status b200s_chol_factor_begin(b200s_chol* F, const double* val, int val_on_device) {
     B200S_NVTX("b200s_chol_factor_begin");
     if (!F) return B200S_INVALID;
     F->numeric = false;
-    if (F->plan.n == 0) return B200S_OK;
-    if (!val && F->plan.nnzA > 0) return B200S_INVALID;
+    if (F->plan().n == 0) return B200S_OK;
+    if (!val && F->plan().nnzA > 0) return B200S_INVALID;
     b200s_status es = ensure_device(F);
     if (es != B200S_OK) return es;
     return (b200s_status)chol_device_factor_begin(F->dev, val, val_on_device != 0);
@@ -210,9 +326,9 @@ b200s_status b200s_chol_factor_level(b200s_chol* F, b200s_int level) {
 b200s_status b200s_chol_factor_end(b200s_chol* F, b200s_int* minor_out) {
     B200S_NVTX("b200s_chol_factor_end");
     if (!F) return B200S_INVALID;
-    if (F->plan.n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
+    if (F->plan().n == 0) { F->numeric = true; if (minor_out) *minor_out = 0; return B200S_OK; }
     if (!F->dev) return B200S_INVALID;
-    i64 minor = F->plan.n;
+    i64 minor = F->plan().n;
     int st = chol_device_factor_end(F->dev, &minor, &F->times);
     F->minor = minor;
     if (minor_out) *minor_out = minor;
@@ -227,7 +343,7 @@ b200s_status b200s_chol_sync(b200s_chol* F) {
 b200s_status b200s_chol_front_layout(const b200s_chol* F, b200s_int* parent, b200s_int* level, b200s_int* ncols, b200s_int* nrows,
                                      b200s_int* loff, b200s_int* lsize, b200s_int* uoff, b200s_int* usize) {
     if (!F) return B200S_INVALID;
-    const CholPlan& P = F->plan;
+    const CholPlan& P = F->plan();
     for (size_t s = 0; s < P.fronts.size(); s++) {
         const Front& f = P.fronts[s];
         const i64 m = f.nr - f.nc, mu = m + (f.nc & 1), ldu = (mu + 1) & ~(i64)1;
@@ -260,8 +376,8 @@ b200s_status b200s_chol_set_numeric(b200s_chol* F, int numeric, b200s_int minor)
 static b200s_status solve_impl(b200s_chol* F, int sys, double* B, b200s_int nrhs, b200s_int ldB, bool on_device) {
     B200S_NVTX("solve_impl");
     if (!F || sys < 0 || sys > 8 || nrhs < 0) return B200S_INVALID;
-    if (F->plan.n == 0 || nrhs == 0) return B200S_OK;
-    if (!B || ldB < F->plan.n) return B200S_INVALID;
+    if (F->plan().n == 0 || nrhs == 0) return B200S_OK;
+    if (!B || ldB < F->plan().n) return B200S_INVALID;
     if (!F->numeric || !F->dev) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
     return (b200s_status)chol_device_solve(F->dev, sys, B, nrhs, ldB, on_device, &F->times);
 }
@@ -275,36 +391,48 @@ b200s_status b200s_chol_solve_dev(b200s_chol* F, int sys, double* B_dev, b200s_i
 b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_int ncols, const b200s_int* Bp,
                                 const b200s_int* Bi, const double* Bx, b200s_int** Xp, b200s_int** Xi, double** Xx) {
     B200S_NVTX("b200s_chol_spsolve");
-    if (!F || !Xp || !Xi || !Xx || nrows != F->plan.n || ncols < 0) return B200S_INVALID;
+    if (!F || !Xp || !Xi || !Xx || nrows != F->plan().n || ncols < 0) return B200S_INVALID;
     *Xp = nullptr; *Xi = nullptr; *Xx = nullptr;
     const i64 n = nrows;
-    // sparse right-hand sides are expanded column by column; the device solve runs on dense blocks
-    std::vector<double> dense;
-    try { dense.assign((size_t)n * (size_t)ncols, 0.0); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
-    for (i64 j = 0; j < ncols; j++)
-        for (i64 k = Bp[j]; k < Bp[j + 1]; k++) {
-            if (Bi[k] < 0 || Bi[k] >= n) return B200S_INVALID;
-            dense[(size_t)j * n + Bi[k]] = Bx[k];
-        }
-    if (n > 0 && ncols > 0) {
-        b200s_status st = solve_impl(F, sys, dense.data(), ncols, n, false);
-        if (st != B200S_OK) return st;
+    const CholPlan& P = F->plan();
+    for (i64 j = 0; j < ncols; j++) {
+        if (Bp[j + 1] < Bp[j]) return B200S_INVALID;
+        for (i64 k = Bp[j]; k < Bp[j + 1]; k++)
+            if (Bi[k] < 0 || Bi[k] >= n || (k > Bp[j] && Bi[k] <= Bi[k - 1])) { set_last_error("spsolve: row indices of B must be sorted and in range"); return B200S_INVALID; }
     }
-    i64 nnz = 0;
-    for (double v : dense) if (v != 0.0) nnz++;
+    std::vector<i64> vp, vi;
+    std::vector<double> vx;
+    try {
+        if (n > 0 && ncols > 0 && (!F->numeric || !F->dev)) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
+        if (sys == 7 || sys == 8 || (sys == 6 && !F->ldl)) {
+            // x = P b, x = P' b (and D = I for LL'): a permutation of the stored entries, done where they are
+            vp.assign((size_t)ncols + 1, 0);
+            std::vector<std::pair<i64, double>> col;
+            for (i64 j = 0; j < ncols; j++) {
+                col.clear();
+                for (i64 k = Bp[j]; k < Bp[j + 1]; k++) {
+                    if (Bx[k] == 0.0) continue;                 // the result holds the numerically nonzero entries
+                    const i64 r = sys == 7 ? P.iperm[Bi[k]] : (sys == 8 ? P.perm[Bi[k]] : Bi[k]);
+                    col.emplace_back(r, Bx[k]);
+                }
+                std::sort(col.begin(), col.end());
+                for (auto& e : col) { vi.push_back(e.first); vx.push_back(e.second); }
+                vp[j + 1] = (i64)vi.size();
+            }
+        } else {
+            // structure-aware device solve: sparse upload, forward sweep restricted to the elimination-tree reach of the
+            // nonzero rows, numerically nonzero entries compacted on the device (chol_gpu.cu, CholDevice::spsolve)
+            int st = chol_device_spsolve(F->dev, sys, ncols, Bp, Bi, Bx, vp, vi, vx, &F->times);
+            if (st != ST_OK) return (b200s_status)st;
+        }
+    } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    const i64 nnz = (i64)vi.size();
     b200s_int* xp = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)(ncols + 1));
     b200s_int* xi = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)std::max<i64>(nnz, 1));
     double* xx = (double*)malloc(sizeof(double) * (size_t)std::max<i64>(nnz, 1));
     if (!xp || !xi || !xx) { free(xp); free(xi); free(xx); return B200S_OUT_OF_MEMORY; }
-    i64 p = 0;
-    xp[0] = 0;
-    for (i64 j = 0; j < ncols; j++) {
-        for (i64 i = 0; i < n; i++) {
-            double v = dense[(size_t)j * n + i];
-            if (v != 0.0) { xi[p] = i; xx[p] = v; p++; }
-        }
-        xp[j + 1] = p;
-    }
+    for (i64 j = 0; j <= ncols; j++) xp[j] = vp[j];
+    for (i64 k = 0; k < nnz; k++) { xi[k] = vi[k]; xx[k] = vx[k]; }
     *Xp = xp; *Xi = xi; *Xx = xx;
     return B200S_OK;
 }
@@ -312,7 +440,7 @@ b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_i
 b200s_status b200s_chol_diag(b200s_chol* F, double* d_out) {
     B200S_NVTX("b200s_chol_diag");
     if (!F) return B200S_INVALID;
-    if (F->plan.n == 0) return B200S_OK;
+    if (F->plan().n == 0) return B200S_OK;
     if (!d_out) return B200S_INVALID;
     if (!F->numeric || !F->dev) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
     if (F->ldl) { set_last_error("F must be a nonsingular supernodal Cholesky factor"); return B200S_INVALID; }    /* cholmod.c:919-922 */
@@ -323,7 +451,7 @@ b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, dou
     B200S_NVTX("b200s_chol_get_L");
     if (!F || !Lp || !Li || !Lx) return B200S_INVALID;
     *Lp = nullptr; *Li = nullptr; *Lx = nullptr;
-    const CholPlan& P = F->plan;
+    const CholPlan& P = F->plan();
     const i64 n = P.n;
     if (n > 0 && (!F->numeric || !F->dev)) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
     std::vector<double> raw;
@@ -370,7 +498,7 @@ b200s_status b200s_chol_get_L(b200s_chol* F, b200s_int** Lp, b200s_int** Li, dou
 
 b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info) {
     if (!F || !info) return B200S_INVALID;
-    const CholPlan& P = F->plan;
+    const CholPlan& P = F->plan();
     memset(info, 0, sizeof *info);
     info->n = P.n; info->nsuper = (b200s_int)P.fronts.size(); info->nnz_L = P.nnzL; info->nnz_A = P.nnzA;
     info->nlevels = P.nlevels; info->max_front_rows = P.max_nr; info->max_front_cols = P.max_nc;
@@ -391,13 +519,13 @@ b200s_status b200s_chol_set_profiling(b200s_chol* F, int on) {
     return B200S_OK;
 }
 b200s_status b200s_chol_get_perm(const b200s_chol* F, b200s_int* perm_out) {
-    if (!F || (!perm_out && F->plan.n > 0)) return B200S_INVALID;
-    for (i32 k = 0; k < F->plan.n; k++) perm_out[k] = F->plan.perm[k];
+    if (!F || (!perm_out && F->plan().n > 0)) return B200S_INVALID;
+    for (i32 k = 0; k < F->plan().n; k++) perm_out[k] = F->plan().perm[k];
     return B200S_OK;
 }
 b200s_status b200s_chol_get_super(const b200s_chol* F, b200s_int* super_out, b200s_int* rowptr_out, b200s_int* rows_out) {
     if (!F) return B200S_INVALID;
-    const CholPlan& P = F->plan;
+    const CholPlan& P = F->plan();
     const size_t ns = P.fronts.size();
     for (size_t s = 0; s < ns; s++) {
         if (super_out) super_out[s] = P.fronts[s].col0;
@@ -410,7 +538,11 @@ b200s_status b200s_chol_get_super(const b200s_chol* F, b200s_int* super_out, b20
 }
 void b200s_chol_free(b200s_chol* F) {
     if (!F) return;
-    if (F->dev) chol_device_destroy(F->dev);
+    if (F->dev) {
+        chol_device_sync(F->dev);
+        // an object whose front ownership was changed (multi-GPU driver) is not handed on
+        if (F->custom_owned || !plan_cache_park_device(F->plan_sp.get(), F->device, F->dev)) chol_device_destroy(F->dev);
+    }
     delete F;
 }
 void b200s_free(void* p) { free(p); }

@@ -1282,6 +1282,7 @@ public:
     FrontD* dF = nullptr;
     int *drows = nullptr, *drel = nullptr, *dchild = nullptr, *dperm = nullptr, *dlevel_fronts = nullptr;
     int *dsched = nullptr, *dminor = nullptr;
+    std::vector<int> hsched;
     double* ddiag = nullptr;       // scratch for factored diagonal blocks of one panel launch
     EAItem* dea = nullptr;
     std::vector<LevelSched> levels;
@@ -1314,6 +1315,8 @@ public:
         pool_free(dL); pool_free(dW); pool_free(dval); pool_free(dT); pool_free(dX); pool_free(dBstage); pool_free(damap); pool_free(dF);
         pool_free(drows); pool_free(drel); pool_free(dchild); pool_free(dperm); pool_free(dlevel_fronts);
         pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(ddiag); pool_free(dpart); pool_free(downed);
+        pool_free(dreach); pool_free(dsp_i); pool_free(dsp_x); pool_free(dsp_cnt); pool_free(dsp_oi); pool_free(dsp_ox); pool_free(dsp_meta);
+        for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
@@ -1335,7 +1338,15 @@ public:
     int factor_level(int l);
     int factor_end(i64* minor, CholTimes* times);
     int set_owned(const unsigned char* owned_host);
-    int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false);
+    int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false,
+              const unsigned char* active_fronts = nullptr);
+    // sparse right-hand sides: reach-restricted forward sweep, sparse upload, compacted download (cholmod.spsolve)
+    int spsolve(int sys, i64 ncols, const i64* Bp, const i64* Bi, const double* Bx, std::vector<i64>& Xp, std::vector<i64>& Xi,
+                std::vector<double>& Xx, CholTimes* times);
+    int* dreach = nullptr; i64 reach_cap = 0;        // filtered per-level lists of small fronts (reach of the current right-hand sides)
+    i64 *dsp_i = nullptr, *dsp_meta = nullptr; double* dsp_x = nullptr; int* dsp_cnt = nullptr; i64 sp_cap = 0, spout_cap = 0, spmeta_cap = 0;
+    cudaEvent_t ev_sp[2] = {nullptr, nullptr};
+    i64* dsp_oi = nullptr; double* dsp_ox = nullptr;
     bool ldl = false;             // LDL' semantics of sys 2..6 (supernodal = 0)
     double* ddiagL = nullptr;     // diagonal of L (permuted order), valid while diagL_valid
     double* dsgn = nullptr;       // ldl: sign of every pivot (+-1, permuted order, padded), written by the factorization kernels
@@ -1415,7 +1426,7 @@ int CholDevice::init() {
 
     lap("cudaMalloc L/W/val");
     // ---- schedule
-    std::vector<int> sched;          // group arrays: [front ids...][prefix...]
+    std::vector<int>& sched = hsched;  // group arrays: [front ids...][prefix...] (host copy kept: the reach-restricted solve filters it)
     std::vector<EAItem> ea;
     levels.resize(P.nlevels);
     sgroups.assign(1, SolveGroups());
@@ -1849,7 +1860,7 @@ int CholDevice::ensure_solve_ws(i64 cols) {
     return ST_OK;
 }
 
-int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async) {
+int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async, const unsigned char* active_fronts) {
     const CholPlan& P = *plan;
     const int n = P.n;
     if (n == 0 || nrhs == 0) return ST_OK;
@@ -1896,6 +1907,31 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                do_bwd = (sys == 0 || sys == 1 || sys == 3 || sys == 5 || sys == 10);
     const int gx = std::min((n + 255) / 256, 148 * 8);
     const i64 tstride = (i64)P.rows.size();
+    // Reach-restricted forward sweep (sparse right-hand sides): only the fronts on the elimination-tree paths
+    // from the nonzero rows to the root can carry nonzeros of L^-1 b.  The small fronts (the bulk of the tree) run from
+    // per-level lists filtered on the host; the work vectors are zeroed first so that a skipped child contributes zeros to
+    // its parent; the few large fronts near the root are all on some path and run as usual.
+    std::vector<int> reach_off, reach_cnt;
+    if (active_fronts && do_fwd) {
+        std::vector<int> lists;
+        reach_off.assign(P.nlevels, 0); reach_cnt.assign(P.nlevels, 0);
+        for (int l = 0; l < P.nlevels; l++) {
+            const LevelSched& LS = levels[l];
+            reach_off[l] = (int)lists.size();
+            for (int q = 0; q < LS.small_all_cnt; q++) {
+                const int f = hsched[LS.small_all_off + q];
+                if (active_fronts[f]) lists.push_back(f);
+            }
+            reach_cnt[l] = (int)lists.size() - reach_off[l];
+        }
+        if ((i64)lists.size() > reach_cap) {
+            pool_free(dreach); dreach = nullptr; reach_cap = 0;
+            CUDA_TRY(pool_malloc((void**)&dreach, std::max<size_t>(lists.size(), 1) * sizeof(int)));
+            reach_cap = (i64)lists.size();
+        }
+        if (!lists.empty()) CUDA_TRY(cudaMemcpyAsync(dreach, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));       // `lists` is a local: the copy must have left it
+    }
     for (i64 j0 = 0; j0 < nrhs; j0 += chunk) {
         const int nc = (int)std::min<i64>(chunk, nrhs - j0);
         double* b = dB + j0 * ldd;
@@ -1919,11 +1955,16 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         const long long pstride = (long long)max_solve_ctas * NB;
         // the level sweeps are a fixed launch sequence (hundreds of short dependent kernels): captured once per
         // (columns, directions) into a CUDA graph and replayed
+        const bool reach = active_fronts && do_fwd;
+        if (reach) CUDA_TRY(cudaMemsetAsync(dT, 0, (size_t)tstride * nc * sizeof(double), stream));
         auto sweeps = [&]() {
         if (do_fwd)
                 for (int l = 0; l < P.nlevels; l++) {
                     const LevelSched& LS = levels[l];
-                    if (LS.small_all_cnt)
+                    if (reach) {
+                        if (reach_cnt[l])
+                            k_fwd<<<dim3(reach_cnt[l], nc), 256, 0, stream>>>(dreach + reach_off[l], dF, dchild, drel, dL, dT, tstride, dX, n);
+                    } else if (LS.small_all_cnt)
                         k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
@@ -1955,7 +1996,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                 }
         };
         const int gkey = nc * 8 + (ldl ? 4 : 0) + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
-        if (!use_graphs) sweeps();
+        if (!use_graphs || reach) sweeps();      // the filtered lists change from call to call: not captured
         else {
             auto it = solve_graphs.find(gkey);
             if (it == solve_graphs.end()) {
@@ -1987,6 +2028,142 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     return ST_OK;
 }
 
+// ---- sparse right-hand sides (cholmod.spsolve, reference src/C/cholmod.c:524-587) ------------------------------------
+// dense block B (n x nc, zeroed) <- the nonzeros of nc sparse columns: cp[c]..cp[c+1] index (ri, vx)
+__global__ void k_sp_scatter(const i64* __restrict__ cp, const i64* __restrict__ ri, const double* __restrict__ vx, int nc,
+                             long long n, double* __restrict__ B) {
+    const int c = blockIdx.y;
+    for (long long p = cp[c] + blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cp[c + 1]; p += (long long)gridDim.x * blockDim.x)
+        B[(long long)c * n + ri[p]] = vx[p];
+}
+// numerically nonzero entries per column
+__global__ void __launch_bounds__(256) k_sp_count(const double* __restrict__ B, long long n, int* __restrict__ cnt) {
+    __shared__ int red[256];
+    const double* b = B + (long long)blockIdx.x * n;
+    int c = 0;
+    for (long long i = threadIdx.x; i < n; i += 256) c += b[i] != 0.0;
+    red[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) cnt[blockIdx.x] = red[0];
+}
+// ordered compaction of column blockIdx.x into (oi, ox) starting at off[blockIdx.x]: tiles of 1024 rows, ballot + warp-sum scan
+__global__ void __launch_bounds__(1024) k_sp_compact(const double* __restrict__ B, long long n, const i64* __restrict__ off,
+                                                     i64* __restrict__ oi, double* __restrict__ ox) {
+    __shared__ int wsum[32];
+    __shared__ long long base;
+    const double* b = B + (long long)blockIdx.x * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = off[blockIdx.x];
+    __syncthreads();
+    for (long long i0 = 0; i0 < n; i0 += 1024) {
+        const long long i = i0 + threadIdx.x;
+        const double v = i < n ? b[i] : 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0.0);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; w++) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
+        if (v != 0.0) {
+            const long long d = base + before + __popc(m & ((1u << lane) - 1u));
+            oi[d] = i; ox[d] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+}
+
+int CholDevice::spsolve(int sys, i64 ncols, const i64* Bp, const i64* Bi, const double* Bx, std::vector<i64>& Xp, std::vector<i64>& Xi,
+                        std::vector<double>& Xx, CholTimes* times) {
+    const CholPlan& P = *plan;
+    const i64 n = P.n;
+    Xp.assign((size_t)ncols + 1, 0); Xi.clear(); Xx.clear();
+    if (n == 0 || ncols == 0) return ST_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    const i64 maxcols = std::max<i64>(1, std::min<i64>(ncols, (i64)(256ll << 20) / std::max<i64>(1, (i64)P.rows.size() * 8)));
+    int rc = ensure_solve_ws(std::min<i64>(maxcols, 64));
+    if (rc) return rc;
+    const i64 chunk = solve_cols;
+    // the systems whose forward sweep starts from b itself (4: L x = b; 2: LD x = b) or from P b (0, 1 have the backward sweep too)
+    const bool fwd = sys == 0 || sys == 1 || sys == 2 || sys == 4, perm_in = sys == 0;
+    const size_t nf = P.fronts.size();
+    std::vector<unsigned char> active(nf);
+    std::vector<i64> cpl((size_t)chunk + 1), offs((size_t)chunk);
+    std::vector<int> cnt((size_t)chunk);
+    float ms_acc = 0.f;
+    for (i64 j0 = 0; j0 < ncols; j0 += chunk) {
+        const int nc = (int)std::min<i64>(chunk, ncols - j0);
+        const i64 e0 = Bp[j0], ne = Bp[j0 + nc] - e0;
+        // reach of the chunk: fronts on the tree paths from its nonzero rows (permuted for the systems that start with P b)
+        if (fwd) {
+            std::fill(active.begin(), active.end(), 0);
+            for (i64 p = e0; p < e0 + ne; p++) {
+                const i64 r = perm_in ? P.iperm[Bi[p]] : Bi[p];
+                for (i32 f = P.sn_of_col[r]; f >= 0 && !active[f]; f = P.fronts[f].parent) active[f] = 1;
+            }
+        }
+        if (ne > sp_cap || !dsp_i) {
+            pool_free(dsp_i); pool_free(dsp_x); dsp_i = nullptr; dsp_x = nullptr; sp_cap = 0;
+            CUDA_TRY(pool_malloc((void**)&dsp_i, (size_t)std::max<i64>(ne, 1) * sizeof(i64)));
+            CUDA_TRY(pool_malloc((void**)&dsp_x, (size_t)std::max<i64>(ne, 1) * sizeof(double)));
+            sp_cap = std::max<i64>(ne, 1);
+        }
+        if (2 * chunk + 2 > spmeta_cap) {
+            pool_free(dsp_meta); pool_free(dsp_cnt); dsp_meta = nullptr; dsp_cnt = nullptr; spmeta_cap = 0;
+            CUDA_TRY(pool_malloc((void**)&dsp_meta, (size_t)(2 * chunk + 2) * sizeof(i64)));
+            CUDA_TRY(pool_malloc((void**)&dsp_cnt, (size_t)chunk * sizeof(int)));
+            spmeta_cap = 2 * chunk + 2;
+        }
+        if ((i64)n * nc > bstage_cap) {
+            pool_free(dBstage); dBstage = nullptr; bstage_cap = 0;
+            CUDA_TRY(pool_malloc((void**)&dBstage, (size_t)n * chunk * sizeof(double)));
+            bstage_cap = (i64)n * chunk;
+        }
+        i64* d_cp = dsp_meta;                  // chunk column pointers (relative to the chunk's first entry)
+        i64* d_off = dsp_meta + chunk + 1;     // output offsets of the chunk's columns
+        for (auto& e : ev_sp) if (!e) CUDA_TRY(cudaEventCreate(&e));
+        for (int c = 0; c <= nc; c++) cpl[c] = Bp[j0 + c] - e0;
+        cudaEvent_t e_a = ev_sp[0], e_b = ev_sp[1];
+        CUDA_TRY(cudaEventRecord(e_a, stream));
+        CUDA_TRY(cudaMemsetAsync(dBstage, 0, (size_t)n * nc * sizeof(double), stream));
+        if (ne) {
+            CUDA_TRY(cudaMemcpyAsync(dsp_i, Bi + e0, (size_t)ne * sizeof(i64), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(dsp_x, Bx + e0, (size_t)ne * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_cp, cpl.data(), (size_t)(nc + 1) * sizeof(i64), cudaMemcpyHostToDevice, stream));
+        if (ne) k_sp_scatter<<<dim3(8, nc), 256, 0, stream>>>(d_cp, dsp_i, dsp_x, nc, n, dBstage);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(stream));       // cpl is reused by the next chunk
+        rc = solve(sys, dBstage, nc, n, true, nullptr, true, fwd ? active.data() : nullptr);
+        if (rc) return rc;
+        k_sp_count<<<nc, 256, 0, stream>>>(dBstage, n, dsp_cnt);
+        CUDA_TRY(cudaMemcpyAsync(cnt.data(), dsp_cnt, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        i64 tot = 0;
+        for (int c = 0; c < nc; c++) { offs[c] = tot; tot += cnt[c]; Xp[j0 + c + 1] = Xp[j0 + c] + cnt[c]; }
+        if (tot > spout_cap) {
+            pool_free(dsp_oi); pool_free(dsp_ox); dsp_oi = nullptr; dsp_ox = nullptr; spout_cap = 0;
+            CUDA_TRY(pool_malloc((void**)&dsp_oi, (size_t)tot * sizeof(i64)));
+            CUDA_TRY(pool_malloc((void**)&dsp_ox, (size_t)tot * sizeof(double)));
+            spout_cap = tot;
+        }
+        if (tot) {
+            CUDA_TRY(cudaMemcpyAsync(d_off, offs.data(), (size_t)nc * sizeof(i64), cudaMemcpyHostToDevice, stream));
+            k_sp_compact<<<nc, 1024, 0, stream>>>(dBstage, n, d_off, dsp_oi, dsp_ox);
+            const size_t old = Xi.size();
+            Xi.resize(old + (size_t)tot); Xx.resize(old + (size_t)tot);
+            CUDA_TRY(cudaMemcpyAsync(Xi.data() + old, dsp_oi, (size_t)tot * sizeof(i64), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(Xx.data() + old, dsp_ox, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        }
+        CUDA_TRY(cudaEventRecord(e_b, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        float ms; cudaEventElapsedTime(&ms, e_a, e_b); ms_acc += ms;
+    }
+    if (times) times->ms_solve = ms_acc;
+    return ST_OK;
+}
+
 CholDevice* chol_device_create(const CholPlan& plan, const CholOpts& opts, int device, int* status) {
     if (device_count() <= 0) { *status = ST_NO_DEVICE; set_last_error("no CUDA device available"); return nullptr; }
     CholDevice* d = new CholDevice();
@@ -2003,6 +2180,10 @@ int chol_device_factorize(CholDevice* d, const double* val, bool val_on_device, 
 }
 int chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times) {
     return d->solve(sys, B, nrhs, ldB, on_device, times, false);
+}
+int chol_device_spsolve(CholDevice* d, int sys, i64 ncols, const i64* Bp, const i64* Bi, const double* Bx, std::vector<i64>& Xp,
+                        std::vector<i64>& Xi, std::vector<double>& Xx, CholTimes* times) {
+    return d->spsolve(sys, ncols, Bp, Bi, Bx, Xp, Xi, Xx, times);
 }
 int chol_device_solve_async(CholDevice* d, int sys, double* B_dev, i64 nrhs, i64 ldB) {
     return d->solve(sys, B_dev, nrhs, ldB, true, nullptr, true);

@@ -2,6 +2,7 @@
 #pragma once
 #include "host.hpp"
 #include <string>
+#include <vector>
 
 namespace b200s {
 
@@ -27,6 +28,10 @@ int  chol_device_factorize(CholDevice* d, const double* val, bool val_on_device,
 int  chol_device_solve(CholDevice* d, int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times);
 // device-resident right-hand sides on the handle's stream, no synchronisation; sys 9 = L x = P b, 10 = x = P' L^-T b
 int  chol_device_solve_async(CholDevice* d, int sys, double* B_dev, i64 nrhs, i64 ldB);
+// sparse right-hand sides (n x ncols CCS, sorted rows): structure-aware solve -- sparse upload, forward sweep restricted to the
+// elimination-tree reach of the nonzero rows, numerically nonzero entries compacted on the device and downloaded as CCS
+int  chol_device_spsolve(CholDevice* d, int sys, i64 ncols, const i64* Bp, const i64* Bi, const double* Bx, std::vector<i64>& Xp,
+                         std::vector<i64>& Xi, std::vector<double>& Xx, CholTimes* times);
 void* chol_device_stream(CholDevice* d);      // cudaStream_t
 int  chol_device_diag(CholDevice* d, double* diag_host);
 int  chol_device_download_L(CholDevice* d, double* L_host);   // raw panel storage, plan.lsize doubles

