@@ -98,6 +98,20 @@ b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_i
                                 const b200s_int* Bp, const b200s_int* Bi, const double* Bx,
                                 b200s_int** Xp, b200s_int** Xi, double** Xx);
 
+/* ---- complex Hermitian matrices ('z' spmatrix, src/C/cholmod.c:144,153,343-357: CHOLMOD_COMPLEX) -------------------------
+ * Factored through the real symmetric embedding a + ib -> [[a, -b], [b, a]] of order 2n (rows/columns 2i, 2i+1 per complex
+ * index i, pairs kept adjacent by the ordering), whose Cholesky factor is the embedding of the complex factor.  Values are
+ * (re, im) pairs as a kvxopt 'z' matrix stores them.  A complex dense right-hand side IS its real embedding: solve it with
+ * b200s_chol_solve(F, sys, (double*)B, nrhs, 2*ldB).  Same status codes; *minor is a complex column index. */
+b200s_status b200s_chol_analyze_z(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, char uplo, const b200s_int* perm,
+                                  const b200s_chol_opts* opts, b200s_chol** out);
+b200s_status b200s_chol_factorize_z(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                    b200s_int* minor_out);
+b200s_status b200s_chol_spsolve_z(b200s_chol* F, int sys, b200s_int nrows, b200s_int ncols, const b200s_int* Bp,
+                                  const b200s_int* Bi, const double* Bx, b200s_int** Xp, b200s_int** Xi, double** Xx);
+b200s_status b200s_chol_diag_z(b200s_chol* F, double* d_out);      /* n (re, im) pairs, im = 0 */
+b200s_status b200s_chol_get_L_z(b200s_chol* F, b200s_int** Lp, b200s_int** Li, double** Lx);
+
 /* cholmod.diag (src/C/cholmod.c:900-945): the n diagonal entries of L, in factor (permuted) order. */
 b200s_status b200s_chol_diag(b200s_chol* F, double* d_out);
 
@@ -118,6 +132,7 @@ typedef struct {
     double    ms_dense_update; /* device time inside the SYRK/GEMM update kernels of the last factorize */
     double    ms_potrf, ms_trsm, ms_extend;
     double    flops_update;   /* flops executed by the tiled DMMA update kernel (numerator of its roofline) */
+    b200s_int zn;             /* complex order for factor objects made by b200s_chol_analyze_z (then n = 2 zn), else 0 */
 } b200s_chol_info_t;
 b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info);
 /* when on, factorize records per-kernel-class CUDA events (adds launch gaps; for profiling only) */

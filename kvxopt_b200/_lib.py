@@ -54,6 +54,11 @@ SIGNATURES = {
     "b200s_chol_spsolve": (C.c_int, vp, C.c_int, i64, i64, p_i64, p_i64, p_f64,
                            C.POINTER(p_i64), C.POINTER(p_i64), C.POINTER(p_f64)),
     "b200s_chol_diag": (C.c_int, vp, p_f64),
+    "b200s_chol_analyze_z": (C.c_int, i64, p_i64, p_i64, C.c_char, p_i64, C.POINTER(CholOpts), C.POINTER(vp)),
+    "b200s_chol_factorize_z": (C.c_int, vp, p_i64, p_i64, p_f64, p_i64),
+    "b200s_chol_spsolve_z": (C.c_int, vp, C.c_int, i64, i64, p_i64, p_i64, p_f64, C.POINTER(p_i64), C.POINTER(p_i64), C.POINTER(p_f64)),
+    "b200s_chol_diag_z": (C.c_int, vp, p_f64),
+    "b200s_chol_get_L_z": (C.c_int, vp, C.POINTER(p_i64), C.POINTER(p_i64), C.POINTER(p_f64)),
     "b200s_chol_get_L": (C.c_int, vp, C.POINTER(p_i64), C.POINTER(p_i64), C.POINTER(p_f64)),
     "b200s_chol_info": (C.c_int, vp, C.POINTER(CholInfo)),
     "b200s_chol_set_profiling": (C.c_int, vp, C.c_int),

@@ -14,7 +14,8 @@ class CholInfo(C.Structure):
                [(k, C.c_double) for k in ("flops", "flops_potrf", "flops_trsm", "flops_syrk")] + \
                [("is_numeric", C.c_int), ("minor", i64)] + \
                [(k, C.c_double) for k in ("ms_h2d", "ms_assemble", "ms_factor", "ms_total", "ms_solve", "ms_analyze",
-                                          "ms_dense_update", "ms_potrf", "ms_trsm", "ms_extend", "flops_update")]
+                                          "ms_dense_update", "ms_potrf", "ms_trsm", "ms_extend", "flops_update")] + \
+               [("zn", i64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -51,6 +51,7 @@ def _capsule_destructor(capsule_addr):        # kvxopt_free_cholmod_factor, chol
         ptr = _raw_GetPointer(capsule_addr, name)
         if ptr:
             _FAMILY.pop(ptr, None)
+            _ZFLAG.pop(ptr, None)
             fn["b200s_chol_free"](ptr)
     except Exception:   # never raise from a destructor
         pass
@@ -116,10 +117,12 @@ def _size(A):
 
 
 def _ccs(A):
-    """(colptr int64, rowind int64, values float64) of a sparse matrix without changing its pattern"""
+    """(colptr int64, rowind int64, values float64) of a sparse matrix without changing its pattern; the values of a complex
+    ('z') matrix come back as interleaved (re, im) pairs, 2 nnz doubles"""
+    vt = np.complex128 if _typecode(A) == "z" else np.float64
     if _is_kvx(A):
         cp, ri, vx = A.CCS        # fresh copies owned by these matrix objects: viewed, not copied again
-        return (_flat_view(cp, np.int64), _flat_view(ri, np.int64), _flat_view(vx, np.float64))
+        return (_flat_view(cp, np.int64), _flat_view(ri, np.int64), _flat_view(vx, vt).view(np.float64))
     import scipy.sparse as sp
     if not sp.isspmatrix_csc(A) and not (hasattr(sp, "csc_array") and isinstance(A, sp.csc_array)):
         A = A.tocsc()
@@ -127,7 +130,7 @@ def _ccs(A):
         A = A.copy()
         A.sort_indices()
     return (np.ascontiguousarray(A.indptr, dtype=np.int64), np.ascontiguousarray(A.indices, dtype=np.int64),
-            np.ascontiguousarray(A.data, dtype=np.float64))
+            np.ascontiguousarray(A.data, dtype=vt).view(np.float64))
 
 
 def _flat_view(m, dtype):
@@ -151,8 +154,8 @@ def _values(A):
     return np.ascontiguousarray(A.data, dtype=np.float64)
 
 
-def _dense_view(B):
-    """flat column-major float64 view that shares memory with B, plus (nrows, ncols)"""
+def _dense_view(B, z=False):
+    """flat column-major view that shares memory with B, plus (nrows, ncols); float64, or complex128 with z=True"""
     if _is_kvx(B):
         a = np.asarray(memoryview(B))
         nrows, ncols = B.size
@@ -162,7 +165,7 @@ def _dense_view(B):
             nrows, ncols = a.shape[0], 1
         else:
             nrows, ncols = a.shape
-    if a.dtype != np.float64:
+    if a.dtype != (np.complex128 if z else np.float64):
         raise TypeError("B must a dense matrix of the same numerical type as F")
     if a.ndim == 1:
         if not a.flags.c_contiguous:
@@ -187,22 +190,22 @@ def _kv_module(like):
     return None
 
 
-def _make_spmatrix(like, values, rowind, colptr, size):
+def _make_spmatrix(like, values, rowind, colptr, size, tc="d"):
     kv = _kv_module(like)
     if kv is not None:
         cols = np.repeat(np.arange(size[1], dtype=np.int64), np.diff(colptr))
-        return kv.spmatrix(kv.matrix(values, (len(values), 1), "d") if len(values) else [],
+        return kv.spmatrix(kv.matrix(values, (len(values), 1), tc) if len(values) else [],
                            kv.matrix(rowind, (len(rowind), 1), "i") if len(rowind) else [],
-                           kv.matrix(cols, (len(cols), 1), "i") if len(cols) else [], size, "d")
+                           kv.matrix(cols, (len(cols), 1), "i") if len(cols) else [], size, tc)
     import scipy.sparse as sp
     return sp.csc_matrix((values, rowind, colptr), shape=size)
 
 
-def _make_matrix(like, values, size):
+def _make_matrix(like, values, size, tc="d"):
     kv = _kv_module(like)
     if kv is not None:
-        return kv.matrix(values, size, "d")
-    return np.asarray(values, dtype=np.float64).reshape(size, order="F")
+        return kv.matrix(values, size, tc)
+    return np.asarray(values, dtype=np.complex128 if tc == "z" else np.float64).reshape(size, order="F")
 
 
 def _factor_handle(F, want_typecode=None):
@@ -213,9 +216,17 @@ def _factor_handle(F, want_typecode=None):
         raise TypeError("F is not a Capsule")
     if name not in (_NAME_L, _NAME_U, _NAME_ZL, _NAME_ZU):
         raise TypeError("F is not a CHOLMOD factor")
-    if name in (_NAME_ZL, _NAME_ZU):
-        raise TypeError("complex factors are not supported by the B200 engine")
-    return _py.PyCapsule_GetPointer(F, name), ("L" if name == _NAME_L else "U")
+    return _py.PyCapsule_GetPointer(F, name), ("L" if name in (_NAME_L, _NAME_ZL) else "U")
+
+
+def _is_z(h):
+    """complex factor object (made by b200s_chol_analyze_z: Hermitian matrix factored through its real embedding)"""
+    return _info(h).zn > 0 or _ZFLAG.get(h if isinstance(h, int) else h.value, False)
+
+
+def _order(inf):
+    """order of the matrix as the caller sees it (complex order for 'z' factors)"""
+    return inf.zn if inf.zn > 0 else inf.n
 
 
 def _info(h):
@@ -227,8 +238,8 @@ def _info(h):
 def _analyze(A, p, uplo, o):
     if not _is_spmatrix(A) or _size(A)[0] != _size(A)[1]:
         raise TypeError("A is not a square sparse matrix")
-    if _typecode(A) == "z":
-        raise TypeError("complex matrices are not supported by the B200 engine")
+    if _typecode(A) not in ("d", "z"):
+        raise TypeError("A is not a square sparse matrix")
     n = _size(A)[0]
     perm = None
     if p is not None:
@@ -249,15 +260,20 @@ def _analyze(A, p, uplo, o):
         raise ValueError("possible values of uplo are: 'L', 'U'")
     cp, ri, vx = _ccs(A)
     h = C.c_void_p()
-    st = fn["b200s_chol_analyze"](n, L.ptr_i64(cp), L.ptr_i64(ri), uplo.encode(), L.ptr_i64(perm), C.byref(o), C.byref(h))
+    z = _typecode(A) == "z"
+    st = fn["b200s_chol_analyze_z" if z else "b200s_chol_analyze"](n, L.ptr_i64(cp), L.ptr_i64(ri), uplo.encode(),
+                                                                   L.ptr_i64(perm), C.byref(o), C.byref(h))
     if st != L.OK:
         _raise_status(st, "symbolic factorization failed")
+    if z:
+        _ZFLAG[h.value] = True      # also marks complex factors of order 0 (zn = 0 there)
     return h, vx
 
 
 def _factorize(h, vx, cp=None, ri=None):
     minor = C.c_int64(0)
-    st = fn["b200s_chol_factorize"](h, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(minor))
+    st = fn["b200s_chol_factorize_z" if _is_z(h) else "b200s_chol_factorize"](h, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx),
+                                                                              C.byref(minor))
     if st == L.NOT_POSDEF:
         raise ArithmeticError(int(minor.value))
     if st != L.OK:
@@ -269,6 +285,8 @@ def symbolic(A, p=None, uplo="L"):
     o = _set_options()
     h, _ = _analyze(A, p, uplo, o)
     _FAMILY[h.value] = type(A).__module__.split(".")[0] if _is_kvx(A) else None   # family diag()/getfactor() return
+    if _typecode(A) == "z":         # cholmod.c:286-290: the capsule name carries the numerical type
+        return _py.PyCapsule_New(h, _NAME_ZL if uplo == "L" else _NAME_ZU, C.cast(_capsule_destructor, C.c_void_p))
     return _py.PyCapsule_New(h, _NAME_L if uplo == "L" else _NAME_U, C.cast(_capsule_destructor, C.c_void_p))
 
 
@@ -279,10 +297,10 @@ def numeric(A, F):
     if not _is_spmatrix(A) or _size(A)[0] != _size(A)[1]:
         raise TypeError("A is not a sparse matrix")
     h, uplo = _factor_handle(F)
-    if _typecode(A) != "d":
+    if _typecode(A) != ("z" if _is_z(h) else "d"):      # cholmod.c:343-357
         raise TypeError("F is not the CHOLMOD factor of a '%s' matrix" % _typecode(A))
     inf = _info(h)
-    if _size(A)[0] != inf.n:
+    if _size(A)[0] != _order(inf):
         raise ValueError("factorization failed")
     # A's own pattern travels with the values (cholmod.c:340-358 rebuilds the cholmod_sparse from A on every call): the
     # library compares it with the analysed pattern and re-maps the values when A stores a subset of it
@@ -300,9 +318,10 @@ def _check_numeric(h):
 
 
 def _solve_dense(h, n, B, sys, nrhs, ldB, offsetB):
-    if not _is_dense(B) or _typecode(B) != "d":
+    z = _is_z(h)
+    if not _is_dense(B) or _typecode(B) != ("z" if z else "d"):      # cholmod.c:460-464
         raise TypeError("B must a dense matrix of the same numerical type as F")
-    flat, nrows, ncols = _dense_view(B)
+    flat, nrows, ncols = _dense_view(B, z)
     if nrhs < 0:
         nrhs = ncols
     if n == 0 or nrhs == 0:
@@ -315,8 +334,12 @@ def _solve_dense(h, n, B, sys, nrhs, ldB, offsetB):
         raise ValueError("offsetB must be a nonnegative integer")
     if offsetB + (nrhs - 1) * ldB + n > flat.size:
         raise TypeError("length of B is too small")
-    sub = flat[offsetB:]
-    st = fn["b200s_chol_solve"](h, sys, L.ptr_f64(sub), nrhs, ldB)
+    if z:       # a complex vector IS its real embedding: (re, im) pairs, 2n real unknowns per column
+        sub = flat[offsetB:].view(np.float64)
+        st = fn["b200s_chol_solve"](h, sys, L.ptr_f64(sub), nrhs, 2 * ldB)
+    else:
+        sub = flat[offsetB:]
+        st = fn["b200s_chol_solve"](h, sys, L.ptr_f64(sub), nrhs, ldB)
     if st != L.OK:
         _raise_status(st, "solve step failed")
 
@@ -328,26 +351,30 @@ def solve(F, B, sys=0, nrhs=-1, ldB=0, offsetB=0):
     inf = _check_numeric(h)
     if sys < 0 or sys > 8:
         raise ValueError("invalid value for sys")
-    _solve_dense(h, inf.n, B, sys, nrhs, ldB, offsetB)
+    _solve_dense(h, _order(inf), B, sys, nrhs, ldB, offsetB)
 
 
 def _spsolve(h, n, B, sys):
-    if not _is_spmatrix(B) or _typecode(B) == "z":
+    z = _is_z(h)
+    if not _is_spmatrix(B) or _typecode(B) != ("z" if z else "d"):   # cholmod.c:557-561
         raise TypeError("B must a sparse matrix of the same numerical type as F")
     if _size(B)[0] != n:
         raise ValueError("incompatible dimensions for B")
     bp, bi, bx = _ccs(B)
     ncols = _size(B)[1]
     xp, xi, xx = L.p_i64(), L.p_i64(), L.p_f64()
-    st = fn["b200s_chol_spsolve"](h, sys, n, ncols, L.ptr_i64(bp), L.ptr_i64(bi), L.ptr_f64(bx),
-                                  C.byref(xp), C.byref(xi), C.byref(xx))
+    st = fn["b200s_chol_spsolve_z" if z else "b200s_chol_spsolve"](h, sys, n, ncols, L.ptr_i64(bp), L.ptr_i64(bi), L.ptr_f64(bx),
+                                                                   C.byref(xp), C.byref(xi), C.byref(xx))
     if st != L.OK:
         _raise_status(st, "solve step failed")
     colptr = L.take_array(xp, ncols + 1, np.int64)
     nnz = int(colptr[-1])
     rowind = L.take_array(xi, max(nnz, 1), np.int64)[:nnz]
-    values = L.take_array(xx, max(nnz, 1), np.float64)[:nnz]
-    return _make_spmatrix(B, values, rowind, colptr, (n, ncols))
+    if z:
+        values = L.take_array(xx, 2 * max(nnz, 1), np.float64)[:2 * nnz].view(np.complex128)
+    else:
+        values = L.take_array(xx, max(nnz, 1), np.float64)[:nnz]
+    return _make_spmatrix(B, values, rowind, colptr, (n, ncols), "z" if z else "d")
 
 
 def spsolve(F, B, sys=0):
@@ -357,7 +384,7 @@ def spsolve(F, B, sys=0):
     inf = _check_numeric(h)
     if sys < 0 or sys > 8:
         raise ValueError("invalid value for sys")
-    return _spsolve(h, inf.n, B, sys)
+    return _spsolve(h, _order(inf), B, sys)
 
 
 def linsolve(A, B, p=None, uplo="L", nrhs=-1, ldB=0, offsetB=0):
@@ -368,7 +395,7 @@ def linsolve(A, B, p=None, uplo="L", nrhs=-1, ldB=0, offsetB=0):
     n = _size(A)[0]
     if not _is_dense(B) or _typecode(B) != _typecode(A):
         raise TypeError("B must be a dense matrix of the same numerical type as A")
-    flat, nrows, ncols = _dense_view(B)
+    flat, nrows, ncols = _dense_view(B, _typecode(A) == "z")
     nr = ncols if nrhs < 0 else nrhs
     if n == 0 or nr == 0:
         return
@@ -384,6 +411,7 @@ def linsolve(A, B, p=None, uplo="L", nrhs=-1, ldB=0, offsetB=0):
         _factorize(h, vx)
         _solve_dense(h, n, B, 0, nrhs, ldB, offsetB)
     finally:
+        _ZFLAG.pop(h.value, None)
         fn["b200s_chol_free"](h)
 
 
@@ -402,6 +430,7 @@ def splinsolve(A, B, p=None, uplo="L"):
         _factorize(h, vx)
         return _spsolve(h, n, B, 0)
     finally:
+        _ZFLAG.pop(h.value, None)
         fn["b200s_chol_free"](h)
 
 
@@ -412,13 +441,17 @@ def diag(F):
     inf = _info(h)
     if not inf.is_numeric and inf.n > 0:
         raise ValueError("F must be a numeric Cholesky factor")
-    d = np.zeros(inf.n, dtype=np.float64)
-    st = fn["b200s_chol_diag"](h, L.ptr_f64(d))
+    z = _is_z(h)
+    n = _order(inf)
+    d = np.zeros(2 * n if z else n, dtype=np.float64)
+    st = fn["b200s_chol_diag_z" if z else "b200s_chol_diag"](h, L.ptr_f64(d))
     if st == L.INVALID:       # LDL' semantics (options['supernodal'] = 0): cholmod.c:919-922
         raise ValueError("F must be a nonsingular supernodal Cholesky factor")
     if st != L.OK:
         _raise_status(st, "diag failed")
-    return _make_matrix(_FAMILY.get(h), d, (inf.n, 1))
+    if z:                     # cholmod.c:923-924: a 'z' matrix for complex factors
+        return _make_matrix(_FAMILY.get(h), d.view(np.complex128), (n, 1), "z")
+    return _make_matrix(_FAMILY.get(h), d, (n, 1))
 
 
 def getfactor(F):
@@ -429,19 +462,25 @@ def getfactor(F):
     if not inf.is_numeric and inf.n > 0:
         raise ValueError("F must be a numeric Cholesky factor")
     lp, li, lx = L.p_i64(), L.p_i64(), L.p_f64()
-    st = fn["b200s_chol_get_L"](h, C.byref(lp), C.byref(li), C.byref(lx))
+    z = _is_z(h)
+    n = _order(inf)
+    st = fn["b200s_chol_get_L_z" if z else "b200s_chol_get_L"](h, C.byref(lp), C.byref(li), C.byref(lx))
     if st != L.OK:
         _raise_status(st, "getfactor failed")
-    colptr = L.take_array(lp, inf.n + 1, np.int64)
-    nnz = int(colptr[-1]) if inf.n else 0
+    colptr = L.take_array(lp, n + 1, np.int64)
+    nnz = int(colptr[-1]) if n else 0
     rowind = L.take_array(li, max(nnz, 1), np.int64)[:nnz]
-    values = L.take_array(lx, max(nnz, 1), np.float64)[:nnz]
-    return _make_spmatrix(_FAMILY.get(h), values, rowind, colptr, (inf.n, inf.n))
+    if z:
+        values = L.take_array(lx, 2 * max(nnz, 1), np.float64)[:2 * nnz].view(np.complex128)
+    else:
+        values = L.take_array(lx, max(nnz, 1), np.float64)[:nnz]
+    return _make_spmatrix(_FAMILY.get(h), values, rowind, colptr, (n, n), "z" if z else "d")
 
 
 # diag/getfactor have no matrix argument: they return the container family (kvxopt or scipy/numpy) of the
 # matrix that was given to symbolic().  Keyed by factor handle, cleared by the capsule destructor.
 _FAMILY = {}
+_ZFLAG = {}        # handles of complex factor objects (covers order 0, where the library's zn is 0 as well)
 
 
 def factor_info(F):
@@ -453,9 +492,10 @@ def factor_info(F):
 def factor_perm(F):
     """extension: the fill-reducing permutation held by F (L->Perm)"""
     h, _ = _factor_handle(F)
-    p = np.zeros(_info(h).n, dtype=np.int64)
+    inf = _info(h)
+    p = np.zeros(inf.n, dtype=np.int64)
     fn["b200s_chol_get_perm"](h, L.ptr_i64(p))
-    return p
+    return p[::2] // 2 if inf.zn > 0 else p      # complex factors: the pair ordering (2k, 2k+1) back to complex indices
 
 
 def install(kvxopt_module=None):

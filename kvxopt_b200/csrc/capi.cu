@@ -31,6 +31,13 @@ struct b200s_chol {
     std::vector<i64> Ap, Ai;      // the pattern given to analyze: numeric() compares the caller's pattern with it (cholmod.c:322-398
                                   // rebuilds the cholmod_sparse from A's own colptr/rowind on every call)
     std::vector<double> remap;    // scratch of the slow path (pattern differs: values re-mapped through A's own indices)
+    // complex Hermitian matrices (b200s_chol_*_z): factored through the real symmetric embedding a + ib -> [[a, -b], [b, a]] of
+    // order 2 zn, rows/columns (2i, 2i+1) per complex index i
+    i64 zn = 0;                   // complex order (0: real factor object)
+    std::vector<i64> zAp, zAi;    // the complex pattern given to analyze_z
+    std::vector<i64> zsrc;        // per entry of the embedded pattern: complex entry it comes from (-1: structural zero)
+    std::vector<signed char> zcode;   // 0: real part, 1: imaginary part, 2: minus the imaginary part
+    std::vector<double> zval;     // embedded values (scratch of factorize_z)
 };
 
 static_assert(int(B200S_OK) == ST_OK && int(B200S_NOT_POSDEF) == ST_NOT_POSDEF && int(B200S_SINGULAR) == ST_SINGULAR &&
@@ -437,6 +444,200 @@ b200s_status b200s_chol_spsolve(b200s_chol* F, int sys, b200s_int nrows, b200s_i
     return B200S_OK;
 }
 
+// ---- complex Hermitian matrices through the real symmetric embedding ---------------------------------------------------
+// z = a + ib  ->  [[a, -b], [b, a]]: a *-homomorphism, so the Cholesky factor of the embedded matrix (pairs (2i, 2i+1) kept
+// adjacent and in this order by the elimination ordering) IS the embedding of the complex Cholesky factor: L_r = emb(L_c),
+// with a real positive diagonal.  Complex vectors embed as interleaved (re, im) pairs -- exactly the memory layout of a
+// kvxopt 'z' matrix -- so solves run on the caller's buffer as 2n real unknowns.
+b200s_status b200s_chol_analyze_z(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, char uplo, const b200s_int* perm,
+                                  const b200s_chol_opts* opts, b200s_chol** out) {
+    B200S_NVTX("b200s_chol_analyze_z");
+    if (!out) return B200S_INVALID;
+    *out = nullptr;
+    if (n < 0 || (n > 0 && (!colptr || (colptr[n] > 0 && !rowind))) || (uplo != 'L' && uplo != 'U') || n > 0x3ffffff0) return B200S_INVALID;
+    try {
+        // ordering of the complex pattern (user permutation, or AMD as for real matrices), expanded to pairs
+        std::vector<i64> p1((size_t)n), p2((size_t)2 * n);
+        if (perm) {
+            std::vector<char> seen((size_t)n, 0);
+            for (i64 k = 0; k < n; k++) {
+                if (perm[k] < 0 || perm[k] >= n || seen[perm[k]]) { set_last_error("invalid permutation"); return B200S_INVALID; }
+                seen[perm[k]] = 1; p1[k] = perm[k];
+            }
+        } else if (opts && opts->ordering == 1) {
+            for (i64 k = 0; k < n; k++) p1[k] = k;
+        } else {
+            std::vector<i32> a = amd_order(sym_pattern_from_triangle(n, colptr, rowind, uplo));
+            for (i64 k = 0; k < n; k++) p1[k] = a[k];
+        }
+        for (i64 k = 0; k < n; k++) { p2[2 * k] = 2 * p1[k]; p2[2 * k + 1] = 2 * p1[k] + 1; }
+        // embedded pattern of the referenced triangle; the diagonal pair always has its three slots (the off-diagonal one of
+        // the pair is a structural zero: it makes 2j the only child of 2j+1 in the elimination tree, so any postorder keeps
+        // the pair adjacent and the two columns fall into one supernode)
+        std::vector<i64> ecp((size_t)2 * n + 1, 0), eri, zsrc;
+        std::vector<signed char> zc;
+        auto push = [&](i64 r, i64 src, int code) { eri.push_back(r); zsrc.push_back(src); zc.push_back((signed char)code); };
+        for (i64 j = 0; j < n; j++) {
+            i64 dsrc = -1;
+            for (i64 k = colptr[j]; k < colptr[j + 1]; k++) {
+                if (rowind[k] < 0 || rowind[k] >= n || (k > colptr[j] && rowind[k] <= rowind[k - 1])) { set_last_error("row indices must be sorted and in range"); return B200S_INVALID; }
+                if (rowind[k] == j) dsrc = k;
+            }
+            for (int half = 0; half < 2; half++) {          // embedded columns 2j and 2j+1
+                if (uplo == 'U') {
+                    for (i64 k = colptr[j]; k < colptr[j + 1] && rowind[k] < j; k++) {
+                        push(2 * rowind[k], k, half == 0 ? 0 : 2);
+                        push(2 * rowind[k] + 1, k, half == 0 ? 1 : 0);
+                    }
+                    if (half == 0) push(2 * j, dsrc, 0);
+                    else { push(2 * j, -1, 0); push(2 * j + 1, dsrc, 0); }
+                } else {
+                    if (half == 0) { push(2 * j, dsrc, 0); push(2 * j + 1, -1, 0); }
+                    else push(2 * j + 1, dsrc, 0);
+                    for (i64 k = colptr[j]; k < colptr[j + 1]; k++) {
+                        if (rowind[k] <= j) continue;
+                        push(2 * rowind[k], k, half == 0 ? 0 : 2);
+                        push(2 * rowind[k] + 1, k, half == 0 ? 1 : 0);
+                    }
+                }
+                ecp[2 * j + half + 1] = (i64)eri.size();
+            }
+        }
+        b200s_chol_opts o2;
+        if (opts) o2 = *opts; else b200s_chol_default_opts(&o2);
+        o2.nmethods = 1;
+        b200s_chol* F = nullptr;
+        b200s_status st = b200s_chol_analyze(2 * n, ecp.data(), eri.data(), uplo, n > 0 ? p2.data() : nullptr, &o2, &F);
+        if (st != B200S_OK) return st;
+        for (i64 k = 0; k < n; k++)
+            if ((F->plan().perm[2 * k] & 1) || F->plan().perm[2 * k + 1] != F->plan().perm[2 * k] + 1) {
+                set_last_error("analyze_z: the ordering separated a (re, im) pair");
+                b200s_chol_free(F);
+                return B200S_INVALID;
+            }
+        F->zn = n;
+        if (n > 0) { F->zAp.assign(colptr, colptr + n + 1); F->zAi.assign(rowind, rowind + colptr[n]); }
+        F->zsrc = std::move(zsrc); F->zcode = std::move(zc);
+        *out = F;
+        return B200S_OK;
+    } catch (const std::bad_alloc&) {
+        return B200S_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return B200S_INVALID;
+    }
+}
+
+/* val: nnz complex numbers as (re, im) pairs, the values of the SAME (colptr, rowind) given to analyze_z; imaginary parts of
+ * the diagonal are ignored (Hermitian).  *minor_out is a complex column index. */
+b200s_status b200s_chol_factorize_z(b200s_chol* F, const b200s_int* colptr, const b200s_int* rowind, const double* val, b200s_int* minor_out) {
+    if (!F) return B200S_INVALID;
+    const i64 n = F->zn;
+    if (F->plan().n == 0) return factorize_impl(F, nullptr, false, minor_out);
+    if (n == 0) { set_last_error("factorize_z on a real factor object"); return B200S_INVALID; }
+    if (!val) return B200S_INVALID;
+    if (colptr) {
+        const i64 nnz = F->zAp[n];
+        if (colptr[n] != nnz || memcmp(colptr, F->zAp.data(), sizeof(i64) * (size_t)(n + 1)) ||
+            (nnz > 0 && (!rowind || memcmp(rowind, F->zAi.data(), sizeof(i64) * (size_t)nnz)))) {
+            set_last_error("numeric: the pattern of a complex matrix must be the one analysed by symbolic()");
+            return B200S_INVALID;
+        }
+    }
+    try { F->zval.resize(F->zsrc.size()); } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    for (size_t e = 0; e < F->zsrc.size(); e++) {
+        const i64 k = F->zsrc[e];
+        F->zval[e] = k < 0 ? 0.0 : (F->zcode[e] == 0 ? val[2 * k] : (F->zcode[e] == 1 ? val[2 * k + 1] : -val[2 * k + 1]));
+    }
+    b200s_int m = 0;
+    b200s_status st = factorize_impl(F, F->zval.data(), false, &m);
+    if (minor_out) *minor_out = m / 2;
+    return st;
+}
+
+/* sparse complex right-hand sides: n x ncols CCS with (re, im) values; result likewise (library-allocated, b200s_free) */
+b200s_status b200s_chol_spsolve_z(b200s_chol* F, int sys, b200s_int nrows, b200s_int ncols, const b200s_int* Bp, const b200s_int* Bi,
+                                  const double* Bx, b200s_int** Xp, b200s_int** Xi, double** Xx) {
+    if (!F || !Xp || !Xi || !Xx || nrows != F->zn || ncols < 0) return B200S_INVALID;
+    *Xp = nullptr; *Xi = nullptr; *Xx = nullptr;
+    std::vector<i64> rp((size_t)ncols + 1, 0), ri;
+    std::vector<double> rx;
+    try {
+        for (i64 j = 0; j < ncols; j++) {
+            for (i64 k = Bp[j]; k < Bp[j + 1]; k++) {
+                ri.push_back(2 * Bi[k]); rx.push_back(Bx[2 * k]);
+                ri.push_back(2 * Bi[k] + 1); rx.push_back(Bx[2 * k + 1]);
+            }
+            rp[j + 1] = (i64)ri.size();
+        }
+    } catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+    static const i64 dummy_i = 0; static const double dummy_x = 0.0;
+    b200s_int *xp = nullptr, *xi = nullptr;
+    double* xx = nullptr;
+    b200s_status st = b200s_chol_spsolve(F, sys, 2 * nrows, ncols, rp.data(), ri.empty() ? &dummy_i : ri.data(), rx.empty() ? &dummy_x : rx.data(), &xp, &xi, &xx);
+    if (st != B200S_OK) return st;
+    // pairs (2i, 2i+1) -> one complex entry
+    const i64 rn = xp[ncols];
+    b200s_int* zp = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)(ncols + 1));
+    b200s_int* zi = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)std::max<i64>(rn, 1));
+    double* zx = (double*)malloc(sizeof(double) * 2 * (size_t)std::max<i64>(rn, 1));
+    if (!zp || !zi || !zx) { free(zp); free(zi); free(zx); free(xp); free(xi); free(xx); return B200S_OUT_OF_MEMORY; }
+    i64 q = 0;
+    zp[0] = 0;
+    for (i64 j = 0; j < ncols; j++) {
+        for (i64 k = xp[j]; k < xp[j + 1]; k++) {
+            const i64 i = xi[k] >> 1;
+            if (q > zp[j] && zi[q - 1] == i) { zx[2 * (q - 1) + (xi[k] & 1)] = xx[k]; continue; }
+            zi[q] = i; zx[2 * q] = 0.0; zx[2 * q + 1] = 0.0; zx[2 * q + (xi[k] & 1)] = xx[k]; q++;
+        }
+        zp[j + 1] = q;
+    }
+    free(xp); free(xi); free(xx);
+    *Xp = zp; *Xi = zi; *Xx = zx;
+    return B200S_OK;
+}
+
+/* diagonal of the complex Cholesky factor as n (re, im) pairs (real and positive: im = 0) */
+b200s_status b200s_chol_diag_z(b200s_chol* F, double* d_out) {
+    if (!F || !d_out) return B200S_INVALID;
+    const i64 n = F->zn;
+    std::vector<double> d((size_t)2 * n + 1);
+    b200s_status st = b200s_chol_diag(F, d.data());
+    if (st != B200S_OK) return st;
+    for (i64 k = 0; k < n; k++) { d_out[2 * k] = d[2 * k]; d_out[2 * k + 1] = 0.0; }
+    return B200S_OK;
+}
+
+/* the complex factor as CCS with (re, im) values (cholmod.getfactor of a 'z' factor) */
+b200s_status b200s_chol_get_L_z(b200s_chol* F, b200s_int** Lp, b200s_int** Li, double** Lx) {
+    if (!F || !Lp || !Li || !Lx) return B200S_INVALID;
+    *Lp = nullptr; *Li = nullptr; *Lx = nullptr;
+    const i64 n = F->zn;
+    b200s_int *rp = nullptr, *ri = nullptr;
+    double* rx = nullptr;
+    b200s_status st = b200s_chol_get_L(F, &rp, &ri, &rx);
+    if (st != B200S_OK) return st;
+    i64 nnz = 0;
+    for (i64 j = 0; j < n; j++) nnz += rp[2 * j + 1] - rp[2 * j];
+    b200s_int* zp = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)(n + 1));
+    b200s_int* zi = (b200s_int*)malloc(sizeof(b200s_int) * (size_t)std::max<i64>(nnz, 1));
+    double* zx = (double*)malloc(sizeof(double) * 2 * (size_t)std::max<i64>(nnz, 1));
+    if (!zp || !zi || !zx) { free(zp); free(zi); free(zx); free(rp); free(ri); free(rx); return B200S_OUT_OF_MEMORY; }
+    i64 q = 0;
+    zp[0] = 0;
+    for (i64 j = 0; j < n; j++) {
+        for (i64 k = rp[2 * j]; k < rp[2 * j + 1]; k++) {          // embedded column 2j: rows 2i carry re(l_ij), rows 2i+1 im(l_ij)
+            const i64 i = ri[k] >> 1;
+            if (q > zp[j] && zi[q - 1] == i) { zx[2 * (q - 1) + (ri[k] & 1)] = rx[k]; continue; }
+            zi[q] = i; zx[2 * q] = 0.0; zx[2 * q + 1] = 0.0; zx[2 * q + (ri[k] & 1)] = rx[k]; q++;
+        }
+        zp[j + 1] = q;
+    }
+    free(rp); free(ri); free(rx);
+    *Lp = zp; *Li = zi; *Lx = zx;
+    return B200S_OK;
+}
+
 b200s_status b200s_chol_diag(b200s_chol* F, double* d_out) {
     B200S_NVTX("b200s_chol_diag");
     if (!F) return B200S_INVALID;
@@ -510,6 +711,7 @@ b200s_status b200s_chol_info(const b200s_chol* F, b200s_chol_info_t* info) {
     info->ms_dense_update = F->times.ms_dense_update; info->ms_potrf = F->times.ms_potrf;
     info->ms_trsm = F->times.ms_trsm; info->ms_extend = F->times.ms_extend;
     info->flops_update = P.flops_update;
+    info->zn = F->zn;
     return B200S_OK;
 }
 b200s_status b200s_chol_set_profiling(b200s_chol* F, int on) {
