@@ -263,6 +263,8 @@ typedef struct {
     /* wave schedule of the fast kernel (klu_gpu.cu): statistics */
     b200s_int nwaves, nwaves_with_deps, nbatches, nsegments, staged_rows;
     b200s_int npieces, npiece_users;     /* staged source blocks (<= 4 columns of one L supernode) x row pieces; (piece, user column) pairs */
+    b200s_int wave_ok;                   /* 0: pattern outside the wave kernel's budget (the level-schedule kernel factors it) */
+    b200s_int nearly, nearly_levels;     /* columns factored level by level before the waves (k_klu_early) and their levels */
 } b200s_klu_plan_view_t;
 b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* view);
 /* Replays the wave-schedule tables of the plan on the HOST for one matrix with the values `val` and returns the factor in the

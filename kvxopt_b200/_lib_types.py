@@ -50,4 +50,5 @@ class KluPlanView(C.Structure):
                [(k, C.POINTER(C.c_int64)) for k in ("cbeg", "rowptr", "upd_ptr", "upd_dest")] + \
                [(k, C.POINTER(C.c_int32)) for k in ("udiag_slot", "slot_src", "slot_row", "rowent", "level_ptr", "level_cols",
                                                     "upd_uslot", "upd_lslot", "upd_cnt", "dest", "lslot0", "fslot0")] + \
-               [(k, i64) for k in ("nwaves", "nwaves_with_deps", "nbatches", "nsegments", "staged_rows", "npieces", "npiece_users")]
+               [(k, i64) for k in ("nwaves", "nwaves_with_deps", "nbatches", "nsegments", "staged_rows", "npieces", "npiece_users",
+                                   "wave_ok", "nearly", "nearly_levels")]

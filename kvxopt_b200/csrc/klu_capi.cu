@@ -275,6 +275,7 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
     v->nbatches = (b200s_int)P.bseg_ptr.size() - 1; v->nsegments = (b200s_int)P.seg_src.size(); v->staged_rows = 0;
     for (int c : P.seg_cnt) v->staged_rows += c;
     v->npieces = (b200s_int)P.pc_j0.size(); v->npiece_users = (b200s_int)P.pc_user_col.size();
+    v->wave_ok = P.wave_ok ? 1 : 0; v->nearly = (b200s_int)P.ecols.size(); v->nearly_levels = (b200s_int)P.elevel_ptr.size() - 1;
     return B200S_OK;
 }
 

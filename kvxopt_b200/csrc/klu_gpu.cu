@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <string>
 #include <chrono>
 
 namespace b200s {
@@ -97,6 +98,61 @@ __global__ void k_klu_scatter(const int* __restrict__ slot_src, const int* __res
     }
 }
 
+// Early columns (KluPlan::early): one warp per (column, group of 32 matrices), lane = matrix.  The column lives in the warp's
+// shared-memory scratch ([row][32]); its sources are finished columns of earlier levels (earlier launches), read straight from
+// LU with coalesced 256-byte rows.  No inter-warp dependency, thousands of columns per level: the launch fills the GPU and runs
+// at memory speed, instead of the one-wave-at-a-time latency of the wave kernel (these columns hold ~85 % of the columns and
+// ~5 % of the multiply-adds of a power-flow Jacobian).
+struct KluEarlyCol { int cb, len, diag, l0, upd0, nupd; };      // first slot, slots, pivot row, first L row, updates
+template <int ROWS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_klu_early(const KluEarlyCol* __restrict__ cols, int c0, int c1,
+                                                          const int4* __restrict__ eupd, const unsigned short* __restrict__ edest,
+                                                          const int* __restrict__ slot_src, long long gstride, int Bp,
+                                                          const double* __restrict__ Axs, double* __restrict__ LU,
+                                                          int* __restrict__ status) {
+    extern __shared__ double smem_early[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = c0 + blockIdx.x * WARPS + warp;
+    if (ci >= c1) return;
+    const KluEarlyCol C = cols[ci];
+    double* x = smem_early + warp * ROWS * 32 + lane;
+    const double* ax = Axs + (long long)blockIdx.y * 32 + lane;
+    double* lu = LU + (long long)blockIdx.y * gstride + lane;
+    // The source rows of all updates are requested from HBM up front (L2 prefetch: no registers, no waiting); the update loop
+    // below is a chain of dependent accesses per update (descriptor -> L rows -> shared-memory read-modify-write) and would
+    // otherwise pay the HBM latency once per update with only a few warps per SM to hide it.
+    for (int u = 0; u < C.nupd; u++) {
+        const int4 U = eupd[C.upd0 + u];
+        const double* lcol = lu + (long long)U.y * 32;
+        for (int t = 0; t < U.z; t++) asm volatile("prefetch.global.L2 [%0];" ::"l"(lcol + t * 32));
+    }
+    for (int r = 0; r < C.len; r++) {          // pre-scaled input values (k_klu_rowscale), zero in fill-in slots
+        const int src = slot_src[C.cb + r];
+        x[r * 32] = src >= 0 ? ax[(long long)src * Bp] : 0.0;
+    }
+    int4 Un = C.nupd > 0 ? eupd[C.upd0] : make_int4(0, 0, 0, 0);
+    for (int u = 0; u < C.nupd; u++) {
+        const int4 U = Un;                     // {row of u_jk, first L slot of the source, rows, first destination}
+        if (u + 1 < C.nupd) Un = eupd[C.upd0 + u + 1];
+        const double ujk = x[U.x * 32];
+        const double* lcol = lu + (long long)U.y * 32;
+        const unsigned short* d = edest + U.w;
+        int t = 0;
+        for (; t + 4 <= U.z; t += 4) {
+            const double l0 = lcol[t * 32], l1 = lcol[(t + 1) * 32], l2 = lcol[(t + 2) * 32], l3 = lcol[(t + 3) * 32];
+            double* p0 = x + d[t] * 32; double* p1 = x + d[t + 1] * 32; double* p2 = x + d[t + 2] * 32; double* p3 = x + d[t + 3] * 32;
+            *p0 = fma(-l0, ujk, *p0); *p1 = fma(-l1, ujk, *p1); *p2 = fma(-l2, ujk, *p2); *p3 = fma(-l3, ujk, *p3);
+        }
+        for (; t < U.z; t++) { double* p0 = x + d[t] * 32; *p0 = fma(-lcol[t * 32], ujk, *p0); }
+    }
+    const double piv = x[C.diag * 32];
+    const bool bad = !(fabs(piv) > 0.0);       // zero or NaN pivot
+    const double rpiv = 1.0 / piv;
+    for (int sl = C.l0; sl < C.len; sl++) x[sl * 32] *= rpiv;
+    for (int r = 0; r < C.len; r++) lu[(long long)(C.cb + r) * 32] = x[r * 32];
+    if (bad) status[blockIdx.y * 32 + lane] = ST_SINGULAR;
+}
+
 struct KluPlanD {
     int n, nlevels;
     long long gstride;          // doubles between the LU blocks of consecutive groups of 32 matrices (= slots * 32)
@@ -151,7 +207,10 @@ __global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, lon
 // the scaled input values is fused into the column initialisation.
 struct KluWaveD {
     int nwaves, spine0;
+    int pf_dist;                // batches the producer prefetches into L2 ahead of the ring (0: off)
     const int *wave_col0, *col_roff, *batch_rowslot, *wave_rowsrc;
+    const int *ne_cols, *wave_rows, *wrun_ptr;      // wave_col0 holds positions in ne_cols (the columns k_klu_early does not factor)
+    const int4* wrun;           // per run of consecutive columns of a wave: {first slot, first shared-memory row, rows, 0}
     const unsigned* bentry;     // per batch [KLU_WAVE_WARPS][KLU_CHUNK_ROWS] staged-row actions
     const unsigned* wblob;      // in-wave update blobs
     const long long *wbatch_ptr, *wblob_ptr;
@@ -178,13 +237,18 @@ __device__ __forceinline__ void klu_mbar_expect_tx(unsigned long long* b, unsign
 __device__ __forceinline__ void klu_mbar_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
 }
+#ifdef KLU_TEST_WAIT
+#define KLU_MBAR_WAIT_OP "mbarrier.test_wait.parity.shared::cta.b64"
+#else
+#define KLU_MBAR_WAIT_OP "mbarrier.try_wait.parity.shared::cta.b64"
+#endif
 __device__ __forceinline__ void klu_mbar_wait(unsigned long long* b, unsigned parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(b);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        KLU_MBAR_WAIT_OP " p, [%0], %1;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
@@ -193,6 +257,96 @@ __device__ __forceinline__ void klu_mbar_wait(unsigned long long* b, unsigned pa
 __device__ __forceinline__ void klu_bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                  "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void klu_bulk_prefetch_l2(const void* gmem, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void klu_mbar_arrive_n(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+// One staged piece applied to one column of the wave by one warp of the column's team (lane = matrix).
+//   x     : the column in shared memory (this lane), rows 32 doubles apart
+//   lb    : staged rectangle, this user's first source column: entry (a, i) at lb[(a * nrows + i) * 32]
+//   tb    : staged strictly lower triangle of the block (column b's g-1-b entries consecutively)
+//   d     : destination row in x of every rectangle row
+//   u     : the block's multipliers u_a = x[uloc + a] after the triangle; kept in registers for continuation pieces
+// The team's warps take 4-row chunks round robin (sub, T); the main loop is unpredicated, the last partial chunk predicated.
+template <int GU>
+__device__ __forceinline__ void klu_piece(double* __restrict__ x, const double* __restrict__ lb, const double* __restrict__ tb,
+                                          const unsigned short* __restrict__ d, int nrows, int uloc, int g, int s0, bool hastri,
+                                          bool cont, int sub, int T, double (&u)[KLU_SN_MAX], double (&pend)[KLU_SN_MAX - 1],
+                                          int& pend_row, int& pend_n) {
+    if (!cont) {
+#pragma unroll
+        for (int a = 0; a < GU; a++) u[a] = x[(uloc + a) * 32];
+    }
+    if (GU > 1 && hastri) {
+        // u_a -= sum_{b < a} L(j0+s0+a, j0+s0+b) u_b: computed by every warp of the team (identical values); warp `sub == 0`
+        // writes the rows back -- at once when it owns the column alone, else after the team's NEXT barrier, so that no warp
+        // of the team can read an already updated row (nobody reads these rows again before that: each row of U belongs to
+        // one source column)
+#pragma unroll
+        for (int b = 0; b < GU - 1; b++) {
+            const int B = s0 + b;
+            const double* tcol = tb + (B * (g - 1) - (B * (B - 1)) / 2) * 32;     // column B of the triangle: rows B+1 ..
+#pragma unroll
+            for (int a = b + 1; a < GU; a++) u[a] = fma(-tcol[(a - b - 1) * 32], u[b], u[a]);
+        }
+        if (sub == 0) {
+            if (T == 1) {
+#pragma unroll
+                for (int a = 1; a < GU; a++) x[(uloc + a) * 32] = u[a];
+            } else {
+                pend_row = uloc + 1; pend_n = GU - 1;
+#pragma unroll
+                for (int a = 1; a < GU; a++) pend[a - 1] = u[a];
+            }
+        }
+    }
+    int i = 4 * sub;
+    const int step = 4 * T;
+    for (; i + 4 <= nrows; i += step) {
+        // all loads of the chunk are issued before the first multiply-add (the compiler otherwise chains every shared-memory
+        // load with its use through one temporary: 4 GU dependent load latencies per chunk)
+        const int e0 = d[i], e1 = d[i + 1], e2 = d[i + 2], e3 = d[i + 3];
+        double lv[GU][4];
+        const double* l = lb + i * 32;
+#pragma unroll
+        for (int a = 0; a < GU; a++) {
+            lv[a][0] = l[0]; lv[a][1] = l[32]; lv[a][2] = l[64]; lv[a][3] = l[96];
+            l += nrows * 32;
+        }
+        double* p0 = x + e0 * 32; double* p1 = x + e1 * 32; double* p2 = x + e2 * 32; double* p3 = x + e3 * 32;
+        double a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
+        asm volatile("" ::"d"(lv[0][0]), "d"(lv[GU - 1][3]), "d"(a0), "d"(a3));      // scheduling fence: loads above, arithmetic below
+#pragma unroll
+        for (int a = 0; a < GU; a++) {
+            a0 = fma(-lv[a][0], u[a], a0); a1 = fma(-lv[a][1], u[a], a1); a2 = fma(-lv[a][2], u[a], a2); a3 = fma(-lv[a][3], u[a], a3);
+        }
+        *p0 = a0; *p1 = a1; *p2 = a2; *p3 = a3;
+    }
+    if (i < nrows) {            // last, partial chunk (1..3 rows): rows past the end repeat row i and are not stored
+        const int left = nrows - i;
+        const int o1 = left > 1 ? 1 : 0, o2 = left > 2 ? 2 : 0;
+        const int e0 = d[i], e1 = d[i + o1], e2 = d[i + o2];
+        double lv[GU][3];
+        const double* l = lb + i * 32;
+#pragma unroll
+        for (int a = 0; a < GU; a++) {
+            lv[a][0] = l[0]; lv[a][1] = l[o1 * 32]; lv[a][2] = l[o2 * 32];
+            l += nrows * 32;
+        }
+        double* p0 = x + e0 * 32; double* p1 = x + e1 * 32; double* p2 = x + e2 * 32;
+        double a0 = *p0, a1 = *p1, a2 = *p2;
+        asm volatile("" ::"d"(lv[0][0]), "d"(lv[GU - 1][2]), "d"(a0), "d"(a2));
+#pragma unroll
+        for (int a = 0; a < GU; a++) {
+            a0 = fma(-lv[a][0], u[a], a0); a1 = fma(-lv[a][1], u[a], a1); a2 = fma(-lv[a][2], u[a], a2);
+        }
+        *p0 = a0;
+        if (left > 1) *p1 = a1;
+        if (left > 2) *p2 = a2;
+    }
 }
 constexpr int KLU_CONS_BAR = 9;      // named barrier of the 16 consumer warps (team barriers use 1..8)
 
@@ -232,6 +386,8 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     if (warp == KLU_WAVE_WARPS) {
         // ---------------- producer warp: lane r issues staged rows r and r + 32 of every batch
         constexpr unsigned META_BYTES = KLU_WAVE_WARPS * KLU_REC_U32 * 4;
+        const long long nbatches_total = W.wbatch_ptr[W.nwaves];
+        const int pf_dist = W.pf_dist;
         for (int w = 0; w < W.nwaves; w++) {
             const long long c0 = W.wbatch_ptr[w], c1 = W.wbatch_ptr[w + 1];
             int s0 = 0, s1 = 0;
@@ -269,6 +425,18 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                     if (a0 + 32 * (q + 1) + lane < a1)
                         klu_bulk_g2s(dst + (ex[q].y & 0xff) * 32, lug + (long long)ex[q].x * 32, (unsigned)(ex[q].y >> 8) * 256u, &full_bar[slot]);
                 if (lane == 0) klu_bulk_g2s(dst + KLU_CHUNK_ROWS * 32, W.bentry + g * KLU_ENTRY_DOUBLES * 2, META_BYTES, &full_bar[slot]);
+                // L2 prefetch of the batch `pf_dist` ahead (also across the end of the wave): the ring holds only KLU_STAGES
+                // batches, which is less than HBM latency x the SM's bandwidth share; the prefetch keeps more bytes in flight at
+                // no shared-memory cost, and the ring's own copies then hit L2.  (A column the current wave is still producing may
+                // be prefetched early: L2 is the coherence point, the wave's bulk store lands in the same lines.)
+                if (pf_dist > 0 && g + pf_dist < nbatches_total) {
+                    const int p0 = W.bseg_ptr[g + pf_dist], p1 = W.bseg_ptr[g + pf_dist + 1];
+                    for (int q = p0 + lane; q < p1; q += 32) {
+                        const int2 pd = W.segd[q];
+                        klu_bulk_prefetch_l2(lug + (long long)pd.x * 32, (unsigned)(pd.y >> 8) * 256u);
+                    }
+                    if (lane == 0) klu_bulk_prefetch_l2(W.bentry + (g + pf_dist) * KLU_ENTRY_DOUBLES * 2, META_BYTES);
+                }
             }
             asm volatile("bar.sync 0;" ::: "memory");       // end of wave: the consumers stored (and fenced) the wave's columns
         }
@@ -283,18 +451,20 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     long long n_c0 = W.wbatch_ptr[0], n_c1 = W.wbatch_ptr[1], n_bp0 = W.wblob_ptr[0], n_bp1 = W.wblob_ptr[1];
     int n_cb = 0, n_len = 0, n_roff = 0, n_diag = 0, n_l0 = 0, n_wrows = 0;
     auto team_size = [](int wc) { return wc <= 8 ? KLU_WAVE_WARPS / wc : 1; };      // warps per column (any size, not only 2^k)
-    auto load_part2 = [&]() {
+    int n_k = 0;
+    auto load_part2 = [&](int wn) {
         const int n_wc = n_k1 - n_k0;
         const int c = warp / team_size(n_wc);
-        const int k = n_k0 + (c < n_wc ? c : 0);
+        const int k = W.ne_cols[n_k0 + (c < n_wc ? c : 0)];
+        n_k = k;
         n_cb = (int)P.cbeg[k];
         n_len = (int)P.cbeg[k + 1] - n_cb;
         n_roff = W.col_roff[k];
         n_diag = P.udiag_slot[k] - n_cb;
         n_l0 = P.lslot0[k] - n_cb;
-        n_wrows = (int)(P.cbeg[n_k1] - P.cbeg[n_k0]);
+        n_wrows = W.wave_rows[wn];
     };
-    load_part2();
+    load_part2(0);
     for (int r = tid; r < KLU_WAVE_ROWS; r += KLU_WAVE_WARPS * 32) rs_tab[r] = W.wave_rowsrc[r];
     asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
     for (int w = 0; w < W.nwaves; w++) {
@@ -303,8 +473,8 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         // team = the warps that share one column: floor(16 / wc) warps
         const int T = team_size(wc), col = warp / T, sub = warp - col * T;
         const bool active = col < wc;
-        const int k = k0 + (active ? col : 0);
-        const int cb = n_cb, len = n_len;
+        const int k = n_k;
+        const int len = n_len;
         double* x = xs + n_roff * 32 + lane;
         const int diag = n_diag, l0 = n_l0;
         const long long c0 = n_c0;
@@ -351,14 +521,19 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
         for (int a = 0; a < KLU_SN_MAX; a++) u[a] = 0.0;
 #pragma unroll
         for (int a = 0; a < KLU_SN_MAX - 1; a++) pend[a] = 0.0;
-        for (int c = 0; c < nb; c++) {
-            const long long g = c0 + c;
-            const int buf = (int)(g % KLU_STAGES);
-            long long q0 = 0;
-            if (dbg) q0 = clock64();
-            klu_mbar_wait(&full_bar[buf], (unsigned)((g / KLU_STAGES) & 1));
-            if (dbg) { t_w += clock64() - q0; if (c == 0) t_w0 += clock64() - q0; }
-            if (active) {
+        // Only the warps that own (a share of) a column walk the staged batches; the 16 arrivals a ring slot waits for are
+        // dealt among them (mbarrier.arrive with a count), so the other warps go straight to the end-of-phase barrier
+        // instead of spinning through every batch.
+        if (active && nb > 0) {
+            const int nact = wc * T;
+            const unsigned arrive_cnt = (unsigned)(KLU_WAVE_WARPS / nact + (warp < KLU_WAVE_WARPS % nact ? 1 : 0));
+            for (int c = 0; c < nb; c++) {
+                const long long g = c0 + c;
+                const int buf = (int)(g % KLU_STAGES);
+                long long q0 = 0;
+                if (dbg) q0 = clock64();
+                klu_mbar_wait(&full_bar[buf], (unsigned)((g / KLU_STAGES) & 1));
+                if (dbg) { t_w += clock64() - q0; if (c == 0) t_w0 += clock64() - q0; }
                 const double* sb = stage + (long long)buf * KLU_STAGE_DOUBLES + lane;
                 const unsigned* rec = reinterpret_cast<const unsigned*>(stage + (long long)buf * KLU_STAGE_DOUBLES + KLU_CHUNK_ROWS * 32) +
                                       col * KLU_REC_U32;
@@ -367,77 +542,34 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                 // A piece = rows [i, i + nrows) below a source BLOCK of g <= KLU_SN_MAX consecutive columns of one L supernode, of
                 // which this column uses the last gu = g - s0 (fill closure).  The block's own rows (u_jk, consecutive rows of
                 // x) first go through the block's unit lower triangle in registers; then every destination row is read and
-                // written ONCE for gu multiply-adds (one read-modify-write per multiply-add before: the kernel was bound by
-                // shared-memory wavefronts and by the ~22 instructions it issued per multiply-add).
+                // written ONCE for gu multiply-adds.  The code is specialised on gu (no predicated-off multiply-adds) and the
+                // next piece's record words are fetched before the current piece runs.
+                unsigned w0 = rec[1], w1 = rec[2];
                 for (int sgi = 0; sgi < nseg; sgi++) {
-                    const unsigned w0 = rec[1 + 2 * sgi], w1 = rec[2 + 2 * sgi];
+                    const unsigned nw0 = rec[3 + 2 * sgi], nw1 = rec[4 + 2 * sgi];      // (one pair past the last piece: inside the record)
                     const int r0 = w0 & 0xffu, nrows = (w0 >> 8) & 0xffu, uloc = (int)(w0 >> 16);
-                    const int g = w1 & 0xfu, s0 = (w1 >> 4) & 0xfu, tri0 = (w1 >> 8) & 0xffu;
+                    const int gg = w1 & 0xfu, s0 = (w1 >> 4) & 0xfu, tri0 = (w1 >> 8) & 0xffu;
                     const bool hastri = (w1 >> 16) & 1u, cont = (w1 >> 17) & 1u;
-                    const int gu = g - s0;
+                    const int gu = gg - s0;
                     team_sync();          // the previous piece of every warp of the team is complete
-                    if (pend_n) {         // rows of the previous block's triangle (see below)
+                    if (pend_n) {         // rows of the previous block's triangle (see klu_piece)
 #pragma unroll
                         for (int a = 0; a < KLU_SN_MAX - 1; a++) if (a < pend_n) x[(pend_row + a) * 32] = pend[a];
                         pend_n = 0;
                     }
-                    // a continuation piece (more rows below the same block, possibly in a later batch) keeps the u_a every
-                    // warp of the team computed for the block's first piece: they are not re-read (warp 0's deferred write
-                    // of them may still be in flight)
-                    if (!cont) {
-#pragma unroll
-                        for (int a = 0; a < KLU_SN_MAX; a++) u[a] = a < gu ? x[(uloc + a) * 32] : 0.0;
-                    }
-                    if (hastri && gu > 1) {
-                        // u_a -= sum_{b < a} L(j0+s0+a, j0+s0+b) u_b: computed by every warp of the team (identical values);
-                        // warp `sub == 0` writes the rows back -- at once when it owns the column alone, else after the team's
-                        // NEXT barrier, so that no warp of the team can read an already updated row (nobody reads these rows
-                        // again before that: each row of U belongs to one source column)
-#pragma unroll
-                        for (int a = 1; a < KLU_SN_MAX; a++)
-                            if (a < gu) {
-                                const int A = s0 + a;
-#pragma unroll
-                                for (int b = 0; b < KLU_SN_MAX - 1; b++)
-                                    if (b < a) {
-                                        const int B = s0 + b;
-                                        u[a] = fma(-sb[(tri0 + B * (g - 1) - (B * (B - 1)) / 2 + (A - B - 1)) * 32], u[b], u[a]);
-                                    }
-                            }
-                        if (sub == 0) {
-                            if (T == 1) {
-#pragma unroll
-                                for (int a = 1; a < KLU_SN_MAX; a++) if (a < gu) x[(uloc + a) * 32] = u[a];
-                            } else {
-                                pend_row = uloc + 1; pend_n = gu - 1;
-#pragma unroll
-                                for (int a = 1; a < KLU_SN_MAX; a++) pend[a - 1] = u[a];
-                            }
-                        }
-                    }
                     const double* lb = sb + (r0 + s0 * nrows) * 32;
-                    for (int i = 4 * sub; i < nrows; i += 4 * T) {
-                        int e[4]; double acc[4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) e[q] = i + q < nrows ? dd[r0 + i + q] * 32 : 0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) acc[q] = x[e[q]];
-#pragma unroll
-                        for (int a = 0; a < KLU_SN_MAX; a++)
-                            if (a < gu) {
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    const double m = i + q < nrows ? lb[(a * nrows + i + q) * 32] : 0.0;
-                                    acc[q] = fma(-m, u[a], acc[q]);
-                                }
-                            }
-#pragma unroll
-                        for (int q = 0; q < 4; q++) if (i + q < nrows) x[e[q]] = acc[q];
+                    const double* tb = sb + tri0 * 32;
+                    switch (gu) {
+                        case 1: klu_piece<1>(x, lb, tb, dd + r0, nrows, uloc, gg, s0, hastri, cont, sub, T, u, pend, pend_row, pend_n); break;
+                        case 2: klu_piece<2>(x, lb, tb, dd + r0, nrows, uloc, gg, s0, hastri, cont, sub, T, u, pend, pend_row, pend_n); break;
+                        case 3: klu_piece<3>(x, lb, tb, dd + r0, nrows, uloc, gg, s0, hastri, cont, sub, T, u, pend, pend_row, pend_n); break;
+                        default: klu_piece<4>(x, lb, tb, dd + r0, nrows, uloc, gg, s0, hastri, cont, sub, T, u, pend, pend_row, pend_n); break;
                     }
+                    w0 = nw0; w1 = nw1;
                 }
+                __syncwarp();
+                if (lane == 0) klu_mbar_arrive_n(&empty_bar[buf], arrive_cnt);
             }
-            __syncwarp();
-            if (lane == 0) klu_mbar_arrive(&empty_bar[buf]);
         }
         if (active && T > 1) team_sync();      // every warp of the team is past the reads of its last piece
         if (pend_n) {             // (T > 1, warp sub == 0) the last triangle rows of this wave
@@ -446,7 +578,7 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
             pend_n = 0;
         }
         if (tid < KLU_WAVE_WARPS) done_round[tid] = 0x7fffffff;
-        if (w + 1 < W.nwaves) load_part2();      // part 2 of the next wave's parameters (depends on part 1)
+        if (w + 1 < W.nwaves) load_part2(w + 1);      // part 2 of the next wave's parameters (depends on part 1)
         asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
         if (dbg) { long long tB = clock64(); t_p1 += tB - tA; tA = tB; }
         // ---- sources inside the wave: rounds.  In round r a column consumes (in pivot order) the in-wave sources
@@ -509,12 +641,15 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
             }
         }
         if (dbg) { long long tB = clock64(); t_p2 += tB - tA; tA = tB; if (tid == 0 && blockIdx.x == 0) { dbg[8 + 2 * w] = t_init + t_p1; dbg[9 + 2 * w] = t_p2; } }
-        // the columns of a wave own consecutive slots and consecutive xs rows: ONE bulk store (TMA) writes the wave
+        // a run of consecutive columns of the wave owns consecutive slots and consecutive xs rows: one bulk store (TMA) per run
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
         if (tid == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(lu + (long long)cb * 32),
-                         "r"((unsigned)__cvta_generic_to_shared(xs)), "r"((unsigned)wrows * 256u) : "memory");
+            for (int rn = W.wrun_ptr[w]; rn < W.wrun_ptr[w + 1]; rn++) {
+                const int4 run = W.wrun[rn];
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(lug + (long long)run.x * 32),
+                             "r"((unsigned)__cvta_generic_to_shared(xs + run.y * 32)), "r"((unsigned)run.z * 256u) : "memory");
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
@@ -1068,6 +1203,11 @@ public:
     bool buf_used[2] = {false, false};
     int npending = 0, next_buf = 0;
     long long* ddbg = nullptr;     // optional phase timers of the wave kernel (B200S_KLU_DEBUG=1)
+    // early columns (k_klu_early): per level the [short | long] column ranges in d_ecols
+    const KluEarlyCol* d_ecols = nullptr;
+    const int4* d_eupd = nullptr;
+    const unsigned short* d_edest = nullptr;
+    std::vector<int> h_elevel_ptr, h_elevel_long;
     long long* d_rowptr = nullptr;
     long long nslots = 0, nnzA = 0;
     int n = 0;
@@ -1119,7 +1259,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     n = P.n; nslots = P.nslots; nnzA = P.nnzA;
-    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(pool_malloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; }
+    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(pool_malloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; cudaMemset(ddbg, 0, (8 + 2 * P.wave_col0.size()) * sizeof(long long)); }
     int rc;
     PD.n = P.n; PD.nlevels = P.nlevels; PD.gstride = (long long)P.nslots * 32;
     std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
@@ -1156,10 +1296,44 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
             if ((rc = up(&WD.bseg_ptr, bsp))) return rc;
             if ((rc = up(&WD.segd, sgd))) return rc;
         }
+        if ((rc = up(&WD.ne_cols, P.ne_cols))) return rc;
+        if ((rc = up(&WD.wave_rows, P.wave_rows))) return rc;
+        if ((rc = up(&WD.wrun_ptr, P.wrun_ptr))) return rc;
+        {
+            std::vector<int4> runs(P.wrun_slot.size());
+            for (size_t q = 0; q < runs.size(); q++) runs[q] = make_int4(P.wrun_slot[q], P.wrun_row[q], P.wrun_cnt[q], 0);
+            if ((rc = up(&WD.wrun, runs))) return rc;
+        }
+        if (use_wave && !P.ecols.empty()) {
+            // compact tables of the early columns, in launch order
+            std::vector<KluEarlyCol> ec(P.ecols.size());
+            std::vector<int4> eu;
+            std::vector<unsigned short> ed;
+            for (size_t e = 0; e < P.ecols.size(); e++) {
+                const int k = P.ecols[e];
+                const long long cb = P.cbeg[k];
+                ec[e].cb = (int)cb; ec[e].len = (int)(P.cbeg[k + 1] - cb);
+                ec[e].diag = P.udiag_slot[k] - (int)cb; ec[e].l0 = P.lslot0[k] - (int)cb;
+                ec[e].upd0 = (int)eu.size(); ec[e].nupd = (int)(P.upd_ptr[k + 1] - P.upd_ptr[k]);
+                for (long long u = P.upd_ptr[k]; u < P.upd_ptr[k + 1]; u++) {
+                    eu.push_back(make_int4(P.upd_uslot[u] - (int)cb, P.upd_lslot[u], P.upd_cnt[u], (int)ed.size()));
+                    for (int t = 0; t < P.upd_cnt[u]; t++) ed.push_back((unsigned short)(P.dest[P.upd_dest[u] + t] - cb));
+                }
+            }
+            if ((rc = up(&d_ecols, ec))) return rc;
+            if ((rc = up(&d_eupd, eu))) return rc;
+            if ((rc = up(&d_edest, ed))) return rc;
+            h_elevel_ptr = P.elevel_ptr; h_elevel_long = P.elevel_long;
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_early<KLU_EARLY_MAXLEN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(KLU_EARLY_MAXLEN * 4 * 256)));
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_early<KLU_EARLY_MID, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(KLU_EARLY_MID * 8 * 256)));
+        }
         static_assert(sizeof(unsigned) == sizeof(uint32_t), "plan tables are uploaded as they are");
         if ((rc = up(&WD.bentry, P.bentry))) return rc;       // the largest table (11.5 MB on ACTIVSg2000): no staging copy
         if ((rc = up(&WD.wblob, P.wblob))) return rc;
         WD.spine0 = use_wave ? P.spine0 : P.n;
+        WD.pf_dist = getenv("B200S_KLU_PF") ? atoi(getenv("B200S_KLU_PF")) : 0;
         spine_nd = use_wave ? P.spine_nd : 0;
         if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;
         if ((rc = up(&d_dense_slot, P.dense_slot))) return rc;
@@ -1228,9 +1402,29 @@ int KluDevice::enqueue_refactor(const double* dv, long long ldv, cudaEvent_t aft
         if (nslots > lu_slots)
             k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1, nslots * 32);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
-        k_klu_refactor_wave<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
+        int early_launches = 0;
+        for (size_t l = 0; l + 1 < h_elevel_ptr.size(); l++) {          // early columns, level by level, by length class
+            const int c0 = h_elevel_ptr[l], cm = h_elevel_long[2 * l], cm2 = h_elevel_long[2 * l + 1], c1 = h_elevel_ptr[l + 1];
+            if (cm > c0) {
+                const dim3 grid((unsigned)((cm - c0 + 7) / 8), (unsigned)(Bp / 32));
+                k_klu_early<KLU_EARLY_SHORT, 8><<<grid, 8 * 32, KLU_EARLY_SHORT * 8 * 256, stream>>>(d_ecols, c0, cm, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
+                early_launches++;
+            }
+            if (cm2 > cm) {
+                const dim3 grid((unsigned)((cm2 - cm + 7) / 8), (unsigned)(Bp / 32));
+                k_klu_early<KLU_EARLY_MID, 8><<<grid, 8 * 32, KLU_EARLY_MID * 8 * 256, stream>>>(d_ecols, cm, cm2, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
+                early_launches++;
+            }
+            if (c1 > cm2) {
+                const dim3 grid((unsigned)((c1 - cm2 + 3) / 4), (unsigned)(Bp / 32));
+                k_klu_early<KLU_EARLY_MAXLEN, 4><<<grid, 4 * 32, KLU_EARLY_MAXLEN * 4 * 256, stream>>>(d_ecols, cm2, c1, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
+                early_launches++;
+            }
+        }
+        if (WD.nwaves > 0)
+            k_klu_refactor_wave<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);
         CUDA_TRY(cudaEventRecord(ev[6], stream));
-        launches = 3 + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
+        launches = 2 + early_launches + (WD.nwaves > 0 ? 1 : 0) + (nslots > lu_slots ? 1 : 0) + (spine_nd > 0 ? 3 : 0);
         if (spine_nd > 0) {
             const dim3 tg(ndp / 32, Bp / 32);
             k_klu_dense_pack<<<tg, 256, 0, stream>>>(d_dense_slot, ndmap, ndp, nslots * 32, dLU, dD, 0);

@@ -480,37 +480,134 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         }
     }
     lap("dense block");
+    // ---- early columns: the wide first levels of the dependency graph (see KluPlan::early)
+    P.early.assign(n, 0);
+    P.elevel_ptr.assign(1, 0);
+    P.ecols.clear(); P.elevel_long.clear();
+    {
+        const char* ev = getenv("B200S_KLU_EARLY");
+        const bool enabled = !(ev && atoi(ev) == 0);
+        // level over row AND column dependencies: columns ascending, level[k] is final once the U part of column k has been
+        // looked at (the L rows of earlier columns were pushed before)
+        std::vector<i32> lv(n, 0);
+        for (i32 k = 0; k < n; k++) {
+            i32 l = lv[k];
+            for (i64 q = N.Up[k]; q < N.Up[k + 1] - 1; q++) l = std::max(l, lv[N.Ui[q]] + 1);
+            lv[k] = l;
+            for (i64 q = N.Lp[k] + 1; q < N.Lp[k + 1]; q++) lv[N.Li[q]] = std::max(lv[N.Li[q]], l + 1);
+        }
+        i32 nl = 0;
+        for (i32 k = 0; k < n; k++) nl = std::max(nl, lv[k] + 1);
+        std::vector<i32> cnt(nl, 0), mlen(nl, 0);
+        for (i32 k = 0; k < n; k++) {
+            if (k >= P.spine0) { mlen[lv[k]] = KLU_EARLY_MAXLEN + 1; continue; }       // the dense block's columns are never early
+            cnt[lv[k]]++;
+            mlen[lv[k]] = std::max<i32>(mlen[lv[k]], (i32)(P.cbeg[k + 1] - P.cbeg[k]));
+        }
+        i32 lmax = -1, total = 0;
+        const i32 minw = getenv("B200S_KLU_EARLY_MINW") ? atoi(getenv("B200S_KLU_EARLY_MINW")) : KLU_EARLY_MINW;
+        const i32 maxlev = getenv("B200S_KLU_EARLY_LEVELS") ? atoi(getenv("B200S_KLU_EARLY_LEVELS")) : 0x7fffffff;
+        while (enabled && lmax + 1 < nl && lmax + 1 < maxlev && cnt[lmax + 1] >= minw && mlen[lmax + 1] <= KLU_EARLY_MAXLEN) { lmax++; total += cnt[lmax]; }
+        if (total < 8 * minw) lmax = -1;          // not worth the extra launches
+        if (tdbg) fprintf(stderr, "[b200s klu plan] dependency levels %d, early levels %d with %d of %d columns\n", nl, lmax + 1, lmax >= 0 ? total : 0, n);
+        if (lmax >= 0) {
+            for (i32 k = 0; k < n; k++) P.early[k] = lv[k] <= lmax;
+            P.elevel_ptr.assign(lmax + 2, 0);
+            for (i32 k = 0; k < n; k++) if (P.early[k]) P.elevel_ptr[lv[k] + 1]++;
+            for (i32 l = 0; l <= lmax; l++) P.elevel_ptr[l + 1] += P.elevel_ptr[l];
+            P.ecols.resize(P.elevel_ptr[lmax + 1]);
+            std::vector<i32> pos(P.elevel_ptr.begin(), P.elevel_ptr.end() - 1);
+            for (i32 k = 0; k < n; k++) if (P.early[k]) P.ecols[pos[lv[k]]++] = k;
+            P.elevel_long.assign(2 * (lmax + 1), 0);
+            for (i32 l = 0; l <= lmax; l++) {
+                i32* b = P.ecols.data() + P.elevel_ptr[l];
+                i32* e = P.ecols.data() + P.elevel_ptr[l + 1];
+                std::stable_sort(b, e, [&](i32 a, i32 c) { return P.cbeg[a + 1] - P.cbeg[a] < P.cbeg[c + 1] - P.cbeg[c]; });
+                i32* m = b;
+                while (m < e && P.cbeg[*m + 1] - P.cbeg[*m] <= KLU_EARLY_SHORT) m++;
+                P.elevel_long[2 * l] = (i32)(m - P.ecols.data());
+                while (m < e && P.cbeg[*m + 1] - P.cbeg[*m] <= KLU_EARLY_MID) m++;
+                P.elevel_long[2 * l + 1] = (i32)(m - P.ecols.data());
+            }
+            // update lists: early sources first (both parts keep their ascending order)
+            std::vector<i32> t_src, t_us, t_ls, t_cnt; std::vector<i64> t_dst;
+            for (i32 k = 0; k < n; k++) {
+                const i64 u0 = P.upd_ptr[k], u1 = P.upd_ptr[k + 1];
+                bool mixed = false, seen_late = false;
+                for (i64 u = u0; u < u1; u++) { if (!P.early[P.upd_src[u]]) seen_late = true; else if (seen_late) mixed = true; }
+                if (P.early[k] && seen_late) throw std::logic_error("klu plan: early column with a late source");
+                if (!mixed) continue;
+                t_src.clear(); t_us.clear(); t_ls.clear(); t_cnt.clear(); t_dst.clear();
+                for (int pass = 0; pass < 2; pass++)
+                    for (i64 u = u0; u < u1; u++)
+                        if ((P.early[P.upd_src[u]] != 0) == (pass == 0)) {
+                            t_src.push_back(P.upd_src[u]); t_us.push_back(P.upd_uslot[u]); t_ls.push_back(P.upd_lslot[u]);
+                            t_cnt.push_back(P.upd_cnt[u]); t_dst.push_back(P.upd_dest[u]);
+                        }
+                for (i64 u = u0; u < u1; u++) {
+                    P.upd_src[u] = t_src[u - u0]; P.upd_uslot[u] = t_us[u - u0]; P.upd_lslot[u] = t_ls[u - u0];
+                    P.upd_cnt[u] = t_cnt[u - u0]; P.upd_dest[u] = t_dst[u - u0];
+                }
+            }
+            // the dense block's columns: the updates the wave kernel applies end where the sources inside the block begin
+            for (i32 k = P.spine0; k < n; k++) {
+                i64 u = P.upd_ptr[k];
+                while (u < P.upd_ptr[k + 1] && P.upd_src[u] < P.spine0) u++;
+                for (i64 v = u; v < P.upd_ptr[k + 1]; v++) if (P.upd_src[v] < P.spine0) throw std::logic_error("klu plan: dense-block sources are not a suffix");
+                P.upd_end[k] = u;
+            }
+        }
+    }
+    P.ne_cols.clear();
+    P.ne_pos.assign(n, -1);
+    for (i32 k = 0; k < n; k++) if (!P.early[k]) { P.ne_pos[k] = (i32)P.ne_cols.size(); P.ne_cols.push_back(k); }
+    const i32 nne = (i32)P.ne_cols.size();
+    // a source is "inside the wave that starts at position p0" when it is a late column at a position >= p0
+    auto in_wave = [&](i32 j, i32 p0) { return !P.early[j] && P.ne_pos[j] >= p0; };
+    lap("early columns");
     // wave schedule
     P.col_roff.assign(n, 0);
     P.upd_split.assign(n, 0);
     P.wave_col0.clear();
+    P.wave_rows.clear();
+    P.wrun_ptr.assign(1, 0);
+    P.wrun_slot.clear(); P.wrun_row.clear(); P.wrun_cnt.clear();
     P.max_col_len = 0;
     for (i32 k = 0; k < n; k++) P.max_col_len = std::max<i32>(P.max_col_len, (i32)(P.cbeg[k + 1] - P.cbeg[k]));
     {
         // in-wave blob size if the wave [k0, k1) were closed: header + updates + dest lists
-        auto blob_bytes = [&](i32 k0, i32 k1) {
+        // (waves are ranges [p0, p1) of positions in ne_cols)
+        auto blob_bytes = [&](i32 p0, i32 p1) {
             i64 nu = 0, nd = 0;
-            for (i32 c = k0; c < k1; c++)
+            for (i32 q = p0; q < p1; q++) {
+                const i32 c = P.ne_cols[q];
                 for (i64 u = P.upd_ptr[c]; u < P.upd_end[c]; u++)
-                    if (P.upd_src[u] >= k0) { nu++; nd += P.upd_cnt[u]; }
+                    if (in_wave(P.upd_src[u], p0)) { nu++; nd += P.upd_cnt[u]; }
+            }
             return (i64)(2 * KLU_WAVE_WARPS) * 4 + nu * 16 + ((nd * 2 + 15) / 16) * 16;
         };
-        i32 k = 0;
-        while (k < n) {
-            P.wave_col0.push_back(k);
-            const i32 k0 = k;
+        i32 pk = 0;
+        while (pk < nne) {
+            P.wave_col0.push_back(pk);
+            const i32 p0 = pk;
             i32 rows = 0, cnt = 0;
-            while (k < n && cnt < KLU_WAVE_WARPS) {
+            while (pk < nne && cnt < KLU_WAVE_WARPS) {
+                const i32 k = P.ne_cols[pk];
                 const i32 len = (i32)(P.cbeg[k + 1] - P.cbeg[k]);
                 if (cnt > 0 && rows + len > KLU_WAVE_ROWS) break;
-                if (cnt > 0 && blob_bytes(k0, k + 1) > KLU_BLOB_BYTES) break;
+                if (cnt > 0 && blob_bytes(p0, pk + 1) > KLU_BLOB_BYTES) break;
                 P.col_roff[k] = rows;
+                // runs of consecutive columns own consecutive slots and consecutive shared-memory rows
+                if (cnt > 0 && P.ne_cols[pk - 1] == k - 1) P.wrun_cnt.back() += len;
+                else { P.wrun_slot.push_back((i32)P.cbeg[k]); P.wrun_row.push_back(rows); P.wrun_cnt.push_back(len); }
                 rows += len;
                 cnt++;
-                k++;
+                pk++;
             }
+            P.wave_rows.push_back(rows);
+            P.wrun_ptr.push_back((i32)P.wrun_slot.size());
         }
-        P.wave_col0.push_back(n);
+        P.wave_col0.push_back(nne);
         // Budget: every wave re-streams the earlier L columns its columns need, with ~52 bytes of records per staged row.
         // With heavy fill (columns longer than the shared-memory wave, or narrow waves over a dense factor) the tables
         // grow like the flop count; such patterns go to the level-schedule kernel instead and no wave tables are built.
@@ -518,17 +615,23 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             i64 staged = 0;
             std::vector<i32> mark(n, -1);
             for (i32 w = 0; w + 1 < (i32)P.wave_col0.size() && staged <= KLU_WAVE_MAX_STAGED; w++) {
-                const i32 k0 = P.wave_col0[w];
-                for (i32 c = k0; c < P.wave_col0[w + 1]; c++)
-                    for (i64 u = P.upd_ptr[c]; u < P.upd_end[c] && P.upd_src[u] < k0; u++)
+                const i32 p0 = P.wave_col0[w];
+                for (i32 q = p0; q < P.wave_col0[w + 1]; q++) {
+                    const i32 c = P.ne_cols[q];
+                    for (i64 u = P.upd_ptr[c]; u < P.upd_end[c] && !in_wave(P.upd_src[u], p0); u++)
                         if (mark[P.upd_src[u]] != w) { mark[P.upd_src[u]] = w; staged += P.upd_cnt[u]; }
+                }
             }
             P.wave_ok = P.max_col_len <= KLU_WAVE_ROWS && staged <= KLU_WAVE_MAX_STAGED;
             if (!P.wave_ok) {
+                // level-schedule kernel for everything (the early-first order of the update lists is a valid order for it too)
                 P.wave_col0.assign(1, 0);
+                P.wave_rows.clear(); P.wrun_ptr.assign(1, 0); P.wrun_slot.clear(); P.wrun_row.clear(); P.wrun_cnt.clear();
                 P.spine0 = n; P.spine_nd = 0;
                 P.dense_meta.clear(); P.dense_slot.clear();
                 for (i32 k = 0; k < n; k++) P.upd_end[k] = P.upd_ptr[k + 1];
+                std::fill(P.early.begin(), P.early.end(), 0);
+                P.elevel_ptr.assign(1, 0); P.ecols.clear(); P.elevel_long.clear();
             }
         }
         const i32 nw = (i32)P.wave_col0.size() - 1;
@@ -548,21 +651,25 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         std::vector<i32> srcs, matched, s0of;
         std::vector<i64> ucur;
         for (i32 w = 0; w < nw; w++) {
-            const i32 k0 = P.wave_col0[w], wc = P.wave_col0[w + 1] - k0;
+            const i32 k0 = P.wave_col0[w], wc = P.wave_col0[w + 1] - k0;        // positions in ne_cols
+            const i32* wcol = P.ne_cols.data() + k0;                              // the wave's columns
             srcs.clear();
-            for (i32 c = k0; c < k0 + wc; c++) {
+            for (i32 q = 0; q < wc; q++) {
+                const i32 c = wcol[q];
                 i64 u = P.upd_ptr[c];
-                while (u < P.upd_end[c] && P.upd_src[u] < k0) { srcs.push_back(P.upd_src[u]); u++; }
+                while (u < P.upd_end[c] && !in_wave(P.upd_src[u], k0)) { srcs.push_back(P.upd_src[u]); u++; }
                 P.upd_split[c] = u;
                 if (u < P.upd_end[c]) P.wave_hasdep[w] = 1;
             }
-            std::sort(srcs.begin(), srcs.end());
+            // the order of every column's update list: early sources first, ascending inside both classes
+            auto src_less = [&](i32 a, i32 b) { return P.early[a] != P.early[b] ? P.early[a] > P.early[b] : a < b; };
+            std::sort(srcs.begin(), srcs.end(), src_less);
             srcs.erase(std::unique(srcs.begin(), srcs.end()), srcs.end());
             i32 fill = KLU_CHUNK_ROWS;      // row units used in the open batch (full => start a new one)
             matched.assign(wc, 0);                                      // pieces of the open batch used by each column
             ucur.resize(wc);
             s0of.resize(wc);
-            for (i32 q = 0; q < wc; q++) ucur[q] = P.upd_ptr[k0 + q];
+            for (i32 q = 0; q < wc; q++) ucur[q] = P.upd_ptr[wcol[q]];
             auto open_batch = [&]() {
                 std::fill(matched.begin(), matched.end(), 0);
                 if (!P.seg_src.empty() && P.bseg_ptr.back() != (i64)P.seg_src.size()) {
@@ -582,16 +689,16 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
                 // ---- source block: up to snmax consecutive columns of one L supernode, each user column taking a suffix of it
                 const i32 j0 = srcs[si];
                 i32 g = 1;
-                while (g < snmax && si + g < srcs.size() && srcs[si + g] == j0 + g && nested[j0 + g - 1]) g++;
+                while (g < snmax && si + g < srcs.size() && srcs[si + g] == j0 + g && nested[j0 + g - 1] && P.early[j0 + g] == P.early[j0]) g++;
                 // users and their first source inside the block; the block is cut where a user would skip a column
                 // (cannot happen for a structurally closed pattern, checked all the same)
                 for (;;) {
                     bool ok = true;
                     for (i32 q = 0; q < wc && ok; q++) {
-                        const i32 c = k0 + q;
+                        const i32 c = wcol[q];
                         i64 u = ucur[q];
                         s0of[q] = -1;
-                        if (u >= P.upd_split[c] || P.upd_src[u] >= j0 + g) continue;
+                        if (u >= P.upd_split[c] || P.early[P.upd_src[u]] != P.early[j0] || P.upd_src[u] < j0 || P.upd_src[u] >= j0 + g) continue;
                         s0of[q] = P.upd_src[u] - j0;
                         for (i32 a = s0of[q]; a < g && ok; a++, u++) ok = u < P.upd_split[c] && P.upd_src[u] == j0 + a;
                     }
@@ -638,11 +745,35 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
                 }
                 for (i32 q = 0; q < wc; q++) if (s0of[q] >= 0) ucur[q] += g - s0of[q];
             }
-            for (i32 q = 0; q < wc; q++) if (ucur[q] != P.upd_split[k0 + q]) throw std::logic_error("klu plan: staged blocks do not cover a column");
+            for (i32 q = 0; q < wc; q++) if (ucur[q] != P.upd_split[wcol[q]]) throw std::logic_error("klu plan: staged blocks do not cover a column");
             if (P.bseg_ptr.back() != (i64)P.seg_src.size()) { P.bseg_ptr.push_back((i64)P.seg_src.size()); P.bpiece_ptr.push_back((i64)P.pc_j0.size()); }
             P.wbatch_ptr.push_back((i64)P.bseg_ptr.size() - 1);
         }
         P.pc_user_ptr.push_back((i64)P.pc_user_col.size());
+        if (getenv("B200S_KLU_DUMP_WAVES")) {
+            // per wave: first column, columns, batches, pieces, (piece, user) pairs, sum over batches of the largest per-column
+            // piece count (what the lock-step batch ring serialises), largest per-column total, multiply-adds
+            for (i32 w = 0; w < nw; w++) {
+                const i32 k0 = P.wave_col0[w], wc = P.wave_col0[w + 1] - k0;
+                i64 npc = 0, npu = 0, lock = 0; double fma = 0;
+                std::vector<i64> tot(wc, 0);
+                for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1]; bi++) {
+                    std::vector<i64> m(wc, 0);
+                    for (i64 pc = P.bpiece_ptr[bi]; pc < P.bpiece_ptr[bi + 1]; pc++) {
+                        npc++;
+                        for (i64 uq = P.pc_user_ptr[pc]; uq < P.pc_user_ptr[pc + 1]; uq++) {
+                            npu++; m[P.pc_user_col[uq]]++; tot[P.pc_user_col[uq]]++;
+                            fma += (double)(P.pc_g[pc] - P.pc_user_s0[uq]) * P.pc_nrows[pc];
+                        }
+                    }
+                    lock += *std::max_element(m.begin(), m.end());
+                }
+                fprintf(stderr, "wave %d col0 %d wc %d rows %d batches %lld pieces %lld users %lld lockstep %lld maxcol %lld fma %.0f\n", w, P.ne_cols[k0], wc,
+                        (int)P.wave_rows[w], (long long)(P.wbatch_ptr[w + 1] - P.wbatch_ptr[w]), (long long)npc, (long long)npu,
+                        (long long)lock, (long long)*std::max_element(tot.begin(), tot.end()), fma);
+                (void)k0;
+            }
+        }
         if (tdbg) {
             // multiply-adds by the number of source columns a (piece, user) pair applies at once
             double fm[KLU_SN_MAX + 1] = {0};
@@ -672,8 +803,9 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         P.wave_rowsrc.assign((size_t)nw * KLU_WAVE_ROWS, -1);
         P.wblob_ptr.assign(1, 0);
         for (i32 w = 0; w < nw; w++) {
-            const i32 k0 = P.wave_col0[w], k1 = P.wave_col0[w + 1];
-            for (i32 c = k0; c < k1; c++) {
+            const i32 k0 = P.wave_col0[w], k1 = P.wave_col0[w + 1];          // positions in ne_cols
+            for (i32 pq = k0; pq < k1; pq++) {
+                const i32 c = P.ne_cols[pq];
                 const i64 cb = P.cbeg[c];
                 const i32 len = (i32)(P.cbeg[c + 1] - cb);
                 if (P.col_roff[c] + len > KLU_WAVE_ROWS) continue;      // oversized single column: fallback kernel
@@ -687,7 +819,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             for (i64 bi = P.wbatch_ptr[w]; bi < P.wbatch_ptr[w + 1]; bi++)
                 for (i64 pc = P.bpiece_ptr[bi]; pc < P.bpiece_ptr[bi + 1]; pc++)
                     for (i64 uq = P.pc_user_ptr[pc]; uq < P.pc_user_ptr[pc + 1]; uq++) {
-                        const i32 q = P.pc_user_col[uq], c = k0 + q, s0 = P.pc_user_s0[uq], g = P.pc_g[pc];
+                        const i32 q = P.pc_user_col[uq], c = P.ne_cols[k0 + q], s0 = P.pc_user_s0[uq], g = P.pc_g[pc];
                         const i64 cb = P.cbeg[c], u0 = P.pc_user_upd[uq], ulast = u0 + (g - 1 - s0);
                         uint32_t* rec = P.bentry.data() + (size_t)bi * BST + (size_t)q * KLU_REC_U32;
                         if (rec[0] >= (uint32_t)KLU_MAXSEG) throw std::logic_error("klu plan: too many pieces in a batch record");
@@ -706,21 +838,23 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
             // in-wave blob
             std::vector<uint32_t> hdr(2 * KLU_WAVE_WARPS, 0), upd;
             std::vector<uint16_t> dst;
-            for (i32 c = k0; c < k1; c++) {
+            for (i32 pq = k0; pq < k1; pq++) {
+                const i32 c = P.ne_cols[pq];
                 const i64 cb = P.cbeg[c];
-                hdr[2 * (c - k0)] = (uint32_t)(upd.size() / 4);
+                hdr[2 * (pq - k0)] = (uint32_t)(upd.size() / 4);
                 for (i64 u = P.upd_split[c]; u < P.upd_end[c]; u++) {
                     {
                         const i32 j = P.upd_src[u];
                         const uint32_t srcrow0 = (uint32_t)(P.col_roff[j] + (P.lslot0[j] - P.cbeg[j]));   // first L row of the source in xs
-                        upd.push_back((uint32_t)(j - k0) | (srcrow0 << 8));
+                        if (P.ne_pos[j] < k0 || P.ne_pos[j] >= pq) throw std::logic_error("klu plan: in-wave source outside the wave");
+                        upd.push_back((uint32_t)(P.ne_pos[j] - k0) | (srcrow0 << 8));
                     }
                     upd.push_back((uint32_t)(P.upd_uslot[u] - cb));
                     upd.push_back((uint32_t)P.upd_cnt[u]);
                     upd.push_back((uint32_t)dst.size());
                     for (i32 r = 0; r < P.upd_cnt[u]; r++) dst.push_back((uint16_t)(P.dest[P.upd_dest[u] + r] - cb));
                 }
-                hdr[2 * (c - k0) + 1] = (uint32_t)(upd.size() / 4) - hdr[2 * (c - k0)];
+                hdr[2 * (pq - k0) + 1] = (uint32_t)(upd.size() / 4) - hdr[2 * (pq - k0)];
             }
             while (dst.size() % 8) dst.push_back(0);
             const size_t before = P.wblob.size();
@@ -771,9 +905,24 @@ int klu_plan_emulate(const KluSymbolic& S, const KluPlan& P, const double* Ax, d
     const size_t BST = (size_t)KLU_WAVE_WARPS * KLU_REC_U32 + KLU_CHUNK_ROWS;
     const i32 nw = (i32)P.wave_col0.size() - 1;
     (void)S;
+    // early columns, level by level, as k_klu_early does: scaled input values, the updates in list order, pivot, scaling
+    for (size_t e = 0; e < P.ecols.size(); e++) {
+        const i32 k = P.ecols[e];
+        const i64 cb = P.cbeg[k], ce = P.cbeg[k + 1];
+        for (i64 sl = cb; sl < ce; sl++) LU[sl] = P.slot_src[sl] >= 0 ? As[P.slot_src[sl]] : 0.0;
+        for (i64 u = P.upd_ptr[k]; u < P.upd_ptr[k + 1]; u++) {
+            if (!P.early[P.upd_src[u]]) return ST_INVALID;
+            const double ujk = LU[P.upd_uslot[u]];
+            for (i32 t = 0; t < P.upd_cnt[u]; t++) LU[P.dest[P.upd_dest[u] + t]] = std::fma(-LU[P.upd_lslot[u] + t], ujk, LU[P.dest[P.upd_dest[u] + t]]);
+        }
+        const double piv = LU[P.udiag_slot[k]];
+        if (!(std::fabs(piv) > 0.0)) status = ST_SINGULAR;
+        const double rpiv = 1.0 / piv;
+        for (i64 sl = P.lslot0[k]; sl < ce; sl++) LU[sl] *= rpiv;
+    }
     for (i32 w = 0; w < nw; w++) {
-        const i32 k0 = P.wave_col0[w], k1 = P.wave_col0[w + 1], wc = k1 - k0;
-        const i32 wrows = (i32)(P.cbeg[k1] - P.cbeg[k0]);
+        const i32 k0 = P.wave_col0[w], k1 = P.wave_col0[w + 1], wc = k1 - k0;       // positions in ne_cols
+        const i32 wrows = P.wave_rows[w];
         for (i32 r = 0; r < wrows; r++) {
             const i32 src = P.wave_rowsrc[(size_t)w * KLU_WAVE_ROWS + r];
             xs[r] = src >= 0 ? As[src] : 0.0;
@@ -785,7 +934,7 @@ int klu_plan_emulate(const KluSymbolic& S, const KluPlan& P, const double* Ax, d
             for (i32 q = 0; q < wc; q++) {
                 const uint32_t* rec = P.bentry.data() + (size_t)bi * BST + (size_t)q * KLU_REC_U32;
                 const uint16_t* dd = reinterpret_cast<const uint16_t*>(rec + KLU_REC_HDR);
-                double* x = xs.data() + P.col_roff[k0 + q];
+                double* x = xs.data() + P.col_roff[P.ne_cols[k0 + q]];
                 for (uint32_t k = 0; k < rec[0]; k++) {
                     const uint32_t w0 = rec[1 + 2 * k], w1 = rec[2 + 2 * k];
                     const i32 r0 = w0 & 0xff, nrows = (w0 >> 8) & 0xff, uloc = w0 >> 16;
@@ -814,7 +963,7 @@ int klu_plan_emulate(const KluSymbolic& S, const KluPlan& P, const double* Ax, d
         const uint32_t* updl = bl + 2 * KLU_WAVE_WARPS;
         const uint16_t* bdst = reinterpret_cast<const uint16_t*>(updl + 4 * nupd_wave);
         for (i32 q = 0; q < wc; q++) {
-            const i32 c = k0 + q;
+            const i32 c = P.ne_cols[k0 + q];
             double* x = xs.data() + P.col_roff[c];
             for (uint32_t ui = bl[2 * q]; ui < bl[2 * q] + bl[2 * q + 1]; ui++) {
                 const uint32_t w0 = updl[4 * ui];
@@ -832,7 +981,8 @@ int klu_plan_emulate(const KluSymbolic& S, const KluPlan& P, const double* Ax, d
                 for (i64 sl = P.lslot0[c] - cb; sl < P.cbeg[c + 1] - cb; sl++) x[sl] *= rpiv;
             }
         }
-        for (i32 r = 0; r < wrows; r++) LU[P.cbeg[k0] + r] = xs[r];
+        for (i32 rn = P.wrun_ptr[w]; rn < P.wrun_ptr[w + 1]; rn++)          // the wave's bulk stores
+            for (i32 r = 0; r < P.wrun_cnt[rn]; r++) LU[P.wrun_slot[rn] + r] = xs[P.wrun_row[rn] + r];
     }
     for (i32 k = P.spine0; k < n; k++) {          // dense trailing block: the updates the wave kernel left out, then the pivot
         for (i64 u = P.upd_end[k]; u < P.upd_ptr[k + 1]; u++) {

@@ -59,7 +59,22 @@ struct KluPlan {
     // warp per column, the column's slots held in shared memory (rows x 32 matrices).  A wave is bounded by the
     // warp count and by the shared-memory rows.  Updates of column k split at upd_split[k]: sources in earlier
     // waves (applied independently by every warp) / sources inside the wave (applied in pivot order).
-    std::vector<i32> wave_col0;       // nwaves+1
+    // EARLY columns: the columns in the first, wide levels of the dependency graph (row and column dependencies: level[k] >
+    // level[j] whenever U(j,k) != 0 or L(k,j) != 0) -- thousands of tiny, mutually independent columns per level.  They are
+    // factored level by level by k_klu_early (one warp per (column, group of 32 matrices), the whole GPU busy, HBM-bound)
+    // before the wave kernel runs; the waves below cover the remaining columns only (ne_cols, in pivot order).  Because the
+    // early set is closed under both kinds of dependency, an early source never needs a value produced by a later column, so
+    // every column's update list is ordered [early sources ascending, the others ascending].
+    std::vector<unsigned char> early;        // n
+    std::vector<i32> elevel_ptr;             // nelevels+1 -> ecols
+    std::vector<i32> ecols;                  // early columns grouped by level, each level sorted by column length
+    std::vector<i32> elevel_long;            // per level two indices into ecols: first column longer than KLU_EARLY_SHORT, than KLU_EARLY_MID
+    std::vector<i32> ne_cols;                // the other columns in pivot order; waves are ranges of POSITIONS in this list
+    std::vector<i32> ne_pos;                 // n: position of a column in ne_cols (-1 for early columns)
+    std::vector<i32> wave_rows;              // nwaves: shared-memory rows of the wave
+    std::vector<i32> wrun_ptr;               // nwaves+1 -> runs of consecutive columns = contiguous slots: one bulk store each
+    std::vector<i32> wrun_slot, wrun_row, wrun_cnt;     // first slot, first shared-memory row, rows
+    std::vector<i32> wave_col0;       // nwaves+1 (positions in ne_cols)
     std::vector<i32> wave_hasdep;     // nwaves: 1 when some column of the wave depends on another column of it
     std::vector<i32> col_roff;        // n: first shared-memory row of the column inside its wave
     std::vector<i64> upd_split;       // n
@@ -105,6 +120,9 @@ struct KluPlan {
     std::vector<i32> lslot0;          // per column: first L slot (below diagonal)
     std::vector<i32> fslot0;          // per column: first F slot
 };
+constexpr int KLU_EARLY_MINW = 256;   // a level is "wide" (early) when it has at least this many columns: its launch is then memory-bound, not latency-bound ...
+constexpr int KLU_EARLY_MAXLEN = 64;  // ... none longer than this (shared-memory scratch rows of one warp of k_klu_early)
+constexpr int KLU_EARLY_SHORT = 16, KLU_EARLY_MID = 32;   // length classes (shared-memory rows per warp) of k_klu_early
 constexpr int KLU_WAVE_WARPS = 16;   // columns (warps) per wave
 constexpr int KLU_WAVE_ROWS = 528;   // shared-memory rows for the columns of a wave (x 32 matrices x 8 B = 132 KiB)
 constexpr int KLU_META_INT4 = 72;    // per batch: header {nseg} + up to 64 segment descriptors, padded to 1152 B

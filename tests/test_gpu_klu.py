@@ -198,11 +198,14 @@ def _variety(case):
     return A.tocsc()
 
 
+@pytest.mark.parametrize("early_minw", [None, 4])
 @pytest.mark.parametrize("case", range(6))
-def test_structure_variety_single_and_batched(klu, case):
+def test_structure_variety_single_and_batched(klu, case, early_minw, monkeypatch):
     """patterns the reference matrices do not cover: many BTF blocks with F entries, columns longer than the shared-memory
     wave (level-schedule kernel), long dense tails, 1 x 1, permuted diagonals, arrow -- LU identity, both solves, and a
     perturbed batch against SuperLU"""
+    if early_minw is not None:      # the level-by-level early-column kernel (k_klu_early) on these small patterns as well
+        monkeypatch.setenv("B200S_KLU_EARLY_MINW", str(early_minw))
     A = _variety(case)
     A.sort_indices()
     n = A.shape[0]

@@ -431,13 +431,16 @@ def _synthetic_unsym(kind, seed=0):
     raise ValueError(kind)
 
 
+@pytest.mark.parametrize("early_minw", [None, 8])
 @pytest.mark.parametrize("name", ["ACTIVSg2000", "bp_800", "bcsstk13", "banded_dense_tail", "blocks2x2", "random"])
-def test_klu_wave_plan_replayed_on_the_host_matches_the_pivoting_factorization(name):
+def test_klu_wave_plan_replayed_on_the_host_matches_the_pivoting_factorization(name, early_minw, monkeypatch):
     """The wave schedule the CUDA refactorization kernel executes (supernode source blocks -> staged pieces -> per-column
     records, in-wave updates, dense trailing block) replayed by the host interpreter b200s_klu_plan_emulate_host: same L, U,
     F and row scales as the pivoting Gilbert-Peierls factorization of the same matrix, and -- with perturbed values -- as an
     independent dense check P R^-1 A Q = L U + F."""
     from conftest import load_matrix
+    if early_minw is not None:      # narrower "wide level" threshold: the early-column path (k_klu_early's tables) on small patterns too
+        monkeypatch.setenv("B200S_KLU_EARLY_MINW", str(early_minw))
     A = (load_matrix(name) if name[0].isupper() or name.startswith("b") and name[1] in "pc" else _synthetic_unsym(name)).tocsc()
     A.sort_indices()
     n = A.shape[0]
@@ -446,7 +449,11 @@ def test_klu_wave_plan_replayed_on_the_host_matches_the_pivoting_factorization(n
     N = L.vp(); assert fn["b200s_klu_pivot_host"](S, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(N)) == 0
     inf = L.KluInfo(); fn["b200s_klu_info"](N, C.byref(inf))
     v = L.KluPlanView(); fn["b200s_klu_plan_view"](N, C.byref(v))
-    if v.nbatches == 0 and v.nwaves <= 1:       # pattern outside the wave kernel's budget: the level-schedule kernel serves it
+    if name == "ACTIVSg2000":
+        assert v.nearly > 2000 and v.nearly_levels >= 4
+    if early_minw is not None and name in ("bp_800", "bcsstk13", "blocks2x2"):
+        assert v.nearly > 0
+    if not v.wave_ok:       # pattern outside the wave kernel's budget: the level-schedule kernel serves it
         assert fn["b200s_klu_plan_emulate_host"](N, L.ptr_f64(vx), None, None, None, None) == L.INVALID
         fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
         return
