@@ -372,7 +372,6 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     __shared__ unsigned long long full_bar[KLU_STAGES], empty_bar[KLU_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x * 32 + lane;
-    double* lu = LU + (long long)blockIdx.x * P.gstride + lane;
     const double* lug = LU + (long long)blockIdx.x * P.gstride;   // group base for the cooperative copies
     const double* axg = Axs + (long long)blockIdx.x * 32;
     int bad = 0;
@@ -469,7 +468,7 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     asm volatile("bar.sync %0, %1;" ::"n"(KLU_CONS_BAR), "n"(KLU_WAVE_WARPS * 32) : "memory");
     for (int w = 0; w < W.nwaves; w++) {
         if (dbg) tA = clock64();
-        const int k0 = n_k0, wc = n_k1 - n_k0;
+        const int wc = n_k1 - n_k0;
         // team = the warps that share one column: floor(16 / wc) warps
         const int T = team_size(wc), col = warp / T, sub = warp - col * T;
         const bool active = col < wc;
@@ -1207,7 +1206,7 @@ public:
     const KluEarlyCol* d_ecols = nullptr;
     const int4* d_eupd = nullptr;
     const unsigned short* d_edest = nullptr;
-    std::vector<int> h_elevel_ptr, h_elevel_long;
+    std::vector<int> h_elevel_ptr;
     long long* d_rowptr = nullptr;
     long long nslots = 0, nnzA = 0;
     int n = 0;
@@ -1323,11 +1322,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
             if ((rc = up(&d_ecols, ec))) return rc;
             if ((rc = up(&d_eupd, eu))) return rc;
             if ((rc = up(&d_edest, ed))) return rc;
-            h_elevel_ptr = P.elevel_ptr; h_elevel_long = P.elevel_long;
-            CUDA_TRY(cudaFuncSetAttribute(k_klu_early<KLU_EARLY_MAXLEN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(KLU_EARLY_MAXLEN * 4 * 256)));
-            CUDA_TRY(cudaFuncSetAttribute(k_klu_early<KLU_EARLY_MID, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(KLU_EARLY_MID * 8 * 256)));
+            h_elevel_ptr = P.elevel_ptr;
         }
         static_assert(sizeof(unsigned) == sizeof(uint32_t), "plan tables are uploaded as they are");
         if ((rc = up(&WD.bentry, P.bentry))) return rc;       // the largest table (11.5 MB on ACTIVSg2000): no staging copy
@@ -1403,23 +1398,12 @@ int KluDevice::enqueue_refactor(const double* dv, long long ldv, cudaEvent_t aft
             k_klu_scatter<<<148 * 8, 256, 0, stream>>>(d_slot_src, d_slot_row, lu_slots, nslots, Bp, dAxt, dRs, dLU, 1, nslots * 32);
         CUDA_TRY(cudaEventRecord(ev[4], stream));
         int early_launches = 0;
-        for (size_t l = 0; l + 1 < h_elevel_ptr.size(); l++) {          // early columns, level by level, by length class
-            const int c0 = h_elevel_ptr[l], cm = h_elevel_long[2 * l], cm2 = h_elevel_long[2 * l + 1], c1 = h_elevel_ptr[l + 1];
-            if (cm > c0) {
-                const dim3 grid((unsigned)((cm - c0 + 7) / 8), (unsigned)(Bp / 32));
-                k_klu_early<KLU_EARLY_SHORT, 8><<<grid, 8 * 32, KLU_EARLY_SHORT * 8 * 256, stream>>>(d_ecols, c0, cm, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
-                early_launches++;
-            }
-            if (cm2 > cm) {
-                const dim3 grid((unsigned)((cm2 - cm + 7) / 8), (unsigned)(Bp / 32));
-                k_klu_early<KLU_EARLY_MID, 8><<<grid, 8 * 32, KLU_EARLY_MID * 8 * 256, stream>>>(d_ecols, cm, cm2, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
-                early_launches++;
-            }
-            if (c1 > cm2) {
-                const dim3 grid((unsigned)((c1 - cm2 + 3) / 4), (unsigned)(Bp / 32));
-                k_klu_early<KLU_EARLY_MAXLEN, 4><<<grid, 4 * 32, KLU_EARLY_MAXLEN * 4 * 256, stream>>>(d_ecols, cm2, c1, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
-                early_launches++;
-            }
+        for (size_t l = 0; l + 1 < h_elevel_ptr.size(); l++) {          // early columns, level by level
+            const int c0 = h_elevel_ptr[l], c1 = h_elevel_ptr[l + 1];
+            if (c1 == c0) continue;
+            const dim3 grid((unsigned)((c1 - c0 + 7) / 8), (unsigned)(Bp / 32));
+            k_klu_early<KLU_EARLY_MAXLEN, 8><<<grid, 8 * 32, KLU_EARLY_MAXLEN * 8 * 256, stream>>>(d_ecols, c0, c1, d_eupd, d_edest, d_slot_src, nslots * 32, Bp, dAxt, dLU, d_status);
+            early_launches++;
         }
         if (WD.nwaves > 0)
             k_klu_refactor_wave<<<Bp / 32, (KLU_WAVE_WARPS + 1) * 32, KLU_WAVE_SMEM, stream>>>(PD, WD, Bp, dAxt, dLU, d_status, ddbg);

@@ -483,7 +483,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
     // ---- early columns: the wide first levels of the dependency graph (see KluPlan::early)
     P.early.assign(n, 0);
     P.elevel_ptr.assign(1, 0);
-    P.ecols.clear(); P.elevel_long.clear();
+    P.ecols.clear();
     {
         const char* ev = getenv("B200S_KLU_EARLY");
         const bool enabled = !(ev && atoi(ev) == 0);
@@ -498,36 +498,37 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         }
         i32 nl = 0;
         for (i32 k = 0; k < n; k++) nl = std::max(nl, lv[k] + 1);
-        std::vector<i32> cnt(nl, 0), mlen(nl, 0);
+        std::vector<i32> cnt(nl, 0);
         for (i32 k = 0; k < n; k++) {
-            if (k >= P.spine0) { mlen[lv[k]] = KLU_EARLY_MAXLEN + 1; continue; }       // the dense block's columns are never early
+            if (k >= P.spine0 || P.cbeg[k + 1] - P.cbeg[k] > KLU_EARLY_MAXLEN) continue;       // long columns and the dense block's are never early
             cnt[lv[k]]++;
-            mlen[lv[k]] = std::max<i32>(mlen[lv[k]], (i32)(P.cbeg[k + 1] - P.cbeg[k]));
         }
         i32 lmax = -1, total = 0;
         const i32 minw = getenv("B200S_KLU_EARLY_MINW") ? atoi(getenv("B200S_KLU_EARLY_MINW")) : KLU_EARLY_MINW;
         const i32 maxlev = getenv("B200S_KLU_EARLY_LEVELS") ? atoi(getenv("B200S_KLU_EARLY_LEVELS")) : 0x7fffffff;
-        while (enabled && lmax + 1 < nl && lmax + 1 < maxlev && cnt[lmax + 1] >= minw && mlen[lmax + 1] <= KLU_EARLY_MAXLEN) { lmax++; total += cnt[lmax]; }
+        while (enabled && lmax + 1 < nl && lmax + 1 < maxlev && cnt[lmax + 1] >= minw) { lmax++; total += cnt[lmax]; }
         if (total < 8 * minw) lmax = -1;          // not worth the extra launches
         if (tdbg) fprintf(stderr, "[b200s klu plan] dependency levels %d, early levels %d with %d of %d columns\n", nl, lmax + 1, lmax >= 0 ? total : 0, n);
         if (lmax >= 0) {
-            for (i32 k = 0; k < n; k++) P.early[k] = lv[k] <= lmax;
+            // early = in a wide level, short enough for the warp's scratch, and depending (by column and by row) on early
+            // columns only -- the set stays closed under both kinds of dependency
+            std::vector<unsigned char> rowdep_late(n, 0);       // row k receives an L entry from a late column
+            for (i32 k = 0; k < n; k++) {
+                bool e = lv[k] <= lmax && k < P.spine0 && P.cbeg[k + 1] - P.cbeg[k] <= KLU_EARLY_MAXLEN && !rowdep_late[k];
+                for (i64 q = N.Up[k]; e && q < N.Up[k + 1] - 1; q++) e = P.early[N.Ui[q]] != 0;
+                P.early[k] = e;
+                if (!e) for (i64 q = N.Lp[k] + 1; q < N.Lp[k + 1]; q++) rowdep_late[N.Li[q]] = 1;
+            }
             P.elevel_ptr.assign(lmax + 2, 0);
             for (i32 k = 0; k < n; k++) if (P.early[k]) P.elevel_ptr[lv[k] + 1]++;
             for (i32 l = 0; l <= lmax; l++) P.elevel_ptr[l + 1] += P.elevel_ptr[l];
             P.ecols.resize(P.elevel_ptr[lmax + 1]);
             std::vector<i32> pos(P.elevel_ptr.begin(), P.elevel_ptr.end() - 1);
             for (i32 k = 0; k < n; k++) if (P.early[k]) P.ecols[pos[lv[k]]++] = k;
-            P.elevel_long.assign(2 * (lmax + 1), 0);
             for (i32 l = 0; l <= lmax; l++) {
                 i32* b = P.ecols.data() + P.elevel_ptr[l];
                 i32* e = P.ecols.data() + P.elevel_ptr[l + 1];
                 std::stable_sort(b, e, [&](i32 a, i32 c) { return P.cbeg[a + 1] - P.cbeg[a] < P.cbeg[c + 1] - P.cbeg[c]; });
-                i32* m = b;
-                while (m < e && P.cbeg[*m + 1] - P.cbeg[*m] <= KLU_EARLY_SHORT) m++;
-                P.elevel_long[2 * l] = (i32)(m - P.ecols.data());
-                while (m < e && P.cbeg[*m + 1] - P.cbeg[*m] <= KLU_EARLY_MID) m++;
-                P.elevel_long[2 * l + 1] = (i32)(m - P.ecols.data());
             }
             // update lists: early sources first (both parts keep their ascending order)
             std::vector<i32> t_src, t_us, t_ls, t_cnt; std::vector<i64> t_dst;
@@ -631,7 +632,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
                 P.dense_meta.clear(); P.dense_slot.clear();
                 for (i32 k = 0; k < n; k++) P.upd_end[k] = P.upd_ptr[k + 1];
                 std::fill(P.early.begin(), P.early.end(), 0);
-                P.elevel_ptr.assign(1, 0); P.ecols.clear(); P.elevel_long.clear();
+                P.elevel_ptr.assign(1, 0); P.ecols.clear();
             }
         }
         const i32 nw = (i32)P.wave_col0.size() - 1;

@@ -68,7 +68,6 @@ struct KluPlan {
     std::vector<unsigned char> early;        // n
     std::vector<i32> elevel_ptr;             // nelevels+1 -> ecols
     std::vector<i32> ecols;                  // early columns grouped by level, each level sorted by column length
-    std::vector<i32> elevel_long;            // per level two indices into ecols: first column longer than KLU_EARLY_SHORT, than KLU_EARLY_MID
     std::vector<i32> ne_cols;                // the other columns in pivot order; waves are ranges of POSITIONS in this list
     std::vector<i32> ne_pos;                 // n: position of a column in ne_cols (-1 for early columns)
     std::vector<i32> wave_rows;              // nwaves: shared-memory rows of the wave
@@ -120,9 +119,8 @@ struct KluPlan {
     std::vector<i32> lslot0;          // per column: first L slot (below diagonal)
     std::vector<i32> fslot0;          // per column: first F slot
 };
-constexpr int KLU_EARLY_MINW = 256;   // a level is "wide" (early) when it has at least this many columns: its launch is then memory-bound, not latency-bound ...
-constexpr int KLU_EARLY_MAXLEN = 64;  // ... none longer than this (shared-memory scratch rows of one warp of k_klu_early)
-constexpr int KLU_EARLY_SHORT = 16, KLU_EARLY_MID = 32;   // length classes (shared-memory rows per warp) of k_klu_early
+constexpr int KLU_EARLY_MINW = 128;   // a level is "wide" (early) when it has at least this many columns: its launch is then memory-bound, not latency-bound ...
+constexpr int KLU_EARLY_MAXLEN = 16;  // ... and a column is early only up to this length (shared-memory scratch rows of one warp of k_klu_early)
 constexpr int KLU_WAVE_WARPS = 16;   // columns (warps) per wave
 constexpr int KLU_WAVE_ROWS = 528;   // shared-memory rows for the columns of a wave (x 32 matrices x 8 B = 132 KiB)
 constexpr int KLU_META_INT4 = 72;    // per batch: header {nseg} + up to 64 segment descriptors, padded to 1152 B
