@@ -16,6 +16,8 @@ namespace b200s {
 class KluDevice;
 KluDevice* klu_device_create(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S, int device, int* status);
 void klu_device_destroy(KluDevice* d);
+int klu_device_init_refactor(KluDevice* d, const KluPlan& P);
+int klu_device_load_host_factor(KluDevice* d, const double* slots_host, const double* rs_host);
 int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status);
 int klu_device_refactor_begin(KluDevice* d, const double* vals, long long batch, long long ldv);
 int klu_device_refactor_end(KluDevice* d, int* status);
@@ -79,7 +81,9 @@ static b200s_status factor_impl(b200s_klu_sym* S, const b200s_int* colptr, const
         int st = klu_factor(N->S, val, N->N);
         if (tdbg) fprintf(stderr, "[b200s klu] pivoting factorization (host) %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
         if (st != ST_OK) { delete N; return (b200s_status)st; }
-        klu_build_plan(N->S, N->N, N->P);
+        // with a device, klu.numeric() serves its own matrix from the values of the pivot search and only needs the slot
+        // layout; the refactorization tables are built when a batch is first refactored (ensure_refactor_tables)
+        klu_build_plan(N->S, N->N, N->P, !with_device || getenv("B200S_KLU_EAGER_PLAN") != nullptr);
     } catch (const std::bad_alloc&) {
         delete N; return B200S_OUT_OF_MEMORY;
     } catch (const std::exception& e) {
@@ -93,12 +97,20 @@ static b200s_status factor_impl(b200s_klu_sym* S, const b200s_int* colptr, const
         N->dev = klu_device_create(N->P, N->N, N->S, N->device, &st);
         if (!N->dev) { delete N; return (b200s_status)st; }
         auto td1 = std::chrono::steady_clock::now();
-        int mst = 0;
-        st = klu_device_refactor(N->dev, val, false, 1, S->S.nnz, &mst);
-        if (tdbg) fprintf(stderr, "[b200s klu] device plan upload %.1f ms, refactorization of the batch of one %.1f ms\n",
+        {
+            // the factor of THIS matrix: the values the pivoting factorization just computed, in the plan's slot layout
+            const KluPlan& P = N->P; const KluNumeric& M = N->N;
+            std::vector<double> slots((size_t)std::max<i64>(P.nslots, 1), 0.0);
+            for (i32 k = 0; k < n; k++) {
+                for (i64 p = M.Up[k]; p < M.Up[k + 1]; p++) slots[P.cbeg[k] + (p - M.Up[k])] = M.Ux[p];
+                for (i64 p = M.Lp[k] + 1; p < M.Lp[k + 1]; p++) slots[P.lslot0[k] + (p - M.Lp[k] - 1)] = M.Lx[p];
+                for (i64 p = M.Fp[k]; p < M.Fp[k + 1]; p++) slots[P.fslot0[k] + (p - M.Fp[k])] = M.Fx[p];
+            }
+            st = klu_device_load_host_factor(N->dev, slots.data(), M.Rs.data());
+        }
+        if (tdbg) fprintf(stderr, "[b200s klu] device tables %.1f ms, factor values to the device %.1f ms\n",
                           std::chrono::duration<double, std::milli>(td1 - td0).count(),
                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td1).count());
-        if (st == ST_OK && mst != 0) st = mst;
         if (st != ST_OK) { klu_device_destroy(N->dev); delete N; return (b200s_status)st; }
     }
     *out = N;
@@ -122,6 +134,21 @@ b200s_status b200s_klu_extract_host(const b200s_klu_num* N, double* Lx, double* 
     return B200S_OK;
 }
 
+// update lists + kernel schedules of the refactorization, built (and uploaded) the first time they are needed
+static b200s_status ensure_refactor_tables(b200s_klu_num* N) {
+    if (N->P.have_refactor) return B200S_OK;
+    B200S_NVTX("klu_refactor_tables");
+    try {
+        klu_build_plan(N->S, N->N, N->P, true);
+    } catch (const std::bad_alloc&) {
+        return B200S_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        set_last_error(e.what()); return B200S_INVALID;
+    }
+    if (N->dev) return (b200s_status)klu_device_init_refactor(N->dev, N->P);
+    return B200S_OK;
+}
+
 static b200s_status refactor_impl(b200s_klu_num* N, const double* vals, bool on_device, b200s_int batch, b200s_int ldv,
                                   int* status_per_matrix) {
     B200S_NVTX("refactor_impl");
@@ -129,6 +156,7 @@ static b200s_status refactor_impl(b200s_klu_num* N, const double* vals, bool on_
     if (N->N.n == 0 || batch == 0) return B200S_OK;
     if (!vals || ldv < N->S.nnz || batch > 0x7fffff00) return B200S_INVALID;
     if (!N->dev) return B200S_NO_DEVICE;
+    if (b200s_status st = ensure_refactor_tables(N)) return st;
     return (b200s_status)klu_device_refactor(N->dev, vals, on_device, batch, ldv, status_per_matrix);
 }
 b200s_status b200s_klu_refactor_batch(b200s_klu_num* N, const double* vals, b200s_int batch, b200s_int ldv, int* status_per_matrix) {
@@ -144,6 +172,7 @@ b200s_status b200s_klu_refactor_batch_begin(b200s_klu_num* N, const double* vals
     if (N->N.n == 0 || batch == 0) return B200S_OK;
     if (!vals || ldv < N->S.nnz || batch > 0x7fffff00) return B200S_INVALID;
     if (!N->dev) return B200S_NO_DEVICE;
+    if (b200s_status st = ensure_refactor_tables(N)) return st;
     return (b200s_status)klu_device_refactor_begin(N->dev, vals, batch, ldv);
 }
 b200s_status b200s_klu_refactor_batch_end(b200s_klu_num* N, int* status_per_matrix) {
@@ -242,6 +271,7 @@ b200s_status b200s_klu_extract_batch(b200s_klu_num* N, b200s_int b, double* Lx, 
  * the Python mirrors calls it and it is not a factorization path. */
 b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* val, double* Lx, double* Ux, double* Fx, double* Rs) {
     if (!N || !val) return B200S_INVALID;
+    if (b200s_status st0 = ensure_refactor_tables(const_cast<b200s_klu_num*>(N))) return st0;       // (lazily built)
     const i32 n = N->N.n;
     std::vector<double> slots((size_t)std::max<i64>(N->P.nslots, 1)), rs((size_t)std::max<i32>(n, 1));
     int st;
@@ -262,6 +292,7 @@ b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* v
 
 b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* v) {
     if (!N || !v) return B200S_INVALID;
+    if (b200s_status st0 = ensure_refactor_tables(const_cast<b200s_klu_num*>(N))) return st0;       // (lazily built)
     const KluPlan& P = N->P;
     v->n = P.n; v->nlevels = P.nlevels; v->nslots = P.nslots; v->lu_slots = P.lu_slots; v->nnz_A = P.nnzA;
     v->nupd = (b200s_int)P.upd_uslot.size(); v->ndest = (b200s_int)P.dest.size();

@@ -1248,6 +1248,9 @@ public:
     int ensure_batch(int b);
     int enqueue_refactor(const double* dv, long long ldv, cudaEvent_t after_transpose);
     int refactor(const double* vals, bool on_device, long long batch_, long long ldv, int* status_host);
+    int init_refactor(const KluPlan& P);
+    int load_host_factor(const double* slots_host, const double* rs_host);
+    bool refactor_ready = false;
     int refactor_begin(const double* vals, long long batch_, long long ldv);
     int refactor_end(int* status_host);
     int solve(int trans, double* B, long long nrhs, long long ldB, long long batch_, bool on_device);
@@ -1258,15 +1261,35 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     n = P.n; nslots = P.nslots; nnzA = P.nnzA;
-    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(pool_malloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; cudaMemset(ddbg, 0, (8 + 2 * P.wave_col0.size()) * sizeof(long long)); }
     int rc;
     PD.n = P.n; PD.nlevels = P.nlevels; PD.gstride = (long long)P.nslots * 32;
-    std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), updp(P.upd_ptr.begin(), P.upd_ptr.end()),
-        updd(P.upd_dest.begin(), P.upd_dest.end()), rowptr(P.rowptr.begin(), P.rowptr.end());
-    use_wave = P.wave_ok && P.max_col_len <= KLU_WAVE_ROWS;
+    std::vector<long long> cbeg(P.cbeg.begin(), P.cbeg.end()), rowptr(P.rowptr.begin(), P.rowptr.end());
     if ((rc = up(&PD.udiag_slot, P.udiag_slot))) return rc;
     if ((rc = up(&PD.lslot0, P.lslot0))) return rc;
     if ((rc = up(&PD.cbeg, cbeg))) return rc;
+    lu_slots = P.lu_slots;
+    const int* tmp_i; const long long* tmp_l;
+    if ((rc = up(&tmp_i, P.slot_src))) return rc; d_slot_src = (int*)tmp_i;
+    if ((rc = up(&tmp_i, P.slot_row))) return rc; d_slot_row = (int*)tmp_i;
+    if ((rc = up(&tmp_i, P.rowent))) return rc; d_rowent = (int*)tmp_i;
+    if ((rc = up(&tmp_l, rowptr))) return rc; d_rowptr = (long long*)tmp_l;
+    if ((rc = up(&d_Pnum, N.Pnum))) return rc;
+    if ((rc = up(&d_Q, S.Q))) return rc;
+    hP = &P; hN = &N; hS = &S;       // the solve schedules are built at the first solve of each kind (ensure_solve_levels)
+    if (P.have_refactor) return init_refactor(P);
+    return ST_OK;
+}
+
+// The tables of the refactorization kernels (update lists or wave schedule, early columns, dense block).  Separate from init():
+// klu.numeric() takes the values of its factor from the host pivot search, so a caller that never refactors a batch (one
+// matrix, klu.linsolve) never pays for building and uploading these tables.
+int KluDevice::init_refactor(const KluPlan& P) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (refactor_ready) return ST_OK;
+    int rc;
+    if (getenv("B200S_KLU_DEBUG")) { CUDA_TRY(pool_malloc((void**)&ddbg, (8 + 2 * P.wave_col0.size()) * sizeof(long long))); owned.push_back(ddbg); h_wave_col0 = P.wave_col0; cudaMemset(ddbg, 0, (8 + 2 * P.wave_col0.size()) * sizeof(long long)); }
+    std::vector<long long> updp(P.upd_ptr.begin(), P.upd_ptr.end()), updd(P.upd_dest.begin(), P.upd_dest.end());
+    use_wave = P.wave_ok && P.max_col_len <= KLU_WAVE_ROWS;
     if (!use_wave) {          // update lists and level schedule: only the level-schedule kernel reads them
         if ((rc = up(&PD.level_ptr, P.level_ptr))) return rc;
         if ((rc = up(&PD.level_cols, P.level_cols))) return rc;
@@ -1277,7 +1300,6 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
         if ((rc = up(&PD.upd_ptr, updp))) return rc;
         if ((rc = up(&PD.upd_dest, updd))) return rc;
     }
-    lu_slots = P.lu_slots;
     {
         WD.nwaves = (int)P.wave_col0.size() - 1;
         if ((rc = up(&WD.wave_col0, P.wave_col0))) return rc;
@@ -1343,14 +1365,40 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
             CUDA_TRY(cudaFuncSetAttribute(k_klu_refactor_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KLU_WAVE_SMEM));
         }
     }
-    const int* tmp_i; const long long* tmp_l;
-    if ((rc = up(&tmp_i, P.slot_src))) return rc; d_slot_src = (int*)tmp_i;
-    if ((rc = up(&tmp_i, P.slot_row))) return rc; d_slot_row = (int*)tmp_i;
-    if ((rc = up(&tmp_i, P.rowent))) return rc; d_rowent = (int*)tmp_i;
-    if ((rc = up(&tmp_l, rowptr))) return rc; d_rowptr = (long long*)tmp_l;
-    if ((rc = up(&d_Pnum, N.Pnum))) return rc;
-    if ((rc = up(&d_Q, S.Q))) return rc;
-    hP = &P; hN = &N; hS = &S;       // the solve schedules are built at the first solve of each kind (ensure_solve_levels)
+    // a batch buffer allocated before the tables existed has no storage for the dense trailing block yet
+    if (spine_nd > 0 && Bp > 0 && !dD) CUDA_TRY(pool_malloc((void**)&dD, (size_t)ndp * Bp * sizeof(double)));
+    refactor_ready = true;
+    return ST_OK;
+}
+
+// lane-replicated load of one factor computed on the host (the pivot search of klu.numeric): slot v of every matrix of the
+// first group = h[v], row scales likewise.  The device then serves solve / extract exactly as after a refactorization.
+__global__ void k_klu_load_one(const double* __restrict__ h, long long nslots, const double* __restrict__ hrs, int n, int Bp,
+                               double* __restrict__ LU, double* __restrict__ Rs) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long v = t >> 5;
+    const int lane = (int)(t & 31);
+    if (v < nslots) LU[v * 32 + lane] = h[v];
+    if (v < n) Rs[v * Bp + lane] = hrs[v];
+}
+
+int KluDevice::load_host_factor(const double* slots_host, const double* rs_host) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (n == 0) return ST_OK;
+    if (npending > 0) return ST_INVALID;
+    int rc = ensure_batch(1);
+    if (rc) return rc;
+    double* tmp = nullptr;
+    CUDA_TRY(pool_malloc((void**)&tmp, (size_t)(nslots + n) * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(tmp, slots_host, (size_t)nslots * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(tmp + nslots, rs_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, Bp * sizeof(int), stream));
+    const long long threads = std::max<long long>(nslots, n) * 32;
+    k_klu_load_one<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(tmp, nslots, tmp + nslots, n, Bp, dLU, dRs);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    pool_free(tmp);
+    batch = 1;
     return ST_OK;
 }
 
@@ -1434,6 +1482,7 @@ int KluDevice::refactor(const double* vals, bool on_device, long long batch_, lo
     // batches begun with refactor_begin still own the staging buffers and the factor storage: the blocking call may
     // neither grow nor free them (the caching allocator would hand live blocks to another handle)
     if (npending > 0) { set_last_error("refactor_batch: batches begun with refactor_batch_begin are still in flight, call refactor_batch_end first"); return ST_INVALID; }
+    if (!refactor_ready) { set_last_error("refactorization tables have not been built"); return ST_INVALID; }
     int rc = ensure_batch((int)batch_);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ev[0], stream));
@@ -1488,6 +1537,7 @@ int KluDevice::refactor_begin(const double* vals, long long batch_, long long ld
     CUDA_TRY(cudaSetDevice(device));
     if (batch_ <= 0 || n == 0) return ST_OK;
     if (npending >= 2) { set_last_error("refactor_batch_begin: two batches already in flight, call refactor_batch_end first"); return ST_INVALID; }
+    if (!refactor_ready) { set_last_error("refactorization tables have not been built"); return ST_INVALID; }
     const int bp = ((int)batch_ + 31) & ~31;
     if (npending > 0 && bp > Bp) { set_last_error("refactor_batch_begin: a larger batch needs the batches in flight to finish first"); return ST_INVALID; }
     int rc = ensure_batch((int)batch_);
@@ -1592,6 +1642,8 @@ KluDevice* klu_device_create(const KluPlan& P, const KluNumeric& N, const KluSym
     return d;
 }
 void klu_device_destroy(KluDevice* d) { delete d; }
+int klu_device_init_refactor(KluDevice* d, const KluPlan& P) { return d->init_refactor(P); }
+int klu_device_load_host_factor(KluDevice* d, const double* slots_host, const double* rs_host) { return d->load_host_factor(slots_host, rs_host); }
 int klu_device_refactor(KluDevice* d, const double* vals, bool on_device, long long batch, long long ldv, int* status) {
     return d->refactor(vals, on_device, batch, ldv, status);
 }

@@ -347,7 +347,7 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
     return status;
 }
 
-void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
+void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P, bool refactor_tables) {
     const i32 n = S.n;
     const bool tdbg = getenv("B200S_DEBUG") != nullptr;
     auto tlast = std::chrono::steady_clock::now();
@@ -385,7 +385,8 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
     // row position (pivotal) -> slot inside the current column
     std::vector<i32> slot_of_row(n, -1), pinvnum(n);
     for (i32 k = 0; k < n; k++) pinvnum[N.Pnum[k]] = k;
-    {
+    P.have_refactor = refactor_tables;
+    if (refactor_tables) {
         // one destination per multiply-add of the factorization, one update per off-diagonal U entry
         const size_t nupd = (size_t)(N.Up[n] - n);
         P.dest.reserve((size_t)(N.flops / 2) + 16);
@@ -414,6 +415,7 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         }
         // updates of column k: for each U entry (j,k), j < k ascending, L(:,j) below the diagonal
         P.upd_ptr.push_back((i64)P.upd_uslot.size());
+        if (refactor_tables)
         for (i64 p = N.Up[k]; p < N.Up[k + 1] - 1; p++) {
             const i32 j = N.Ui[p];
             const i64 cnt = N.Lp[j + 1] - N.Lp[j] - 1;
@@ -442,6 +444,18 @@ void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P) {
         for (i64 p = 0; p < S.nnz; p++) P.rowent[pos[pinvnum[S.Ai[p]]]++] = (i32)p;
     }
     lap("slots + update lists");
+    {
+        // number of levels of the column dependency graph (column k depends on every column j with U(j,k) != 0)
+        std::vector<i32> lvq(n, 0);
+        P.nlevels = 0;
+        for (i32 k = 0; k < n; k++) {
+            i32 l = 0;
+            for (i64 p = N.Up[k]; p < N.Up[k + 1] - 1; p++) l = std::max(l, lvq[N.Ui[p]] + 1);
+            lvq[k] = l;
+            P.nlevels = std::max(P.nlevels, l + 1);
+        }
+    }
+    if (!refactor_tables) return;
     // ---- dense trailing block: the largest nd <= KLU_DENSE_MAX (multiple of 16) inside the last BTF block whose
     // L+U pattern restricted to the last nd rows/columns is at least 30 % dense
     P.upd_end.assign(n, 0);

@@ -108,6 +108,7 @@ struct KluPlan {
     std::vector<uint32_t> wblob;
     i32 max_col_len = 0;
     bool wave_ok = true;              // false: pattern outside the wave kernel's budget (level-schedule kernel instead)
+    bool have_refactor = false;       // the update lists and kernel schedules below the slot layout have been built
     // dense trailing block ("spine"): the last spine_nd columns are nearly dense after fill (76 % of the work of a
     // power-flow Jacobian).  The wave kernel applies to them only the updates from columns < spine0; the block itself
     // is then factored per matrix by a dense tensor-core LU (k_klu_dense_lu).  spine_nd = 0: disabled.
@@ -137,7 +138,10 @@ constexpr long long KLU_WAVE_MAX_STAGED = 8ll << 20;   // staged rows over all w
 // 4096 x ACTIVSg2000, wave kernel + dense block per batch: 160 columns, one CTA per SM 5.6 + 1.7 ms; 112: 6.1 + 1.05 ms;
 // 96: 6.3 + 0.84 ms; 80: 6.7 + 0.64 ms)
 constexpr int KLU_DENSE_MAX = 112, KLU_DENSE_META = 1 + (KLU_DENSE_MAX + 31) / 32;
-void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan);
+// refactor_tables = false: only the slot layout (what loading host values, extraction and the solves need) and the level
+// count; the update lists and the schedules of the refactorization kernels are added by a second call with true (the slot
+// layout is a pure function of (S, N): both calls agree).
+void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& plan, bool refactor_tables = true);
 // Host interpreter of the WAVE schedule (the tables k_klu_refactor_wave executes: gather, staged pieces, in-wave updates,
 // dense trailing block) for one matrix.  Verification of the host-built plan in CPU tests; not a factorization path of the
 // product.  Ax: the caller's values; out: LU[nslots] (U above diagonal, pivot, L below, then F), Rs[n].  Returns 0 or ST_SINGULAR.
