@@ -813,11 +813,12 @@ def main():
                 "synchronous_call": {"value": e2e_sync_value, "ms_per_step": e2e_sync_ms / args.steps,
                                      "api": "kvxopt_b200.klu.refactor_batch(Fn, values) -> status, one blocking call per step"}},
         "gpu_launches": int(nlaunch),
-        "roofline": {"bound": "hbm", "kernel": "k_klu_refactor_wave", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_klu_early (one launch per wide dependency level) + k_klu_refactor_wave", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)",
                      "algorithmic_bytes_per_refactor": bytes_per, "kernel_ms_per_launch": ker_avg_ms,
                      "dense_block_ms_per_step": dense_ms / args.steps,
-                     "traffic": traffic_from_profiles("k_klu_refactor_wave")},
+                     "traffic": (traffic_from_profiles("k_klu_refactor_wave") or 0) + (traffic_from_profiles("k_klu_early") or 0) or None,
+                     "traffic_source": "profiles/r02c_ncu_klu_wave_early.txt: dram bytes of the wave kernel (8.72 GB) + the six early launches (1.64 GB), one batch of 4096"},
         "parity_spot_check_rel_vs_superlu": spot,
         "clocks": clk,
     }

@@ -156,6 +156,18 @@ b200s_status b200s_chol_factor_begin(b200s_chol* F, const double* val, int val_o
 b200s_status b200s_chol_factor_level(b200s_chol* F, b200s_int level);
 b200s_status b200s_chol_factor_end(b200s_chol* F, b200s_int* minor_out);
 b200s_status b200s_chol_sync(b200s_chol* F);             /* wait for the handle's stream */
+/* A level in two steps, for fronts whose Schur complement C = -L21 L21' is SHARED by several GPUs (the top separators of the
+ * tree, which would otherwise run on one GPU while the others idle): phase 1 = extend-add, small fronts, panels and in-panel
+ * updates of the owned fronts; then the caller copies the factored panel L_dev[loff[s] .. +lsize[s]) of every shared front
+ * to its helpers; phase 2 = the Schur complements; phase 3 = both (= b200s_chol_factor_level).
+ * b200s_chol_set_syrk_split: per front (arrays of nsuper) own[s] != 0: this process computes the column tiles
+ * [tile_lo[s], tile_hi[s]) (tiles of 64 columns of the update matrix) -- in place in W_dev when base[s] == LLONG_MIN (the
+ * front's owner: W already holds the children's contributions), else into scratch_dev[base[s] ..) (a helper: the buffer
+ * must be zero; column tile tile_lo[s] first, leading dimension as in W, i.e. the even number >= nrows - ncols + (ncols & 1)).
+ * own == NULL restores the default (every owned front complete and in place). */
+b200s_status b200s_chol_factor_level_phase(b200s_chol* F, b200s_int level, int phase);
+b200s_status b200s_chol_set_syrk_split(b200s_chol* F, const unsigned char* own, const int* tile_lo, const int* tile_hi,
+                                       const long long* base, double* scratch_dev);
 /* per front (arrays of nsuper, any may be NULL); offsets and sizes in doubles */
 b200s_status b200s_chol_front_layout(const b200s_chol* F, b200s_int* parent, b200s_int* level, b200s_int* ncols,
                                      b200s_int* nrows, b200s_int* loff, b200s_int* lsize, b200s_int* uoff,

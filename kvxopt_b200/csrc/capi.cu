@@ -330,6 +330,20 @@ b200s_status b200s_chol_factor_level(b200s_chol* F, b200s_int level) {
     if (!F || !F->dev) return B200S_INVALID;
     return (b200s_status)chol_device_factor_level(F->dev, (int)level);
 }
+b200s_status b200s_chol_factor_level_phase(b200s_chol* F, b200s_int level, int phase) {
+    B200S_NVTX("b200s_chol_factor_level_phase");
+    if (!F || !F->dev || phase < 1 || phase > 3) return B200S_INVALID;
+    return (b200s_status)chol_device_factor_level_phase(F->dev, (int)level, phase);
+}
+b200s_status b200s_chol_set_syrk_split(b200s_chol* F, const unsigned char* own, const int* tile_lo, const int* tile_hi,
+                                       const long long* base, double* scratch_dev) {
+    if (!F) return B200S_INVALID;
+    if (F->plan().n == 0) return B200S_OK;
+    if (F->ldl && own) { set_last_error("shared Schur complements are not available with supernodal = 0 (LDL')"); return B200S_INVALID; }
+    b200s_status es = ensure_device(F);
+    if (es != B200S_OK) return es;
+    return (b200s_status)chol_device_set_syrk_split(F->dev, own, tile_lo, tile_hi, base, scratch_dev);
+}
 b200s_status b200s_chol_factor_end(b200s_chol* F, b200s_int* minor_out) {
     B200S_NVTX("b200s_chol_factor_end");
     if (!F) return B200S_INVALID;

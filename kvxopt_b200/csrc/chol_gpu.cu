@@ -19,6 +19,7 @@
 #include "gpu.hpp"
 #include "devpool.hpp"
 #include <cuda_runtime.h>
+#include <climits>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -563,11 +564,22 @@ __device__ __forceinline__ void load_tile_async(double* dst, const double* __res
 // 512 B of the column block, issued by the lanes of warp 0, completion counted in bytes on one mbarrier per stage) instead of
 // 16-byte LDGSTS from all 256 threads.  Rows past the tile edge are simply not copied (they only feed accumulators that are
 // never stored); k-columns past K are zeroed by plain stores.
+// Schur complement of one front shared by several GPUs (multi-GPU factorization, kvxopt_b200/dist.py): every participant has
+// the front's factored panel and computes the column tiles [lo, hi) of C = -L21 L21^T; the front's owner in place in its
+// update matrix (which already holds the children's contributions), a helper into a zeroed scratch buffer that the owner of
+// the parent front adds to the update matrix it receives.  All arrays are indexed by front; own == nullptr: not in use.
+struct SyrkSplit {
+    const unsigned char* own;     // this rank computes a slab of the front's Schur complement
+    const int *lo, *hi;           // its column tiles (of BTN columns)
+    const long long* base;        // LLONG_MIN: in place in W; else the slab starts at scratch[base] (column tile lo)
+    double* scratch;
+};
+
 template <bool SGN, bool TMA>
 __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix,
                                                            int ngroups, int mode, int kb, const FrontD* __restrict__ F,
                                                            double* __restrict__ L, double* __restrict__ W,
-                                                           const unsigned char* __restrict__ owned,
+                                                           const unsigned char* __restrict__ owned, const SyrkSplit sp,
                                                            const double* __restrict__ sgn) {
     extern __shared__ double sm[];
     double* As = sm;                          // [STAGES][BK][LDT]    rows of the tile's row block (128)
@@ -576,7 +588,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
     int t;
     const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, t);
     const FrontS f = load_front(sg, gfront, F, g);
-    if (!owned[f.id]) return;
+    if (mode == 1 && sp.own) { if (!sp.own[f.id]) return; }
+    else if (!owned[f.id]) return;
     const int nr = f.nr, nc = f.nc, ld = f.ld;
     const double* P = L + f.loff;
     int rowI, rowJ, k0, K, ldc, crows, ccols, lo;
@@ -609,6 +622,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
         rowI = r0 + ti * BT; rowJ = r0 + cj * BTN;
         k0 = 0; K = nc;
         C = W + f.uoff + (long long)ti * BT + (long long)cj * BTN * ldu; ldc = ldu;
+        if (sp.own) {            // a slab of a shared Schur complement
+            const int tlo = sp.lo[f.id];
+            if (cj < tlo || cj >= sp.hi[f.id]) return;
+            const long long base = sp.base[f.id];
+            if (base != LLONG_MIN) C = sp.scratch + base + (long long)ti * BT + (long long)(cj - tlo) * BTN * ldu;
+        }
         crows = min(BT, nr - rowI); ccols = min(BTN, nr - rowJ);
         lo = nc;
     }
@@ -1335,7 +1354,10 @@ public:
     int init();
     int factorize(const double* val, bool on_device, i64* minor, CholTimes* times);
     int factor_begin(const double* val, bool on_device);
-    int factor_level(int l);
+    int factor_level(int l, int phase = 3);     // phase bit 0: everything up to the panels' in-panel updates, bit 1: the Schur complements
+    int set_syrk_split(const unsigned char* own, const int* lo, const int* hi, const long long* base, double* scratch);
+    SyrkSplit syrk_split = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned char* dsy_own = nullptr; int *dsy_lo = nullptr, *dsy_hi = nullptr; long long* dsy_base = nullptr;
     int factor_end(i64* minor, CholTimes* times);
     int set_owned(const unsigned char* owned_host);
     int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false,
@@ -1665,10 +1687,10 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
     } while (0)
 #define LAUNCH_UPD(GRID, BLOCK, SMEM, STREAM, ...)                                                \
     do {                                                                                          \
-        if (ldl) { if (upd_tma) k_update<true, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn);       \
-                   else k_update<true, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, dsgn); }            \
-        else { if (upd_tma) k_update<false, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr);       \
-               else k_update<false, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr); }            \
+        if (ldl) { if (upd_tma) k_update<true, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, syrk_split, dsgn);       \
+                   else k_update<true, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, syrk_split, dsgn); }            \
+        else { if (upd_tma) k_update<false, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, syrk_split, nullptr);       \
+               else k_update<false, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, syrk_split, nullptr); }            \
     } while (0)
 #define LAUNCH_SMALL(T, GRID, BLOCK, SMEM, STREAM, ...)                                          \
     do {                                                                                          \
@@ -1676,10 +1698,38 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
         else k_small_front<T, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__, nullptr);        \
     } while (0)
 
-int CholDevice::factor_level(int l) {
+int CholDevice::set_syrk_split(const unsigned char* own, const int* lo, const int* hi, const long long* base, double* scratch) {
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t ns = std::max<size_t>(plan->fronts.size(), 1);
+    if (!own) { syrk_split = {nullptr, nullptr, nullptr, nullptr, nullptr}; return ST_OK; }
+    if (!lo || !hi || !base) return ST_INVALID;
+    if (!dsy_own) {
+        CUDA_TRY(cudaMalloc((void**)&dsy_own, ns));
+        CUDA_TRY(cudaMalloc((void**)&dsy_lo, ns * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void**)&dsy_hi, ns * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void**)&dsy_base, ns * sizeof(long long)));
+    }
+    CUDA_TRY(cudaMemcpy(dsy_own, own, plan->fronts.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dsy_lo, lo, plan->fronts.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dsy_hi, hi, plan->fronts.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dsy_base, base, plan->fronts.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    syrk_split = {dsy_own, dsy_lo, dsy_hi, dsy_base, scratch};
+    return ST_OK;
+}
+
+int CholDevice::factor_level(int l, int phase) {
     const CholPlan& P = *plan;
     if (l < 0 || l >= P.nlevels) return ST_INVALID;
     CUDA_TRY(cudaSetDevice(device));
+    if (!(phase & 1)) {          // the Schur complements alone (the panels were factored by an earlier call, here or elsewhere)
+        const LevelSched& LS2 = levels[l];
+        if ((phase & 2) && LS2.syrk.ctas)
+            LAUNCH_UPD(LS2.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream,
+                       sgroups[std::max(LS2.syrk.sgi, 0)], dsched + LS2.syrk.goff, dsched + LS2.syrk.goff + LS2.syrk.ng,
+                       LS2.syrk.ng, 1, 0, dF, dL, dW, downed);
+        CUDA_TRY(cudaGetLastError());
+        return ST_OK;
+    }
     auto prof_begin = [&](int cls) {
         if (!profiling) return;
         while (pev.size() < pe + 2) { cudaEvent_t e; cudaEventCreate(&e); pev.push_back(e); }
@@ -1788,7 +1838,7 @@ int CholDevice::factor_level(int l) {
         }
     }
     if (pendingB) CUDA_TRY(cudaStreamWaitEvent(stream, evB, 0));
-    if (LS.syrk.ctas) {
+    if (LS.syrk.ctas && (phase & 2)) {
         prof_begin(3);
         LAUNCH_UPD(LS.syrk.ctas, UPD_THREADS, SMEM_UPDATE, stream,
                        sgroups[std::max(LS.syrk.sgi, 0)], dsched + LS.syrk.goff, dsched + LS.syrk.goff + LS.syrk.ng,
@@ -2221,6 +2271,8 @@ int chol_device_download_sign(CholDevice* d, double* sign_host) {
 int chol_device_set_owned(CholDevice* d, const unsigned char* owned) { return d->set_owned(owned); }
 int chol_device_factor_begin(CholDevice* d, const double* val, bool on_device) { return d->factor_begin(val, on_device); }
 int chol_device_factor_level(CholDevice* d, int level) { return d->factor_level(level); }
+int chol_device_factor_level_phase(CholDevice* d, int level, int phase) { return d->factor_level(level, phase); }
+int chol_device_set_syrk_split(CholDevice* d, const unsigned char* own, const int* lo, const int* hi, const long long* base, double* scratch) { return d->set_syrk_split(own, lo, hi, base, scratch); }
 int chol_device_factor_end(CholDevice* d, i64* minor, CholTimes* times) { return d->factor_end(minor, times); }
 int chol_device_sync(CholDevice* d) {
     CUDA_TRY(cudaSetDevice(d->device));

@@ -63,8 +63,9 @@ def front_work(lay):
     return c ** 3 / 3.0 + c * c * r + c * r * r
 
 
-def ownership(lay, world):
-    """subtree-to-subcube: owner[s] in [0, world) for every front"""
+def ownership(lay, world, with_groups=False):
+    """subtree-to-subcube: owner[s] in [0, world) for every front; with_groups: also the rank group [g0[s], g1[s]) that works
+    on the subtree of s (the owner is its first rank; a group of one below the cut)"""
     ns = len(lay["parent"])
     parent = lay["parent"]
     work = front_work(lay)
@@ -77,6 +78,8 @@ def ownership(lay, world):
     for s in range(ns):
         (kids[parent[s]] if parent[s] >= 0 else roots).append(s)
     owner = np.zeros(ns, dtype=np.int64)
+    g0 = np.zeros(ns, dtype=np.int64)
+    g1 = np.ones(ns, dtype=np.int64)
     first = np.zeros(ns, dtype=np.int64)      # first descendant of s in postorder (subtree = [first[s], s])
     for s in range(ns):
         first[s] = first[kids[s][0]] if kids[s] else s
@@ -89,10 +92,13 @@ def ownership(lay, world):
         if r1 - r0 == 1:
             for s in nodes:
                 owner[first[s]:s + 1] = r0
+                g0[first[s]:s + 1] = r0
+                g1[first[s]:s + 1] = r1
             continue
         if len(nodes) == 1:
             s = nodes[0]
             owner[s] = r0
+            g0[s], g1[s] = r0, r1
             stack.append((kids[s], r0, r1))
             continue
         # split the set of subtrees into two bins of similar work, the rank group into two halves
@@ -105,7 +111,94 @@ def ownership(lay, world):
         mid = r0 + max(1, min(r1 - r0 - 1, int(round((r1 - r0) * load[0] / max(load[0] + load[1], 1e-300)))))
         stack.append((bins[0], r0, mid))
         stack.append((bins[1], mid, r1))
-    return owner
+    return (owner, g0, g1) if with_groups else owner
+
+
+BT, BTN = 128, 64        # row / column tile of the Schur-complement kernel (k_update in csrc/chol_gpu.cu)
+
+
+def split_plan(lay, owner, g0, g1, min_flops=2.0e10, min_rows=1024):
+    """Fronts whose Schur complement C = -L21 L21' is shared by the ranks of their subtree group (they would idle while the
+    owner works through the top separators).  For every such front s: its participants (owner first) and their column-tile
+    ranges [lo, hi) (tiles of BTN columns, contiguous, about the same number of 128 x 64 tiles each).
+    Returns {s: [(rank, lo, hi), ...]} -- a pure function of the plan, identical on every rank."""
+    plan = {}
+    nc, nr = lay["nc"], lay["nr"]
+    for s in range(len(owner)):
+        m = int(nr[s] - nc[s])
+        g = int(g1[s] - g0[s])
+        if g < 2 or m < min_rows or float(nc[s]) * m * m < min_flops:
+            continue
+        mu = m + int(nc[s] & 1)
+        T = (mu + BT - 1) // BT
+        ncj = (mu + BTN - 1) // BTN
+        tiles = np.array([T - (cj >> 1) for cj in range(ncj)], dtype=np.float64)
+        cum = np.concatenate([[0.0], np.cumsum(tiles)])
+        ranks = [int(owner[s])] + [r for r in range(int(g0[s]), int(g1[s])) if r != owner[s]]
+        cuts = [0]
+        for q in range(1, g):
+            cuts.append(int(np.searchsorted(cum, cum[-1] * q / g)))
+        cuts.append(ncj)
+        cuts = [min(max(c, 0), ncj) for c in cuts]
+        for q in range(1, len(cuts)):
+            cuts[q] = max(cuts[q], cuts[q - 1])
+        parts = [(ranks[q], cuts[q], cuts[q + 1]) for q in range(g) if cuts[q + 1] > cuts[q]]
+        if len(parts) >= 2:
+            plan[s] = parts
+    return plan
+
+
+def slab_range(lay, s, lo, hi):
+    """(offset from uoff[s], count) in doubles of the column tiles [lo, hi) of the update matrix of front s"""
+    mu = int(lay["nr"][s] - lay["nc"][s]) + int(lay["nc"][s] & 1)
+    ldu = (mu + 1) & ~1
+    c0, c1 = lo * BTN, min(hi * BTN, mu)
+    return c0 * ldu, (c1 - c0) * ldu
+
+
+class SplitTables:
+    """what one rank needs to take part in the shared Schur complements: the arrays for b200s_chol_set_syrk_split, the size
+    and layout of its scratch buffer, and the transfer lists (panels before phase 2 of a level, slabs before the parent's level)"""
+
+    def __init__(self, lay, owner, splan, rank):
+        ns = len(owner)
+        self.own = (owner == rank).astype(np.uint8)          # default: the owned fronts, complete, in place
+        self.lo = np.zeros(ns, dtype=np.int32)
+        self.hi = np.full(ns, 0x7fffffff, dtype=np.int32)
+        self.base = np.full(ns, np.iinfo(np.int64).min, dtype=np.int64)
+        self.scratch_size = 0
+        self.scratch_off = {}
+        for s, parts in splan.items():
+            self.own[s] = 0
+            for r, lo, hi in parts:
+                if r != rank:
+                    continue
+                self.own[s] = 1
+                self.lo[s], self.hi[s] = lo, hi
+                if r != owner[s]:
+                    off, cnt = slab_range(lay, s, lo, hi)
+                    self.base[s] = self.scratch_size
+                    self.scratch_off[s] = (self.scratch_size, cnt, off)
+                    self.scratch_size += cnt
+        self.any = bool(splan)
+
+
+def split_moves(lay, owner, splan):
+    """panel_moves[l]: (s, owner, helper) -- the factored panel of s goes to every helper between the two phases of level l;
+    slab_moves[l]: (s, helper, dst, lo, hi) -- the helper's slab of s is added to the update matrix of s on dst = the owner of
+    the parent of s before level l = level[parent] runs."""
+    nl = lay["nlevels"]
+    panel_moves = [[] for _ in range(nl)]
+    slab_moves = [[] for _ in range(nl)]
+    for s, parts in sorted(splan.items()):
+        p = lay["parent"][s]
+        for r, lo, hi in parts:
+            if r == owner[s]:
+                continue
+            panel_moves[lay["level"][s]].append((s, int(owner[s]), r))
+            if p >= 0:
+                slab_moves[lay["level"][p]].append((s, r, int(owner[p]), lo, hi))
+    return panel_moves, slab_moves
 
 
 def exchange_plan(lay, owner):
@@ -159,45 +252,116 @@ def _check(st, what):
     return st
 
 
+def _install_split(h, st):
+    """hand the split tables of one rank to its factor handle; returns the (zeroed) scratch tensor or None"""
+    import torch
+    if not st.any:
+        return None
+    scratch = torch.zeros(max(1, st.scratch_size), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+    _check(fn["b200s_chol_set_syrk_split"](h, st.own.tobytes(), st.lo.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           st.hi.ctypes.data_as(C.POINTER(C.c_int32)), L.ptr_i64(st.base),
+                                           C.c_void_p(scratch.data_ptr())), "set_syrk_split")
+    return scratch
+
+
+def _work_share(lay, owner, splan, rank):
+    """flops this rank executes: its fronts, minus the Schur-complement tiles it gives away, plus those it takes"""
+    w = front_work(lay)
+    total = float(w[owner == rank].sum())
+    for s, parts in splan.items():
+        c = float(lay["nc"][s]); m = float(lay["nr"][s] - lay["nc"][s])
+        mu = int(m) + int(lay["nc"][s] & 1)
+        T = (mu + BT - 1) // BT
+        tiles = {r: sum(T - (cj >> 1) for cj in range(lo, hi)) for r, lo, hi in parts}
+        alltiles = float(sum(tiles.values()))
+        syrk = c * m * m
+        if owner[s] == rank:
+            total -= syrk
+        if rank in tiles:
+            total += syrk * tiles[rank] / alltiles
+    return total
+
+
 class DistCholesky:
     """one instance per rank; `F` is the capsule from kvxopt_b200.cholmod.symbolic on this rank's GPU"""
 
-    def __init__(self, F, world, rank, group=None):
+    def __init__(self, F, world, rank, group=None, split=True):
         from . import cholmod
         self.h, _ = cholmod._factor_handle(F)
         self.F = F
         self.world, self.rank, self.group = world, rank, group
         self.lay = front_layout(self.h)
-        self.owner = ownership(self.lay, world)
+        self.owner, g0, g1 = ownership(self.lay, world, with_groups=True)
         self.xplan = exchange_plan(self.lay, self.owner)
         self.gplan = gather_plan(self.lay, self.owner)
         mine = (self.owner == rank).astype(np.uint8)
         _check(fn["b200s_chol_set_owned"](self.h, mine.tobytes()), "set_owned")
         self.Lt, self.Wt = _device_views(self.h, self.lay)
-        self.work_share = float(front_work(self.lay)[self.owner == rank].sum())
+        # shared Schur complements of the top separators (split=False: every front entirely on its owner, as in round 1)
+        self.splan = split_plan(self.lay, self.owner, g0, g1) if split and world > 1 else {}
+        self.st = SplitTables(self.lay, self.owner, self.splan, rank)
+        self.panel_moves, self.slab_moves = split_moves(self.lay, self.owner, self.splan)
+        self.split_levels = {int(self.lay["level"][s]) for s in self.splan}
+        self.scratch = _install_split(self.h, self.st)
+        self.work_share = float(_work_share(self.lay, self.owner, self.splan, rank))
 
     def factorize(self, values_ptr, on_device):
         """level-stepped factorization with NCCL exchange of the update matrices; returns (status, minor)"""
         import torch
         import torch.distributed as dist
         lay = self.lay
+        if self.scratch is not None:
+            self.scratch.zero_()
+            torch.cuda.current_stream().synchronize()
         _check(fn["b200s_chol_factor_begin"](self.h, values_ptr, 1 if on_device else 0), "factor_begin")
         for l in range(lay["nlevels"]):
-            moves = self.xplan[l]
-            mine = [m for m in moves if self.rank in (m[1], m[2])]
-            if mine:
-                fn["b200s_chol_sync"](self.h)                 # my update matrices of earlier levels are complete
-                ops = []
+            mine = [m for m in self.xplan[l] if self.rank in (m[1], m[2])]
+            slabs = [m for m in self.slab_moves[l] if self.rank in (m[1], m[2])]
+            if mine or slabs:
+                fn["b200s_chol_sync"](self.h)                 # my update matrices and slabs of earlier levels are complete
+                ops, adds = [], []
                 for s, src, dst in mine:
                     t = self.Wt[lay["uoff"][s]: lay["uoff"][s] + lay["usize"][s]]
                     if src == self.rank:
                         ops.append(dist.P2POp(dist.isend, t, dst, group=self.group))
                     else:
                         ops.append(dist.P2POp(dist.irecv, t, src, group=self.group))
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+                for s, helper, dst, lo, hi in slabs:           # slabs of shared Schur complements -> the parent's owner
+                    off, cnt = slab_range(lay, s, lo, hi)
+                    w0 = int(lay["uoff"][s]) + off
+                    if helper == self.rank:
+                        so = self.st.scratch_off[s][0]
+                        t = self.scratch[so: so + cnt]
+                        if dst == self.rank:
+                            adds.append((w0, cnt, t))
+                        else:
+                            ops.append(dist.P2POp(dist.isend, t, dst, group=self.group))
+                    else:
+                        t = torch.empty(cnt, dtype=torch.float64, device=self.Wt.device)
+                        ops.append(dist.P2POp(dist.irecv, t, helper, group=self.group))
+                        adds.append((w0, cnt, t))
+                if ops:
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                for w0, cnt, t in adds:                        # after the update matrix itself has arrived
+                    self.Wt[w0: w0 + cnt] += t
                 torch.cuda.current_stream().synchronize()      # received data visible to the handle's stream
-            _check(fn["b200s_chol_factor_level"](self.h, l), "factor_level")
+            if l in self.split_levels:
+                _check(fn["b200s_chol_factor_level_phase"](self.h, l, 1), "factor_level (panels)")
+                pm = [m for m in self.panel_moves[l] if self.rank in (m[1], m[2])]
+                if pm:
+                    fn["b200s_chol_sync"](self.h)             # the panels of my shared fronts are factored
+                    ops = []
+                    for s, src, dst in pm:
+                        t = self.Lt[lay["loff"][s]: lay["loff"][s] + lay["lsize"][s]]
+                        ops.append(dist.P2POp(dist.isend if src == self.rank else dist.irecv, t, dst if src == self.rank else src,
+                                              group=self.group))
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                    torch.cuda.current_stream().synchronize()
+                _check(fn["b200s_chol_factor_level_phase"](self.h, l, 2), "factor_level (Schur complements)")
+            else:
+                _check(fn["b200s_chol_factor_level"](self.h, l), "factor_level")
         minor = C.c_int64()
         st = _check(fn["b200s_chol_factor_end"](self.h, C.byref(minor)), "factor_end")
         m = torch.tensor([int(minor.value) if st == 1 else lay["n"]], device="cuda", dtype=torch.int64)
@@ -230,35 +394,61 @@ class VirtualRanks:
     """The same protocol with `world` handles on ONE GPU (device-to-device copies instead of NCCL): lets the ownership
     split, the exchange plan and the level-stepped kernels be verified on a single-GPU box."""
 
-    def __init__(self, capsules):
+    def __init__(self, capsules, split=True, split_args=None):
         from . import cholmod
         self.hs = [cholmod._factor_handle(F)[0] for F in capsules]
         self.world = len(self.hs)
         self.lay = front_layout(self.hs[0])
-        self.owner = ownership(self.lay, self.world)
+        self.owner, g0, g1 = ownership(self.lay, self.world, with_groups=True)
         self.xplan = exchange_plan(self.lay, self.owner)
         self.gplan = gather_plan(self.lay, self.owner)
-        self.views = []
+        self.splan = split_plan(self.lay, self.owner, g0, g1, **(split_args or {})) if split and self.world > 1 else {}
+        self.panel_moves, self.slab_moves = split_moves(self.lay, self.owner, self.splan)
+        self.split_levels = {int(self.lay["level"][s]) for s in self.splan}
+        self.views, self.sts, self.scratch = [], [], []
         for r, h in enumerate(self.hs):
             _check(fn["b200s_chol_set_owned"](h, (self.owner == r).astype(np.uint8).tobytes()), "set_owned")
             self.views.append(_device_views(h, self.lay))
+            self.sts.append(SplitTables(self.lay, self.owner, self.splan, r))
+            self.scratch.append(_install_split(h, self.sts[-1]))
 
     def factorize(self, values):
         import torch
         lay = self.lay
         v = np.ascontiguousarray(values, dtype=np.float64)
+        for sc in self.scratch:
+            if sc is not None:
+                sc.zero_()
+        torch.cuda.synchronize()
         for h in self.hs:
             _check(fn["b200s_chol_factor_begin"](h, v.ctypes.data_as(C.c_void_p), 0), "factor_begin")
         for l in range(lay["nlevels"]):
-            if self.xplan[l]:
+            if self.xplan[l] or self.slab_moves[l]:
                 for h in self.hs:
                     fn["b200s_chol_sync"](h)
                 for s, src, dst in self.xplan[l]:
                     a, b = lay["uoff"][s], lay["uoff"][s] + lay["usize"][s]
                     self.views[dst][1][a:b].copy_(self.views[src][1][a:b])
+                for s, helper, dst, lo, hi in self.slab_moves[l]:
+                    off, cnt = slab_range(lay, s, lo, hi)
+                    w0 = int(lay["uoff"][s]) + off
+                    so = self.sts[helper].scratch_off[s][0]
+                    self.views[dst][1][w0: w0 + cnt] += self.scratch[helper][so: so + cnt]
                 torch.cuda.synchronize()
-            for h in self.hs:
-                _check(fn["b200s_chol_factor_level"](h, l), "factor_level")
+            if l in self.split_levels:
+                for h in self.hs:
+                    _check(fn["b200s_chol_factor_level_phase"](h, l, 1), "factor_level (panels)")
+                for h in self.hs:
+                    fn["b200s_chol_sync"](h)
+                for s, src, dst in self.panel_moves[l]:
+                    a, b = lay["loff"][s], lay["loff"][s] + lay["lsize"][s]
+                    self.views[dst][0][a:b].copy_(self.views[src][0][a:b])
+                torch.cuda.synchronize()
+                for h in self.hs:
+                    _check(fn["b200s_chol_factor_level_phase"](h, l, 2), "factor_level (Schur complements)")
+            else:
+                for h in self.hs:
+                    _check(fn["b200s_chol_factor_level"](h, l), "factor_level")
         minors = []
         for h in self.hs:
             m = C.c_int64()

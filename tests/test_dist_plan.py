@@ -54,3 +54,65 @@ def test_subtree_to_subcube_mapping(world):
         covered[s0:s1 + 1] = True
     assert np.array_equal(covered, owner != 0)
     fn["b200s_chol_free"](F)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_shared_schur_complement_plan(world):
+    """split_plan / SplitTables / split_moves: the column tiles of every shared Schur complement are dealt exactly once, to
+    ranks of the front's subtree group, the owner works in place and helpers in disjoint scratch ranges, and every helper's
+    slab is sent to the owner of the parent front before the parent's level"""
+    F = handle_for(24, 24, 24)
+    lay = D.front_layout(F)
+    owner, g0, g1 = D.ownership(lay, world, with_groups=True)
+    assert np.array_equal(owner, D.ownership(lay, world))
+    assert np.all((g0 <= owner) & (owner < g1))
+    splan = D.split_plan(lay, owner, g0, g1, min_flops=1e5, min_rows=100)
+    if world >= 4:          # (two ranks: only the root front has a group of two, and it has no Schur complement)
+        assert splan, "the top separators of a 24^3 grid are large enough for these thresholds"
+    for s, parts in splan.items():
+        mu = int(lay["nr"][s] - lay["nc"][s]) + int(lay["nc"][s] & 1)
+        ncj = (mu + D.BTN - 1) // D.BTN
+        assert parts[0][0] == owner[s] and len({r for r, _, _ in parts}) == len(parts) >= 2
+        assert parts[0][1] == 0 and parts[-1][2] == ncj
+        for (r, lo, hi), nxt in zip(parts, parts[1:] + [None]):
+            assert g0[s] <= r < g1[s] and lo < hi
+            if nxt is not None:
+                assert nxt[1] == hi
+        # about the same number of tiles each
+        T = (mu + D.BT - 1) // D.BT
+        tiles = [sum(T - (cj >> 1) for cj in range(lo, hi)) for _, lo, hi in parts]
+        assert max(tiles) <= 2 * (sum(tiles) / len(tiles)) + T
+    pm, sm = D.split_moves(lay, owner, splan)
+    for l, lv in enumerate(pm):
+        for s, src, dst in lv:
+            assert lay["level"][s] == l and src == owner[s] and dst != src
+    for l, lv in enumerate(sm):
+        for s, helper, dst, lo, hi in lv:
+            p = lay["parent"][s]
+            assert lay["level"][p] == l and dst == owner[p] and helper != owner[s]
+    for r in range(world):
+        st = D.SplitTables(lay, owner, splan, r)
+        used = []
+        for s, parts in splan.items():
+            mine = [q for q in parts if q[0] == r]
+            assert st.own[s] == (1 if mine else 0)
+            if mine:
+                _, lo, hi = mine[0]
+                assert (st.lo[s], st.hi[s]) == (lo, hi)
+                if r == owner[s]:
+                    assert st.base[s] == np.iinfo(np.int64).min
+                else:
+                    off, cnt = D.slab_range(lay, s, lo, hi)
+                    assert st.base[s] >= 0 and st.scratch_off[s] == (st.base[s], cnt, off)
+                    assert off + cnt <= lay["usize"][s]
+                    used.append((int(st.base[s]), int(st.base[s]) + cnt))
+        used.sort()
+        assert all(a[1] <= b[0] for a, b in zip(used, used[1:])) and (not used or used[-1][1] == st.scratch_size)
+        # fronts that are not shared keep the default: owned fronts complete and in place
+        for s in range(len(owner)):
+            if s not in splan:
+                assert st.own[s] == (owner[s] == r) and st.lo[s] == 0 and st.hi[s] == 0x7fffffff
+    # flops accounting: the shares of all ranks add up to the total
+    tot = sum(D._work_share(lay, owner, splan, r) for r in range(world))
+    assert abs(tot - D.front_work(lay).sum()) <= 1e-9 * tot
+    fn["b200s_chol_free"](F)

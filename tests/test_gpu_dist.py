@@ -10,9 +10,10 @@ from conftest import lap3d, lower_ccs, rand_spd
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("case", ["lap3d", "rand"])
-def test_virtual_ranks_match_single_gpu_bitwise(world, case):
+def test_virtual_ranks_match_single_gpu_bitwise(world, case, split):
     from kvxopt_b200 import _lib as L, cholmod, dist as D
     assert L.device_count() > 0
     if case == "lap3d":
@@ -30,13 +31,24 @@ def test_virtual_ranks_match_single_gpu_bitwise(world, case):
     cholmod.numeric(Al, Fs)
     Xs = np.asfortranarray(B.copy()); cholmod.solve(Fs, Xs)
     caps = [cholmod.symbolic(Al, p=perm) for _ in range(world)]
-    vr = D.VirtualRanks(caps)
+    # split: the Schur complements of the top separators are shared by the ranks of their subtree group (thresholds lowered
+    # so that these small matrices have shared fronts at all)
+    vr = D.VirtualRanks(caps, split=split, split_args=dict(min_flops=1e5, min_rows=100))
     assert len(set(vr.owner.tolist())) == world
+    if split and case == "lap3d" and world >= 4:
+        assert len(vr.splan) >= 1 and any(len(p) >= 2 for p in vr.splan.values())
     minor = vr.factorize(Al.data)
     assert minor == n
     Xd = np.asfortranarray(B.copy()); cholmod.solve(caps[0], Xd)
-    # same kernels, same summation order per front => identical bits
-    assert np.array_equal(Xs, Xd)
+    if not vr.splan:
+        # same kernels, same summation order per front => identical bits
+        assert np.array_equal(Xs, Xd)
+    else:
+        # a helper's slab is E + (0 - L21 L21') instead of E - L21 L21' accumulated in one pass: one more rounding
+        assert np.linalg.norm(Xs - Xd) <= 1e-12 * np.linalg.norm(Xs)
+        minor2 = vr.factorize(Al.data)                     # a second factorization reuses (re-zeroed) scratch buffers
+        Xd2 = np.asfortranarray(B.copy()); cholmod.solve(caps[0], Xd2)
+        assert minor2 == n and np.array_equal(Xd, Xd2)
     berr = (np.linalg.norm(A @ Xd - B, axis=0) / (spla.norm(A, 1) * np.linalg.norm(Xd, axis=0) + np.linalg.norm(B, axis=0))).max()
     assert berr <= 1e-12
     # not positive definite: the smallest failing column over all ranks is reported
