@@ -399,7 +399,10 @@ def bench_cholesky_multi(nx, steps, rank, world):
     n = Al.shape[0]
     perm = np.zeros(n, np.int64)
     L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm))
+    # top-level separators are kept as fronts of their own (a merged front has no Schur complement left to share)
+    cholmod.engine_options["max_merge_cols"] = D.DIST_MAX_MERGE_COLS
     F = cholmod.symbolic(Al, p=perm)
+    cholmod.engine_options.pop("max_merge_cols", None)
     dc = D.DistCholesky(F, world, rank)
     vals = torch.from_numpy(Al.data.copy()).cuda()
     times, gtimes = [], []
@@ -428,10 +431,15 @@ def bench_cholesky_multi(nx, steps, rank, world):
                "factor_gather_solve_ms": fm + gm + d["ms_solve"],
                "factor_tflops": d["flops"] / (fm * 1e-3) / 1e12,
                "backward_error": berr, "timing": "host clock between barrier+synchronize pairs, max over ranks by construction",
-               "work_share_per_rank": [round(float(w[dc.owner == r].sum() / w.sum()), 3) for r in range(world)],
-               "nccl_transfers": int(sum(len(l) for l in dc.xplan)),
-               "nccl_bytes": int(sum(int(dc.lay["usize"][m[0]]) for l in dc.xplan for m in l) * 8),
-               "limitation": "fronts are not split across GPUs: the top log2(N) levels run on one GPU each; solves on rank 0 after "
+               "work_share_per_rank": [round(float(D._work_share(dc.lay, dc.owner, dc.splan, r) / w.sum()), 3) for r in range(world)],
+               "work_share_per_rank_fronts_only": [round(float(w[dc.owner == r].sum() / w.sum()), 3) for r in range(world)],
+               "shared_fronts": {int(s): [[int(r), int(lo), int(hi)] for r, lo, hi in parts] for s, parts in dc.splan.items()},
+               "nccl_transfers": int(sum(len(l) for l in dc.xplan) + sum(len(l) for l in dc.panel_moves) + sum(len(l) for l in dc.slab_moves)),
+               "nccl_bytes": int((sum(int(dc.lay["usize"][m[0]]) for l in dc.xplan for m in l)
+                                  + sum(int(dc.lay["lsize"][m[0]]) for l in dc.panel_moves for m in l)
+                                  + sum(D.slab_range(dc.lay, m[0], m[3], m[4])[1] for l in dc.slab_moves for m in l)) * 8),
+               "limitation": "the Schur complements of the top separators are shared by the ranks of their subtree group; their panels "
+                             "(potrf + trsm + in-panel updates) and the root front still run on one GPU each; solves on rank 0 after "
                              "the panel gather (both inside factor_gather_solve_ms)"}
     del dc, F
     return out

@@ -63,6 +63,10 @@ typedef struct {
     int    nrelax[3];    /* relaxed amalgamation thresholds, default {4,16,48}                      */
     double zrelax[3];    /* default {0.8,0.1,0.05}                                                  */
     int    block;        /* dense block-column width used inside large fronts (0 = default 128)     */
+    int    max_merge_cols; /* 0 = no limit.  Amalgamation does not merge a supernode into its parent when the result would
+                              be wider than this.  The multi-GPU factorization sets it (kvxopt_b200/dist.py) so that a top-level
+                              separator is not absorbed by its parent -- a free merge (same structure), but the merged front has
+                              no Schur complement left to share between GPUs */
 } b200s_chol_opts;
 
 void b200s_chol_default_opts(b200s_chol_opts* o);

@@ -5,7 +5,7 @@ i64 = C.c_int64
 
 class CholOpts(C.Structure):
     _fields_ = [("supernodal", C.c_int), ("nmethods", C.c_int), ("postorder", C.c_int), ("dbound", C.c_double),
-                ("ordering", C.c_int), ("nrelax", C.c_int * 3), ("zrelax", C.c_double * 3), ("block", C.c_int)]
+                ("ordering", C.c_int), ("nrelax", C.c_int * 3), ("zrelax", C.c_double * 3), ("block", C.c_int), ("max_merge_cols", C.c_int)]
 
 
 class CholInfo(C.Structure):

@@ -20,6 +20,8 @@ fn = L.fn
 
 # reference cholmod.c:98-125 -- recognised keys; anything else raises ValueError on every call
 options = {}
+# engine extensions that are NOT part of the reference's `options` contract (b200s_chol_opts fields): 'max_merge_cols'
+engine_options = {}
 
 _NAME_L = b"CHOLMOD SYM D FACTOR L"     # cholmod.c:44-48
 _NAME_U = b"CHOLMOD SYM D FACTOR U"
@@ -69,6 +71,7 @@ def _set_options():
     """cholmod.c:87-129: defaults, print=0, supernodal=2, then overlay `options`."""
     o = L.CholOpts()
     fn["b200s_chol_default_opts"](C.byref(o))
+    o.max_merge_cols = int(engine_options.get("max_merge_cols", 0))
     for key, value in options.items():
         if not isinstance(key, str):
             continue

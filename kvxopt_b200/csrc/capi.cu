@@ -87,7 +87,7 @@ unsigned long long fnv(const void* p, size_t bytes, unsigned long long h) {
 }
 bool same_opts(const CholOpts& a, const CholOpts& b) {
     return a.supernodal == b.supernodal && a.nmethods == b.nmethods && a.postorder == b.postorder && a.ordering == b.ordering &&
-           a.dbound == b.dbound && a.block == b.block && !memcmp(a.nrelax, b.nrelax, sizeof a.nrelax) && !memcmp(a.zrelax, b.zrelax, sizeof a.zrelax);
+           a.dbound == b.dbound && a.block == b.block && a.max_merge_cols == b.max_merge_cols && !memcmp(a.nrelax, b.nrelax, sizeof a.nrelax) && !memcmp(a.zrelax, b.zrelax, sizeof a.zrelax);
 }
 bool plan_cache_enabled() { static const bool on = getenv("B200S_NO_PLAN_CACHE") == nullptr; return on; }
 unsigned long long pattern_hash(i64 n, const b200s_int* cp, const b200s_int* ri, const b200s_int* perm) {
@@ -171,7 +171,7 @@ void b200s_chol_default_opts(b200s_chol_opts* o) {
     if (!o) return;
     CholOpts d;
     o->supernodal = d.supernodal; o->nmethods = d.nmethods; o->postorder = d.postorder; o->dbound = d.dbound;
-    o->ordering = d.ordering; o->block = d.block;
+    o->ordering = d.ordering; o->block = d.block; o->max_merge_cols = d.max_merge_cols;
     for (int i = 0; i < 3; i++) { o->nrelax[i] = d.nrelax[i]; o->zrelax[i] = d.zrelax[i]; }
 }
 
@@ -187,6 +187,7 @@ b200s_status b200s_chol_analyze(b200s_int n, const b200s_int* colptr, const b200
         F->opts.supernodal = opts->supernodal; F->opts.nmethods = opts->nmethods; F->opts.postorder = opts->postorder;
         F->opts.dbound = opts->dbound; F->opts.ordering = opts->ordering;
         if (opts->block > 0) F->opts.block = opts->block;
+        F->opts.max_merge_cols = opts->max_merge_cols > 0 ? opts->max_merge_cols : 0;
         for (int i = 0; i < 3; i++) { F->opts.nrelax[i] = opts->nrelax[i]; F->opts.zrelax[i] = opts->zrelax[i]; }
     }
     // supernodal = 0 asks CHOLMOD for a simplicial LDL' factorization (no pivoting; any symmetric matrix with nonzero

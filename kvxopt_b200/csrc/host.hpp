@@ -36,6 +36,7 @@ struct CholOpts {
     int nrelax[3] = {4, 16, 48};
     double zrelax[3] = {0.8, 0.1, 0.05};
     int block = 128;
+    int max_merge_cols = 0;   // relaxed amalgamation never builds a supernode wider than this (0 = no limit); see b200sparse.h
 };
 
 // One front (= supernode) of the multifrontal plan.

@@ -314,6 +314,7 @@ void chol_analyze(i64 n64, const i64* colptr, const i64* rowind, char uplo, cons
             else merge = z < opts.zrelax[2];
         }
         if (newzeros == 0) merge = true;                            // free merge (same structure)
+        if (opts.max_merge_cols > 0 && ntot > opts.max_merge_cols) merge = false;      // (multi-GPU: keep the top separators apart)
         if (!merge) continue;
         alive[s] = 0;
         sfirst[p] = sfirst[s];

@@ -115,6 +115,10 @@ def ownership(lay, world, with_groups=False):
 
 
 BT, BTN = 128, 64        # row / column tile of the Schur-complement kernel (k_update in csrc/chol_gpu.cu)
+# cholmod.engine_options["max_merge_cols"] for factor objects that are going to be distributed: relaxed amalgamation would
+# merge a top-level separator into its parent for free (same structure), and the merged front's work is all panel work on
+# one GPU; as fronts of their own, the child's Schur complement (most of its flops) is shared by its rank group
+DIST_MAX_MERGE_COLS = 2048
 
 
 def split_plan(lay, owner, g0, g1, min_flops=2.0e10, min_rows=1024):
@@ -285,7 +289,7 @@ def _work_share(lay, owner, splan, rank):
 class DistCholesky:
     """one instance per rank; `F` is the capsule from kvxopt_b200.cholmod.symbolic on this rank's GPU"""
 
-    def __init__(self, F, world, rank, group=None, split=True):
+    def __init__(self, F, world, rank, group=None, split=True, split_args=None):
         from . import cholmod
         self.h, _ = cholmod._factor_handle(F)
         self.F = F
@@ -298,7 +302,7 @@ class DistCholesky:
         _check(fn["b200s_chol_set_owned"](self.h, mine.tobytes()), "set_owned")
         self.Lt, self.Wt = _device_views(self.h, self.lay)
         # shared Schur complements of the top separators (split=False: every front entirely on its owner, as in round 1)
-        self.splan = split_plan(self.lay, self.owner, g0, g1) if split and world > 1 else {}
+        self.splan = split_plan(self.lay, self.owner, g0, g1, **(split_args or {})) if split and world > 1 else {}
         self.st = SplitTables(self.lay, self.owner, self.splan, rank)
         self.panel_moves, self.slab_moves = split_moves(self.lay, self.owner, self.splan)
         self.split_levels = {int(self.lay["level"][s]) for s in self.splan}

@@ -1,5 +1,6 @@
-"""torchrun --nproc-per-node N tools/dist_chol_check.py [nx]: NCCL subtree-to-subcube factorization of the nx^3
-Laplacian, checked against the residual and (for small nx) the oracle; prints timing per rank count."""
+"""torchrun --nproc-per-node N tools/dist_chol_check.py [nx [max_merge_cols [split]]]: NCCL subtree-to-subcube factorization of
+the nx^3 Laplacian (shared Schur complements of the top separators unless split = 0), checked against the residual; prints
+timing per rank count."""
 import ctypes as C, os, sys, time
 import numpy as np
 import torch, torch.distributed as dist
@@ -14,8 +15,12 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 Al = lap3d_lower(nx); n = Al.shape[0]
 perm = np.zeros(n, np.int64); L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm))
+cap = int(sys.argv[2]) if len(sys.argv) > 2 else D.DIST_MAX_MERGE_COLS
+split = (int(sys.argv[3]) != 0) if len(sys.argv) > 3 else True
+cholmod.engine_options["max_merge_cols"] = cap
 F = cholmod.symbolic(Al, p=perm)
-dc = D.DistCholesky(F, world, rank)
+dc = D.DistCholesky(F, world, rank, split=split,
+                    split_args=dict(min_flops=float(sys.argv[4]), min_rows=int(sys.argv[5])) if len(sys.argv) > 5 else None)
 vals = torch.from_numpy(Al.data.copy()).cuda()
 torch.cuda.synchronize(); dist.barrier()
 for rep in range(3):
@@ -34,7 +39,10 @@ if rank == 0:
     berr = np.linalg.norm(A @ x - b) / (12 * np.linalg.norm(x) + np.linalg.norm(b))
     shares = D.front_work(dc.lay); tot = shares.sum()
     print("backward error %.2e | flops %.3g | work share per rank: %s | transfers: %d update matrices, %.1f MB" % (
-        berr, info["flops"], [round(float(shares[dc.owner == r].sum() / tot), 3) for r in range(world)],
+        berr, info["flops"], [round(float(D._work_share(dc.lay, dc.owner, dc.splan, r) / tot), 3) for r in range(world)],
         sum(len(l) for l in dc.xplan), sum(dc.lay["usize"][m[0]] for l in dc.xplan for m in l) * 8 / 1e6), flush=True)
+    print("max_merge_cols %d, shared fronts: %s" % (cap, {int(k): [(int(r), int(lo), int(hi)) for r, lo, hi in v] for k, v in dc.splan.items()}), flush=True)
+    top = sorted(range(len(shares)), key=lambda q: -shares[q])[:8]
+    print("largest fronts (id, nc, nr, owner, level, share):", [(int(q), int(dc.lay["nc"][q]), int(dc.lay["nr"][q]), int(dc.owner[q]), int(dc.lay["level"][q]), round(float(shares[q] / tot), 3)) for q in top], flush=True)
     assert berr < 1e-12
 dist.barrier(); dist.destroy_process_group()
