@@ -460,7 +460,7 @@ def bench_config1(steps):
             t = time.perf_counter(); r = f(); ts.append((time.perf_counter() - t) * 1e3)
         return min(ts), r
 
-    reps = max(3, steps)
+    reps = max(8, steps)
     # headline = COLD calls: the engine keeps the symbolic analysis of the last few patterns (kvxopt re-analyses the same pattern
     # in every linsolve call and every IPM iteration); a benchmark that repeats one matrix would only time that cache, so the
     # pattern is changed between repetitions (one explicit zero moved), and the warm (cache-hit) time is reported next to it

@@ -318,6 +318,15 @@ class DistCholesky:
             self.scratch.zero_()
             torch.cuda.current_stream().synchronize()
         _check(fn["b200s_chol_factor_begin"](self.h, values_ptr, 1 if on_device else 0), "factor_begin")
+        import os, time
+        trace = [] if os.environ.get("B200S_DIST_TRACE") else None       # (level, what, ms since begin), device-synchronised
+        t_begin = time.perf_counter()
+
+        def mark(l, what):
+            if trace is not None:
+                fn["b200s_chol_sync"](self.h)
+                trace.append((l, what, (time.perf_counter() - t_begin) * 1e3))
+        self.trace = trace
         for l in range(lay["nlevels"]):
             mine = [m for m in self.xplan[l] if self.rank in (m[1], m[2])]
             slabs = [m for m in self.slab_moves[l] if self.rank in (m[1], m[2])]
@@ -350,8 +359,10 @@ class DistCholesky:
                 for w0, cnt, t in adds:                        # after the update matrix itself has arrived
                     self.Wt[w0: w0 + cnt] += t
                 torch.cuda.current_stream().synchronize()      # received data visible to the handle's stream
+                mark(l, "exchange")
             if l in self.split_levels:
                 _check(fn["b200s_chol_factor_level_phase"](self.h, l, 1), "factor_level (panels)")
+                mark(l, "panels")
                 pm = [m for m in self.panel_moves[l] if self.rank in (m[1], m[2])]
                 if pm:
                     fn["b200s_chol_sync"](self.h)             # the panels of my shared fronts are factored
@@ -363,9 +374,13 @@ class DistCholesky:
                     for w in dist.batch_isend_irecv(ops):
                         w.wait()
                     torch.cuda.current_stream().synchronize()
+                    mark(l, "panel copies")
                 _check(fn["b200s_chol_factor_level_phase"](self.h, l, 2), "factor_level (Schur complements)")
+                mark(l, "schur")
             else:
                 _check(fn["b200s_chol_factor_level"](self.h, l), "factor_level")
+                if l >= lay["nlevels"] - 8:
+                    mark(l, "level")
         minor = C.c_int64()
         st = _check(fn["b200s_chol_factor_end"](self.h, C.byref(minor)), "factor_end")
         m = torch.tensor([int(minor.value) if st == 1 else lay["n"]], device="cuda", dtype=torch.int64)

@@ -31,6 +31,11 @@ for rep in range(3):
     torch.cuda.synchronize(); dist.barrier(); t2 = time.perf_counter()
     if rank == 0:
         print("world %d nx %d rep %d: factor %.1f ms  gather %.1f ms  status %d" % (world, nx, rep, (t1 - t0) * 1e3, (t2 - t1) * 1e3, st), flush=True)
+if os.environ.get("B200S_DIST_TRACE"):
+    for r in range(world):
+        dist.barrier()
+        if r == rank and rank in (0, 1, 4):
+            print("rank %d trace: %s" % (rank, " | ".join("L%d %s %.1f" % t for t in dc.trace)), flush=True)
 if rank == 0:
     info = cholmod.factor_info(F)
     b = np.random.default_rng(0).standard_normal((n, 1)); x = np.asfortranarray(b.copy())
