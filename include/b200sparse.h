@@ -287,6 +287,9 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
  * layout of b200s_klu_extract_host.  Verification of the host-built plan in CPU tests; not a factorization path. */
 b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* val, double* Lx, double* Ux, double* Fx, double* Rs);
 
+/* the pre-ordering held by a symbolic object (klu_symbolic's P, Q, R: BTF + per-block AMD, before any numeric pivoting):
+ * P[n], Q[n], R[nblocks+1]; any may be NULL; *nblocks may be NULL.  For tests and tools. */
+b200s_status b200s_klu_symbolic_perm(const b200s_klu_sym* S, b200s_int* P, b200s_int* Q, b200s_int* R, b200s_int* nblocks);
 void b200s_klu_free_symbolic(b200s_klu_sym* S);   /* src/C/klu.c:51-61 */
 void b200s_klu_free_numeric(b200s_klu_num* N);    /* src/C/klu.c:63-72 */
 

@@ -310,6 +310,13 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
     return B200S_OK;
 }
 
+b200s_status b200s_klu_symbolic_perm(const b200s_klu_sym* S, b200s_int* P, b200s_int* Q, b200s_int* R, b200s_int* nblocks) {
+    if (!S) return B200S_INVALID;
+    for (i32 k = 0; k < S->S.n; k++) { if (P) P[k] = S->S.P[k]; if (Q) Q[k] = S->S.Q[k]; }
+    if (R) for (i32 b = 0; b <= S->S.nblocks; b++) R[b] = S->S.R[b];
+    if (nblocks) *nblocks = S->S.nblocks;
+    return B200S_OK;
+}
 void b200s_klu_free_symbolic(b200s_klu_sym* S) { delete S; }
 void b200s_klu_free_numeric(b200s_klu_num* N) {
     if (!N) return;

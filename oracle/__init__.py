@@ -117,6 +117,7 @@ def _klu_sigs():
     L.oracle_klu_nnz.argtypes = [C.c_void_p, C.c_int]
     L.oracle_klu_flops.restype = C.c_double
     L.oracle_klu_flops.argtypes = [C.c_void_p]
+    L.oracle_klu_pnum.argtypes = [C.c_void_p, pi]
     L._klu_ready = True
     return L
 
@@ -160,6 +161,13 @@ class KluOracle:
 
     def det(self):
         return float(lib().oracle_klu_det(self.h))
+
+    @property
+    def pnum(self):
+        """the pivot sequence chosen by the oracle's own threshold pivoting: pnum[k] = original row of pivotal row k"""
+        out = np.zeros(max(self.n, 1), dtype=np.int64)
+        lib().oracle_klu_pnum(self.h, _p(out, pi))
+        return out[:self.n]
 
     @property
     def nnz_L(self):

@@ -244,3 +244,5 @@ double oracle_klu_det(const oracle_klu* F) {
 }
 i64 oracle_klu_nnz(const oracle_klu* F, int which) { return which ? F->Up[F->n] : F->Lp[F->n]; }
 double oracle_klu_flops(const oracle_klu* F) { return F->flops; }
+/* the pivot sequence the factorization chose: out[k] = original row of pivotal row k (tests compare it with the product's) */
+void oracle_klu_pnum(const oracle_klu* F, i64* out) { for (i64 k = 0; k < F->n; k++) out[k] = F->Pnum[k]; }

@@ -484,3 +484,40 @@ def test_klu_wave_plan_replayed_on_the_host_matches_the_pivoting_factorization(n
     res = abs(lhs - (Lm @ Um + Fm)).max()
     assert res <= 1e-12 * max(1.0, abs(Um).max())
     fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
+@pytest.mark.parametrize("name", ["ACTIVSg2000", "bp_800", "unsym_offdiag", "random"])
+def test_klu_pivot_rule_against_an_independent_run(name):
+    """The pivot RULE of the host pivot search (threshold partial pivoting, tol 1e-3, diagonal preferred, on the row-scaled
+    matrix; klu_defaults) against an independent run: the CPU oracle is given only the SYMBOLIC pre-ordering (BTF + AMD, before
+    any numeric pivoting) and chooses its pivots itself; its pivot sequence must be the product's, row by row."""
+    from conftest import load_matrix
+    from oracle import KluOracle
+    if name == "unsym_offdiag":       # small diagonal entries: most pivots are off the diagonal
+        rng = np.random.default_rng(11)
+        n = 400
+        A = (sp.random(n, n, density=0.02, random_state=rng) + sp.identity(n) * 1e-6 +
+             sp.csc_matrix((rng.uniform(1, 2, n), (rng.permutation(n), np.arange(n))), shape=(n, n))).tocsc()
+    elif name == "random":
+        A = _synthetic_unsym("random")
+    else:
+        A = load_matrix(name).tocsc()
+    A.sort_indices()
+    n = A.shape[0]
+    cp, ri, vx = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+    S = L.vp(); assert fn["b200s_klu_analyze"](n, L.ptr_i64(cp), L.ptr_i64(ri), C.byref(S)) == 0
+    N = L.vp(); assert fn["b200s_klu_pivot_host"](S, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(N)) == 0
+    P0, Q0 = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    assert fn["b200s_klu_symbolic_perm"](S, L.ptr_i64(P0), L.ptr_i64(Q0), None, None) == 0
+    Pn, Qn = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    fn["b200s_klu_extract"](N, None, None, None, None, None, None, None, None, None, L.ptr_i64(Pn), L.ptr_i64(Qn), None, None)
+    assert np.array_equal(Qn, Q0)                       # numeric pivoting permutes rows only
+    O = KluOracle(n, cp, ri, vx, P0=P0, Q=Q0)            # the oracle's own pivoting from the symbolic pre-ordering
+    assert np.array_equal(O.pnum, Pn)
+    if name == "unsym_offdiag":
+        assert (Pn != P0).sum() > n // 4                # the case really pivots off the diagonal
+    inf = L.KluInfo(); fn["b200s_klu_info"](N, C.byref(inf))
+    # same pivots => same L pattern (L is block diagonal in BTF form); with several blocks the one-block oracle fills the
+    # off-diagonal part of U that KLU keeps unfactored in F
+    assert O.nnz_L == inf.nnz_L and (inf.nblocks > 1 or O.nnz_U == inf.nnz_U)
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)

@@ -1,5 +1,8 @@
-"""Small end-to-end pass over every kernel for compute-sanitizer (memcheck): Cholesky (small + tiled fronts, solves,
-sys modes, diag, getfactor) and KLU (factor, batch refactor wave kernel, solves)."""
+"""Small end-to-end pass over every kernel for compute-sanitizer:
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py        (also --tool racecheck / synccheck)
+Cholesky (small + tiled fronts, solves, sys modes, diag, getfactor, sparse right-hand sides, complex Hermitian, shared Schur
+complements through virtual ranks), KLU (factor, early-column kernel, batch refactor wave kernel, dense block, solves), the KKT
+solvers."""
 import os, sys
 import numpy as np, scipy.sparse as sp
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -48,3 +51,33 @@ for rep in range(2):
     sol = fac({"di": 1.0 / rng.uniform(0.3, 3.0, mk)}, sp.tril(Hk).tocsc())
     x, y, zz = rng.standard_normal(nk), rng.standard_normal(pk), rng.standard_normal(mk); sol(x, y, zz)
 print("streaming + ldl + kkt ok", flush=True)
+
+# early-column kernel on a small pattern (threshold lowered), sparse right-hand sides, complex Hermitian matrices, dense 'chol'
+os.environ["B200S_KLU_EARLY_MINW"] = "4"
+z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "bp_800.npz"))
+K = sp.csc_matrix((z["values"], z["rowind"].astype(np.int64), z["colptr"]), shape=(int(z["n"]),) * 2)
+Fs = klu.symbolic(K); Fn = klu.numeric(K, Fs)
+vals = K.data[None, :] * (1 + 1e-3 * rng.uniform(-1, 1, size=(40, K.nnz)))
+assert not klu.refactor_batch(Fn, vals).any()
+del os.environ["B200S_KLU_EARLY_MINW"]
+Al, perm = lap(10); n = Al.shape[0]
+F = cholmod.symbolic(Al, p=perm); cholmod.numeric(Al, F)
+Bs = sp.random(n, 3, density=0.01, random_state=rng, format="csc"); Bs.sort_indices()
+for s_ in (0, 4, 7):
+    cholmod.spsolve(F, Bs, sys=s_)
+Mz = sp.random(300, 300, density=0.02, random_state=rng, format="csc")
+Az = (Mz + 1j * sp.random(300, 300, density=0.02, random_state=rng, format="csc")).tocsc(); Az = (Az + Az.getH()).tocsc()
+Az = (Az + sp.diags(np.asarray(abs(Az).sum(axis=1)).ravel() + 1.0)).tocsc()
+Azl = sp.tril(Az).tocsc(); Azl.sort_indices()
+Xz = np.asfortranarray(np.ones((300, 2), dtype=complex)); cholmod.linsolve(Azl, Xz)
+Fz = cholmod.symbolic(Azl); cholmod.numeric(Azl, Fz); cholmod.diag(Fz); cholmod.getfactor(Fz)
+fc = kkt.chol(Gk, {"l": mk, "q": [], "s": []}, Ak)
+solc = fc({"di": 1.0 / rng.uniform(0.3, 3.0, mk)}, Hk)
+x, y, zz = rng.standard_normal(nk), rng.standard_normal(pk), rng.standard_normal(mk); solc(x, y, zz)
+from kvxopt_b200 import dist as D
+Al, perm = lap(16)
+caps = [cholmod.symbolic(Al, p=perm) for _ in range(4)]
+vr = D.VirtualRanks(caps, split=True, split_args=dict(min_flops=1e4, min_rows=64))
+assert vr.factorize(Al.data) == Al.shape[0]
+X = np.ones((Al.shape[0], 1), order="F"); cholmod.solve(caps[0], X)
+print("early + spsolve + complex + kkt.chol + shared Schur complements (%d shared fronts) ok" % len(vr.splan), flush=True)
