@@ -86,3 +86,48 @@ def test_cholesky_100cubed_properties():
     cholmod.numeric(Al, F)
     X2 = np.asfortranarray(B.copy()); cholmod.solve(F, X2)
     assert np.array_equal(X, X2)
+
+
+_C5_CHILD = r"""
+import json, os, sys
+import numpy as np, scipy.sparse as sp
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "oracle", "_ref")); sys.path.insert(0, os.path.join(root, "tests", "golden"))
+import kvxopt
+from kvxopt import matrix, spmatrix, solvers
+from kvxopt_b200 import kkt
+from generators import qp_instance
+solvers.options["show_progress"] = False
+P, q, G, h = qp_instance(500, 400, 5000)
+def tosp(M):
+    M = sp.coo_matrix(M)
+    return spmatrix(M.data.tolist(), M.row.tolist(), M.col.tolist(), M.shape)
+Pk, Gk = tosp(sp.tril(P)), tosp(G)
+sol = solvers.qp(Pk, matrix(q), Gk, matrix(h), kktsolver=kkt.qp_kktsolver(Pk, Gk))
+x = np.array(sol["x"]).ravel()
+print("C5RESULT " + json.dumps({"status": sol["status"], "iterations": sol["iterations"], "pobj": sol["primal objective"],
+                                 "max_violation": float((G @ x - h).max())}))
+"""
+
+
+def test_config5_qp_200k_variables_through_coneqp():
+    """BASELINE configs[4] at full size: the 200 000-variable sparse QP through the UNMODIFIED reference coneqp with the device
+    KKT solver plugged in through kktsolver=; golden = the same IPM with the CPU oracle as its factorization
+    (tests/golden/qp_config5_golden.json): same iteration count, objective to 1e-8 relative.  Runs in a child process with
+    OPENBLAS_NUM_THREADS=1 set before the BLAS loads: the reference's own misc_solvers.scale crashes under multi-threaded
+    OpenBLAS at m >= 4e5 rows."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLD, ROOT
+    gold = json.load(open(os.path.join(GOLD, "qp_config5_golden.json")))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-c", _C5_CHILD, ROOT], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("C5RESULT ")][-1]
+    sol = json.loads(line[len("C5RESULT "):])
+    assert sol["status"] == gold["status"]
+    assert sol["iterations"] == gold["iterations"]
+    assert abs(sol["pobj"] - gold["primal_objective"]) <= 1e-8 * abs(gold["primal_objective"])
+    assert sol["max_violation"] <= 1e-6          # G x <= h at the returned point
