@@ -177,6 +177,22 @@ b200s_status b200s_chol_front_layout(const b200s_chol* F, b200s_int* parent, b20
                                      b200s_int* nrows, b200s_int* loff, b200s_int* lsize, b200s_int* uoff,
                                      b200s_int* usize);
 b200s_status b200s_chol_device_buffers(b200s_chol* F, double** L_dev, double** W_dev);
+/* Distributed triangular solves (one right-hand side; LL' factors): the panels stay on the GPUs that factored them.
+ *   begin: X = P b (b_dev: n doubles on this device; every process passes the same b);
+ *   level (backward = 0, levels 0 .. nlevels-1): the owned fronts of the level gather their pivots from X and their children's
+ *     update vectors from the work-vector buffer T, solve, leave y in X[col0 ..] and their own update vector in
+ *     T[rowptr[s] + ncols[s] .. rowptr[s] + nrows[s]) -- before the call the caller copies the update vectors of children owned
+ *     by another process to the same place in its T (identical layout everywhere);
+ *   level (backward = 1, levels nlevels-1 .. 0): the owned fronts gather x at their row lists from X and write x(columns) to
+ *     X[col0[s] .. col0[s] + ncols[s]) -- before the call the caller copies the solution entries of ancestors owned elsewhere;
+ *   end: x_dev = P' X (meaningful where X is complete: the caller collects the column ranges first).
+ * b200s_chol_solve_buffers returns T and X (device pointers, valid until the factor object is freed or solves with more
+ * right-hand-side columns grow the workspace); b200s_chol_front_layout2 the per-front offsets into them. */
+b200s_status b200s_chol_solve_dist_begin(b200s_chol* F, const double* b_dev);
+b200s_status b200s_chol_solve_dist_level(b200s_chol* F, int backward, b200s_int level);
+b200s_status b200s_chol_solve_dist_end(b200s_chol* F, double* x_dev);
+b200s_status b200s_chol_solve_buffers(b200s_chol* F, double** T_dev, double** X_dev);
+b200s_status b200s_chol_front_layout2(const b200s_chol* F, b200s_int* rowptr, b200s_int* col0);
 /* after the panels of all fronts have been gathered into L_dev: declare the factor numeric so that solves run */
 b200s_status b200s_chol_set_numeric(b200s_chol* F, int numeric, b200s_int minor);
 

@@ -68,6 +68,11 @@ SIGNATURES = {
     "b200s_chol_factor_begin": (C.c_int, vp, vp, C.c_int),
     "b200s_chol_factor_level": (C.c_int, vp, i64),
     "b200s_chol_factor_level_phase": (C.c_int, vp, i64, C.c_int),
+    "b200s_chol_solve_dist_begin": (C.c_int, vp, vp),
+    "b200s_chol_solve_dist_level": (C.c_int, vp, C.c_int, i64),
+    "b200s_chol_solve_dist_end": (C.c_int, vp, vp),
+    "b200s_chol_solve_buffers": (C.c_int, vp, C.POINTER(vp), C.POINTER(vp)),
+    "b200s_chol_front_layout2": (C.c_int, vp, p_i64, p_i64),
     "b200s_chol_set_syrk_split": (C.c_int, vp, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), p_i64, vp),
     "b200s_chol_factor_end": (C.c_int, vp, p_i64),
     "b200s_chol_sync": (C.c_int, vp),

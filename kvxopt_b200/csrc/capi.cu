@@ -380,6 +380,35 @@ b200s_status b200s_chol_front_layout(const b200s_chol* F, b200s_int* parent, b20
     }
     return B200S_OK;
 }
+/* distributed solves: one right-hand side, level by level over the fronts marked by b200s_chol_set_owned */
+b200s_status b200s_chol_solve_dist_begin(b200s_chol* F, const double* b_dev) {
+    if (!F || !F->dev || !b_dev) return B200S_INVALID;
+    if (!F->numeric) { set_last_error("called with symbolic factor"); return B200S_INVALID; }
+    return (b200s_status)chol_device_solve_dist_begin(F->dev, b_dev);
+}
+b200s_status b200s_chol_solve_dist_level(b200s_chol* F, int backward, b200s_int level) {
+    if (!F || !F->dev) return B200S_INVALID;
+    return (b200s_status)chol_device_solve_dist_level(F->dev, backward, (int)level);
+}
+b200s_status b200s_chol_solve_dist_end(b200s_chol* F, double* x_dev) {
+    if (!F || !F->dev || !x_dev) return B200S_INVALID;
+    return (b200s_status)chol_device_solve_dist_end(F->dev, x_dev);
+}
+b200s_status b200s_chol_solve_buffers(b200s_chol* F, double** T_dev, double** X_dev) {
+    if (!F || !T_dev || !X_dev) return B200S_INVALID;
+    b200s_status es = ensure_device(F);
+    if (es != B200S_OK) return es;
+    return (b200s_status)chol_device_solve_buffers(F->dev, T_dev, X_dev);
+}
+b200s_status b200s_chol_front_layout2(const b200s_chol* F, b200s_int* rowptr, b200s_int* col0) {
+    if (!F) return B200S_INVALID;
+    const CholPlan& P = F->plan();
+    for (size_t s = 0; s < P.fronts.size(); s++) {
+        if (rowptr) rowptr[s] = P.fronts[s].rowptr;
+        if (col0) col0[s] = P.fronts[s].col0;
+    }
+    return B200S_OK;
+}
 b200s_status b200s_chol_device_buffers(b200s_chol* F, double** L_dev, double** W_dev) {
     if (!F || !L_dev || !W_dev) return B200S_INVALID;
     b200s_status es = ensure_device(F);

@@ -771,9 +771,11 @@ constexpr int CB = 32;
 __global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const FrontD* __restrict__ F,
                                              const int* __restrict__ child_idx, const int* __restrict__ rel,
                                              const double* __restrict__ L, double* __restrict__ T, long long tstride,
-                                             double* __restrict__ X, long long xstride) {
+                                             double* __restrict__ X, long long xstride,
+                                             const unsigned char* __restrict__ owned = nullptr) {
     __shared__ double D[CB][CB + 1];
     __shared__ double xs[CB];
+    if (owned && !owned[list[blockIdx.x]]) return;       // distributed solves: another GPU's front
     const FrontD f = F[list[blockIdx.x]];
     double* t = T + blockIdx.y * tstride + f.rowptr;
     double* x = X + blockIdx.y * xstride + f.col0;
@@ -819,9 +821,10 @@ __global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const
 __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const FrontD* __restrict__ F,
                                              const int* __restrict__ rows, const double* __restrict__ L,
                                              double* __restrict__ T, long long tstride, double* __restrict__ X,
-                                             long long xstride) {
+                                             long long xstride, const unsigned char* __restrict__ owned = nullptr) {
     __shared__ double D[CB][CB + 1];
     __shared__ double zs[CB];
+    if (owned && !owned[list[blockIdx.x]]) return;
     const FrontD f = F[list[blockIdx.x]];
     double* t = T + blockIdx.y * tstride + f.rowptr;
     double* xg = X + blockIdx.y * xstride;
@@ -912,8 +915,9 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list
                                                     const FrontD* __restrict__ F,
                                                     const int* __restrict__ child_idx, const int* __restrict__ rel,
                                                     double* __restrict__ T, long long tstride, const double* __restrict__ X,
-                                                    long long xstride) {
+                                                    long long xstride, const unsigned char* __restrict__ owned = nullptr) {
     const int g = find_group(cprefix, nfronts, blockIdx.x);
+    if (owned && !owned[list[g]]) return;
     const FrontD f = F[list[g]];
     const int a = (blockIdx.x - cprefix[g]) * GATHER_ROWS, b = min(f.nr, a + GATHER_ROWS);
     double* t = T + blockIdx.y * tstride + f.rowptr;
@@ -939,7 +943,9 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list
 // backward: t = x(rows of the front)
 __global__ void __launch_bounds__(256) k_bwd_gather(const int* __restrict__ list, const FrontD* __restrict__ F,
                                                     const int* __restrict__ rows, double* __restrict__ T, long long tstride,
-                                                    const double* __restrict__ X, long long xstride) {
+                                                    const double* __restrict__ X, long long xstride,
+                                                    const unsigned char* __restrict__ owned = nullptr) {
+    if (owned && !owned[list[blockIdx.x]]) return;
     const FrontD f = F[list[blockIdx.x]];
     double* t = T + blockIdx.y * tstride + f.rowptr;
     const double* xg = X + blockIdx.y * xstride;
@@ -968,12 +974,14 @@ __device__ __forceinline__ void stage_diag_block(const double* __restrict__ P, i
 __global__ void __launch_bounds__(256) k_fwd_diag(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, int kb, const FrontD* __restrict__ F,
                                                   const double* __restrict__ L, const double* __restrict__ Minv,
                                                   double* __restrict__ T, long long tstride,
-                                                  double* __restrict__ X, long long xstride) {
+                                                  double* __restrict__ X, long long xstride,
+                                                  const unsigned char* __restrict__ owned = nullptr) {
     extern __shared__ double sm[];
     double* Ls = sm;                       // [col][row], stride LDD
     double* Ms = Ls + NB * LDD;            // [sub-block][col][row], stride LDM
     double* ts = Ms + MINV_HALF;
     const FrontS f = load_front(sg, gfront, F, blockIdx.x);
+    if (owned && !owned[f.id]) return;
     double* t = T + blockIdx.y * tstride + f.rowptr;
     double* x = X + blockIdx.y * xstride + f.col0;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1022,7 +1030,8 @@ __device__ __forceinline__ void stage_rows64(const double* __restrict__ P, int l
 template <int CG>
 __global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
-                                                 double* __restrict__ T, long long tstride, int ncols) {
+                                                 double* __restrict__ T, long long tstride, int ncols,
+                                                 const unsigned char* __restrict__ owned = nullptr) {
     extern __shared__ double sm[];
     double* S = sm;                        // [128 columns][64 rows]
     __shared__ double xs[CG][NB];
@@ -1030,6 +1039,7 @@ __global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGr
     int tile;
     const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
     const FrontS f = load_front(sg, gfront, F, g);
+    if (owned && !owned[f.id]) return;
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x;
     const int rr = tid & (SOLVE_FT - 1), cq = tid >> 6;
     const int rb = k0 + w, r0 = (rb & ~1) + tile * SOLVE_FT;      // tiles start at an even row (16-byte LDGSTS)
@@ -1081,12 +1091,13 @@ template <int CG>
 __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
                                                  const double* __restrict__ T, long long tstride, double* __restrict__ part,
-                                                 long long pstride, int ncols) {
+                                                 long long pstride, int ncols, const unsigned char* __restrict__ owned = nullptr) {
     extern __shared__ double sm[];         // 3 buffers of [128 columns][64 rows]
     __shared__ double red[CG][8][32];
     int tile;
     const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
     const FrontS f = load_front(sg, gfront, F, g);
+    if (owned && !owned[f.id]) return;
     const int c0 = blockIdx.y * CG, cn = min(CG, ncols - c0);
     const double* t = T + c0 * tstride + f.rowptr;
     const double* P = L + f.loff;
@@ -1159,7 +1170,8 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
                                                   const FrontD* __restrict__ F, const double* __restrict__ L,
                                                   const double* __restrict__ Minv,
                                                   double* __restrict__ T, long long tstride, double* __restrict__ X,
-                                                  long long xstride, const double* __restrict__ part, long long pstride) {
+                                                  long long xstride, const double* __restrict__ part, long long pstride,
+                                                  const unsigned char* __restrict__ owned = nullptr) {
     extern __shared__ double sm[];
     double* Ls = sm;
     double* Ms = Ls + NB * LDD;
@@ -1167,6 +1179,7 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
     double* Ps = zs + NB;                  // [PT_CHUNK][128] staged partial sums
     __shared__ double zh[NB];
     const FrontS f = load_front(sg, gfront, F, blockIdx.x);
+    if (owned && !owned[f.id]) return;
     double* t = T + blockIdx.y * tstride + f.rowptr;
     double* x = X + blockIdx.y * xstride + f.col0;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1374,6 +1387,10 @@ public:
     double* dsgn = nullptr;       // ldl: sign of every pivot (+-1, permuted order, padded), written by the factorization kernels
     bool diagL_valid = false;
     int ensure_solve_ws(i64 cols);
+    // distributed solves (kvxopt_b200/dist.py): one right-hand side, level by level, only the fronts marked by set_owned
+    int solve_dist_begin(const double* b_dev);
+    int solve_dist_level(int backward, int l);
+    int solve_dist_end(double* x_dev);
 };
 
 static constexpr size_t SMEM_PANEL = (size_t)(NB * LDL + NB * LDX + NB) * sizeof(double);
@@ -2022,7 +2039,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                             const Launch& la = LS.sfwd[kb];
                             k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n);
                             if (la.ctas)
-                                (nc == 1 ? k_fwd_upd<1> : k_fwd_upd<4>)<<<la.ctas, 256, SMEM_FUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride, nc);
+                                (nc == 1 ? k_fwd_upd<1> : k_fwd_upd<4>)<<<la.ctas, 256, SMEM_FUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride, nc, (const unsigned char*)nullptr);
                         }
                     }
                 }
@@ -2037,7 +2054,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                             const Launch& la = LS.sbwd[kb];
                             if (la.ctas)
                                 (nc == 1 ? k_bwd_upd<1> : k_bwd_upd<BWD_CG>)<<<dim3(la.ctas, nc == 1 ? 1 : (nc + BWD_CG - 1) / BWD_CG), 256, SMEM_BUPD, stream>>>(
-                                    sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride, nc);
+                                    sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride, nc, (const unsigned char*)nullptr);
                             k_bwd_diag<<<dim3(la.ng, nc), 256, SMEM_BDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dMinv, dT, tstride, dX, n, dpart, pstride);
                         }
                     }
@@ -2075,6 +2092,78 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     CUDA_TRY(le);
     CUDA_TRY(se);
     if (times) { float ms; cudaEventElapsedTime(&ms, ev[4], ev[5]); times->ms_solve = ms; }
+    return ST_OK;
+}
+
+// ---- level-stepped solve for factors whose fronts live on several GPUs -------------------------------------------------
+// begin: X = P b (every rank has b); level (forward, leaves to root): the owned fronts of one level gather their pivots
+// from X and their children's update vectors from T -- the caller has copied the update vectors of children owned by another
+// GPU into T before (identical layout on every rank) --, solve, and leave y in X and their update vector in T; level
+// (backward, root to leaves): the owned fronts gather x at their row lists from X -- the caller has copied the solution
+// entries of ancestors owned elsewhere into X --, and write x(columns) to X; end: x = P' X.  LL' factors only.
+int CholDevice::solve_dist_begin(const double* b_dev) {
+    const int n = plan->n;
+    CUDA_TRY(cudaSetDevice(device));
+    if (n == 0) return ST_OK;
+    if (ldl) return ST_INVALID;
+    int rc = ensure_solve_ws(1);
+    if (rc) return rc;
+    if (ninvblk > 0 && !minv_valid) {
+        k_diag_inverse<<<ninvblk, 128, 0, stream>>>(dinv_front, dinv_kb, dF, dL, dMinv);
+        minv_valid = true;
+    }
+    const int gx = std::min((n + 255) / 256, 148 * 8);
+    k_perm_gather<<<dim3(gx, 1), 256, 0, stream>>>(b_dev, n, dperm, n, dX, n);
+    CUDA_TRY(cudaGetLastError());
+    return ST_OK;
+}
+
+int CholDevice::solve_dist_level(int backward, int l) {
+    const CholPlan& P = *plan;
+    if (l < 0 || l >= P.nlevels) return ST_INVALID;
+    CUDA_TRY(cudaSetDevice(device));
+    const int n = P.n, nc = 1;
+    const i64 tstride = (i64)P.rows.size();
+    const long long pstride = (long long)max_solve_ctas * NB;
+    const LevelSched& LS = levels[l];
+    if (!backward) {
+        if (LS.small_all_cnt)
+            k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n, downed);
+        if (!LS.panel.empty() && LS.panel[0].ng) {
+            k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, downed);
+            for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
+                const Launch& la = LS.sfwd[kb];
+                k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n, downed);
+                if (la.ctas)
+                    k_fwd_upd<1><<<la.ctas, 256, SMEM_FUPD, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, (int)kb, dF, dL, dT, tstride, nc, downed);
+            }
+        }
+    } else {
+        if (!LS.panel.empty() && LS.panel[0].ng) {
+            k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n, downed);
+            for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
+                const Launch& la = LS.sbwd[kb];
+                if (la.ctas)
+                    k_bwd_upd<1><<<dim3(la.ctas, 1), 256, SMEM_BUPD, stream>>>(
+                        sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, la.ng, kb, dF, dL, dT, tstride, dpart, pstride, nc, downed);
+                k_bwd_diag<<<dim3(la.ng, nc), 256, SMEM_BDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dMinv, dT, tstride, dX, n, dpart, pstride, downed);
+            }
+        }
+        if (LS.small_all_cnt)
+            k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n, downed);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ST_OK;
+}
+
+int CholDevice::solve_dist_end(double* x_dev) {
+    const int n = plan->n;
+    CUDA_TRY(cudaSetDevice(device));
+    if (n == 0) return ST_OK;
+    const int gx = std::min((n + 255) / 256, 148 * 8);
+    k_perm_scatter<<<dim3(gx, 1), 256, 0, stream>>>(x_dev, n, dperm, n, dX, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
     return ST_OK;
 }
 
@@ -2280,6 +2369,14 @@ int chol_device_sync(CholDevice* d) {
     return ST_OK;
 }
 void chol_device_buffers(CholDevice* d, double** L, double** W) { *L = d->dL; *W = d->dW; }
+int chol_device_solve_dist_begin(CholDevice* d, const double* b_dev) { return d->solve_dist_begin(b_dev); }
+int chol_device_solve_dist_level(CholDevice* d, int backward, int level) { return d->solve_dist_level(backward, level); }
+int chol_device_solve_dist_end(CholDevice* d, double* x_dev) { return d->solve_dist_end(x_dev); }
+int chol_device_solve_buffers(CholDevice* d, double** T, double** X) {
+    int rc = d->ensure_solve_ws(1);
+    *T = d->dT; *X = d->dX;
+    return rc;
+}
 void chol_device_mark_numeric(CholDevice* d, bool numeric) { d->numeric = numeric; d->minv_valid = false; }
 i64 chol_device_workspace_bytes(const CholDevice* d) { return d->total_bytes; }
 

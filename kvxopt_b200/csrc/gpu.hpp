@@ -43,6 +43,10 @@ int  chol_device_set_owned(CholDevice* d, const unsigned char* owned);
 int  chol_device_factor_begin(CholDevice* d, const double* val, bool on_device);
 int  chol_device_factor_level(CholDevice* d, int level);
 int  chol_device_factor_level_phase(CholDevice* d, int level, int phase);
+int  chol_device_solve_dist_begin(CholDevice* d, const double* b_dev);
+int  chol_device_solve_dist_level(CholDevice* d, int backward, int level);
+int  chol_device_solve_dist_end(CholDevice* d, double* x_dev);
+int  chol_device_solve_buffers(CholDevice* d, double** T, double** X);
 int  chol_device_set_syrk_split(CholDevice* d, const unsigned char* own, const int* lo, const int* hi, const long long* base, double* scratch);
 int  chol_device_factor_end(CholDevice* d, i64* minor, CholTimes* times);
 int  chol_device_sync(CholDevice* d);

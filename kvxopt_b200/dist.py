@@ -52,6 +52,9 @@ def front_layout(h):
     st = fn["b200s_chol_front_layout"](h, *[L.ptr_i64(a[k]) for k in ("parent", "level", "nc", "nr", "loff", "lsize", "uoff", "usize")])
     assert st == 0
     lay = {k: v[:ns] for k, v in a.items()}
+    rp, c0 = np.zeros(max(ns, 1), dtype=np.int64), np.zeros(max(ns, 1), dtype=np.int64)
+    assert fn["b200s_chol_front_layout2"](h, L.ptr_i64(rp), L.ptr_i64(c0)) == 0
+    lay["rowptr"], lay["col0"] = rp[:ns], c0[:ns]       # offsets into the solve work vectors / the permuted solution
     lay["nlevels"] = int(inf.nlevels)
     lay["n"] = int(inf.n)
     return lay
@@ -231,6 +234,50 @@ def gather_plan(lay, owner, root=0):
     return runs
 
 
+def solve_moves(lay, owner, g0, g1, root=0):
+    """Transfers of the distributed triangular solves (pure function of the plan):
+    fwd[l]:  (child s, src, dst) -- the update vector of s, T[rowptr[s] + nc[s] .. rowptr[s] + nr[s]), goes to the owner of its
+             parent before forward level l = level[parent] runs (the cut edges of exchange_plan);
+    bwd[l]:  (front f, src, dst) -- after backward level l = level[f] the solution entries X[col0[f] .. + nc[f]) go from the
+             owner of f to every other rank of its subtree group (their fronts below need them in their row gathers);
+    gather:  (rank, c0, c1) -- column ranges of the permuted solution that `root` collects at the end."""
+    parent, level = lay["parent"], lay["level"]
+    nl = lay["nlevels"]
+    fwd = [[] for _ in range(nl)]
+    bwd = [[] for _ in range(nl)]
+    for s in range(len(owner)):
+        p = parent[s]
+        if p >= 0 and owner[p] != owner[s] and lay["nr"][s] > lay["nc"][s]:
+            fwd[level[p]].append((s, int(owner[s]), int(owner[p])))
+        for r in range(int(g0[s]), int(g1[s])):
+            if r != owner[s]:
+                bwd[level[s]].append((s, int(owner[s]), r))
+    gather = []
+    ns = len(owner)
+    s = 0
+    while s < ns:
+        e = s
+        while e + 1 < ns and owner[e + 1] == owner[s]:
+            e += 1
+        if owner[s] != root:
+            gather.append((int(owner[s]), int(lay["col0"][s]), int(lay["col0"][e] + lay["nc"][e])))
+        s = e + 1
+    return fwd, bwd, gather
+
+
+def _solve_views(h, lay):
+    import torch
+    Tp, Xp = L.vp(), L.vp()
+    st = fn["b200s_chol_solve_buffers"](h, C.byref(Tp), C.byref(Xp))
+    if st != 0:
+        raise RuntimeError("solve buffers: %s (%s)" % (L.strerror(st), L.last_error()))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tsize = int((lay["rowptr"] + lay["nr"]).max()) if len(lay["nr"]) else 0
+    Tt = torch.as_tensor(_DevArray(Tp.value, max(tsize, 1)), device=dev)
+    Xt = torch.as_tensor(_DevArray(Xp.value, max(lay["n"], 1)), device=dev)
+    return Tt, Xt
+
+
 class _DevArray:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
@@ -298,6 +345,8 @@ class DistCholesky:
         self.owner, g0, g1 = ownership(self.lay, world, with_groups=True)
         self.xplan = exchange_plan(self.lay, self.owner)
         self.gplan = gather_plan(self.lay, self.owner)
+        self.sfwd, self.sbwd, self.sgather = solve_moves(self.lay, self.owner, g0, g1)
+        self.minor = self.lay["n"]
         mine = (self.owner == rank).astype(np.uint8)
         _check(fn["b200s_chol_set_owned"](self.h, mine.tobytes()), "set_owned")
         self.Lt, self.Wt = _device_views(self.h, self.lay)
@@ -388,6 +437,62 @@ class DistCholesky:
         self.minor = int(m.item())
         return (1 if self.minor < lay["n"] else 0), self.minor
 
+    def solve(self, b):
+        """Distributed solve of A x = b with the panels where they were factored (no gather_factor needed): `b` is a CUDA
+        float64 tensor of length n, meaningful on rank 0 (it is broadcast); returns x as a CUDA tensor on rank 0 (None
+        elsewhere).  Forward sweep leaves to root with the update vectors of the cut edges sent up, backward sweep root to
+        leaves with the solution entries of the top fronts sent down their subtree groups."""
+        import torch
+        import torch.distributed as dist
+        lay, h, rank = self.lay, self.h, self.rank
+        if self.minor < lay["n"]:
+            raise ArithmeticError("singular matrix")
+        if not hasattr(self, "Tt"):
+            _check(fn["b200s_chol_set_numeric"](h, 1, lay["n"]), "set_numeric")     # this rank's panels are numeric
+            self.Tt, self.Xt = _solve_views(h, lay)
+        bb = b if rank == 0 else torch.empty(lay["n"], dtype=torch.float64, device=self.Xt.device)
+        dist.broadcast(bb, src=0, group=self.group)
+        torch.cuda.current_stream().synchronize()
+        _check(fn["b200s_chol_solve_dist_begin"](h, C.c_void_p(bb.data_ptr())), "solve_begin")
+
+        def exchange(moves, view, rng):
+            mine = [m for m in moves if rank in (m[1], m[2])]
+            if not mine:
+                return
+            fn["b200s_chol_sync"](h)
+            ops = []
+            for s_, src, dst in mine:
+                a, e = rng(s_)
+                t = view[a:e]
+                ops.append(dist.P2POp(dist.isend if src == rank else dist.irecv, t, dst if src == rank else src, group=self.group))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            torch.cuda.current_stream().synchronize()
+        upd = lambda s_: (int(lay["rowptr"][s_] + lay["nc"][s_]), int(lay["rowptr"][s_] + lay["nr"][s_]))
+        cols = lambda s_: (int(lay["col0"][s_]), int(lay["col0"][s_] + lay["nc"][s_]))
+        for l in range(lay["nlevels"]):
+            exchange(self.sfwd[l], self.Tt, upd)
+            _check(fn["b200s_chol_solve_dist_level"](h, 0, l), "solve_level (forward)")
+        for l in range(lay["nlevels"] - 1, -1, -1):
+            _check(fn["b200s_chol_solve_dist_level"](h, 1, l), "solve_level (backward)")
+            exchange(self.sbwd[l], self.Xt, cols)
+        fn["b200s_chol_sync"](h)
+        ops = []
+        for rk, c0, c1 in self.sgather:
+            if rank == rk:
+                ops.append(dist.P2POp(dist.isend, self.Xt[c0:c1], 0, group=self.group))
+            elif rank == 0:
+                ops.append(dist.P2POp(dist.irecv, self.Xt[c0:c1], rk, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        torch.cuda.current_stream().synchronize()
+        if rank != 0:
+            return None
+        x = torch.empty(lay["n"], dtype=torch.float64, device=self.Xt.device)
+        _check(fn["b200s_chol_solve_dist_end"](h, C.c_void_p(x.data_ptr())), "solve_end")
+        return x
+
     def gather_factor(self, root=0):
         """collect all panels on `root` (contiguous runs of fronts per owner) and mark its factor numeric"""
         import torch
@@ -424,6 +529,8 @@ class VirtualRanks:
         self.splan = split_plan(self.lay, self.owner, g0, g1, **(split_args or {})) if split and self.world > 1 else {}
         self.panel_moves, self.slab_moves = split_moves(self.lay, self.owner, self.splan)
         self.split_levels = {int(self.lay["level"][s]) for s in self.splan}
+        self.sfwd, self.sbwd, self.sgather = solve_moves(self.lay, self.owner, g0, g1)
+        self.sviews = None
         self.views, self.sts, self.scratch = [], [], []
         for r, h in enumerate(self.hs):
             _check(fn["b200s_chol_set_owned"](h, (self.owner == r).astype(np.uint8).tobytes()), "set_owned")
@@ -480,3 +587,46 @@ class VirtualRanks:
         torch.cuda.synchronize()
         _check(fn["b200s_chol_set_numeric"](self.hs[0], 1 if self.minor >= lay["n"] else 0, self.minor), "set_numeric")
         return self.minor
+
+    def solve(self, b):
+        """the distributed solve protocol of DistCholesky.solve with device-to-device copies (every handle keeps its own panels:
+        call it right after factorize(); the panel gather is not needed for it)"""
+        import torch
+        lay = self.lay
+        dev = torch.device("cuda", torch.cuda.current_device())
+        bb = torch.as_tensor(np.ascontiguousarray(b, dtype=np.float64).reshape(-1), device=dev)
+        if self.sviews is None:
+            for h in self.hs:
+                _check(fn["b200s_chol_set_numeric"](h, 1, lay["n"]), "set_numeric")
+            self.sviews = [_solve_views(h, lay) for h in self.hs]
+        for h in self.hs:
+            _check(fn["b200s_chol_solve_dist_begin"](h, C.c_void_p(bb.data_ptr())), "solve_begin")
+
+        def sync_all():
+            for h in self.hs:
+                fn["b200s_chol_sync"](h)
+        for l in range(lay["nlevels"]):
+            if self.sfwd[l]:
+                sync_all()
+                for s_, src, dst in self.sfwd[l]:
+                    a, e = int(lay["rowptr"][s_] + lay["nc"][s_]), int(lay["rowptr"][s_] + lay["nr"][s_])
+                    self.sviews[dst][0][a:e].copy_(self.sviews[src][0][a:e])
+                torch.cuda.synchronize()
+            for h in self.hs:
+                _check(fn["b200s_chol_solve_dist_level"](h, 0, l), "solve_level (forward)")
+        for l in range(lay["nlevels"] - 1, -1, -1):
+            for h in self.hs:
+                _check(fn["b200s_chol_solve_dist_level"](h, 1, l), "solve_level (backward)")
+            if self.sbwd[l]:
+                sync_all()
+                for s_, src, dst in self.sbwd[l]:
+                    a, e = int(lay["col0"][s_]), int(lay["col0"][s_] + lay["nc"][s_])
+                    self.sviews[dst][1][a:e].copy_(self.sviews[src][1][a:e])
+                torch.cuda.synchronize()
+        sync_all()
+        for rk, c0, c1 in self.sgather:
+            self.sviews[0][1][c0:c1].copy_(self.sviews[rk][1][c0:c1])
+        torch.cuda.synchronize()
+        x = torch.empty(lay["n"], dtype=torch.float64, device=dev)
+        _check(fn["b200s_chol_solve_dist_end"](self.hs[0], C.c_void_p(x.data_ptr())), "solve_end")
+        return x.cpu().numpy()

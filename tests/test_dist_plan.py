@@ -116,3 +116,44 @@ def test_shared_schur_complement_plan(world):
     tot = sum(D._work_share(lay, owner, splan, r) for r in range(world))
     assert abs(tot - D.front_work(lay).sum()) <= 1e-9 * tot
     fn["b200s_chol_free"](F)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_distributed_solve_moves(world):
+    """solve_moves: update vectors travel exactly along the cut edges before the parent's forward level; after a top front's
+    backward level its solution entries reach every other rank that owns a descendant; the final gather covers exactly the
+    columns not owned by rank 0"""
+    F = handle_for(20, 20, 20)
+    lay = D.front_layout(F)
+    owner, g0, g1 = D.ownership(lay, world, with_groups=True)
+    fwd, bwd, gather = D.solve_moves(lay, owner, g0, g1)
+    parent, level = lay["parent"], lay["level"]
+    ns = len(owner)
+    cut = sorted(s for s in range(ns) if parent[s] >= 0 and owner[parent[s]] != owner[s] and lay["nr"][s] > lay["nc"][s])
+    assert sorted(m[0] for lv in fwd for m in lv) == cut
+    for l, lv in enumerate(fwd):
+        for s, src, dst in lv:
+            assert level[parent[s]] == l and src == owner[s] and dst == owner[parent[s]]
+    # every (ancestor f, descendant owner r != owner[f]) pair is served by a backward move of f, scheduled at level[f]
+    need = set()
+    for s in range(ns):
+        a = parent[s]
+        while a >= 0:
+            if owner[a] != owner[s]:
+                need.add((int(a), int(owner[s])))
+            a = parent[a]
+    have = {(m[0], m[2]) for lv in bwd for m in lv}
+    assert need <= have
+    for l, lv in enumerate(bwd):
+        for f, src, dst in lv:
+            assert level[f] == l and src == owner[f] and dst != src
+    covered = np.zeros(lay["n"], dtype=bool)
+    for rk, c0, c1 in gather:
+        assert rk != 0 and not covered[c0:c1].any()
+        covered[c0:c1] = True
+    mine0 = np.zeros(lay["n"], dtype=bool)
+    for s in range(ns):
+        if owner[s] == 0:
+            mine0[lay["col0"][s]: lay["col0"][s] + lay["nc"][s]] = True
+    assert np.array_equal(covered, ~mine0)
+    fn["b200s_chol_free"](F)

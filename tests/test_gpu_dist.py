@@ -51,6 +51,15 @@ def test_virtual_ranks_match_single_gpu_bitwise(world, case, split):
         assert minor2 == n and np.array_equal(Xd, Xd2)
     berr = (np.linalg.norm(A @ Xd - B, axis=0) / (spla.norm(A, 1) * np.linalg.norm(Xd, axis=0) + np.linalg.norm(B, axis=0))).max()
     assert berr <= 1e-12
+    # distributed triangular solves: every rank sweeps over its own fronts, update vectors go up the cut edges, solution
+    # entries of the top fronts go down their subtree groups; same kernels and summation order as the single-GPU solve
+    for col in range(2):
+        xv = vr.solve(B[:, col])
+        if not vr.splan:
+            assert np.array_equal(xv, Xs[:, col])
+        else:
+            assert np.linalg.norm(xv - Xs[:, col]) <= 1e-12 * np.linalg.norm(Xs[:, col])
+    assert any(vr.sfwd) and any(vr.sbwd) and vr.sgather
     # not positive definite: the smallest failing column over all ranks is reported
     Abad = A.tolil(); Abad[n // 2, n // 2] = -1.0
     Albad = lower_ccs(Abad.tocsc())
