@@ -12,9 +12,11 @@
 //   LU  [Bp/32][slots][32]  GROUP-MAJOR: the slots of a group of 32 matrices are contiguous (value v of matrix b at
 //       (b/32)*slots*32 + v*32 + b%32), so a run of consecutive slots -- the L part of a column -- is ONE contiguous
 //       block that a single cp.async.bulk (TMA) moves.  Per column: U above the diagonal, U diagonal, L below; then F
-// Kernels: k_klu_transpose (tiled), k_klu_rowscale (row maxima + scaling), k_klu_scatter, k_klu_refactor_wave (fast path: TMA
+// Kernels: k_klu_transpose (tiled), k_klu_rowscale (row maxima + scaling), k_klu_scatter, k_klu_early (the wide first levels of
+// the dependency graph: one warp per (column, group), one launch per level), k_klu_refactor_wave (the remaining columns: TMA
 // producer warp + 16 consumer warps per group of 32 matrices), k_klu_dense_pack / k_klu_dense_lu (dense trailing block),
-// k_klu_refactor (level-schedule kernel for patterns outside the wave kernel's budget), k_klu_solve_lvl.
+// k_klu_refactor (level-schedule kernel for patterns outside the wave kernel's budget), k_klu_load_one (klu.numeric: the host
+// pivot search's values), k_klu_solve_lvl.
 #include "gpu.hpp"
 #include "devpool.hpp"
 #include "klu_host.hpp"
@@ -207,7 +209,6 @@ __global__ void __launch_bounds__(KLU_WARPS * 32) k_klu_refactor(KluPlanD P, lon
 // the scaled input values is fused into the column initialisation.
 struct KluWaveD {
     int nwaves, spine0;
-    int pf_dist;                // batches the producer prefetches into L2 ahead of the ring (0: off)
     const int *wave_col0, *col_roff, *batch_rowslot, *wave_rowsrc;
     const int *ne_cols, *wave_rows, *wrun_ptr;      // wave_col0 holds positions in ne_cols (the columns k_klu_early does not factor)
     const int4* wrun;           // per run of consecutive columns of a wave: {first slot, first shared-memory row, rows, 0}
@@ -237,18 +238,13 @@ __device__ __forceinline__ void klu_mbar_expect_tx(unsigned long long* b, unsign
 __device__ __forceinline__ void klu_mbar_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
 }
-#ifdef KLU_TEST_WAIT
-#define KLU_MBAR_WAIT_OP "mbarrier.test_wait.parity.shared::cta.b64"
-#else
-#define KLU_MBAR_WAIT_OP "mbarrier.try_wait.parity.shared::cta.b64"
-#endif
 __device__ __forceinline__ void klu_mbar_wait(unsigned long long* b, unsigned parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(b);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        KLU_MBAR_WAIT_OP " p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
@@ -257,9 +253,6 @@ __device__ __forceinline__ void klu_mbar_wait(unsigned long long* b, unsigned pa
 __device__ __forceinline__ void klu_bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                  "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void klu_bulk_prefetch_l2(const void* gmem, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void klu_mbar_arrive_n(unsigned long long* b, unsigned count) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
@@ -385,8 +378,6 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
     if (warp == KLU_WAVE_WARPS) {
         // ---------------- producer warp: lane r issues staged rows r and r + 32 of every batch
         constexpr unsigned META_BYTES = KLU_WAVE_WARPS * KLU_REC_U32 * 4;
-        const long long nbatches_total = W.wbatch_ptr[W.nwaves];
-        const int pf_dist = W.pf_dist;
         for (int w = 0; w < W.nwaves; w++) {
             const long long c0 = W.wbatch_ptr[w], c1 = W.wbatch_ptr[w + 1];
             int s0 = 0, s1 = 0;
@@ -424,18 +415,6 @@ __global__ void __launch_bounds__((KLU_WAVE_WARPS + 1) * 32, 1) k_klu_refactor_w
                     if (a0 + 32 * (q + 1) + lane < a1)
                         klu_bulk_g2s(dst + (ex[q].y & 0xff) * 32, lug + (long long)ex[q].x * 32, (unsigned)(ex[q].y >> 8) * 256u, &full_bar[slot]);
                 if (lane == 0) klu_bulk_g2s(dst + KLU_CHUNK_ROWS * 32, W.bentry + g * KLU_ENTRY_DOUBLES * 2, META_BYTES, &full_bar[slot]);
-                // L2 prefetch of the batch `pf_dist` ahead (also across the end of the wave): the ring holds only KLU_STAGES
-                // batches, which is less than HBM latency x the SM's bandwidth share; the prefetch keeps more bytes in flight at
-                // no shared-memory cost, and the ring's own copies then hit L2.  (A column the current wave is still producing may
-                // be prefetched early: L2 is the coherence point, the wave's bulk store lands in the same lines.)
-                if (pf_dist > 0 && g + pf_dist < nbatches_total) {
-                    const int p0 = W.bseg_ptr[g + pf_dist], p1 = W.bseg_ptr[g + pf_dist + 1];
-                    for (int q = p0 + lane; q < p1; q += 32) {
-                        const int2 pd = W.segd[q];
-                        klu_bulk_prefetch_l2(lug + (long long)pd.x * 32, (unsigned)(pd.y >> 8) * 256u);
-                    }
-                    if (lane == 0) klu_bulk_prefetch_l2(W.bentry + (g + pf_dist) * KLU_ENTRY_DOUBLES * 2, META_BYTES);
-                }
             }
             asm volatile("bar.sync 0;" ::: "memory");       // end of wave: the consumers stored (and fenced) the wave's columns
         }
@@ -1350,7 +1329,6 @@ int KluDevice::init_refactor(const KluPlan& P) {
         if ((rc = up(&WD.bentry, P.bentry))) return rc;       // the largest table (11.5 MB on ACTIVSg2000): no staging copy
         if ((rc = up(&WD.wblob, P.wblob))) return rc;
         WD.spine0 = use_wave ? P.spine0 : P.n;
-        WD.pf_dist = getenv("B200S_KLU_PF") ? atoi(getenv("B200S_KLU_PF")) : 0;
         spine_nd = use_wave ? P.spine_nd : 0;
         if ((rc = up(&d_dense_meta, P.dense_meta))) return rc;
         if ((rc = up(&d_dense_slot, P.dense_slot))) return rc;
