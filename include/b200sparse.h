@@ -303,6 +303,20 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
  * layout of b200s_klu_extract_host.  Verification of the host-built plan in CPU tests; not a factorization path. */
 b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* val, double* Lx, double* Ux, double* Fx, double* Rs);
 
+/* ---- complex matrices ('z'; klu_zl_*: src/C/klu.c:161-162,348-355,468-479,661-668,754-813) ------------------------------------
+ * b200s_klu_analyze is type-independent (klu.c:266).  val: nnz (re, im) pairs.  The threshold-pivoting factorization runs on
+ * the host in complex arithmetic and is what b200s_klu_extract_z returns (get_numeric, get_det); the solves run on the device
+ * through the real embedding a + ib -> [[a, -b], [b, a]] of order 2n, whose factor object b200s_klu_embedded exposes for the
+ * batched entry points.  b200s_klu_solve_z: trans 0 = A x = b, 1 = A^T x = b, 2 = A^H x = b; B holds (re, im) pairs, ldB counts
+ * complex numbers.  b200s_klu_info reports the counts of the complex factor. */
+b200s_status b200s_klu_factor_z(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                b200s_klu_num** out);
+b200s_status b200s_klu_solve_z(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB);
+b200s_status b200s_klu_extract_z(const b200s_klu_num* N, b200s_int* Lp, b200s_int* Li, double* Lx, b200s_int* Up, b200s_int* Ui,
+                                 double* Ux, b200s_int* Fp, b200s_int* Fi, double* Fx, b200s_int* P, b200s_int* Q, double* Rs,
+                                 b200s_int* R);
+b200s_klu_num* b200s_klu_embedded(b200s_klu_num* N);
+
 /* the pre-ordering held by a symbolic object (klu_symbolic's P, Q, R: BTF + per-block AMD, before any numeric pivoting):
  * P[n], Q[n], R[nblocks+1]; any may be NULL; *nblocks may be NULL.  For tests and tools. */
 b200s_status b200s_klu_symbolic_perm(const b200s_klu_sym* S, b200s_int* P, b200s_int* Q, b200s_int* R, b200s_int* nblocks);

@@ -74,6 +74,7 @@ typedef struct cholmod_factor_struct {
     int xtype, is_ll, is_super;
     void* b200s;                 /* b200s_chol* */
     int stype;
+    int zfactor;                 /* analysed from a CHOLMOD_COMPLEX matrix: the b200s_chol_*_z entry points serve it */
 } cholmod_factor;
 
 int cholmod_l_start(cholmod_common*);

@@ -9,7 +9,8 @@
  *   klu_l_solve / klu_l_tsolve (:189,651)   -> b200s_klu_solve
  *   klu_l_extract (:461)                    -> b200s_klu_extract
  *   klu_l_free_symbolic / _numeric          -> b200s_klu_free_symbolic / _numeric
- * The complex entry points (klu_zl_*) report KLU_INVALID: the FP64-real engine has no 'z' kernels.
+ * The complex entry points (klu_zl_*) are served by b200s_klu_factor_z / _solve_z / _extract_z (complex factor of the host
+ * pivot search for extract / determinant, solves on the device through the real embedding).
  */
 #ifndef B200S_SHIM_KLU_H
 #define B200S_SHIM_KLU_H

@@ -36,6 +36,11 @@ struct b200s_klu_num {
     KluPlan P;
     KluDevice* dev = nullptr;
     int device = 0;
+    // complex matrices (b200s_klu_factor_z): the complex factor of the host pivot search (get_numeric / get_det) and the
+    // factorization of the real embedding a + ib -> [[a, -b], [b, a]] of order 2n that serves the solves on the device
+    KluNumericZ* zN = nullptr;
+    b200s_klu_sym* emb_sym = nullptr;
+    b200s_klu_num* emb = nullptr;
 };
 
 extern "C" {
@@ -204,6 +209,19 @@ b200s_status b200s_klu_solve(b200s_klu_num* N, int trans, double* B, b200s_int n
 b200s_status b200s_klu_info(const b200s_klu_num* N, b200s_klu_info_t* info) {
     if (!N || !info) return B200S_INVALID;
     memset(info, 0, sizeof *info);
+    if (N->zN) {          // complex factor object: the counts of the complex factor, the timings of the embedded device object
+        const i32 nz = N->zN->n;
+        info->n = nz; info->nblocks = N->S.nblocks; info->nnz_A = N->S.nnz; info->max_block = N->S.maxblock;
+        info->nnz_L = N->zN->Lp[nz]; info->nnz_U = N->zN->Up[nz]; info->nnz_F = N->zN->Fp[nz];
+        info->flops = 4.0 * N->zN->flops;
+        info->bytes_per_refactor = 16 * (info->nnz_A + info->nnz_L + info->nnz_U + info->nnz_F) + 8 * 2 * (i64)nz;
+        if (N->emb && N->emb->dev) {
+            long long nl = 0;
+            klu_device_times(N->emb->dev, &info->ms_h2d, &info->ms_refactor, &info->ms_solve, &info->ms_kernel, &info->ms_dense, &nl);
+            info->launches = nl;
+        }
+        return B200S_OK;
+    }
     const i32 n = N->N.n;
     info->n = n; info->nblocks = N->S.nblocks; info->nnz_A = N->S.nnz;
     info->nnz_L = N->N.Lp[n]; info->nnz_U = N->N.Up[n]; info->nnz_F = N->N.Fp[n];
@@ -242,7 +260,7 @@ static b200s_status extract_values(b200s_klu_num* N, b200s_int b, double* Lx, do
 b200s_status b200s_klu_extract(const b200s_klu_num* Nc, b200s_int* Lp, b200s_int* Li, double* Lx, b200s_int* Up, b200s_int* Ui,
                                double* Ux, b200s_int* Fp, b200s_int* Fi, double* Fx, b200s_int* P, b200s_int* Q, double* Rs,
                                b200s_int* R) {
-    if (!Nc) return B200S_INVALID;
+    if (!Nc || Nc->zN) return B200S_INVALID;
     b200s_klu_num* N = const_cast<b200s_klu_num*>(Nc);
     const i32 n = N->N.n;
     for (i32 k = 0; k <= n; k++) {
@@ -321,7 +339,120 @@ void b200s_klu_free_symbolic(b200s_klu_sym* S) { delete S; }
 void b200s_klu_free_numeric(b200s_klu_num* N) {
     if (!N) return;
     if (N->dev) klu_device_destroy(N->dev);
+    if (N->emb) b200s_klu_free_numeric(N->emb);
+    if (N->emb_sym) b200s_klu_free_symbolic(N->emb_sym);
+    delete N->zN;
     delete N;
+}
+
+/* ---- complex matrices ('z' spmatrix; klu_zl_*: src/C/klu.c:161-162,348-355,468-479,661-668,754-813) -----------------------
+ * val: nnz (re, im) pairs.  The threshold-pivoting factorization runs on the host in complex arithmetic (|z| = hypot, row
+ * scale = max |z| of the row: KLU's rules) and IS the factor get_numeric / get_det return; the solves run on the device
+ * through the real embedding a + ib -> [[a, -b], [b, a]] of order 2n -- a complex vector is its own embedding (interleaved
+ * (re, im)), so b200s_klu_solve_z works on the caller's buffer. */
+b200s_status b200s_klu_factor_z(b200s_klu_sym* S, const b200s_int* colptr, const b200s_int* rowind, const double* val,
+                                b200s_klu_num** out) {
+    B200S_NVTX("b200s_klu_factor_z");
+    if (!S || !out) return B200S_INVALID;
+    *out = nullptr;
+    const i32 n = S->S.n;
+    if (n > 0) {
+        if (!colptr || !val) return B200S_INVALID;
+        if (colptr[n] != S->S.nnz) { set_last_error("matrix pattern differs from the analysed pattern"); return B200S_INVALID; }
+        for (i32 j = 0; j <= n; j++) if (colptr[j] != S->S.Ap[j]) { set_last_error("matrix pattern differs from the analysed pattern"); return B200S_INVALID; }
+        for (i64 p = 0; p < S->S.nnz; p++) if (rowind[p] != S->S.Ai[p]) { set_last_error("matrix pattern differs from the analysed pattern"); return B200S_INVALID; }
+    }
+    b200s_klu_num* N = new (std::nothrow) b200s_klu_num();
+    if (!N) return B200S_OUT_OF_MEMORY;
+    N->S = S->S;
+    N->device = current_device();
+    b200s_status rs = B200S_OK;
+    try {
+        N->zN = new KluNumericZ();
+        int st = klu_factor_z(N->S, reinterpret_cast<const std::complex<double>*>(val), *N->zN);
+        if (st != ST_OK) { b200s_klu_free_numeric(N); return (b200s_status)st; }
+        N->N.n = 0;           // the real members stay empty: every entry point dispatches on zN
+        if (n > 0) {
+            // embedded real matrix: column j -> columns 2j, 2j+1; entry (i, a + ib) -> rows 2i, 2i+1
+            const i64 nnz = S->S.nnz;
+            std::vector<i64> ecp((size_t)2 * n + 1), eri((size_t)4 * nnz);
+            std::vector<double> ev((size_t)4 * nnz);
+            i64 q = 0;
+            ecp[0] = 0;
+            for (i32 j = 0; j < n; j++) {
+                for (int half = 0; half < 2; half++) {
+                    for (i64 p = colptr[j]; p < colptr[j + 1]; p++) {
+                        const double a = val[2 * p], b = val[2 * p + 1];
+                        eri[q] = 2 * rowind[p];     ev[q++] = half == 0 ? a : -b;
+                        eri[q] = 2 * rowind[p] + 1; ev[q++] = half == 0 ? b : a;
+                    }
+                    ecp[2 * j + half + 1] = q;
+                }
+            }
+            rs = b200s_klu_analyze(2 * (i64)n, ecp.data(), eri.data(), &N->emb_sym);
+            if (rs == B200S_OK) rs = b200s_klu_factor(N->emb_sym, ecp.data(), eri.data(), ev.data(), &N->emb);
+        }
+    } catch (const std::bad_alloc&) {
+        b200s_klu_free_numeric(N); return B200S_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        set_last_error(e.what()); b200s_klu_free_numeric(N); return B200S_INVALID;
+    }
+    if (rs != B200S_OK) { b200s_klu_free_numeric(N); return rs; }
+    *out = N;
+    return B200S_OK;
+}
+
+/* trans: 0 = A x = b, 1 = A^T x = b, 2 = A^H x = b (klu.c:651-668: klu_zl_solve / klu_zl_tsolve with conj_solve).
+ * B: nrhs columns of (re, im) pairs, leading dimension ldB (in complex numbers), overwritten by the solution. */
+b200s_status b200s_klu_solve_z(b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB) {
+    B200S_NVTX("b200s_klu_solve_z");
+    if (!N || !N->zN || trans < 0 || trans > 2 || nrhs < 0) return B200S_INVALID;
+    const i64 n = N->zN->n;
+    if (n == 0 || nrhs == 0) return B200S_OK;
+    if (!B || ldB < n || !N->emb) return B200S_INVALID;
+    // emb(A)^T = emb(A^H): the real transposed solve is the conjugate-transposed complex one; A^T x = b is
+    // conj(A^H conj(x)) = b, i.e. conjugate the right-hand side, solve with A^H, conjugate the result
+    auto conj_cols = [&]() {
+        for (i64 c = 0; c < nrhs; c++)
+            for (i64 i = 0; i < n; i++) B[2 * (c * ldB + i) + 1] = -B[2 * (c * ldB + i) + 1];
+    };
+    if (trans == 1) conj_cols();
+    b200s_status st = b200s_klu_solve(N->emb, trans == 0 ? 0 : 1, B, nrhs, 2 * ldB);
+    if (trans == 1) conj_cols();
+    return st;
+}
+
+/* the factor object of the real embedding (order 2n; column j -> columns 2j, 2j+1; per complex entry (i, a + ib) the
+ * embedded CCS holds, in column 2j: (2i, a), (2i+1, b), in column 2j+1: (2i, -b), (2i+1, a), entries in the caller's order):
+ * the batched entry points (b200s_klu_refactor_batch*, b200s_klu_solve_batch*) take it with embedded values / interleaved
+ * (re, im) right-hand sides.  Owned by N. */
+b200s_klu_num* b200s_klu_embedded(b200s_klu_num* N) { return N ? N->emb : nullptr; }
+
+/* klu_zl_extract (klu.c:468-479): the complex factors; Lx, Ux, Fx receive (re, im) pairs */
+b200s_status b200s_klu_extract_z(const b200s_klu_num* N, b200s_int* Lp, b200s_int* Li, double* Lx, b200s_int* Up, b200s_int* Ui,
+                                 double* Ux, b200s_int* Fp, b200s_int* Fi, double* Fx, b200s_int* P, b200s_int* Q, double* Rs,
+                                 b200s_int* R) {
+    if (!N || !N->zN) return B200S_INVALID;
+    const KluNumericZ& Z = *N->zN;
+    const i32 n = Z.n;
+    for (i32 k = 0; k <= n; k++) {
+        if (Lp) Lp[k] = Z.Lp[k];
+        if (Up) Up[k] = Z.Up[k];
+        if (Fp) Fp[k] = Z.Fp[k];
+    }
+    if (Li) for (size_t p = 0; p < Z.Li.size(); p++) Li[p] = Z.Li[p];
+    if (Ui) for (size_t p = 0; p < Z.Ui.size(); p++) Ui[p] = Z.Ui[p];
+    if (Fi) for (size_t p = 0; p < Z.Fi.size(); p++) Fi[p] = Z.Fi[p];
+    if (Lx) for (size_t p = 0; p < Z.Lx.size(); p++) { Lx[2 * p] = Z.Lx[p].real(); Lx[2 * p + 1] = Z.Lx[p].imag(); }
+    if (Ux) for (size_t p = 0; p < Z.Ux.size(); p++) { Ux[2 * p] = Z.Ux[p].real(); Ux[2 * p + 1] = Z.Ux[p].imag(); }
+    if (Fx) for (size_t p = 0; p < Z.Fx.size(); p++) { Fx[2 * p] = Z.Fx[p].real(); Fx[2 * p + 1] = Z.Fx[p].imag(); }
+    for (i32 k = 0; k < n; k++) {
+        if (P) P[k] = Z.Pnum[k];
+        if (Q) Q[k] = N->S.Q[k];
+        if (Rs) Rs[k] = Z.Rs[k];
+    }
+    if (R) for (i32 b = 0; b <= N->S.nblocks; b++) R[b] = N->S.R[b];
+    return B200S_OK;
 }
 
 }  // extern "C"

@@ -1579,13 +1579,15 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     double* db = B;
     const long long totalB = bstride * batch_;
+    // the caller's buffer ends with the n entries of the last column: (ldB - n) doubles fewer than batch * nrhs * ldB
+    const long long hostB = totalB - (ldB - n);
     if (!on_device) {
         if (totalB > capB) {
             pool_free(dB); dB = nullptr; capB = 0;
             CUDA_TRY(pool_malloc((void**)&dB, totalB * sizeof(double)));
             capB = totalB;
         }
-        CUDA_TRY(cudaMemcpyAsync(dB, B, totalB * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dB, B, hostB * sizeof(double), cudaMemcpyHostToDevice, stream));
         db = dB;
     }
     {
@@ -1602,7 +1604,7 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
         k_klu_solve_store<<<tg, 256, 0, stream>>>(n, nb, Bp, trans ? d_Pnum : d_Q, trans ? dRs : nullptr, db, ldB, bstride, dX);
     }
     CUDA_TRY(cudaGetLastError());
-    if (!on_device) CUDA_TRY(cudaMemcpyAsync(B, dB, totalB * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(B, dB, hostB * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaEventRecord(ev[1], stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     float ms;

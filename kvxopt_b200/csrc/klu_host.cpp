@@ -191,9 +191,10 @@ void klu_analyze(i64 n64, const i64* Ap, const i64* Ai64, KluSymbolic& S) {
     for (i32 k = 0; k < n; k++) S.Q[k] = match[order[k]];
 }
 
-int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
+template <class T>
+static int klu_factor_t(const KluSymbolic& S, const T* Ax, KluNumericT<T>& N) {
     const i32 n = S.n;
-    N = KluNumeric();
+    N = KluNumericT<T>();
     N.n = n;
     N.Lp.assign(n + 1, 0); N.Up.assign(n + 1, 0); N.Fp.assign(n + 1, 0);
     N.Pnum.assign(n, -1); N.Rs.assign(n, 1.0);
@@ -204,18 +205,18 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
     // row scaling by max |row| (scale = 2); a zero row is left unscaled and will produce a zero pivot
     std::vector<double> rs(n, 0.0);
     for (i32 j = 0; j < n; j++)
-        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) rs[Ai[p]] = std::max(rs[Ai[p]], std::fabs(Ax[p]));
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) rs[Ai[p]] = std::max(rs[Ai[p]], (double)std::abs(Ax[p]));
     for (i32 i = 0; i < n; i++) if (!(rs[i] > 0.0)) rs[i] = 1.0;
     std::vector<i32> pinvP(n);                    // row (original) -> position after the symbolic permutation
     for (i32 k = 0; k < n; k++) pinvP[S.P[k]] = k;
     std::vector<i32> pivpos(n, -1);               // symbolic row position -> final pivotal position
     std::vector<i32> rowat(n, -1);                // final pivotal position -> symbolic row position
-    std::vector<double> x(n, 0.0);
+    std::vector<T> x(n, T(0));
     std::vector<i32> mark(n, -1), reach, dstack, lcol_of(n, -1);
     std::vector<i64> pstack;
     reach.reserve(n); dstack.reserve(n); pstack.reserve(n);
     // L is built with symbolic row positions and remapped to pivotal positions at the end
-    std::vector<i32> Li_tmp; std::vector<double> Lx_tmp;
+    std::vector<i32> Li_tmp; std::vector<T> Lx_tmp;
     std::vector<i32> xi;
     // Symmetric pruning (Eisenstat-Liu, as in KLU's kernel): once some later column k has U(j,k) != 0 and its pivot row in
     // L(:,j), the rows of L(:,j) that were not pivotal then are all in L(:,k), so the depth-first search only needs the
@@ -234,7 +235,7 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
             reach.clear();
             for (i64 p = Ap[col]; p < Ap[col + 1]; p++) {
                 const i32 r = pinvP[Ai[p]];
-                const double v = Ax[p] / rs[Ai[p]];
+                const T v = Ax[p] / rs[Ai[p]];
                 if (r < k0) { N.Fi.push_back(r); N.Fx.push_back(v); }        // r is remapped to pivotal later
                 else if (r >= k1) throw std::logic_error("klu: entry below the block diagonal");
                 else { x[r] = v; if (mark[r] != k) { mark[r] = k; xi.push_back(r); } }
@@ -254,7 +255,7 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
                     const i64 pend = lpend[jc];
                     for (; pp < pend; pp++) {
                         const i32 rr = Li_tmp[pp];
-                        if (mark[rr] != k) { mark[rr] = k; xi.push_back(rr); x[rr] = 0.0; }
+                        if (mark[rr] != k) { mark[rr] = k; xi.push_back(rr); x[rr] = T(0); }
                         if (pivpos[rr] >= 0 && lcol_of[rr] != k) {
                             lcol_of[rr] = k;
                             pp++;
@@ -269,23 +270,23 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
             // numeric sparse triangular solve in topological order (reverse of the DFS finish order)
             for (i32 t = (i32)reach.size() - 1; t >= 0; t--) {
                 const i32 r = reach[t], jc = pivpos[r];
-                const double xj = x[r];
+                const T xj = x[r];
                 for (i64 pp = N.Lp[jc] + 1; pp < N.Lp[jc + 1]; pp++) x[Li_tmp[pp]] -= Lx_tmp[pp] * xj;
                 fl += 2.0 * (double)(N.Lp[jc + 1] - N.Lp[jc] - 1);
             }
             // pivot search among the non-pivotal rows; prefer the diagonal (symbolic row position k)
             double amax = -1.0; i32 prow = -1;
             for (i32 r : xi)
-                if (pivpos[r] < 0) { double a = std::fabs(x[r]); if (a > amax) { amax = a; prow = r; } }
-            if (pivpos[k] < 0 && mark[k] == k && std::fabs(x[k]) >= tol * amax && x[k] != 0.0) prow = k;
-            if (prow < 0 || !(amax > 0.0) || x[prow] == 0.0) {
+                if (pivpos[r] < 0) { double a = (double)std::abs(x[r]); if (a > amax) { amax = a; prow = r; } }
+            if (pivpos[k] < 0 && mark[k] == k && (double)std::abs(x[k]) >= tol * amax && x[k] != T(0)) prow = k;
+            if (prow < 0 || !(amax > 0.0) || x[prow] == T(0)) {
                 // numerically (or structurally) singular column: KLU with halt_if_singular stops here
                 N.singular_col = k;
                 status = ST_SINGULAR;
-                for (i32 r : xi) x[r] = 0.0;
+                for (i32 r : xi) x[r] = T(0);
                 return status;
             }
-            const double piv = x[prow];
+            const T piv = x[prow];
             pivpos[prow] = k;
             rowat[k] = prow;
             // U(:,k): pivotal rows (stored with pivotal positions), diagonal last
@@ -294,7 +295,7 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
             N.Ui.push_back(k); N.Ux.push_back(piv);
             N.Up[k + 1] = (i64)N.Ui.size();
             // L(:,k): unit diagonal first, then non-pivotal rows divided by the pivot
-            Li_tmp.push_back(prow); Lx_tmp.push_back(1.0);
+            Li_tmp.push_back(prow); Lx_tmp.push_back(T(1));
             for (i32 r : xi)
                 if (pivpos[r] < 0) { Li_tmp.push_back(r); Lx_tmp.push_back(x[r] / piv); }
             N.Lp[k + 1] = (i64)Li_tmp.size();
@@ -316,7 +317,7 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
                 lpend[j] = head;
                 pruned[j] = 1;
             }
-            for (i32 r : xi) x[r] = 0.0;
+            for (i32 r : xi) x[r] = T(0);
         }
     }
     // remap rows to pivotal positions, sort columns by row
@@ -325,13 +326,13 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
     for (size_t p = 0; p < N.Fi.size(); p++) N.Fi[p] = pivpos[N.Fi[p]];
     // rows ascending inside every column by a double transposition (bucket by row, then read the rows in order):
     // O(nnz + n) instead of one comparison sort per column
-    auto sort_cols = [&](std::vector<i64>& Cp, std::vector<i32>& Ci, std::vector<double>& Cx) {
+    auto sort_cols = [&](std::vector<i64>& Cp, std::vector<i32>& Ci, std::vector<T>& Cx) {
         const i64 nz = Cp[n];
         if (nz == 0) return;
         std::vector<i64> rp(n + 1, 0), cpos(Cp.begin(), Cp.end() - 1);
         for (i64 p = 0; p < nz; p++) rp[Ci[p] + 1]++;
         for (i32 i = 0; i < n; i++) rp[i + 1] += rp[i];
-        std::vector<i32> rc(nz); std::vector<double> rx(nz);
+        std::vector<i32> rc(nz); std::vector<T> rx(nz);
         for (i32 k = 0; k < n; k++)
             for (i64 p = Cp[k]; p < Cp[k + 1]; p++) { const i64 q = rp[Ci[p]]++; rc[q] = k; rx[q] = Cx[p]; }
         // rp[i] is now the end of row i
@@ -346,6 +347,9 @@ int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) {
     N.flops = fl;
     return status;
 }
+
+int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N) { return klu_factor_t<double>(S, Ax, N); }
+int klu_factor_z(const KluSymbolic& S, const std::complex<double>* Ax, KluNumericZ& N) { return klu_factor_t<std::complex<double>>(S, Ax, N); }
 
 void klu_build_plan(const KluSymbolic& S, const KluNumeric& N, KluPlan& P, bool refactor_tables) {
     const i32 n = S.n;

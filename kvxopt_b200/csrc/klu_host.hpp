@@ -3,6 +3,7 @@
 // that the batched CUDA kernels execute.
 #pragma once
 #include "host.hpp"
+#include <complex>
 #include <cstdint>
 
 namespace b200s {
@@ -17,22 +18,29 @@ struct KluSymbolic {
     std::vector<i32> Ai;
 };
 
-struct KluNumeric {
+// T = double (klu_l_*) or std::complex<double> (klu_zl_*: src/C/klu.c:161-162,348-355)
+template <class T>
+struct KluNumericT {
     i32 n = 0;
     // all row/column indices below are in FINAL permuted numbering (row k = pivotal row k, column k = Q[k])
     std::vector<i64> Lp, Up, Fp; // n+1 each
     std::vector<i32> Li, Ui, Fi;
-    std::vector<double> Lx, Ux, Fx;   // L has its unit diagonal stored first in each column; U's diagonal is last
+    std::vector<T> Lx, Ux, Fx;        // L has its unit diagonal stored first in each column; U's diagonal is last
     std::vector<i32> Pnum;       // Pnum[k] = original row of pivotal row k
     std::vector<double> Rs;      // Rs[k] = scale factor of pivotal row k  (row k of  R \ (P A Q))
     double flops = 0;            // 2 * multiply-adds of one (re)factorization
     i32 singular_col = -1;
 };
+using KluNumeric = KluNumericT<double>;
+using KluNumericZ = KluNumericT<std::complex<double>>;
 
 // klu_l_analyze with klu_defaults: btf = 1, ordering = AMD.  Throws std::invalid_argument on bad input.
 void klu_analyze(i64 n, const i64* Ap, const i64* Ai, KluSymbolic& S);
 // klu_l_factor with klu_defaults: scale = 2 (max |row|), tol = 1e-3.  Returns 0, or 2 (singular).
 int klu_factor(const KluSymbolic& S, const double* Ax, KluNumeric& N);
+// the same for complex values (|z| = hypot as KLU's ABS, row scale = max |z| of the row); host only: the complex factor serves
+// get_numeric / get_det, the solves run on the device through the real embedding (klu_capi.cu)
+int klu_factor_z(const KluSymbolic& S, const std::complex<double>* Ax, KluNumericZ& N);
 
 // ---- static refactorization plan (pattern + pivot order fixed) ------------------------------------
 // Value slots: slot v of matrix b lives at LU[v * batch + b].  Column k of the permuted matrix owns the

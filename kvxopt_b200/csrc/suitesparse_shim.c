@@ -100,14 +100,20 @@ cholmod_factor* cholmod_l_analyze_p(cholmod_sparse* A, void* UserPerm, void* fse
     b200s_chol_default_opts(&o);
     o.supernodal = cm->supernodal; o.nmethods = cm->nmethods; o.postorder = cm->postorder; o.dbound = cm->dbound;
     b200s_chol* F = NULL;
-    b200s_status st = b200s_chol_analyze((b200s_int)A->nrow, (const b200s_int*)A->p, (const b200s_int*)A->i, A->stype < 0 ? 'L' : 'U',
-                                         (const b200s_int*)UserPerm, &o, &F);
+    /* 'z' matrices (pack() builds the cholmod_sparse with CHOLMOD_COMPLEX, cholmod.c:144,153): the factor object of the real
+     * embedding, b200s_chol_analyze_z */
+    b200s_status st = A->xtype == CHOLMOD_COMPLEX
+        ? b200s_chol_analyze_z((b200s_int)A->nrow, (const b200s_int*)A->p, (const b200s_int*)A->i, A->stype < 0 ? 'L' : 'U',
+                               (const b200s_int*)UserPerm, &o, &F)
+        : b200s_chol_analyze((b200s_int)A->nrow, (const b200s_int*)A->p, (const b200s_int*)A->i, A->stype < 0 ? 'L' : 'U',
+                             (const b200s_int*)UserPerm, &o, &F);
     if (st != B200S_OK) { cm->status = chol_status_of(st); return NULL; }
     cholmod_factor* L = (cholmod_factor*)calloc(1, sizeof *L);
     if (!L) { b200s_chol_free(F); cm->status = CHOLMOD_OUT_OF_MEMORY; return NULL; }
     L->n = A->nrow; L->minor = A->nrow; L->xtype = CHOLMOD_PATTERN; L->b200s = F; L->stype = A->stype;
     L->is_ll = cm->supernodal != 0;      /* supernodal = 0 asks for LDL' (cholmod.c:60-64); 1 and 2 are LL' in this engine */
     L->is_super = L->is_ll;
+    L->zfactor = A->xtype == CHOLMOD_COMPLEX;
     cm->status = CHOLMOD_OK;
     return L;
 }
@@ -115,16 +121,15 @@ cholmod_factor* cholmod_l_analyze_p(cholmod_sparse* A, void* UserPerm, void* fse
 /* cholmod.c:362,677,824 -> b200s_chol_factorize: A's own (colptr, rowind, values) travel, the pattern is checked there */
 int cholmod_l_factorize(cholmod_sparse* A, cholmod_factor* L, cholmod_common* cm) {
     if (!A || !L || !cm) { if (cm) cm->status = CHOLMOD_INVALID; return 0; }
-    if (A->xtype != CHOLMOD_REAL) {      /* 'z' matrices: no complex kernels in the FP64-real engine */
-        fprintf(stderr, "kvxopt.cholmod (B200): complex matrices are not supported by the B200 engine\n");
-        cm->status = CHOLMOD_INVALID;
-        return 0;
-    }
+    const int z = A->xtype == CHOLMOD_COMPLEX;
+    if ((A->xtype != CHOLMOD_REAL && !z) || z != L->zfactor) { cm->status = CHOLMOD_INVALID; return 0; }
     b200s_int minor = (b200s_int)L->n;
-    b200s_status st = b200s_chol_factorize((b200s_chol*)L->b200s, (const b200s_int*)A->p, (const b200s_int*)A->i, (const double*)A->x, &minor);
+    b200s_status st = z
+        ? b200s_chol_factorize_z((b200s_chol*)L->b200s, (const b200s_int*)A->p, (const b200s_int*)A->i, (const double*)A->x, &minor)
+        : b200s_chol_factorize((b200s_chol*)L->b200s, (const b200s_int*)A->p, (const b200s_int*)A->i, (const double*)A->x, &minor);
     cm->status = chol_status_of(st);
     if (st == B200S_OK || st == B200S_NOT_POSDEF) {
-        L->xtype = CHOLMOD_REAL;
+        L->xtype = z ? CHOLMOD_COMPLEX : CHOLMOD_REAL;
         L->minor = st == B200S_OK ? L->n : (size_t)minor;
     } else {
         L->xtype = CHOLMOD_PATTERN;
@@ -138,10 +143,12 @@ int cholmod_l_factorize(cholmod_sparse* A, cholmod_factor* L, cholmod_common* cm
             int64_t* idx = (int64_t*)malloc((n + 1) * sizeof(int64_t));
             if (idx) for (size_t k = 0; k <= n; k++) idx[k] = (int64_t)k;
             L->super = idx; L->pi = idx; L->px = idx;
-            L->x = malloc(n * sizeof(double));
+            L->x = malloc(n * (z ? 2 : 1) * sizeof(double));
         }
         if (!L->super || !L->x) { cm->status = CHOLMOD_OUT_OF_MEMORY; return 0; }
-        if (b200s_chol_diag((b200s_chol*)L->b200s, (double*)L->x) != B200S_OK) { cm->status = CHOLMOD_GPU_PROBLEM; return 0; }
+        if ((z ? b200s_chol_diag_z((b200s_chol*)L->b200s, (double*)L->x) : b200s_chol_diag((b200s_chol*)L->b200s, (double*)L->x)) != B200S_OK) {
+            cm->status = CHOLMOD_GPU_PROBLEM; return 0;
+        }
         L->nsuper = n;
     }
     return 1;
@@ -150,11 +157,13 @@ int cholmod_l_factorize(cholmod_sparse* A, cholmod_factor* L, cholmod_common* cm
 /* cholmod.c:483,735 -> b200s_chol_solve (one column per call, as the wrapper's loop asks) */
 cholmod_dense* cholmod_l_solve(int sys, cholmod_factor* L, cholmod_dense* B, cholmod_common* cm) {
     if (!L || !B || !cm) { if (cm) cm->status = CHOLMOD_INVALID; return NULL; }
-    if (B->xtype != CHOLMOD_REAL || L->xtype != CHOLMOD_REAL) { cm->status = CHOLMOD_INVALID; return NULL; }
-    cholmod_dense* X = cholmod_l_allocate_dense(L->n, B->ncol, L->n, CHOLMOD_REAL, cm);
+    if (B->xtype != L->xtype || (L->xtype != CHOLMOD_REAL && L->xtype != CHOLMOD_COMPLEX)) { cm->status = CHOLMOD_INVALID; return NULL; }
+    /* a complex vector is its own real embedding: (re, im) pairs = 2n real unknowns per column */
+    const size_t w = L->xtype == CHOLMOD_COMPLEX ? 2 : 1;
+    cholmod_dense* X = cholmod_l_allocate_dense(L->n, B->ncol, L->n, L->xtype, cm);
     if (!X) return NULL;
-    for (size_t c = 0; c < B->ncol; c++) memcpy((double*)X->x + c * L->n, (const double*)B->x + c * B->d, L->n * sizeof(double));
-    b200s_status st = b200s_chol_solve((b200s_chol*)L->b200s, sys, (double*)X->x, (b200s_int)B->ncol, (b200s_int)L->n);
+    for (size_t c = 0; c < B->ncol; c++) memcpy((double*)X->x + c * w * L->n, (const double*)B->x + c * w * B->d, w * L->n * sizeof(double));
+    b200s_status st = b200s_chol_solve((b200s_chol*)L->b200s, sys, (double*)X->x, (b200s_int)B->ncol, (b200s_int)(w * L->n));
     cm->status = chol_status_of(st);
     return X;
 }
@@ -162,17 +171,20 @@ cholmod_dense* cholmod_l_solve(int sys, cholmod_factor* L, cholmod_dense* B, cho
 /* cholmod.c:567,858 -> b200s_chol_spsolve */
 cholmod_sparse* cholmod_l_spsolve(int sys, cholmod_factor* L, cholmod_sparse* B, cholmod_common* cm) {
     if (!L || !B || !cm) { if (cm) cm->status = CHOLMOD_INVALID; return NULL; }
-    if (B->xtype != CHOLMOD_REAL || L->xtype != CHOLMOD_REAL) { cm->status = CHOLMOD_INVALID; return NULL; }
+    if (B->xtype != L->xtype || (L->xtype != CHOLMOD_REAL && L->xtype != CHOLMOD_COMPLEX)) { cm->status = CHOLMOD_INVALID; return NULL; }
     b200s_int *xp = NULL, *xi = NULL;
     double* xx = NULL;
-    b200s_status st = b200s_chol_spsolve((b200s_chol*)L->b200s, sys, (b200s_int)B->nrow, (b200s_int)B->ncol, (const b200s_int*)B->p,
-                                         (const b200s_int*)B->i, (const double*)B->x, &xp, &xi, &xx);
+    b200s_status st = L->xtype == CHOLMOD_COMPLEX
+        ? b200s_chol_spsolve_z((b200s_chol*)L->b200s, sys, (b200s_int)B->nrow, (b200s_int)B->ncol, (const b200s_int*)B->p,
+                               (const b200s_int*)B->i, (const double*)B->x, &xp, &xi, &xx)
+        : b200s_chol_spsolve((b200s_chol*)L->b200s, sys, (b200s_int)B->nrow, (b200s_int)B->ncol, (const b200s_int*)B->p,
+                             (const b200s_int*)B->i, (const double*)B->x, &xp, &xi, &xx);
     cm->status = chol_status_of(st);
     if (st != B200S_OK) return NULL;
     cholmod_sparse* X = (cholmod_sparse*)calloc(1, sizeof *X);
     if (!X) { b200s_free(xp); b200s_free(xi); b200s_free(xx); cm->status = CHOLMOD_OUT_OF_MEMORY; return NULL; }
     X->nrow = B->nrow; X->ncol = B->ncol; X->nzmax = (size_t)xp[B->ncol]; X->p = xp; X->i = xi; X->x = xx;
-    X->sorted = 1; X->packed = 1; X->xtype = CHOLMOD_REAL;
+    X->sorted = 1; X->packed = 1; X->xtype = L->xtype;
     return X;
 }
 
@@ -181,13 +193,14 @@ cholmod_sparse* cholmod_l_factor_to_sparse(cholmod_factor* L, cholmod_common* cm
     if (!L || !cm) { if (cm) cm->status = CHOLMOD_INVALID; return NULL; }
     b200s_int *lp = NULL, *li = NULL;
     double* lx = NULL;
-    b200s_status st = b200s_chol_get_L((b200s_chol*)L->b200s, &lp, &li, &lx);
+    b200s_status st = L->xtype == CHOLMOD_COMPLEX ? b200s_chol_get_L_z((b200s_chol*)L->b200s, &lp, &li, &lx)
+                                                  : b200s_chol_get_L((b200s_chol*)L->b200s, &lp, &li, &lx);
     cm->status = chol_status_of(st);
     if (st != B200S_OK) return NULL;
     cholmod_sparse* S = (cholmod_sparse*)calloc(1, sizeof *S);
     if (!S) { b200s_free(lp); b200s_free(li); b200s_free(lx); cm->status = CHOLMOD_OUT_OF_MEMORY; return NULL; }
     S->nrow = L->n; S->ncol = L->n; S->nzmax = L->n ? (size_t)lp[L->n] : 0; S->p = lp; S->i = li; S->x = lx;
-    S->sorted = 1; S->packed = 1; S->xtype = CHOLMOD_REAL;
+    S->sorted = 1; S->packed = 1; S->xtype = L->xtype;
     return S;
 }
 
@@ -330,32 +343,92 @@ int klu_l_free_numeric(klu_l_numeric** F, klu_l_common* cm) {
     return 1;
 }
 
-/* complex KLU: not provided by the FP64-real engine */
-static void klu_no_complex(klu_l_common* cm) {
-    fprintf(stderr, "kvxopt.klu (B200): complex matrices are not supported by the B200 engine\n");
-    if (cm) cm->status = KLU_INVALID;
-}
+/* ---- complex KLU (klu.c:161-162,348-355,468-479,661-668,754-813): b200s_klu_factor_z / _solve_z / _extract_z ------------- */
+/* klu.c:352 -> b200s_klu_factor_z; Udiag holds (re, im) pairs (klu.c:760 reads it as double complex) */
 klu_l_numeric* klu_zl_factor(int64_t* Ap, int64_t* Ai, double* Ax, klu_l_symbolic* Y, klu_l_common* cm) {
-    (void)Ap; (void)Ai; (void)Ax; (void)Y;
-    klu_no_complex(cm);
-    return NULL;
+    if (!cm) return NULL;
+    if (!Y) { cm->status = KLU_INVALID; return NULL; }
+    b200s_klu_num* N = NULL;
+    b200s_status st = b200s_klu_factor_z((b200s_klu_sym*)Y->b200s, Ap, Ai, Ax, &N);
+    cm->status = klu_status_of(st);
+    if (st != B200S_OK) return NULL;
+    b200s_klu_info_t inf;
+    b200s_klu_info(N, &inf);
+    const int64_t n = inf.n;
+    klu_l_numeric* F = (klu_l_numeric*)calloc(1, sizeof *F);
+    int64_t *Up = NULL, *Ui = NULL, *Q = NULL, *R = NULL;
+    double* Ux = NULL;
+    if (F) {
+        F->n = n; F->nblocks = inf.nblocks; F->lnz = inf.nnz_L; F->unz = inf.nnz_U; F->nzoff = inf.nnz_F; F->b200s = N;
+        F->Pnum = (int64_t*)malloc((size_t)(n + 1) * sizeof(int64_t));
+        F->Rs = (double*)malloc((size_t)(n + 1) * sizeof(double));
+        F->Udiag = malloc((size_t)(n + 1) * 2 * sizeof(double));
+        Up = (int64_t*)malloc((size_t)(n + 1) * sizeof(int64_t));
+        Ui = (int64_t*)malloc((size_t)(inf.nnz_U + 1) * sizeof(int64_t));
+        Ux = (double*)malloc((size_t)(inf.nnz_U + 1) * 2 * sizeof(double));
+        Q = (int64_t*)malloc((size_t)(n + 1) * sizeof(int64_t));
+        R = (int64_t*)malloc((size_t)(inf.nblocks + 2) * sizeof(int64_t));
+    }
+    if (!F || !F->Pnum || !F->Rs || !F->Udiag || !Up || !Ui || !Ux || !Q || !R) {
+        if (F) { free(F->Pnum); free(F->Rs); free(F->Udiag); free(F); }
+        free(Up); free(Ui); free(Ux); free(Q); free(R);
+        b200s_klu_free_numeric(N);
+        cm->status = KLU_OUT_OF_MEMORY;
+        return NULL;
+    }
+    st = b200s_klu_extract_z(N, NULL, NULL, NULL, Up, Ui, Ux, NULL, NULL, NULL, F->Pnum, Q, F->Rs, R);
+    if (st == B200S_OK) {
+        for (int64_t k = 0; k < n; k++) {
+            ((double*)F->Udiag)[2 * k] = Ux[2 * (Up[k + 1] - 1)];
+            ((double*)F->Udiag)[2 * k + 1] = Ux[2 * (Up[k + 1] - 1) + 1];
+        }
+        if (!Y->Q) { Y->Q = Q; Q = NULL; Y->R = R; R = NULL; Y->nblocks = inf.nblocks; Y->maxblock = inf.max_block; }
+    }
+    free(Up); free(Ui); free(Ux); free(Q); free(R);
+    if (st != B200S_OK) {
+        klu_l_numeric* f = F;
+        klu_l_free_numeric(&f, cm);
+        cm->status = klu_status_of(st);
+        return NULL;
+    }
+    return F;
 }
+/* klu.c:661 -> b200s_klu_solve_z(trans = 0); klu.c:665 -> trans = 1 (A^T) or 2 (A^H, conj_solve) */
 int klu_zl_solve(klu_l_symbolic* Y, klu_l_numeric* F, int64_t ldim, int64_t nrhs, double* B, klu_l_common* cm) {
-    (void)Y; (void)F; (void)ldim; (void)nrhs; (void)B;
-    klu_no_complex(cm);
-    return 0;
+    (void)Y;
+    if (!cm) return 0;
+    if (!F) { cm->status = KLU_INVALID; return 0; }
+    b200s_status st = b200s_klu_solve_z((b200s_klu_num*)F->b200s, 0, B, nrhs, ldim);
+    cm->status = klu_status_of(st);
+    return st == B200S_OK;
 }
 int klu_zl_tsolve(klu_l_symbolic* Y, klu_l_numeric* F, int64_t ldim, int64_t nrhs, double* B, int conj_solve, klu_l_common* cm) {
-    (void)Y; (void)F; (void)ldim; (void)nrhs; (void)B; (void)conj_solve;
-    klu_no_complex(cm);
-    return 0;
+    (void)Y;
+    if (!cm) return 0;
+    if (!F) { cm->status = KLU_INVALID; return 0; }
+    b200s_status st = b200s_klu_solve_z((b200s_klu_num*)F->b200s, conj_solve ? 2 : 1, B, nrhs, ldim);
+    cm->status = klu_status_of(st);
+    return st == B200S_OK;
 }
 int klu_zl_free_numeric(klu_l_numeric** F, klu_l_common* cm) { return klu_l_free_numeric(F, cm); }
+/* klu.c:480: SuiteSparse's split real / imaginary arrays, filled from the interleaved values of b200s_klu_extract_z */
 int klu_zl_extract(klu_l_numeric* F, klu_l_symbolic* Y, int64_t* Lp, int64_t* Li, double* Lx, double* Lz, int64_t* Up, int64_t* Ui,
                    double* Ux, double* Uz, int64_t* Fp, int64_t* Fi, double* Fx, double* Fz, int64_t* P, int64_t* Q, double* Rs,
                    int64_t* R, klu_l_common* cm) {
-    (void)F; (void)Y; (void)Lp; (void)Li; (void)Lx; (void)Lz; (void)Up; (void)Ui; (void)Ux; (void)Uz; (void)Fp; (void)Fi; (void)Fx;
-    (void)Fz; (void)P; (void)Q; (void)Rs; (void)R;
-    klu_no_complex(cm);
-    return 0;
+    (void)Y;
+    if (!cm) return 0;
+    if (!F) { cm->status = KLU_INVALID; return 0; }
+    double* l = (double*)malloc((size_t)(2 * F->lnz + 2) * sizeof(double));
+    double* u = (double*)malloc((size_t)(2 * F->unz + 2) * sizeof(double));
+    double* f = (double*)malloc((size_t)(2 * F->nzoff + 2) * sizeof(double));
+    if (!l || !u || !f) { free(l); free(u); free(f); cm->status = KLU_OUT_OF_MEMORY; return 0; }
+    b200s_status st = b200s_klu_extract_z((b200s_klu_num*)F->b200s, Lp, Li, l, Up, Ui, u, Fp, Fi, f, P, Q, Rs, R);
+    if (st == B200S_OK) {
+        for (int64_t p = 0; p < F->lnz; p++) { if (Lx) Lx[p] = l[2 * p]; if (Lz) Lz[p] = l[2 * p + 1]; }
+        for (int64_t p = 0; p < F->unz; p++) { if (Ux) Ux[p] = u[2 * p]; if (Uz) Uz[p] = u[2 * p + 1]; }
+        for (int64_t p = 0; p < F->nzoff; p++) { if (Fx) Fx[p] = f[2 * p]; if (Fz) Fz[p] = f[2 * p + 1]; }
+    }
+    free(l); free(u); free(f);
+    cm->status = klu_status_of(st);
+    return st == B200S_OK;
 }

@@ -6,8 +6,10 @@ batched extension the B200 engine exists for: `refactor_batch` / `solve_batch` (
 semantics: same pattern, same pivot sequence, fresh row scaling; the reference never calls
 klu_refactor, klu.c:296-301 documents it only).
 
-The pivot search of `numeric` runs once on the host; every numeric value that `solve`,
-`get_numeric` and `get_det` use comes from the CUDA refactorization.  No GPU => RuntimeError.
+The pivot search of `numeric` runs once on the host and its values are the factor of the analysed matrix; batched
+refactorizations and all solves run on the device.  Complex ('z') matrices: the complex factor of the host pivot search serves
+`get_numeric` / `get_det`, the solves run on the device through the real embedding of order 2n.
+No GPU => RuntimeError.
 """
 import ctypes as C
 import sys
@@ -37,6 +39,26 @@ def _free_symbolic(capsule_addr):            # free_klu_d_symbolic, klu.c:51-61
 
 
 @C.CFUNCTYPE(None, C.c_void_p)
+def _free_symbolic_z(capsule_addr):
+    try:
+        ptr = _raw_GetPointer(capsule_addr, _NAME_SYM_Z)
+        if ptr:
+            fn["b200s_klu_free_symbolic"](ptr)
+    except Exception:
+        pass
+
+
+@C.CFUNCTYPE(None, C.c_void_p)
+def _free_numeric_z(capsule_addr):           # free_klu_z_numeric, klu.c:74-81
+    try:
+        ptr = _raw_GetPointer(capsule_addr, _NAME_NUM_Z)
+        if ptr:
+            fn["b200s_klu_free_numeric"](ptr)
+    except Exception:
+        pass
+
+
+@C.CFUNCTYPE(None, C.c_void_p)
 def _free_numeric(capsule_addr):             # free_klu_d_numeric, klu.c:63-72
     try:
         ptr = _raw_GetPointer(capsule_addr, _NAME_NUM)
@@ -60,8 +82,9 @@ def _raise_status(st):
 def _check_A(A, msg):
     if not _is_spmatrix(A) or _size(A)[0] != _size(A)[1]:
         raise TypeError(msg)
-    if _typecode(A) == "z":
-        raise TypeError("complex matrices are not supported by the B200 engine")
+    if _typecode(A) not in ("d", "z"):
+        raise TypeError(msg)
+    return _typecode(A) == "z"
 
 
 def _capsule_ptr(F, name, msg, argname):
@@ -81,16 +104,16 @@ def _analyze(cp, ri, n):
     return h
 
 
-def _factor(hs, cp, ri, vx):
+def _factor(hs, cp, ri, vx, z=False):
     h = C.c_void_p()
-    st = fn["b200s_klu_factor"](hs, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(h))
+    st = fn["b200s_klu_factor_z" if z else "b200s_klu_factor"](hs, L.ptr_i64(cp), L.ptr_i64(ri), L.ptr_f64(vx), C.byref(h))
     if st != L.OK:
         _raise_status(st)
     return h
 
 
-def _dense_args(B, n, nrhs, ldB, offsetB):
-    flat, nrows, ncols = _dense_view(B)
+def _dense_args(B, n, nrhs, ldB, offsetB, z=False):
+    flat, nrows, ncols = _dense_view(B, z)
     if nrhs < 0:
         nrhs = ncols
     if n == 0 or nrhs == 0:
@@ -103,34 +126,40 @@ def _dense_args(B, n, nrhs, ldB, offsetB):
         raise ValueError("offsetB must be a nonnegative integer")
     if offsetB + (nrhs - 1) * ldB + n > flat.size:
         raise TypeError("length of B is too small")
-    return flat[offsetB:], nrhs, ldB
+    return (flat[offsetB:].view(np.float64) if z else flat[offsetB:]), nrhs, ldB
 
 
-def _trans_flag(trans):
+def _trans_flag(trans, z=False):
     if trans not in ("N", "T", "C"):
         raise ValueError("possible values of trans are: 'N', 'T', 'C'")
+    if z:
+        return {"N": 0, "T": 1, "C": 2}[trans]       # klu.c:661-668: klu_zl_tsolve with conj_solve for 'C'
     return 0 if trans == "N" else 1      # real matrices: 'C' == 'T'
+
+
+def _solve_call(hn, z, t, args):
+    st = fn["b200s_klu_solve_z" if z else "b200s_klu_solve"](hn, t, L.ptr_f64(args[0]), args[1], args[2])
+    if st != L.OK:
+        _raise_status(st)
 
 
 def linsolve(A, B, trans="N", nrhs=-1, ldB=0, offsetB=0):
     """linsolve(A, B, trans='N', nrhs, ldB, offsetB): solves A X = B (or A^T X = B) in place -- klu.c:94-230.
     Returns 0 on empty input like the reference (klu.c:126), None otherwise."""
-    _check_A(A, "A must be a square sparse matrix")
+    z = _check_A(A, "A must be a square sparse matrix")
     n = _size(A)[0]
     if not _is_dense(B) or _typecode(B) != _typecode(A):
         raise TypeError("B must a dense matrix of the same numeric type as A")
-    args = _dense_args(B, n, nrhs, ldB, offsetB)
+    args = _dense_args(B, n, nrhs, ldB, offsetB, z)
     if args is None:
         return 0
-    t = _trans_flag(trans)
+    t = _trans_flag(trans, z)
     cp, ri, vx = _ccs(A)
     hs = _analyze(cp, ri, n)
     try:
-        hn = _factor(hs, cp, ri, vx)
+        hn = _factor(hs, cp, ri, vx, z)
         try:
-            st = fn["b200s_klu_solve"](hn, t, L.ptr_f64(args[0]), args[1], args[2])
-            if st != L.OK:
-                _raise_status(st)
+            _solve_call(hn, z, t, args)
         finally:
             fn["b200s_klu_free_numeric"](hn)
     finally:
@@ -140,37 +169,56 @@ def linsolve(A, B, trans="N", nrhs=-1, ldB=0, offsetB=0):
 
 def symbolic(A):
     """Fs = symbolic(A): BTF + per-block AMD ordering -- klu.c:242-291"""
-    _check_A(A, "A must be a square sparse matrix")
+    z = _check_A(A, "A must be a square sparse matrix")
     cp, ri, _ = _ccs(A)
     h = _analyze(cp, ri, _size(A)[0])
+    if z:       # the analysis is the same for both types (klu.c:266); the capsule name carries the type (klu.c:284-288)
+        return _py.PyCapsule_New(h, _NAME_SYM_Z, C.cast(_free_symbolic_z, C.c_void_p))
     return _py.PyCapsule_New(h, _NAME_SYM, C.cast(_free_symbolic, C.c_void_p))
 
 
 def numeric(A, Fs):
     """Fn = numeric(A, Fs): numeric LU with partial pivoting -- klu.c:310-379.
     Raises ArithmeticError("singular matrix") for singular input."""
-    _check_A(A, "A must a square sparse matrix")
-    hs = _capsule_ptr(Fs, _NAME_SYM, "Fs is not the KLU symbolic factor of a 'd' matrix", "Fs")
+    z = _check_A(A, "A must a square sparse matrix")
+    hs = _capsule_ptr(Fs, _NAME_SYM_Z if z else _NAME_SYM, "Fs is not the KLU symbolic factor of a '%s' matrix" % ("z" if z else "d"), "Fs")
     cp, ri, vx = _ccs(A)
-    h = _factor(hs, cp, ri, vx)
+    h = _factor(hs, cp, ri, vx, z)
+    if z:
+        return _py.PyCapsule_New(h, _NAME_NUM_Z, C.cast(_free_numeric_z, C.c_void_p))
     return _py.PyCapsule_New(h, _NAME_NUM, C.cast(_free_numeric, C.c_void_p))
 
 
 def solve(A, Fs, F, B, trans="N", nrhs=-1, ldB=0, offsetB=0):
     """solve(A, Fs, F, B, trans='N', nrhs, ldB, offsetB): B overwritten by the solution -- klu.c:593-690"""
-    _check_A(A, "A must a square sparse matrix")
+    z = _check_A(A, "A must a square sparse matrix")
     n = _size(A)[0]
-    hn = _capsule_ptr(F, _NAME_NUM, "F is not the KLU numeric factor of a 'd' matrix", "F")
-    _capsule_ptr(Fs, _NAME_SYM, "F is not the KLU symbolic factor of a 'd' matrix", "Fs")
+    tc = "z" if z else "d"
+    hn = _capsule_ptr(F, _NAME_NUM_Z if z else _NAME_NUM, "F is not the KLU numeric factor of a '%s' matrix" % tc, "F")
+    _capsule_ptr(Fs, _NAME_SYM_Z if z else _NAME_SYM, "F is not the KLU symbolic factor of a '%s' matrix" % tc, "Fs")
     if not _is_dense(B) or _typecode(B) != _typecode(A):
         raise TypeError("B must a dense matrix of the same numeric type as A")
-    args = _dense_args(B, n, nrhs, ldB, offsetB)
+    args = _dense_args(B, n, nrhs, ldB, offsetB, z)
     if args is None:
         return
-    t = _trans_flag(trans)
-    st = fn["b200s_klu_solve"](hn, t, L.ptr_f64(args[0]), args[1], args[2])
+    _solve_call(hn, z, _trans_flag(trans, z), args)
+
+
+def _extract_z(hn):
+    inf = L.KluInfo()
+    fn["b200s_klu_info"](hn, C.byref(inf))
+    n = inf.n
+    Lp = np.zeros(n + 1, np.int64); Up = np.zeros(n + 1, np.int64); Fp = np.zeros(n + 1, np.int64)
+    Li = np.zeros(max(inf.nnz_L, 1), np.int64); Ui = np.zeros(max(inf.nnz_U, 1), np.int64); Fi = np.zeros(max(inf.nnz_F, 1), np.int64)
+    Lx = np.zeros(2 * max(inf.nnz_L, 1)); Ux = np.zeros(2 * max(inf.nnz_U, 1)); Fx = np.zeros(2 * max(inf.nnz_F, 1))
+    P = np.zeros(max(n, 1), np.int64); Q = np.zeros(max(n, 1), np.int64); Rs = np.zeros(max(n, 1)); R = np.zeros(inf.nblocks + 1, np.int64)
+    st = fn["b200s_klu_extract_z"](hn, L.ptr_i64(Lp), L.ptr_i64(Li), L.ptr_f64(Lx), L.ptr_i64(Up), L.ptr_i64(Ui), L.ptr_f64(Ux),
+                                   L.ptr_i64(Fp), L.ptr_i64(Fi), L.ptr_f64(Fx), L.ptr_i64(P), L.ptr_i64(Q), L.ptr_f64(Rs), L.ptr_i64(R))
     if st != L.OK:
         _raise_status(st)
+    cz = lambda a, k: a.view(np.complex128)[:k]
+    return dict(n=n, Lp=Lp, Li=Li[:inf.nnz_L], Lx=cz(Lx, inf.nnz_L), Up=Up, Ui=Ui[:inf.nnz_U], Ux=cz(Ux, inf.nnz_U),
+                Fp=Fp, Fi=Fi[:inf.nnz_F], Fx=cz(Fx, inf.nnz_F), P=P[:n], Q=Q[:n], Rs=Rs[:n], R=R)
 
 
 def _extract(hn, batch_index=None):
@@ -196,15 +244,16 @@ def _extract(hn, batch_index=None):
 def get_numeric(A, Fs, Fn):
     """L, U, P, Q, R, F, r = get_numeric(A, Fs, Fn) with R*P*A*Q = L*U + F -- klu.c:392-566
     (R is returned already inverted, klu.c:516-522)."""
-    _check_A(A, "A must a square sparse matrix")
-    hn = _capsule_ptr(Fn, _NAME_NUM, "F is not the KLU numeric factor of a 'd' matrix", "F")
-    _capsule_ptr(Fs, _NAME_SYM, "F is not the KLU symbolic factor of a 'd' matrix", "Fs")
-    e = _extract(hn)
+    z = _check_A(A, "A must a square sparse matrix")
+    tc = "z" if z else "d"
+    hn = _capsule_ptr(Fn, _NAME_NUM_Z if z else _NAME_NUM, "F is not the KLU numeric factor of a '%s' matrix" % tc, "F")
+    _capsule_ptr(Fs, _NAME_SYM_Z if z else _NAME_SYM, "F is not the KLU symbolic factor of a '%s' matrix" % tc, "Fs")
+    e = _extract_z(hn) if z else _extract(hn)
     n = e["n"]
     ar = np.arange(n + 1, dtype=np.int64)
-    Lm = _make_spmatrix(A, e["Lx"], e["Li"], e["Lp"], (n, n))
-    Um = _make_spmatrix(A, e["Ux"], e["Ui"], e["Up"], (n, n))
-    Fm = _make_spmatrix(A, e["Fx"], e["Fi"], e["Fp"], (n, n))
+    Lm = _make_spmatrix(A, e["Lx"], e["Li"], e["Lp"], (n, n), tc)          # complex L, U, F for 'z' (klu.c:468-479, 486-512)
+    Um = _make_spmatrix(A, e["Ux"], e["Ui"], e["Up"], (n, n), tc)
+    Fm = _make_spmatrix(A, e["Fx"], e["Fi"], e["Fp"], (n, n), tc)
     prow = np.zeros(n, dtype=np.int64)
     prow[e["P"]] = np.arange(n)                     # P[i, Pnum[i]] = 1  (klu.c:526-532)
     Pm = _make_spmatrix(A, np.ones(n), prow, ar, (n, n))
@@ -227,12 +276,13 @@ def _perm_swaps(p):
 
 def get_det(A, Fs, Fn):
     """d = get_det(A, Fs, Fn): determinant from the factors -- klu.c:707-828"""
-    _check_A(A, "A must a square sparse matrix")
-    hn = _capsule_ptr(Fn, _NAME_NUM, "F is not the UMFPACK numeric factor of a 'd' matrix", "F")
-    _capsule_ptr(Fs, _NAME_SYM, "F is not the UMFPACK symbolic factor of a 'd' matrix", "Fs")
-    e = _extract(hn)
+    z = _check_A(A, "A must a square sparse matrix")
+    tc = "z" if z else "d"
+    hn = _capsule_ptr(Fn, _NAME_NUM_Z if z else _NAME_NUM, "F is not the UMFPACK numeric factor of a '%s' matrix" % tc, "F")
+    _capsule_ptr(Fs, _NAME_SYM_Z if z else _NAME_SYM, "F is not the UMFPACK symbolic factor of a '%s' matrix" % tc, "Fs")
+    e = _extract_z(hn) if z else _extract(hn)
     n = e["n"]
-    det = 1.0
+    det = 1.0 + 0.0j if z else 1.0
     for k in range(n):
         det *= e["Ux"][e["Up"][k + 1] - 1] * e["Rs"][k]
     sign = -1.0 if (_perm_swaps(e["P"]) + _perm_swaps(e["Q"])) % 2 else 1.0

@@ -114,8 +114,20 @@ def run(cls, method):
 
 
 ts = load("test_sparse_solvers")
-ts.product = lambda cases, flags: ((c, f) for c in cases for f in flags if not f)      # the real half of every loop
-out["ref_tests"] = {m: run(ts.TestKLU, m) for m in ("test_lu", "test_linsolve", "test_solve")}
+# complex Hermitian matrix through the compiled cholmod wrapper ('z' spmatrix, cholmod.c:144,153,343-357)
+Az = spmatrix([10, 3 + 1j, 5, -2 - 2j, 5, 2], [0, 2, 1, 3, 2, 3], [0, 0, 1, 1, 2, 3], (4, 4), "z")
+Azd = np.array(matrix(Az)); Azd = np.tril(Azd) + np.tril(Azd, -1).conj().T
+bz = matrix([1 + 1j, 2, 3 - 2j, 4j])
+xz = +bz
+cholmod.linsolve(Az, xz)
+out["cholmod_z_linsolve_err"] = float(np.abs(np.array(xz).ravel() - np.linalg.solve(Azd, np.array(bz).ravel())).max())
+Fz = cholmod.symbolic(Az); cholmod.numeric(Az, Fz)
+dz = cholmod.diag(Fz)
+Lz = np.array(matrix(cholmod.getfactor(Fz)))
+out["cholmod_z_diag_err"] = float(np.abs(np.array(dz).ravel() - np.diag(Lz)).max())
+out["cholmod_z_typecode"] = dz.typecode
+# the reference's own loops, real and complex ('z') cases alike
+out["ref_tests"] = {m: run(ts.TestKLU, m) for m in ("test_lu", "test_linsolve", "test_solve", "test_get_det")}
 te = load("test_examples")
 for m in ("test_ch9_acent", "test_ch8_lp", "test_ch8_coneqp"):
     out["ref_tests"][m] = run(te.TestExamples, m)

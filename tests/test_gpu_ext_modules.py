@@ -36,6 +36,10 @@ def test_cholmod_documented_answers(ext):
     assert ext["diag_ldl_refused"] and ext["getfactor_nnz"] >= 6
 
 
+def test_cholmod_complex_hermitian_through_the_compiled_wrapper(ext):
+    assert ext["cholmod_z_linsolve_err"] < 1e-12 and ext["cholmod_z_diag_err"] < 1e-12 and ext["cholmod_z_typecode"] == "z"
+
+
 def test_cholmod_error_contract(ext):
     assert ext["npd"].startswith("ArithmeticError(")                     # documented: numeric raises with the failing column
     assert ext["npd_solve"] == "singular matrix"                         # cholmod.c:456
@@ -49,7 +53,7 @@ def test_klu_documented_answers(ext):
     assert ext["klu_singular"] == "singular matrix"                      # klu.c:370-371
 
 
-@pytest.mark.parametrize("name", ["test_lu", "test_linsolve", "test_solve", "test_ch9_acent", "test_ch8_lp", "test_ch8_coneqp"])
+@pytest.mark.parametrize("name", ["test_lu", "test_linsolve", "test_solve", "test_get_det", "test_ch9_acent", "test_ch8_lp", "test_ch8_coneqp"])
 def test_reference_suite_verbatim_on_compiled_modules(ext, name):
     assert ext["ref_tests"][name]["ok"], ext["ref_tests"][name]["detail"]
 

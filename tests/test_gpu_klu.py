@@ -231,3 +231,24 @@ def test_structure_variety_single_and_batched(klu, case, early_minw, monkeypatch
         Ab = sp.csc_matrix((vals[b], A.indices, A.indptr), shape=(n, n))
         xref = spla.splu(Ab.tocsc()).solve(Bb[b, 0])
         assert np.linalg.norm(Xb[b, 0] - xref) <= 1e-9 * np.linalg.norm(xref)
+
+
+def test_solve_ldB_buffer_ends_with_the_last_column(klu):
+    """klu.c:593-690: B needs offsetB + (nrhs-1)*ldB + n entries, not nrhs*ldB: nothing past the last column's n entries
+    may be read or written (regression: the host copies used nrhs*ldB doubles)"""
+    A = load_matrix("bp_800")
+    n = A.shape[0]
+    Fs = klu.symbolic(A); Fn = klu.numeric(A, Fs)
+    rng = np.random.default_rng(5)
+    ld, off = n + 7, 3
+    buf = rng.standard_normal(off + ld + n)            # exactly the documented minimum for nrhs = 2
+    keep = buf.copy()
+    klu.solve(A, Fs, Fn, buf, nrhs=2, ldB=ld, offsetB=off)
+    for j in range(2):
+        b = keep[off + j * ld: off + j * ld + n]
+        x = buf[off + j * ld: off + j * ld + n]
+        assert np.abs(A @ x - b).max() <= 1e-9 * max(1.0, np.abs(x).max()) * abs(A).sum(axis=0).max()
+    mask = np.ones(buf.size, bool)
+    for j in range(2):
+        mask[off + j * ld: off + j * ld + n] = False
+    assert np.array_equal(buf[mask], keep[mask])

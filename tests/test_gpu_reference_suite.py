@@ -1,9 +1,8 @@
 """The reference's OWN acceptance tests, executed verbatim from the copy oracle/build_ref.sh places
 under oracle/_ref/tests (git-ignored build output; the files are not part of this repository) against the B200 modules
 registered as kvxopt.klu / kvxopt.cholmod:
-  * tests/test_sparse_solvers.py::TestKLU  (reference tests/test_sparse_solvers.py:216-323) -- the real ('d') cases; the
-    complex half of each loop is dropped by replacing the module-level `product` (complex KLU is SURVEY section 8f-4 and
-    the engine rejects 'z' input with TypeError, checked here as well);
+  * tests/test_sparse_solvers.py::TestKLU  (reference tests/test_sparse_solvers.py:216-323) -- all four methods, real AND
+    complex cases, exactly as the reference loops over them;
   * tests/test_examples.py: the doc examples that reach cholmod through the IPM (test_ch9_acent: solvers.cp ->
     misc.kkt_chol2 -> cholmod.solve with 50 right-hand sides; test_ch8_lp; test_ch10_lp ...)."""
 import importlib.util
@@ -35,29 +34,32 @@ def run_case(cls, method):
     return res
 
 
-@pytest.mark.parametrize("method", ["test_lu", "test_linsolve", "test_solve"])
-def test_reference_TestKLU_real_cases(kvx, method):
+@pytest.mark.parametrize("method", ["test_lu", "test_linsolve", "test_solve", "test_get_det"])
+def test_reference_TestKLU_verbatim(kvx, method):
+    """the reference's own loops: product(cases, [True, False]) with True = complex ('z') matrices, trans in N, T, C"""
     mod = load_ref_module("test_sparse_solvers")
-    # the reference loops over product(cases, [True, False]) with True = complex: keep the real half
-    mod.product = lambda cases, flags: ((c, f) for c in cases for f in flags if not f)
     res = run_case(mod.TestKLU, method)
     assert res.testsRun == 1 and not res.skipped, res.skipped
     assert not res.failures and not res.errors, (res.failures, res.errors)
 
 
-def test_reference_TestKLU_get_det(kvx):
-    """the real determinant (= 114) passes; the complex half of the same reference test is refused with TypeError"""
+def test_reference_TestKLU_complex_cases_really_run(kvx):
+    """guard against a silently shortened loop: count the complex factorizations the reference test makes"""
     mod = load_ref_module("test_sparse_solvers")
-    res = run_case(mod.TestKLU, "test_get_det")
-    assert res.testsRun == 1 and not res.failures
-    assert len(res.errors) == 1 and "TypeError" in res.errors[0][1] and "Ac" in res.errors[0][1], res.errors
+    from kvxopt import klu
+    seen = {"z": 0, "d": 0}
+    orig = klu.numeric
 
-
-def test_reference_TestKLU_complex_is_refused_not_wrong(kvx):
-    mod = load_ref_module("test_sparse_solvers")
-    mod.product = lambda cases, flags: ((c, f) for c in cases[:1] for f in flags if f)
-    res = run_case(mod.TestKLU, "test_lu")
-    assert len(res.errors) == 1 and "TypeError" in res.errors[0][1]
+    def numeric(A, Fs):
+        seen[A.typecode] += 1
+        return orig(A, Fs)
+    klu.numeric = numeric
+    try:
+        res = run_case(mod.TestKLU, "test_lu")
+    finally:
+        klu.numeric = orig
+    assert not res.failures and not res.errors, (res.failures, res.errors)
+    assert seen["z"] >= 1 and seen["z"] == seen["d"]
 
 
 @pytest.mark.parametrize("method", ["test_ch9_acent", "test_ch8_lp", "test_ch8_coneqp", "test_ch10_lp", "test_ch9_acent2", "test_ch9_l2ac"])
