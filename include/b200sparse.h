@@ -203,6 +203,17 @@ void b200s_free(void* p);
  * perm_out[k] = grid index eliminated k-th; pass it as `perm` to b200s_chol_analyze. */
 b200s_status b200s_grid_nd_perm(b200s_int nx, b200s_int ny, b200s_int nz, b200s_int leaf,
                                 b200s_int* perm_out);
+/* Engine extension: which triangular sweeps of one-right-hand-side solves run as ONE persistent kernel per level over the
+ * level's large fronts (bit 0: forward, bit 1: backward; -1: the default = both, or B200S_SOLVE_PERSIST) instead of two
+ * launches per 128-column block step.  Both paths give bit-identical solutions; the launch-per-step path also serves several
+ * right-hand sides and the ownership-masked distributed solves. */
+b200s_status b200s_chol_set_solve_sweeps(b200s_chol* F, int mode);
+/* Test hook (host only, no device needed): replays on the CPU the static work lists and the flag / counter waits of the
+ * persistent solve sweeps (k_fwd_persist / k_bwd_persist: one kernel per level runs every 128-column block step of the level's
+ * large fronts, one right-hand side) for one front of nr rows and nc pivot columns on nctas CTAs.  0: every (block, tile) is
+ * applied exactly once and in the order of the launch-per-step kernels, every block is solved once and only after the rows it
+ * reads, and no CTA is left waiting; > 0: the first rule broken; -1: invalid arguments. */
+int b200s_persist_schedule_check(b200s_int nr, b200s_int nc, b200s_int nctas);
 /* AMD ordering of the symmetric pattern of the `uplo` triangle (src/C/amd.c `order`, host only). */
 b200s_status b200s_amd_order(b200s_int n, const b200s_int* colptr, const b200s_int* rowind,
                              char uplo, b200s_int* perm_out);

@@ -492,6 +492,15 @@ def factor_info(F):
     return _info(h).asdict()
 
 
+def set_solve_sweeps(F, mode=-1):
+    """extension: bit 0 / bit 1 of `mode` run the forward / backward sweep of one-right-hand-side solves as one persistent
+    kernel per level (the default, -1) instead of two launches per 128-column block step; bit-identical solutions"""
+    h, _ = _factor_handle(F)
+    st = fn["b200s_chol_set_solve_sweeps"](h, int(mode))
+    if st != L.OK:
+        _raise_status(st, "set_solve_sweeps failed")
+
+
 def factor_perm(F):
     """extension: the fill-reducing permutation held by F (L->Perm)"""
     h, _ = _factor_handle(F)

@@ -787,6 +787,7 @@ void b200s_chol_free(b200s_chol* F) {
     if (F->dev) {
         chol_device_sync(F->dev);
         // an object whose front ownership was changed (multi-GPU driver) is not handed on
+        chol_device_set_solve_sweeps(F->dev, -1);
         if (F->custom_owned || !plan_cache_park_device(F->plan_sp.get(), F->device, F->dev)) chol_device_destroy(F->dev);
     }
     delete F;
@@ -798,6 +799,18 @@ b200s_status b200s_grid_nd_perm(b200s_int nx, b200s_int ny, b200s_int nz, b200s_
     std::vector<i32> p = grid_nd(nx, ny, nz, leaf);
     for (size_t k = 0; k < p.size(); k++) perm_out[k] = p[k];
     return B200S_OK;
+}
+b200s_status b200s_chol_set_solve_sweeps(b200s_chol* F, int mode) {
+    if (!F || mode < -1 || mode > 3) return B200S_INVALID;
+    if (F->plan().n == 0) return B200S_OK;
+    b200s_status es = ensure_device(F);
+    if (es != B200S_OK) return es;
+    chol_device_set_solve_sweeps(F->dev, mode);
+    return B200S_OK;
+}
+int b200s_persist_schedule_check(b200s_int nr, b200s_int nc, b200s_int nctas) {
+    if (nr < 1 || nr > 0x3fffffff || nc < 1 || nc > nr || nctas < 1 || nctas > 4096) return -1;
+    return persist_schedule_check((int)nr, (int)nc, (int)nctas);
 }
 b200s_status b200s_amd_order(b200s_int n, const b200s_int* colptr, const b200s_int* rowind, char uplo, b200s_int* perm_out) {
     if (n < 0 || n > 0x7fffffff - 16 || (n > 0 && (!colptr || !perm_out))) return B200S_INVALID;

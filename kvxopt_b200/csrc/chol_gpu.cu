@@ -870,9 +870,17 @@ constexpr int SOLVE_BT = 192;    // rows per CTA in the backward (transposed) up
 constexpr int SB = 32;           // inverted diagonal sub-block
 constexpr int MINV_HALF = (NB / SB) * SB * SB;  // the four inverse sub-blocks of a 128-column block, column-major
 constexpr int MINV_BLK = 2 * MINV_HALF;         // ... followed by their transposes (backward solve)
-constexpr int LDD = NB + 2;      // smem stride of the staged diagonal block (even: 16-byte LDGSTS rows)
 constexpr int LDM = SB;          // smem stride of a staged inverse sub-block (always read column-wise)
-static constexpr size_t SMEM_SDIAG = (size_t)(NB * LDD + MINV_HALF + NB) * sizeof(double);
+// Staged diagonal block, PACKED: only the part below the inverted 32 x 32 sub-blocks is ever read -- for the 32 columns of
+// sub-block s the rows (s + 1) * 32 .. 127.  Column strides 104 / 72 / 40 (= rows + 8: stride % 16 == 8 keeps the
+// 8-rows-per-column access of the backward block solve at the two-wavefront minimum; even: 16-byte LDGSTS rows).
+constexpr int DPK_R0 = 104, DPK_R1 = 72, DPK_R2 = 40;
+constexpr int DPK_B1 = 32 * DPK_R0, DPK_B2 = DPK_B1 + 32 * DPK_R1, DIAG_PACK = DPK_B2 + 32 * DPK_R2;
+__device__ __forceinline__ int dpk_base(int s) { return s == 0 ? 0 : (s == 1 ? DPK_B1 : DPK_B2); }
+__device__ __forceinline__ int dpk_rows(int s) { return s == 0 ? DPK_R0 : (s == 1 ? DPK_R1 : DPK_R2); }
+// element (row r, column c) of the block, r >= ((c >> 5) + 1) * 32
+__device__ __forceinline__ int dpk(int c, int r) { const int s = c >> 5; return dpk_base(s) + (c & 31) * dpk_rows(s) + (r - 32 * (s + 1)); }
+static constexpr size_t SMEM_SDIAG = (size_t)(DIAG_PACK + MINV_HALF + NB) * sizeof(double);
 
 // inverse of the SB x SB lower-triangular diagonal sub-blocks: one CTA per 128-column block, one warp per sub-block,
 // lane j solves L x = e_j by substitution
@@ -958,37 +966,24 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const int* __restrict__ list
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
-__device__ __forceinline__ void stage_diag_block(const double* __restrict__ P, int ld, int k0, int w,
+__device__ __forceinline__ void stage_diag_issue(const double* __restrict__ P, int ld, int k0, int w,
                                                  const double* __restrict__ minv, double* Ls, double* Ms, int tid) {
     const unsigned lbase = (unsigned)__cvta_generic_to_shared(Ls), mbase = (unsigned)__cvta_generic_to_shared(Ms);
     const int nm = min(NB / SB, (w + SB - 1) / SB) * SB * SB;
     for (int i = tid * 2; i < nm; i += 512) cp_async16(mbase + 8u * (unsigned)i, minv + i);
     for (int idx = tid; idx < NB * (NB / 2); idx += 256) {
         const int c = idx >> 6, r = (idx & 63) * 2;
-        if (c < w && r < w && r >= ((c >> 5) + 1) * SB) cp_async16(lbase + 8u * (unsigned)(c * LDD + r), P + (long long)(k0 + c) * ld + k0 + r);
+        if (c < w && r < w && r >= ((c >> 5) + 1) * SB) cp_async16(lbase + 8u * (unsigned)dpk(c, r), P + (long long)(k0 + c) * ld + k0 + r);
     }
+}
+__device__ __forceinline__ void stage_diag_block(const double* __restrict__ P, int ld, int k0, int w,
+                                                 const double* __restrict__ minv, double* Ls, double* Ms, int tid) {
+    stage_diag_issue(P, ld, k0, w, minv, Ls, Ms, tid);
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
 }
-
-// forward, block kb: solve the (<=128)^2 diagonal block for t[k0..k0+w)
-__global__ void __launch_bounds__(256) k_fwd_diag(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, int kb, const FrontD* __restrict__ F,
-                                                  const double* __restrict__ L, const double* __restrict__ Minv,
-                                                  double* __restrict__ T, long long tstride,
-                                                  double* __restrict__ X, long long xstride,
-                                                  const unsigned char* __restrict__ owned = nullptr) {
-    extern __shared__ double sm[];
-    double* Ls = sm;                       // [col][row], stride LDD
-    double* Ms = Ls + NB * LDD;            // [sub-block][col][row], stride LDM
-    double* ts = Ms + MINV_HALF;
-    const FrontS f = load_front(sg, gfront, F, blockIdx.x);
-    if (owned && !owned[f.id]) return;
-    double* t = T + blockIdx.y * tstride + f.rowptr;
-    double* x = X + blockIdx.y * xstride + f.col0;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int k0 = kb * NB, w = min(NB, f.nc - k0);
-    stage_diag_block(L + f.loff, f.ld, k0, w, Minv + f.ioff + (long long)kb * MINV_BLK, Ls, Ms, tid);
-    if (tid < NB) ts[tid] = (tid < w) ? t[k0 + tid] : 0.0;
-    __syncthreads();
+// Forward block solve out of shared memory: ts[0..w) <- inv(L11) ts.  All 256 threads; ends with a CTA barrier.
+__device__ __forceinline__ void fwd_diag_core(const double* Ls, const double* Ms, double* ts, int w, int tid) {
+    const int lane = tid & 31;
     for (int b0 = 0; b0 < w; b0 += SB) {
         const double* M = Ms + (b0 / SB) * SB * SB;
         double xv = 0.0;
@@ -1003,13 +998,70 @@ __global__ void __launch_bounds__(256) k_fwd_diag(const __grid_constant__ SolveG
         __syncthreads();
         const int r = b0 + SB + tid;       // rows of this 128-block below the sub-block
         if (r < w) {
+            const int s = b0 / SB, rows = dpk_rows(s);
+            const double* lc = Ls + dpk_base(s) + tid;      // (row r, column b0): r - 32 (s + 1) = tid
             double a0 = 0, a1 = 0;
 #pragma unroll
-            for (int c = 0; c < SB; c += 2) { a0 = fma(Ls[(b0 + c) * LDD + r], ts[b0 + c], a0); a1 = fma(Ls[(b0 + c + 1) * LDD + r], ts[b0 + c + 1], a1); }
+            for (int c = 0; c < SB; c += 2) { a0 = fma(lc[c * rows], ts[b0 + c], a0); a1 = fma(lc[(c + 1) * rows], ts[b0 + c + 1], a1); }
             ts[r] -= a0 + a1;
         }
         __syncthreads();
     }
+}
+// Backward block solve: zs[0..w) <- inv(L11)^T zs (Ms holds the transposed inverses).  All 256 threads; ends with a CTA barrier.
+__device__ __forceinline__ void bwd_diag_core(const double* Ls, const double* Ms, double* zs, int w, int tid) {
+    const int lane = tid & 31;
+    const int nsb = (w + SB - 1) / SB;
+    for (int sbk = nsb - 1; sbk >= 0; sbk--) {
+        const int b0 = sbk * SB;
+        // contributions of the already solved rows of this 128-block (below the sub-block): 8 threads per column
+        {
+            const int q = tid >> 3, gq = tid & 7;
+            double sv = 0.0;
+            if (sbk < NB / SB - 1) {
+                const double* lc = Ls + dpk_base(sbk) + q * dpk_rows(sbk) - (b0 + SB);     // + r: element (row r, column b0 + q)
+                for (int r = b0 + SB + gq; r < w; r += 8) sv = fma(lc[r], zs[r], sv);
+            }
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+            if (gq == 0) zs[b0 + q] -= sv;
+        }
+        __syncthreads();
+        double xv = 0.0;
+        if (tid < 32) {                    // x_sub = inv(L_sub)^T z_sub
+            const double* M = Ms + sbk * SB * SB;          // transposed inverse, column-major
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int c = 0; c < SB; c += 2) { a0 = fma(M[c * LDM + lane], zs[b0 + c], a0); a1 = fma(M[(c + 1) * LDM + lane], zs[b0 + c + 1], a1); }
+            xv = a0 + a1;
+        }
+        __syncthreads();
+        if (tid < 32) zs[b0 + lane] = xv;
+        __syncthreads();
+    }
+}
+
+// forward, block kb: solve the (<=128)^2 diagonal block for t[k0..k0+w)
+__global__ void __launch_bounds__(256) k_fwd_diag(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, int kb, const FrontD* __restrict__ F,
+                                                  const double* __restrict__ L, const double* __restrict__ Minv,
+                                                  double* __restrict__ T, long long tstride,
+                                                  double* __restrict__ X, long long xstride,
+                                                  const unsigned char* __restrict__ owned = nullptr) {
+    extern __shared__ double sm[];
+    double* Ls = sm;                       // packed part of the block below the inverted sub-blocks (dpk)
+    double* Ms = Ls + DIAG_PACK;           // [sub-block][col][row], stride LDM
+    double* ts = Ms + MINV_HALF;
+    const FrontS f = load_front(sg, gfront, F, blockIdx.x);
+    if (owned && !owned[f.id]) return;
+    double* t = T + blockIdx.y * tstride + f.rowptr;
+    double* x = X + blockIdx.y * xstride + f.col0;
+    const int tid = threadIdx.x;
+    const int k0 = kb * NB, w = min(NB, f.nc - k0);
+    stage_diag_block(L + f.loff, f.ld, k0, w, Minv + f.ioff + (long long)kb * MINV_BLK, Ls, Ms, tid);
+    if (tid < NB) ts[tid] = (tid < w) ? t[k0 + tid] : 0.0;
+    __syncthreads();
+    fwd_diag_core(Ls, Ms, ts, w, tid);
     if (tid < w) { t[k0 + tid] = ts[tid]; x[k0 + tid] = ts[tid]; }
 }
 // stage a 64-row x w-column slice of the panel (rows r0.. with r0 even, columns k0..) in shared memory as S[col][64]:
@@ -1113,8 +1165,10 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
         for (int j = 0; j < 32; j++) p[c][j] = 0.0;
     static_assert(NSUB == 3, "one buffer per slice");
     double tv[CG][NSUB];
+    // slices in DESCENDING row order (2, 1, 0): the order of the persistent sweep, whose freshest rows are those of slice 0
 #pragma unroll
-    for (int sub = 0; sub < NSUB; sub++) {
+    for (int s_ = 0; s_ < NSUB; s_++) {
+        const int sub = NSUB - 1 - s_;
         stage_rows64(P, f.ld, f.nr, k0, w, r0 + sub * 64, sm + sub * NB * 64, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
         const int r = r0 + sub * 64 + rr;
@@ -1122,10 +1176,11 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
         for (int c = 0; c < CG; c++) tv[c][sub] = (c < cn && r < f.nr && r >= rb) ? t[c * tstride + r] : 0.0;
     }
 #pragma unroll
-    for (int sub = 0; sub < NSUB; sub++) {
-        if (sub == 0) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        if (sub == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        if (sub == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int s_ = 0; s_ < NSUB; s_++) {
+        const int sub = NSUB - 1 - s_;
+        if (s_ == 0) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        if (s_ == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (s_ == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const int r = r0 + sub * 64 + rr;
         if (r < f.nr && r >= rb) {
@@ -1174,7 +1229,7 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
                                                   const unsigned char* __restrict__ owned = nullptr) {
     extern __shared__ double sm[];
     double* Ls = sm;
-    double* Ms = Ls + NB * LDD;
+    double* Ms = Ls + DIAG_PACK;
     double* zs = Ms + MINV_HALF;
     double* Ps = zs + NB;                  // [PT_CHUNK][128] staged partial sums
     __shared__ double zh[NB];
@@ -1182,7 +1237,7 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
     if (owned && !owned[f.id]) return;
     double* t = T + blockIdx.y * tstride + f.rowptr;
     double* x = X + blockIdx.y * xstride + f.col0;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int k0 = kb * NB, w = min(NB, f.nc - k0);
     const int tile0 = sg.ng ? sg.prefix[blockIdx.x] : gprefix[blockIdx.x], tile1 = sg.ng ? sg.prefix[blockIdx.x + 1] : gprefix[blockIdx.x + 1];
     const double* pp = part + blockIdx.y * pstride + (long long)tile0 * NB;
@@ -1194,9 +1249,10 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
     }
     stage_diag_block(L + f.loff, f.ld, k0, w, Minv + f.ioff + (long long)kb * MINV_BLK + MINV_HALF, Ls, Ms, tid);   // commits + waits for all
     __syncthreads();
-    {   // two threads per column sum alternate partial rows; combined in a fixed order
+    {   // z = t - (P[0] + (P[2] + P[4] + ...) + (P[1] + P[3] + ...)), each chain in ascending tile order: the order of the
+        // persistent sweep (k_bwd_persist), which has every partial but the first long before it needs them
         const int q = tid & (NB - 1), h = tid >> 7;
-        double z = 0.0;
+        double z = 0.0, p0 = 0.0;
         for (int c0 = 0; c0 < tile1 - tile0; c0 += PT_CHUNK) {
             const int cnt = min(PT_CHUNK, tile1 - tile0 - c0);
             if (c0 > 0) {
@@ -1206,40 +1262,544 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
                 asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
                 __syncthreads();
             }
-            for (int tl = h; tl < cnt; tl += 2) z += Ps[tl * NB + q];
+            if (c0 == 0 && h == 0) p0 = Ps[q];
+            for (int tl = (c0 == 0 && h == 0) ? 2 : h; tl < cnt; tl += 2) z += Ps[tl * NB + q];
         }
         if (h == 1) zh[q] = z;
         __syncthreads();
-        if (h == 0) zs[q] = (q < w) ? t[k0 + q] - (z + zh[q]) : 0.0;
+        if (h == 0) zs[q] = (q < w) ? t[k0 + q] - (p0 + (z + zh[q])) : 0.0;
     }
     __syncthreads();
-    const int nsb = (w + SB - 1) / SB;
-    for (int sbk = nsb - 1; sbk >= 0; sbk--) {
-        const int b0 = sbk * SB;
-        // contributions of the already solved rows of this 128-block (below the sub-block): 8 threads per column
-        {
-            const int q = tid >> 3, gq = tid & 7;
-            double sv = 0.0;
-            for (int r = b0 + SB + gq; r < w; r += 8) sv = fma(Ls[(b0 + q) * LDD + r], zs[r], sv);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
-            if (gq == 0) zs[b0 + q] -= sv;
-        }
-        __syncthreads();
-        double xv = 0.0;
-        if (tid < 32) {                    // x_sub = inv(L_sub)^T z_sub
-            const double* M = Ms + sbk * SB * SB;          // transposed inverse, column-major
-            double a0 = 0, a1 = 0;
-#pragma unroll
-            for (int c = 0; c < SB; c += 2) { a0 = fma(M[c * LDM + lane], zs[b0 + c], a0); a1 = fma(M[(c + 1) * LDM + lane], zs[b0 + c + 1], a1); }
-            xv = a0 + a1;
-        }
-        __syncthreads();
-        if (tid < 32) zs[b0 + lane] = xv;
-        __syncthreads();
-    }
+    bwd_diag_core(Ls, Ms, zs, w, tid);
     if (tid < w) { t[k0 + tid] = zs[tid]; x[k0 + tid] = zs[tid]; }
+}
+
+// ---- persistent sweeps over the large fronts of one level (one right-hand side) -----------------------------------------
+// The level-by-level launches above pay one launch + one dependent load chain per 128-column block step (two kernels per
+// step, ~230 steps per sweep of the 100^3 factor: 0.25 of the HBM roofline).  Here ONE kernel per level runs all block steps
+// of all its large fronts: the CTAs of a front (one per SM) hand the solved block from one to the next through flags in
+// global memory (release / acquire), and stream their slices of the panel through a two-stage LDGSTS ring whose loads do not
+// depend on the solve chain -- so the chain per block step is one L2 round trip plus the block solve, and the panel is read at
+// memory speed underneath it.  Arithmetic and summation order are exactly those of k_fwd_diag / k_fwd_upd / k_bwd_upd /
+// k_bwd_diag (same device functions, same thread mapping): the results are bit-identical to the launch-per-step path, which
+// remains for several right-hand sides and for the ownership-masked distributed solves.
+struct PersistFront { FrontS f; int cta0, ncta, sync0, pad_; long long poff; };      // first CTA, CTAs, first flag, first partial tile
+constexpr int PMAXG = 32;
+struct PersistGroups { int ng, pad_; PersistFront fr[PMAXG]; };
+static constexpr size_t SMEM_PERSIST = (size_t)(2 * NB * 64 + DIAG_PACK + MINV_HALF + 3 * NB + 256) * sizeof(double);
+constexpr unsigned PERSIST_SPIN_LIMIT = 1u << 25;      // polls before a wait gives up and reports (never reached by a correct schedule)
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// wait until *p >= need; false when the wait was abandoned (error word set: the host reports ST_CUDA instead of hanging)
+__device__ __forceinline__ bool persist_wait(const int* p, int need, int* err) {
+    unsigned spins = 0;
+    while (ld_acquire(p) < need) {
+        if ((++spins & 1023u) == 0 && (spins > PERSIST_SPIN_LIMIT || *(volatile int*)err)) { *(volatile int*)err = 1; return false; }
+    }
+    return true;
+}
+
+// Static work lists of the persistent sweeps (host + device: persist_schedule_check replays them on the CPU).
+// Forward: item = (block kb, 64-row tile m), m in a 128-row pair owned by CTA c (pair p -> CTA p % G), rows at or below
+// rb(kb) = min(nc, (kb + 1) * 128); per CTA in (kb, m) ascending order.
+struct FwdSched {
+    int nr, nc, c, G;
+    __host__ __device__ int nblk() const { return (nc + NB - 1) / NB; }
+    __host__ __device__ int ntile() const { return (nr + SOLVE_FT - 1) / SOLVE_FT; }
+    __host__ __device__ int rb_of(int kb) const { return nc < (kb + 1) * NB ? nc : (kb + 1) * NB; }
+    __host__ __device__ bool first_tile(int kb, int& m) const {      // first item of block kb at or after tile m; false: none
+        const int rb = rb_of(kb), pmin = rb / NB;
+        int pr = (m >> 1) > pmin ? (m >> 1) : pmin;
+        pr += ((c - pr) % G + G) % G;            // next pair owned by this CTA
+        if (m < 2 * pr) m = 2 * pr;
+        if (m * SOLVE_FT + SOLVE_FT - 1 < rb) m++;       // first tile of the pair entirely above rb (last block only)
+        return m < ntile();
+    }
+    __host__ __device__ bool next_item(int& kb, int& m) const {      // advances (kb, m) to the item after it; false: done
+        if ((m & 1) == 0 && m + 1 < ntile()) { m++; return true; }
+        m = (m | 1) + 1 + 2 * (G - 1);           // first tile of the next owned pair
+        while (true) {
+            if (m < ntile() && first_tile(kb, m)) return true;
+            if (++kb >= nblk()) return false;
+            m = 0;
+            if (first_tile(kb, m)) return true;
+            m = ntile();
+        }
+    }
+};
+// Backward: block kb (descending) is solved by CTA kb % G; its 192-row tiles tl >= 1 go to CTA (kb + tl) % G, tile 0 to the
+// owner, after its other tiles.  Item = (kb, tl, 64-row slice sub).
+struct BwdSched {
+    int nr, nc, c, G;
+    __host__ __device__ int nblk() const { return (nc + NB - 1) / NB; }
+    __host__ __device__ int rb_of(int kb) const { return nc < (kb + 1) * NB ? nc : (kb + 1) * NB; }
+    __host__ __device__ int tiles_of(int kb) const { const int below = nr - (rb_of(kb) & ~1); return below > 0 ? (below + SOLVE_BT - 1) / SOLVE_BT : 0; }
+    __host__ __device__ int subs_of(int kb, int tl) const {          // 64-row slices of the tile that hold rows of the front
+        const int left = nr - ((rb_of(kb) & ~1) + tl * SOLVE_BT);
+        const int q = (left + 63) / 64;
+        return q < 3 ? q : 3;
+    }
+    __host__ __device__ bool first_in_block(int kb, int& tl) const { // first tile of block kb for this CTA; false: none
+        const int nt = tiles_of(kb);
+        int a = ((c - kb) % G + G) % G;          // (kb + tl) % G == c
+        if (a == 0) a = G;                       // tl >= 1 (tile 0 comes last)
+        if (a < nt) { tl = a; return true; }
+        if (kb % G == c && nt > 0) { tl = 0; return true; }
+        return false;
+    }
+    // slices of a tile in DESCENDING row order: sub = subs_of - 1 .. 0 (slice 0 holds the most recently solved rows)
+    __host__ __device__ bool next_slice(int& kb, int& tl, int& sub) const {
+        if (sub > 0) { sub--; return true; }
+        if (tl != 0) {
+            if (tl + G < tiles_of(kb)) { tl += G; sub = subs_of(kb, tl) - 1; return true; }
+            if (kb % G == c) { tl = 0; sub = subs_of(kb, 0) - 1; return true; }      // (tiles_of(kb) > tl >= 1)
+        }
+        while (--kb >= 0) if (first_in_block(kb, tl)) { sub = subs_of(kb, tl) - 1; return true; }
+        return false;
+    }
+};
+
+// CPU replay of both persistent schedules for ONE front (nr rows, nc pivot columns) on G CTAs: every CTA's program is followed
+// with the waits the kernels make, the CTAs advanced round robin.  Returns 0 when every (block, tile) is applied exactly once
+// and in the order of the launch-per-step kernels, every block is solved once and only after everything it reads, and no CTA
+// is left waiting (deadlock); a positive code otherwise (tests/test_host.py).
+int persist_schedule_check(int nr, int nc, int G) {
+    if (nr < 1 || nc < 1 || nc > nr || G < 1) return 1;
+    const int nblk = (nc + NB - 1) / NB;
+    {   // ---- forward
+        const int ntile = (nr + SOLVE_FT - 1) / SOLVE_FT;
+        std::vector<int> flag(nblk, 0), applied((size_t)nblk * ntile, 0), last_kb(ntile, -1);
+        struct St { int kb, m; bool have, started; };
+        std::vector<St> st(G);
+        auto diag = [&](int kb) -> int {          // all earlier blocks applied to the rows of block kb
+            if (flag[kb]) return 10;
+            for (int j = 0; j < kb; j++)
+                for (int m = 2 * kb; m < std::min(ntile, 2 * kb + 2); m++)
+                    if (applied[(size_t)j * ntile + m] != 1) return 11;
+            flag[kb] = 1;
+            return 0;
+        };
+        for (int c = 0; c < G; c++) {
+            const FwdSched S{nr, nc, c, G};
+            St& q = st[c];
+            q.kb = 0; q.m = 0; q.started = false;
+            q.have = S.first_tile(0, q.m);
+            if (!q.have) { q.m = ntile; q.have = S.next_item(q.kb, q.m); }
+        }
+        bool progress = true, all_done = false;
+        while (progress && !all_done) {
+            progress = false; all_done = true;
+            for (int c = 0; c < G; c++) {
+                const FwdSched S{nr, nc, c, G};
+                St& q = st[c];
+                if (!q.started) { q.started = true; progress = true; if (c == 0) { int e = diag(0); if (e) return e; } }
+                while (q.have) {
+                    if (!flag[q.kb]) break;      // persist_wait(flag + kb)
+                    const int rb = S.rb_of(q.kb);
+                    if (q.m >= ntile || q.m * SOLVE_FT + SOLVE_FT - 1 < rb) return 12;      // not a tile below the block
+                    if ((q.m >> 1) % G != c) return 13;                                     // not this CTA's pair
+                    if (applied[(size_t)q.kb * ntile + q.m]++) return 14;
+                    if (last_kb[q.m] >= q.kb) return 15;
+                    last_kb[q.m] = q.kb;
+                    const bool pair_done = (q.m & 1) || q.m + 1 >= ntile;
+                    if (pair_done && (q.m >> 1) == q.kb + 1 && q.kb + 1 < nblk) { int e = diag(q.kb + 1); if (e) return e; }
+                    q.have = S.next_item(q.kb, q.m);
+                    progress = true;
+                }
+                if (q.have) all_done = false;
+            }
+        }
+        if (!all_done) return 16;                // deadlock
+        for (int kb = 0; kb < nblk; kb++) {
+            if (!flag[kb]) return 17;
+            const int rb = std::min(nc, (kb + 1) * NB);
+            for (int m = 0; m < ntile; m++)
+                if (applied[(size_t)kb * ntile + m] != (m * SOLVE_FT + SOLVE_FT - 1 >= rb ? 1 : 0)) return 18;
+        }
+    }
+    {   // ---- backward
+        const BwdSched S0{nr, nc, 0, G};
+        std::vector<int> flag(nblk, 0), cnt(nblk, 0), toff(nblk + 1, 0);
+        for (int kb = 0; kb < nblk; kb++) toff[kb + 1] = toff[kb] + S0.tiles_of(kb);
+        std::vector<int> done(toff[nblk], 0);
+        struct St { int kb, tl, sub, dkb, acq; bool have, started; };
+        std::vector<St> st(G);
+        auto pivots_ready = [&](int first, int end) {       // every pivot row in [first, end) belongs to a solved block
+            for (int r = first; r < std::min(end, nc); r++) if (!flag[r / NB]) return false;
+            return true;
+        };
+        auto solve = [&](int kb, int c) -> int {
+            if (flag[kb]) return 20;
+            if (kb % G != c) return 21;
+            for (int j = kb + 1; j < nblk; j++) if (!flag[j]) return 22;
+            for (int tl = 0; tl < S0.tiles_of(kb); tl++) if (done[toff[kb] + tl] != 1) return 23;
+            flag[kb] = 1;
+            return 0;
+        };
+        bool progress = true, all_done = false;
+        while (progress && !all_done) {
+            progress = false; all_done = true;
+            for (int c = 0; c < G; c++) {
+                const BwdSched S{nr, nc, c, G};
+                St& q = st[c];
+                // owned blocks without a tile: solved as soon as the block after them is (owner_blocks_down_to)
+                auto owner_blocks = [&](int kstop, bool& blocked) -> int {
+                    while (q.dkb > kstop && q.dkb >= 0 && S.tiles_of(q.dkb) == 0) {
+                        if (q.dkb + 1 < nblk && !flag[q.dkb + 1]) { blocked = true; return 0; }
+                        int e = solve(q.dkb, c); if (e) return e;
+                        q.dkb -= G; progress = true;
+                    }
+                    return 0;
+                };
+                if (!q.started) {
+                    q.started = true; progress = true;
+                    q.dkb = nblk - 1 - (((nblk - 1 - c) % G) + G) % G;
+                    q.acq = nblk; q.kb = nblk; q.tl = 0; q.sub = 0; q.have = false;
+                    while (--q.kb >= 0) if (S.first_in_block(q.kb, q.tl)) { q.have = true; q.sub = S.subs_of(q.kb, q.tl) - 1; break; }
+                }
+                bool blocked = false;
+                if (!q.have) {                   // (also the first call of a CTA whose list is empty)
+                    int e = owner_blocks(-1, blocked); if (e) return e;
+                    if (blocked || (q.dkb >= 0 && S.tiles_of(q.dkb) == 0)) all_done = false;
+                    continue;
+                }
+                {   // blocks above the current item that the kernel solves before it (entry / end of the previous iteration)
+                    int e = owner_blocks(q.kb, blocked); if (e) return e;
+                    if (blocked) { all_done = false; continue; }
+                }
+                while (q.have) {
+                    const int rb = S.rb_of(q.kb), nt = S.tiles_of(q.kb), r0 = (rb & ~1) + q.tl * SOLVE_BT;
+                    if (q.tl >= nt || (q.tl != 0 && (q.kb + q.tl) % G != c) || (q.tl == 0 && q.kb % G != c)) return 24;
+                    if (q.sub == S.subs_of(q.kb, 0) - 1 && q.tl == 0 && nt > 1 && cnt[q.kb] < nt - 1) break;     // presum: persist_wait(cnt + kb)
+                    const int first = std::max(r0 + q.sub * 64, rb);
+                    if (first < nc && first / NB < q.acq) {
+                        if (!flag[first / NB]) break;                                       // persist_wait(flag + bneed)
+                        q.acq = first / NB;
+                    }
+                    if (!pivots_ready(first, r0 + q.sub * 64 + 64)) return 25;              // reads a row that is not solved yet
+                    if (q.sub < 0 || q.sub >= S.subs_of(q.kb, q.tl)) return 31;
+                    if (q.sub == 0) {
+                        if (done[toff[q.kb] + q.tl]++) return 26;
+                        if (q.tl != 0) cnt[q.kb]++;
+                        else { int e = solve(q.kb, c); if (e) return e; q.dkb = q.kb - G; }
+                    }
+                    int nkb = q.kb, ntl = q.tl, nsub = q.sub;
+                    const bool hnext = S.next_slice(nkb, ntl, nsub);
+                    if (q.sub > 0 && !(hnext && nkb == q.kb && ntl == q.tl && nsub == q.sub - 1)) return 27;
+                    progress = true;
+                    const int prev_kb = q.kb;
+                    q.have = hnext; q.kb = nkb; q.tl = ntl; q.sub = nsub;
+                    if (!hnext || nkb != prev_kb) {
+                        int e = owner_blocks(hnext ? nkb : -1, blocked); if (e) return e;
+                        if (blocked) break;
+                    }
+                }
+                if (q.have || blocked || (q.dkb >= 0 && S.tiles_of(q.dkb) == 0)) all_done = false;
+            }
+        }
+        if (!all_done) return 28;                // deadlock
+        for (int kb = 0; kb < nblk; kb++) {
+            if (!flag[kb]) return 29;
+            for (int tl = 0; tl < S0.tiles_of(kb); tl++) if (done[toff[kb] + tl] != 1) return 30;
+        }
+    }
+    return 0;
+}
+
+// CTA-wide wait: ONE thread polls (a front's CTAs all wait for the same word: 256 pollers per CTA saturate its L2 slice and
+// delay the very store they wait for), the barrier hands the acquired state to the others
+__device__ __forceinline__ void persist_wait_cta(const int* p, int need, int* err) {
+    if (threadIdx.x == 0) persist_wait(p, need, err);
+    __syncthreads();
+}
+// forward sweep of the large fronts of one level.  Rows are dealt in PAIRS of 64-row tiles (128 rows: pair p -> CTA p % G of
+// the front); the CTA that owns pair kb solves diagonal block kb right after it has applied block kb - 1 to that pair.
+__global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ PersistGroups pg, const double* __restrict__ L,
+                                                        const double* __restrict__ Minv, double* T, double* X, int* flags, int* err) {
+    extern __shared__ double sm[];
+    double* ring = sm;                     // 2 x [128 columns][64 rows]
+    double* Ls = ring + 2 * NB * 64;
+    double* Ms = Ls + DIAG_PACK;
+    double* ts = Ms + MINV_HALF;
+    double* xs = ts + NB;
+    double* red = xs + 2 * NB;             // [4][64]
+    int g = 0;
+    while (g + 1 < pg.ng && pg.fr[g + 1].cta0 <= (int)blockIdx.x) g++;
+    const FrontS f = pg.fr[g].f;
+    const int c = blockIdx.x - pg.fr[g].cta0, G = pg.fr[g].ncta;
+    int* flag = flags + pg.fr[g].sync0;
+    double* t = T + f.rowptr;
+    double* x = X + f.col0;
+    const double* P = L + f.loff;
+    const double* minv = Minv + f.ioff;
+    const int tid = threadIdx.x, rr = tid & (SOLVE_FT - 1), cq = tid >> 6;
+    const int nblk = (f.nc + NB - 1) / NB, ntile = (f.nr + SOLVE_FT - 1) / SOLVE_FT;
+    const FwdSched S{f.nr, f.nc, c, G};
+    auto first_tile = [&](int kb, int& m) { return S.first_tile(kb, m); };
+    auto next_item = [&](int& kb, int& m) { return S.next_item(kb, m); };
+    auto issue = [&](int kb, int m, int buf) {
+        const int k0 = kb * NB;
+        stage_rows64(P, f.ld, f.nr, k0, min(NB, f.nc - k0), m * SOLVE_FT, ring + buf * NB * 64, tid);
+    };
+    auto diag = [&](int kb, bool ts_ready) {     // staged data of block kb complete and visible (caller); ts_ready: so is ts
+        const int k0 = kb * NB, w = min(NB, f.nc - k0);
+        if (!ts_ready) {
+            if (tid < NB) ts[tid] = (tid < w) ? __ldcg(t + k0 + tid) : 0.0;
+            __syncthreads();
+        }
+        fwd_diag_core(Ls, Ms, ts, w, tid);
+        if (tid < w) { __stcg(t + k0 + tid, ts[tid]); __stcg(x + k0 + tid, ts[tid]); }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release(flag + kb, 1); }
+        if (kb + G < nblk) {
+            const int k1 = (kb + G) * NB;
+            stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)(kb + G) * MINV_BLK, Ls, Ms, tid);
+        }
+        cp_async_commit();
+    };
+    if (c < nblk) {
+        const int k1 = c * NB;
+        stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)c * MINV_BLK, Ls, Ms, tid);
+    }
+    cp_async_commit();
+    int kb = 0, m = 0;
+    bool have = first_tile(0, m);
+    if (!have) { m = ntile; have = next_item(kb, m); }
+    if (have) issue(kb, m, 0);
+    cp_async_commit();
+    if (c == 0) {
+        cp_async_wait<1>();
+        __syncthreads();
+        diag(0, false);
+    }
+    int xs_kb = -1, it = 0;
+    while (have) {
+        int nkb = kb, nm = m;
+        const bool hnext = next_item(nkb, nm);
+        if (hnext) issue(nkb, nm, (it + 1) & 1);
+        cp_async_commit();
+        const int k0 = kb * NB, w = min(NB, f.nc - k0), rb = k0 + w;
+        if (kb != xs_kb) {                       // x of block kb: published by the owner of pair kb
+            persist_wait_cta(flag + kb, 1, err);
+            if (tid < NB) xs[tid] = (tid < w) ? __ldcg(t + k0 + tid) : 0.0;
+            xs_kb = kb;
+        }
+        const int r0 = m * SOLVE_FT;
+        const bool wr = tid < SOLVE_FT && r0 + tid < f.nr && r0 + tid >= rb;
+        const double tprev = wr ? __ldcg(t + r0 + tid) : 0.0;
+        cp_async_wait<1>();
+        __syncthreads();
+        {
+            const bool rowok = r0 + rr < f.nr && r0 + rr >= rb;
+            const int wq = min(32, w - cq * 32);
+            const double* sp = ring + (it & 1) * NB * 64 + cq * 32 * 64 + rr;
+            double a0 = 0.0, a1 = 0.0;
+            if (rowok) {
+                int j = 0;
+                for (; j + 1 < wq; j += 2) {
+                    const double s0 = sp[j * 64], s1 = sp[(j + 1) * 64];
+                    a0 = fma(s0, xs[cq * 32 + j], a0); a1 = fma(s1, xs[cq * 32 + j + 1], a1);
+                }
+                if (j < wq) a0 = fma(sp[j * 64], xs[cq * 32 + j], a0);
+            }
+            red[cq * SOLVE_FT + rr] = a0 + a1;
+        }
+        __syncthreads();
+        // pair kb + 1: its owner solves the next diagonal block as soon as the pair is complete (the chain), then goes on with
+        // block kb; the right-hand side of that solve goes straight to shared memory (same values as written to T)
+        const bool chain = (m >> 1) == kb + 1 && kb + 1 < nblk;
+        const bool pair_done = (m & 1) || m + 1 >= ntile;
+        if (tid < SOLVE_FT) {
+            const double v = tprev - ((red[tid] + red[SOLVE_FT + tid]) + (red[2 * SOLVE_FT + tid] + red[3 * SOLVE_FT + tid]));
+            if (wr) __stcg(t + r0 + tid, v);
+            if (chain) {
+                ts[(m & 1) * SOLVE_FT + tid] = (wr && r0 + tid < f.nc) ? v : 0.0;
+                if (pair_done && !(m & 1)) ts[SOLVE_FT + tid] = 0.0;      // the pair has one tile only
+            }
+        }
+        if (chain && pair_done) {
+            __syncthreads();
+            diag(kb + 1, true);
+        }
+        have = hnext; kb = nkb; m = nm; it++;
+    }
+    cp_async_wait<0>();
+}
+
+// backward sweep of the large fronts of one level.  Block kb (descending) is solved by CTA kb % G of the front; the partial
+// sums of its 192-row tiles tl >= 1 are computed one step ahead by the CTAs (kb + tl) % G (their rows were solved two steps
+// earlier), written to `part` and counted in cnt[kb]; the owner pre-sums them, computes tile 0 -- the only piece that needs
+// the block just solved -- and solves.
+__global__ void __launch_bounds__(256, 1) k_bwd_persist(const __grid_constant__ PersistGroups pg, const double* __restrict__ L,
+                                                        const double* __restrict__ Minv, double* T, double* X, double* part, int* flags,
+                                                        int* cnts, int* err) {
+    extern __shared__ double sm[];
+    double* ring = sm;
+    double* Ls = ring + 2 * NB * 64;
+    double* Ms = Ls + DIAG_PACK;
+    double* zs = Ms + MINV_HALF;
+    double* zh = zs + NB;
+    double* p0s = zh + NB;
+    double* red = p0s + NB;                // [8][32]
+    int g = 0;
+    while (g + 1 < pg.ng && pg.fr[g + 1].cta0 <= (int)blockIdx.x) g++;
+    const FrontS f = pg.fr[g].f;
+    const int c = blockIdx.x - pg.fr[g].cta0, G = pg.fr[g].ncta;
+    int* flag = flags + pg.fr[g].sync0;
+    int* cnt = cnts + pg.fr[g].sync0;
+    double* t = T + f.rowptr;
+    double* x = X + f.col0;
+    const double* P = L + f.loff;
+    const double* minv = Minv + f.ioff + MINV_HALF;
+    double* pp = part + pg.fr[g].poff * NB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rr = tid & 63, cq = tid >> 6;
+    const int nblk = (f.nc + NB - 1) / NB;
+    const BwdSched S{f.nr, f.nc, c, G};
+    auto rb_of = [&](int kb) { return S.rb_of(kb); };
+    auto tiles_of = [&](int kb) { return S.tiles_of(kb); };
+    auto subs_of = [&](int kb, int tl) { return S.subs_of(kb, tl); };
+    auto first_in_block = [&](int kb, int& tl) { return S.first_in_block(kb, tl); };
+    auto next_slice = [&](int& kb, int& tl, int& sub) { return S.next_slice(kb, tl, sub); };
+    auto issue = [&](int kb, int tl, int sub, int buf) {
+        const int k0 = kb * NB;
+        stage_rows64(P, f.ld, f.nr, k0, min(NB, f.nc - k0), (rb_of(kb) & ~1) + tl * SOLVE_BT + sub * 64, ring + buf * NB * 64, tid);
+    };
+    // diagonal blocks this CTA solves: kb % G == c, descending
+    int dnext = nblk - 1 - (((nblk - 1 - c) % G) + G) % G;
+    if (dnext >= 0) {
+        const int k1 = dnext * NB;
+        stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)dnext * MINV_BLK, Ls, Ms, tid);
+    }
+    cp_async_commit();
+    int kb = nblk, tl = 0, sub = 0;
+    bool have = false;
+    while (--kb >= 0) if (first_in_block(kb, tl)) { have = true; sub = subs_of(kb, tl) - 1; break; }
+    if (have) issue(kb, tl, sub, 0);
+    cp_async_commit();
+    int acq = nblk;                              // blocks >= acq are known to be published
+    int it = 0;
+    double p[32];
+    double zpre = 0.0;                           // owner: sum of the partials of its chain (tiles 2, 4, .. or 1, 3, ..)
+    double tk0 = 0.0;                            // owner: t of the block it is about to solve (thread q < 128), fetched ahead
+    // the owner's part of a block that has NO tile at all (nothing below it: the last block of a root front)
+    auto solve_block = [&](int kb_, bool have_p0) {
+        const int k0 = kb_ * NB, w = min(NB, f.nc - k0);
+        const int q = tid & (NB - 1), h = tid >> 7;
+        if (h == 1) zh[q] = zpre;
+        __syncthreads();
+        if (h == 0) zs[q] = (q < w) ? (have_p0 ? tk0 : __ldcg(t + k0 + q)) - ((have_p0 ? p0s[q] : 0.0) + (zpre + zh[q])) : 0.0;
+        __syncthreads();
+        bwd_diag_core(Ls, Ms, zs, w, tid);
+        if (tid < w) { __stcg(t + k0 + tid, zs[tid]); __stcg(x + k0 + tid, zs[tid]); }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release(flag + kb_, 1); }
+        if (kb_ - G >= 0) {
+            const int k1 = (kb_ - G) * NB;
+            stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)(kb_ - G) * MINV_BLK, Ls, Ms, tid);
+        }
+        cp_async_commit();
+    };
+    // pre-sum of the other CTAs' partials of block kb_ (all counted in cnt[kb_]); the chain of this thread: h = 0 -> tiles 2, 4, ..
+    auto presum = [&](int kb_, long long pbase) {
+        const int nt = tiles_of(kb_);
+        const int q = tid & (NB - 1), h = tid >> 7;
+        zpre = 0.0;
+        if (nt > 1) {
+            persist_wait_cta(cnt + kb_, nt - 1, err);
+            const double* ps = pp + pbase * NB + q;
+            int tl_ = h == 0 ? 2 : 1;
+            for (; tl_ + 6 < nt; tl_ += 8) {     // four loads in flight, added in order
+                const double v0 = __ldcg(ps + (long long)tl_ * NB), v1 = __ldcg(ps + (long long)(tl_ + 2) * NB),
+                             v2 = __ldcg(ps + (long long)(tl_ + 4) * NB), v3 = __ldcg(ps + (long long)(tl_ + 6) * NB);
+                zpre += v0; zpre += v1; zpre += v2; zpre += v3;
+            }
+            for (; tl_ < nt; tl_ += 2) zpre += __ldcg(ps + (long long)tl_ * NB);
+        }
+    };
+    // first partial tile of every block: pbase(nblk - 1) = 0, pbase(kb) = pbase(kb + 1) + tiles(kb + 1)
+    long long pb = 0;
+    int pb_kb = nblk - 1;
+    auto pbase_of = [&](int kb_) { while (pb_kb > kb_) { pb += tiles_of(pb_kb); pb_kb--; } return pb; };
+    int dkb = dnext;                             // next block this CTA owns
+    // blocks owned by this CTA that come BEFORE its first item and have no tile of their own to trigger the solve
+    auto owner_blocks_down_to = [&](int kstop) { // solve owned blocks > kstop that have no tiles (no item will trigger them)
+        while (dkb > kstop && dkb >= 0) {
+            if (tiles_of(dkb) == 0) {
+                if (dkb + 1 < nblk && dkb + 1 < acq) { persist_wait_cta(flag + dkb + 1, 1, err); acq = dkb + 1; }
+                cp_async_wait<0>();
+                __syncthreads();
+                zpre = 0.0;
+                solve_block(dkb, false);
+                dkb -= G;
+            } else break;
+        }
+    };
+    owner_blocks_down_to(have ? kb : -1);
+    while (have) {
+        int nkb = kb, ntl = tl, nsub = sub;
+        const bool hnext = next_slice(nkb, ntl, nsub);
+        if (hnext) issue(nkb, ntl, nsub, (it + 1) & 1);
+        cp_async_commit();
+        const int k0 = kb * NB, w = min(NB, f.nc - k0), rb = k0 + w;
+        const int r0 = (rb & ~1) + tl * SOLVE_BT;
+        if (sub + 1 == subs_of(kb, tl)) {        // first slice of a tile
+#pragma unroll
+            for (int j = 0; j < 32; j++) p[j] = 0.0;
+            if (tl == 0) {                       // owner: everything but tile 0, before the wait for block kb + 1
+                presum(kb, pbase_of(kb));
+                tk0 = (tid < NB && tid < w) ? __ldcg(t + k0 + tid) : 0.0;
+            }
+        }
+        const int r = r0 + sub * 64 + rr;
+        {   // the rows of this slice: pivot rows of block r / 128 (published when flag is set) or rows below the pivots
+            const int first = max(r0 + sub * 64, rb);
+            const int bneed = first / NB;
+            if (first < f.nc && bneed < acq) { persist_wait_cta(flag + bneed, 1, err); acq = bneed; }
+        }
+        const double tv = (r < f.nr && r >= rb) ? __ldcg(t + r) : 0.0;
+        cp_async_wait<1>();
+        __syncthreads();
+        if (r < f.nr && r >= rb) {
+            const int wq = min(32, w - cq * 32);
+            const double* sp = ring + (it & 1) * NB * 64 + cq * 32 * 64 + rr;
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (j < wq) p[j] = fma(sp[j * 64], tv, p[j]);
+        }
+        if (sub == 0) {                          // tile complete: column sums over the 64 x 3 rows
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int j = 0; j < o; j++) {
+                    const double send = up ? p[j] : p[j + o];
+                    const double keep = up ? p[j + o] : p[j];
+                    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            red[warp * 32 + lane] = p[0];
+            __syncthreads();
+            if (tl != 0) {
+                double* dst = pp + (pbase_of(kb) + tl) * NB;
+                if (tid < NB) __stcg(dst + tid, red[(2 * (tid >> 5)) * 32 + (tid & 31)] + red[(2 * (tid >> 5) + 1) * 32 + (tid & 31)]);
+                __syncthreads();
+                if (tid == 0) { __threadfence(); atomicAdd(cnt + kb, 1); }
+            } else {
+                if (tid < NB) p0s[tid] = red[(2 * (tid >> 5)) * 32 + (tid & 31)] + red[(2 * (tid >> 5) + 1) * 32 + (tid & 31)];
+                // (solve_block's first barrier orders p0s before its readers)
+                solve_block(kb, true);
+                dkb = kb - G;
+            }
+        } else __syncthreads();                  // the ring buffer is free for the slice after the next
+        if (!hnext || nkb != kb) owner_blocks_down_to(hnext ? nkb : -1);
+        have = hnext; kb = nkb; tl = ntl; sub = nsub; it++;
+    }
+    cp_async_wait<0>();
 }
 
 __global__ void k_perm_gather(const double* __restrict__ B, long long ldB, const int* __restrict__ perm, int n,
@@ -1299,6 +1859,7 @@ struct LevelSched {
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
     Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
     int small_all_off = 0, small_all_cnt = 0;
+    int pgi = -1, pctas = 0;          // persistent sweeps (one right-hand side): index in CholDevice::pgroups, CTAs
 };
 
 class CholDevice {
@@ -1325,6 +1886,13 @@ public:
     void drop_graphs() { for (auto& kv : solve_graphs) cudaGraphExecDestroy(kv.second); solve_graphs.clear(); }
     i64 solve_cols = 0;            // capacity (columns) of dT / dX
     int max_solve_ctas = 1;        // most CTAs of one backward-update launch (sizes the partial-sum buffer)
+    std::vector<PersistGroups> pgroups;   // persistent sweeps: by-value launch records of the levels with 1..PMAXG large fronts
+    int persist_mode = 3;          // bit 0: forward, bit 1: backward sweep by k_fwd_persist / k_bwd_persist (B200S_SOLVE_PERSIST)
+    int persist_default = 3, persist_hw = 3;      // B200S_SOLVE_PERSIST or 3; 0 when a persistent CTA does not fit an SM
+    int* dsync = nullptr;          // [3][nsync]: forward flags, backward flags, backward partial counters (zeroed per sweep pair)
+    int nsync = 0;
+    double* dppart = nullptr;      // partial sums of the persistent backward sweep, one 128-vector per (front, block, tile)
+    int* herr = nullptr;           // mapped host word: a persistent kernel gave up a wait (schedule error instead of a hang)
     double* dpart = nullptr;
     double* dMinv = nullptr;       // inverted 32 x 32 diagonal sub-blocks of the large fronts (solve phase)
     int *dinv_front = nullptr, *dinv_kb = nullptr;
@@ -1350,6 +1918,8 @@ public:
         pool_free(dreach); pool_free(dsp_i); pool_free(dsp_x); pool_free(dsp_cnt); pool_free(dsp_oi); pool_free(dsp_ox); pool_free(dsp_meta);
         for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
+        pool_free(dsync); pool_free(dppart);
+        if (herr) cudaFreeHost(herr);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -1631,6 +2201,58 @@ int CholDevice::init() {
                 cnt.push_back((int)tiles);
             }
             emit(LS.syrk, fr, cnt);
+        }
+    }
+    {   // persistent sweeps: CTAs of a level dealt to its large fronts by panel area, one CTA per SM
+        if (const char* e = getenv("B200S_SOLVE_PERSIST")) persist_default = atoi(e) & 3;
+        int nsm = 0, occ_f = 0, occ_b = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+        CUDA_TRY(cudaFuncSetAttribute(k_fwd_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PERSIST));
+        CUDA_TRY(cudaFuncSetAttribute(k_bwd_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PERSIST));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_persist, 256, SMEM_PERSIST));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_persist, 256, SMEM_PERSIST));
+        if (occ_f < 1 || occ_b < 1 || nsm < 1) persist_hw = 0;        // every CTA of a launch must be resident (they wait for each other)
+        persist_default &= persist_hw;
+        persist_mode = persist_default;
+        long long ptiles = 0;
+        for (int l = 0; l < P.nlevels && persist_hw; l++) {
+            LevelSched& LS = levels[l];
+            if (LS.panel.empty() || LS.panel[0].ng < 1 || LS.panel[0].ng > PMAXG || LS.panel[0].ng > nsm) continue;
+            const int ng = LS.panel[0].ng;
+            const int* fr = sched.data() + LS.panel[0].goff;      // the large fronts of the level
+            PersistGroups G;
+            memset(&G, 0, sizeof(G));
+            G.ng = ng;
+            double area = 0;
+            for (int i = 0; i < ng; i++) area += (double)hf[fr[i]].nr * hf[fr[i]].nc;
+            int cta = 0;
+            for (int i = 0; i < ng; i++) {
+                const FrontD& d = hf[fr[i]];
+                const int npairs = (d.nr + NB - 1) / NB, nblk = (d.nc + NB - 1) / NB;
+                const int extra = (int)((double)(nsm - ng) * ((double)d.nr * d.nc / area));
+                PersistFront& pf = G.fr[i];
+                pf.f = FrontS{d.loff, d.rowptr, d.ioff, d.uoff, d.nc, d.nr, d.ld, d.col0, fr[i], 0};
+                pf.cta0 = cta;
+                pf.ncta = 1 + std::max(0, std::min(npairs - 1, extra));
+                pf.sync0 = nsync;
+                pf.poff = ptiles;
+                cta += pf.ncta;
+                nsync += nblk;
+                for (int kb = 0; kb < nblk; kb++) {
+                    const int below = d.nr - (std::min(d.nc, (kb + 1) * NB) & ~1);
+                    if (below > 0) ptiles += (below + SOLVE_BT - 1) / SOLVE_BT;
+                }
+            }
+            LS.pgi = (int)pgroups.size();
+            LS.pctas = cta;
+            pgroups.push_back(G);
+        }
+        if (!pgroups.empty()) {
+            CUDA_TRY(pool_malloc((void**)&dsync, (size_t)3 * nsync * sizeof(int)));
+            CUDA_TRY(pool_malloc((void**)&dppart, std::max<size_t>((size_t)ptiles * NB, 1) * sizeof(double)));
+            CUDA_TRY(cudaHostAlloc((void**)&herr, sizeof(int), cudaHostAllocMapped));
+            *herr = 0;
+            total_bytes += (size_t)3 * nsync * sizeof(int) + (size_t)ptiles * NB * sizeof(double);
         }
     }
     {
@@ -2024,8 +2646,10 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         // (columns, directions) into a CUDA graph and replayed
         const bool reach = active_fronts && do_fwd;
         if (reach) CUDA_TRY(cudaMemsetAsync(dT, 0, (size_t)tstride * nc * sizeof(double), stream));
+        const bool pfwd = nc == 1 && (persist_mode & 1) && !pgroups.empty(), pbwd = nc == 1 && (persist_mode & 2) && !pgroups.empty();
         auto sweeps = [&]() {
-        if (do_fwd)
+            if ((pfwd && do_fwd) || (pbwd && do_bwd)) cudaMemsetAsync(dsync, 0, (size_t)3 * nsync * sizeof(int), stream);
+            if (do_fwd)
                 for (int l = 0; l < P.nlevels; l++) {
                     const LevelSched& LS = levels[l];
                     if (reach) {
@@ -2035,6 +2659,9 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                         k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
+                        if (pfwd && LS.pgi >= 0)
+                            k_fwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(pgroups[LS.pgi], dL, dMinv, dT, dX, dsync, herr);
+                        else
                         for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
                             const Launch& la = LS.sfwd[kb];
                             k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n);
@@ -2050,6 +2677,9 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     const LevelSched& LS = levels[l];
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
+                        if (pbwd && LS.pgi >= 0)
+                            k_bwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(pgroups[LS.pgi], dL, dMinv, dT, dX, dppart, dsync + nsync, dsync + 2 * nsync, herr);
+                        else
                         for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
                             const Launch& la = LS.sbwd[kb];
                             if (la.ctas)
@@ -2062,7 +2692,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                         k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
                 }
         };
-        const int gkey = nc * 8 + (ldl ? 4 : 0) + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
+        const int gkey = nc * 32 + (pfwd ? 16 : 0) + (pbwd ? 8 : 0) + (ldl ? 4 : 0) + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
         if (!use_graphs || reach) sweeps();      // the filtered lists change from call to call: not captured
         else {
             auto it = solve_graphs.find(gkey);
@@ -2091,6 +2721,11 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     cudaError_t se = cudaStreamSynchronize(stream);
     CUDA_TRY(le);
     CUDA_TRY(se);
+    if (herr && *herr) {
+        *herr = 0;
+        set_last_error("persistent solve sweep: a CTA gave up waiting for another one (schedule error); set B200S_SOLVE_PERSIST=0");
+        return ST_CUDA;
+    }
     if (times) { float ms; cudaEventElapsedTime(&ms, ev[4], ev[5]); times->ms_solve = ms; }
     return ST_OK;
 }
@@ -2377,6 +3012,7 @@ int chol_device_solve_buffers(CholDevice* d, double** T, double** X) {
     *T = d->dT; *X = d->dX;
     return rc;
 }
+void chol_device_set_solve_sweeps(CholDevice* d, int mode) { d->persist_mode = mode < 0 ? d->persist_default : (mode & d->persist_hw); }
 void chol_device_mark_numeric(CholDevice* d, bool numeric) { d->numeric = numeric; d->minv_valid = false; }
 i64 chol_device_workspace_bytes(const CholDevice* d) { return d->total_bytes; }
 

@@ -340,6 +340,51 @@ def test_multi_rhs_solve_equals_column_by_column(cholmod):
                 assert np.array_equal(X[:, k - 1], x1[:, 0]), (k, sys_)
 
 
+@pytest.mark.parametrize("case", ["lap22", "lap40", "dense1500", "lap30_ldl"])
+def test_persistent_sweeps_bit_identical_to_the_launch_per_step_path(cholmod, case):
+    """one right-hand side: the forward / backward sweeps over a level's large fronts run as ONE persistent kernel per level
+    (CTAs hand the solved 128-column block on through flags, chol_gpu.cu k_fwd_persist / k_bwd_persist).  Same arithmetic in
+    the same order as the launch-per-step kernels: solutions are bit-identical for every combination of the two sweeps and
+    every system of cholmod.c:437-439 that runs a sweep; several blocks per front, several fronts per level, a root front
+    with nothing below its last block (dense1500), signed LDL' mode."""
+    from kvxopt_b200 import _lib as L
+    opts = dict(cholmod.options)
+    try:
+        if case.startswith("lap"):
+            nx = int(case[3:5])
+            A = lap3d(nx, nx, nx); Al = lower_ccs(A); n = A.shape[0]
+            perm = np.zeros(n, np.int64)
+            assert L.fn["b200s_grid_nd_perm"](nx, nx, nx, 64, L.ptr_i64(perm)) == 0
+            if case.endswith("ldl"):
+                cholmod.options["supernodal"] = 0
+            F = cholmod.symbolic(Al, p=perm)
+        else:
+            n = 1500
+            rng = np.random.default_rng(11)
+            M = rng.standard_normal((n, n)) / np.sqrt(n)
+            A = sp.csc_matrix(M @ M.T + 2.0 * np.eye(n)); Al = lower_ccs(A)
+            F = cholmod.symbolic(Al, p=np.arange(n, dtype=np.int64))
+        cholmod.numeric(Al, F)
+        assert cholmod.factor_info(F)["max_front_rows"] > 256
+        b = np.random.default_rng(5).standard_normal((n, 1))
+        ref = {}
+        for mode in (0, 1, 2, 3, -1):
+            cholmod.set_solve_sweeps(F, mode)
+            for sys_ in (0, 1, 4, 5) + ((2, 3) if case.endswith("ldl") else ()):
+                x = np.asfortranarray(b.copy()); cholmod.solve(F, x, sys=sys_)
+                if mode == 0:
+                    ref[sys_] = x
+                    if sys_ == 0:
+                        assert berr(A, x, b) <= BERR_TOL
+                else:
+                    assert np.array_equal(x, ref[sys_]), (case, mode, sys_, np.abs(x - ref[sys_]).max())
+            if mode == 3:       # replayed from the captured graph: same bits again
+                x = np.asfortranarray(b.copy()); cholmod.solve(F, x)
+                assert np.array_equal(x, ref[0])
+    finally:
+        cholmod.options.clear(); cholmod.options.update(opts)
+
+
 def test_numeric_with_subset_and_changed_pattern(cholmod):
     """cholmod.numeric rebuilds the matrix from A's own pattern (cholmod.c:340-358): a matrix that stores a SUBSET of the
     analysed pattern factors correctly (missing entries are zeros); an entry outside the analysed pattern is refused instead

@@ -521,3 +521,24 @@ def test_klu_pivot_rule_against_an_independent_run(name):
     # off-diagonal part of U that KLU keeps unfactored in F
     assert O.nnz_L == inf.nnz_L and (inf.nblocks > 1 or O.nnz_U == inf.nnz_U)
     fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
+def test_persistent_solve_schedules_replayed_on_the_host():
+    """k_fwd_persist / k_bwd_persist run every block step of a level's large fronts in ONE kernel whose CTAs wait for each other
+    through flags: the static work lists and the waits are replayed on the CPU (b200s_persist_schedule_check, the same
+    host/device iterators the kernels use) -- every (block, tile) exactly once and in block order, every block solved once
+    after the rows it reads, no CTA left waiting -- over the shapes of the 100^3 root front, fronts with nr == nc (nothing
+    below the last block), odd pivot counts, more CTAs than blocks, and random shapes."""
+    import random
+    from kvxopt_b200 import _lib
+    chk = _lib.fn["b200s_persist_schedule_check"]
+    cases = [(15000, 14900, 148), (15000, 14900, 1), (10000, 10000, 79), (5000, 2500, 37), (129, 1, 1), (129, 129, 2),
+             (300, 200, 3), (256, 256, 2), (257, 257, 3), (1000, 999, 8), (1000, 1000, 8), (640, 130, 5), (193, 65, 2),
+             (2563, 1283, 21), (385, 383, 4)]
+    rng = random.Random(7)
+    for _ in range(600):
+        nr = rng.randint(129, 4000)
+        cases.append((nr, rng.randint(1, nr), rng.randint(1, (nr + 127) // 128)))
+    for nr, nc, g in cases:
+        assert chk(nr, nc, g) == 0, (nr, nc, g, chk(nr, nc, g))
+    assert chk(100, 200, 1) == -1 and chk(100, 50, 0) == -1
