@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const
 // The 32 x 32 diagonal sub-blocks of every 128-column block are inverted once per factorization (k_diag_inverse), so
 // a block step is four small matrix-vector products instead of a 128-step substitution chain.
 constexpr int SOLVE_FT = 64;     // rows per CTA in the forward update  (256 threads = 64 rows x 4 column quarters)
-constexpr int SOLVE_BT = 192;    // rows per CTA in the backward (transposed) update: three 64-row slices, all in flight
+constexpr int SOLVE_BT = 128;    // rows per CTA in the backward (transposed) update: the two 64-row slices of an ABSOLUTE 128-row pair
 constexpr int SB = 32;           // inverted diagonal sub-block
 constexpr int MINV_HALF = (NB / SB) * SB * SB;  // the four inverse sub-blocks of a 128-column block, column-major
 constexpr int MINV_BLK = 2 * MINV_HALF;         // ... followed by their transposes (backward solve)
@@ -1135,16 +1135,16 @@ __global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGr
         }
     }
 }
-// backward, block kb: partial[q] = sum over a 192-row tile of the rows below the block of L[r, k0+q] * t[r].
-// Three 64-row slices, one shared-memory buffer each (192 KB in flight); thread = (row, column quarter);
-// the 32 per-lane column sums of a warp are combined by a halving butterfly.  CG right-hand sides share the staged tile
-// (blockIdx.y = group of CG columns): one shared-memory read feeds CG sums.
+// backward, block kb: partial[q] = sum over the rows r >= rb of ONE 128-row pair (rows 128 p .. 128 p + 127, p = rb / 128 +
+// tile: the same absolute pairs as the forward sweep) of L[r, k0+q] * t[r].  Two 64-row slices, one shared-memory buffer each
+// (128 KB in flight); thread = (row, column quarter) accumulates slice 1 then slice 0; the 32 per-lane column sums of a warp are
+// combined by a halving butterfly.  CG right-hand sides share the staged tile (blockIdx.y = group of CG columns).
 template <int CG>
 __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
                                                  int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
                                                  const double* __restrict__ T, long long tstride, double* __restrict__ part,
                                                  long long pstride, int ncols, const unsigned char* __restrict__ owned = nullptr) {
-    extern __shared__ double sm[];         // 3 buffers of [128 columns][64 rows]
+    extern __shared__ double sm[];         // 2 buffers of [128 columns][64 rows]
     __shared__ double red[CG][8][32];
     int tile;
     const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
@@ -1156,16 +1156,16 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rr = tid & 63, cq = tid >> 6;
     const int wq = min(32, w - cq * 32);
-    const int rb = k0 + w, r0 = (rb & ~1) + tile * SOLVE_BT;
+    const int rb = k0 + w, r0 = (rb / NB + tile) * SOLVE_BT;
     constexpr int NSUB = SOLVE_BT / 64;
     double p[CG][32];
 #pragma unroll
     for (int c = 0; c < CG; c++)
 #pragma unroll
         for (int j = 0; j < 32; j++) p[c][j] = 0.0;
-    static_assert(NSUB == 3, "one buffer per slice");
+    static_assert(NSUB == 2, "one buffer per slice");
     double tv[CG][NSUB];
-    // slices in DESCENDING row order (2, 1, 0): the order of the persistent sweep, whose freshest rows are those of slice 0
+    // slices in DESCENDING row order (1, 0): the order of the persistent sweep
 #pragma unroll
     for (int s_ = 0; s_ < NSUB; s_++) {
         const int sub = NSUB - 1 - s_;
@@ -1178,9 +1178,8 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
 #pragma unroll
     for (int s_ = 0; s_ < NSUB; s_++) {
         const int sub = NSUB - 1 - s_;
-        if (s_ == 0) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        if (s_ == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        if (s_ == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (s_ == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (s_ == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const int r = r0 + sub * 64 + rr;
         if (r < f.nr && r >= rb) {
@@ -1219,7 +1218,7 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
 // backward, block kb: z = t_blk - sum of the tile partials (fixed order), then solve L11^T x = z
 constexpr int BWD_CG = 4;        // right-hand sides per CTA in the backward update (multi-column solves)
 constexpr int PT_CHUNK = 48;     // partial rows staged per pass
-static constexpr size_t SMEM_FUPD = (size_t)NB * 64 * sizeof(double), SMEM_BUPD = 3 * SMEM_FUPD;
+static constexpr size_t SMEM_FUPD = (size_t)NB * 64 * sizeof(double), SMEM_BUPD = 2 * SMEM_FUPD;
 static constexpr size_t SMEM_BDIAG = SMEM_SDIAG + (size_t)PT_CHUNK * NB * sizeof(double);
 __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int kb,
                                                   const FrontD* __restrict__ F, const double* __restrict__ L,
@@ -1232,7 +1231,6 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
     double* Ms = Ls + DIAG_PACK;
     double* zs = Ms + MINV_HALF;
     double* Ps = zs + NB;                  // [PT_CHUNK][128] staged partial sums
-    __shared__ double zh[NB];
     const FrontS f = load_front(sg, gfront, F, blockIdx.x);
     if (owned && !owned[f.id]) return;
     double* t = T + blockIdx.y * tstride + f.rowptr;
@@ -1242,32 +1240,30 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
     const int tile0 = sg.ng ? sg.prefix[blockIdx.x] : gprefix[blockIdx.x], tile1 = sg.ng ? sg.prefix[blockIdx.x + 1] : gprefix[blockIdx.x + 1];
     const double* pp = part + blockIdx.y * pstride + (long long)tile0 * NB;
     const unsigned pbase = (unsigned)__cvta_generic_to_shared(Ps);
-    {
-        const int cnt = min(PT_CHUNK, tile1 - tile0) * NB;
-        for (int i = tid * 2; i < cnt; i += 512)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pbase + 8u * (unsigned)i), "l"(pp + i));
+    const int nt = tile1 - tile0;
+    {   // the partials are subtracted one after the other from the LAST pair down (the order in which the persistent sweep
+        // meets them: the rows below the pivots first, then block after block as they are solved): top chunk first
+        const int c0 = max(0, nt - PT_CHUNK);
+        for (int i = tid * 2; i < (nt - c0) * NB; i += 512)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pbase + 8u * (unsigned)i), "l"(pp + (long long)c0 * NB + i));
     }
     stage_diag_block(L + f.loff, f.ld, k0, w, Minv + f.ioff + (long long)kb * MINV_BLK + MINV_HALF, Ls, Ms, tid);   // commits + waits for all
     __syncthreads();
-    {   // z = t - (P[0] + (P[2] + P[4] + ...) + (P[1] + P[3] + ...)), each chain in ascending tile order: the order of the
-        // persistent sweep (k_bwd_persist), which has every partial but the first long before it needs them
-        const int q = tid & (NB - 1), h = tid >> 7;
-        double z = 0.0, p0 = 0.0;
-        for (int c0 = 0; c0 < tile1 - tile0; c0 += PT_CHUNK) {
-            const int cnt = min(PT_CHUNK, tile1 - tile0 - c0);
-            if (c0 > 0) {
+    {
+        double z = (tid < w) ? t[k0 + tid] : 0.0;
+        for (int c1 = nt; c1 > 0; c1 -= PT_CHUNK) {
+            const int c0 = max(0, c1 - PT_CHUNK);
+            if (c1 < nt) {
                 __syncthreads();
-                for (int i = tid * 2; i < cnt * NB; i += 512)
+                for (int i = tid * 2; i < (c1 - c0) * NB; i += 512)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pbase + 8u * (unsigned)i), "l"(pp + (long long)c0 * NB + i));
                 asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
                 __syncthreads();
             }
-            if (c0 == 0 && h == 0) p0 = Ps[q];
-            for (int tl = (c0 == 0 && h == 0) ? 2 : h; tl < cnt; tl += 2) z += Ps[tl * NB + q];
+            if (tid < NB)
+                for (int tl = c1 - 1; tl >= c0; tl--) z -= Ps[(tl - c0) * NB + tid];
         }
-        if (h == 1) zh[q] = z;
-        __syncthreads();
-        if (h == 0) zs[q] = (q < w) ? t[k0 + q] - (p0 + (z + zh[q])) : 0.0;
+        if (tid < NB) zs[tid] = (tid < w) ? z : 0.0;
     }
     __syncthreads();
     bwd_diag_core(Ls, Ms, zs, w, tid);
@@ -1283,10 +1279,12 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
 // memory speed underneath it.  Arithmetic and summation order are exactly those of k_fwd_diag / k_fwd_upd / k_bwd_upd /
 // k_bwd_diag (same device functions, same thread mapping): the results are bit-identical to the launch-per-step path, which
 // remains for several right-hand sides and for the ownership-masked distributed solves.
-struct PersistFront { FrontS f; int cta0, ncta, sync0, pad_; long long poff; };      // first CTA, CTAs, first flag, first partial tile
-constexpr int PMAXG = 32;
-struct PersistGroups { int ng, pad_; PersistFront fr[PMAXG]; };
-static constexpr size_t SMEM_PERSIST = (size_t)(2 * NB * 64 + DIAG_PACK + MINV_HALF + 3 * NB + 256) * sizeof(double);
+struct PersistFront { FrontS f; int cta0, ncta, sync0, pad_; };      // first CTA, CTAs, first flag
+// A level's launch: `nf` records in global memory (a persistent kernel starts once per level: one dependent load is nothing).
+// nf <= CTAs: front i runs on the CTAs cta0 .. cta0 + ncta - 1 (`cmap` gives the front of every CTA); more fronts than SMs:
+// every front runs on ONE CTA (ncta == 1), CTA b takes the fronts b, b + gridDim.x, ...
+struct PersistLevel { const PersistFront* fr; const int* cmap; int nf, shared; };
+static constexpr size_t SMEM_PERSIST = (size_t)(2 * NB * 64 + DIAG_PACK + MINV_HALF + 4 * NB + 256) * sizeof(double);
 constexpr unsigned PERSIST_SPIN_LIMIT = 1u << 25;      // polls before a wait gives up and reports (never reached by a correct schedule)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -1323,44 +1321,53 @@ struct FwdSched {
     __host__ __device__ bool next_item(int& kb, int& m) const {      // advances (kb, m) to the item after it; false: done
         if ((m & 1) == 0 && m + 1 < ntile()) { m++; return true; }
         m = (m | 1) + 1 + 2 * (G - 1);           // first tile of the next owned pair
+        const int npairs = (nr + NB - 1) / NB;
+        const int pmax = c < npairs ? c + ((npairs - 1 - c) / G) * G : -1;     // last pair of this CTA
         while (true) {
             if (m < ntile() && first_tile(kb, m)) return true;
-            if (++kb >= nblk()) return false;
+            // (the first pair below a block only moves down: once it is past pmax the CTA is done -- no scan over the
+            // remaining blocks, which sat in the middle of the solve chain)
+            if (++kb >= nblk() || rb_of(kb) / NB > pmax) return false;
             m = 0;
             if (first_tile(kb, m)) return true;
             m = ntile();
         }
     }
 };
-// Backward: block kb (descending) is solved by CTA kb % G; its 192-row tiles tl >= 1 go to CTA (kb + tl) % G, tile 0 to the
-// owner, after its other tiles.  Item = (kb, tl, 64-row slice sub).
+// Backward (the mirror image): COLUMN blocks are dealt to the CTAs (block kb -> CTA kb % G, which also solves it); the row
+// pairs are met from the last one down -- the rows below the pivots first, then pair p as soon as block p is solved -- and pair
+// p is applied to every owned block kb whose rows below the pivots reach into it (pmin(kb) = rb(kb) / 128 <= p), the highest
+// block first: kb = p - 1 is the one the chain waits for.  Item = (pair p, block kb, 64-row slice sub), slice 1 before 0.
 struct BwdSched {
     int nr, nc, c, G;
     __host__ __device__ int nblk() const { return (nc + NB - 1) / NB; }
+    __host__ __device__ int npairs() const { return (nr + NB - 1) / NB; }
     __host__ __device__ int rb_of(int kb) const { return nc < (kb + 1) * NB ? nc : (kb + 1) * NB; }
-    __host__ __device__ int tiles_of(int kb) const { const int below = nr - (rb_of(kb) & ~1); return below > 0 ? (below + SOLVE_BT - 1) / SOLVE_BT : 0; }
-    __host__ __device__ int subs_of(int kb, int tl) const {          // 64-row slices of the tile that hold rows of the front
-        const int left = nr - ((rb_of(kb) & ~1) + tl * SOLVE_BT);
-        const int q = (left + 63) / 64;
-        return q < 3 ? q : 3;
+    __host__ __device__ int pmin_of(int kb) const { return rb_of(kb) / NB; }
+    __host__ __device__ int subs_of(int p) const { return p * NB + 64 < nr ? 2 : 1; }       // 64-row slices of pair p inside the front
+    // highest block owned by this CTA that pair p is applied to; < 0: none
+    __host__ __device__ int first_kb(int p) const {
+        const int last = nblk() - 1;
+        int kmax = p >= pmin_of(last) ? last : (last - 1 < p - 1 ? last - 1 : p - 1);
+        if (kmax < c) return -1;
+        return kmax - (kmax - c) % G;
     }
-    __host__ __device__ bool first_in_block(int kb, int& tl) const { // first tile of block kb for this CTA; false: none
-        const int nt = tiles_of(kb);
-        int a = ((c - kb) % G + G) % G;          // (kb + tl) % G == c
-        if (a == 0) a = G;                       // tl >= 1 (tile 0 comes last)
-        if (a < nt) { tl = a; return true; }
-        if (kb % G == c && nt > 0) { tl = 0; return true; }
-        return false;
-    }
-    // slices of a tile in DESCENDING row order: sub = subs_of - 1 .. 0 (slice 0 holds the most recently solved rows)
-    __host__ __device__ bool next_slice(int& kb, int& tl, int& sub) const {
-        if (sub > 0) { sub--; return true; }
-        if (tl != 0) {
-            if (tl + G < tiles_of(kb)) { tl += G; sub = subs_of(kb, tl) - 1; return true; }
-            if (kb % G == c) { tl = 0; sub = subs_of(kb, 0) - 1; return true; }      // (tiles_of(kb) > tl >= 1)
+    __host__ __device__ bool first_item(int& p, int& kb, int& sub) const {
+        for (p = npairs() - 1; p >= 0; p--) {
+            kb = first_kb(p);
+            if (kb >= 0) { sub = subs_of(p) - 1; return true; }
+            if (p < nblk()) break;               // below the last pivot pair first_kb only shrinks
         }
-        while (--kb >= 0) if (first_in_block(kb, tl)) { sub = subs_of(kb, tl) - 1; return true; }
         return false;
+    }
+    __host__ __device__ bool next_slice(int& p, int& kb, int& sub) const {
+        if (sub > 0) { sub--; return true; }
+        if (kb - G >= 0) { kb -= G; sub = subs_of(p) - 1; return true; }
+        if (--p < 0) return false;
+        kb = first_kb(p);
+        if (kb < 0) return false;                // (p < nblk here: first_kb(p) only shrinks with p)
+        sub = subs_of(p) - 1;
+        return true;
     }
 };
 
@@ -1424,20 +1431,15 @@ int persist_schedule_check(int nr, int nc, int G) {
     }
     {   // ---- backward
         const BwdSched S0{nr, nc, 0, G};
-        std::vector<int> flag(nblk, 0), cnt(nblk, 0), toff(nblk + 1, 0);
-        for (int kb = 0; kb < nblk; kb++) toff[kb + 1] = toff[kb] + S0.tiles_of(kb);
-        std::vector<int> done(toff[nblk], 0);
-        struct St { int kb, tl, sub, dkb, acq; bool have, started; };
+        const int np = S0.npairs();
+        std::vector<int> flag(nblk, 0), applied((size_t)nblk * np, 0), last_p(nblk, np);
+        struct St { int p, kb, sub; bool have, started; };
         std::vector<St> st(G);
-        auto pivots_ready = [&](int first, int end) {       // every pivot row in [first, end) belongs to a solved block
-            for (int r = first; r < std::min(end, nc); r++) if (!flag[r / NB]) return false;
-            return true;
-        };
         auto solve = [&](int kb, int c) -> int {
             if (flag[kb]) return 20;
             if (kb % G != c) return 21;
-            for (int j = kb + 1; j < nblk; j++) if (!flag[j]) return 22;
-            for (int tl = 0; tl < S0.tiles_of(kb); tl++) if (done[toff[kb] + tl] != 1) return 23;
+            for (int p = S0.pmin_of(kb); p < np; p++) if (applied[(size_t)kb * np + p] != 1) return 22;
+            for (int j = kb + 1; j < nblk; j++) if (!flag[j]) return 23;
             flag[kb] = 1;
             return 0;
         };
@@ -1447,65 +1449,40 @@ int persist_schedule_check(int nr, int nc, int G) {
             for (int c = 0; c < G; c++) {
                 const BwdSched S{nr, nc, c, G};
                 St& q = st[c];
-                // owned blocks without a tile: solved as soon as the block after them is (owner_blocks_down_to)
-                auto owner_blocks = [&](int kstop, bool& blocked) -> int {
-                    while (q.dkb > kstop && q.dkb >= 0 && S.tiles_of(q.dkb) == 0) {
-                        if (q.dkb + 1 < nblk && !flag[q.dkb + 1]) { blocked = true; return 0; }
-                        int e = solve(q.dkb, c); if (e) return e;
-                        q.dkb -= G; progress = true;
-                    }
-                    return 0;
-                };
                 if (!q.started) {
                     q.started = true; progress = true;
-                    q.dkb = nblk - 1 - (((nblk - 1 - c) % G) + G) % G;
-                    q.acq = nblk; q.kb = nblk; q.tl = 0; q.sub = 0; q.have = false;
-                    while (--q.kb >= 0) if (S.first_in_block(q.kb, q.tl)) { q.have = true; q.sub = S.subs_of(q.kb, q.tl) - 1; break; }
-                }
-                bool blocked = false;
-                if (!q.have) {                   // (also the first call of a CTA whose list is empty)
-                    int e = owner_blocks(-1, blocked); if (e) return e;
-                    if (blocked || (q.dkb >= 0 && S.tiles_of(q.dkb) == 0)) all_done = false;
-                    continue;
-                }
-                {   // blocks above the current item that the kernel solves before it (entry / end of the previous iteration)
-                    int e = owner_blocks(q.kb, blocked); if (e) return e;
-                    if (blocked) { all_done = false; continue; }
+                    q.have = S.first_item(q.p, q.kb, q.sub);
+                    // a block with no row below it at all (last block of a front with nr == nc, nc % 128 == 0): solved up front
+                    const int last = nblk - 1;
+                    if (last % G == c && S.pmin_of(last) >= np) { int e = solve(last, c); if (e) return e; }
                 }
                 while (q.have) {
-                    const int rb = S.rb_of(q.kb), nt = S.tiles_of(q.kb), r0 = (rb & ~1) + q.tl * SOLVE_BT;
-                    if (q.tl >= nt || (q.tl != 0 && (q.kb + q.tl) % G != c) || (q.tl == 0 && q.kb % G != c)) return 24;
-                    if (q.sub == S.subs_of(q.kb, 0) - 1 && q.tl == 0 && nt > 1 && cnt[q.kb] < nt - 1) break;     // presum: persist_wait(cnt + kb)
-                    const int first = std::max(r0 + q.sub * 64, rb);
-                    if (first < nc && first / NB < q.acq) {
-                        if (!flag[first / NB]) break;                                       // persist_wait(flag + bneed)
-                        q.acq = first / NB;
+                    if (q.p < nblk && q.p > q.kb && !flag[q.p]) break;             // persist_wait(flag + p)
+                    if (q.kb % G != c || q.kb < 0 || q.kb >= nblk || q.p < S.pmin_of(q.kb) || q.p >= np) return 24;
+                    if (q.sub < 0 || q.sub >= S.subs_of(q.p)) return 25;
+                    {   // every pivot row of the pair that the item reads (r >= rb of its block) is solved
+                        const int lo = std::max(q.p * NB, S.rb_of(q.kb)), hi = std::min(q.p * NB + NB, nc);
+                        if (lo < hi && !flag[q.p]) return 32;
                     }
-                    if (!pivots_ready(first, r0 + q.sub * 64 + 64)) return 25;              // reads a row that is not solved yet
-                    if (q.sub < 0 || q.sub >= S.subs_of(q.kb, q.tl)) return 31;
                     if (q.sub == 0) {
-                        if (done[toff[q.kb] + q.tl]++) return 26;
-                        if (q.tl != 0) cnt[q.kb]++;
-                        else { int e = solve(q.kb, c); if (e) return e; q.dkb = q.kb - G; }
+                        if (applied[(size_t)q.kb * np + q.p]++) return 26;
+                        if (last_p[q.kb] != q.p + 1) return 27;      // pairs of a block from the last one down, none skipped
+                        last_p[q.kb] = q.p;
+                        if (q.p == S.pmin_of(q.kb)) { int e = solve(q.kb, c); if (e) return e; }
                     }
-                    int nkb = q.kb, ntl = q.tl, nsub = q.sub;
-                    const bool hnext = S.next_slice(nkb, ntl, nsub);
-                    if (q.sub > 0 && !(hnext && nkb == q.kb && ntl == q.tl && nsub == q.sub - 1)) return 27;
+                    int np_ = q.p, nkb = q.kb, nsub = q.sub;
+                    const bool hnext = S.next_slice(np_, nkb, nsub);
+                    if (q.sub > 0 && !(hnext && np_ == q.p && nkb == q.kb && nsub == q.sub - 1)) return 28;
+                    q.have = hnext; q.p = np_; q.kb = nkb; q.sub = nsub;
                     progress = true;
-                    const int prev_kb = q.kb;
-                    q.have = hnext; q.kb = nkb; q.tl = ntl; q.sub = nsub;
-                    if (!hnext || nkb != prev_kb) {
-                        int e = owner_blocks(hnext ? nkb : -1, blocked); if (e) return e;
-                        if (blocked) break;
-                    }
                 }
-                if (q.have || blocked || (q.dkb >= 0 && S.tiles_of(q.dkb) == 0)) all_done = false;
+                if (q.have) all_done = false;
             }
         }
-        if (!all_done) return 28;                // deadlock
+        if (!all_done) return 29;                // deadlock
         for (int kb = 0; kb < nblk; kb++) {
-            if (!flag[kb]) return 29;
-            for (int tl = 0; tl < S0.tiles_of(kb); tl++) if (done[toff[kb] + tl] != 1) return 30;
+            if (!flag[kb]) return 30;
+            for (int p = 0; p < np; p++) if (applied[(size_t)kb * np + p] != (p >= S0.pmin_of(kb) ? 1 : 0)) return 31;
         }
     }
     return 0;
@@ -1519,8 +1496,9 @@ __device__ __forceinline__ void persist_wait_cta(const int* p, int need, int* er
 }
 // forward sweep of the large fronts of one level.  Rows are dealt in PAIRS of 64-row tiles (128 rows: pair p -> CTA p % G of
 // the front); the CTA that owns pair kb solves diagonal block kb right after it has applied block kb - 1 to that pair.
-__global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ PersistGroups pg, const double* __restrict__ L,
-                                                        const double* __restrict__ Minv, double* T, double* X, int* flags, int* err) {
+__global__ void __launch_bounds__(256, 1) k_fwd_persist(const PersistLevel pl, const double* __restrict__ L,
+                                                        const double* __restrict__ Minv, double* T, double* X, int* flags, int* err,
+                                                        long long* dbg) {
     extern __shared__ double sm[];
     double* ring = sm;                     // 2 x [128 columns][64 rows]
     double* Ls = ring + 2 * NB * 64;
@@ -1528,11 +1506,11 @@ __global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ 
     double* ts = Ms + MINV_HALF;
     double* xs = ts + NB;
     double* red = xs + 2 * NB;             // [4][64]
-    int g = 0;
-    while (g + 1 < pg.ng && pg.fr[g + 1].cta0 <= (int)blockIdx.x) g++;
-    const FrontS f = pg.fr[g].f;
-    const int c = blockIdx.x - pg.fr[g].cta0, G = pg.fr[g].ncta;
-    int* flag = flags + pg.fr[g].sync0;
+    for (int fi = pl.shared ? pl.cmap[blockIdx.x] : (int)blockIdx.x; fi < pl.nf; fi += pl.shared ? pl.nf : (int)gridDim.x) {
+    const PersistFront pfr = pl.fr[fi];
+    const FrontS f = pfr.f;
+    const int c = pl.shared ? (int)blockIdx.x - pfr.cta0 : 0, G = pfr.ncta;
+    int* flag = flags + pfr.sync0;
     double* t = T + f.rowptr;
     double* x = X + f.col0;
     const double* P = L + f.loff;
@@ -1553,9 +1531,11 @@ __global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ 
             __syncthreads();
         }
         fwd_diag_core(Ls, Ms, ts, w, tid);
+        if (dbg && tid == 0) dbg[c * 8 + 4] = clock64();
         if (tid < w) { __stcg(t + k0 + tid, ts[tid]); __stcg(x + k0 + tid, ts[tid]); }
         __syncthreads();
         if (tid == 0) { __threadfence(); st_release(flag + kb, 1); }
+        if (dbg && tid == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[c * 8 + 6] = gt; dbg[c * 8 + 5] = clock64(); }
         if (kb + G < nblk) {
             const int k1 = (kb + G) * NB;
             stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)(kb + G) * MINV_BLK, Ls, Ms, tid);
@@ -1585,7 +1565,9 @@ __global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ 
         cp_async_commit();
         const int k0 = kb * NB, w = min(NB, f.nc - k0), rb = k0 + w;
         if (kb != xs_kb) {                       // x of block kb: published by the owner of pair kb
+            if (dbg && tid == 0 && kb + 1 == c) dbg[c * 8 + 7] = clock64();
             persist_wait_cta(flag + kb, 1, err);
+            if (dbg && tid == 0 && kb + 1 == c) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[c * 8 + 0] = gt; dbg[c * 8 + 1] = clock64(); }
             if (tid < NB) xs[tid] = (tid < w) ? __ldcg(t + k0 + tid) : 0.0;
             xs_kb = kb;
         }
@@ -1594,6 +1576,7 @@ __global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ 
         const double tprev = wr ? __ldcg(t + r0 + tid) : 0.0;
         cp_async_wait<1>();
         __syncthreads();
+        if (dbg && tid == 0 && kb + 1 == c && !(m & 1)) dbg[c * 8 + 2] = clock64();
         {
             const bool rowok = r0 + rr < f.nr && r0 + rr >= rb;
             const int wq = min(32, w - cq * 32);
@@ -1624,76 +1607,47 @@ __global__ void __launch_bounds__(256, 1) k_fwd_persist(const __grid_constant__ 
         }
         if (chain && pair_done) {
             __syncthreads();
+            if (dbg && tid == 0) dbg[c * 8 + 3] = clock64();
             diag(kb + 1, true);
         }
         have = hnext; kb = nkb; m = nm; it++;
     }
     cp_async_wait<0>();
+    __syncthreads();                             // (several fronts per CTA: shared memory is reused by the next one)
+    }
 }
 
-// backward sweep of the large fronts of one level.  Block kb (descending) is solved by CTA kb % G of the front; the partial
-// sums of its 192-row tiles tl >= 1 are computed one step ahead by the CTAs (kb + tl) % G (their rows were solved two steps
-// earlier), written to `part` and counted in cnt[kb]; the owner pre-sums them, computes tile 0 -- the only piece that needs
-// the block just solved -- and solves.
-__global__ void __launch_bounds__(256, 1) k_bwd_persist(const __grid_constant__ PersistGroups pg, const double* __restrict__ L,
-                                                        const double* __restrict__ Minv, double* T, double* X, double* part, int* flags,
-                                                        int* cnts, int* err) {
+// backward sweep of the large fronts of one level, the mirror image of the forward one: the CTA that owns column block kb keeps
+// z_kb = t_kb - sum over the pairs p (from the last one down) of L[pair p, block kb]^T x[pair p] in place in T, applies pair
+// kb + 1 the moment block kb + 1 is published, and solves L11^T x = z at once.  No partial sums travel between CTAs.
+__global__ void __launch_bounds__(256, 1) k_bwd_persist(const PersistLevel pl, const double* __restrict__ L,
+                                                        const double* __restrict__ Minv, double* T, double* X, int* flags,
+                                                        int* err, long long* dbg) {
     extern __shared__ double sm[];
     double* ring = sm;
     double* Ls = ring + 2 * NB * 64;
     double* Ms = Ls + DIAG_PACK;
     double* zs = Ms + MINV_HALF;
-    double* zh = zs + NB;
-    double* p0s = zh + NB;
-    double* red = p0s + NB;                // [8][32]
-    int g = 0;
-    while (g + 1 < pg.ng && pg.fr[g + 1].cta0 <= (int)blockIdx.x) g++;
-    const FrontS f = pg.fr[g].f;
-    const int c = blockIdx.x - pg.fr[g].cta0, G = pg.fr[g].ncta;
-    int* flag = flags + pg.fr[g].sync0;
-    int* cnt = cnts + pg.fr[g].sync0;
+    double* red = zs + NB;                 // [8][32]
+    for (int fi = pl.shared ? pl.cmap[blockIdx.x] : (int)blockIdx.x; fi < pl.nf; fi += pl.shared ? pl.nf : (int)gridDim.x) {
+    const PersistFront pfr = pl.fr[fi];
+    const FrontS f = pfr.f;
+    const int c = pl.shared ? (int)blockIdx.x - pfr.cta0 : 0, G = pfr.ncta;
+    int* flag = flags + pfr.sync0;
     double* t = T + f.rowptr;
     double* x = X + f.col0;
     const double* P = L + f.loff;
     const double* minv = Minv + f.ioff + MINV_HALF;
-    double* pp = part + pg.fr[g].poff * NB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rr = tid & 63, cq = tid >> 6;
     const int nblk = (f.nc + NB - 1) / NB;
     const BwdSched S{f.nr, f.nc, c, G};
-    auto rb_of = [&](int kb) { return S.rb_of(kb); };
-    auto tiles_of = [&](int kb) { return S.tiles_of(kb); };
-    auto subs_of = [&](int kb, int tl) { return S.subs_of(kb, tl); };
-    auto first_in_block = [&](int kb, int& tl) { return S.first_in_block(kb, tl); };
-    auto next_slice = [&](int& kb, int& tl, int& sub) { return S.next_slice(kb, tl, sub); };
-    auto issue = [&](int kb, int tl, int sub, int buf) {
+    auto issue = [&](int p, int kb, int sub, int buf) {
         const int k0 = kb * NB;
-        stage_rows64(P, f.ld, f.nr, k0, min(NB, f.nc - k0), (rb_of(kb) & ~1) + tl * SOLVE_BT + sub * 64, ring + buf * NB * 64, tid);
+        stage_rows64(P, f.ld, f.nr, k0, min(NB, f.nc - k0), p * NB + sub * 64, ring + buf * NB * 64, tid);
     };
-    // diagonal blocks this CTA solves: kb % G == c, descending
-    int dnext = nblk - 1 - (((nblk - 1 - c) % G) + G) % G;
-    if (dnext >= 0) {
-        const int k1 = dnext * NB;
-        stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)dnext * MINV_BLK, Ls, Ms, tid);
-    }
-    cp_async_commit();
-    int kb = nblk, tl = 0, sub = 0;
-    bool have = false;
-    while (--kb >= 0) if (first_in_block(kb, tl)) { have = true; sub = subs_of(kb, tl) - 1; break; }
-    if (have) issue(kb, tl, sub, 0);
-    cp_async_commit();
-    int acq = nblk;                              // blocks >= acq are known to be published
-    int it = 0;
-    double p[32];
-    double zpre = 0.0;                           // owner: sum of the partials of its chain (tiles 2, 4, .. or 1, 3, ..)
-    double tk0 = 0.0;                            // owner: t of the block it is about to solve (thread q < 128), fetched ahead
-    // the owner's part of a block that has NO tile at all (nothing below it: the last block of a root front)
-    auto solve_block = [&](int kb_, bool have_p0) {
+    // zs holds z of block kb_ (zero past w): solve, publish, stage the diagonal block of the next owned block
+    auto solve_block = [&](int kb_) {
         const int k0 = kb_ * NB, w = min(NB, f.nc - k0);
-        const int q = tid & (NB - 1), h = tid >> 7;
-        if (h == 1) zh[q] = zpre;
-        __syncthreads();
-        if (h == 0) zs[q] = (q < w) ? (have_p0 ? tk0 : __ldcg(t + k0 + q)) - ((have_p0 ? p0s[q] : 0.0) + (zpre + zh[q])) : 0.0;
-        __syncthreads();
         bwd_diag_core(Ls, Ms, zs, w, tid);
         if (tid < w) { __stcg(t + k0 + tid, zs[tid]); __stcg(x + k0 + tid, zs[tid]); }
         __syncthreads();
@@ -1704,63 +1658,47 @@ __global__ void __launch_bounds__(256, 1) k_bwd_persist(const __grid_constant__ 
         }
         cp_async_commit();
     };
-    // pre-sum of the other CTAs' partials of block kb_ (all counted in cnt[kb_]); the chain of this thread: h = 0 -> tiles 2, 4, ..
-    auto presum = [&](int kb_, long long pbase) {
-        const int nt = tiles_of(kb_);
-        const int q = tid & (NB - 1), h = tid >> 7;
-        zpre = 0.0;
-        if (nt > 1) {
-            persist_wait_cta(cnt + kb_, nt - 1, err);
-            const double* ps = pp + pbase * NB + q;
-            int tl_ = h == 0 ? 2 : 1;
-            for (; tl_ + 6 < nt; tl_ += 8) {     // four loads in flight, added in order
-                const double v0 = __ldcg(ps + (long long)tl_ * NB), v1 = __ldcg(ps + (long long)(tl_ + 2) * NB),
-                             v2 = __ldcg(ps + (long long)(tl_ + 4) * NB), v3 = __ldcg(ps + (long long)(tl_ + 6) * NB);
-                zpre += v0; zpre += v1; zpre += v2; zpre += v3;
-            }
-            for (; tl_ < nt; tl_ += 2) zpre += __ldcg(ps + (long long)tl_ * NB);
-        }
-    };
-    // first partial tile of every block: pbase(nblk - 1) = 0, pbase(kb) = pbase(kb + 1) + tiles(kb + 1)
-    long long pb = 0;
-    int pb_kb = nblk - 1;
-    auto pbase_of = [&](int kb_) { while (pb_kb > kb_) { pb += tiles_of(pb_kb); pb_kb--; } return pb; };
-    int dkb = dnext;                             // next block this CTA owns
-    // blocks owned by this CTA that come BEFORE its first item and have no tile of their own to trigger the solve
-    auto owner_blocks_down_to = [&](int kstop) { // solve owned blocks > kstop that have no tiles (no item will trigger them)
-        while (dkb > kstop && dkb >= 0) {
-            if (tiles_of(dkb) == 0) {
-                if (dkb + 1 < nblk && dkb + 1 < acq) { persist_wait_cta(flag + dkb + 1, 1, err); acq = dkb + 1; }
-                cp_async_wait<0>();
-                __syncthreads();
-                zpre = 0.0;
-                solve_block(dkb, false);
-                dkb -= G;
-            } else break;
-        }
-    };
-    owner_blocks_down_to(have ? kb : -1);
+    // diagonal blocks this CTA solves: kb % G == c, descending
+    const int dfirst = nblk - 1 - (((nblk - 1 - c) % G) + G) % G;
+    if (dfirst >= 0) {
+        const int k1 = dfirst * NB;
+        stage_diag_issue(P, f.ld, k1, min(NB, f.nc - k1), minv + (long long)dfirst * MINV_BLK, Ls, Ms, tid);
+    }
+    cp_async_commit();
+    int p = 0, kb = 0, sub = 0;
+    bool have = S.first_item(p, kb, sub);
+    if (have) issue(p, kb, sub, 0);
+    cp_async_commit();
+    if (dfirst == nblk - 1 && S.pmin_of(nblk - 1) >= S.npairs()) {      // nothing below the last block: z = t
+        const int k0 = dfirst * NB, w = min(NB, f.nc - k0);
+        if (tid < NB) zs[tid] = (tid < w) ? __ldcg(t + k0 + tid) : 0.0;
+        cp_async_wait<1>();
+        __syncthreads();
+        solve_block(dfirst);
+    }
+    int acq = nblk;                              // blocks >= acq are known to be published
+    int it = 0;
+    double pj[32];
+    double zprev = 0.0;
     while (have) {
-        int nkb = kb, ntl = tl, nsub = sub;
-        const bool hnext = next_slice(nkb, ntl, nsub);
-        if (hnext) issue(nkb, ntl, nsub, (it + 1) & 1);
+        int np = p, nkb = kb, nsub = sub;
+        const bool hnext = S.next_slice(np, nkb, nsub);
+        if (hnext) issue(np, nkb, nsub, (it + 1) & 1);
         cp_async_commit();
         const int k0 = kb * NB, w = min(NB, f.nc - k0), rb = k0 + w;
-        const int r0 = (rb & ~1) + tl * SOLVE_BT;
-        if (sub + 1 == subs_of(kb, tl)) {        // first slice of a tile
+        const bool first_slice = sub + 1 == S.subs_of(p);
+        if (first_slice) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) p[j] = 0.0;
-            if (tl == 0) {                       // owner: everything but tile 0, before the wait for block kb + 1
-                presum(kb, pbase_of(kb));
-                tk0 = (tid < NB && tid < w) ? __ldcg(t + k0 + tid) : 0.0;
-            }
+            for (int j = 0; j < 32; j++) pj[j] = 0.0;
+            if (tid < NB) zprev = (tid < w) ? __ldcg(t + k0 + tid) : 0.0;      // (written by this thread when the pair before was applied)
         }
-        const int r = r0 + sub * 64 + rr;
-        {   // the rows of this slice: pivot rows of block r / 128 (published when flag is set) or rows below the pivots
-            const int first = max(r0 + sub * 64, rb);
-            const int bneed = first / NB;
-            if (first < f.nc && bneed < acq) { persist_wait_cta(flag + bneed, 1, err); acq = bneed; }
+        if (p < nblk && p > kb && p < acq) {     // the pivot rows of pair p at or below rb: block p (p == kb: only rows below the pivots)
+            if (dbg && tid == 0 && kb == p - 1) dbg[2048 + c * 16 + 0] = clock64();
+            persist_wait_cta(flag + p, 1, err);
+            acq = p;
+            if (dbg && tid == 0 && kb == p - 1) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[2048 + c * 16 + 8] = gt; dbg[2048 + c * 16 + 1] = clock64(); }
         }
+        const int r = p * NB + sub * 64 + rr;
         const double tv = (r < f.nr && r >= rb) ? __ldcg(t + r) : 0.0;
         cp_async_wait<1>();
         __syncthreads();
@@ -1769,37 +1707,40 @@ __global__ void __launch_bounds__(256, 1) k_bwd_persist(const __grid_constant__ 
             const double* sp = ring + (it & 1) * NB * 64 + cq * 32 * 64 + rr;
 #pragma unroll
             for (int j = 0; j < 32; j++)
-                if (j < wq) p[j] = fma(sp[j * 64], tv, p[j]);
+                if (j < wq) pj[j] = fma(sp[j * 64], tv, pj[j]);
         }
-        if (sub == 0) {                          // tile complete: column sums over the 64 x 3 rows
+        if (sub == 0) {                          // pair complete: column sums over its 128 rows
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const bool up = (lane & o) != 0;
 #pragma unroll
                 for (int j = 0; j < o; j++) {
-                    const double send = up ? p[j] : p[j + o];
-                    const double keep = up ? p[j + o] : p[j];
-                    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    const double send = up ? pj[j] : pj[j + o];
+                    const double keep = up ? pj[j + o] : pj[j];
+                    pj[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                 }
             }
-            red[warp * 32 + lane] = p[0];
+            red[warp * 32 + lane] = pj[0];
             __syncthreads();
-            if (tl != 0) {
-                double* dst = pp + (pbase_of(kb) + tl) * NB;
-                if (tid < NB) __stcg(dst + tid, red[(2 * (tid >> 5)) * 32 + (tid & 31)] + red[(2 * (tid >> 5) + 1) * 32 + (tid & 31)]);
-                __syncthreads();
-                if (tid == 0) { __threadfence(); atomicAdd(cnt + kb, 1); }
-            } else {
-                if (tid < NB) p0s[tid] = red[(2 * (tid >> 5)) * 32 + (tid & 31)] + red[(2 * (tid >> 5) + 1) * 32 + (tid & 31)];
-                // (solve_block's first barrier orders p0s before its readers)
-                solve_block(kb, true);
-                dkb = kb - G;
+            const bool last_pair = p == S.pmin_of(kb);       // every pair of block kb applied: solve it
+            if (tid < NB) {
+                const double z = zprev - (red[(2 * (tid >> 5)) * 32 + (tid & 31)] + red[(2 * (tid >> 5) + 1) * 32 + (tid & 31)]);
+                if (last_pair) zs[tid] = (tid < w) ? z : 0.0;
+                else if (tid < w) __stcg(t + k0 + tid, z);
             }
-        } else __syncthreads();                  // the ring buffer is free for the slice after the next
-        if (!hnext || nkb != kb) owner_blocks_down_to(hnext ? nkb : -1);
-        have = hnext; kb = nkb; tl = ntl; sub = nsub; it++;
+            if (last_pair) {
+                __syncthreads();
+                if (dbg && tid == 0) dbg[2048 + c * 16 + 2] = clock64();
+                solve_block(kb);
+                if (dbg && tid == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[2048 + c * 16 + 9] = gt; dbg[2048 + c * 16 + 3] = clock64(); }
+            }
+        }
+        __syncthreads();                         // ring buffer / red free for the slice after the next
+        have = hnext; p = np; kb = nkb; sub = nsub; it++;
     }
     cp_async_wait<0>();
+    __syncthreads();
+    }
 }
 
 __global__ void k_perm_gather(const double* __restrict__ B, long long ldB, const int* __restrict__ perm, int n,
@@ -1859,7 +1800,7 @@ struct LevelSched {
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
     Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
     int small_all_off = 0, small_all_cnt = 0;
-    int pgi = -1, pctas = 0;          // persistent sweeps (one right-hand side): index in CholDevice::pgroups, CTAs
+    int pgi = -1, pctas = 0;          // persistent sweeps (one right-hand side): index in CholDevice::plevels, CTAs
 };
 
 class CholDevice {
@@ -1886,12 +1827,14 @@ public:
     void drop_graphs() { for (auto& kv : solve_graphs) cudaGraphExecDestroy(kv.second); solve_graphs.clear(); }
     i64 solve_cols = 0;            // capacity (columns) of dT / dX
     int max_solve_ctas = 1;        // most CTAs of one backward-update launch (sizes the partial-sum buffer)
-    std::vector<PersistGroups> pgroups;   // persistent sweeps: by-value launch records of the levels with 1..PMAXG large fronts
+    std::vector<PersistLevel> plevels;    // persistent sweeps: launch records of the levels with 1 .. 2 x SMs large fronts
+    PersistFront* dpfront = nullptr;      // their front records and CTA -> front maps (device)
+    int* dpcmap = nullptr;
     int persist_mode = 3;          // bit 0: forward, bit 1: backward sweep by k_fwd_persist / k_bwd_persist (B200S_SOLVE_PERSIST)
     int persist_default = 3, persist_hw = 3;      // B200S_SOLVE_PERSIST or 3; 0 when a persistent CTA does not fit an SM
-    int* dsync = nullptr;          // [3][nsync]: forward flags, backward flags, backward partial counters (zeroed per sweep pair)
+    int* dsync = nullptr;          // [2][nsync]: forward flags, backward flags (zeroed per sweep pair)
     int nsync = 0;
-    double* dppart = nullptr;      // partial sums of the persistent backward sweep, one 128-vector per (front, block, tile)
+    long long* persist_dbg = nullptr;   // B200S_PERSIST_DBG: phase clocks of the root front's forward chain (mapped host memory)
     int* herr = nullptr;           // mapped host word: a persistent kernel gave up a wait (schedule error instead of a hang)
     double* dpart = nullptr;
     double* dMinv = nullptr;       // inverted 32 x 32 diagonal sub-blocks of the large fronts (solve phase)
@@ -1918,7 +1861,7 @@ public:
         pool_free(dreach); pool_free(dsp_i); pool_free(dsp_x); pool_free(dsp_cnt); pool_free(dsp_oi); pool_free(dsp_ox); pool_free(dsp_meta);
         for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
-        pool_free(dsync); pool_free(dppart);
+        pool_free(dsync); pool_free(dpfront); pool_free(dpcmap);
         if (herr) cudaFreeHost(herr);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
@@ -2119,10 +2062,10 @@ int CholDevice::init() {
                 const int nblk = (f.nc + NB - 1) / NB;
                 if (kb >= nblk) continue;
                 const int w = std::min(NB, f.nc - kb * NB);
-                const int below = f.nr - ((kb * NB + w) & ~1);      // row tiles of the solve start at an even row
+                const int below = f.nr - ((kb * NB + w) & ~1);      // row tiles of the forward update start at an even row
                 fs.push_back(s);
                 cf.push_back((below + SOLVE_FT - 1) / SOLVE_FT);
-                cb2.push_back((below + SOLVE_BT - 1) / SOLVE_BT);
+                cb2.push_back(std::max(0, (f.nr + NB - 1) / NB - (kb * NB + w) / NB));      // backward: the 128-row pairs that hold rows >= rb
             }
             emit(LS.sfwd[kb], fs, cf);
             emit(LS.sbwd[kb], fs, cb2);
@@ -2214,45 +2157,56 @@ int CholDevice::init() {
         if (occ_f < 1 || occ_b < 1 || nsm < 1) persist_hw = 0;        // every CTA of a launch must be resident (they wait for each other)
         persist_default &= persist_hw;
         persist_mode = persist_default;
-        long long ptiles = 0;
+        // levels with more large fronts than this keep the launch-per-step kernels: their launches are wide (many fronts) and few
+        // (short fronts), which the level-wide kernels handle at memory speed, while 1-2 CTAs per front would serialise
+        // each front's steps (measured on 100^3: 32 -> 9.4 ms per solve, 296 -> 9.8 ms)
+        int maxf = 32;
+        if (const char* e = getenv("B200S_PERSIST_MAXF")) maxf = std::max(0, std::min(atoi(e), 2 * nsm));
+        std::vector<PersistFront> hpf;
+        std::vector<int> hcmap;
+        std::vector<std::pair<size_t, size_t>> offs;       // per persistent level: first record, first map entry
         for (int l = 0; l < P.nlevels && persist_hw; l++) {
             LevelSched& LS = levels[l];
-            if (LS.panel.empty() || LS.panel[0].ng < 1 || LS.panel[0].ng > PMAXG || LS.panel[0].ng > nsm) continue;
+            if (LS.panel.empty() || LS.panel[0].ng < 1 || LS.panel[0].ng > maxf) continue;
             const int ng = LS.panel[0].ng;
             const int* fr = sched.data() + LS.panel[0].goff;      // the large fronts of the level
-            PersistGroups G;
-            memset(&G, 0, sizeof(G));
-            G.ng = ng;
+            const bool shared = ng <= nsm;                        // else: one CTA per front, several fronts per CTA
             double area = 0;
             for (int i = 0; i < ng; i++) area += (double)hf[fr[i]].nr * hf[fr[i]].nc;
             int cta = 0;
+            offs.push_back({hpf.size(), hcmap.size()});
             for (int i = 0; i < ng; i++) {
                 const FrontD& d = hf[fr[i]];
                 const int npairs = (d.nr + NB - 1) / NB, nblk = (d.nc + NB - 1) / NB;
-                const int extra = (int)((double)(nsm - ng) * ((double)d.nr * d.nc / area));
-                PersistFront& pf = G.fr[i];
+                const int extra = shared ? (int)((double)(nsm - ng) * ((double)d.nr * d.nc / area)) : 0;
+                PersistFront pf;
+                memset(&pf, 0, sizeof(pf));
                 pf.f = FrontS{d.loff, d.rowptr, d.ioff, d.uoff, d.nc, d.nr, d.ld, d.col0, fr[i], 0};
                 pf.cta0 = cta;
                 pf.ncta = 1 + std::max(0, std::min(npairs - 1, extra));
                 pf.sync0 = nsync;
-                pf.poff = ptiles;
+                if (shared) for (int q = 0; q < pf.ncta; q++) hcmap.push_back(i);
                 cta += pf.ncta;
                 nsync += nblk;
-                for (int kb = 0; kb < nblk; kb++) {
-                    const int below = d.nr - (std::min(d.nc, (kb + 1) * NB) & ~1);
-                    if (below > 0) ptiles += (below + SOLVE_BT - 1) / SOLVE_BT;
-                }
+                hpf.push_back(pf);
             }
-            LS.pgi = (int)pgroups.size();
-            LS.pctas = cta;
-            pgroups.push_back(G);
+            PersistLevel pl;
+            pl.fr = nullptr; pl.cmap = nullptr; pl.nf = ng; pl.shared = shared ? 1 : 0;
+            LS.pgi = (int)plevels.size();
+            LS.pctas = shared ? cta : nsm;
+            plevels.push_back(pl);
         }
-        if (!pgroups.empty()) {
-            CUDA_TRY(pool_malloc((void**)&dsync, (size_t)3 * nsync * sizeof(int)));
-            CUDA_TRY(pool_malloc((void**)&dppart, std::max<size_t>((size_t)ptiles * NB, 1) * sizeof(double)));
+        if (!plevels.empty()) {
+            if ((rc = upload(&dpfront, hpf.data(), hpf.size()))) return rc;
+            if ((rc = upload(&dpcmap, hcmap.data(), hcmap.size()))) return rc;
+            for (size_t i = 0; i < plevels.size(); i++) { plevels[i].fr = dpfront + offs[i].first; plevels[i].cmap = dpcmap + offs[i].second; }
+        }
+        if (!plevels.empty()) {
+            CUDA_TRY(pool_malloc((void**)&dsync, (size_t)2 * nsync * sizeof(int)));
             CUDA_TRY(cudaHostAlloc((void**)&herr, sizeof(int), cudaHostAllocMapped));
             *herr = 0;
-            total_bytes += (size_t)3 * nsync * sizeof(int) + (size_t)ptiles * NB * sizeof(double);
+            if (getenv("B200S_PERSIST_DBG")) { CUDA_TRY(cudaHostAlloc((void**)&persist_dbg, 8192 * sizeof(long long), cudaHostAllocMapped)); memset(persist_dbg, 0, 8192 * sizeof(long long)); }
+            total_bytes += (size_t)2 * nsync * sizeof(int);
         }
     }
     {
@@ -2646,9 +2600,9 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         // (columns, directions) into a CUDA graph and replayed
         const bool reach = active_fronts && do_fwd;
         if (reach) CUDA_TRY(cudaMemsetAsync(dT, 0, (size_t)tstride * nc * sizeof(double), stream));
-        const bool pfwd = nc == 1 && (persist_mode & 1) && !pgroups.empty(), pbwd = nc == 1 && (persist_mode & 2) && !pgroups.empty();
+        const bool pfwd = nc == 1 && (persist_mode & 1) && !plevels.empty(), pbwd = nc == 1 && (persist_mode & 2) && !plevels.empty();
         auto sweeps = [&]() {
-            if ((pfwd && do_fwd) || (pbwd && do_bwd)) cudaMemsetAsync(dsync, 0, (size_t)3 * nsync * sizeof(int), stream);
+            if ((pfwd && do_fwd) || (pbwd && do_bwd)) cudaMemsetAsync(dsync, 0, (size_t)2 * nsync * sizeof(int), stream);
             if (do_fwd)
                 for (int l = 0; l < P.nlevels; l++) {
                     const LevelSched& LS = levels[l];
@@ -2660,7 +2614,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
                         if (pfwd && LS.pgi >= 0)
-                            k_fwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(pgroups[LS.pgi], dL, dMinv, dT, dX, dsync, herr);
+                            k_fwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(plevels[LS.pgi], dL, dMinv, dT, dX, dsync, herr, (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : nullptr);
                         else
                         for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
                             const Launch& la = LS.sfwd[kb];
@@ -2678,7 +2632,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
                         if (pbwd && LS.pgi >= 0)
-                            k_bwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(pgroups[LS.pgi], dL, dMinv, dT, dX, dppart, dsync + nsync, dsync + 2 * nsync, herr);
+                            k_bwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(plevels[LS.pgi], dL, dMinv, dT, dX, dsync + nsync, herr, (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : nullptr);
                         else
                         for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
                             const Launch& la = LS.sbwd[kb];
@@ -2721,6 +2675,27 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     cudaError_t se = cudaStreamSynchronize(stream);
     CUDA_TRY(le);
     CUDA_TRY(se);
+    if (persist_dbg) {
+        double seen_to_item = 0, items = 0, dg = 0, pub = 0, prop = 0, idle = 0; int cnt = 0;
+        for (int c = 2; c < 116; c++) {
+            const long long* d = persist_dbg + c * 8; const long long* dp = persist_dbg + (c - 1) * 8;
+            if (!d[0] || !dp[6]) continue;
+            prop += (double)(d[0] - dp[6]); seen_to_item += (double)(d[2] - d[1]); items += (double)(d[3] - d[2]); dg += (double)(d[4] - d[3]); pub += (double)(d[5] - d[4]);
+            idle += (double)(d[1] - d[7]); cnt++;
+        }
+        if (cnt) fprintf(stderr, "[persist dbg] steps %d: publish->seen %.0f ns | cycles: seen->item1 %.0f, items %.0f, diag %.0f, publish %.0f, waited %.0f\n", cnt, prop / cnt, seen_to_item / cnt, items / cnt, dg / cnt, pub / cnt, idle / cnt);
+        {
+            double a[4] = {0}; int n2 = 0;
+            for (int c = 2; c < 110; c++) {
+                const long long* d = persist_dbg + 2048 + c * 16; const long long* dn = persist_dbg + 2048 + (c + 1) * 16;
+                if (!d[8] || !dn[9]) continue;
+                a[0] += (double)(d[1] - d[0]); a[1] += (double)(d[2] - d[1]); a[2] += (double)(d[3] - d[2]); a[3] += (double)(d[8] - dn[9]); n2++;
+            }
+            if (n2) fprintf(stderr, "[persist dbg bwd] steps %d: cycles waited %.0f, seen->solve %.0f, solve+publish %.0f | publish->seen %.0f ns\n",
+                            n2, a[0] / n2, a[1] / n2, a[2] / n2, a[3] / n2);
+        }
+        memset(persist_dbg, 0, 8192 * sizeof(long long));
+    }
     if (herr && *herr) {
         *herr = 0;
         set_last_error("persistent solve sweep: a CTA gave up waiting for another one (schedule error); set B200S_SOLVE_PERSIST=0");
