@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <vector>
+#include <mutex>
 
 namespace b200s {
 
@@ -915,10 +916,10 @@ __global__ void __launch_bounds__(128) k_diag_inverse(const int* __restrict__ bl
     for (int c = 0; c < SB; c++) { out[c * SB + lane] = D[s][lane][c]; out[MINV_HALF + c * SB + lane] = D[s][c][lane]; }
 }
 
-// forward: t = [x(cols); 0] + children's update vectors.  One CTA per 2048-row chunk of a front: a child's relative
+// forward: t = [x(cols); 0] + children's update vectors.  One CTA per GATHER_ROWS-row chunk of a front: a child's relative
 // indices ascend, so the entries that fall into the chunk are a contiguous run found by binary search; children are
 // applied one after the other (deterministic sums).
-constexpr int GATHER_ROWS = 2048;
+constexpr int GATHER_ROWS = 512;       // (2048: the top levels ran 8-40 CTAs of 8 dependent rounds per child, ~30 us per launch)
 __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list, const int* __restrict__ cprefix, int nfronts,
                                                     const FrontD* __restrict__ F,
                                                     const int* __restrict__ child_idx, const int* __restrict__ rel,
@@ -1862,7 +1863,6 @@ public:
         for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
         pool_free(dsync); pool_free(dpfront); pool_free(dpcmap);
-        if (herr) cudaFreeHost(herr);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -2203,8 +2203,18 @@ int CholDevice::init() {
         }
         if (!plevels.empty()) {
             CUDA_TRY(pool_malloc((void**)&dsync, (size_t)2 * nsync * sizeof(int)));
-            CUDA_TRY(cudaHostAlloc((void**)&herr, sizeof(int), cudaHostAllocMapped));
-            *herr = 0;
+            // one mapped error word per process (a pinned allocation per factor object costs milliseconds, which the small
+            // configurations -- a new KKT object per LP -- would pay every time); a set word is a schedule bug, whoever sees it
+            {
+                static std::mutex mu;
+                static int* g_err = nullptr;
+                std::lock_guard<std::mutex> lk(mu);
+                if (!g_err) {
+                    CUDA_TRY(cudaHostAlloc((void**)&g_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+                    *g_err = 0;
+                }
+                herr = g_err;
+            }
             if (getenv("B200S_PERSIST_DBG")) { CUDA_TRY(cudaHostAlloc((void**)&persist_dbg, 8192 * sizeof(long long), cudaHostAllocMapped)); memset(persist_dbg, 0, 8192 * sizeof(long long)); }
             total_bytes += (size_t)2 * nsync * sizeof(int);
         }
