@@ -1140,24 +1140,16 @@ __global__ void __launch_bounds__(256) k_fwd_upd(const __grid_constant__ SolveGr
 // tile: the same absolute pairs as the forward sweep) of L[r, k0+q] * t[r].  Two 64-row slices, one shared-memory buffer each
 // (128 KB in flight); thread = (row, column quarter) accumulates slice 1 then slice 0; the 32 per-lane column sums of a warp are
 // combined by a halving butterfly.  CG right-hand sides share the staged tile (blockIdx.y = group of CG columns).
+// column sums of one pair: red[c][2 cq .. 2 cq + 1][lane] hold, after the closing barrier, the two half sums of column
+// cq * 32 + lane of right-hand side c (added by the callers)
 template <int CG>
-__global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
-                                                 int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
-                                                 const double* __restrict__ T, long long tstride, double* __restrict__ part,
-                                                 long long pstride, int ncols, const unsigned char* __restrict__ owned = nullptr) {
-    extern __shared__ double sm[];         // 2 buffers of [128 columns][64 rows]
-    __shared__ double red[CG][8][32];
-    int tile;
-    const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
-    const FrontS f = load_front(sg, gfront, F, g);
-    if (owned && !owned[f.id]) return;
-    const int c0 = blockIdx.y * CG, cn = min(CG, ncols - c0);
-    const double* t = T + c0 * tstride + f.rowptr;
+__device__ __forceinline__ void bwd_pair_sums(const FrontS& f, int kb, int r0, const double* __restrict__ L, const double* __restrict__ t,
+                                              long long tstride, int cn, double* sm, double (&red)[CG][8][32]) {
     const double* P = L + f.loff;
     const int k0 = kb * NB, w = min(NB, f.nc - k0), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rr = tid & 63, cq = tid >> 6;
     const int wq = min(32, w - cq * 32);
-    const int rb = k0 + w, r0 = (rb / NB + tile) * SOLVE_BT;
+    const int rb = k0 + w;
     constexpr int NSUB = SOLVE_BT / 64;
     double p[CG][32];
 #pragma unroll
@@ -1211,6 +1203,21 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGr
         red[c][warp][lane] = p[c][0];
     }
     __syncthreads();
+}
+template <int CG>
+__global__ void __launch_bounds__(256) k_bwd_upd(const __grid_constant__ SolveGroups sg, const int* __restrict__ gfront, const int* __restrict__ gprefix, int ngroups,
+                                                 int kb, const FrontD* __restrict__ F, const double* __restrict__ L,
+                                                 const double* __restrict__ T, long long tstride, double* __restrict__ part,
+                                                 long long pstride, int ncols, const unsigned char* __restrict__ owned = nullptr) {
+    extern __shared__ double sm[];         // 2 buffers of [128 columns][64 rows]
+    __shared__ double red[CG][8][32];
+    int tile;
+    const int g = locate_group(sg, gprefix, ngroups, blockIdx.x, tile);
+    const FrontS f = load_front(sg, gfront, F, g);
+    if (owned && !owned[f.id]) return;
+    const int c0 = blockIdx.y * CG, cn = min(CG, ncols - c0), tid = threadIdx.x;
+    const int rb = min(f.nc, (kb + 1) * NB);
+    bwd_pair_sums<CG>(f, kb, (rb / NB + tile) * SOLVE_BT, L, T + c0 * tstride + f.rowptr, tstride, cn, sm, red);
     for (int i = tid; i < cn * NB; i += 256) {
         const int c = i / NB, q = i - c * NB;
         part[(c0 + c) * pstride + (long long)blockIdx.x * NB + q] = red[c][2 * (q >> 5)][q & 31] + red[c][2 * (q >> 5) + 1][q & 31];
@@ -1280,7 +1287,7 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const __grid_constant__ SolveG
 // memory speed underneath it.  Arithmetic and summation order are exactly those of k_fwd_diag / k_fwd_upd / k_bwd_upd /
 // k_bwd_diag (same device functions, same thread mapping): the results are bit-identical to the launch-per-step path, which
 // remains for several right-hand sides and for the ownership-masked distributed solves.
-struct PersistFront { FrontS f; int cta0, ncta, sync0, pad_; };      // first CTA, CTAs, first flag
+struct PersistFront { FrontS f; int cta0, ncta, sync0, rect0; };     // first CTA, CTAs, first flag, first tile of the rectangle pre-pass
 // A level's launch: `nf` records in global memory (a persistent kernel starts once per level: one dependent load is nothing).
 // nf <= CTAs: front i runs on the CTAs cta0 .. cta0 + ncta - 1 (`cmap` gives the front of every CTA); more fronts than SMs:
 // every front runs on ONE CTA (ncta == 1), CTA b takes the fronts b, b + gridDim.x, ...
@@ -1339,10 +1346,13 @@ struct FwdSched {
 // pairs are met from the last one down -- the rows below the pivots first, then pair p as soon as block p is solved -- and pair
 // p is applied to every owned block kb whose rows below the pivots reach into it (pmin(kb) = rb(kb) / 128 <= p), the highest
 // block first: kb = p - 1 is the one the chain waits for.  Item = (pair p, block kb, 64-row slice sub), slice 1 before 0.
+// rect != 0: the pairs that hold only rows below the pivots (p >= nblk) were summed by the level-wide pre-pass (k_bwd_rect)
+// and are not items: pend() bounds the pairs of the work list.
 struct BwdSched {
-    int nr, nc, c, G;
+    int nr, nc, c, G, rect;
     __host__ __device__ int nblk() const { return (nc + NB - 1) / NB; }
     __host__ __device__ int npairs() const { return (nr + NB - 1) / NB; }
+    __host__ __device__ int pend() const { return rect ? nblk() : npairs(); }
     __host__ __device__ int rb_of(int kb) const { return nc < (kb + 1) * NB ? nc : (kb + 1) * NB; }
     __host__ __device__ int pmin_of(int kb) const { return rb_of(kb) / NB; }
     __host__ __device__ int subs_of(int p) const { return p * NB + 64 < nr ? 2 : 1; }       // 64-row slices of pair p inside the front
@@ -1354,7 +1364,7 @@ struct BwdSched {
         return kmax - (kmax - c) % G;
     }
     __host__ __device__ bool first_item(int& p, int& kb, int& sub) const {
-        for (p = npairs() - 1; p >= 0; p--) {
+        for (p = pend() - 1; p >= 0; p--) {
             kb = first_kb(p);
             if (kb >= 0) { sub = subs_of(p) - 1; return true; }
             if (p < nblk()) break;               // below the last pivot pair first_kb only shrinks
@@ -1430,9 +1440,9 @@ int persist_schedule_check(int nr, int nc, int G) {
                 if (applied[(size_t)kb * ntile + m] != (m * SOLVE_FT + SOLVE_FT - 1 >= rb ? 1 : 0)) return 18;
         }
     }
-    {   // ---- backward
-        const BwdSched S0{nr, nc, 0, G};
-        const int np = S0.npairs();
+    for (int rect = 0; rect < 2; rect++) {   // ---- backward, without / with the rectangle pre-pass
+        const BwdSched S0{nr, nc, 0, G, rect};
+        const int np = S0.pend();
         std::vector<int> flag(nblk, 0), applied((size_t)nblk * np, 0), last_p(nblk, np);
         struct St { int p, kb, sub; bool have, started; };
         std::vector<St> st(G);
@@ -1448,7 +1458,7 @@ int persist_schedule_check(int nr, int nc, int G) {
         while (progress && !all_done) {
             progress = false; all_done = true;
             for (int c = 0; c < G; c++) {
-                const BwdSched S{nr, nc, c, G};
+                const BwdSched S{nr, nc, c, G, rect};
                 St& q = st[c];
                 if (!q.started) {
                     q.started = true; progress = true;
@@ -1618,12 +1628,31 @@ __global__ void __launch_bounds__(256, 1) k_fwd_persist(const PersistLevel pl, c
     }
 }
 
+// Rectangle pre-pass of the backward sweep: for every front of the level, every column block kb and every pair p that holds
+// only rows below the pivots (p >= nblk: their x is known before the sweep starts), the column sums of L[pair p, block kb]^T x
+// -- the tile of k_bwd_upd, same code -- into rect[(rect0 + kb * nR + p - nblk) * 128 ..].  One launch at memory speed over
+// all (front, block, pair) instead of the block owners streaming their rectangles one 64 KB slice at a time.
+__global__ void __launch_bounds__(256) k_bwd_rect(const PersistLevel pl, const double* __restrict__ L, const double* __restrict__ T,
+                                                  double* __restrict__ rect) {
+    extern __shared__ double sm[];
+    __shared__ double red[1][8][32];
+    int lo = 0, hi = pl.nf - 1;                  // last front with rect0 <= blockIdx.x
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pl.fr[mid].rect0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+    const PersistFront pfr = pl.fr[lo];
+    const FrontS f = pfr.f;
+    const int nblk = (f.nc + NB - 1) / NB, nR = (f.nr + NB - 1) / NB - nblk;
+    const int idx = blockIdx.x - pfr.rect0, kb = idx / nR, p = nblk + idx - kb * nR;
+    bwd_pair_sums<1>(f, kb, p * SOLVE_BT, L, T + f.rowptr, 0, 1, sm, red);
+    const int tid = threadIdx.x;
+    if (tid < NB) rect[(long long)blockIdx.x * NB + tid] = red[0][2 * (tid >> 5)][tid & 31] + red[0][2 * (tid >> 5) + 1][tid & 31];
+}
+
 // backward sweep of the large fronts of one level, the mirror image of the forward one: the CTA that owns column block kb keeps
 // z_kb = t_kb - sum over the pairs p (from the last one down) of L[pair p, block kb]^T x[pair p] in place in T, applies pair
 // kb + 1 the moment block kb + 1 is published, and solves L11^T x = z at once.  No partial sums travel between CTAs.
 __global__ void __launch_bounds__(256, 1) k_bwd_persist(const PersistLevel pl, const double* __restrict__ L,
                                                         const double* __restrict__ Minv, double* T, double* X, int* flags,
-                                                        int* err, long long* dbg) {
+                                                        const double* __restrict__ rect, int* err, long long* dbg) {
     extern __shared__ double sm[];
     double* ring = sm;
     double* Ls = ring + 2 * NB * 64;
@@ -1641,7 +1670,7 @@ __global__ void __launch_bounds__(256, 1) k_bwd_persist(const PersistLevel pl, c
     const double* minv = Minv + f.ioff + MINV_HALF;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rr = tid & 63, cq = tid >> 6;
     const int nblk = (f.nc + NB - 1) / NB;
-    const BwdSched S{f.nr, f.nc, c, G};
+    const BwdSched S{f.nr, f.nc, c, G, rect != nullptr};
     auto issue = [&](int p, int kb, int sub, int buf) {
         const int k0 = kb * NB;
         stage_rows64(P, f.ld, f.nr, k0, min(NB, f.nc - k0), p * NB + sub * 64, ring + buf * NB * 64, tid);
@@ -1670,7 +1699,30 @@ __global__ void __launch_bounds__(256, 1) k_bwd_persist(const PersistLevel pl, c
     bool have = S.first_item(p, kb, sub);
     if (have) issue(p, kb, sub, 0);
     cp_async_commit();
-    if (dfirst == nblk - 1 && S.pmin_of(nblk - 1) >= S.npairs()) {      // nothing below the last block: z = t
+    if (rect) {
+        // the rows below the pivots, summed by k_bwd_rect: z_kb = t_kb - R[last pair] - ... - R[nblk] for every owned block, the
+        // order of the launch-per-step kernels (sixteen loads in flight, subtracted one after the other)
+        const int nR = S.npairs() - nblk;
+        if (nR > 0 && tid < NB)
+            for (int kq = dfirst; kq >= 0; kq -= G) {
+                const int k0 = kq * NB, w = min(NB, f.nc - k0);
+                if (tid >= w) continue;
+                const double* rp = rect + ((long long)pfr.rect0 + (long long)kq * nR) * NB + tid;
+                double z = __ldcg(t + k0 + tid);
+                int q = nR - 1;
+                for (; q >= 15; q -= 16) {
+                    double v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) v[e] = __ldg(rp + (long long)(q - e) * NB);
+#pragma unroll
+                    for (int e = 0; e < 16; e++) z -= v[e];
+                }
+                for (; q >= 0; q--) z -= __ldg(rp + (long long)q * NB);
+                __stcg(t + k0 + tid, z);
+            }
+        __syncthreads();
+    }
+    if (dfirst == nblk - 1 && S.pmin_of(nblk - 1) >= S.pend()) {        // no pair left to apply to the last block: z = t
         const int k0 = dfirst * NB, w = min(NB, f.nc - k0);
         if (tid < NB) zs[tid] = (tid < w) ? __ldcg(t + k0 + tid) : 0.0;
         cp_async_wait<1>();
@@ -1802,6 +1854,7 @@ struct LevelSched {
     Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
     int small_all_off = 0, small_all_cnt = 0;
     int pgi = -1, pctas = 0;          // persistent sweeps (one right-hand side): index in CholDevice::plevels, CTAs
+    int prect = 0;                    // tiles of the backward rectangle pre-pass (k_bwd_rect)
 };
 
 class CholDevice {
@@ -1831,6 +1884,8 @@ public:
     std::vector<PersistLevel> plevels;    // persistent sweeps: launch records of the levels with 1 .. 2 x SMs large fronts
     PersistFront* dpfront = nullptr;      // their front records and CTA -> front maps (device)
     int* dpcmap = nullptr;
+    double* drect = nullptr;              // column sums of the rectangle pre-pass of one level (reused level after level)
+    bool persist_rect = true;             // B200S_PERSIST_RECT=0: the block owners stream the rows below the pivots themselves
     int persist_mode = 3;          // bit 0: forward, bit 1: backward sweep by k_fwd_persist / k_bwd_persist (B200S_SOLVE_PERSIST)
     int persist_default = 3, persist_hw = 3;      // B200S_SOLVE_PERSIST or 3; 0 when a persistent CTA does not fit an SM
     int* dsync = nullptr;          // [2][nsync]: forward flags, backward flags (zeroed per sweep pair)
@@ -1862,7 +1917,7 @@ public:
         pool_free(dreach); pool_free(dsp_i); pool_free(dsp_x); pool_free(dsp_cnt); pool_free(dsp_oi); pool_free(dsp_ox); pool_free(dsp_meta);
         for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
-        pool_free(dsync); pool_free(dpfront); pool_free(dpcmap);
+        pool_free(dsync); pool_free(dpfront); pool_free(dpcmap); pool_free(drect);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : pev) cudaEventDestroy(e);
         if (evP) cudaEventDestroy(evP);
@@ -2162,6 +2217,8 @@ int CholDevice::init() {
         // each front's steps (measured on 100^3: 32 -> 9.4 ms per solve, 296 -> 9.8 ms)
         int maxf = 32;
         if (const char* e = getenv("B200S_PERSIST_MAXF")) maxf = std::max(0, std::min(atoi(e), 2 * nsm));
+        if (const char* e = getenv("B200S_PERSIST_RECT")) persist_rect = atoi(e) != 0;
+        int max_rect = 0;
         std::vector<PersistFront> hpf;
         std::vector<int> hcmap;
         std::vector<std::pair<size_t, size_t>> offs;       // per persistent level: first record, first map entry
@@ -2173,7 +2230,7 @@ int CholDevice::init() {
             const bool shared = ng <= nsm;                        // else: one CTA per front, several fronts per CTA
             double area = 0;
             for (int i = 0; i < ng; i++) area += (double)hf[fr[i]].nr * hf[fr[i]].nc;
-            int cta = 0;
+            int cta = 0, rtiles = 0;
             offs.push_back({hpf.size(), hcmap.size()});
             for (int i = 0; i < ng; i++) {
                 const FrontD& d = hf[fr[i]];
@@ -2185,6 +2242,8 @@ int CholDevice::init() {
                 pf.cta0 = cta;
                 pf.ncta = 1 + std::max(0, std::min(npairs - 1, extra));
                 pf.sync0 = nsync;
+                pf.rect0 = rtiles;
+                rtiles += (npairs - nblk) * nblk;
                 if (shared) for (int q = 0; q < pf.ncta; q++) hcmap.push_back(i);
                 cta += pf.ncta;
                 nsync += nblk;
@@ -2194,7 +2253,14 @@ int CholDevice::init() {
             pl.fr = nullptr; pl.cmap = nullptr; pl.nf = ng; pl.shared = shared ? 1 : 0;
             LS.pgi = (int)plevels.size();
             LS.pctas = shared ? cta : nsm;
+            LS.prect = persist_rect ? rtiles : 0;
+            max_rect = std::max(max_rect, LS.prect);
             plevels.push_back(pl);
+        }
+        if (max_rect > 0) {
+            CUDA_TRY(pool_malloc((void**)&drect, (size_t)max_rect * NB * sizeof(double)));
+            total_bytes += (size_t)max_rect * NB * sizeof(double);
+            CUDA_TRY(cudaFuncSetAttribute(k_bwd_rect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUPD));
         }
         if (!plevels.empty()) {
             if ((rc = upload(&dpfront, hpf.data(), hpf.size()))) return rc;
@@ -2641,9 +2707,10 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     const LevelSched& LS = levels[l];
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
-                        if (pbwd && LS.pgi >= 0)
-                            k_bwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(plevels[LS.pgi], dL, dMinv, dT, dX, dsync + nsync, herr, (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : nullptr);
-                        else
+                        if (pbwd && LS.pgi >= 0) {
+                            if (LS.prect) k_bwd_rect<<<LS.prect, 256, SMEM_BUPD, stream>>>(plevels[LS.pgi], dL, dT, drect);
+                            k_bwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(plevels[LS.pgi], dL, dMinv, dT, dX, dsync + nsync, LS.prect ? drect : nullptr, herr, (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : nullptr);
+                        } else
                         for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
                             const Launch& la = LS.sbwd[kb];
                             if (la.ctas)
