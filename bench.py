@@ -329,6 +329,17 @@ def bench_cholesky(nx, steps, fp64_peak, full=True):
         fn["b200s_chol_info"](h, C.byref(inf))
         ms_s.append(inf.ms_solve)
     x = Xd.cpu().numpy()
+    # the same solve with the launch-per-step sweeps (what the persistent level kernels replace): time and bitwise comparison
+    cholmod.set_solve_sweeps(F, 0)
+    ms_s0 = []
+    for _ in range(max(2, steps)):
+        Xd0 = Bd.clone()
+        torch.cuda.synchronize()
+        assert fn["b200s_chol_solve_dev"](h, 0, Xd0.data_ptr(), 1, n) == 0
+        fn["b200s_chol_info"](h, C.byref(inf))
+        ms_s0.append(inf.ms_solve)
+    same_bits = bool(np.array_equal(x, Xd0.cpu().numpy()))
+    cholmod.set_solve_sweeps(F, -1)
     A = (Al + sp.tril(Al, -1).T).tocsr()
     berr = float(np.linalg.norm(A @ x - B[:, 0]) / (12.0 * np.linalg.norm(x) + np.linalg.norm(B)))
     # end to end through the public API with host buffers (H2D of values and RHS, D2H of the solution)
@@ -347,7 +358,14 @@ def bench_cholesky(nx, steps, fp64_peak, full=True):
         "factor_tflops": d["flops"] / (best_f * 1e-3) / 1e12,
         "solve_gbs": (16.0 * d["nnz_L"] + 16.0 * n) / (best_s * 1e-3) / 1e9,
         "e2e_factor_plus_solve_ms_host_buffers": e2e_ms, "backward_error": berr,
+        "solve_ms_launch_per_step": float(np.min(ms_s0)), "solve_bitwise_equal_both_paths": same_bits,
     }
+    hbm, hbm_src, _ = measured_peaks()
+    out["solve_roofline"] = {"bound": "hbm", "kernel": "k_fwd_persist / k_bwd_persist / k_bwd_rect + the launch-per-step sweeps of the wide levels",
+                             "achieved": out["solve_gbs"], "peak": hbm, "peak_source": hbm_src, "unit": "GB/s", "frac": out["solve_gbs"] / hbm,
+                             "algorithmic_bytes": 16.0 * d["nnz_L"] + 16.0 * n,
+                             "note": "L is read once per sweep (2 x 8 x nnz(L)); the chain of the root front (117 dependent block steps) and one "
+                                     "64 KB slice in flight per SM in the streaming levels bound it, DESIGN.md 2.4"}
     if not full:
         del F
         return out
