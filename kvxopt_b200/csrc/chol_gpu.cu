@@ -1886,6 +1886,7 @@ public:
     PersistFront* dpfront = nullptr;      // their front records and CTA -> front maps (device)
     int* dpcmap = nullptr;
     double* drect = nullptr;              // column sums of the rectangle pre-pass of one level (reused level after level)
+    bool persist_coop = true;             // B200S_PERSIST_COOP=0: plain launches
     bool persist_rect = true;             // B200S_PERSIST_RECT=0: the block owners stream the rows below the pivots themselves
     int persist_mode = 3;          // bit 0: forward, bit 1: backward sweep by k_fwd_persist / k_bwd_persist (B200S_SOLVE_PERSIST)
     int persist_default = 3, persist_hw = 3;      // B200S_SOLVE_PERSIST or 3; 0 when a persistent CTA does not fit an SM
@@ -2219,6 +2220,8 @@ int CholDevice::init() {
         int maxf = 32;
         if (const char* e = getenv("B200S_PERSIST_MAXF")) maxf = std::max(0, std::min(atoi(e), 2 * nsm));
         if (const char* e = getenv("B200S_PERSIST_RECT")) persist_rect = atoi(e) != 0;
+        if (const char* e = getenv("B200S_PERSIST_COOP")) persist_coop = atoi(e) != 0;
+        { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device); if (!coop) persist_coop = false; }
         int max_rect = 0;
         std::vector<PersistFront> hpf;
         std::vector<int> hcmap;
@@ -2678,6 +2681,16 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
         const bool reach = active_fronts && do_fwd;
         if (reach) CUDA_TRY(cudaMemsetAsync(dT, 0, (size_t)tstride * nc * sizeof(double), stream));
         const bool pfwd = nc == 1 && (persist_mode & 1) && !plevels.empty(), pbwd = nc == 1 && (persist_mode & 2) && !plevels.empty();
+        // The CTAs of a persistent sweep wait for each other: launched COOPERATIVELY, so that the grid only starts when all of
+        // it is resident (a second persistent sweep on another stream of the process cannot interleave and starve both).
+        auto launch_persist = [&](int ctas, auto kernel, auto... args) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SMEM_PERSIST; cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = persist_coop ? 1 : 0;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, kernel, args...);
+        };
         auto sweeps = [&]() {
             if ((pfwd && do_fwd) || (pbwd && do_bwd)) cudaMemsetAsync(dsync, 0, (size_t)2 * nsync * sizeof(int), stream);
             if (do_fwd)
@@ -2691,7 +2704,8 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     if (!LS.panel.empty() && LS.panel[0].ng) {
                         k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
                         if (pfwd && LS.pgi >= 0)
-                            k_fwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(plevels[LS.pgi], dL, dMinv, dT, dX, dsync, herr, (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : nullptr);
+                            launch_persist(LS.pctas, k_fwd_persist, plevels[LS.pgi], (const double*)dL, (const double*)dMinv, dT, dX, dsync, herr,
+                                           (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : (long long*)nullptr);
                         else
                         for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
                             const Launch& la = LS.sfwd[kb];
@@ -2710,7 +2724,9 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                         k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
                         if (pbwd && LS.pgi >= 0) {
                             if (LS.prect) k_bwd_rect<<<LS.prect, 256, SMEM_BUPD, stream>>>(plevels[LS.pgi], dL, dT, drect);
-                            k_bwd_persist<<<LS.pctas, 256, SMEM_PERSIST, stream>>>(plevels[LS.pgi], dL, dMinv, dT, dX, dsync + nsync, LS.prect ? drect : nullptr, herr, (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : nullptr);
+                            launch_persist(LS.pctas, k_bwd_persist, plevels[LS.pgi], (const double*)dL, (const double*)dMinv, dT, dX, dsync + nsync,
+                                           (const double*)(LS.prect ? drect : nullptr), herr,
+                                           (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : (long long*)nullptr);
                         } else
                         for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
                             const Launch& la = LS.sbwd[kb];
