@@ -2593,8 +2593,13 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     int rc = ensure_solve_ws(std::min<i64>(maxcols, 64));
     if (rc) return rc;
     const i64 chunk = solve_cols;
-    CUDA_TRY(cudaEventRecord(ev[4], stream));
-    if (!minv_valid && ninvblk > 0) {
+    // called inside a caller's stream capture (the dense KKT solver records its whole solve into one graph): no nested capture,
+    // and the inverses of the diagonal blocks are recomputed in the graph (it is replayed after later factorizations)
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap_st);
+    const bool capturing = cap_st == cudaStreamCaptureStatusActive;
+    if (!capturing) CUDA_TRY(cudaEventRecord(ev[4], stream));
+    if ((capturing || !minv_valid) && ninvblk > 0) {
         k_diag_inverse<<<ninvblk, 128, 0, stream>>>(dinv_front, dinv_kb, dF, dL, dMinv);
         minv_valid = true;
     }
@@ -2741,7 +2746,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                 }
         };
         const int gkey = nc * 32 + (pfwd ? 16 : 0) + (pbwd ? 8 : 0) + (ldl ? 4 : 0) + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
-        if (!use_graphs || reach) sweeps();      // the filtered lists change from call to call: not captured
+        if (!use_graphs || reach || capturing) sweeps();      // the filtered lists change from call to call: not captured
         else {
             auto it = solve_graphs.find(gkey);
             if (it == solve_graphs.end()) {
@@ -2764,7 +2769,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
     cudaError_t le = cudaGetLastError();
     if (!on_device && le == cudaSuccess)
         le = cudaMemcpy2DAsync(B, (size_t)ldB * 8, dBstage, (size_t)n * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, stream);
-    cudaEventRecord(ev[5], stream);
+    if (!capturing) cudaEventRecord(ev[5], stream);
     if (async && on_device) { CUDA_TRY(le); return ST_OK; }
     cudaError_t se = cudaStreamSynchronize(stream);
     CUDA_TRY(le);

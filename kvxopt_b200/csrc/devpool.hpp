@@ -79,6 +79,38 @@ class DevPool {
     size_t cached_ = 0;
 };
 
+// Cached pinned host staging buffers: cudaHostAlloc / cudaFreeHost cost milliseconds each, which an object that lives for one
+// small LP (a KKT solver per solvers.lp call) would pay every time.  Freed buffers are kept (grow-only, a few KB each).
+class PinnedPool {
+  public:
+    static PinnedPool& get() { static PinnedPool p; return p; }
+    cudaError_t malloc(void** out, size_t bytes) {
+        const size_t want = ((bytes ? bytes : 1) + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            auto it = free_.lower_bound(want);
+            if (it != free_.end() && it->first <= 4 * want) { *out = it->second; live_[*out] = it->first; free_.erase(it); return cudaSuccess; }
+        }
+        cudaError_t e = cudaHostAlloc(out, want, cudaHostAllocPortable);
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu_); live_[*out] = want; }
+        return e;
+    }
+    void free(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu_);
+        auto it = live_.find(p);
+        if (it == live_.end()) { cudaFreeHost(p); return; }
+        free_.emplace(it->second, p);
+        live_.erase(it);
+    }
+  private:
+    std::mutex mu_;
+    std::multimap<size_t, void*> free_;
+    std::unordered_map<void*, size_t> live_;
+};
+inline cudaError_t pinned_malloc(void** out, size_t bytes) { return PinnedPool::get().malloc(out, bytes); }
+inline void pinned_free(void* p) { PinnedPool::get().free(p); }
+
 inline cudaError_t pool_malloc(void** out, size_t bytes) { return DevPool::get().malloc(out, bytes); }
 inline void pool_free(void* p) { DevPool::get().free(p); }
 

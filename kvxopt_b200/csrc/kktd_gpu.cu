@@ -194,6 +194,13 @@ struct b200s_kktd {
     double ms_factor = 0, ms_solve = 0;
     cudaEvent_t ev[2] = {};
     long long launches = 0;
+    // the solve as ONE graph: x, y, z through a pinned staging buffer (fixed addresses), every kernel of misc.py:1284-1345 and the
+    // sweeps of the Cholesky object recorded once (second call: the first one allocates the workspaces) and replayed -- a 143-variable
+    // LP makes ~90 solves of a few microseconds of work each, 15 launches and 6 pageable copies apiece otherwise
+    double* h_stage = nullptr;
+    cudaGraphExec_t solve_graph = nullptr;
+    long long solve_calls = 0;
+    bool use_graph = true;
     cudaStream_t stream() const { return chol ? (cudaStream_t)chol_device_stream(chol) : own_stream; }
     ~b200s_kktd() {
         if (uploaded || chol) cudaSetDevice(device);
@@ -201,6 +208,8 @@ struct b200s_kktd {
         if (own_stream) { cudaStreamSynchronize(own_stream); cudaStreamDestroy(own_stream); }
         for (double* q : {d_G, d_Gs, d_V, d_T, d_R, d_K, d_H, d_W1, d_W2, d_di, d_x, d_y, d_z, d_t, d_t2, d_pack, d_yy}) pool_free(q);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (solve_graph) cudaGraphExecDestroy(solve_graph);
+        pinned_free(h_stage);
     }
 };
 
@@ -403,16 +412,10 @@ b200s_status b200s_kktd_factor(b200s_kktd* K, const double* di, const double* H,
     return (b200s_status)kktd_factor_impl(K, di, H, minor_out);
 }
 
-static int kktd_solve_impl(b200s_kktd* K, double* x, double* y, double* z) {
-    B200S_NVTX("kktd_solve_impl");
-    if (!K || (K->n > 0 && !x) || (K->p > 0 && !y) || (K->ml > 0 && !z)) return ST_INVALID;
-    if (!K->factored) { set_last_error("kkt 'chol': solve called before a successful factor"); return ST_INVALID; }
+// the device part of solve(): hx, hy, hz -> device, misc.py:1303-1342, device -> hx, hy, hz; everything on stream st
+static int kktd_solve_enqueue(b200s_kktd* K, cudaStream_t st, double* x, double* y, double* z) {
     const long long n = K->n, ml = K->ml, p = K->p, q = n - p;
-    if (n == 0) return ST_OK;
-    CUDA_TRY(cudaSetDevice(K->device));
-    cudaStream_t st = K->stream();
     int rc;
-    CUDA_TRY(cudaEventRecord(K->ev[0], st));
     CUDA_TRY(cudaMemcpyAsync(K->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, st));
     if (p) CUDA_TRY(cudaMemcpyAsync(K->d_yy, y, p * sizeof(double), cudaMemcpyHostToDevice, st));
     if (ml) {
@@ -439,6 +442,54 @@ static int kktd_solve_impl(b200s_kktd* K, double* x, double* y, double* z) {
     CUDA_TRY(cudaMemcpyAsync(x, K->d_x, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (p) CUDA_TRY(cudaMemcpyAsync(y, K->d_y, p * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (ml) CUDA_TRY(cudaMemcpyAsync(z, K->d_z, ml * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return ST_OK;
+}
+
+static int kktd_solve_impl(b200s_kktd* K, double* x, double* y, double* z) {
+    B200S_NVTX("kktd_solve_impl");
+    if (!K || (K->n > 0 && !x) || (K->p > 0 && !y) || (K->ml > 0 && !z)) return ST_INVALID;
+    if (!K->factored) { set_last_error("kkt 'chol': solve called before a successful factor"); return ST_INVALID; }
+    const long long n = K->n, ml = K->ml, p = K->p;
+    if (n == 0) return ST_OK;
+    CUDA_TRY(cudaSetDevice(K->device));
+    cudaStream_t st = K->stream();
+    int rc;
+    if (K->solve_calls++ == 0 || !K->use_graph) {     // first call: plain launches (workspaces of the Cholesky object are allocated here)
+        CUDA_TRY(cudaEventRecord(K->ev[0], st));
+        if ((rc = kktd_solve_enqueue(K, st, x, y, z))) return rc;
+    } else {
+        if (!K->h_stage) CUDA_TRY(pinned_malloc((void**)&K->h_stage, (size_t)(n + p + ml) * sizeof(double)));
+        double *hx = K->h_stage, *hy = hx + n, *hz = hy + p;
+        if (!K->solve_graph) {
+            cudaGraph_t gr = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = kktd_solve_enqueue(K, st, hx, hy, hz);
+            cudaError_t ce = cudaStreamEndCapture(st, &gr);
+            if (rc != ST_OK || ce != cudaSuccess) {      // not capturable here: stay with plain launches
+                if (gr) cudaGraphDestroy(gr);
+                cudaGetLastError();
+                K->use_graph = false;
+                K->solve_calls = 0;
+                return kktd_solve_impl(K, x, y, z);
+            }
+            cudaError_t ie = cudaGraphInstantiate(&K->solve_graph, gr, 0);
+            cudaGraphDestroy(gr);
+            CUDA_TRY(ie);
+        }
+        memcpy(hx, x, n * sizeof(double));
+        if (p) memcpy(hy, y, p * sizeof(double));
+        if (ml) memcpy(hz, z, ml * sizeof(double));
+        CUDA_TRY(cudaEventRecord(K->ev[0], st));
+        CUDA_TRY(cudaGraphLaunch(K->solve_graph, st));
+        CUDA_TRY(cudaEventRecord(K->ev[1], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(x, hx, n * sizeof(double));
+        if (p) memcpy(y, hy, p * sizeof(double));
+        if (ml) memcpy(z, hz, ml * sizeof(double));
+        float ms;
+        cudaEventElapsedTime(&ms, K->ev[0], K->ev[1]); K->ms_solve = ms;
+        return ST_OK;
+    }
     CUDA_TRY(cudaEventRecord(K->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms;
