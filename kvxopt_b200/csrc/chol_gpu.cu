@@ -154,6 +154,7 @@ __device__ __forceinline__ int locate_group(const SolveGroups& sg, const int* gp
 // ---------------------------------------------------------------------------------------------------
 // K1: scatter the caller's CCS values into the (zeroed) panels
 // ---------------------------------------------------------------------------------------------------
+__global__ void k_set_int(int* p, int v) { *p = v; }
 __global__ void k_scatter_A(const double* __restrict__ val, const long long* __restrict__ amap, long long nnz,
                             double* __restrict__ L) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
@@ -1942,6 +1943,7 @@ public:
     SyrkSplit syrk_split = {nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned char* dsy_own = nullptr; int *dsy_lo = nullptr, *dsy_hi = nullptr; long long* dsy_base = nullptr;
     int factor_end(i64* minor, CholTimes* times);
+    int factor_enqueue(const double* val_dev);
     int set_owned(const unsigned char* owned_host);
     int solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, CholTimes* times, bool async = false,
               const unsigned char* active_fronts = nullptr);
@@ -2339,8 +2341,7 @@ int CholDevice::factor_begin(const double* val, bool on_device) {
         dv = dval;
     }
     CUDA_TRY(cudaEventRecord(ev[1], stream));
-    const int big = 0x7fffffff;
-    CUDA_TRY(cudaMemcpyAsync(dminor, &big, sizeof(int), cudaMemcpyHostToDevice, stream));
+    k_set_int<<<1, 1, 0, stream>>>(dminor, 0x7fffffff);      // (a kernel, not a copy from the stack: this sequence may be recorded into a caller's graph)
     if (P.lsize) CUDA_TRY(cudaMemsetAsync(dL, 0, P.lsize * sizeof(double), stream));
     if (P.nnzA) {
         int blocks = (int)std::min<i64>((P.nnzA + 255) / 256, 148 * 16);
@@ -2560,6 +2561,17 @@ int CholDevice::factorize(const double* val, bool on_device, i64* minor, CholTim
     for (int l = 0; l < plan->nlevels; l++)
         if ((rc = factor_level(l))) return rc;
     return factor_end(minor, times);
+}
+
+// the whole factorization enqueued on the streams, nothing read back: for callers that record it into a CUDA graph (dense KKT
+// solver); `minor` stays on the device (chol_device_minor_ptr: 0x7fffffff = positive definite), the caller marks the factor
+// numeric after it has looked at it
+int CholDevice::factor_enqueue(const double* val_dev) {
+    int rc = factor_begin(val_dev, true);
+    if (rc) return rc;
+    for (int l = 0; l < plan->nlevels; l++)
+        if ((rc = factor_level(l))) return rc;
+    return ST_OK;
 }
 
 int CholDevice::set_owned(const unsigned char* owned_host) {
@@ -3086,6 +3098,8 @@ int chol_device_solve_buffers(CholDevice* d, double** T, double** X) {
     *T = d->dT; *X = d->dX;
     return rc;
 }
+int chol_device_factor_enqueue(CholDevice* d, const double* val_dev) { return d->factor_enqueue(val_dev); }
+const int* chol_device_minor_ptr(CholDevice* d) { return d->dminor; }
 void chol_device_set_solve_sweeps(CholDevice* d, int mode) { d->persist_mode = mode < 0 ? d->persist_default : (mode & d->persist_hw); }
 void chol_device_mark_numeric(CholDevice* d, bool numeric) { d->numeric = numeric; d->minv_valid = false; }
 i64 chol_device_workspace_bytes(const CholDevice* d) { return d->total_bytes; }

@@ -198,8 +198,9 @@ struct b200s_kktd {
     // sweeps of the Cholesky object recorded once (second call: the first one allocates the workspaces) and replayed -- a 143-variable
     // LP makes ~90 solves of a few microseconds of work each, 15 launches and 6 pageable copies apiece otherwise
     double* h_stage = nullptr;
-    cudaGraphExec_t solve_graph = nullptr;
-    long long solve_calls = 0;
+    cudaGraphExec_t solve_graph = nullptr, factor_graph = nullptr;     // factor(W) with H = None likewise (di and the pivot word staged)
+    double* h_fstage = nullptr;
+    long long solve_calls = 0, factor_calls = 0;
     bool use_graph = true;
     cudaStream_t stream() const { return chol ? (cudaStream_t)chol_device_stream(chol) : own_stream; }
     ~b200s_kktd() {
@@ -209,7 +210,8 @@ struct b200s_kktd {
         for (double* q : {d_G, d_Gs, d_V, d_T, d_R, d_K, d_H, d_W1, d_W2, d_di, d_x, d_y, d_z, d_t, d_t2, d_pack, d_yy}) pool_free(q);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (solve_graph) cudaGraphExecDestroy(solve_graph);
-        pinned_free(h_stage);
+        if (factor_graph) cudaGraphExecDestroy(factor_graph);
+        pinned_free(h_stage); pinned_free(h_fstage);
     }
 };
 
@@ -362,16 +364,9 @@ static int kktd_ensure_device(b200s_kktd* K) {
     return ST_OK;
 }
 
-static int kktd_factor_impl(b200s_kktd* K, const double* di, const double* H, b200s_int* minor_out) {
-    B200S_NVTX("kktd_factor_impl");
-    if (!K || (K->ml > 0 && !di)) return ST_INVALID;
-    K->factored = false;
+// the device part of factor(): di (and H) -> device, K = Q'(H + Gs'Gs)Q, lower triangle of K22 packed for the Cholesky object
+static int kktd_factor_enqueue(b200s_kktd* K, cudaStream_t st, const double* di, const double* H) {
     const long long n = K->n, ml = K->ml, p = K->p, q = n - p;
-    if (n == 0) { K->factored = true; return ST_OK; }
-    { int rc0 = kktd_ensure_device(K); if (rc0) return rc0; }
-    CUDA_TRY(cudaSetDevice(K->device));
-    cudaStream_t st = K->stream();
-    CUDA_TRY(cudaEventRecord(K->ev[0], st));
     K->launches = 0;
     if (ml) CUDA_TRY(cudaMemcpyAsync(K->d_di, di, ml * sizeof(double), cudaMemcpyHostToDevice, st));
     if (H) CUDA_TRY(cudaMemcpyAsync(K->d_H, H, n * n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -389,11 +384,66 @@ static int kktd_factor_impl(b200s_kktd* K, const double* di, const double* H, b2
         gemm(st, (int)n, (int)p, (int)p, 1.0, K->d_W2, 1, n, K->d_T, 1, p, 0.0, K->d_W1, n, K->launches);          // W1 (n x p) = W2 T
         gemm(st, (int)n, (int)n, (int)p, -1.0, K->d_W1, 1, n, K->d_V, n, 1, 1.0, K->d_K, n, K->launches);          // K = S - W1 V'
     }
+    if (q > 0) { k_pack_lower<<<grid1(q * q), 256, 0, st>>>(n, p, K->d_K, K->d_pack); K->launches++; }
     CUDA_TRY(cudaGetLastError());
+    return ST_OK;
+}
+
+static int kktd_factor_impl(b200s_kktd* K, const double* di, const double* H, b200s_int* minor_out) {
+    B200S_NVTX("kktd_factor_impl");
+    if (!K || (K->ml > 0 && !di)) return ST_INVALID;
+    K->factored = false;
+    const long long n = K->n, ml = K->ml, p = K->p, q = n - p;
+    if (n == 0) { K->factored = true; return ST_OK; }
+    { int rc0 = kktd_ensure_device(K); if (rc0) return rc0; }
+    CUDA_TRY(cudaSetDevice(K->device));
+    cudaStream_t st = K->stream();
+    int rc;
     i64 minor = q;
+    // From the second call on (the first one allocates the Cholesky object's panels) factor(W) with H = None is ONE graph: di
+    // through pinned staging, the products above, the factorization of K22 enqueued without read-back, the pivot word back
+    if (K->factor_calls++ > 0 && K->use_graph && !H && q > 0) {
+        if (!K->h_fstage) CUDA_TRY(pinned_malloc((void**)&K->h_fstage, (size_t)(ml + 2) * sizeof(double)));
+        double* hdi = K->h_fstage;
+        int* hminor = reinterpret_cast<int*>(K->h_fstage + ml);
+        if (!K->factor_graph) {
+            cudaGraph_t gr = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = kktd_factor_enqueue(K, st, hdi, nullptr);
+            if (rc == ST_OK) rc = chol_device_factor_enqueue(K->chol, K->d_pack);
+            if (rc == ST_OK && cudaMemcpyAsync(hminor, chol_device_minor_ptr(K->chol), sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = ST_CUDA;
+            cudaError_t ce = cudaStreamEndCapture(st, &gr);
+            if (rc != ST_OK || ce != cudaSuccess) {      // not capturable here: plain launches from now on
+                if (gr) cudaGraphDestroy(gr);
+                cudaGetLastError();
+                K->use_graph = false;
+                return kktd_factor_impl(K, di, H, minor_out);
+            }
+            cudaError_t ie = cudaGraphInstantiate(&K->factor_graph, gr, 0);
+            cudaGraphDestroy(gr);
+            CUDA_TRY(ie);
+        }
+        if (ml) memcpy(hdi, di, ml * sizeof(double));
+        chol_device_mark_numeric(K->chol, false);
+        CUDA_TRY(cudaEventRecord(K->ev[0], st));
+        CUDA_TRY(cudaGraphLaunch(K->factor_graph, st));
+        CUDA_TRY(cudaEventRecord(K->ev[1], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms;
+        cudaEventElapsedTime(&ms, K->ev[0], K->ev[1]); K->ms_factor = ms;
+        if (*hminor != 0x7fffffff) {
+            if (minor_out) *minor_out = *hminor;
+            return ST_NOT_POSDEF;
+        }
+        chol_device_mark_numeric(K->chol, true);
+        if (minor_out) *minor_out = q;
+        K->factored = true;
+        return ST_OK;
+    }
+    CUDA_TRY(cudaEventRecord(K->ev[0], st));
+    if ((rc = kktd_factor_enqueue(K, st, di, H))) return rc;
     if (q > 0) {
-        k_pack_lower<<<grid1(q * q), 256, 0, st>>>(n, p, K->d_K, K->d_pack); K->launches++;
-        int rc = chol_device_factorize(K->chol, K->d_pack, true, &minor, &K->times);
+        rc = chol_device_factorize(K->chol, K->d_pack, true, &minor, &K->times);
         if (minor_out) *minor_out = minor;
         if (rc != ST_OK) return rc;
     }
