@@ -66,6 +66,35 @@ def test_not_positive_definite_raises_like_potrf(kvx):
         factor({"di": matrix(1.0, (ml, 1))}, matrix(H))
 
 
+def test_graph_replayed_factor_and_solve_report_and_recover(kvx):
+    """from its second call on factor(W) (H = None) and solve() are replayed CUDA graphs (kktd_gpu.cu): a scaling that makes
+    K22 singular inside the replayed graph still raises ArithmeticError (the pivot word travels back through the staging
+    buffer), the next factorization works again, and replayed solves give the same answers as the first, plainly launched one"""
+    from kvxopt import matrix
+    from kvxopt_b200 import kkt
+    G, A, H, d, rng = problem(5, 143, 352, 4, False)
+    n, ml, p = 143, 352, 4
+    factor = kkt.chol(matrix(G), {"l": ml, "q": [], "s": []}, matrix(A))
+    bx, by, bz = rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(ml)
+
+    def run(dd):
+        solve = factor({"di": matrix(1.0 / dd)})
+        outs = []
+        for _ in range(3):
+            x, y, z = matrix(bx), matrix(by), matrix(bz)
+            solve(x, y, z)
+            outs.append(np.concatenate([np.array(x).ravel(), np.array(y).ravel(), np.array(z).ravel()]))
+        return outs
+    first = run(d)                                   # plain launches, then the captured solve
+    assert np.array_equal(first[0], first[1]) and np.array_equal(first[1], first[2])
+    second = run(d)                                  # the captured factorization
+    assert np.array_equal(second[0], first[0])
+    with pytest.raises(ArithmeticError):
+        factor({"di": matrix(0.0, (ml, 1))})         # K = 0: zero pivot inside the replayed graph
+    third = run(d)
+    assert np.array_equal(third[0], first[0])
+
+
 def test_rank_deficient_A_raises(kvx):
     from kvxopt import matrix
     from kvxopt_b200 import kkt
