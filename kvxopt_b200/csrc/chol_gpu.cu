@@ -1853,7 +1853,8 @@ struct LevelSched {
     std::vector<Launch> updFA, updFB; // far split: column tiles of the next super-block / the rest (look-ahead)
     Launch syrk;
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
-    Launch gfwd;                      // forward gather of large fronts: 2048-row chunks
+    Launch gfwd;                      // forward gather of large fronts: GATHER_ROWS-row chunks
+    Launch sbig;                      // the fronts the SOLVES treat as large (one entry each): panel[0] minus the one-block fronts with few rows
     int small_all_off = 0, small_all_cnt = 0;
     int pgi = -1, pctas = 0;          // persistent sweeps (one right-hand side): index in CholDevice::plevels, CTAs
     int prect = 0;                    // tiles of the backward rectangle pre-pass (k_bwd_rect)
@@ -1889,6 +1890,7 @@ public:
     double* drect = nullptr;              // column sums of the rectangle pre-pass of one level (reused level after level)
     bool persist_coop = true;             // B200S_PERSIST_COOP=0: plain launches
     bool persist_rect = true;             // B200S_PERSIST_RECT=0: the block owners stream the rows below the pivots themselves
+    int solve_medium_nr = 320;     // solves: one-block large fronts with at most this many rows run with the small fronts (B200S_SOLVE_MEDIUM_NR)
     int persist_mode = 3;          // bit 0: forward, bit 1: backward sweep by k_fwd_persist / k_bwd_persist (B200S_SOLVE_PERSIST)
     int persist_default = 3, persist_hw = 3;      // B200S_SOLVE_PERSIST or 3; 0 when a persistent CTA does not fit an SM
     int* dsync = nullptr;          // [2][nsync]: forward flags, backward flags (zeroed per sweep pair)
@@ -1982,6 +1984,7 @@ int CholDevice::init() {
     CUDA_TRY(cudaFree(0));
     lap("context");
     use_graphs = getenv("B200S_NO_GRAPH") == nullptr;
+    if (const char* e = getenv("B200S_SOLVE_MEDIUM_NR")) solve_medium_nr = atoi(e);
     if (const char* e = getenv("B200S_UPDATE_TMA")) upd_tma = atoi(e) != 0;
     {   // the main stream carries the latency-bound panel chain: its CTAs must get the SM slots that the bulk update
         // kernels on stream2 free up, ahead of that kernel's own queued CTAs
@@ -2071,6 +2074,18 @@ int CholDevice::init() {
             LS.small_cnt[c] = (int)smalls[c].size();
             sched.insert(sched.end(), smalls[c].begin(), smalls[c].end());
         }
+        // SOLVE phase only: large fronts with one block column and few rows (the deep levels of a 3-D problem hold thousands of
+        // them: 100^3 has 3653 in one level) go with the small fronts -- one CTA per front (k_fwd / k_bwd take any nr) instead of a
+        // 128 KB tile CTA per 128 rows at one CTA per SM (their two block-step launches took 135 / 278 us per level and sweep).
+        // Row limit swept on the B200 (100^3 / 64^3 solve through the host API): none 8.77 / 2.63 ms, 200: 8.31 / 2.58, 256: 8.16 /
+        // 2.48, 320: 8.12 / 2.50, 448: 8.28 / 2.58, 640: 8.37 / 2.91 (beyond ~320 rows the one-CTA kernels are the slower ones).
+        // Their ids follow the small fronts' in the schedule array, so the small-front list of the solves simply grows.
+        std::vector<int> mediums, sbigs;
+        for (int s : bigs) {
+            const Front& f = P.fronts[s];
+            if (f.nc <= NB && f.nr <= solve_medium_nr) mediums.push_back(s); else sbigs.push_back(s);
+        }
+        sched.insert(sched.end(), mediums.begin(), mediums.end());
         int maxblk = 0;
         for (int s : bigs) maxblk = std::max(maxblk, (P.fronts[s].nc + NB - 1) / NB);
         LS.panel.resize(maxblk);
@@ -2105,18 +2120,21 @@ int CholDevice::init() {
                 sgroups.push_back(G);
             }
         };
-        if (!bigs.empty()) {
+        if (!sbigs.empty()) {
             std::vector<int> cnt;
-            for (int s : bigs) cnt.push_back((P.fronts[s].nr + GATHER_ROWS - 1) / GATHER_ROWS);
-            emit(LS.gfwd, bigs, cnt);
+            for (int s : sbigs) cnt.push_back((P.fronts[s].nr + GATHER_ROWS - 1) / GATHER_ROWS);
+            emit(LS.gfwd, sbigs, cnt);
+            emit(LS.sbig, sbigs, std::vector<int>(sbigs.size(), 1));
         }
         LS.small_all_off = LS.small_off[0];
-        LS.small_all_cnt = LS.small_cnt[0] + LS.small_cnt[1] + LS.small_cnt[2];
-        LS.sfwd.resize(maxblk);
-        LS.sbwd.resize(maxblk);
-        for (int kb = 0; kb < maxblk; kb++) {
+        LS.small_all_cnt = LS.small_cnt[0] + LS.small_cnt[1] + LS.small_cnt[2] + (int)mediums.size();
+        int maxblk_s = 0;
+        for (int s : sbigs) maxblk_s = std::max(maxblk_s, (P.fronts[s].nc + NB - 1) / NB);
+        LS.sfwd.resize(maxblk_s);
+        LS.sbwd.resize(maxblk_s);
+        for (int kb = 0; kb < maxblk_s; kb++) {
             std::vector<int> fs, cf, cb2;
-            for (int s : bigs) {
+            for (int s : sbigs) {
                 const Front& f = P.fronts[s];
                 const int nblk = (f.nc + NB - 1) / NB;
                 if (kb >= nblk) continue;
@@ -2230,9 +2248,9 @@ int CholDevice::init() {
         std::vector<std::pair<size_t, size_t>> offs;       // per persistent level: first record, first map entry
         for (int l = 0; l < P.nlevels && persist_hw; l++) {
             LevelSched& LS = levels[l];
-            if (LS.panel.empty() || LS.panel[0].ng < 1 || LS.panel[0].ng > maxf) continue;
-            const int ng = LS.panel[0].ng;
-            const int* fr = sched.data() + LS.panel[0].goff;      // the large fronts of the level
+            if (LS.sbig.ng < 1 || LS.sbig.ng > maxf) continue;
+            const int ng = LS.sbig.ng;
+            const int* fr = sched.data() + LS.sbig.goff;          // the fronts of the level that the solves treat as large
             const bool shared = ng <= nsm;                        // else: one CTA per front, several fronts per CTA
             double area = 0;
             for (int i = 0; i < ng; i++) area += (double)hf[fr[i]].nr * hf[fr[i]].nc;
@@ -2718,7 +2736,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                             k_fwd<<<dim3(reach_cnt[l], nc), 256, 0, stream>>>(dreach + reach_off[l], dF, dchild, drel, dL, dT, tstride, dX, n);
                     } else if (LS.small_all_cnt)
                         k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
-                    if (!LS.panel.empty() && LS.panel[0].ng) {
+                    if (LS.sbig.ng) {
                         k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
                         if (pfwd && LS.pgi >= 0)
                             launch_persist(LS.pctas, k_fwd_persist, plevels[LS.pgi], (const double*)dL, (const double*)dMinv, dT, dX, dsync, herr,
@@ -2737,8 +2755,8 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
             if (do_bwd)
                 for (int l = P.nlevels - 1; l >= 0; l--) {
                     const LevelSched& LS = levels[l];
-                    if (!LS.panel.empty() && LS.panel[0].ng) {
-                        k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n);
+                    if (LS.sbig.ng) {
+                        k_bwd_gather<<<dim3(LS.sbig.ng, nc), 256, 0, stream>>>(dsched + LS.sbig.goff, dF, drows, dT, tstride, dX, n);
                         if (pbwd && LS.pgi >= 0) {
                             if (LS.prect) k_bwd_rect<<<LS.prect, 256, SMEM_BUPD, stream>>>(plevels[LS.pgi], dL, dT, drect);
                             launch_persist(LS.pctas, k_bwd_persist, plevels[LS.pgi], (const double*)dL, (const double*)dMinv, dT, dX, dsync + nsync,
@@ -2850,7 +2868,7 @@ int CholDevice::solve_dist_level(int backward, int l) {
     if (!backward) {
         if (LS.small_all_cnt)
             k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n, downed);
-        if (!LS.panel.empty() && LS.panel[0].ng) {
+        if (LS.sbig.ng) {
             k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, downed);
             for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
                 const Launch& la = LS.sfwd[kb];
@@ -2860,8 +2878,8 @@ int CholDevice::solve_dist_level(int backward, int l) {
             }
         }
     } else {
-        if (!LS.panel.empty() && LS.panel[0].ng) {
-            k_bwd_gather<<<dim3(LS.panel[0].ng, nc), 256, 0, stream>>>(dsched + LS.panel[0].goff, dF, drows, dT, tstride, dX, n, downed);
+        if (LS.sbig.ng) {
+            k_bwd_gather<<<dim3(LS.sbig.ng, nc), 256, 0, stream>>>(dsched + LS.sbig.goff, dF, drows, dT, tstride, dX, n, downed);
             for (int kb = (int)LS.sbwd.size() - 1; kb >= 0; kb--) {
                 const Launch& la = LS.sbwd[kb];
                 if (la.ctas)
