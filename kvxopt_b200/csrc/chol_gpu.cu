@@ -803,8 +803,9 @@ __global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const
         __syncthreads();
         if (tid < 32) {
             double v = (lane < wb) ? t[b0 + lane] : 0.0;
+            const double rd = (lane < wb) ? 1.0 / D[lane][lane] : 1.0;      // one division per lane, off the 32-step chain
             for (int qq = 0; qq < wb; qq++) {
-                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
+                double xq = __shfl_sync(0xffffffffu, v, qq) * __shfl_sync(0xffffffffu, rd, qq);
                 if (lane == qq) v = xq;
                 else if (lane > qq && lane < wb) v -= xq * D[lane][qq];
             }
@@ -854,8 +855,9 @@ __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const
         __syncthreads();
         if (tid < 32) {
             double v = (lane < wb) ? zs[lane] : 0.0;
+            const double rd = (lane < wb) ? 1.0 / D[lane][lane] : 1.0;
             for (int qq = wb - 1; qq >= 0; qq--) {
-                double xq = __shfl_sync(0xffffffffu, v, qq) / D[qq][qq];
+                double xq = __shfl_sync(0xffffffffu, v, qq) * __shfl_sync(0xffffffffu, rd, qq);
                 if (lane == qq) v = xq;
                 else if (lane < qq) v -= xq * D[qq][lane];
             }
