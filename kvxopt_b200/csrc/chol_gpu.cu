@@ -1848,7 +1848,11 @@ struct Launch {            // one grouped launch: groups [goff, goff+ng) in the 
 };
 struct LevelSched {
     int ea_off = 0, ea_cnt = 0;
-    int small_off[3] = {0, 0, 0}, small_cnt[3] = {0, 0, 0}, small_maxnr[3] = {0, 0, 0};
+    // small fronts by rows: <= 32, <= 64, then three classes of the 256-thread kernel by how many CTAs fit an SM with the whole
+    // front in shared memory: <= 96 rows (74.5 KB: three), <= 118 (112 KB: two), <= 128 (one).  One class for 65..128 rows sized
+    // every launch for its largest front: a level of 8082 fronts of <= 96 rows and 400 of up to 128 ran at one CTA per SM.
+    static constexpr int NSMALL = 5;
+    int small_off[NSMALL] = {0, 0, 0, 0, 0}, small_cnt[NSMALL] = {0, 0, 0, 0, 0}, small_maxnr[NSMALL] = {0, 0, 0, 0, 0};
     std::vector<Launch> panel, upd;   // per block step kb (upd = all trailing column tiles)
     std::vector<Launch> updA, updB;   // lookahead split of upd: next block column / the rest
     std::vector<Launch> updN, updF;   // two-level update: near (inside the super-block, K = 128) / far (K = super-block)
@@ -2050,7 +2054,7 @@ int CholDevice::init() {
     const long long EA_TARGET = 16384;
     for (int l = 0; l < P.nlevels; l++) {
         LevelSched& LS = levels[l];
-        std::vector<int> smalls[3], bigs;
+        std::vector<int> smalls[LevelSched::NSMALL], bigs;
         LS.ea_off = (int)ea.size();
         for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; q++) {
             const int s = P.level_fronts[q];
@@ -2065,13 +2069,13 @@ int CholDevice::init() {
                 if (acc >= EA_TARGET || c == f.nr - 1) { ea.push_back({s, c0, c + 1}); c0 = c + 1; acc = 0; }
             }
             if (f.nr <= SMALL_NR) {
-                int cls = f.nr <= 32 ? 0 : (f.nr <= 64 ? 1 : 2);
+                int cls = f.nr <= 32 ? 0 : (f.nr <= 64 ? 1 : (f.nr <= 96 ? 2 : (f.nr <= 118 ? 3 : 4)));
                 smalls[cls].push_back(s);
                 LS.small_maxnr[cls] = std::max(LS.small_maxnr[cls], f.nr);
             } else bigs.push_back(s);
         }
         LS.ea_cnt = (int)ea.size() - LS.ea_off;
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < LevelSched::NSMALL; c++) {
             LS.small_off[c] = (int)sched.size();
             LS.small_cnt[c] = (int)smalls[c].size();
             sched.insert(sched.end(), smalls[c].begin(), smalls[c].end());
@@ -2129,7 +2133,8 @@ int CholDevice::init() {
             emit(LS.sbig, sbigs, std::vector<int>(sbigs.size(), 1));
         }
         LS.small_all_off = LS.small_off[0];
-        LS.small_all_cnt = LS.small_cnt[0] + LS.small_cnt[1] + LS.small_cnt[2] + (int)mediums.size();
+        LS.small_all_cnt = (int)mediums.size();
+        for (int c = 0; c < LevelSched::NSMALL; c++) LS.small_all_cnt += LS.small_cnt[c];
         int maxblk_s = 0;
         for (int s : sbigs) maxblk_s = std::max(maxblk_s, (P.fronts[s].nc + NB - 1) / NB);
         LS.sfwd.resize(maxblk_s);
@@ -2445,9 +2450,10 @@ int CholDevice::factor_level(int l, int phase) {
     if (LS.small_cnt[1])
         LAUNCH_SMALL(128, LS.small_cnt[1], 128, (size_t)(LS.small_maxnr[1] | 1) * LS.small_maxnr[1] * 8, stream,
                          dsched + LS.small_off[1], dF, dL, dW, dminor, opts.dbound, downed);
-    if (LS.small_cnt[2])
-        LAUNCH_SMALL(256, LS.small_cnt[2], 256, (size_t)(LS.small_maxnr[2] | 1) * LS.small_maxnr[2] * 8, stream,
-                         dsched + LS.small_off[2], dF, dL, dW, dminor, opts.dbound, downed);
+    for (int c = 2; c < LevelSched::NSMALL; c++)
+        if (LS.small_cnt[c])
+            LAUNCH_SMALL(256, LS.small_cnt[c], 256, (size_t)(LS.small_maxnr[c] | 1) * LS.small_maxnr[c] * 8, stream,
+                             dsched + LS.small_off[c], dF, dL, dW, dminor, opts.dbound, downed);
     prof_end();
     // Lookahead of depth one: after panel kb, part A of its trailing update (the next block column only) runs on
     // the main stream, then panel kb+1; part B (all other column tiles) runs on stream2 concurrently with panel
