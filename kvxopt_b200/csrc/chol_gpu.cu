@@ -16,6 +16,11 @@
 //   k_update      C -= A_i A_j^T on 128x128 tiles with FP64 tensor-core DMMA (mma.sync m8n8k4.f64),
 //                 operands staged by a 2-stage cp.async pipeline of 32-column k-tiles; used for the in-panel trailing update
 //                 (K = 128) and for the Schur complement (K = nc).
+// Solves: k_fwd / k_bwd (small fronts and, in the solve phase, one-block fronts with few rows: one CTA per front);
+//   k_fwd_gather + k_fwd_diag / k_fwd_upd and k_bwd_gather + k_bwd_upd / k_bwd_diag (large fronts, two launches per
+//   128-column block step: several right-hand sides, ownership-masked distributed sweeps, wide levels);
+//   k_fwd_persist / k_bwd_persist / k_bwd_rect (one right-hand side, levels with <= 32 large fronts: ONE cooperative kernel
+//   per level and direction, CTAs hand the solved block on through release / acquire flags; bit-identical to the above).
 #include "gpu.hpp"
 #include "devpool.hpp"
 #include <cuda_runtime.h>
