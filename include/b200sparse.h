@@ -314,6 +314,11 @@ b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* 
  * layout of b200s_klu_extract_host.  Verification of the host-built plan in CPU tests; not a factorization path. */
 b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* val, double* Lx, double* Ux, double* Fx, double* Rs);
 
+/* Replays on the HOST the operation tape of the one-matrix solve kernel (klu_solve / klu_tsolve, klu.c:593-690, written down
+ * once per pattern as column operations in execution order) with the values of the pivot search, in place on B (n x nrhs,
+ * leading dimension ldB); trans: 0 = 'N', 1 = 'T'.  Verification of the host-built tape in CPU tests; not a solve path. */
+b200s_status b200s_klu_solve_tape_host(const b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB);
+
 /* ---- complex matrices ('z'; klu_zl_*: src/C/klu.c:161-162,348-355,468-479,661-668,754-813) ------------------------------------
  * b200s_klu_analyze is type-independent (klu.c:266).  val: nnz (re, im) pairs.  The threshold-pivoting factorization runs on
  * the host in complex arithmetic and is what b200s_klu_extract_z returns (get_numeric, get_det); the solves run on the device

@@ -107,6 +107,7 @@ SIGNATURES = {
     "b200s_klu_extract_z": (C.c_int, vp, p_i64, p_i64, p_f64, p_i64, p_i64, p_f64, p_i64, p_i64, p_f64, p_i64, p_i64, p_f64, p_i64),
     "b200s_klu_embedded": (vp, vp),
     "b200s_klu_plan_emulate_host": (C.c_int, vp, p_f64, p_f64, p_f64, p_f64, p_f64),
+    "b200s_klu_solve_tape_host": (C.c_int, vp, C.c_int, p_f64, i64, i64),
     "b200s_kkt_create": (C.c_int, i64, i64, i64, p_i64, p_i64, p_f64, p_i64, p_i64, p_f64, p_i64, p_i64, C.POINTER(vp)),
     "b200s_kkt_set_singular": (C.c_int, vp, C.c_int),
     "b200s_kkt_factor": (C.c_int, vp, p_f64, p_f64, p_i64),

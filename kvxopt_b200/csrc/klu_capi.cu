@@ -23,6 +23,8 @@ int klu_device_refactor_begin(KluDevice* d, const double* vals, long long batch,
 int klu_device_refactor_end(KluDevice* d, int* status);
 int klu_device_solve(KluDevice* d, int trans, double* B, long long nrhs, long long ldB, long long batch, bool on_device);
 int klu_device_extract(KluDevice* d, long long b, double* slots_host, double* rs_host);
+int klu_solve_tape_host(const KluSymbolic& S, const KluNumeric& N, const KluPlan& P, int trans, const double* slots, double* B,
+                        long long nrhs, long long ldB);
 void klu_device_times(const KluDevice* d, double* h2d, double* refactor, double* solve, double* kernel, double* dense, long long* launches);
 }  // namespace b200s
 
@@ -306,6 +308,27 @@ b200s_status b200s_klu_plan_emulate_host(const b200s_klu_num* N, const double* v
         if (Rs) Rs[k] = rs[k];
     }
     return (b200s_status)st;
+}
+
+/* Test hook: the operation tape of the one-matrix solve kernel (k_klu_solve_one) replayed on the HOST with the values of the
+ * pivot search, in place on B (n x nrhs, leading dimension ldB).  Verifies the tape without a GPU; not a solve path. */
+b200s_status b200s_klu_solve_tape_host(const b200s_klu_num* N, int trans, double* B, b200s_int nrhs, b200s_int ldB) {
+    if (!N || nrhs < 0 || (trans != 0 && trans != 1) || N->zN) return B200S_INVALID;
+    const i32 n = N->N.n;
+    if (n == 0 || nrhs == 0) return B200S_OK;
+    if (!B || ldB < n) return B200S_INVALID;
+    const KluPlan& P = N->P; const KluNumeric& M = N->N;
+    try {
+        std::vector<double> slots((size_t)std::max<i64>(P.nslots, 1), 0.0);
+        for (i32 k = 0; k < n; k++) {
+            for (i64 p = M.Up[k]; p < M.Up[k + 1]; p++) slots[P.cbeg[k] + (p - M.Up[k])] = M.Ux[p];
+            for (i64 p = M.Lp[k] + 1; p < M.Lp[k + 1]; p++) slots[P.lslot0[k] + (p - M.Lp[k] - 1)] = M.Lx[p];
+            for (i64 p = M.Fp[k]; p < M.Fp[k + 1]; p++) slots[P.fslot0[k] + (p - M.Fp[k])] = M.Fx[p];
+        }
+        return (b200s_status)klu_solve_tape_host(N->S, M, P, trans, slots.data(), B, nrhs, ldB);
+    } catch (const std::bad_alloc&) {
+        return B200S_OUT_OF_MEMORY;
+    }
 }
 
 b200s_status b200s_klu_plan_view(const b200s_klu_num* N, b200s_klu_plan_view_t* v) {

@@ -1148,6 +1148,202 @@ __global__ void __launch_bounds__(KLU_SOLVE_WARPS * 32) k_klu_solve_lvl(KluSolve
     }
 }
 
+// ---- one matrix, one CTA per right-hand side (klu.solve / klu.linsolve: batch of one) ----------------------------------------
+// A batch of one leaves 31 lanes of every warp of k_klu_solve_lvl idle and pays its level barriers and its dependent
+// global loads for one matrix (ACTIVSg2000: 492 levels, 2 ms), and the level schedule itself costs more host time than the
+// solve.  Here the SEQUENTIAL algorithm of klu_solve / klu_tsolve (klu.c:593-690) is written down once per pattern as a
+// tape of column operations in execution order -- 'N': x_k (/= u_kk), x[rows] -= column * x_k (L columns ascending, U
+// columns descending, then the block's F columns; BTF blocks last to first); 'T': x_k = (x_k - column . x[rows]) (/ u_kk)
+// (U+F columns ascending, L columns descending; blocks first to last) -- O(nnz) to build, no sorting.  The work vector
+// lives in shared memory; the tape is cut into chunks of whole (or split) operations that warps 1..7 stage into a
+// double buffer (row index + factor value of the first matrix of the handle + reciprocal pivots: all static, so nothing
+// on the dependent chain touches global memory) while warp 0 runs the previous chunk, lanes across the entries of a column.
+constexpr int KLU_ONE_ENT = 2048, KLU_ONE_OPS = 512, KLU_ONE_THREADS = 256, KLU_ONE_MAXN = 16384;
+struct KluSolveOneD {
+    int n = 0, nchunks = 0;
+    const int4* ops = nullptr;      // {k, diagonal slot or -1, first entry relative to its chunk, entries}
+    const int2* ent = nullptr;      // {row, value slot}
+    const int2* chunk = nullptr;    // nchunks + 1: {first op, first entry}
+};
+struct KluSolveOneH { std::vector<int4> ops; std::vector<int2> ent, chunk; };
+
+static void build_solve_tape(const KluSymbolic& S, const KluNumeric& N, const KluPlan& P, bool trans, KluSolveOneH& H) {
+    H.ops.clear(); H.ent.clear(); H.chunk.assign(1, make_int2(0, 0));
+    int cops = 0, cent = 0;          // operations / entries of the open chunk
+    std::vector<int2> e;
+    // an operation longer than a chunk is cut into parts: 'N' parts re-read the finished x_k, 'T' parts subtract their partial
+    // dot products one after the other; the pivot goes with the first ('N') / last ('T') part
+    auto add_op = [&](int k, int diag) {
+        if (e.empty() && diag < 0) return;
+        const int total = (int)e.size();
+        int done = 0;
+        do {
+            const int cnt = std::min(total - done, KLU_ONE_ENT);
+            if (cops + 1 > KLU_ONE_OPS || cent + cnt > KLU_ONE_ENT) {
+                H.chunk.push_back(make_int2((int)H.ops.size(), (int)H.ent.size()));
+                cops = 0; cent = 0;
+            }
+            const bool first = done == 0, last = done + cnt == total;
+            H.ops.push_back(make_int4(k, (trans ? last : first) ? diag : -1, cent, cnt));
+            H.ent.insert(H.ent.end(), e.begin() + done, e.begin() + done + cnt);
+            cops++; cent += cnt; done += cnt;
+        } while (done < total);
+        e.clear();
+    };
+    auto Lcol = [&](int k) { for (long long p = N.Lp[k] + 1; p < N.Lp[k + 1]; p++) e.push_back(make_int2(N.Li[p], P.lslot0[k] + (int)(p - N.Lp[k] - 1))); };
+    auto Ucol = [&](int k) { for (long long p = N.Up[k]; p < N.Up[k + 1] - 1; p++) e.push_back(make_int2(N.Ui[p], (int)P.cbeg[k] + (int)(p - N.Up[k]))); };
+    auto Fcol = [&](int k) { for (long long p = N.Fp[k]; p < N.Fp[k + 1]; p++) e.push_back(make_int2(N.Fi[p], P.fslot0[k] + (int)(p - N.Fp[k]))); };
+    if (!trans)
+        for (int blk = S.nblocks - 1; blk >= 0; blk--) {
+            const int k1 = S.R[blk], k2 = S.R[blk + 1];
+            for (int k = k1; k < k2; k++) { Lcol(k); add_op(k, -1); }
+            for (int k = k2 - 1; k >= k1; k--) { Ucol(k); add_op(k, P.udiag_slot[k]); }
+            for (int k = k1; k < k2; k++) { Fcol(k); add_op(k, -1); }
+        }
+    else
+        for (int blk = 0; blk < S.nblocks; blk++) {
+            const int k1 = S.R[blk], k2 = S.R[blk + 1];
+            for (int k = k1; k < k2; k++) { Ucol(k); Fcol(k); add_op(k, P.udiag_slot[k]); }
+            for (int k = k2 - 1; k >= k1; k--) { Lcol(k); add_op(k, -1); }
+        }
+    H.chunk.push_back(make_int2((int)H.ops.size(), (int)H.ent.size()));
+}
+
+// x / d with the reciprocal taken off the dependent chain: one residual correction of q = x * (1/d)
+__device__ __forceinline__ double klu_div_rcp(double x, double d, double rd) {
+    const double q = x * rd;
+    return fma(fma(-q, d, x), rd, q);
+}
+
+template <bool TRANS>
+__global__ void __launch_bounds__(KLU_ONE_THREADS) k_klu_solve_one(KluSolveOneD T, int Bp, const double* __restrict__ LU, const double* __restrict__ Rs,
+                                                                    const int* __restrict__ pin, const int* __restrict__ pout,
+                                                                    double* __restrict__ B, long long ldB) {
+    extern __shared__ double smo[];
+    const int n = T.n, np = (n + 1) & ~1;
+    double* x = smo;                                              // n
+    double* sval = x + np;                                        // [2][KLU_ONE_ENT]
+    double* sdg = sval + 2 * KLU_ONE_ENT;                         // [2][KLU_ONE_OPS] pivots
+    double* srd = sdg + 2 * KLU_ONE_OPS;                          // [2][KLU_ONE_OPS] their reciprocals
+    int4* sop = reinterpret_cast<int4*>(srd + 2 * KLU_ONE_OPS);   // [2][KLU_ONE_OPS]
+    int* sidx = reinterpret_cast<int*>(sop + 2 * KLU_ONE_OPS);    // [2][KLU_ONE_ENT]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* b = B + (long long)blockIdx.x * ldB;
+    auto stage = [&](int c, int t, int nt) {
+        const int bf = c & 1;
+        const int2 c0 = T.chunk[c], c1 = T.chunk[c + 1];
+        const int nops = c1.x - c0.x, nent = c1.y - c0.y;
+        for (int i = t; i < nent; i += nt) {
+            const int2 en = T.ent[c0.y + i];
+            sidx[bf * KLU_ONE_ENT + i] = en.x;
+            sval[bf * KLU_ONE_ENT + i] = LU[(long long)en.y * 32];
+        }
+        for (int i = t; i < nops; i += nt) {
+            const int4 o = T.ops[c0.x + i];
+            const double d = o.y >= 0 ? LU[(long long)o.y * 32] : 1.0;
+            sop[bf * KLU_ONE_OPS + i] = o;
+            sdg[bf * KLU_ONE_OPS + i] = d;
+            srd[bf * KLU_ONE_OPS + i] = 1.0 / d;
+        }
+    };
+    for (int k = tid; k < n; k += KLU_ONE_THREADS) {
+        double v = b[pin[k]];
+        if (!TRANS) v /= Rs[(long long)k * Bp];
+        x[k] = v;
+    }
+    if (T.nchunks > 0) stage(0, tid, KLU_ONE_THREADS);
+    __syncthreads();
+    for (int c = 0; c < T.nchunks; c++) {
+        if (warp != 0) {
+            if (c + 1 < T.nchunks) stage(c + 1, tid - 32, KLU_ONE_THREADS - 32);
+        } else {
+            const int bf = c & 1;
+            const int nops = T.chunk[c + 1].x - T.chunk[c].x;
+            const int4* ops = sop + bf * KLU_ONE_OPS;
+            const double *dg = sdg + bf * KLU_ONE_OPS, *rd = srd + bf * KLU_ONE_OPS, *val = sval + bf * KLU_ONE_ENT;
+            const int* idx = sidx + bf * KLU_ONE_ENT;
+            // (fetching the next operation's first 32 entries ahead as well was measured slower: one warp is bound by the
+            // number of instructions on the chain, not by the shared-memory latency: 1.12 -> 1.22 ms on ACTIVSg2000)
+            int4 o = ops[0];
+            double d = dg[0], r = rd[0];
+            for (int i = 0; i < nops; i++) {
+                int4 on = o; double dn = d, rn = r;
+                if (i + 1 < nops) { on = ops[i + 1]; dn = dg[i + 1]; rn = rd[i + 1]; }
+                const int k = o.x, e0 = o.z, cnt = o.w;
+                if (!TRANS) {
+                    double xk = x[k];
+                    if (o.y >= 0) {
+                        xk = klu_div_rcp(xk, d, r);
+                        __syncwarp();                              // every lane has read x_k before lane 0 replaces it
+                        if (lane == 0) x[k] = xk;
+                    }
+                    for (int e = lane; e < cnt; e += 32) {
+                        const int row = idx[e0 + e];
+                        x[row] = fma(-val[e0 + e], xk, x[row]);
+                    }
+                } else {
+                    double s = 0.0;
+                    for (int e = lane; e < cnt; e += 32) s = fma(val[e0 + e], x[idx[e0 + e]], s);
+#pragma unroll
+                    for (int off = 16; off; off >>= 1)
+                        if (cnt > off) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0) {
+                        double xk = x[k] - s;
+                        if (o.y >= 0) xk = klu_div_rcp(xk, d, r);
+                        x[k] = xk;
+                    }
+                }
+                __syncwarp();
+                o = on; d = dn; r = rn;
+            }
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < n; k += KLU_ONE_THREADS) {
+        double v = x[k];
+        if (TRANS) v /= Rs[(long long)k * Bp];
+        b[pout[k]] = v;
+    }
+}
+// Host replay of the tape (test hook behind b200s_klu_solve_tape_host: the tape is verified without a GPU): the operations in
+// order on one right-hand side, exactly as warp 0 of k_klu_solve_one applies them (the sums of a 'T' operation in index order).
+int klu_solve_tape_host(const KluSymbolic& S, const KluNumeric& N, const KluPlan& P, int trans, const double* slots, double* B,
+                        long long nrhs, long long ldB) {
+    KluSolveOneH H;
+    build_solve_tape(S, N, P, trans != 0, H);
+    const int n = P.n;
+    std::vector<double> x((size_t)std::max(n, 1));
+    const int* pin = trans ? S.Q.data() : N.Pnum.data();
+    const int* pout = trans ? N.Pnum.data() : S.Q.data();
+    for (long long r = 0; r < nrhs; r++) {
+        double* b = B + r * ldB;
+        for (int k = 0; k < n; k++) x[k] = trans ? b[pin[k]] : b[pin[k]] / N.Rs[k];
+        for (size_t c = 0; c + 1 < H.chunk.size(); c++) {
+            if (H.chunk[c + 1].x - H.chunk[c].x > KLU_ONE_OPS || H.chunk[c + 1].y - H.chunk[c].y > KLU_ONE_ENT) return ST_INVALID;
+            for (int q = H.chunk[c].x; q < H.chunk[c + 1].x; q++) {
+                const int4 o = H.ops[q];
+                const int2* e = H.ent.data() + H.chunk[c].y + o.z;
+                if (H.chunk[c].y + o.z + o.w > H.chunk[c + 1].y) return ST_INVALID;
+                if (!trans) {
+                    if (o.y >= 0) x[o.x] /= slots[o.y];
+                    for (int i = 0; i < o.w; i++) x[e[i].x] -= slots[e[i].y] * x[o.x];
+                } else {
+                    double s = 0.0;
+                    for (int i = 0; i < o.w; i++) s += slots[e[i].y] * x[e[i].x];
+                    x[o.x] -= s;
+                    if (o.y >= 0) x[o.x] /= slots[o.y];
+                }
+            }
+        }
+        for (int k = 0; k < n; k++) b[pout[k]] = trans ? x[k] / N.Rs[k] : x[k];
+    }
+    return ST_OK;
+}
+
+static size_t klu_solve_one_smem(int n) {
+    return (size_t)((n + 1) & ~1) * 8 + 2 * (size_t)KLU_ONE_ENT * 12 + 2 * (size_t)KLU_ONE_OPS * 32;
+}
+
 __global__ void k_klu_gather_slots(const double* __restrict__ LU, int Bp, int b, long long nslots, double* __restrict__ out) {
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nslots; v += (long long)gridDim.x * blockDim.x)
         out[v] = LU[(long long)(b >> 5) * nslots * 32 + v * 32 + (b & 31)];
@@ -1161,6 +1357,8 @@ public:
     KluPlanD PD{};
     KluWaveD WD{};
     KluSolveLvlD SL[2] = {};          // [0] = 'N', [1] = 'T'
+    KluSolveOneD SO[2] = {};          // the tapes of the one-matrix solve (k_klu_solve_one)
+    bool solve_one_ok = true;         // B200S_KLU_SOLVE_ONE=0: a batch of one runs through the level kernel as well
     const int *d_Pnum = nullptr, *d_Q = nullptr;
     bool use_wave = false;
     long long lu_slots = 0;
@@ -1223,6 +1421,7 @@ public:
     }
     int init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S);
     int ensure_solve_levels(int tr);
+    int ensure_solve_tape(int tr);
     const KluPlan* hP = nullptr; const KluNumeric* hN = nullptr; const KluSymbolic* hS = nullptr;   // owned by the numeric object
     int ensure_batch(int b);
     int enqueue_refactor(const double* dv, long long ldv, cudaEvent_t after_transpose);
@@ -1255,6 +1454,7 @@ int KluDevice::init(const KluPlan& P, const KluNumeric& N, const KluSymbolic& S)
     if ((rc = up(&d_Pnum, N.Pnum))) return rc;
     if ((rc = up(&d_Q, S.Q))) return rc;
     hP = &P; hN = &N; hS = &S;       // the solve schedules are built at the first solve of each kind (ensure_solve_levels)
+    { const char* e1 = getenv("B200S_KLU_SOLVE_ONE"); solve_one_ok = !(e1 && e1[0] == '0'); }
     if (P.have_refactor) return init_refactor(P);
     return ST_OK;
 }
@@ -1392,6 +1592,18 @@ int KluDevice::ensure_solve_levels(int tr) {
     if ((rc = up(&SL[tr].tsrc, H.tsrc))) return rc;
     if ((rc = up(&SL[tr].extra, H.extra))) return rc;
     if ((rc = up(&SL[tr].mode, H.mode))) return rc;
+    return ST_OK;
+}
+
+int KluDevice::ensure_solve_tape(int tr) {
+    if (SO[tr].n == n && SO[tr].chunk) return ST_OK;
+    int rc;
+    KluSolveOneH H;
+    build_solve_tape(*hS, *hN, *hP, tr != 0, H);
+    SO[tr].n = n; SO[tr].nchunks = (int)H.chunk.size() - 1;
+    if ((rc = up(&SO[tr].ops, H.ops))) return rc;
+    if ((rc = up(&SO[tr].ent, H.ent))) return rc;
+    if ((rc = up(&SO[tr].chunk, H.chunk))) return rc;
     return ST_OK;
 }
 
@@ -1570,7 +1782,8 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
     if (batch_ <= 0 || n == 0 || nrhs <= 0) return ST_OK;
     if (batch_ > batch) { set_last_error("solve_batch: batch larger than the last refactored batch"); return ST_INVALID; }
     const long long bstride = ldB * nrhs;
-    const long long needX = 2ll * n * Bp * nrhs;      // V = [Y; Z] per right-hand side
+    const bool one = batch_ == 1 && solve_one_ok && n <= KLU_ONE_MAXN;
+    const long long needX = one ? 0 : 2ll * n * Bp * nrhs;      // V = [Y; Z] per right-hand side
     if (needX > capX) {
         pool_free(dX); dX = nullptr; capX = 0;
         CUDA_TRY(pool_malloc((void**)&dX, needX * sizeof(double)));
@@ -1590,7 +1803,18 @@ int KluDevice::solve(int trans, double* B, long long nrhs, long long ldB, long l
         CUDA_TRY(cudaMemcpyAsync(dB, B, hostB * sizeof(double), cudaMemcpyHostToDevice, stream));
         db = dB;
     }
-    {
+    if (one) {
+        // one matrix: the sequential tape, one CTA per right-hand side, permutations and row scaling inside the kernel
+        { const int rct = ensure_solve_tape(trans ? 1 : 0); if (rct) return rct; }
+        const size_t sm = klu_solve_one_smem(n);
+        if (trans) {
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_solve_one<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_klu_solve_one<true><<<(unsigned)nrhs, KLU_ONE_THREADS, sm, stream>>>(SO[1], Bp, dLU, dRs, d_Q, d_Pnum, db, ldB);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(k_klu_solve_one<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_klu_solve_one<false><<<(unsigned)nrhs, KLU_ONE_THREADS, sm, stream>>>(SO[0], Bp, dLU, dRs, d_Pnum, d_Q, db, ldB);
+        }
+    } else {
         { const int rcl = ensure_solve_levels(trans ? 1 : 0); if (rcl) return rcl; }
         const KluSolveLvlD& L_ = SL[trans ? 1 : 0];
         const dim3 tg((unsigned)((n + 31) / 32), (unsigned)(Bp / 32), (unsigned)nrhs);

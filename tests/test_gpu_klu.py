@@ -252,3 +252,34 @@ def test_solve_ldB_buffer_ends_with_the_last_column(klu):
     for j in range(2):
         mask[off + j * ld: off + j * ld + n] = False
     assert np.array_equal(buf[mask], keep[mask])
+
+
+@pytest.mark.parametrize("name", ["ACTIVSg2000", "bp_800", "bcsstk13", "arrow"])
+@pytest.mark.parametrize("trans", ["N", "T"])
+def test_one_matrix_solve_kernel_matches_level_kernel(klu, name, trans, monkeypatch):
+    """klu.solve on ONE matrix runs the sequential operation tape in one CTA per right-hand side (k_klu_solve_one); with
+    B200S_KLU_SOLVE_ONE=0 the same call goes through the batched level kernel (k_klu_solve_lvl).  Same factor, two summation
+    orders: the solutions agree to rounding and with SuperLU; 'arrow' has a column longer than one chunk of the tape."""
+    if name == "arrow":
+        n = 2600
+        rng = np.random.default_rng(3)
+        A = sp.lil_matrix((n, n)); A.setdiag(rng.uniform(2, 3, n))
+        A[n - 1, :] = rng.uniform(-1e-2, 1e-2, n); A[:, n - 1] = rng.uniform(-1e-2, 1e-2, (n, 1)); A[n - 1, n - 1] = 4.0
+        A = A.tocsc(); A.sort_indices()
+    else:
+        A = load_matrix(name)
+    n = A.shape[0]
+    B = np.random.default_rng(1).standard_normal((n, 5))
+    sols = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200S_KLU_SOLVE_ONE", flag)        # read when the numeric object is created
+        Fs = klu.symbolic(A); Fn = klu.numeric(A, Fs)
+        X = np.asfortranarray(B.copy())
+        klu.solve(A, Fs, Fn, X, trans=trans)
+        sols.append(X)
+    M = (A if trans == "N" else A.T).tocsc()
+    Xref = spla.splu(M).solve(B)
+    for X in sols:
+        assert np.linalg.norm(X - Xref) / np.linalg.norm(Xref) < 1e-10
+    assert np.linalg.norm(sols[0] - sols[1]) / np.linalg.norm(sols[1]) < 1e-12
+    assert not np.array_equal(sols[0], sols[1]) or name == "bcsstk13"      # two kernels really ran (different rounding)

@@ -486,6 +486,49 @@ def test_klu_wave_plan_replayed_on_the_host_matches_the_pivoting_factorization(n
     fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
 
 
+@pytest.mark.parametrize("name", ["ACTIVSg2000", "bp_800", "bcsstk13", "unsym_offdiag", "random", "arrow"])
+@pytest.mark.parametrize("trans", [0, 1])
+def test_klu_one_matrix_solve_tape_replayed_on_the_host(name, trans):
+    """The operation tape of the one-matrix solve kernel (k_klu_solve_one: klu_solve / klu_tsolve of klu.c:593-690 as column
+    operations in execution order, cut into shared-memory chunks) replayed by b200s_klu_solve_tape_host with the values of
+    the pivot search: A x = b ('N') and A' x = b ('T') to SuperLU's solution, several BTF blocks and off-diagonal pivots
+    included, a right-hand side with a leading dimension > n."""
+    import scipy.sparse.linalg as spla
+    if name == "unsym_offdiag":
+        rng = np.random.default_rng(11)
+        n = 400
+        A = (sp.random(n, n, density=0.02, random_state=rng) + sp.identity(n) * 1e-6 +
+             sp.csc_matrix((rng.uniform(1, 2, n), (rng.permutation(n), np.arange(n))), shape=(n, n))).tocsc()
+    elif name == "random":
+        A = _synthetic_unsym("random")
+    elif name == "arrow":             # a column of U and a row of L longer than one chunk of the tape: split operations
+        n = 2600
+        rng = np.random.default_rng(3)
+        A = sp.lil_matrix((n, n)); A.setdiag(rng.uniform(2, 3, n))
+        A[n - 1, :] = rng.uniform(-1e-2, 1e-2, n); A[:, n - 1] = rng.uniform(-1e-2, 1e-2, (n, 1)); A[n - 1, n - 1] = 4.0
+        A = A.tocsc()
+    else:
+        A = load_matrix(name).tocsc()
+    st, S, N, A = klu_pivot(A)
+    assert st == 0
+    n = A.shape[0]
+    if name == "arrow":
+        inf = L.KluInfo(); fn["b200s_klu_info"](N, C.byref(inf))
+        assert inf.nblocks == 1 and inf.nnz_U >= 2 * n - 1
+    ld = n + 3
+    rng = np.random.default_rng(5)
+    B = np.full((2, ld), np.nan); B[:, :n] = rng.standard_normal((2, n))
+    X = B.copy()
+    assert fn["b200s_klu_solve_tape_host"](N, trans, L.ptr_f64(X), 2, ld) == 0
+    assert np.isnan(X[:, n:]).all()                      # the padding rows are not touched
+    M = (A.T if trans else A).tocsc()
+    Xref = spla.splu(M).solve(B[:, :n].T).T
+    assert np.linalg.norm(X[:, :n] - Xref) / np.linalg.norm(Xref) < 1e-10
+    assert fn["b200s_klu_solve_tape_host"](N, 2, L.ptr_f64(X), 2, ld) == L.INVALID
+    assert fn["b200s_klu_solve_tape_host"](N, trans, L.ptr_f64(X), 2, n - 1) == L.INVALID
+    fn["b200s_klu_free_numeric"](N); fn["b200s_klu_free_symbolic"](S)
+
+
 @pytest.mark.parametrize("name", ["ACTIVSg2000", "bp_800", "unsym_offdiag", "random"])
 def test_klu_pivot_rule_against_an_independent_run(name):
     """The pivot RULE of the host pivot search (threshold partial pivoting, tol 1e-3, diagonal preferred, on the row-scaled
