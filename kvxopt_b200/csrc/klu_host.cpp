@@ -95,8 +95,18 @@ void klu_analyze(i64 n64, const i64* Ap, const i64* Ai64, KluSymbolic& S) {
     for (i64 p = 0; p < S.nnz; p++) S.Ai[p] = (i32)Ai64[p];
     const i32* Ai = S.Ai.data();
 
+    const bool tdbg = getenv("B200S_DEBUG") != nullptr;
+    auto tlast = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!tdbg) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200s klu analyze] %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tlast).count());
+        tlast = now;
+    };
+    lap("checks + copy");
     i32 nmatch = 0;
     std::vector<i32> match = max_transversal(n, Ap, Ai, nmatch);
+    lap("maximum transversal");
     S.structural_rank = nmatch;
     if (nmatch < n) {
         // structurally singular: complete the matching arbitrarily so that the permutations stay valid;
@@ -154,6 +164,7 @@ void klu_analyze(i64 n64, const i64* Ap, const i64* Ai64, KluSymbolic& S) {
     bstart.push_back(n);
     S.nblocks = nb;
     S.R.assign(bstart.begin(), bstart.end());
+    lap("strongly connected comp.");
     // per-block AMD on B + B' (B = diagonal block of C), applied symmetrically
     std::vector<i32> local(n, -1);
     for (i32 b = 0; b < nb; b++) {
@@ -163,25 +174,44 @@ void klu_analyze(i64 n64, const i64* Ap, const i64* Ai64, KluSymbolic& S) {
         for (i32 t = 0; t < nk; t++) local[order[k0 + t]] = t;
         SymPattern G;
         G.n = nk;
-        std::vector<std::vector<i32>> adj(nk);
+        // pattern of B + B' without the diagonal, as CSR built in two counting passes (duplicates removed per row after a sort
+        // of the short rows; a vector per row cost more than AMD itself on ACTIVSg2000)
+        std::vector<i64> rp((size_t)nk + 1, 0);
         for (i32 t = 0; t < nk; t++) {
             const i32 v = order[k0 + t], col = match[v];
             for (i64 p = Ap[col]; p < Ap[col + 1]; p++) {
                 const i32 w = Ai[p];
                 if (w == v || blockof[w] != b) continue;
-                adj[t].push_back(local[w]);
-                adj[local[w]].push_back(t);
+                rp[t + 1]++; rp[local[w] + 1]++;
+            }
+        }
+        for (i32 t = 0; t < nk; t++) rp[t + 1] += rp[t];
+        std::vector<i32> flat((size_t)rp[nk]);
+        {
+            std::vector<i64> cur(rp.begin(), rp.end() - 1);
+            for (i32 t = 0; t < nk; t++) {
+                const i32 v = order[k0 + t], col = match[v];
+                for (i64 p = Ap[col]; p < Ap[col + 1]; p++) {
+                    const i32 w = Ai[p];
+                    if (w == v || blockof[w] != b) continue;
+                    flat[cur[t]++] = local[w];
+                    flat[cur[local[w]]++] = t;
+                }
             }
         }
         G.ptr.assign(nk + 1, 0);
+        G.idx.reserve(flat.size());
         for (i32 t = 0; t < nk; t++) {
-            std::sort(adj[t].begin(), adj[t].end());
-            adj[t].erase(std::unique(adj[t].begin(), adj[t].end()), adj[t].end());
-            G.ptr[t + 1] = G.ptr[t] + (i64)adj[t].size();
+            i32* r0 = flat.data() + rp[t];
+            i32* r1 = flat.data() + rp[t + 1];
+            std::sort(r0, r1);
+            r1 = std::unique(r0, r1);
+            G.idx.insert(G.idx.end(), r0, r1);
+            G.ptr[t + 1] = (i64)G.idx.size();
         }
-        G.idx.reserve(G.ptr[nk]);
-        for (i32 t = 0; t < nk; t++) G.idx.insert(G.idx.end(), adj[t].begin(), adj[t].end());
+        if (nk > n / 2) lap("block graph");
         std::vector<i32> pl = amd_order(G);
+        if (nk > n / 2) lap("AMD of the block");
         std::vector<i32> neworder(nk);
         for (i32 t = 0; t < nk; t++) neworder[t] = order[k0 + pl[t]];
         std::copy(neworder.begin(), neworder.end(), order.begin() + k0);
