@@ -343,11 +343,16 @@ def bench_cholesky(nx, steps, fp64_peak, full=True):
     A = (Al + sp.tril(Al, -1).T).tocsr()
     berr = float(np.linalg.norm(A @ x - B[:, 0]) / (12.0 * np.linalg.norm(x) + np.linalg.norm(B)))
     # end to end through the public API with host buffers (H2D of values and RHS, D2H of the solution)
-    Xh = np.asfortranarray(B.copy())
-    t0 = time.perf_counter()
-    cholmod.numeric(Al, F)
-    cholmod.solve(F, Xh)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    # (one untimed pass first: the host-buffer entry points stage through their own buffers and record their own solve graph,
+    #  and the sweep-mode switch above rebuilt the solve schedules; then the best of two timed passes, tools/prof_chol_e2e.py)
+    e2e_all = []
+    for _ in range(3):
+        Xh = np.asfortranarray(B.copy())
+        t0 = time.perf_counter()
+        cholmod.numeric(Al, F)
+        cholmod.solve(F, Xh)
+        e2e_all.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = float(min(e2e_all[1:]))
     d = cholmod.factor_info(F)
     best_f, best_s = float(np.min(ms_f)), float(np.min(ms_s))
     out = {
@@ -357,7 +362,7 @@ def bench_cholesky(nx, steps, fp64_peak, full=True):
         "factor_ms": best_f, "solve_ms": best_s, "factor_plus_solve_ms": best_f + best_s,
         "factor_tflops": d["flops"] / (best_f * 1e-3) / 1e12,
         "solve_gbs": (16.0 * d["nnz_L"] + 16.0 * n) / (best_s * 1e-3) / 1e9,
-        "e2e_factor_plus_solve_ms_host_buffers": e2e_ms, "backward_error": berr,
+        "e2e_factor_plus_solve_ms_host_buffers": e2e_ms, "e2e_first_pass_ms_host_buffers": float(e2e_all[0]), "backward_error": berr,
         "solve_ms_launch_per_step": float(np.min(ms_s0)), "solve_bitwise_equal_both_paths": same_bits,
     }
     hbm, hbm_src, _ = measured_peaks()
