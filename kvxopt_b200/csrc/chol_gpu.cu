@@ -72,7 +72,9 @@ struct FrontD {
     int col0, nc, nr, ld;
     int nchild, childptr, parent, level;
 };
-struct EAItem { int front, c0, c1; };
+// one CTA of k_extend_add: the destination columns [c0, c1) of a front; [q_off, q_off + q_cnt) in the item-child list = the
+// positions (ascending: the order of summation) of the front's children that have an update column in that range
+struct EAItem { int front, c0, c1, q_off, q_cnt; };
 
 constexpr int NB = PLAN_NB;    // block-column width inside large fronts
 constexpr int TR = 64;         // rows per CTA in the panel triangular solve
@@ -176,7 +178,7 @@ __global__ void k_scatter_A(const double* __restrict__ val, const long long* __r
 __global__ void __launch_bounds__(256) k_extend_add(const EAItem* __restrict__ items, const FrontD* __restrict__ F,
                                                     const int* __restrict__ child_idx, const int* __restrict__ rel,
                                                     double* __restrict__ L, double* __restrict__ W,
-                                                    const unsigned char* __restrict__ owned) {
+                                                    const unsigned char* __restrict__ owned, const int* __restrict__ item_child) {
     const EAItem it = items[blockIdx.x];
     if (!owned[it.front]) return;
     const FrontD fp = F[it.front];
@@ -190,8 +192,10 @@ __global__ void __launch_bounds__(256) k_extend_add(const EAItem* __restrict__ i
         for (int r = c + lane; r < nr; r += 32) col[r] = 0.0;
     }
     __syncthreads();
-    for (int q = 0; q < fp.nchild; q++) {
-        const FrontD fc = F[child_idx[fp.childptr + q]];
+    // only the children that reach into [c0, c1) (a front of a KKT matrix can have thousands of one-entry children: every CTA
+    // of the root front of BASELINE config 5's 3 x 3 system looped over 18 800 of them, 44 of the 77 ms of that factorization)
+    for (int t = 0; t < it.q_cnt; t++) {
+        const FrontD fc = F[child_idx[fp.childptr + item_child[it.q_off + t]]];
         const int mc = fc.nr - fc.nc, uoc = fc.nc & 1;
         const int ldc = ((mc + uoc) + 1) & ~1;
         const int* rl = rel + fc.reloff;
@@ -1887,6 +1891,7 @@ public:
     std::vector<int> hsched;
     double* ddiag = nullptr;       // scratch for factored diagonal blocks of one panel launch
     EAItem* dea = nullptr;
+    int* dea_child = nullptr;      // item-child list of the extend-add items
     std::vector<LevelSched> levels;
     std::vector<SolveGroups> sgroups;   // sgroups[0] = empty (use the schedule arrays)
     std::map<int, cudaGraphExec_t> solve_graphs;   // key: columns * 4 + forward * 2 + backward
@@ -1929,7 +1934,7 @@ public:
         drop_graphs();
         pool_free(dL); pool_free(dW); pool_free(dval); pool_free(dT); pool_free(dX); pool_free(dBstage); pool_free(damap); pool_free(dF);
         pool_free(drows); pool_free(drel); pool_free(dchild); pool_free(dperm); pool_free(dlevel_fronts);
-        pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(ddiag); pool_free(dpart); pool_free(downed);
+        pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(dea_child); pool_free(ddiag); pool_free(dpart); pool_free(downed);
         pool_free(dreach); pool_free(dsp_i); pool_free(dsp_x); pool_free(dsp_cnt); pool_free(dsp_oi); pool_free(dsp_ox); pool_free(dsp_meta);
         for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
@@ -2053,6 +2058,7 @@ int CholDevice::init() {
     // ---- schedule
     std::vector<int>& sched = hsched;  // group arrays: [front ids...][prefix...] (host copy kept: the reach-restricted solve filters it)
     std::vector<EAItem> ea;
+    std::vector<int> ea_child;
     levels.resize(P.nlevels);
     sgroups.assign(1, SolveGroups());
     memset(&sgroups[0], 0, sizeof(SolveGroups));
@@ -2069,9 +2075,39 @@ int CholDevice::init() {
             int cbeg = nchild > 0 ? 0 : f.nc;
             long long acc = 0;
             int c0 = cbeg;
+            const size_t item0 = ea.size();
             for (int c = cbeg; c < f.nr; c++) {
                 acc += f.nr - c;
-                if (acc >= EA_TARGET || c == f.nr - 1) { ea.push_back({s, c0, c + 1}); c0 = c + 1; acc = 0; }
+                if (acc >= EA_TARGET || c == f.nr - 1) { ea.push_back({s, c0, c + 1, 0, 0}); c0 = c + 1; acc = 0; }
+            }
+            // per item the children with an update column inside it: two passes (count, fill) over the children in order, each
+            // child hopping from item to item through its sorted relative indices
+            const int nit = (int)(ea.size() - item0);
+            if (nchild > 0 && nit > 0) {
+                auto item_of = [&](int c) {          // the item whose range holds destination column c (ranges are consecutive from cbeg = 0)
+                    int lo = 0, hi = nit - 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ea[item0 + mid].c1 <= c) lo = mid + 1; else hi = mid; }
+                    return lo;
+                };
+                for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 1) {
+                        int off = (int)ea_child.size();
+                        for (int i = 0; i < nit; i++) { ea[item0 + i].q_off = off; off += ea[item0 + i].q_cnt; ea[item0 + i].q_cnt = 0; }
+                        ea_child.resize(off);
+                    }
+                    for (int q = 0; q < nchild; q++) {
+                        const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
+                        const int mc = fc.nr - fc.nc;
+                        const i32* rl = P.rel.data() + fc.reloff;
+                        int j = 0;
+                        while (j < mc) {
+                            EAItem& e = ea[item0 + item_of(rl[j])];
+                            if (pass == 1) ea_child[e.q_off + e.q_cnt] = q;
+                            e.q_cnt++;
+                            j = (int)(std::lower_bound(rl + j, rl + mc, e.c1) - rl);
+                        }
+                    }
+                }
             }
             if (f.nr <= SMALL_NR) {
                 int cls = f.nr <= 32 ? 0 : (f.nr <= 64 ? 1 : (f.nr <= 96 ? 2 : (f.nr <= 118 ? 3 : 4)));
@@ -2330,6 +2366,7 @@ int CholDevice::init() {
     lap("schedule build");
     if ((rc = upload(&dsched, sched.data(), sched.size()))) return rc;
     if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
+    if ((rc = upload(&dea_child, ea_child.data(), ea_child.size()))) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
     CUDA_TRY(cudaFuncSetAttribute(k_update<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
     CUDA_TRY(cudaFuncSetAttribute(k_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
@@ -2445,7 +2482,7 @@ int CholDevice::factor_level(int l, int phase) {
     const LevelSched& LS = levels[l];
     if (LS.ea_cnt) {
         prof_begin(0);
-        k_extend_add<<<LS.ea_cnt, 256, 0, stream>>>(dea + LS.ea_off, dF, dchild, drel, dL, dW, downed);
+        k_extend_add<<<LS.ea_cnt, 256, 0, stream>>>(dea + LS.ea_off, dF, dchild, drel, dL, dW, downed, dea_child);
         prof_end();
     }
     prof_begin(1);
