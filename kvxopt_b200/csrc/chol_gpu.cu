@@ -937,7 +937,8 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list
                                                     const FrontD* __restrict__ F,
                                                     const int* __restrict__ child_idx, const int* __restrict__ rel,
                                                     double* __restrict__ T, long long tstride, const double* __restrict__ X,
-                                                    long long xstride, const unsigned char* __restrict__ owned = nullptr) {
+                                                    long long xstride, const int2* __restrict__ chunk_q, const int* __restrict__ chunk_child,
+                                                    const unsigned char* __restrict__ owned = nullptr) {
     const int g = find_group(cprefix, nfronts, blockIdx.x);
     if (owned && !owned[list[g]]) return;
     const FrontD f = F[list[g]];
@@ -947,8 +948,11 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list
     const int nc = f.nc, tid = threadIdx.x;
     for (int i = a + tid; i < b; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
     __syncthreads();
-    for (int q = 0; q < f.nchild; q++) {
-        const FrontD fc = F[child_idx[f.childptr + q]];
+    // chunk_q[CTA] = {first, count} in chunk_child: the positions (ascending) of the children with an update row in [a, b) -- the
+    // root front of a 3 x 3 KKT matrix has thousands of one-row children, each of which concerns one chunk
+    const int2 qc = chunk_q[blockIdx.x];
+    for (int t_ = 0; t_ < qc.y; t_++) {
+        const FrontD fc = F[child_idx[f.childptr + chunk_child[qc.x + t_]]];
         const int mc = fc.nr - fc.nc;
         const int* rl = rel + fc.reloff;
         const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
@@ -1869,6 +1873,7 @@ struct LevelSched {
     Launch syrk;
     std::vector<Launch> sfwd, sbwd;   // triangular solves of large fronts: row tiles per block step
     Launch gfwd;                      // forward gather of large fronts: GATHER_ROWS-row chunks
+    int gq_off = 0;                   // first chunk of this level in the chunk-child table
     Launch sbig;                      // the fronts the SOLVES treat as large (one entry each): panel[0] minus the one-block fronts with few rows
     int small_all_off = 0, small_all_cnt = 0;
     int pgi = -1, pctas = 0;          // persistent sweeps (one right-hand side): index in CholDevice::plevels, CTAs
@@ -1892,6 +1897,8 @@ public:
     double* ddiag = nullptr;       // scratch for factored diagonal blocks of one panel launch
     EAItem* dea = nullptr;
     int* dea_child = nullptr;      // item-child list of the extend-add items
+    int2* dgq = nullptr;           // chunk-child lists of the forward gather (k_fwd_gather)
+    int* dgq_child = nullptr;
     std::vector<LevelSched> levels;
     std::vector<SolveGroups> sgroups;   // sgroups[0] = empty (use the schedule arrays)
     std::map<int, cudaGraphExec_t> solve_graphs;   // key: columns * 4 + forward * 2 + backward
@@ -1934,7 +1941,7 @@ public:
         drop_graphs();
         pool_free(dL); pool_free(dW); pool_free(dval); pool_free(dT); pool_free(dX); pool_free(dBstage); pool_free(damap); pool_free(dF);
         pool_free(drows); pool_free(drel); pool_free(dchild); pool_free(dperm); pool_free(dlevel_fronts);
-        pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(dea_child); pool_free(ddiag); pool_free(dpart); pool_free(downed);
+        pool_free(dsched); pool_free(dminor); pool_free(dea); pool_free(dea_child); pool_free(dgq); pool_free(dgq_child); pool_free(ddiag); pool_free(dpart); pool_free(downed);
         pool_free(dreach); pool_free(dsp_i); pool_free(dsp_x); pool_free(dsp_cnt); pool_free(dsp_oi); pool_free(dsp_ox); pool_free(dsp_meta);
         for (auto& e : ev_sp) if (e) cudaEventDestroy(e);
         pool_free(dMinv); pool_free(dinv_front); pool_free(dinv_kb); pool_free(ddiagL); pool_free(dsgn);
@@ -2059,6 +2066,8 @@ int CholDevice::init() {
     std::vector<int>& sched = hsched;  // group arrays: [front ids...][prefix...] (host copy kept: the reach-restricted solve filters it)
     std::vector<EAItem> ea;
     std::vector<int> ea_child;
+    std::vector<int2> gq;          // k_fwd_gather: per chunk {first, count} in gq_child
+    std::vector<int> gq_child;
     levels.resize(P.nlevels);
     sgroups.assign(1, SolveGroups());
     memset(&sgroups[0], 0, sizeof(SolveGroups));
@@ -2171,6 +2180,33 @@ int CholDevice::init() {
             std::vector<int> cnt;
             for (int s : sbigs) cnt.push_back((P.fronts[s].nr + GATHER_ROWS - 1) / GATHER_ROWS);
             emit(LS.gfwd, sbigs, cnt);
+            // per gather chunk (= CTA of k_fwd_gather, in launch order) the children with an update row inside it
+            LS.gq_off = (int)gq.size();
+            for (size_t fi = 0; fi < sbigs.size(); fi++) {
+                const int s = sbigs[fi], nch = cnt[fi], nchild = P.child_ptr[s + 1] - P.child_ptr[s];
+                const size_t q0 = gq.size();
+                gq.resize(q0 + nch, make_int2(0, 0));
+                for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 1) {
+                        int off = (int)gq_child.size();
+                        for (int i = 0; i < nch; i++) { gq[q0 + i].x = off; off += gq[q0 + i].y; gq[q0 + i].y = 0; }
+                        gq_child.resize(off);
+                    }
+                    for (int q = 0; q < nchild; q++) {
+                        const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
+                        const int mc = fc.nr - fc.nc;
+                        const i32* rl = P.rel.data() + fc.reloff;
+                        int j = 0;
+                        while (j < mc) {
+                            const int ch = rl[j] / GATHER_ROWS;
+                            int2& e = gq[q0 + ch];
+                            if (pass == 1) gq_child[e.x + e.y] = q;
+                            e.y++;
+                            j = (int)(std::lower_bound(rl + j, rl + mc, (ch + 1) * GATHER_ROWS) - rl);
+                        }
+                    }
+                }
+            }
             emit(LS.sbig, sbigs, std::vector<int>(sbigs.size(), 1));
         }
         LS.small_all_off = LS.small_off[0];
@@ -2367,6 +2403,8 @@ int CholDevice::init() {
     if ((rc = upload(&dsched, sched.data(), sched.size()))) return rc;
     if ((rc = upload(&dea, ea.data(), ea.size()))) return rc;
     if ((rc = upload(&dea_child, ea_child.data(), ea_child.size()))) return rc;
+    if ((rc = upload(&dgq, gq.data(), gq.size()))) return rc;
+    if ((rc = upload(&dgq_child, gq_child.data(), gq_child.size()))) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PANEL));
     CUDA_TRY(cudaFuncSetAttribute(k_update<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
     CUDA_TRY(cudaFuncSetAttribute(k_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_UPDATE));
@@ -2787,7 +2825,7 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     } else if (LS.small_all_cnt)
                         k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
                     if (LS.sbig.ng) {
-                        k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n);
+                        k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, dgq + LS.gq_off, dgq_child);
                         if (pfwd && LS.pgi >= 0)
                             launch_persist(LS.pctas, k_fwd_persist, plevels[LS.pgi], (const double*)dL, (const double*)dMinv, dT, dX, dsync, herr,
                                            (persist_dbg && plevels[LS.pgi].nf == 1 && l == P.nlevels - 1) ? persist_dbg : (long long*)nullptr);
@@ -2919,7 +2957,7 @@ int CholDevice::solve_dist_level(int backward, int l) {
         if (LS.small_all_cnt)
             k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n, downed);
         if (LS.sbig.ng) {
-            k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, downed);
+            k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, dgq + LS.gq_off, dgq_child, downed);
             for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
                 const Launch& la = LS.sfwd[kb];
                 k_fwd_diag<<<dim3(la.ng, nc), 256, SMEM_SDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, (int)kb, dF, dL, dMinv, dT, tstride, dX, n, downed);

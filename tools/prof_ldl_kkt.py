@@ -24,3 +24,12 @@ for prof in (0, 1):
         i = L.CholInfo(); L.fn["b200s_chol_info"](hF, C.byref(i))
         print("profiling %d: n %d nsuper %d nnz(L) %.3e flops %.3e | total %.2f ms (h2d %.2f assemble %.2f factor %.2f) | ext %.2f small %.2f panel %.2f upd %.2f | levels %d" % (
             prof, i.n, i.nsuper, i.nnz_L, i.flops, i.ms_total, i.ms_h2d, i.ms_assemble, i.ms_factor, i.ms_extend, i.ms_potrf, i.ms_trsm, i.ms_dense_update, i.nlevels), flush=True)
+L.fn["b200s_chol_set_profiling"](hF, 0)
+solve = f3(W, Pk)
+n = Pk.size[0]
+rng = np.random.default_rng(1)
+for _ in range(3):
+    x, y, z = matrix(rng.standard_normal(n)), matrix(0.0, (0, 1)), matrix(rng.standard_normal(m))
+    solve(x, y, z)
+    i = L.CholInfo(); L.fn["b200s_chol_info"](hF, C.byref(i))
+    print("solve: device %.2f ms" % i.ms_solve, flush=True)
