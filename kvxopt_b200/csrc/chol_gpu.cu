@@ -932,6 +932,7 @@ __global__ void __launch_bounds__(128) k_diag_inverse(const int* __restrict__ bl
 // forward: t = [x(cols); 0] + children's update vectors.  One CTA per GATHER_ROWS-row chunk of a front: a child's relative
 // indices ascend, so the entries that fall into the chunk are a contiguous run found by binary search; children are
 // applied one after the other (deterministic sums).
+constexpr int GATHER_SINGLE = 0x40000000;   // chunk-child entry: the child has exactly one update row
 constexpr int GATHER_ROWS = 512;       // (2048: the top levels ran 8-40 CTAs of 8 dependent rounds per child, ~30 us per launch)
 __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list, const int* __restrict__ cprefix, int nfronts,
                                                     const FrontD* __restrict__ F,
@@ -949,21 +950,50 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const int* __restrict__ list
     for (int i = a + tid; i < b; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
     __syncthreads();
     // chunk_q[CTA] = {first, count} in chunk_child: the positions (ascending) of the children with an update row in [a, b) -- the
-    // root front of a 3 x 3 KKT matrix has thousands of one-row children, each of which concerns one chunk
+    // root front of a 3 x 3 KKT matrix has thousands of one-row children, each of which concerns one chunk.  Children with ONE
+    // update row carry GATHER_SINGLE: a run of up to 256 of them is fetched by 256 threads at once (one latency instead of one
+    // per child and no barrier per child), then every thread adds, in child order, the values that land on the two rows it
+    // owns; the other children are added by the whole CTA, one after the other.  Sums stay in child order either way.
+    __shared__ int s_first, s_code, s_row[256];
+    __shared__ double s_val[256];
     const int2 qc = chunk_q[blockIdx.x];
-    for (int t_ = 0; t_ < qc.y; t_++) {
-        const FrontD fc = F[child_idx[f.childptr + chunk_child[qc.x + t_]]];
-        const int mc = fc.nr - fc.nc;
-        const int* rl = rel + fc.reloff;
-        const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
-        int lo = 0, hi = mc;                       // first entry with rl >= a
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < a) lo = mid + 1; else hi = mid; }
-        for (int i = lo + tid; i < mc; i += 256) {
-            const int d = rl[i];
-            if (d >= b) break;
-            t[d] += tc[i];
-        }
+    int t_ = 0;
+    while (t_ < qc.y) {
+        if (tid == 0) s_first = 256;
         __syncthreads();
+        const int myq = t_ + tid;
+        const int code = myq < qc.y ? chunk_child[qc.x + myq] : 0;
+        if (!(myq < qc.y && (code & GATHER_SINGLE))) atomicMin(&s_first, tid);
+        if (tid == 0) s_code = code;
+        __syncthreads();
+        const int nrun = s_first;
+        if (nrun > 0) {
+            if (tid < nrun) {
+                const FrontD fc = F[child_idx[f.childptr + (code & ~GATHER_SINGLE)]];
+                s_row[tid] = rel[fc.reloff];
+                s_val[tid] = T[blockIdx.y * tstride + fc.rowptr + fc.nc];
+            }
+            __syncthreads();
+            for (int k = 0; k < nrun; k++) {
+                const int d = s_row[k];
+                if (((d - a) & 255) == tid) t[d] += s_val[k];
+            }
+            t_ += nrun;
+        } else {
+            const FrontD fc = F[child_idx[f.childptr + (s_code & ~GATHER_SINGLE)]];
+            const int mc = fc.nr - fc.nc;
+            const int* rl = rel + fc.reloff;
+            const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
+            int lo = 0, hi = mc;                       // first entry with rl >= a
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < a) lo = mid + 1; else hi = mid; }
+            for (int i = lo + tid; i < mc; i += 256) {
+                const int d = rl[i];
+                if (d >= b) break;
+                t[d] += tc[i];
+            }
+            t_ += 1;
+            __syncthreads();        // s_first / s_code are rewritten at the top of the loop
+        }
     }
 }
 // backward: t = x(rows of the front)
@@ -2200,7 +2230,7 @@ int CholDevice::init() {
                         while (j < mc) {
                             const int ch = rl[j] / GATHER_ROWS;
                             int2& e = gq[q0 + ch];
-                            if (pass == 1) gq_child[e.x + e.y] = q;
+                            if (pass == 1) gq_child[e.x + e.y] = mc == 1 ? (q | GATHER_SINGLE) : q;
                             e.y++;
                             j = (int)(std::lower_bound(rl + j, rl + mc, (ch + 1) * GATHER_ROWS) - rl);
                         }

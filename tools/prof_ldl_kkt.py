@@ -33,3 +33,8 @@ for _ in range(3):
     solve(x, y, z)
     i = L.CholInfo(); L.fn["b200s_chol_info"](hF, C.byref(i))
     print("solve: device %.2f ms" % i.ms_solve, flush=True)
+if os.environ.get("PROF_SOLVE_NCU"):      # ncu --profile-from-start off: the launch list of ONE solve (B200S_NO_GRAPH=1)
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    x, y, z = matrix(rng.standard_normal(n)), matrix(0.0, (0, 1)), matrix(rng.standard_normal(m))
+    rt.cudaProfilerStart(); solve(x, y, z); rt.cudaProfilerStop()
