@@ -364,6 +364,19 @@ b200s_status b200s_kkt_info(const b200s_kkt* K, b200s_kkt_info_t* info);
 b200s_status b200s_kkt_plan_check_host(const b200s_kkt* K, const double* di, const double* Hx, double* Sx);
 void b200s_kkt_free(b200s_kkt* K);
 
+/* ---- value assembler: y = M w on the device, M a fixed sparse matrix in CSR ------------------------------------------------------
+ * For the KKT plug-ins that assemble their matrix outside the library (kvxopt_b200.kkt.ldl2: the dense syrk / gemm assembly of
+ * misc.kkt_ldl2, misc.py:1160-1178, as a sparse linear map from w = [W['di']^2; values of H; values of A] to the stored entries
+ * of K).  create uploads M once per pattern; apply uploads w (ncols doubles, host), evaluates y (nrows) on the device -- one
+ * thread per row, terms in list order -- and returns the device pointer (valid until the next apply or free), ready for
+ * b200s_chol_factorize_dev; get copies the last y to the host (tests). */
+typedef struct b200s_spmv b200s_spmv;
+b200s_status b200s_spmv_create(b200s_int nrows, b200s_int ncols, const b200s_int* rowptr, const b200s_int* colind, const double* val,
+                               b200s_spmv** out);
+b200s_status b200s_spmv_apply(b200s_spmv* M, const double* w_host, double** y_dev_out);
+b200s_status b200s_spmv_get(b200s_spmv* M, double* y_host);
+void b200s_spmv_free(b200s_spmv* M);
+
 /* ---- dense reduced KKT solver: the GPU counterpart of misc.kkt_chol, the 'chol' kktsolver ----------------------------
  * (reference src/python/misc.py:1213-1349).  G ml x n and A p x n are dense column-major.  create: QR of A' on the host
  * once per problem (misc.py:1246-1251), kept as compact WY.  factor(di, H): K = [Q1 Q2]'(H + G' diag(di)^2 G)[Q1 Q2] and the

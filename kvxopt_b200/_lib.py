@@ -115,6 +115,10 @@ SIGNATURES = {
     "b200s_kkt_info": (C.c_int, vp, C.POINTER(KktInfo)),
     "b200s_kkt_plan_check_host": (C.c_int, vp, p_f64, p_f64, p_f64),
     "b200s_kkt_free": (None, vp),
+    "b200s_spmv_create": (C.c_int, i64, i64, p_i64, p_i64, p_f64, C.POINTER(vp)),
+    "b200s_spmv_apply": (C.c_int, vp, p_f64, C.POINTER(vp)),
+    "b200s_spmv_get": (C.c_int, vp, p_f64),
+    "b200s_spmv_free": (None, vp),
     "b200s_kktd_create": (C.c_int, i64, i64, i64, p_f64, p_f64, C.POINTER(vp)),
     "b200s_kktd_factor": (C.c_int, vp, p_f64, p_f64, p_i64),
     "b200s_kktd_solve": (C.c_int, vp, p_f64, p_f64, p_f64),

@@ -528,3 +528,96 @@ b200s_status b200s_kkt_plan_check_host(const b200s_kkt* K, const double* di, con
 }
 
 }  // extern "C"
+
+
+/* ---- value assembler: y = M w on the device, M a fixed sparse matrix in CSR (include/b200sparse.h: b200s_spmv_*) ---------------
+ * The KKT plug-ins whose matrix is assembled outside this file (kkt.ldl2: K = [[H + G' D^2 G, A'], [A, 0]]) write every stored
+ * entry of K as a fixed linear combination of the numbers that change per interior-point iteration (w = [d^2; H values; A
+ * values]); the combination is evaluated here, one thread per entry, terms in list order (deterministic sums), and the result
+ * stays in device memory for b200s_chol_factorize_dev. */
+namespace {
+__global__ void k_spmv_rows(long long nrows, const long long* __restrict__ rowptr, const int* __restrict__ colind,
+                            const double* __restrict__ val, const double* __restrict__ w, double* __restrict__ y) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nrows; r += (long long)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (long long t = rowptr[r]; t < rowptr[r + 1]; t++) v = fma(val[t], w[colind[t]], v);
+        y[r] = v;
+    }
+}
+}  // namespace
+
+struct b200s_spmv {
+    i64 nrows = 0, ncols = 0, nnz = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long* d_rowptr = nullptr;
+    int* d_colind = nullptr;
+    double *d_val = nullptr, *d_w = nullptr, *d_y = nullptr;
+    ~b200s_spmv() {
+        cudaSetDevice(device);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        pool_free(d_rowptr); pool_free(d_colind); pool_free(d_val); pool_free(d_w); pool_free(d_y);
+    }
+};
+
+static int spmv_create_impl(b200s_spmv& M, const b200s_int* rowptr, const b200s_int* colind, const double* val) {
+    CUDA_TRY(cudaSetDevice(M.device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&M.stream, cudaStreamNonBlocking));
+    std::vector<long long> rp(rowptr, rowptr + M.nrows + 1);
+    std::vector<int> ci((size_t)M.nnz);
+    for (i64 t = 0; t < M.nnz; t++) ci[t] = (int)colind[t];
+    std::vector<double> vx(val, val + M.nnz);
+    int rc;
+    if ((rc = up(&M.d_rowptr, rp))) return rc;
+    if ((rc = up(&M.d_colind, ci))) return rc;
+    if ((rc = up(&M.d_val, vx))) return rc;
+    CUDA_TRY(pool_malloc((void**)&M.d_w, std::max<i64>(M.ncols, 1) * sizeof(double)));
+    CUDA_TRY(pool_malloc((void**)&M.d_y, std::max<i64>(M.nrows, 1) * sizeof(double)));
+    return ST_OK;
+}
+
+b200s_status b200s_spmv_create(b200s_int nrows, b200s_int ncols, const b200s_int* rowptr, const b200s_int* colind, const double* val,
+                               b200s_spmv** out) {
+    if (!out) return B200S_INVALID;
+    *out = nullptr;
+    if (nrows < 0 || ncols < 0 || nrows > 0x7fffffff - 16 || ncols > 0x7fffffff - 16 || !rowptr || rowptr[0] != 0) return B200S_INVALID;
+    const i64 nnz = rowptr[nrows];
+    if (nnz < 0 || (nnz > 0 && (!colind || !val))) return B200S_INVALID;
+    for (i64 r = 0; r < nrows; r++) if (rowptr[r + 1] < rowptr[r]) { set_last_error("spmv: row pointers must be nondecreasing"); return B200S_INVALID; }
+    for (i64 t = 0; t < nnz; t++) if (colind[t] < 0 || colind[t] >= ncols) { set_last_error("spmv: column index out of range"); return B200S_INVALID; }
+    if (device_count() <= 0) return B200S_NO_DEVICE;
+    b200s_spmv* M = new (std::nothrow) b200s_spmv();
+    if (!M) return B200S_OUT_OF_MEMORY;
+    M->nrows = nrows; M->ncols = ncols; M->nnz = nnz; M->device = current_device();
+    int rc;
+    try { rc = spmv_create_impl(*M, rowptr, colind, val); }
+    catch (const std::bad_alloc&) { rc = ST_OOM; }
+    if (rc != ST_OK) { delete M; return (b200s_status)rc; }
+    *out = M;
+    return B200S_OK;
+}
+
+static int spmv_apply_impl(b200s_spmv* M, const double* w_host, double** y_dev) {
+    B200S_NVTX("spmv_apply");
+    CUDA_TRY(cudaSetDevice(M->device));
+    if (M->ncols) CUDA_TRY(cudaMemcpyAsync(M->d_w, w_host, M->ncols * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+    if (M->nrows) {
+        const int grid = (int)std::max<i64>(1, std::min<i64>((M->nrows + 255) / 256, 148 * 8));
+        k_spmv_rows<<<grid, 256, 0, M->stream>>>(M->nrows, M->d_rowptr, M->d_colind, M->d_val, M->d_w, M->d_y);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(M->stream));
+    *y_dev = M->d_y;
+    return ST_OK;
+}
+b200s_status b200s_spmv_apply(b200s_spmv* M, const double* w_host, double** y_dev_out) {
+    if (!M || !y_dev_out || (M->ncols > 0 && !w_host)) return B200S_INVALID;
+    return (b200s_status)spmv_apply_impl(M, w_host, y_dev_out);
+}
+b200s_status b200s_spmv_get(b200s_spmv* M, double* y_host) {
+    if (!M || (M->nrows > 0 && !y_host)) return B200S_INVALID;
+    if (cudaSetDevice(M->device) != cudaSuccess) return B200S_CUDA_ERROR;
+    if (M->nrows && cudaMemcpy(y_host, M->d_y, M->nrows * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return B200S_CUDA_ERROR;
+    return B200S_OK;
+}
+void b200s_spmv_free(b200s_spmv* M) { delete M; }

@@ -244,6 +244,16 @@ def chol(G, dims, A, mnl=0):
     return factor
 
 
+class _SpmvHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            fn["b200s_spmv_free"](self.h)
+            self.h = None
+
+
 class _CholHandle:
     def __init__(self, h):
         self.h = h
@@ -429,8 +439,9 @@ def ldl2(G, dims, A, mnl=0):
     Cholesky factorization of S, the y pivots those of -A S^-1 A').  The reference forms K densely (sytrf, or potrf when
     there are no equalities).  Unlike kkt.chol2 there is no dense p x p Schur complement, so problems with many equality
     constraints stay sparse.  Componentwise inequalities only (dims['q'], dims['s'] empty, mnl = 0).  The pattern of K and the
-    list of products g_ki g_kj behind every entry of G'D^2 G are built once; factor() evaluates the values (numpy) and
-    sends them; solve() is two sparse products with G on the host around one host-buffer solve.  No CPU fallback."""
+    list of products g_ki g_kj behind every entry of G'D^2 G are built once; factor() sends di^2 and the values of H and A, the
+    entries of K are evaluated on the device (b200s_spmv_apply: K's values as a fixed sparse linear map of those numbers) and
+    factored where they are; solve() is two sparse products with G on the host around one host-buffer solve.  No CPU fallback."""
     import scipy.sparse as sp
     if dims["q"] or dims["s"]:
         raise ValueError("kvxopt_b200.kkt.ldl2 is implemented only for problems with no second-order or semidefinite "
@@ -511,9 +522,19 @@ def ldl2(G, dims, A, mnl=0):
         st = fn["b200s_chol_analyze"](N, L.ptr_i64(kp), L.ptr_i64(ki), b"L", L.ptr_i64(perm), C.byref(o), C.byref(h))
         if st != L.OK:
             _raise(st)
-        state.update(handle=_CholHandle(h), Hnnz=(nh if H is not None else None), keep=keep, kp=kp, ki=ki,
-                     tslot=slot[:nt], tk=tk, tc=tc, hslot=slot[nt:nt + nh], aslot=slot[nt + nh + n:nt + nh + n + len(Ai)],
-                     nk=len(uniq), kv=np.zeros(len(uniq)), u=np.zeros(N))
+        # the stored entries of K as a fixed linear map of w = [di^2; values of H (lower); values of A], evaluated on the device
+        # (b200s_spmv_*): rows = entries of K in CCS order, terms in the order [G'D^2G products, H, A] within a row
+        na = len(Ai)
+        trow = np.concatenate([slot[:nt], slot[nt:nt + nh], slot[nt + nh + n:nt + nh + n + na]]).astype(np.int64)
+        tcol = np.concatenate([tk, m + np.arange(nh), m + nh + np.arange(na)]).astype(np.int64)
+        tval = np.concatenate([tc, np.ones(nh + na)])
+        order = np.argsort(trow, kind="stable")
+        mp = np.zeros(len(uniq) + 1, dtype=np.int64)
+        np.add.at(mp, trow + 1, 1)
+        mp = np.cumsum(mp)
+        state.update(handle=_CholHandle(h), asm=None, Hnnz=(nh if H is not None else None), keep=keep, kp=kp, ki=ki,
+                     asm_csr=(np.ascontiguousarray(mp), np.ascontiguousarray(tcol[order]), np.ascontiguousarray(tval[order])),
+                     nk=len(uniq), w=np.zeros(m + nh + na), u=np.zeros(N))
 
     def factor(W, H=None, Df=None):
         if Df is not None:
@@ -524,17 +545,25 @@ def ldl2(G, dims, A, mnl=0):
             raise ValueError("H must be given in every call or in none")
         di = np.ascontiguousarray(_vec(W["di"], m, "W['di']") if m else np.zeros(0), dtype=np.float64)
         d2 = di * di
-        kv = np.bincount(state["tslot"], weights=state["tc"] * d2[state["tk"]], minlength=state["nk"]) if len(state["tk"]) \
-            else np.zeros(state["nk"])
+        w = state["w"]
+        w[:m] = d2
         if H is not None:
-            Hx = _checked_values(H, state["Hpat"])[state["keep"]]
-            np.add.at(kv, state["hslot"], Hx)
-        kv[state["aslot"]] = Ax
-        kv = np.ascontiguousarray(kv)
-        state["kv"] = kv
+            w[m:m + state["Hnnz"]] = _checked_values(H, state["Hpat"])[state["keep"]]
+        w[len(w) - len(Ax):] = Ax
+        if state["asm"] is None:                 # the map goes to the device once per pattern
+            mp, mc, mv = state["asm_csr"]
+            hm = C.c_void_p()
+            st = fn["b200s_spmv_create"](state["nk"], len(w), L.ptr_i64(mp), L.ptr_i64(mc), L.ptr_f64(mv), C.byref(hm))
+            if st != L.OK:
+                _raise(st)
+            state["asm"] = _SpmvHandle(hm)
+        kv_dev = C.c_void_p()
+        st = fn["b200s_spmv_apply"](state["asm"].h, L.ptr_f64(w), C.byref(kv_dev))        # K's values, assembled in HBM
+        if st != L.OK:
+            _raise(st)
         handle = state["handle"]
         minor = C.c_int64(0)
-        st = fn["b200s_chol_factorize"](handle.h, None, None, L.ptr_f64(kv), C.byref(minor))
+        st = fn["b200s_chol_factorize_dev"](handle.h, kv_dev, C.byref(minor))
         state["factors"] = state.get("factors", 0) + 1
         if st == L.NOT_POSDEF:
             raise ArithmeticError("zero pivot in the LDL' factorization of the KKT matrix (column %d)" % minor.value)

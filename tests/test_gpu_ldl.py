@@ -279,3 +279,30 @@ def test_boeing2_ipm_with_sparse_ldl2(kvx):
     assert sol["status"] == "optimal"
     assert sol["iterations"] == int(z["iters_ldl"])
     assert abs(sol["primal objective"] - float(z["pobj_ldl"])) <= 1e-8 * abs(float(z["pobj_ldl"]))
+
+
+def test_value_assembler_matches_scipy():
+    """b200s_spmv_*: y = M w on the device (the linear map from [di^2; H; A] to the stored entries of K that kkt.ldl2 uses),
+    against scipy; rows without terms give 0; bad indices are rejected."""
+    import ctypes as C
+    import scipy.sparse as sp
+    from kvxopt_b200 import _lib as L
+    fn = L.fn
+    rng = np.random.default_rng(4)
+    M = sp.random(5000, 700, density=0.004, random_state=rng, format="csr"); M.sort_indices()
+    rp = M.indptr.astype(np.int64); ci = M.indices.astype(np.int64); vx = M.data.astype(np.float64)
+    h = C.c_void_p()
+    assert fn["b200s_spmv_create"](M.shape[0], M.shape[1], L.ptr_i64(rp), L.ptr_i64(ci), L.ptr_f64(vx), C.byref(h)) == 0
+    for _ in range(2):
+        w = rng.standard_normal(M.shape[1])
+        yd = C.c_void_p()
+        assert fn["b200s_spmv_apply"](h, L.ptr_f64(w), C.byref(yd)) == 0 and yd.value
+        y = np.full(M.shape[0], np.nan)
+        assert fn["b200s_spmv_get"](h, L.ptr_f64(y)) == 0
+        ref = M @ w
+        assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+        assert (y[np.diff(rp) == 0] == 0).all()
+    fn["b200s_spmv_free"](h)
+    bad = ci.copy(); bad[3] = M.shape[1]
+    h2 = C.c_void_p()
+    assert fn["b200s_spmv_create"](M.shape[0], M.shape[1], L.ptr_i64(rp), L.ptr_i64(bad), L.ptr_f64(vx), C.byref(h2)) == L.INVALID

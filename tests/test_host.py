@@ -385,8 +385,11 @@ def test_kkt_ldl_assembles_the_reference_matrix_and_fails_loudly_without_gpu():
 
 
 def test_kkt_ldl2_assembles_the_reduced_matrix():
-    """kkt.ldl2 (counterpart of misc.kkt_ldl2, misc.py:1128-1210): the values sent to the engine are the lower triangle of
-    [[H + G' W^-2 G, A'], [A, 0]] evaluated from the fixed list of products g_ki g_kj"""
+    """kkt.ldl2 (counterpart of misc.kkt_ldl2, misc.py:1128-1210): the values the engine factors are the lower triangle of
+    [[H + G' W^-2 G, A'], [A, 0]], a fixed sparse linear map (the list of products g_ki g_kj, H, A) of w = [di^2; H; A] that
+    the device evaluates (b200s_spmv_apply); here the map and w are taken from the solver's state and applied with scipy, and
+    on a GPU box the device's own result is read back and compared as well"""
+    import ctypes as C
     import scipy.sparse as sp
     from kvxopt_b200 import kkt, _lib
     rng = np.random.default_rng(3)
@@ -403,7 +406,13 @@ def test_kkt_ldl2_assembles_the_reduced_matrix():
         except RuntimeError:
             assert _lib.device_count() == 0
         st = factor._state
-        K = sp.csc_matrix((st["kv"], st["ki"], st["kp"]), shape=(n + p, n + p)).toarray()
+        mp, mc, mv = st["asm_csr"]
+        kv = sp.csr_matrix((mv, mc, mp), shape=(st["nk"], len(st["w"]))) @ st["w"]
+        if _lib.device_count() > 0:
+            kd = np.zeros(st["nk"])
+            assert _lib.fn["b200s_spmv_get"](st["asm"].h, _lib.ptr_f64(kd)) == 0
+            assert np.abs(kd - kv).max() <= 1e-13 * np.abs(kv).max()
+        K = sp.csc_matrix((kv, st["ki"], st["kp"]), shape=(n + p, n + p)).toarray()
         S = (G.T @ sp.diags(di * di) @ G).toarray() + (H.toarray() if Hm is not None else 0.0)
         want = np.zeros((n + p, n + p)); want[:n, :n] = np.tril(S); want[n:, :n] = A.toarray()
         assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
