@@ -780,7 +780,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(const __grid_constant
 // vector handed to the parent through the same relative indices as the factorization).
 // ---------------------------------------------------------------------------------------------------
 constexpr int CB = 32;
-__global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const FrontD* __restrict__ F,
+// THREADS = 256, or 32 for the fronts with <= 32 rows (one warp per front, 32 fronts resident per SM instead of 8: the leaf
+// levels of a KKT matrix hold hundreds of thousands of two- and three-row fronts); same arithmetic per entry either way.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fwd(const int* __restrict__ list, const FrontD* __restrict__ F,
                                              const int* __restrict__ child_idx, const int* __restrict__ rel,
                                              const double* __restrict__ L, double* __restrict__ T, long long tstride,
                                              double* __restrict__ X, long long xstride,
@@ -793,19 +796,19 @@ __global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const
     double* x = X + blockIdx.y * xstride + f.col0;
     const double* P = L + f.loff;
     const int nr = f.nr, nc = f.nc, ld = f.ld, tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < nr; i += 256) t[i] = (i < nc) ? x[i] : 0.0;
+    for (int i = tid; i < nr; i += THREADS) t[i] = (i < nc) ? x[i] : 0.0;
     __syncthreads();
     for (int q = 0; q < f.nchild; q++) {
         const FrontD fc = F[child_idx[f.childptr + q]];
         const int mc = fc.nr - fc.nc;
         const int* rl = rel + fc.reloff;
         const double* tc = T + blockIdx.y * tstride + fc.rowptr + fc.nc;
-        for (int i = tid; i < mc; i += 256) t[rl[i]] += tc[i];
+        for (int i = tid; i < mc; i += THREADS) t[rl[i]] += tc[i];
         __syncthreads();
     }
     for (int b0 = 0; b0 < nc; b0 += CB) {
         const int wb = min(CB, nc - b0);
-        for (int idx = tid; idx < wb * wb; idx += 256) {
+        for (int idx = tid; idx < wb * wb; idx += THREADS) {
             int c = idx / wb, r = idx - c * wb;
             D[r][c] = (r >= c) ? P[(long long)(b0 + c) * ld + b0 + r] : 0.0;
         }
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const
             if (lane < wb) { xs[lane] = v; t[b0 + lane] = v; x[b0 + lane] = v; }
         }
         __syncthreads();
-        for (int r = b0 + wb + tid; r < nr; r += 256) {
+        for (int r = b0 + wb + tid; r < nr; r += THREADS) {
             double acc = t[r];
             const double* col = P + (long long)b0 * ld + r;
             for (int qq = 0; qq < wb; qq++) acc -= col[(long long)qq * ld] * xs[qq];
@@ -831,7 +834,8 @@ __global__ void __launch_bounds__(256) k_fwd(const int* __restrict__ list, const
     }
 }
 
-__global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const FrontD* __restrict__ F,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bwd(const int* __restrict__ list, const FrontD* __restrict__ F,
                                              const int* __restrict__ rows, const double* __restrict__ L,
                                              double* __restrict__ T, long long tstride, double* __restrict__ X,
                                              long long xstride, const unsigned char* __restrict__ owned = nullptr) {
@@ -844,16 +848,16 @@ __global__ void __launch_bounds__(256) k_bwd(const int* __restrict__ list, const
     const double* P = L + f.loff;
     const int* rw = rows + f.rowptr;
     const int nr = f.nr, nc = f.nc, ld = f.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < nr; i += 256) t[i] = xg[rw[i]];
+    for (int i = tid; i < nr; i += THREADS) t[i] = xg[rw[i]];
     __syncthreads();
     const int nblk = (nc + CB - 1) / CB;
     for (int b = nblk - 1; b >= 0; b--) {
         const int b0 = b * CB, wb = min(CB, nc - b0);
-        for (int idx = tid; idx < wb * wb; idx += 256) {
+        for (int idx = tid; idx < wb * wb; idx += THREADS) {
             int c = idx / wb, r = idx - c * wb;
             D[r][c] = (r >= c) ? P[(long long)(b0 + c) * ld + b0 + r] : 0.0;
         }
-        for (int qq = warp; qq < wb; qq += 8) {
+        for (int qq = warp; qq < wb; qq += THREADS / 32) {
             const double* col = P + (long long)(b0 + qq) * ld;
             double s = 0.0;
             for (int r = b0 + wb + lane; r < nr; r += 32) s += col[r] * t[r];
@@ -2851,9 +2855,13 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                     const LevelSched& LS = levels[l];
                     if (reach) {
                         if (reach_cnt[l])
-                            k_fwd<<<dim3(reach_cnt[l], nc), 256, 0, stream>>>(dreach + reach_off[l], dF, dchild, drel, dL, dT, tstride, dX, n);
-                    } else if (LS.small_all_cnt)
-                        k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
+                            k_fwd<256><<<dim3(reach_cnt[l], nc), 256, 0, stream>>>(dreach + reach_off[l], dF, dchild, drel, dL, dT, tstride, dX, n);
+                    } else if (LS.small_all_cnt) {
+                        const int tiny = LS.small_cnt[0];          // nr <= 32: first in the small-front list
+                        if (tiny) k_fwd<32><<<dim3(tiny, nc), 32, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n);
+                        if (LS.small_all_cnt > tiny)
+                            k_fwd<256><<<dim3(LS.small_all_cnt - tiny, nc), 256, 0, stream>>>(dsched + LS.small_all_off + tiny, dF, dchild, drel, dL, dT, tstride, dX, n);
+                    }
                     if (LS.sbig.ng) {
                         k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, dgq + LS.gq_off, dgq_child);
                         if (pfwd && LS.pgi >= 0)
@@ -2889,8 +2897,12 @@ int CholDevice::solve(int sys, double* B, i64 nrhs, i64 ldB, bool on_device, Cho
                             k_bwd_diag<<<dim3(la.ng, nc), 256, SMEM_BDIAG, stream>>>(sgroups[std::max(la.sgi, 0)], dsched + la.goff, dsched + la.goff + la.ng, kb, dF, dL, dMinv, dT, tstride, dX, n, dpart, pstride);
                         }
                     }
-                    if (LS.small_all_cnt)
-                        k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
+                    if (LS.small_all_cnt) {
+                        const int tiny = LS.small_cnt[0];
+                        if (LS.small_all_cnt > tiny)
+                            k_bwd<256><<<dim3(LS.small_all_cnt - tiny, nc), 256, 0, stream>>>(dsched + LS.small_all_off + tiny, dF, drows, dL, dT, tstride, dX, n);
+                        if (tiny) k_bwd<32><<<dim3(tiny, nc), 32, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n);
+                    }
                 }
         };
         const int gkey = nc * 32 + (pfwd ? 16 : 0) + (pbwd ? 8 : 0) + (ldl ? 4 : 0) + (do_fwd ? 2 : 0) + (do_bwd ? 1 : 0);
@@ -2985,7 +2997,7 @@ int CholDevice::solve_dist_level(int backward, int l) {
     const LevelSched& LS = levels[l];
     if (!backward) {
         if (LS.small_all_cnt)
-            k_fwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n, downed);
+            k_fwd<256><<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, dchild, drel, dL, dT, tstride, dX, n, downed);
         if (LS.sbig.ng) {
             k_fwd_gather<<<dim3(LS.gfwd.ctas, nc), 256, 0, stream>>>(dsched + LS.gfwd.goff, dsched + LS.gfwd.goff + LS.gfwd.ng, LS.gfwd.ng, dF, dchild, drel, dT, tstride, dX, n, dgq + LS.gq_off, dgq_child, downed);
             for (size_t kb = 0; kb < LS.sfwd.size(); kb++) {
@@ -3007,7 +3019,7 @@ int CholDevice::solve_dist_level(int backward, int l) {
             }
         }
         if (LS.small_all_cnt)
-            k_bwd<<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n, downed);
+            k_bwd<256><<<dim3(LS.small_all_cnt, nc), 256, 0, stream>>>(dsched + LS.small_all_off, dF, drows, dL, dT, tstride, dX, n, downed);
     }
     CUDA_TRY(cudaGetLastError());
     return ST_OK;
