@@ -214,6 +214,11 @@ b200s_status b200s_chol_set_solve_sweeps(b200s_chol* F, int mode);
  * applied exactly once and in the order of the launch-per-step kernels, every block is solved once and only after the rows it
  * reads, and no CTA is left waiting; > 0: the first rule broken; -1: invalid arguments. */
 int b200s_persist_schedule_check(b200s_int nr, b200s_int nc, b200s_int nctas);
+/* Test hook (host only): the child lists of the numeric phase -- per assembly item (k_extend_add: a column range of a front) and
+ * per forward-gather chunk (k_fwd_gather: 512 rows of a front) the children that reach into it, which is what lets a front
+ * with thousands of one-entry children (the 3 x 3 KKT matrices of kkt.ldl) be assembled without every CTA walking all of them
+ * -- rebuilt for EVERY front of the analysed plan and compared with their definition.  B200S_OK or B200S_INVALID (b200s_last_error). */
+b200s_status b200s_chol_child_lists_check(const b200s_chol* F);
 /* AMD ordering of the symmetric pattern of the `uplo` triangle (src/C/amd.c `order`, host only). */
 b200s_status b200s_amd_order(b200s_int n, const b200s_int* colptr, const b200s_int* rowind,
                              char uplo, b200s_int* perm_out);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200s_free": (None, vp),
     "b200s_grid_nd_perm": (C.c_int, i64, i64, i64, i64, p_i64),
     "b200s_persist_schedule_check": (C.c_int, i64, i64, i64),
+    "b200s_chol_child_lists_check": (C.c_int, vp),
     "b200s_chol_set_solve_sweeps": (C.c_int, vp, C.c_int),
     "b200s_amd_order": (C.c_int, i64, p_i64, p_i64, C.c_char, p_i64),
     "b200s_klu_analyze": (C.c_int, i64, p_i64, p_i64, C.POINTER(vp)),

@@ -808,6 +808,11 @@ b200s_status b200s_chol_set_solve_sweeps(b200s_chol* F, int mode) {
     chol_device_set_solve_sweeps(F->dev, mode);
     return B200S_OK;
 }
+b200s_status b200s_chol_child_lists_check(const b200s_chol* F) {
+    if (!F) return B200S_INVALID;
+    try { return (b200s_status)chol_child_lists_check(F->plan()); }
+    catch (const std::bad_alloc&) { return B200S_OUT_OF_MEMORY; }
+}
 int b200s_persist_schedule_check(b200s_int nr, b200s_int nc, b200s_int nctas) {
     if (nr < 1 || nr > 0x3fffffff || nc < 1 || nc > nr || nctas < 1 || nctas > 4096) return -1;
     return persist_schedule_check((int)nr, (int)nc, (int)nctas);

@@ -2027,6 +2027,125 @@ public:
 static constexpr size_t SMEM_PANEL = (size_t)(NB * LDL + NB * LDX + NB) * sizeof(double);
 static constexpr size_t SMEM_UPDATE = (size_t)(STAGES * BK * (LDT + LDTB)) * sizeof(double);
 
+// ---- child lists of the assembly items and of the forward-gather chunks (host; verified by chol_child_lists_check) -------------
+// extend-add items of front s: its destination columns cut into ranges of about EA_TARGET entries, and per item the children
+// with an update column inside it -- two passes (count, fill) over the children in order, each child hopping from item to item
+// through its sorted relative indices
+static void ea_items_of_front(const CholPlan& P, int s, std::vector<EAItem>& ea, std::vector<int>& ea_child) {
+    const long long EA_TARGET = 16384;
+    const Front& f = P.fronts[s];
+    const int nchild = P.child_ptr[s + 1] - P.child_ptr[s];
+    int cbeg = nchild > 0 ? 0 : f.nc;
+    long long acc = 0;
+    int c0 = cbeg;
+    const size_t item0 = ea.size();
+    for (int c = cbeg; c < f.nr; c++) {
+        acc += f.nr - c;
+        if (acc >= EA_TARGET || c == f.nr - 1) { ea.push_back({s, c0, c + 1, 0, 0}); c0 = c + 1; acc = 0; }
+    }
+    const int nit = (int)(ea.size() - item0);
+    if (nchild == 0 || nit == 0) return;
+    auto item_of = [&](int c) {          // the item whose range holds destination column c (ranges are consecutive from cbeg = 0)
+        int lo = 0, hi = nit - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ea[item0 + mid].c1 <= c) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            int off = (int)ea_child.size();
+            for (int i = 0; i < nit; i++) { ea[item0 + i].q_off = off; off += ea[item0 + i].q_cnt; ea[item0 + i].q_cnt = 0; }
+            ea_child.resize(off);
+        }
+        for (int q = 0; q < nchild; q++) {
+            const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
+            const int mc = fc.nr - fc.nc;
+            const i32* rl = P.rel.data() + fc.reloff;
+            int j = 0;
+            while (j < mc) {
+                EAItem& e = ea[item0 + item_of(rl[j])];
+                if (pass == 1) ea_child[e.q_off + e.q_cnt] = q;
+                e.q_cnt++;
+                j = (int)(std::lower_bound(rl + j, rl + mc, e.c1) - rl);
+            }
+        }
+    }
+}
+// gather chunks of front s (nch = ceil(nr / GATHER_ROWS) CTAs of k_fwd_gather): per chunk {first, count} in gq_child = the children
+// with an update row inside the chunk, ascending; children with exactly one update row carry GATHER_SINGLE
+static void gather_chunks_of_front(const CholPlan& P, int s, int nch, std::vector<int2>& gq, std::vector<int>& gq_child) {
+    const int nchild = P.child_ptr[s + 1] - P.child_ptr[s];
+    const size_t q0 = gq.size();
+    gq.resize(q0 + nch, make_int2(0, 0));
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            int off = (int)gq_child.size();
+            for (int i = 0; i < nch; i++) { gq[q0 + i].x = off; off += gq[q0 + i].y; gq[q0 + i].y = 0; }
+            gq_child.resize(off);
+        }
+        for (int q = 0; q < nchild; q++) {
+            const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
+            const int mc = fc.nr - fc.nc;
+            const i32* rl = P.rel.data() + fc.reloff;
+            int j = 0;
+            while (j < mc) {
+                const int ch = rl[j] / GATHER_ROWS;
+                int2& e = gq[q0 + ch];
+                if (pass == 1) gq_child[e.x + e.y] = mc == 1 ? (q | GATHER_SINGLE) : q;
+                e.y++;
+                j = (int)(std::lower_bound(rl + j, rl + mc, (ch + 1) * GATHER_ROWS) - rl);
+            }
+        }
+    }
+}
+// Test hook (b200s_chol_child_lists_check): both tables rebuilt for EVERY front of the plan and compared with the definition --
+// a child is listed for an item / a chunk exactly when one of its relative indices falls into the item's column range / the
+// chunk's row range, lists ascend, items tile [0 or nc, nr), the one-row flag is right.  Host only.
+int chol_child_lists_check(const CholPlan& P) {
+    for (int s = 0; s < (int)P.fronts.size(); s++) {
+        const Front& f = P.fronts[s];
+        const int nchild = P.child_ptr[s + 1] - P.child_ptr[s];
+        std::vector<EAItem> ea; std::vector<int> ec;
+        ea_items_of_front(P, s, ea, ec);
+        int expect = nchild > 0 ? 0 : f.nc;
+        for (const EAItem& e : ea) {
+            if (e.front != s || e.c0 != expect || e.c1 <= e.c0) { set_last_error("child lists: items do not tile the columns"); return ST_INVALID; }
+            expect = e.c1;
+            int t = 0;
+            for (int q = 0; q < nchild; q++) {
+                const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
+                const i32* rl = P.rel.data() + fc.reloff;
+                bool hit = false;
+                for (int i = 0; i < fc.nr - fc.nc; i++) hit |= rl[i] >= e.c0 && rl[i] < e.c1;
+                if (hit) {
+                    if (t >= e.q_cnt || ec[e.q_off + t] != q) { set_last_error("child lists: extend-add item misses a child"); return ST_INVALID; }
+                    t++;
+                }
+            }
+            if (t != e.q_cnt) { set_last_error("child lists: extend-add item lists a child without a column in its range"); return ST_INVALID; }
+        }
+        if (expect != f.nr && !(ea.empty() && expect >= f.nr)) { set_last_error("child lists: items do not reach the last column"); return ST_INVALID; }
+        const int nch = (f.nr + GATHER_ROWS - 1) / GATHER_ROWS;
+        std::vector<int2> gq; std::vector<int> gc;
+        gather_chunks_of_front(P, s, nch, gq, gc);
+        for (int ch = 0; ch < nch; ch++) {
+            int t = 0;
+            for (int q = 0; q < nchild; q++) {
+                const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
+                const i32* rl = P.rel.data() + fc.reloff;
+                const int mc = fc.nr - fc.nc;
+                bool hit = false;
+                for (int i = 0; i < mc; i++) hit |= rl[i] / GATHER_ROWS == ch;
+                if (hit) {
+                    if (t >= gq[ch].y || gc[gq[ch].x + t] != (mc == 1 ? (q | GATHER_SINGLE) : q)) { set_last_error("child lists: gather chunk misses a child"); return ST_INVALID; }
+                    t++;
+                }
+            }
+            if (t != gq[ch].y) { set_last_error("child lists: gather chunk lists a child without a row in it"); return ST_INVALID; }
+        }
+    }
+    return ST_OK;
+}
+
 int CholDevice::init() {
     const CholPlan& P = *plan;
     const bool dbg = getenv("B200S_DEBUG") != nullptr;
@@ -2105,7 +2224,6 @@ int CholDevice::init() {
     levels.resize(P.nlevels);
     sgroups.assign(1, SolveGroups());
     memset(&sgroups[0], 0, sizeof(SolveGroups));
-    const long long EA_TARGET = 16384;
     for (int l = 0; l < P.nlevels; l++) {
         LevelSched& LS = levels[l];
         std::vector<int> smalls[LevelSched::NSMALL], bigs;
@@ -2113,45 +2231,7 @@ int CholDevice::init() {
         for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; q++) {
             const int s = P.level_fronts[q];
             const Front& f = P.fronts[s];
-            const int nchild = P.child_ptr[s + 1] - P.child_ptr[s];
-            // extend-add items
-            int cbeg = nchild > 0 ? 0 : f.nc;
-            long long acc = 0;
-            int c0 = cbeg;
-            const size_t item0 = ea.size();
-            for (int c = cbeg; c < f.nr; c++) {
-                acc += f.nr - c;
-                if (acc >= EA_TARGET || c == f.nr - 1) { ea.push_back({s, c0, c + 1, 0, 0}); c0 = c + 1; acc = 0; }
-            }
-            // per item the children with an update column inside it: two passes (count, fill) over the children in order, each
-            // child hopping from item to item through its sorted relative indices
-            const int nit = (int)(ea.size() - item0);
-            if (nchild > 0 && nit > 0) {
-                auto item_of = [&](int c) {          // the item whose range holds destination column c (ranges are consecutive from cbeg = 0)
-                    int lo = 0, hi = nit - 1;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ea[item0 + mid].c1 <= c) lo = mid + 1; else hi = mid; }
-                    return lo;
-                };
-                for (int pass = 0; pass < 2; pass++) {
-                    if (pass == 1) {
-                        int off = (int)ea_child.size();
-                        for (int i = 0; i < nit; i++) { ea[item0 + i].q_off = off; off += ea[item0 + i].q_cnt; ea[item0 + i].q_cnt = 0; }
-                        ea_child.resize(off);
-                    }
-                    for (int q = 0; q < nchild; q++) {
-                        const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
-                        const int mc = fc.nr - fc.nc;
-                        const i32* rl = P.rel.data() + fc.reloff;
-                        int j = 0;
-                        while (j < mc) {
-                            EAItem& e = ea[item0 + item_of(rl[j])];
-                            if (pass == 1) ea_child[e.q_off + e.q_cnt] = q;
-                            e.q_cnt++;
-                            j = (int)(std::lower_bound(rl + j, rl + mc, e.c1) - rl);
-                        }
-                    }
-                }
-            }
+            ea_items_of_front(P, s, ea, ea_child);
             if (f.nr <= SMALL_NR) {
                 int cls = f.nr <= 32 ? 0 : (f.nr <= 64 ? 1 : (f.nr <= 96 ? 2 : (f.nr <= 118 ? 3 : 4)));
                 smalls[cls].push_back(s);
@@ -2216,31 +2296,7 @@ int CholDevice::init() {
             emit(LS.gfwd, sbigs, cnt);
             // per gather chunk (= CTA of k_fwd_gather, in launch order) the children with an update row inside it
             LS.gq_off = (int)gq.size();
-            for (size_t fi = 0; fi < sbigs.size(); fi++) {
-                const int s = sbigs[fi], nch = cnt[fi], nchild = P.child_ptr[s + 1] - P.child_ptr[s];
-                const size_t q0 = gq.size();
-                gq.resize(q0 + nch, make_int2(0, 0));
-                for (int pass = 0; pass < 2; pass++) {
-                    if (pass == 1) {
-                        int off = (int)gq_child.size();
-                        for (int i = 0; i < nch; i++) { gq[q0 + i].x = off; off += gq[q0 + i].y; gq[q0 + i].y = 0; }
-                        gq_child.resize(off);
-                    }
-                    for (int q = 0; q < nchild; q++) {
-                        const Front& fc = P.fronts[P.child_idx[P.child_ptr[s] + q]];
-                        const int mc = fc.nr - fc.nc;
-                        const i32* rl = P.rel.data() + fc.reloff;
-                        int j = 0;
-                        while (j < mc) {
-                            const int ch = rl[j] / GATHER_ROWS;
-                            int2& e = gq[q0 + ch];
-                            if (pass == 1) gq_child[e.x + e.y] = mc == 1 ? (q | GATHER_SINGLE) : q;
-                            e.y++;
-                            j = (int)(std::lower_bound(rl + j, rl + mc, (ch + 1) * GATHER_ROWS) - rl);
-                        }
-                    }
-                }
-            }
+            for (size_t fi = 0; fi < sbigs.size(); fi++) gather_chunks_of_front(P, sbigs[fi], cnt[fi], gq, gq_child);
             emit(LS.sbig, sbigs, std::vector<int>(sbigs.size(), 1));
         }
         LS.small_all_off = LS.small_off[0];

@@ -55,6 +55,7 @@ void chol_device_mark_numeric(CholDevice* d, bool numeric);
 int  chol_device_factor_enqueue(CholDevice* d, const double* val_dev);   // no read-back, capturable; see chol_device_minor_ptr
 const int* chol_device_minor_ptr(CholDevice* d);                         // device word: first non-positive pivot or 0x7fffffff
 void chol_device_set_solve_sweeps(CholDevice* d, int mode);   // -1: default; bit 0 forward, bit 1 backward persistent sweep
+int  chol_child_lists_check(const CholPlan& P);              // assembly-item / gather-chunk child lists against their definition (test hook)
 int  persist_schedule_check(int nr, int nc, int nctas);   // CPU replay of the persistent solve schedules (test hook)
 i64  chol_device_workspace_bytes(const CholDevice* d);
 

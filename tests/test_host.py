@@ -594,3 +594,47 @@ def test_persistent_solve_schedules_replayed_on_the_host():
     for nr, nc, g in cases:
         assert chk(nr, nc, g) == 0, (nr, nc, g, chk(nr, nc, g))
     assert chk(100, 200, 1) == -1 and chk(100, 50, 0) == -1
+
+
+@pytest.mark.parametrize("case", ["bcsstk24", "lap24_nd", "kkt3x3"])
+def test_assembly_and_gather_child_lists_match_their_definition(case):
+    """k_extend_add and k_fwd_gather visit, per column range / 512-row chunk of a front, only the children listed for it
+    (b200s_chol_child_lists_check rebuilds the lists for every front of the plan and compares them with the definition: a child
+    is listed exactly when one of its relative indices falls into the range, in child order, one-row children flagged).
+    'kkt3x3' is the unreduced KKT matrix of a box-constrained QP in the z -> x order of kkt.ldl: fronts with hundreds of
+    one-entry children, the structure that made every CTA of the root front walk 18 800 children at full size."""
+    from bench import lap3d_lower
+    perm = None
+    if case == "bcsstk24":
+        A = sp.tril(load_matrix("bcsstk24")).tocsc()
+    elif case == "lap24_nd":
+        A = lap3d_lower(24)
+        perm = np.zeros(A.shape[0], np.int64)
+        fn["b200s_grid_nd_perm"](24, 24, 24, 64, L.ptr_i64(perm))
+    else:
+        import os, sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+        from generators import qp_instance
+        P, q, G, h = qp_instance(60, 50, 300)
+        n, m = P.shape[0], G.shape[0]
+        K = sp.bmat([[sp.tril(P), None], [G, -sp.identity(m)]]).tocsc()
+        A = sp.tril(K).tocsc()
+        perm = np.concatenate([n + np.arange(m), np.arange(n)]).astype(np.int64)       # z first, then x
+    A.sort_indices()
+    N = A.shape[0]
+    o = L.CholOpts(); fn["b200s_chol_default_opts"](C.byref(o))
+    if case == "kkt3x3":
+        o.supernodal = 0
+    h = C.c_void_p()
+    assert fn["b200s_chol_analyze"](N, L.ptr_i64(A.indptr.astype(np.int64)), L.ptr_i64(A.indices.astype(np.int64)), b"L",
+                                    L.ptr_i64(perm) if perm is not None else None, C.byref(o), C.byref(h)) == 0
+    inf = L.CholInfo(); fn["b200s_chol_info"](h, C.byref(inf))
+    assert fn["b200s_chol_child_lists_check"](h) == 0, L.last_error()
+    if case == "kkt3x3":
+        ns = inf.nsuper
+        parent = np.zeros(ns, np.int64); nrows = np.zeros(ns, np.int64); ncols = np.zeros(ns, np.int64)
+        assert fn["b200s_chol_front_layout"](h, L.ptr_i64(parent), None, L.ptr_i64(ncols), L.ptr_i64(nrows), None, None, None, None) == 0
+        kids = np.bincount(parent[parent >= 0], minlength=ns)
+        assert kids.max() > 100                                # a many-children front (lap24_nd has the multi-chunk fronts)
+    fn["b200s_chol_free"](h)
+    assert fn["b200s_chol_child_lists_check"](None) == L.INVALID
